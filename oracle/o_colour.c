@@ -1,0 +1,294 @@
+/* ORACLE — test infrastructure only (see o_common.h).
+ * CPU restatement of src/pipe/modules/colour/main.c:88-186,219-365 (commit_params) and
+ * colour/main-impl.glsl:49-67,118-341 for the paths that need no external LUT input
+ * (clut / abney / spectra / picked connectors unconnected: have_clut = have_pick = have_abney = 0),
+ * plus shared/dtucs.glsl:11-83 and colourspaces.glsl:1-18.
+ * Out of scope (documented in DESIGN.md): camera-log TRCs 7..15 and camera gamuts 8,9,11..16. */
+#include "o_common.h"
+#include "vkdt_oracle.h"
+
+static const float M_cat16_Mi[9] = {1.86206786f, -1.01125463f, 0.14918677f, 0.38752654f, 0.62144744f, -0.00897398f, -0.01584150f, -0.03412294f, 1.04996444f};
+static const float M_cat16_M[9]  = {0.401288f, 0.650173f, -0.051461f, -0.250268f, 1.204414f, 0.045854f, -0.002079f, 0.048952f, 0.953127f};
+static const float M_2020_to_xyz[9] = {0.636958048301290991f, 0.144616903586208406f, 0.168880975164172054f, 0.26270021201126692f, 0.677998071518871148f, 0.0593017164698619384f, 4.9999999999999999e-17f, 0.0280726930490874452f, 1.06098505771079066f};
+static const float M_xyz_to_2020[9] = {1.71665119f, -0.35567078f, -0.25336628f, -0.66668435f, 1.61648124f, 0.01576855f, 0.01763986f, -0.04277061f, 0.94210312f};
+static const float M_709_to_2020[9] = {0.62750375f, 0.32927542f, 0.04330266f, 0.06910828f, 0.91951916f, 0.0113596f, 0.01639406f, 0.08801125f, 0.89538035f};
+static const float M_adobe_to_2020[9] = {0.87736306f, 0.07751751f, 0.04516292f, 0.0966218f, 0.89152263f, 0.01186405f, 0.02291617f, 0.04301452f, 0.93367996f};
+static const float M_p3d65_to_2020[9] = {0.75386031f, 0.19861268f, 0.04757049f, 0.04575344f, 0.94178472f, 0.01247032f, -0.00121501f, 0.01760596f, 0.98321971f};
+static const float M_ap0_to_2020[9] = {1.51286139f, -0.2589874f, -0.22978603f, -0.07903646f, 1.17706683f, -0.10075565f, 0.00209124f, -0.03114411f, 0.95350416f};
+static const float M_ap1_to_2020[9] = {1.03866457f, -1.14744180e-02f, -2.72327263e-02f, -4.33683734e-04f, 1.00062477f, 1.01851049e-04f, -5.64306018e-03f, -2.23568741e-02f, 1.02483276f};
+static const float M_redwg_to_2020[9] = {1.180431f, -0.094040f, -0.086391f, -0.028017f, 1.311442f, -0.283425f, -0.074360f, -0.362078f, 1.436437f};
+
+/* colour/main.c:76-186: thin plate (linear kernel) rbf coefficients; coef has 4*(3+N) floats, zero-inited */
+static void compute_coefficients(int N, const float *source, const float *target, float *coef)
+{
+  const int N2 = N + 3;
+  if(N == 0) { for(int co = 0; co < 3; co++) coef[co*4+co] = 1.0f; return; }
+  if(N == 1) { for(int co = 0; co < 3; co++) coef[co*4+co] = target[co] / source[co]; return; }
+  double *A = (double *)malloc(sizeof(double) * N2 * N2);
+  double *b = (double *)malloc(sizeof(double) * N2);
+  double *A0 = (double *)malloc(sizeof(double) * N2 * N2);
+  for(int j = 0; j < N; j++) for(int i = j; i < N; i++)
+  {
+    const float *x = source + 3*i, *y = source + 3*j;
+    const double r2 = (x[0]-y[0])*(x[0]-y[0]) + (x[1]-y[1])*(x[1]-y[1]) + (x[2]-y[2])*(x[2]-y[2]);
+    A[j*N2+i] = A[i*N2+j] = sqrt(r2);
+  }
+  for(int k = 0; k < 3; k++) for(int i = 0; i < N; i++) A[i*N2+N+k] = A[(N+k)*N2+i] = source[3*i+k];
+  for(int j = N; j < N2; j++) for(int i = N; i < N2; i++) A[j*N2+i] = 0;
+  /* the reference triangularises once and back-substitutes three times; solving the same
+   * factorisation three times is arithmetically identical to re-running o_gauss_solve on a copy. */
+  memcpy(A0, A, sizeof(double) * N2 * N2);
+  for(int ch = 0; ch < 3; ch++)
+  {
+    memcpy(A, A0, sizeof(double) * N2 * N2);
+    for(int i = 0; i < N; i++) b[i] = target[3*i+ch];
+    for(int i = N; i < N2; i++) b[i] = 0;
+    if(!o_gauss_solve(A, b, N2)) break;
+    for(int i = 0; i < N; i++) coef[12 + 4*i + ch] = b[i];
+    for(int i = 0; i < 3; i++) coef[4*i + ch] = b[N+i];
+  }
+  free(A); free(A0); free(b);
+}
+
+/* colour/main.c:219-365.  f has O_COLOUR_COMMITTED_FLOATS entries.  p_wb is written back (side effect of the reference). */
+void o_colour_commit(const o_colour_params_t *p, float *p_wb, const float *img_wb, const float *img_cam_to_rec2020,
+    int img_primaries, int img_trc, float *f)
+{
+  uint32_t *ii = (uint32_t *)f;
+  memset(f, 0, sizeof(float) * O_COLOUR_COMMITTED_FLOATS);
+  if(p_wb[0] == 0.0f && p_wb[1] == 0.0f && p_wb[2] == 0.0f)
+  {
+    float w0[3] = {0}, w[3] = { img_wb[0], img_wb[1], img_wb[2] };
+    for(int j = 0; j < 3; j++) for(int i = 0; i < 3; i++) w0[j] += img_cam_to_rec2020[3*j+i] / w[i];
+    w0[0] /= w0[1]; w0[2] /= w0[1]; w0[1] = 1.0f;
+    p_wb[0] = 1 / w0[0]; p_wb[1] = 1; p_wb[2] = 1 / w0[2];
+  }
+  if(!(p_wb[0] == p_wb[0]) || p_wb[0] == 0.0f || p_wb[1] == 0.0f || p_wb[2] == 0.0f)
+    p_wb[0] = p_wb[1] = p_wb[2] = 1.0f;
+  f[0] = p_wb[0] / p_wb[1];
+  f[1] = 1.0f;
+  f[2] = p_wb[2] / p_wb[1];
+  f[3] = powf(2.0f, p->exposure);
+  const int off = 4+12+4+12+4*24+4*24;
+  /* clut unconnected: nbands = 3, legacy mapping (colour/main.c:272-292) */
+  if(p->temp <= 0.0f) f[off+0] = -1.0f;
+  else
+  {
+    float v = tanf(asinhf(46.3407f + p->temp)) + (-0.0287128f * cosf(0.000798585f * (714.855f - p->temp))) + 0.942275f;
+    v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
+    f[off+0] = 1.0f - v;
+  }
+  ii[off+1] = p->matrix == 4 ? 1 : 0;
+  f[off+2] = p->sat;
+  ii[off+3] = p->picked;
+  ii[off+4] = p->gamut;
+  ii[off+5] = img_primaries;
+  ii[off+6] = img_trc;
+  f[off+7] = p->clip ? p->clipmax : 0.0;
+  float awb[3] = { img_wb[0], img_wb[1], img_wb[2] };
+  if(!(awb[0] > 0.0f) || !(awb[1] > 0.0f) || !(awb[2] > 0.0f)) awb[0] = awb[1] = awb[2] = 1.0f;
+  f[off+8] = awb[0] / awb[1]; f[off+9] = 1.0f; f[off+10] = awb[2] / awb[1]; f[off+11] = 1.0f;
+  if(p->matrix == 1)
+  { for(int j = 0; j < 3; j++) for(int i = 0; i < 3; i++) f[4+4*i+j] = img_cam_to_rec2020[3*j+i]; }
+  else if(p->matrix == 2) { ii[off+5] = 5; ii[off+6] = 0; }  /* XYZ, linear */
+  else if(p->matrix == 3) { ii[off+5] = 1; ii[off+6] = 0; }  /* rec709, linear */
+  else if(p->matrix == 5)
+  {
+    ii[off+5] = 0; ii[off+6] = 0;
+    for(int j = 0; j < 3; j++) for(int i = 0; i < 3; i++) f[4+4*i+j] = p->mat[3*j+i];
+  }
+  else
+  {
+    ii[off+5] = 2; ii[off+6] = 0;
+    for(int j = 0; j < 3; j++) for(int i = 0; i < 3; i++) f[4+4*j+i] = i == j ? 1.0f : 0.0f;
+  }
+  if(p->mode == 1)
+  {
+    const int N = p->cnt < 0 ? 0 : (p->cnt > 24 ? 24 : p->cnt);
+    ii[16] = N; ii[17] = ii[18] = ii[19] = 0;
+    float src[72], tgt[72];
+    for(int i = 0; i < N; i++) for(int k = 0; k < 3; k++)
+    {
+      src[3*i+k] = p->rbmap[6*i+k];
+      tgt[3*i+k] = p->rbmap[6*i+3+k];
+    }
+    memset(f + 20, 0, sizeof(float) * (12 + 24*4 + 24*4));
+    for(int k = 0; k < N; k++)
+    {
+      f[128 + 4*k + 0] = src[3*k+0];
+      f[128 + 4*k + 1] = src[3*k+1];
+      f[128 + 4*k + 2] = src[3*k+2];
+      f[128 + 4*k + 3] = 0.0f;
+    }
+    compute_coefficients(N, src, tgt, f + 20);
+  }
+  else ii[16] = ii[17] = ii[18] = ii[19] = 0;
+}
+
+/* colour/main-impl.glsl:118-198 */
+static void decode_colour(const float *f, float *rgb)
+{
+  const uint32_t *ii = (const uint32_t *)f;
+  const int off = 224;
+  const uint32_t trc = ii[off+6], prim = ii[off+5];
+  if(trc == 1)
+  {
+    const float a = 1.09929682680944f, b = 0.018053968510807f;
+    for(int k = 0; k < 3; k++) rgb[k] = rgb[k] > b * 4.5f ? powf((rgb[k] + (a - 1)) / a, 2.2f) : rgb[k] / 4.5f;
+  }
+  else if(trc == 2)
+  { for(int k = 0; k < 3; k++) rgb[k] = rgb[k] > 0.04045f ? powf((rgb[k] + 0.055f) / 1.055f, 2.4f) : rgb[k] / 12.92f; }
+  else if(trc == 3)
+  {
+    const float m1 = 1305.0f/8192.0f, m2 = 2523.0f/32.0f, c1 = 107.0f/128.0f, c2 = 2413.0f/128.0f, c3 = 2392.0f/128.0f;
+    for(int k = 0; k < 3; k++)
+    {
+      const float xpow = powf(o_max(0.0f, rgb[k]), 1.0f / m2);
+      const float num = o_max(xpow - c1, 0.0f);
+      const float den = o_max(c2 - c3 * xpow, 1e-10f);
+      rgb[k] = powf(num / den, 1.0f / m1);
+    }
+  }
+  else if(trc == 4) { for(int k = 0; k < 3; k++) rgb[k] = powf(rgb[k], 2.6f); }
+  else if(trc == 5)
+  {
+    const float a = 0.17883277f, b = 0.28466892f, c = 0.55991073f;
+    for(int k = 0; k < 3; k++) rgb[k] = rgb[k] <= 0.5f ? rgb[k] * rgb[k] / 3.0f : (expf((rgb[k] - c) / a) + b) / 12.0f;
+  }
+  else if(trc == 6) { for(int k = 0; k < 3; k++) rgb[k] = powf(o_max(rgb[k], 0.0f), 2.2f); }
+  if(prim == 0)
+  { /* custom matrix, uploaded column major in f[4..15] */
+    const float r = f[4] * rgb[0] + f[8]  * rgb[1] + f[12] * rgb[2];
+    const float g = f[5] * rgb[0] + f[9]  * rgb[1] + f[13] * rgb[2];
+    const float b = f[6] * rgb[0] + f[10] * rgb[1] + f[14] * rgb[2];
+    rgb[0] = r; rgb[1] = g; rgb[2] = b;
+  }
+  else if(prim == 1) o_mat3mulv(M_709_to_2020, rgb, rgb);
+  else if(prim == 3) o_mat3mulv(M_adobe_to_2020, rgb, rgb);
+  else if(prim == 4) o_mat3mulv(M_p3d65_to_2020, rgb, rgb);
+  else if(prim == 5) o_mat3mulv(M_xyz_to_2020, rgb, rgb);
+  else if(prim == 6) o_mat3mulv(M_ap0_to_2020, rgb, rgb);
+  else if(prim == 7) o_mat3mulv(M_ap1_to_2020, rgb, rgb);
+  else if(prim == 10) o_mat3mulv(M_redwg_to_2020, rgb, rgb);
+}
+
+/* colour/main-impl.glsl:49-67.  glsl evaluates M16 * rec2020_to_xyz * v left to right: (M16*R)*v */
+static void cat16(float *rgb, const float *src, const float *dst)
+{
+  float MR[9];
+  for(int j = 0; j < 3; j++) for(int i = 0; i < 3; i++)
+    MR[3*j+i] = M_cat16_M[3*j+0] * M_2020_to_xyz[i] + M_cat16_M[3*j+1] * M_2020_to_xyz[3+i] + M_cat16_M[3*j+2] * M_2020_to_xyz[6+i];
+  float XM[9];
+  for(int j = 0; j < 3; j++) for(int i = 0; i < 3; i++)
+    XM[3*j+i] = M_xyz_to_2020[3*j+0] * M_cat16_Mi[i] + M_xyz_to_2020[3*j+1] * M_cat16_Mi[3+i] + M_xyz_to_2020[3*j+2] * M_cat16_Mi[6+i];
+  float cs[3], cd[3], cl[3];
+  o_mat3mulv(MR, src, cs);
+  o_mat3mulv(MR, dst, cd);
+  o_mat3mulv(MR, rgb, cl);
+  for(int k = 0; k < 3; k++) cl[k] *= cd[k] / cs[k];
+  o_mat3mulv(XM, cl, rgb);
+}
+
+/* colourspaces.glsl:2-18 */
+static void rec2020_to_xyY(const float *rgb, float *xyY)
+{
+  float xyz[3];
+  o_mat3mulv(M_2020_to_xyz, rgb, xyz);
+  const float s = xyz[0] + xyz[1] + xyz[2];
+  xyY[0] = xyz[0] / s; xyY[1] = xyz[1] / s; xyY[2] = xyz[1];
+}
+static void xyY_to_rec2020(const float *xyY, float *rgb)
+{
+  const float xyz[3] = { xyY[0] * xyY[2] / xyY[1], xyY[1] * xyY[2] / xyY[1], (1.0f - xyY[0] - xyY[1]) * xyY[2] / xyY[1] };
+  o_mat3mulv(M_xyz_to_2020, xyz, rgb);
+}
+
+/* shared/dtucs.glsl:11-83 */
+void o_xyY_to_dt_UCS_JCH(const float *xyY, float L_white, float *JCH)
+{
+  /* M1 given as column vectors */
+  const float ux = -0.783941002840055f * xyY[0] + 0.277512987809202f * xyY[1] + 0.153836578598858f;
+  const float uy =  0.745273540913283f * xyY[0] - 0.205375866083878f * xyY[1] - 0.165478376301988f;
+  const float ud =  0.318707282433486f * xyY[0] + 2.16743692732158f  * xyY[1] + 0.291320554395942f;
+  const float u = ux / ud, v = uy / ud;
+  const float us = 1.39656225667f * u / (fabsf(u) + 1.49217352929f);
+  const float vs = 1.4513954287f  * v / (fabsf(v) + 1.52488637914f);
+  /* M2 = mat2(-1.124983854323892, 1.86323315098672, -0.980483721769325, 1.971853092390862) columns */
+  const float Up = -1.124983854323892f * us - 0.980483721769325f * vs;
+  const float Vp =  1.86323315098672f  * us + 1.971853092390862f * vs;
+  const float Y_hat = powf(xyY[2], 0.631651345306265f);
+  const float L_star = 2.098883786377f * Y_hat / (Y_hat + 1.12426773749357f);
+  const float M2 = Up * Up + Vp * Vp;
+  JCH[0] = L_star / L_white;
+  JCH[1] = 15.932993652962535f * powf(L_star, 0.6523997524738018f) * powf(M2, 0.6007557017508491f) / L_white;
+  JCH[2] = atan2f(Vp, Up);
+}
+void o_dt_UCS_JCH_to_xyY(const float *JCH, float L_white, float *xyY)
+{
+  const float L_star = JCH[0] * L_white;
+  float M = powf(JCH[1] * L_white / (15.932993652962535f * powf(L_star, 0.6523997524738018f)), 0.8322850678616855f);
+  M = o_clamp(M, 0.0f, 0.05f);
+  const float a = M * cosf(JCH[2]), b = M * sinf(JCH[2]);
+  /* M1 = mat2(-5.037522385190711, 4.760029407436461, -2.504856328185843, 2.874012963239247) columns */
+  const float us = -5.037522385190711f * a - 2.504856328185843f * b;
+  const float vs =  4.760029407436461f * a + 2.874012963239247f * b;
+  const float U = -1.49217352929f * us / (fabsf(us) - 1.39656225667f);
+  const float V = -1.52488637914f * vs / (fabsf(vs) - 1.4513954287f);
+  const float x = 0.167171472114775f * U + 0.141299802443708f * V - 0.00801531300850582f;
+  const float y = -0.150959086409163f * U - 0.155185060382272f * V - 0.00843312433578007f;
+  const float d = 0.940254742367256f * U + 1.000000000000000f * V - 0.0256325967652889f;
+  xyY[0] = x / d; xyY[1] = y / d;
+  xyY[2] = powf((1.12426773749357f * L_star / (2.098883786377f - L_star)), 1.5831518565279648f);
+}
+
+/* colour/main-impl.glsl:200-341 with have_clut = have_pick = have_abney = 0 */
+void o_colour_main(const oimg_t *in, oimg_t *out, const float *f, int out_f16)
+{
+  const uint32_t *ii = (const uint32_t *)f;
+  const int off = 224;
+  const float sat = f[off+2], clip_hl = f[off+7];
+  const uint32_t N = ii[16] > 24 ? 24 : ii[16];
+  const float one[3] = {1.0f, 1.0f, 1.0f};
+#pragma omp parallel for schedule(static)
+  for(int y = 0; y < out->h; y++) for(int x = 0; x < out->w; x++)
+  {
+    float rgb[4];
+    o_tex4(in, (x + 0.5f) / (float)out->w, (y + 0.5f) / (float)out->h, rgb);
+    decode_colour(f, rgb);
+    cat16(rgb, one, f);
+    if(clip_hl > 0.0f)
+    {
+      float clip[3] = { clip_hl, clip_hl, clip_hl };
+      decode_colour(f, clip);
+      cat16(clip, one, f);
+      const float t = o_min(clip[0], o_min(clip[1], clip[2]));
+      for(int k = 0; k < 3; k++) rgb[k] = o_min(rgb[k], t);
+    }
+    for(int k = 0; k < 3; k++) rgb[k] *= f[3];
+    if(ii[16] > 0)
+    { /* rbf_P at f[20..31] as 3 column vec4s, rbf_c at f[32..], rbf_p at f[128..] */
+      float co[3];
+      for(int k = 0; k < 3; k++) co[k] = f[20+k] * rgb[0] + f[24+k] * rgb[1] + f[28+k] * rgb[2];
+      for(uint32_t i = 0; i < N; i++)
+      {
+        const float d0 = rgb[0] - f[128+4*i], d1 = rgb[1] - f[129+4*i], d2 = rgb[2] - f[130+4*i];
+        const float r = sqrtf(d0*d0 + d1*d1 + d2*d2);
+        for(int k = 0; k < 3; k++) co[k] += f[32+4*i+k] * r;
+      }
+      for(int k = 0; k < 3; k++) rgb[k] = co[k];
+    }
+    if(sat != 1.0f)
+    {
+      for(int k = 0; k < 3; k++) rgb[k] = o_max(rgb[k], 0.0f);
+      float xyY[3], JCH[3];
+      rec2020_to_xyY(rgb, xyY);
+      o_xyY_to_dt_UCS_JCH(xyY, 1.0f, JCH);
+      JCH[1] = o_clamp(JCH[1] * sat, 0.0f, 1.0f);
+      o_dt_UCS_JCH_to_xyY(JCH, 1.0f, xyY);
+      xyY_to_rec2020(xyY, rgb);
+    }
+    for(int k = 0; k < 3; k++) rgb[k] = o_clamp(rgb[k], -65535.0f, 65535.0f);
+    rgb[3] = 1.0f;
+    o_store4(out, x, y, rgb, out_f16);
+  }
+}

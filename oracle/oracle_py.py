@@ -1,0 +1,184 @@
+"""ORACLE — test infrastructure only.
+
+ctypes bindings for oracle/liboracle.so (CPU restatement of vkdt's raw->display kernels) and
+oracle/_ref/libmlvref.so (the reference's own MLV decoder compiled in place).  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class OImg(C.Structure):
+    _fields_ = [("w", C.c_int), ("h", C.c_int), ("c", C.c_int), ("p", C.POINTER(C.c_float))]
+
+
+class DenoiseParams(C.Structure):
+    _fields_ = [("strength", C.c_float), ("luma", C.c_float), ("detail", C.c_float), ("pad", C.c_float),
+                ("edges", C.c_float * 4), ("gainmap", C.c_int)]
+
+
+class HiliteParams(C.Structure):
+    _fields_ = [("white", C.c_float), ("desat", C.c_float), ("soft", C.c_float)]
+
+
+class DemosaicParams(C.Structure):
+    _fields_ = [("colour", C.c_int), ("method", C.c_int)]
+
+
+class CropParams(C.Structure):
+    _fields_ = [("perspect", C.c_float * 8), ("crop", C.c_float * 4), ("rotate", C.c_float)]
+
+
+class ColourParams(C.Structure):
+    _fields_ = [("exposure", C.c_float), ("sat", C.c_float), ("picked", C.c_int), ("matrix", C.c_int),
+                ("gamut", C.c_int), ("clip", C.c_int), ("clipmax", C.c_float), ("temp", C.c_float),
+                ("white", C.c_float * 4), ("mat", C.c_float * 9), ("mode", C.c_int), ("cnt", C.c_int),
+                ("rbmap", C.c_float * 144), ("import_", C.c_char * 8)]
+
+
+class FilmcurvParams(C.Structure):
+    _fields_ = [("light", C.c_float), ("contrast", C.c_float), ("bias", C.c_float), ("colour", C.c_int),
+                ("chroma", C.c_float), ("rolloff", C.c_float), ("red", C.c_float), ("yellow", C.c_float),
+                ("blue", C.c_float), ("shadows", C.c_float)]
+
+
+class LlapParams(C.Structure):
+    _fields_ = [("sigma", C.c_float), ("shadows", C.c_float), ("hilights", C.c_float), ("clarity", C.c_float)]
+
+
+class GradeParams(C.Structure):
+    _fields_ = [("lift", C.c_float * 4), ("gamma", C.c_float * 4), ("gain", C.c_float * 4),
+                ("offset", C.c_float * 4), ("mode", C.c_int), ("sh_pivot", C.c_float), ("hi_pivot", C.c_float)]
+
+
+class Darkroom(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("filters", C.c_uint32),
+                ("crop_aabb", C.c_uint32 * 4), ("black", C.c_float * 4), ("white", C.c_float * 4),
+                ("whitebalance", C.c_float * 4), ("cam_to_rec2020", C.c_float * 9),
+                ("noise_a", C.c_float), ("noise_b", C.c_float), ("orientation", C.c_uint32),
+                ("colour_primaries", C.c_int), ("colour_trc", C.c_int),
+                ("denoise", DenoiseParams), ("hilite", HiliteParams), ("demosaic", DemosaicParams),
+                ("crop", CropParams), ("colour", ColourParams), ("filmcurv", FilmcurvParams),
+                ("llap", LlapParams), ("grade", GradeParams),
+                ("enable_llap", C.c_int), ("enable_grade", C.c_int)]
+
+
+_lib = None
+_ref = None
+
+
+def build(ref=True):
+    """compile liboracle.so (and oracle/_ref when /root/reference is present). building the checker is not using it."""
+    subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    if ref and os.path.isdir("/root/reference/src/pipe/modules/i-mlv"):
+        subprocess.run(["make", "-C", _HERE, "-s", "ref"], check=True)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build(ref=False)
+        _lib = C.CDLL(path)
+        _lib.o_darkroom_run.restype = C.c_int
+    return _lib
+
+
+def ref_lib():
+    """the reference's own video_mlv.c, compiled by `make -C oracle ref`; None when it was never built."""
+    global _ref
+    if _ref is None:
+        path = os.path.join(_HERE, "_ref", "libmlvref.so")
+        if not os.path.exists(path):
+            return None
+        _ref = C.CDLL(path)
+    return _ref
+
+
+def img(a):
+    """wrap a float32 numpy array (h,w) or (h,w,4) as oimg_t (keeps a reference to the array)."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    h, w = a.shape[:2]
+    c = 1 if a.ndim == 2 else a.shape[2]
+    o = OImg(w, h, c, a.ctypes.data_as(C.POINTER(C.c_float)))
+    o._keep = a
+    return o
+
+
+def new_img(h, w, c=1):
+    a = np.zeros((h, w) if c == 1 else (h, w, c), dtype=np.float32)
+    return a, img(a)
+
+
+def fptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def f4(*v):
+    return (C.c_float * 4)(*v)
+
+
+def i4(*v):
+    return (C.c_int * 4)(*v)
+
+
+def darkroom_defaults(width, height):
+    d = Darkroom()
+    lib().o_darkroom_defaults(C.byref(d), C.c_uint32(width), C.c_uint32(height))
+    return d
+
+
+def darkroom_out_size(d):
+    w, h = C.c_uint32(), C.c_uint32()
+    lib().o_darkroom_out_size(C.byref(d), C.byref(w), C.byref(h))
+    return w.value, h.value
+
+
+_STAGE_CH = {1: 1, 2: 1, 3: 4, 4: 4, 5: 4, 6: 4, 7: 4}
+
+
+def darkroom_run(d, raw, stage=-1):
+    """run the default darkroom graph on a (H,W) uint16 mosaic; returns (oh,ow,4) float32, or the
+    intermediate image of `stage` (see vkdt_oracle.h)."""
+    raw = np.ascontiguousarray(raw, dtype=np.uint16)
+    assert raw.shape == (d.height, d.width)
+    ow, oh = darkroom_out_size(d)
+    cw, ch = d.crop_aabb[2] - d.crop_aabb[0], d.crop_aabb[3] - d.crop_aabb[1]
+    rp = raw.ctypes.data_as(C.POINTER(C.c_uint16))
+    if stage < 0:
+        out = np.zeros((oh, ow, 4), dtype=np.float32)
+        lib().o_darkroom_run(C.byref(d), rp, fptr(out), -1, None)
+        return out
+    c = _STAGE_CH[stage]
+    shape = (ch, cw) if stage <= 2 else ((ch, cw, 4) if stage == 3 else (oh, ow, 4))
+    so = np.zeros(shape, dtype=np.float32)
+    lib().o_darkroom_run(C.byref(d), rp, None, stage, fptr(so))
+    return so
+
+
+def mlv_unpack(words, pixel_cnt, bpp):
+    """words: uint16 array of the packed payload with at least one spare word at the end."""
+    words = np.ascontiguousarray(words, dtype=np.uint16)
+    out = np.zeros(pixel_cnt, dtype=np.uint16)
+    lib().o_mlv_unpack(words.ctypes.data_as(C.POINTER(C.c_uint16)), C.c_uint64(pixel_cnt), C.c_int(bpp),
+                       out.ctypes.data_as(C.POINTER(C.c_uint16)))
+    return out
+
+
+def ref_mlv_decode(filename, frame=0):
+    r = ref_lib()
+    if r is None:
+        raise RuntimeError("oracle/_ref/libmlvref.so not built (run `make -C oracle ref` where /root/reference exists)")
+    info = (C.c_int * 6)()
+    if r.ref_mlv_info(filename.encode(), info):
+        raise RuntimeError("reference mlv_open_clip failed on " + filename)
+    w, h = info[0], info[1]
+    out = np.zeros((h, w), dtype=np.uint16)
+    if r.ref_mlv_decode(filename.encode(), C.c_uint64(frame), out.ctypes.data_as(C.POINTER(C.c_uint16))):
+        raise RuntimeError("reference mlv_get_frame failed")
+    return out, dict(width=w, height=h, bpp=info[2], black=info[3], white=info[4], frames=info[5])

@@ -1,0 +1,134 @@
+"""Synthetic raw inputs of the shapes BASELINE.json names and a minimal MLV writer
+(container layout per SURVEY.md Appendix E: MLVI + RAWI + N x VIDF, little endian, packed(1)).
+
+There is no network and no camera file in the image, so every benchmark/test input is generated here:
+a smooth scene (low-frequency sinusoids) + sharp rectangles + two discs driven 1.5x over the white level
+(so that hilite has work to do), sampled through the CFA, scaled to 14 bit with black 2048 / white 15000,
+plus Poisson-Gaussian noise sigma^2 = a + b (x - black).
+"""
+import struct
+import numpy as np
+
+BLACK = 2048
+WHITE = 15000
+
+# canonical 6x6 x-trans layout after alignment (0 r, 1 g, 2 b), rows top to bottom
+XTRANS = np.array([[1, 0, 1, 1, 2, 1],
+                   [2, 1, 2, 0, 1, 0],
+                   [1, 0, 1, 1, 2, 1],
+                   [1, 2, 1, 1, 0, 1],
+                   [0, 1, 0, 2, 1, 2],
+                   [1, 2, 1, 1, 0, 1]], dtype=np.int32)
+
+
+def cfa_pattern(width, height, xtrans=False):
+    """(H,W) int32 map of colour index 0 r / 1 g / 2 b; bayer is RGGB starting at (0,0)."""
+    if xtrans:
+        return np.tile(XTRANS, ((height + 5) // 6, (width + 5) // 6))[:height, :width]
+    return np.tile(np.array([[0, 1], [1, 2]], dtype=np.int32), ((height + 1) // 2, (width + 1) // 2))[:height, :width]
+
+
+def scene_rgb(width, height, seed=0x5EED0000):
+    """linear camera rgb in [0, ~1.5], float32 (H,W,3); deterministic in (width, height, seed)."""
+    rng = np.random.default_rng(seed & 0xFFFFFFFF)
+    y = np.linspace(0.0, 1.0, height, dtype=np.float32)[:, None]
+    x = np.linspace(0.0, 1.0, width, dtype=np.float32)[None, :]
+    img = np.zeros((height, width, 3), dtype=np.float32)
+    base = np.full((height, width), 0.28, dtype=np.float32)
+    for _ in range(6):
+        fx, fy = rng.uniform(0.5, 6.0, 2)
+        ph = rng.uniform(0, 2 * np.pi)
+        amp = rng.uniform(0.02, 0.08)
+        base += np.float32(amp) * np.sin(np.float32(2 * np.pi) * (np.float32(fx) * x + np.float32(fy) * y) + np.float32(ph))
+    tint = np.array([0.9, 1.0, 0.8], dtype=np.float32)
+    img[:] = base[:, :, None] * tint
+    for k in range(3):  # sharp edged rectangles
+        x0, y0 = rng.uniform(0.05, 0.6, 2)
+        w, h = rng.uniform(0.1, 0.3, 2)
+        col = rng.uniform(0.05, 0.9, 3).astype(np.float32)
+        xa, xb = int(x0 * width), int(min(1.0, x0 + w) * width)
+        ya, yb = int(y0 * height), int(min(1.0, y0 + h) * height)
+        img[ya:yb, xa:xb] = col
+    for k in range(2):  # clipped discs
+        cx, cy = rng.uniform(0.2, 0.8, 2)
+        r = rng.uniform(0.03, 0.08)
+        asp = width / float(height)
+        d2 = ((x - np.float32(cx)) * np.float32(asp)) ** 2 + (y - np.float32(cy)) ** 2
+        m = d2 < np.float32(r * r)
+        img[m] = np.array([1.5, 1.45, 1.2], dtype=np.float32)
+    return np.maximum(img, 0.0)
+
+
+def mosaic(width, height, seed=0x5EED0000, xtrans=False, noise_a=100.0, noise_b=2.0, wb=(2.0, 1.0, 1.5)):
+    """(H,W) uint16 14-bit mosaic. wb: camera white balance multipliers; the sensor sees scene/wb."""
+    rgb = scene_rgb(width, height, seed)
+    pat = cfa_pattern(width, height, xtrans)
+    val = np.take_along_axis(rgb, pat[:, :, None], axis=2)[:, :, 0]
+    val = val / np.asarray(wb, dtype=np.float32)[pat]
+    lin = val * np.float32(WHITE - BLACK)
+    rng = np.random.default_rng((seed ^ 0xA5A5A5A5) & 0xFFFFFFFF)
+    sigma = np.sqrt(np.float32(noise_a) + np.float32(noise_b) * np.maximum(lin, 0.0))
+    lin = lin + sigma * rng.standard_normal(lin.shape, dtype=np.float32)
+    return np.clip(np.rint(lin + BLACK), 0, 16383).astype(np.uint16)
+
+
+def pack_bits(pix, bpp=14):
+    """pack (N,) uint16 pixels MSB-first into a stream of little-endian 16-bit words (raw.h:30-43,
+    video_mlv.c:261-273).  returns uint16 words incl. 2 spare words of padding."""
+    pix = np.ascontiguousarray(pix, dtype=np.uint16).ravel()
+    n = pix.size
+    nbits = n * bpp
+    nwords = (nbits + 15) // 16
+    shifts = np.arange(bpp - 1, -1, -1, dtype=np.uint16)
+    bits = ((pix[:, None] >> shifts) & 1).astype(np.uint8).ravel()
+    pad = nwords * 16 - nbits
+    if pad:
+        bits = np.concatenate([bits, np.zeros(pad, dtype=np.uint8)])
+    by = np.packbits(bits)  # big-endian bit order within bytes, byte stream = big-endian words
+    words = by.reshape(-1, 2)
+    words = (words[:, 0].astype(np.uint16) << 8) | words[:, 1].astype(np.uint16)
+    return np.concatenate([words, np.zeros(2, dtype=np.uint16)])
+
+
+def pack_bits_fast14(pix):
+    """vectorised 14-bit packer: 8 pixels -> 7 words. pix.size must be a multiple of 8."""
+    p = np.ascontiguousarray(pix, dtype=np.uint16).ravel().astype(np.uint32).reshape(-1, 8)
+    acc = np.zeros((p.shape[0], 7), dtype=np.uint32)
+    # bit position of pixel i in the 112-bit group: [14 i, 14 i + 14)
+    for i in range(8):
+        start = 14 * i
+        wi, sh = divmod(start, 16)
+        # pixel occupies bits sh..sh+13 of word wi (MSB first), may spill into word wi+1
+        room = 16 - sh
+        if room >= 14:
+            acc[:, wi] |= p[:, i] << (room - 14)
+        else:
+            acc[:, wi] |= p[:, i] >> (14 - room)
+            acc[:, wi + 1] |= (p[:, i] << (16 - (14 - room))) & 0xFFFF
+    words = (acc & 0xFFFF).astype(np.uint16).ravel()
+    return np.concatenate([words, np.zeros(2, dtype=np.uint16)])
+
+
+RAWI_SIZE = 4 + 4 + 8 + 2 + 2 + 160
+
+
+def write_mlv(filename, frames, bpp=14, black=BLACK, white=WHITE, fps=(24000, 1000), camera_name=None):
+    """frames: list of (H,W) uint16 arrays. writes MLVI + RAWI [+ IDNT] + VIDF*N (uncompressed)."""
+    h, w = frames[0].shape
+    with open(filename, "wb") as f:
+        f.write(struct.pack("<4sI8sQHHIHHIIII", b"MLVI", 52, b"v2.0\0\0\0\0", 0x1234, 0, 1, 0, 1, 0,
+                            len(frames), 0, fps[0], fps[1]))
+        raw_info = struct.pack("<II3iiiii4i4i2iii18ii", 1, 0, h, w, w * bpp // 8, w * h * bpp // 8, bpp, black, white,
+                               0, 0, w, h, 0, 0, h, w, 0, 0, 0x02010100, 21, *([0] * 18), 1100)
+        assert len(raw_info) == 160, len(raw_info)
+        f.write(struct.pack("<4sIQHH", b"RAWI", RAWI_SIZE, 1, w, h) + raw_info)
+        if camera_name:
+            name = camera_name.encode()[:31]
+            f.write(struct.pack("<4sIQ32sI32s", b"IDNT", 4 + 4 + 8 + 32 + 4 + 32, 2, name, 0x80000285, b""))
+        for i, fr in enumerate(frames):
+            assert fr.shape == (h, w)
+            words = pack_bits_fast14(fr) if (bpp == 14 and fr.size % 8 == 0) else pack_bits(fr, bpp)
+            payload = words[:(w * h * bpp // 8 + 1) // 2].tobytes()[: w * h * bpp // 8]
+            f.write(struct.pack("<4sIQIHHHHI", b"VIDF", 32 + len(payload), 10 + i, i, 0, 0, 0, 0, 0))
+            f.write(payload)
+    return filename
