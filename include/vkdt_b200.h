@@ -1,0 +1,144 @@
+/* vkdt_b200 — C-ABI of the B200-native raw-development engine.
+ *
+ * One shared library (libvkdt_b200.so), plain pointers and sizes only.  Three layers, each replacing a
+ * named interface of the reference (hanatos/vkdt, paths relative to its tree):
+ *
+ *  1. runtime      vkb_init / vkb_cleanup / vkb_malloc ...     replaces src/qvk/qvk.h:96-146 (global `qvk`),
+ *                                                              qvk_init src/qvk/qvk.c:138, qvk_cleanup
+ *  2. dispatch     vkb_dispatch(name, kernel, push, params,    replaces the per-node body of record_command_buffer,
+ *                  connectors)                                 src/pipe/graph-run-nodes-record-cmd.h:333-416: pipeline
+ *                                                              lookup by (node->name, node->kernel) (src/pipe/graph.c:312-314),
+ *                                                              push constants, params uniform, one binding per connector in
+ *                                                              connector order, vkCmdDispatch
+ *  3. graph        vkb_graph_*                                 replaces dt_graph_init/run/cleanup (src/pipe/graph.h:176-194),
+ *                                                              dt_graph_read_config_ascii (src/pipe/graph-io.c:282),
+ *                                                              dt_graph_read_config_line (graph-io.c:232),
+ *                                                              dt_graph_export (src/pipe/graph-export.c:108)
+ *
+ * There is no CPU fallback: every compute entry point returns VKB_ERR_NO_DEVICE when no CUDA device is present.
+ * All functions return 0 on success, a negative vkb_err_t otherwise (the reference returns VkResult, 0 = ok).
+ * A graph is owned by one thread at a time (src/pipe/graph.h:66-69).
+ */
+#ifndef VKDT_B200_H
+#define VKDT_B200_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VKB_API __attribute__((visibility("default")))
+
+typedef enum vkb_err_t
+{
+  VKB_OK              =  0,
+  VKB_ERR_NO_DEVICE   = -1,  /* no CUDA device / driver: the product path refuses to run */
+  VKB_ERR_UNKNOWN_KERNEL = -2, /* no kernel registered for (name, kernel) */
+  VKB_ERR_BAD_ARG     = -3,
+  VKB_ERR_CUDA        = -4,  /* a CUDA call failed; see vkb_last_error() */
+  VKB_ERR_IO          = -5,
+  VKB_ERR_GRAPH       = -6,  /* graph incomplete (the reference's VK_INCOMPLETE, src/pipe/graph.c:745-793) */
+  VKB_ERR_OOM         = -7,
+} vkb_err_t;
+
+/* ---- tokens: <= 8 chars packed little endian into a u64, identical to dt_token_t (src/pipe/token.h:15,39-56) ---- */
+typedef uint64_t vkb_token_t;
+VKB_API vkb_token_t vkb_token(const char *str);
+
+/* ---- 1. runtime ---- */
+VKB_API int  vkb_init(int device_id);            /* qvk_init(): pick device, create the pool + streams */
+VKB_API void vkb_cleanup(void);                  /* qvk_cleanup() */
+VKB_API int  vkb_device_count(void);
+VKB_API const char *vkb_last_error(void);
+VKB_API const char *vkb_version(void);
+VKB_API int  vkb_malloc(void **dptr, size_t bytes);   /* plain device allocation helpers for callers without their own */
+VKB_API int  vkb_free(void *dptr);
+VKB_API int  vkb_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
+VKB_API int  vkb_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
+VKB_API int  vkb_stream_sync(void *stream);
+VKB_API int  vkb_host_alloc(void **hptr, size_t bytes);  /* pinned host staging, the "mapped" pointer of read_source/write_sink */
+VKB_API int  vkb_host_free(void *hptr);
+
+/* ---- 2. dispatch ---- */
+/* one connector image as a kernel sees it (dt_connector_t + dt_connector_image_t, src/pipe/connector.h:156-210) */
+typedef struct vkb_image_t
+{
+  void       *data;     /* device pointer; array layers are contiguous, layer stride = wd*ht*chan*sizeof(format) */
+  uint32_t    wd, ht;   /* roi.wd, roi.ht */
+  uint32_t    chan;     /* channels stored per texel: 1 or 4 (src/pipe/connector.h:281-291) */
+  uint32_t    layers;   /* array_length, >= 1 */
+  vkb_token_t format;   /* "ui16" | "f16" | "f32" */
+} vkb_image_t;
+
+/* launch the kernel registered for (name, kernel) on `stream` (cudaStream_t or 0).
+ * wd/ht/dp: the node's dispatch extent; push: the node's push constant blob (same layout as the reference's
+ * `pc[]` arrays, ints are bit-cast floats); params: the module's (committed) parameter blob;
+ * conn[]: connector images in the node's connector order.  Asynchronous. */
+VKB_API int vkb_dispatch(vkb_token_t name, vkb_token_t kernel, uint32_t wd, uint32_t ht, uint32_t dp,
+                         const void *push, uint32_t push_size, const void *params, uint32_t params_size,
+                         const vkb_image_t *conn, uint32_t num_conn, void *stream);
+/* number of registered (name, kernel) pairs and their names, for introspection / tests */
+VKB_API int vkb_kernel_count(void);
+VKB_API int vkb_kernel_name(int idx, vkb_token_t *name, vkb_token_t *kernel);
+/* kernels launched through vkb_dispatch / vkb_graph_run since the last reset (the bench's gpu_launches) */
+VKB_API uint64_t vkb_launch_count(void);
+VKB_API void     vkb_launch_count_reset(void);
+
+/* ---- 3. graph ---- */
+typedef struct vkb_graph_t vkb_graph_t;
+
+/* run flags, same bits as dt_graph_run_constants_t (src/pipe/modules/api.h:25-37) */
+enum
+{
+  VKB_RUN_ROI            = 1 << 0,
+  VKB_RUN_CREATE_NODES   = 1 << 1,
+  VKB_RUN_ALLOC          = 1 << 2,
+  VKB_RUN_RECORD_CMD_BUF = 1 << 3,
+  VKB_RUN_UPLOAD_SOURCE  = 1 << 4,
+  VKB_RUN_DOWNLOAD_SINK  = 1 << 5,
+  VKB_RUN_WAIT_DONE      = 1 << 6,
+  VKB_RUN_ALL            = -1,
+};
+
+VKB_API vkb_graph_t *vkb_graph_new(void);                                   /* dt_graph_init */
+VKB_API void vkb_graph_free(vkb_graph_t *g);                                /* dt_graph_cleanup */
+VKB_API int  vkb_graph_read_config_ascii(vkb_graph_t *g, const char *filename); /* graph-io.c:282 */
+VKB_API int  vkb_graph_read_config_line(vkb_graph_t *g, const char *line);  /* graph-io.c:232: module: connect: param: frames: fps: */
+VKB_API int  vkb_graph_replace_display(vkb_graph_t *g, const char *sink_module); /* graph-export.c:23-96, e.g. "o-pfm" */
+/* feed a source module from memory instead of a file (what read_source() would have written into the mapped
+ * staging buffer): an already decoded u16 mosaic + the dt_image_params_t fields the source module would fill
+ * (src/pipe/module.h:72-109).  the pointer must stay valid until the run that uploads it finished. */
+typedef struct vkb_raw_params_t
+{
+  uint32_t width, height;
+  uint32_t filters;            /* 0 rgb, 9 x-trans, else bayer (rggb after alignment) */
+  uint32_t crop_aabb[4];
+  float    black[4], white[4];
+  float    whitebalance[4];
+  float    cam_to_rec2020[9];
+  float    noise_a, noise_b;
+  uint32_t orientation;
+  uint32_t packed_bpp;         /* 0: `data` is u16 per pixel; 10/12/14: MLV style packed bit stream, unpacked on the device */
+} vkb_raw_params_t;
+VKB_API int  vkb_graph_set_source(vkb_graph_t *g, const char *inst, const void *data, const vkb_raw_params_t *p);
+/* redirect a sink (o-pfm:main ...) into caller memory instead of a file: rgba f32, wd*ht*16 bytes */
+VKB_API int  vkb_graph_set_sink_buffer(vkb_graph_t *g, const char *inst, void *dst, size_t bytes);
+VKB_API int  vkb_graph_sink_size(vkb_graph_t *g, const char *inst, uint32_t *wd, uint32_t *ht);
+VKB_API int  vkb_graph_set_frame(vkb_graph_t *g, uint32_t frame);
+VKB_API int  vkb_graph_run(vkb_graph_t *g, int runflags);                   /* dt_graph_run, src/pipe/graph.c:719 */
+/* -d perf equivalent (graph.c:881-933): per-kernel milliseconds of the last run; returns number of entries */
+VKB_API int  vkb_graph_perf(vkb_graph_t *g, char *buf, size_t bufsize);
+/* host-side half of a run only (module passes, node rewrite/fusion, liveness + pool layout): needs no device.
+ * writes the launch list as text: one line per kernel launch with its connector images and pool offsets */
+VKB_API int  vkb_graph_plan(vkb_graph_t *g, char *buf, size_t bufsize);
+VKB_API int  vkb_graph_dump_nodes(vkb_graph_t *g, char *buf, size_t bufsize); /* --dump-nodes, graph-print.h:76 */
+/* device-resident variant for kernel-only timing: source already in HBM, sink left in HBM */
+VKB_API int  vkb_graph_set_source_device(vkb_graph_t *g, const char *inst, const void *d_data, const vkb_raw_params_t *p);
+VKB_API int  vkb_graph_sink_device(vkb_graph_t *g, const char *inst, void **d_ptr);
+VKB_API uint64_t vkb_graph_pool_bytes(vkb_graph_t *g);                      /* -d mem: peak pooled HBM */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -253,7 +253,7 @@ void o_colour_main(const oimg_t *in, oimg_t *out, const float *f, int out_f16)
   for(int y = 0; y < out->h; y++) for(int x = 0; x < out->w; x++)
   {
     float rgb[4];
-    o_tex4(in, (x + 0.5f) / (float)out->w, (y + 0.5f) / (float)out->h, rgb);
+    o_tex4(in, (x + 0.5) / (double)out->w, (y + 0.5) / (double)out->h, rgb);
     decode_colour(f, rgb);
     cat16(rgb, one, f);
     if(clip_hl > 0.0f)

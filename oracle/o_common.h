@@ -119,11 +119,19 @@ static inline float o_fetch1(const oimg_t *im, int x, int y)
   return im->p[((size_t)y * im->w + x) * im->c];
 }
 /* texture(img, vec2(u,v)): bilinear, mirrored repeat, normalised coordinates */
-static inline void o_tex4(const oimg_t *im, float u, float v, float *o)
+static inline void o_tex4(const oimg_t *im, double u, double v, float *o)
 {
-  const float x = u * (float)im->w - 0.5f, y = v * (float)im->h - 0.5f;
-  const float fx = floorf(x), fy = floorf(y);
-  const float ax = x - fx, ay = y - fy;
+  /* the oracle is an IDEAL sampler: texture coordinates are carried in double so that the fp32 noise a shader's
+   * (i+0.5)/size division adds (implementation specific, below any texture unit's weight precision) is absent */
+  double x = u * (double)im->w - 0.5, y = v * (double)im->h - 0.5;
+  /* taps the shaders aim at texel centres ((i+0.5)/size) come back from the float division a few ulps off.
+   * every real texture unit resolves those to the exact texel (NVIDIA filters with 8 fractional bits, Vulkan
+   * requires >= 4): snap coordinates closer than 1/4096 to a texel centre.  genuinely fractional taps
+   * (flower +-1.2/0.4, soft +-1.5, semisoft +-0.5) keep exact float weights. */
+  if(fabs(x - rint(x)) < 1.0 / 4096.0) x = rint(x);
+  if(fabs(y - rint(y)) < 1.0 / 4096.0) y = rint(y);
+  const double fx = floor(x), fy = floor(y);
+  const float ax = (float)(x - fx), ay = (float)(y - fy);
   const int x0 = o_mirror((int)fx, im->w), x1 = o_mirror((int)fx + 1, im->w);
   const int y0 = o_mirror((int)fy, im->h), y1 = o_mirror((int)fy + 1, im->h);
   float t00[4], t10[4], t01[4], t11[4];
@@ -133,15 +141,15 @@ static inline void o_tex4(const oimg_t *im, float u, float v, float *o)
     o[k] = (t00[k] * (1.0f - ax) + t10[k] * ax) * (1.0f - ay)
          + (t01[k] * (1.0f - ax) + t11[k] * ax) * ay;
 }
-static inline float o_tex1(const oimg_t *im, float u, float v)
+static inline float o_tex1(const oimg_t *im, double u, double v)
 {
   float t[4]; o_tex4(im, u, v, t); return t[0];
 }
 /* textureGather(img, vec2(u,v), 0): x=(i0,j1) y=(i1,j1) z=(i1,j0) w=(i0,j0), red channel */
-static inline void o_gather(const oimg_t *im, float u, float v, float *o)
+static inline void o_gather(const oimg_t *im, double u, double v, float *o)
 {
-  const float x = u * (float)im->w - 0.5f, y = v * (float)im->h - 0.5f;
-  const int fx = (int)floorf(x), fy = (int)floorf(y);
+  const double x = u * (double)im->w - 0.5, y = v * (double)im->h - 0.5;
+  const int fx = (int)floor(x + 1e-6), fy = (int)floor(y + 1e-6);
   const int x0 = o_mirror(fx, im->w), x1 = o_mirror(fx + 1, im->w);
   const int y0 = o_mirror(fy, im->h), y1 = o_mirror(fy + 1, im->h);
   o[0] = im->p[((size_t)y1 * im->w + x0) * im->c];

@@ -41,7 +41,7 @@ void o_demosaic_gauss(const oimg_t *orig, oimg_t *out, uint32_t filters)
     for(int j = lo; j < hi; j++) for(int i = lo; i < hi; i++)
     {
       if(xt ? (((j + i) & 1) == 1) : (((j + i) & 1) != 1)) continue;
-      const float px = o_tex1(orig, (blk * x + 0.5f + (float)i) / (float)orig->w, (blk * y + 0.5f + (float)j) / (float)orig->h);
+      const float px = o_tex1(orig, (blk * x + 0.5 + (double)i) / (double)orig->w, (blk * y + 0.5 + (double)j) / (double)orig->h);
       mw[0] += (float)i * px; mw[1] += (float)j * px;
       smw += px;
       mb[0] += (float)i / px; mb[1] += (float)j / px;
@@ -52,7 +52,7 @@ void o_demosaic_gauss(const oimg_t *orig, oimg_t *out, uint32_t filters)
     for(int j = lo; j < hi; j++) for(int i = lo; i < hi; i++)
     {
       if(xt ? (((j + i) & 1) == 1) : (((j + i) & 1) != 1)) continue;
-      const float px = o_tex1(orig, (blk * x + 0.5f + (float)i) / (float)orig->w, (blk * y + 0.5f + (float)j) / (float)orig->h);
+      const float px = o_tex1(orig, (blk * x + 0.5 + (double)i) / (double)orig->w, (blk * y + 0.5 + (double)j) / (double)orig->h);
       float p2 = px * px;
       float p0 = (float)i - mw[0], p1 = (float)j - mw[1];
       Sw[0] += p2 * p0 * p0; Sw[1] += p2 * p0 * p1;
@@ -144,15 +144,15 @@ void o_demosaic_fix(const oimg_t *in, const oimg_t *green, const oimg_t *covimg,
   for(int y = 0; y < out->h; y++) for(int x = 0; x < out->w; x++)
   {
     float rgb[3] = {0}, w[3] = {0};
-    const float gc = o_tex1(green, (x + 0.5f) / (float)green->w, (y + 0.5f) / (float)green->h);
+    const float gc = o_tex1(green, (x + 0.5) / (double)green->w, (y + 0.5) / (double)green->h);
     float cov[4];
     if(xt) { o_fetch4(covimg, (x + 1) / 3, (y + 1) / 3, cov); cov[0] = o_clamp(cov[0], 1.f, 10.f); cov[1] = o_clamp(cov[1], 1.f, 10.f); }
     else   { o_fetch4(covimg, (x + 1) / 2, (y + 1) / 2, cov); cov[0] = o_clamp(cov[0], 1.0f, 49.f); cov[1] = o_clamp(cov[1], 1.0f, 49.f); }
     const float ks = xt ? 3.0f : 2.0f;
     for(int j = -r; j <= r; j++) for(int i = -r; i <= r; i++)
     {
-      const float gh  = o_tex1(green, (x + i + 0.5f) / (float)green->w, (y + j + 0.5f) / (float)green->h);
-      const float col = o_tex1(in,    (x + i + 0.5f) / (float)in->w,    (y + j + 0.5f) / (float)in->h);
+      const float gh  = o_tex1(green, (x + i + 0.5) / (double)green->w, (y + j + 0.5) / (double)green->h);
+      const float col = o_tex1(in,    (x + i + 0.5) / (double)in->w,    (y + j + 0.5) / (double)in->h);
       const int px = x + i, py = y + j;
       int c;
       if(xt) c = o_xtrans_colour(px, py); /* no +6 margin in fix.comp:38-40; int division truncates toward zero for negatives */

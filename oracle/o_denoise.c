@@ -50,7 +50,7 @@ void o_denoise_half(const oimg_t *in, oimg_t *out, const int *crop, const float 
     else
     {
       float c[4];
-      o_gather(in, (crop[0] + 2.0f * (x + .5f)) / (float)in->w, (crop[1] + 2.0f * (y + .5f)) / (float)in->h, c);
+      o_gather(in, (crop[0] + 2.0 * (x + .5)) / (double)in->w, (crop[1] + 2.0 * (y + .5)) / (double)in->h, c);
       if(c[0] >= white) c[0] = c[2];
       if(c[2] >= white) c[2] = c[0];
       rgba[0] = c[3]; rgba[1] = (c[0] + c[2]) / 2.0f; rgba[2] = c[1]; rgba[3] = 1.0f;
@@ -70,7 +70,7 @@ static inline void noise_sigma(float a, float b, float black, float white, const
 /* denoise/cov.glsl:21-138 `response` */
 static void response(const oimg_t *img, int px_, int py_, float *cov, float *res)
 {
-  const float iszx = 1.0f / (float)img->w, iszy = 1.0f / (float)img->h;
+  const double iszx = 1.0 / (double)img->w, iszy = 1.0 / (double)img->h;
   float Sw[4] = {0}, Sb[4] = {0}; /* [0][0] [0][1] [1][0] [1][1] */
   float sw = 0.0f, sb = 0.0f;
   float mw[2] = {0}, mb[2] = {0};
@@ -78,7 +78,7 @@ static void response(const oimg_t *img, int px_, int py_, float *cov, float *res
   float t[4];
   for(int j = -2; j <= 2; j++) for(int i = -2; i <= 2; i++)
   {
-    o_tex4(img, (px_ + 0.5f + i) * iszx, (py_ + 0.5f + j) * iszy, t);
+    o_tex4(img, (px_ + 0.5 + i) * iszx, (py_ + 0.5 + j) * iszy, t);
     const float px = o_lum2020(t);
     const float w = 1.0f;
     mw[0] += (float)i * px * w; mw[1] += (float)j * px * w;
@@ -90,7 +90,7 @@ static void response(const oimg_t *img, int px_, int py_, float *cov, float *res
   mb[0] /= smb; mb[1] /= smb;
   for(int j = -2; j <= 2; j++) for(int i = -2; i <= 2; i++)
   {
-    o_tex4(img, (px_ + 0.5f + i) * iszx, (py_ + 0.5f + j) * iszy, t);
+    o_tex4(img, (px_ + 0.5 + i) * iszx, (py_ + 0.5 + j) * iszy, t);
     const float px = o_lum2020(t);
     const float w = 1.0f;
     mean_b += px / 25.0f;
@@ -119,7 +119,7 @@ static void response(const oimg_t *img, int px_, int py_, float *cov, float *res
   float acc[3] = {0}, wt = 0.0f;
   for(int j = -2; j <= 2; j++) for(int i = -2; i <= 2; i++)
   {
-    o_tex4(img, (px_ + 0.5f + i) * iszx, (py_ + 0.5f + j) * iszy, t);
+    o_tex4(img, (px_ + 0.5 + i) * iszx, (py_ + 0.5 + j) * iszy, t);
     const float ht = 2.0f;
     if(t[0] > ht * mean_b) continue; /* hot pixels */
     const float x0 = (float)i * evec0[0] + (float)j * evec0[1];
@@ -164,7 +164,7 @@ void o_denoise_down(const oimg_t *in, oimg_t *out, const o_denoise_params_t *p,
 {
   const float t = 0.2f;
   const float blk = (block == 3) ? 2.23607f : (block == 2 ? 1.414213f : 1.0f);
-  const float szx = (float)in->w, szy = (float)in->h;
+  const double szx = (double)in->w, szy = (double)in->h;
   static const float off[4][2] = {
     { (float)(0.5 + 1.2), (float)(0.5 + 0.4) }, { (float)(0.5 - 1.2), (float)(0.5 - 0.4) },
     { (float)(0.5 + 0.4), (float)(0.5 - 1.2) }, { (float)(0.5 - 0.4), (float)(0.5 + 1.2) } }; /* glslang folds constants in double */
@@ -172,7 +172,7 @@ void o_denoise_down(const oimg_t *in, oimg_t *out, const o_denoise_params_t *p,
   for(int y = 0; y < out->h; y++) for(int x = 0; x < out->w; x++)
   {
     float c0[4];
-    o_tex4(in, (x + 0.5f) / szx, (y + 0.5f) / szy, c0);
+    o_tex4(in, (x + 0.5) / szx, (y + 0.5) / szy, c0);
     float sum[3], wgt[3], sigma[3], wc[3];
     noise_sigma(noise_a, noise_b, black4[1], white4[1], p->edges, c0[0], sigma);
     const float lv = powf(0.7f, (float)level);
@@ -185,7 +185,7 @@ void o_denoise_down(const oimg_t *in, oimg_t *out, const o_denoise_params_t *p,
     for(int o = 0; o < 4; o++)
     {
       float col[4];
-      o_tex4(in, ((float)x + off[o][0]) / szx, ((float)y + off[o][1]) / szy, col);
+      o_tex4(in, ((double)x + off[o][0]) / szx, ((double)y + off[o][1]) / szy, col);
       for(int k = 0; k < 3; k++)
       {
         const float e = o_clamp(1.0f - 0.5f * (wc[k] * fabsf(gamma08(col[k]) - gamma08(c0[k]))), 0.0f, 1.0f);
@@ -287,8 +287,8 @@ void o_denoise_doub(const oimg_t *in, const oimg_t *crs0, const oimg_t *crs1, oi
   for(int y = 0; y < out->h; y++) for(int x = 0; x < out->w; x++)
   {
     float upsm[4], down[4];
-    o_tex4(crs0, (x + 0.5f) / (float)out->w, (y + 0.5f) / (float)out->h, upsm);
-    o_tex4(crs1, (x + 0.5f) / (float)out->w, (y + 0.5f) / (float)out->h, down);
+    o_tex4(crs0, (x + 0.5) / (double)out->w, (y + 0.5) / (double)out->h, upsm);
+    o_tex4(crs1, (x + 0.5) / (double)out->w, (y + 0.5) / (double)out->h, down);
     float black = black4[1], white = white4[1], crs = upsm[1], crs1v = down[1];
     float T = 0.5f * p->strength * upsm[3], blendw = p->luma;
     int col; /* 0 r 1 g 2 b */
@@ -302,7 +302,7 @@ void o_denoise_doub(const oimg_t *in, const oimg_t *crs0, const oimg_t *crs1, oi
     }
     float sigma[3];
     noise_sigma(noise_a, noise_b, black, white, p->edges, crs, sigma);
-    float val = o_tex1(in, (x + crop[0] + .5f) / (float)in->w, (y + crop[1] + .5f) / (float)in->h);
+    float val = o_tex1(in, (x + crop[0] + .5) / (double)in->w, (y + crop[1] + .5) / (double)in->h);
     blendw = 0.5f * (blendw + 1.0f);
     if(val < white)
     {

@@ -31,7 +31,7 @@ void o_hilite_half(const oimg_t *in, oimg_t *out, const o_hilite_params_t *p, ui
     else
     {
       float c[4];
-      o_gather(in, 2.0f * (x + .5f) / (float)in->w, 2.0f * (y + .5f) / (float)in->h, c);
+      o_gather(in, 2.0 * (x + .5) / (double)in->w, 2.0 * (y + .5) / (double)in->h, c);
       if(c[0] >= white) c[0] = c[2];
       if(c[2] >= white) c[2] = c[0];
       rgba[0] = c[3]; rgba[1] = (c[0] + c[2]) / 2.0f; rgba[2] = c[1]; rgba[3] = 1.0f;
@@ -56,7 +56,7 @@ void o_hilite_reduce(const oimg_t *in, oimg_t *out, const o_hilite_params_t *p, 
     for(int jj = -2; jj <= 2; jj++) for(int ii = -2; ii <= 2; ii++)
     {
       float rgb[4];
-      o_tex4(in, (float)(2*x + ii + 0.5f) / (float)in->w, (float)(2*y + jj + 0.5f) / (float)in->h, rgb);
+      o_tex4(in, (double)(2*x + ii + 0.5) / (double)in->w, (double)(2*y + jj + 0.5) / (double)in->h, rgb);
       const float l = o_lum2020(rgb);
       edge[0] += w[jj+2] * sw[ii+2] * l;
       edge[1] += w[ii+2] * sw[jj+2] * l;
@@ -100,7 +100,7 @@ static void gauss_expand(const oimg_t *im, int ox, int oy, float *c)
   for(int ii = i0; ii <= 1; ii++) for(int jj = j0; jj <= 1; jj++)
   {
     float rgb[4];
-    o_tex4(im, (float)(ix + ii + 0.5f) / (float)im->w, (float)(iy + jj + 0.5f) / (float)im->h, rgb);
+    o_tex4(im, (double)(ix + ii + 0.5) / (double)im->w, (double)(iy + jj + 0.5) / (double)im->h, rgb);
     const float wy = dy ? w[2*jj+1] : w[2*jj+2];
     const float wx = dx ? w[2*ii+1] : w[2*ii+2];
     for(int k = 0; k < 3; k++) c[k] += rgb[k] * wy * wx;
@@ -193,7 +193,7 @@ void o_hilite_doub(const oimg_t *in, const oimg_t *coarse, oimg_t *out, const o_
     else
     {
       float c[4];
-      o_gather(in, 2.0f * (x + .5f) / (float)in->w, 2.0f * (y + .5f) / (float)in->h, c);
+      o_gather(in, 2.0 * (x + .5) / (double)in->w, 2.0 * (y + .5) / (double)in->h, c);
       const float ming = o_min(c[0], c[2]);
       const float sr = c[3] / o_max(0.001f, upsm[0]);
       const float sg = ming / o_max(0.001f, upsm[1]);

@@ -52,12 +52,12 @@ void o_llap_curve(const oimg_t *in, oimg_t *out, const o_llap_params_t *p)
 }
 
 /* shared.glsl:130-148 */
-static float sample_semisoft(const oimg_t *tex, float u, float v)
+static float sample_semisoft(const oimg_t *tex, double u, double v)
 {
-  const float sx = (float)tex->w, sy = (float)tex->h;
-  const float cx = u * sx, cy = v * sy;
-  const float x0 = (cx - .5f) / sx, x1 = (cx + .5f) / sx;
-  const float y0 = (cy - .5f) / sy, y1 = (cy + .5f) / sy;
+  const double sx = (double)tex->w, sy = (double)tex->h;
+  const double cx = u * sx, cy = v * sy;
+  const double x0 = (cx - .5) / sx, x1 = (cx + .5) / sx;
+  const double y0 = (cy - .5) / sy, y1 = (cy + .5) / sy;
   float r = 0.0f;
   r += o_tex1(tex, x0, y0);
   r += o_tex1(tex, x1, y0);
@@ -66,12 +66,12 @@ static float sample_semisoft(const oimg_t *tex, float u, float v)
   return r / 4.0f;
 }
 /* shared.glsl:99-127 */
-static float sample_soft(const oimg_t *tex, float u, float v)
+static float sample_soft(const oimg_t *tex, double u, double v)
 {
-  const float sx = (float)tex->w, sy = (float)tex->h;
-  const float cx = u * sx, cy = v * sy;
-  const float px[3] = { (cx - 1.5f) / sx, cx / sx, (cx + 1.5f) / sx };
-  const float py[3] = { (cy - 1.5f) / sy, cy / sy, (cy + 1.5f) / sy };
+  const double sx = (double)tex->w, sy = (double)tex->h;
+  const double cx = u * sx, cy = v * sy;
+  const double px[3] = { (cx - 1.5) / sx, cx / sx, (cx + 1.5) / sx };
+  const double py[3] = { (cy - 1.5) / sy, cy / sy, (cy + 1.5) / sy };
   float r = 0.0f;
   for(int j = 0; j < 3; j++) for(int i = 0; i < 3; i++) r += o_tex1(tex, px[i], py[j]);
   return r / 9.0f;
@@ -82,12 +82,12 @@ void o_llap_reduce(const oimg_t *in, oimg_t *out)
 {
 #pragma omp parallel for schedule(static)
   for(int y = 0; y < out->h; y++) for(int x = 0; x < out->w; x++)
-    o_store1(out, x, y, sample_semisoft(in, (2 * x + 0.5f) / (float)in->w, (2 * y + 0.5f) / (float)in->h), 1);
+    o_store1(out, x, y, sample_semisoft(in, (2 * x + 0.5) / (double)in->w, (2 * y + 0.5) / (double)in->h), 1);
 }
 
 static inline float gauss_expand(const oimg_t *im, int ox, int oy)
 { /* llap/assemble.comp:19-24 */
-  return sample_soft(im, (ox * 0.5f + 0.5f) / (float)im->w, (oy * 0.5f + 0.5f) / (float)im->h);
+  return sample_soft(im, (ox * 0.5 + 0.5) / (double)im->w, (oy * 0.5 + 0.5) / (double)im->h);
 }
 
 /* llap/assemble.comp:52-88.  l0/l1: arrays of NUM_GAMMA+1 layers of the fine / coarse level.

@@ -1,0 +1,172 @@
+// gaussian splatting demosaic for bayer and x-trans.
+// replaces src/pipe/modules/demosaic/{gauss,splat,fix}.comp (wired by demosaic/main.c:159-202, method 0).
+// `down.comp` is not needed: gauss.comp declares its output as img_in but never samples it.
+// the 1:1 shared/resample node vkdt-cli appends (demosaic/main.c:193-201) is the identity and is elided.
+#include "common.cuh"
+
+struct demosaic_push_t { float wb[4]; uint32_t filters; };
+
+// ---- gauss: green-only structure tensor per block -> (eval.xy, axis snapped evec) (gauss.comp:17-126) ----
+__global__ void __launch_bounds__(256) k_demosaic_gauss(const __half *__restrict__ orig, int iw, int ih,
+    uint2 *__restrict__ out, int ow, int oh, int xtrans)
+{
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if(x >= ow || y >= oh) return;
+  const int blk = xtrans ? 3 : 2, lo = xtrans ? 0 : -1;
+  float px[16];
+  int n = 0;
+  float mwx = 0, mwy = 0, mbx = 0, mby = 0, smw = 0, smb = 0;
+  for(int j = lo; j < 3; j++) for(int i = lo; i < 3; i++)
+  {
+    if(xtrans ? (((j + i) & 1) == 1) : (((j + i) & 1) != 1)) continue;
+    const float p = ld_h_mirror(orig, iw, ih, blk * x + i, blk * y + j);
+    px[n++] = p;
+    mwx += (float)i * p; mwy += (float)j * p; smw += p;
+    mbx += (float)i / p; mby += (float)j / p; smb += 1.0f / p;
+  }
+  mwx /= smw; mwy /= smw; mbx /= smb; mby /= smb;
+  float Sw0 = 0, Sw1 = 0, Sw2 = 0, Sw3 = 0, Sb0 = 0, Sb1 = 0, Sb2 = 0, Sb3 = 0, sw = 0, sb = 0;
+  n = 0;
+  for(int j = lo; j < 3; j++) for(int i = lo; i < 3; i++)
+  {
+    if(xtrans ? (((j + i) & 1) == 1) : (((j + i) & 1) != 1)) continue;
+    const float p = px[n++];
+    float p2 = p * p;
+    float p0 = (float)i - mwx, p1 = (float)j - mwy;
+    Sw0 += p2 * p0 * p0; Sw1 += p2 * p0 * p1; Sw2 += p2 * p1 * p0; Sw3 += p2 * p1 * p1;
+    sw += p2;
+    p0 = (float)i - mbx; p1 = (float)j - mby;
+    p2 = 1.0f / p2;
+    Sb0 += p2 * p0 * p0; Sb1 += p2 * p0 * p1; Sb2 += p2 * p1 * p0; Sb3 += p2 * p1 * p1;
+    sb += p2;
+  }
+  Sw0 /= sw; Sw1 /= sw; Sw2 /= sw; Sw3 /= sw;
+  Sb0 /= sb; Sb1 /= sb; Sb2 /= sb; Sb3 /= sb;
+  const bool usew = (Sw0 * Sw3 - Sw1 * Sw2) < (Sb0 * Sb3 - Sb1 * Sb2);
+  float e0, e1, v0x, v0y, v1x, v1y;
+  evd2x2(usew ? Sw0 : Sb0, usew ? Sw2 : Sb2, usew ? Sw3 : Sb3, e0, e1, v0x, v0y, v1x, v1y);
+  if(!xtrans)
+  {
+    e0 *= 0.2f; e1 *= 0.2f;
+    if(fabsf(v0x) > fabsf(v0y)) { v0x = 1; v0y = 0; }
+    else                        { v0x = 0; v0y = 1; }
+  }
+  else
+  {
+    e0 *= 0.4f; e1 *= 0.4f;
+    if     (fabsf(v0x) > 2.f * fabsf(v0y)) { v0x = 1; v0y = 0; }
+    else if(fabsf(v0y) > 2.f * fabsf(v0x)) { v0x = 0; v0y = 1; }
+    else e0 = e1 = .1f;
+  }
+  st_rgba(out, ow, x, y, make_float4(e0, e1, v0x, v0y));
+}
+
+// ---- splat: green by anisotropic gaussian weights (splat.comp:16-140) ----
+__global__ void __launch_bounds__(256) k_demosaic_splat(const __half *__restrict__ in, int w, int h,
+    const uint2 *__restrict__ gauss, int gw, int gh, __half *__restrict__ out, int xtrans)
+{
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if(x >= w || y >= h) return;
+  const float4 cov = xtrans ? ld_rgba_clamp(gauss, gw, gh, x / 3, y / 3) : ld_rgba_clamp(gauss, gw, gh, (x + 1) / 2, (y + 1) / 2);
+  const float e0 = clampf(cov.x, 0.01f, 25.0f), e1 = clampf(cov.y, 0.01f, 25.0f);
+  const int r = xtrans ? 2 : 1;
+  float g = 0.0f, wg = 0.0f;
+  for(int j = -r; j <= r; j++) for(int i = -r; i <= r; i++)
+  {
+    const int c = xtrans ? xtrans_colour(x + i + 6, y + j + 6) : bayer_colour(x + i, y + j);
+    if(c != 1) continue; // only the green accumulator reaches the output
+    int px = x + i, py = y + j;
+    if(px < 0) px += 6;
+    if(py < 0) py += 6;
+    if(px >= w) px -= 6;
+    if(py >= h) py -= 6;
+    const float col = ld_h_clamp(in, w, h, px, py);
+    const float of0 = cov.z * (float)i + cov.w * (float)j;
+    const float of1 = -cov.w * (float)i + cov.z * (float)j;
+    float weight = clampf(expf(-0.5f * (of0 / e0 * of0 + of1 / e1 * of1)), 1e-4f, 1.0f);
+    if(i == 0 && j == 0) weight = 666.0f;
+    g += col * weight;
+    wg += weight;
+  }
+  out[(size_t)y * w + x] = __float2half_rn(g / fmaxf(1e-8f, wg));
+}
+
+VKB_DEV float fix_gauss(float e0, float e1, float cz, float cw, int i, int j)
+{
+  const float of0 = cz * (float)i + cw * (float)j;
+  const float of1 = -cw * (float)i + cz * (float)j;
+  return clampf(expf(-0.5f * (of0 / e0 * of0 + of1 / e1 * of1)), 1e-3f, 1.0f);
+}
+
+// ---- fix: red/blue by interpolating the ratio to green (fix.comp:25-135) ----
+__global__ void __launch_bounds__(256) k_demosaic_fix(const __half *__restrict__ in, const __half *__restrict__ green, int w, int h,
+    const uint2 *__restrict__ covimg, int gw, int gh, uint2 *__restrict__ out, int xtrans, int fixup)
+{
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if(x >= w || y >= h) return;
+  const float gc = ld_h(green, w, x, y);
+  float4 cov = xtrans ? ld_rgba_clamp(covimg, gw, gh, (x + 1) / 3, (y + 1) / 3) : ld_rgba_clamp(covimg, gw, gh, (x + 1) / 2, (y + 1) / 2);
+  const int r = xtrans ? clampi(fixup + 2, 2, 3) : clampi(fixup + 1, 1, 2);
+  if(xtrans) { cov.x = clampf(cov.x, 1.f, 10.f); cov.y = clampf(cov.y, 1.f, 10.f); }
+  else       { cov.x = clampf(cov.x, 1.0f, 49.f); cov.y = clampf(cov.y, 1.0f, 49.f); }
+  const float ks = xtrans ? 3.0f : 2.0f;
+  float rgb[3] = {0, 0, 0}, wt[3] = {0, 0, 0};
+  for(int j = -r; j <= r; j++) for(int i = -r; i <= r; i++)
+  {
+    const int px = x + i, py = y + j;
+    const int c = xtrans ? xtrans_colour(px, py) : bayer_colour(px, py);
+    if(c == 1) { rgb[1] = gc; wt[1] = 1.0f; continue; }
+    const float gh_ = ld_h_mirror(green, w, h, px, py);
+    const float col = ld_h_mirror(in, w, h, px, py);
+    const float weight = fix_gauss(ks * cov.x, ks * cov.y, cov.z, cov.w, i, j);
+    if(xtrans) { const float corr = (1e-4f + gc) / (1e-4f + gh_); rgb[c] += col * corr * weight; }
+    else rgb[c] += col * (1e-4f + gc) / (1e-4f + gh_) * weight;
+    wt[c] += weight;
+  }
+  st_rgba(out, w, x, y, make_float4(rgb[0] / fmaxf(1e-8f, wt[0]), rgb[1] / fmaxf(1e-8f, wt[1]), rgb[2] / fmaxf(1e-8f, wt[2]), 1.0f));
+}
+
+static inline dim3 grid2d(unsigned w, unsigned h) { return dim3(vkb_cdiv(w, 32), vkb_cdiv(h, 8)); }
+static const dim3 blk2d(32, 8);
+
+// conn: [0] (unused `down` output, may be null) [1] orig mosaic f16 [2] output rgba f16
+static int launch_demosaic_gauss(const vkb_launch_t *l)
+{
+  VKB_REQUIRE(l->num_conn >= 3 && l->push_size >= sizeof(demosaic_push_t));
+  const demosaic_push_t *pc = (const demosaic_push_t *)l->push;
+  const vkb_image_t *orig = l->conn + 1, *out = l->conn + 2;
+  VKB_REQUIRE(orig->chan == 1 && orig->format == VKB_TOKEN_F16 && out->chan == 4 && out->format == VKB_TOKEN_F16);
+  k_demosaic_gauss<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const __half *)orig->data, orig->wd, orig->ht,
+      (uint2 *)out->data, out->wd, out->ht, pc->filters == 9);
+  VKB_CHECK_LAUNCH();
+  return VKB_OK;
+}
+VKB_REGISTER("demosaic", "gauss", launch_demosaic_gauss);
+
+// conn: [0] input mosaic f16 [1] gauss rgba f16 [2] output green f16
+static int launch_demosaic_splat(const vkb_launch_t *l)
+{
+  VKB_REQUIRE(l->num_conn >= 3 && l->push_size >= sizeof(demosaic_push_t));
+  const demosaic_push_t *pc = (const demosaic_push_t *)l->push;
+  const vkb_image_t *in = l->conn, *g = l->conn + 1, *out = l->conn + 2;
+  VKB_REQUIRE(in->chan == 1 && g->chan == 4 && out->chan == 1 && in->wd == out->wd && in->ht == out->ht);
+  k_demosaic_splat<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const __half *)in->data, in->wd, in->ht,
+      (const uint2 *)g->data, g->wd, g->ht, (__half *)out->data, pc->filters == 9);
+  VKB_CHECK_LAUNCH();
+  return VKB_OK;
+}
+VKB_REGISTER("demosaic", "splat", launch_demosaic_splat);
+
+// conn: [0] input mosaic f16 [1] green f16 [2] cov rgba f16 [3] output rgba f16.  params: { int colour(fixup); int method }
+static int launch_demosaic_fix(const vkb_launch_t *l)
+{
+  VKB_REQUIRE(l->num_conn >= 4 && l->push_size >= sizeof(demosaic_push_t) && l->params_size >= 4);
+  const demosaic_push_t *pc = (const demosaic_push_t *)l->push;
+  const vkb_image_t *in = l->conn, *g = l->conn + 1, *cov = l->conn + 2, *out = l->conn + 3;
+  VKB_REQUIRE(in->chan == 1 && g->chan == 1 && cov->chan == 4 && out->chan == 4 && in->wd == out->wd && g->wd == out->wd);
+  k_demosaic_fix<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const __half *)in->data, (const __half *)g->data, in->wd, in->ht,
+      (const uint2 *)cov->data, cov->wd, cov->ht, (uint2 *)out->data, pc->filters == 9, ((const int32_t *)l->params)[0]);
+  VKB_CHECK_LAUNCH();
+  return VKB_OK;
+}
+VKB_REGISTER("demosaic", "fix", launch_demosaic_fix);

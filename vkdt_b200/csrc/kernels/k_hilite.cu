@@ -1,0 +1,268 @@
+// highlight reconstruction on the mosaic via a clip-aware gaussian pyramid.
+// replaces src/pipe/modules/hilite/{half,reduce,assemble,doub}.comp (wired by hilite/main.c:5-90).
+// all taps of the reference sit on exact texel centres, so the sampler reduces to mirrored texel fetches.
+#include "common.cuh"
+
+struct hilite_params_t { float white, desat, soft; };          // hilite/params
+struct hilite_push_t   { float wb[4]; uint32_t filters; };     // hilite/main.c:26
+
+// ---- half: mosaic block -> rgb, clipped greens replaced (half.comp:24-72) ----
+__global__ void __launch_bounds__(256) k_hilite_half(const __half *__restrict__ in, int iw, int ih,
+    uint2 *__restrict__ out, int ow, int oh, float white, int xtrans)
+{
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if(x >= ow || y >= oh) return;
+  float4 rgba;
+  if(xtrans)
+  {
+    float c[9];
+#pragma unroll
+    for(int i = 0; i < 3; i++)
+#pragma unroll
+      for(int j = 0; j < 3; j++) c[3 * i + j] = ld_h_clamp(in, iw, ih, 3 * x + i, 3 * y + j);
+    if(c[1] >= white) c[1] = c[7];
+    if(c[7] >= white) c[7] = c[1];
+    if(c[3] >= white) c[3] = c[5];
+    if(c[5] >= white) c[5] = c[3];
+    const float maxg = fmaxf(fmaxf(fmaxf(c[0], c[2]), c[4]), fmaxf(c[6], c[8]));
+    if(maxg >= white) c[0] = c[2] = c[4] = c[6] = c[8] = 1.0f;
+    const float col0 = (c[1] + c[7]) * 0.5f, col1 = (c[3] + c[5]) * .5f;
+    if(((x + y) & 1) > 0) { rgba.x = col0; rgba.z = col1; }
+    else                  { rgba.z = col0; rgba.x = col1; }
+    rgba.y = (c[0] + c[2] + c[4] + c[6] + c[8]) / 5.0f;
+    rgba.w = 1.0f;
+  }
+  else
+  { // textureGather at the block centre: x=(0,1) y=(1,1) z=(1,0) w=(0,0)
+    const int x0 = mirror1(2 * x, iw), x1 = mirror1(2 * x + 1, iw), y0 = mirror1(2 * y, ih), y1 = mirror1(2 * y + 1, ih);
+    float cx = ld_h(in, iw, x0, y1), cy = ld_h(in, iw, x1, y1), cz = ld_h(in, iw, x1, y0), cw = ld_h(in, iw, x0, y0);
+    if(cx >= white) cx = cz;
+    if(cz >= white) cz = cx;
+    rgba = make_float4(cw, (cx + cz) / 2.0f, cy, 1.0f);
+  }
+  st_rgba(out, ow, x, y, rgba);
+}
+
+// ---- reduce: 5x5 binomial over unclipped pixels, desaturating near white (reduce.comp:21-60) ----
+__global__ void __launch_bounds__(256) k_hilite_reduce(const uint2 *__restrict__ in, int iw, int ih,
+    uint2 *__restrict__ out, int ow, int oh, hilite_params_t p, float wbr, float wbg, float wbb)
+{
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if(x >= ow || y >= oh) return;
+  float white = p.white;
+  if(!(white > 0.0f)) white = 1.0f;
+  const float w[5] = {1.0f / 16.0f, 4.0f / 16.0f, 6.0f / 16.0f, 4.0f / 16.0f, 1.0f / 16.0f};
+  const float sw[5] = {1.0f, 2.0f, 0.0f, -2.0f, -1.0f};
+  float ex = 0.0f, ey = 0.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f, wgt = 0.0f;
+  const float ds = p.desat * p.desat;
+#pragma unroll
+  for(int jj = -2; jj <= 2; jj++)
+#pragma unroll
+    for(int ii = -2; ii <= 2; ii++)
+    {
+      const float4 rgb = ld_rgba_mirror(in, iw, ih, 2 * x + ii, 2 * y + jj);
+      const float l = lum2020(rgb.x, rgb.y, rgb.z);
+      ex += w[jj + 2] * sw[ii + 2] * l;
+      ey += w[ii + 2] * sw[jj + 2] * l;
+      const float u = w[ii + 2] * w[jj + 2];
+      const float rw = rgb.x * wbr, gw = rgb.y * wbg, bw = rgb.z * wbb;
+      const float cmax = fmaxf(rw, fmaxf(gw, bw));
+      const float cmin = fminf(rw, fminf(gw, bw));
+      const float sat = (cmax - cmin) / fmaxf(1e-3f, cmax);
+      if(rgb.x < white && rgb.y < white && rgb.z < white)
+      {
+        const float s = smoothstepf(0.2f, 1.0f, fmaxf(rgb.x, fmaxf(rgb.y, rgb.z)) / white);
+        float t = smoothstepf(0.15f, 0.9f, sat);
+        t = clampf(5.0f * ds * ds * s * t, 0.0f, 1.0f);
+        cr += mixf(rgb.x, (cmax + cmin) / wbr * .5f, t) * u;
+        cg += mixf(rgb.y, (cmax + cmin) / wbg * .5f, t) * u;
+        cb += mixf(rgb.z, (cmax + cmin) / wbb * .5f, t) * u;
+        wgt += u;
+      }
+    }
+  float4 o;
+  if(wgt == 0.0f) { o.x = o.y = o.z = 1.0f; }
+  else { o.x = cr / wgt; o.y = cg / wgt; o.z = cb / wgt; }
+  o.w = sqrtf(ex * ex + ey * ey);
+  st_rgba(out, ow, x, y, o);
+}
+
+// ---- assemble: expand coarse, rescale to the fine level's unclipped channels, blend (assemble.comp:23-118) ----
+__global__ void __launch_bounds__(256) k_hilite_assemble(const uint2 *__restrict__ fine_img, const uint2 *__restrict__ coarse,
+    int cw, int ch, uint2 *__restrict__ out, int ow, int oh, hilite_params_t p)
+{
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if(x >= ow || y >= oh) return;
+  const float w[5] = {1.0f / 16.0f, 4.0f / 16.0f, 6.0f / 16.0f, 4.0f / 16.0f, 1.0f / 16.0f};
+  const int ix = x / 2, iy = y / 2, dx = x & 1, dy = y & 1;
+  float ur = 0.0f, ug = 0.0f, ub = 0.0f, wgt = 0.0f;
+  for(int ii = dx ? 0 : -1; ii <= 1; ii++) for(int jj = dy ? 0 : -1; jj <= 1; jj++)
+  {
+    const float4 rgb = ld_rgba_mirror(coarse, cw, ch, ix + ii, iy + jj);
+    const float wy = dy ? w[2 * jj + 1] : w[2 * jj + 2];
+    const float wx = dx ? w[2 * ii + 1] : w[2 * ii + 2];
+    ur += rgb.x * wy * wx; ug += rgb.y * wy * wx; ub += rgb.z * wy * wx;
+    wgt += wy * wx;
+  }
+  if(wgt == 0.0f) { ur = 0.0f; ug = 1.0f; ub = 1.0f; }
+  else { ur /= wgt; ug /= wgt; ub /= wgt; }
+  float4 fine = ld_rgba(fine_img, ow, x, y);
+  const float white = p.white;
+  const float sr = fine.x / fmaxf(0.001f, ur);
+  const float sg = fine.y / fmaxf(0.001f, ug);
+  const float sb = fine.z / fmaxf(0.001f, ub);
+  const float wr = expf(ur - fmaxf(ug, ub));
+  const float wg = expf(ug - fmaxf(ur, ub));
+  const float wb = expf(ub - fmaxf(ur, ug));
+  const float scale = (sr * wr + sg * wg + sb * wb) / (wr + wg + wb);
+  float t = p.soft;
+  if(fine.x >= white || fine.y >= white || fine.z >= white) t = 1.0f;
+  if(isnan(fine.w)) fine.w = 0.0f;
+  t = clampf(mixf(t, 1.0f, sqrtf(fmaxf(0.0f, fine.w))), 0.0f, 1.0f);
+  float4 o;
+  o.x = mixf(fine.x, clampf(ur * scale, -65535.0f, 65535.0f), t);
+  o.y = mixf(fine.y, clampf(ug * scale, -65535.0f, 65535.0f), t);
+  o.z = mixf(fine.z, clampf(ub * scale, -65535.0f, 65535.0f), t);
+  o.w = 1.0f;
+  st_rgba(out, ow, x, y, o);
+}
+
+// ---- doub: write reconstructed values back into the mosaic where it clips (doub.comp:22-121) ----
+__global__ void __launch_bounds__(256) k_hilite_doub(const __half *__restrict__ in, int iw, int ih,
+    const uint2 *__restrict__ coarse, int cw, int ch, __half *__restrict__ out, int ow, int oh, float white, int xtrans)
+{
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  const int bw = xtrans ? ow / 3 : ow / 2, bh = xtrans ? oh / 3 : oh / 2;
+  if(x >= bw || y >= bh) return;
+  float4 upsm = ld_rgba_clamp(coarse, cw, ch, x, y);
+  const float softw = 0.97f * white;
+  if(xtrans)
+  {
+    if(((x + y) & 1) == 0) { const float t = upsm.x; upsm.x = upsm.z; upsm.z = t; }
+    float c[9];
+#pragma unroll
+    for(int i = 0; i < 3; i++)
+#pragma unroll
+      for(int j = 0; j < 3; j++) c[3 * i + j] = ld_h_clamp(in, iw, ih, 3 * x + i, 3 * y + j);
+    const float minr = fminf(c[1], c[7]), minb = fminf(c[3], c[5]);
+    const float ming = fminf(fminf(fminf(c[0], c[2]), c[4]), fminf(c[6], c[8]));
+    const float sr = minr / fmaxf(0.001f, upsm.x);
+    const float sg = ming / fmaxf(0.001f, upsm.y);
+    const float sb = minb / fmaxf(0.001f, upsm.z);
+    const float wr = expf(upsm.x - fmaxf(upsm.y, upsm.z));
+    const float wg = expf(upsm.y - fmaxf(upsm.x, upsm.z));
+    const float wb = expf(upsm.z - fmaxf(upsm.x, upsm.y));
+    const float scale = (sr * wr + sg * wg + sb * wb) / (wr + wg + wb);
+    const float maxr = fmaxf(c[1], c[7]), maxb = fmaxf(c[3], c[5]);
+    const float maxg = fmaxf(fmaxf(fmaxf(c[0], c[2]), c[4]), fmaxf(c[6], c[8]));
+    const float maxrgb = fmaxf(maxr, fmaxf(maxg, maxb));
+    if(maxrgb > softw)
+    {
+      float t = smoothstepf(softw, white, maxrgb);
+      c[1] = mixf(c[1], upsm.x * scale, t); c[7] = mixf(c[7], upsm.x * scale, t);
+      c[3] = mixf(c[3], upsm.z * scale, t); c[5] = mixf(c[5], upsm.z * scale, t);
+      t = smoothstepf(softw, white, ming);
+      c[0] = mixf(c[0], upsm.y * scale, t); c[2] = mixf(c[2], upsm.y * scale, t);
+      c[4] = mixf(c[4], upsm.y * scale, t); c[6] = mixf(c[6], upsm.y * scale, t);
+      c[8] = mixf(c[8], upsm.y * scale, t);
+    }
+#pragma unroll
+    for(int i = 0; i < 3; i++)
+#pragma unroll
+      for(int j = 0; j < 3; j++)
+        if(3 * x + i < ow && 3 * y + j < oh) out[(size_t)(3 * y + j) * ow + 3 * x + i] = __float2half_rn(c[3 * i + j]);
+  }
+  else
+  {
+    const int x0 = mirror1(2 * x, iw), x1 = mirror1(2 * x + 1, iw), y0 = mirror1(2 * y, ih), y1 = mirror1(2 * y + 1, ih);
+    float c[4] = { ld_h(in, iw, x0, y1), ld_h(in, iw, x1, y1), ld_h(in, iw, x1, y0), ld_h(in, iw, x0, y0) };
+    const float ming = fminf(c[0], c[2]);
+    const float sr = c[3] / fmaxf(0.001f, upsm.x);
+    const float sg = ming / fmaxf(0.001f, upsm.y);
+    const float sb = c[1] / fmaxf(0.001f, upsm.z);
+    const float wr = expf(upsm.x - fmaxf(upsm.y, upsm.z));
+    const float wg = expf(upsm.y - fmaxf(upsm.x, upsm.z));
+    const float wb = expf(upsm.z - fmaxf(upsm.x, upsm.y));
+    const float scale = (sr * wr + sg * wg + sb * wb) / (wr + wg + wb);
+    const float maxrgb = fmaxf(fmaxf(c[0], c[1]), fmaxf(c[2], c[3]));
+    if(maxrgb > softw)
+    {
+      const float t = smoothstepf(softw, white, maxrgb);
+      c[0] = mixf(c[0], scale * upsm.y, t); c[1] = mixf(c[1], scale * upsm.z, t);
+      c[2] = mixf(c[2], scale * upsm.y, t); c[3] = mixf(c[3], scale * upsm.x, t);
+    }
+    // two texels per row -> one 4 byte store each
+    const __half2 top = __floats2half2_rn(c[3], c[2]), bot = __floats2half2_rn(c[0], c[1]);
+    if((ow & 1) == 0)
+    {
+      *reinterpret_cast<__half2 *>(out + (size_t)(2 * y) * ow + 2 * x) = top;
+      *reinterpret_cast<__half2 *>(out + (size_t)(2 * y + 1) * ow + 2 * x) = bot;
+    }
+    else
+    {
+      out[(size_t)(2 * y) * ow + 2 * x] = __low2half(top);     out[(size_t)(2 * y) * ow + 2 * x + 1] = __high2half(top);
+      out[(size_t)(2 * y + 1) * ow + 2 * x] = __low2half(bot); out[(size_t)(2 * y + 1) * ow + 2 * x + 1] = __high2half(bot);
+    }
+  }
+}
+
+static inline dim3 grid2d(unsigned w, unsigned h) { return dim3(vkb_cdiv(w, 32), vkb_cdiv(h, 8)); }
+static const dim3 blk2d(32, 8);
+
+// conn: [0] input mosaic f16 1ch, [1] output rgba f16
+static int launch_hilite_half(const vkb_launch_t *l)
+{
+  VKB_REQUIRE(l->num_conn >= 2 && l->push_size >= sizeof(hilite_push_t) && l->params_size >= 4);
+  const hilite_push_t *pc = (const hilite_push_t *)l->push;
+  const vkb_image_t *in = l->conn, *out = l->conn + 1;
+  VKB_REQUIRE(in->format == VKB_TOKEN_F16 && in->chan == 1 && out->format == VKB_TOKEN_F16 && out->chan == 4);
+  k_hilite_half<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const __half *)in->data, in->wd, in->ht,
+      (uint2 *)out->data, out->wd, out->ht, ((const float *)l->params)[0], pc->filters == 9);
+  VKB_CHECK_LAUNCH();
+  return VKB_OK;
+}
+VKB_REGISTER("hilite", "half", launch_hilite_half);
+
+// conn: [0] input rgba f16, [1] output rgba f16
+static int launch_hilite_reduce(const vkb_launch_t *l)
+{
+  VKB_REQUIRE(l->num_conn >= 2 && l->push_size >= sizeof(hilite_push_t) && l->params_size >= sizeof(hilite_params_t));
+  const hilite_push_t *pc = (const hilite_push_t *)l->push;
+  const vkb_image_t *in = l->conn, *out = l->conn + 1;
+  VKB_REQUIRE(in->chan == 4 && out->chan == 4 && in->format == VKB_TOKEN_F16 && out->format == VKB_TOKEN_F16);
+  float wb[3] = { pc->wb[0], pc->wb[1], pc->wb[2] };
+  if(!(wb[0] * wb[0] + wb[1] * wb[1] + wb[2] * wb[2] > 1e-3f)) wb[0] = wb[1] = wb[2] = 1.0f;
+  k_hilite_reduce<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht,
+      (uint2 *)out->data, out->wd, out->ht, *(const hilite_params_t *)l->params, wb[0], wb[1], wb[2]);
+  VKB_CHECK_LAUNCH();
+  return VKB_OK;
+}
+VKB_REGISTER("hilite", "reduce", launch_hilite_reduce);
+
+// conn: [0] fine rgba f16, [1] coarse rgba f16, [2] output rgba f16 (fine dims)
+static int launch_hilite_assemble(const vkb_launch_t *l)
+{
+  VKB_REQUIRE(l->num_conn >= 3 && l->params_size >= sizeof(hilite_params_t));
+  const vkb_image_t *fine = l->conn, *coarse = l->conn + 1, *out = l->conn + 2;
+  VKB_REQUIRE(fine->chan == 4 && coarse->chan == 4 && out->chan == 4 && fine->wd == out->wd && fine->ht == out->ht);
+  k_hilite_assemble<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint2 *)fine->data, (const uint2 *)coarse->data,
+      coarse->wd, coarse->ht, (uint2 *)out->data, out->wd, out->ht, *(const hilite_params_t *)l->params);
+  VKB_CHECK_LAUNCH();
+  return VKB_OK;
+}
+VKB_REGISTER("hilite", "assemble", launch_hilite_assemble);
+
+// conn: [0] input mosaic f16, [1] coarse rgba f16, [2] output mosaic f16
+static int launch_hilite_doub(const vkb_launch_t *l)
+{
+  VKB_REQUIRE(l->num_conn >= 3 && l->push_size >= sizeof(hilite_push_t) && l->params_size >= 4);
+  const hilite_push_t *pc = (const hilite_push_t *)l->push;
+  const vkb_image_t *in = l->conn, *coarse = l->conn + 1, *out = l->conn + 2;
+  VKB_REQUIRE(in->chan == 1 && coarse->chan == 4 && out->chan == 1 && out->format == VKB_TOKEN_F16);
+  const int xt = pc->filters == 9;
+  k_hilite_doub<<<grid2d(out->wd / (xt ? 3 : 2), out->ht / (xt ? 3 : 2)), blk2d, 0, l->stream>>>((const __half *)in->data, in->wd, in->ht,
+      (const uint2 *)coarse->data, coarse->wd, coarse->ht, (__half *)out->data, out->wd, out->ht, ((const float *)l->params)[0], xt);
+  VKB_CHECK_LAUNCH();
+  return VKB_OK;
+}
+VKB_REGISTER("hilite", "doub", launch_hilite_doub);

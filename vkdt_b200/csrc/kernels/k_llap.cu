@@ -1,0 +1,267 @@
+// local laplacian pyramids, restructured for HBM: the 11 x full-res level-0 stack of the reference
+// (llap/curve.comp writes 22 B/px, reduce and assemble re-read it) is never materialised.
+//  - (b200, llapr0)  curve + first reduce fused: rgba in -> 11 planes of level 1 (tile staged in shared memory)
+//  - (llap, reduce)  11-layer [1 2 1]^2/16 reduce of the coarse levels (reduce.comp:16-35, sample_semisoft)
+//  - (llap, assemble) coarse-level collapse (assemble.comp:52-88, sample_soft)
+//  - (b200, llapfin) finest assemble + llap/colour.comp (+ grade) fused: level-0 laplacians are recomputed
+//    from the input pixel (curve() rounded to f16 in registers = the value the reference would have stored)
+// wiring: llap/main.c:31-105.  gamma/curve: llap/llap.glsl:3-22, llap/curve.comp:40-63.
+#include "pointwise.cuh"
+#include <string.h>
+
+#define NUM_GAMMA 10
+#define NL (NUM_GAMMA + 1)
+
+struct llap_params_t { float sigma, shadows, hilights, clarity; };
+
+VKB_DEV float gamma_from_i(int i) { return (float)i / (NUM_GAMMA - 1.0f); }
+VKB_DEV int gamma_hi_from_v(float v)
+{
+  int hi = 1;
+  for(; hi < NUM_GAMMA - 1 && gamma_from_i(hi) <= v; hi++);
+  return hi;
+}
+VKB_DEV float llap_curve(float x, float g, const llap_params_t &p)
+{
+  const float c = x - g;
+  float val;
+  const float ssigma = c > 0.0f ? p.sigma : -p.sigma;
+  const float shadhi = c > 0.0f ? p.shadows : p.hilights;
+  if(fabsf(c) > 2 * p.sigma) val = g + ssigma + shadhi * (c - ssigma);
+  else
+  {
+    const float t = clampf(c / (2.0f * ssigma), 0.0f, 1.0f);
+    const float t2 = t * t;
+    const float mt = 1.0f - t;
+    val = g + ssigma * 2.0f * mt * t + t2 * (ssigma + ssigma * shadhi);
+  }
+  val += p.clarity * c * expf(-c * c / (2.0f * p.sigma * p.sigma / 3.0f));
+  return val;
+}
+VKB_DEV float llap_grey(float4 px)
+{ // curve.comp:72: clamp away nans and infs
+  return lum2020(clampf(px.x, -1000.0f, 1000.0f), clampf(px.y, -1000.0f, 1000.0f), clampf(px.z, -1000.0f, 1000.0f));
+}
+
+// ---- curve + reduce to level 1 ----
+// block = 32x8 outputs, input tile (2*32+1) x (2*8+1) texels around them, 11 f16 values per texel in smem.
+#define R0_TW 65
+#define R0_TH 17
+__global__ void __launch_bounds__(256) k_llap_reduce0(const uint2 *__restrict__ in, int iw, int ih,
+    __half *__restrict__ out, int ow, int oh, llap_params_t p)
+{
+  __shared__ __half tile[NL][R0_TH][R0_TW + 1];
+  const int tx0 = blockIdx.x * 64 - 1, ty0 = blockIdx.y * 16 - 1;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  for(int t = tid; t < R0_TW * R0_TH; t += 256)
+  {
+    const int lx = t % R0_TW, ly = t / R0_TW;
+    const int gx = mirrori(tx0 + lx, iw), gy = mirrori(ty0 + ly, ih);
+    const float y = llap_grey(ld_rgba(in, iw, gx, gy));
+#pragma unroll
+    for(int g = 0; g < NUM_GAMMA; g++) tile[g][ly][lx] = __float2half_rn(llap_curve(y, gamma_from_i(g), p));
+    tile[NUM_GAMMA][ly][lx] = __float2half_rn(y);
+  }
+  __syncthreads();
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if(x >= ow || y >= oh) return;
+  const int lx = 2 * threadIdx.x, ly = 2 * threadIdx.y; // tile coords of texel (2x-1, 2y-1)
+  const size_t plane = (size_t)ow * oh;
+#pragma unroll
+  for(int g = 0; g < NL; g++)
+  {
+    float t[3][3];
+#pragma unroll
+    for(int j = 0; j < 3; j++)
+#pragma unroll
+      for(int i = 0; i < 3; i++) t[j][i] = __half2float(tile[g][ly + j][lx + i]);
+    // sample_semisoft: four bilinear taps with weights 1/2, summed, / 4
+    const float b00 = (t[0][0] * 0.5f + t[0][1] * 0.5f) * 0.5f + (t[1][0] * 0.5f + t[1][1] * 0.5f) * 0.5f;
+    const float b10 = (t[0][1] * 0.5f + t[0][2] * 0.5f) * 0.5f + (t[1][1] * 0.5f + t[1][2] * 0.5f) * 0.5f;
+    const float b01 = (t[1][0] * 0.5f + t[1][1] * 0.5f) * 0.5f + (t[2][0] * 0.5f + t[2][1] * 0.5f) * 0.5f;
+    const float b11 = (t[1][1] * 0.5f + t[1][2] * 0.5f) * 0.5f + (t[2][1] * 0.5f + t[2][2] * 0.5f) * 0.5f;
+    out[g * plane + (size_t)y * ow + x] = __float2half_rn((((b00 + b10) + b01) + b11) / 4.0f);
+  }
+}
+
+// ---- reduce of coarse levels: blockIdx.z = layer ----
+__global__ void __launch_bounds__(256) k_llap_reduce(const __half *__restrict__ in, int iw, int ih,
+    __half *__restrict__ out, int ow, int oh)
+{
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, g = blockIdx.z;
+  if(x >= ow || y >= oh) return;
+  const __half *src = in + (size_t)g * iw * ih;
+  float t[3][3];
+#pragma unroll
+  for(int j = 0; j < 3; j++)
+#pragma unroll
+    for(int i = 0; i < 3; i++) t[j][i] = ld_h_mirror(src, iw, ih, 2 * x - 1 + i, 2 * y - 1 + j);
+  const float b00 = (t[0][0] * 0.5f + t[0][1] * 0.5f) * 0.5f + (t[1][0] * 0.5f + t[1][1] * 0.5f) * 0.5f;
+  const float b10 = (t[0][1] * 0.5f + t[0][2] * 0.5f) * 0.5f + (t[1][1] * 0.5f + t[1][2] * 0.5f) * 0.5f;
+  const float b01 = (t[1][0] * 0.5f + t[1][1] * 0.5f) * 0.5f + (t[2][0] * 0.5f + t[2][1] * 0.5f) * 0.5f;
+  const float b11 = (t[1][1] * 0.5f + t[1][2] * 0.5f) * 0.5f + (t[2][1] * 0.5f + t[2][2] * 0.5f) * 0.5f;
+  out[(size_t)g * ow * oh + (size_t)y * ow + x] = __float2half_rn((((b00 + b10) + b01) + b11) / 4.0f);
+}
+
+// sample_soft(img, (opos*0.5+0.5)/size): 3x3 bilinear taps at -1.5, 0, +1.5 texels, / 9 (shared.glsl:99-127).
+// per axis the taps land on: even o=2k: {k-2|k-1 (1/2), k, k+1|k+2 (1/2)}, odd o=2k+1: {k-1, k|k+1 (1/2), k+2}
+struct soft_axis_t { int i0[3]; float a[3]; };
+VKB_DEV soft_axis_t soft_axis(int o)
+{
+  soft_axis_t s;
+  const int k = o >> 1;
+  if(o & 1) { s.i0[0] = k - 1; s.a[0] = 0.0f; s.i0[1] = k; s.a[1] = 0.5f; s.i0[2] = k + 2; s.a[2] = 0.0f; }
+  else      { s.i0[0] = k - 2; s.a[0] = 0.5f; s.i0[1] = k; s.a[1] = 0.0f; s.i0[2] = k + 1; s.a[2] = 0.5f; }
+  return s;
+}
+VKB_DEV float gauss_expand(const __half *__restrict__ img, int w, int h, const soft_axis_t &sx, const soft_axis_t &sy)
+{
+  float r = 0.0f;
+#pragma unroll
+  for(int j = 0; j < 3; j++)
+  {
+    const int y0 = mirrori(sy.i0[j], h), y1 = mirrori(sy.i0[j] + 1, h);
+    const float ay = sy.a[j];
+#pragma unroll
+    for(int i = 0; i < 3; i++)
+    {
+      const int x0 = mirrori(sx.i0[i], w), x1 = mirrori(sx.i0[i] + 1, w);
+      const float ax = sx.a[i];
+      float top = ld_h(img, w, x0, y0) * (1.0f - ax);
+      if(ax != 0.0f) top += ld_h(img, w, x1, y0) * ax;
+      float v = top * (1.0f - ay);
+      if(ay != 0.0f)
+      {
+        float bot = ld_h(img, w, x0, y1) * (1.0f - ax);
+        if(ax != 0.0f) bot += ld_h(img, w, x1, y1) * ax;
+        v += bot * ay;
+      }
+      r += v;
+    }
+  }
+  return r / 9.0f;
+}
+
+// ---- assemble for coarse levels (both l0 and l1 stacks are in memory) ----
+__global__ void __launch_bounds__(256) k_llap_assemble(const __half *__restrict__ coarse, const __half *__restrict__ l0,
+    const __half *__restrict__ l1, int cw, int ch, __half *__restrict__ out, int ow, int oh, int first)
+{
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if(x >= ow || y >= oh) return;
+  const size_t p0 = (size_t)ow * oh, p1 = (size_t)cw * ch;
+  const soft_axis_t sx = soft_axis(x), sy = soft_axis(y);
+  const float res = first ? gauss_expand(l1 + NUM_GAMMA * p1, cw, ch, sx, sy) : gauss_expand(coarse, cw, ch, sx, sy);
+  const float v = ld_h(l0 + NUM_GAMMA * p0, ow, x, y);
+  const int hi = gamma_hi_from_v(v), lo = hi - 1;
+  const float glo = gamma_from_i(lo), ghi = gamma_from_i(hi);
+  const float a = clampf((v - glo) / (ghi - glo), 0.0f, 1.0f);
+  const float lap0 = ld_h(l0 + lo * p0, ow, x, y) - gauss_expand(l1 + lo * p1, cw, ch, sx, sy);
+  const float lap1 = ld_h(l0 + hi * p0, ow, x, y) - gauss_expand(l1 + hi * p1, cw, ch, sx, sy);
+  out[(size_t)y * ow + x] = __float2half_rn(res + lap0 * (1.0f - a) + lap1 * a);
+}
+
+// ---- finest assemble + recolouring (+ grade) ----
+struct llapfin_t { llap_params_t p; int first; int have_grade; int out_f32; grade_params_t grade; };
+
+__global__ void __launch_bounds__(256) k_llap_final(const uint2 *__restrict__ in, const __half *__restrict__ coarse,
+    const __half *__restrict__ l1, int cw, int ch, void *__restrict__ outv, int ow, int oh, const __grid_constant__ llapfin_t P)
+{
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if(x >= ow || y >= oh) return;
+  const size_t p1 = (size_t)cw * ch;
+  const float4 px = ld_rgba(in, ow, x, y);
+  const float grey = llap_grey(px);
+  const soft_axis_t sx = soft_axis(x), sy = soft_axis(y);
+  const float res = P.first ? gauss_expand(l1 + NUM_GAMMA * p1, cw, ch, sx, sy) : gauss_expand(coarse, cw, ch, sx, sy);
+  const float v = f16r(grey);
+  const int hi = gamma_hi_from_v(v), lo = hi - 1;
+  const float glo = gamma_from_i(lo), ghi = gamma_from_i(hi);
+  const float a = clampf((v - glo) / (ghi - glo), 0.0f, 1.0f);
+  const float lap0 = f16r(llap_curve(grey, glo, P.p)) - gauss_expand(l1 + lo * p1, cw, ch, sx, sy);
+  const float lap1 = f16r(llap_curve(grey, ghi, P.p)) - gauss_expand(l1 + hi * p1, cw, ch, sx, sy);
+  float l = f16r(res + lap0 * (1.0f - a) + lap1 * a);
+  // llap/colour.comp:17-37
+  const float yo = fmaxf(lum2020(px.x, px.y, px.z), 1e-8f);
+  if(l < yo) l = yo * expf(1.0f * (l - yo));
+  f3 c = { fmaxf(0.0f, px.x * l / yo), fmaxf(0.0f, px.y * l / yo), fmaxf(0.0f, px.z * l / yo) };
+  if(P.have_grade)
+  {
+    c = { f16r(c.x), f16r(c.y), f16r(c.z) };
+    c = grade_px(c, P.grade);
+  }
+  if(P.out_f32) reinterpret_cast<float4 *>(outv)[(size_t)y * ow + x] = make_float4(c.x, c.y, c.z, 1.0f);
+  else st_rgba(reinterpret_cast<uint2 *>(outv), ow, x, y, make_float4(c.x, c.y, c.z, 1.0f));
+}
+
+static inline dim3 grid2d(unsigned w, unsigned h, unsigned z = 1) { return dim3(vkb_cdiv(w, 32), vkb_cdiv(h, 8), z); }
+static const dim3 blk2d(32, 8);
+
+// conn: [0] input rgba f16 (level 0), [1] output y f16 x 11 layers (level 1).  params: llap params
+static int launch_llapr0(const vkb_launch_t *l)
+{
+  VKB_REQUIRE(l->num_conn >= 2 && l->params_size >= sizeof(llap_params_t));
+  const vkb_image_t *in = l->conn, *out = l->conn + 1;
+  VKB_REQUIRE(in->chan == 4 && in->format == VKB_TOKEN_F16 && out->chan == 1 && out->layers == NL && out->format == VKB_TOKEN_F16);
+  VKB_REQUIRE(out->wd == (in->wd - 1) / 2 + 1 && out->ht == (in->ht - 1) / 2 + 1);
+  k_llap_reduce0<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht,
+      (__half *)out->data, out->wd, out->ht, *(const llap_params_t *)l->params);
+  VKB_CHECK_LAUNCH();
+  return VKB_OK;
+}
+VKB_REGISTER("b200", "llapr0", launch_llapr0);
+
+// conn: [0] inhi y f16 x 11, [1] outlo y f16 x 11
+static int launch_llap_reduce(const vkb_launch_t *l)
+{
+  VKB_REQUIRE(l->num_conn >= 2);
+  const vkb_image_t *in = l->conn, *out = l->conn + 1;
+  VKB_REQUIRE(in->chan == 1 && out->chan == 1 && in->layers == out->layers && in->format == VKB_TOKEN_F16 && out->format == VKB_TOKEN_F16);
+  k_llap_reduce<<<grid2d(out->wd, out->ht, out->layers), blk2d, 0, l->stream>>>((const __half *)in->data, in->wd, in->ht,
+      (__half *)out->data, out->wd, out->ht);
+  VKB_CHECK_LAUNCH();
+  return VKB_OK;
+}
+VKB_REGISTER("llap", "reduce", launch_llap_reduce);
+
+// conn: [0] coarse y f16 (ignored when push.first), [1] currlo x11 (fine), [2] currhi x11 (coarse), [3] fine out y f16
+// push: { u32 num_gamma; u32 first } (llap/main.c:66,92)
+static int launch_llap_assemble(const vkb_launch_t *l)
+{
+  VKB_REQUIRE(l->num_conn >= 4 && l->push_size >= 8);
+  const uint32_t *pc = (const uint32_t *)l->push;
+  const vkb_image_t *coarse = l->conn, *l0 = l->conn + 1, *l1 = l->conn + 2, *out = l->conn + 3;
+  VKB_REQUIRE(pc[0] == NUM_GAMMA && l0->layers == NL && l1->layers == NL && out->chan == 1);
+  VKB_REQUIRE(l0->wd == out->wd && l0->ht == out->ht);
+  VKB_REQUIRE(pc[1] || (coarse->wd == l1->wd && coarse->ht == l1->ht));
+  k_llap_assemble<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const __half *)coarse->data, (const __half *)l0->data,
+      (const __half *)l1->data, l1->wd, l1->ht, (__half *)out->data, out->wd, out->ht, (int)pc[1]);
+  VKB_CHECK_LAUNCH();
+  return VKB_OK;
+}
+VKB_REGISTER("llap", "assemble", launch_llap_assemble);
+
+// conn: [0] input rgba f16, [1] coarse y f16 (level 1 assembled; ignored when first), [2] level-1 stack x11, [3] output rgba f16|f32
+// push: { u32 first; u32 have_grade }.  params: llap params (16 B) followed by grade params (76 B) when have_grade
+static int launch_llapfin(const vkb_launch_t *l)
+{
+  VKB_REQUIRE(l->num_conn >= 4 && l->push_size >= 8 && l->params_size >= sizeof(llap_params_t));
+  const uint32_t *pc = (const uint32_t *)l->push;
+  const vkb_image_t *in = l->conn, *coarse = l->conn + 1, *l1 = l->conn + 2, *out = l->conn + 3;
+  VKB_REQUIRE(in->chan == 4 && in->format == VKB_TOKEN_F16 && l1->layers == NL && out->chan == 4);
+  VKB_REQUIRE(in->wd == out->wd && in->ht == out->ht);
+  VKB_REQUIRE(out->format == VKB_TOKEN_F16 || out->format == VKB_TOKEN_F32);
+  llapfin_t P;
+  memset(&P, 0, sizeof(P));
+  memcpy(&P.p, l->params, sizeof(llap_params_t));
+  P.first = pc[0]; P.have_grade = pc[1]; P.out_f32 = out->format == VKB_TOKEN_F32;
+  if(P.have_grade)
+  {
+    VKB_REQUIRE(l->params_size >= sizeof(llap_params_t) + sizeof(grade_params_t));
+    memcpy(&P.grade, (const uint8_t *)l->params + sizeof(llap_params_t), sizeof(grade_params_t));
+  }
+  k_llap_final<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint2 *)in->data, (const __half *)coarse->data,
+      (const __half *)l1->data, l1->wd, l1->ht, out->data, out->wd, out->ht, P);
+  VKB_CHECK_LAUNCH();
+  return VKB_OK;
+}
+VKB_REGISTER("b200", "llapfin", launch_llapfin);

@@ -1,0 +1,208 @@
+// fused pointwise chain: any sequence of crop -> colour -> filmcurv -> grade runs as ONE kernel,
+// one 8-byte read and one 8/16-byte write per pixel, f16 rounding applied in registers at exactly the
+// edges where the reference stores an f16 image (so results match the unfused graph).
+//  - (crop, main) (colour, main) (filmcurv, main) (grade, main): single-op chains, drop-in per node
+//  - (b200, pointw): the fused chain.  push: { u32 n_ops; u32 op[7] }, params: the ops' parameter blobs
+//    back to back (crop: 20 floats committed, colour: 242 floats committed, filmcurv: 10 x 4 B, grade: 19 x 4 B)
+// replaces crop/main.comp, colour/main.comp, filmcurv/main.comp, grade/main.comp and the three HBM
+// round trips between them.
+#include "pointwise.cuh"
+#include <string.h>
+#include <math.h>
+
+enum { PW_CROP = 1, PW_COLOUR = 2, PW_FILMCURV = 3, PW_GRADE = 4 };
+
+struct pw_chain_t
+{
+  int n_ops;
+  int op[8];
+  int out_f32;
+  crop_committed_t crop;
+  filmcurv_params_t film;
+  grade_params_t grade;
+  colour_digest_t colour;
+};
+
+VKB_DEV f3 round3(f3 c) { return { f16r(c.x), f16r(c.y), f16r(c.z) }; }
+
+__global__ void __launch_bounds__(256) k_pointwise(const uint2 *__restrict__ in, int iw, int ih,
+    void *__restrict__ outv, int ow, int oh, const __grid_constant__ pw_chain_t P)
+{
+  const int y = blockIdx.y * 8 + threadIdx.y;
+  if(y >= oh) return;
+#pragma unroll
+  for(int rep = 0; rep < 2; rep++)
+  {
+    const int x = blockIdx.x * 64 + rep * 32 + threadIdx.x;
+    if(x >= ow) continue;
+    float4 px;
+    int first = 0;
+    if(P.op[0] == PW_CROP) { px = crop_fetch(in, iw, ih, x, y, P.crop); first = 1; }
+    else px = ld_rgba(in, iw, min(x, iw - 1), min(y, ih - 1));
+    f3 c = { px.x, px.y, px.z };
+    // every edge between two modules is an f16 image in the reference: round in registers where it would store
+    if(first && P.n_ops > 1) c = round3(c);
+    for(int o = first; o < P.n_ops; o++)
+    {
+      if(P.op[o] == PW_COLOUR)        c = colour_px(c, P.colour);
+      else if(P.op[o] == PW_FILMCURV) c = filmcurv_px(c, P.film);
+      else if(P.op[o] == PW_GRADE)    c = grade_px(c, P.grade);
+      if(o < P.n_ops - 1) c = round3(c);
+    }
+    if(P.out_f32) reinterpret_cast<float4 *>(outv)[(size_t)y * ow + x] = make_float4(c.x, c.y, c.z, 1.0f);
+    else st_rgba(reinterpret_cast<uint2 *>(outv), ow, x, y, make_float4(c.x, c.y, c.z, 1.0f));
+  }
+}
+
+// ---- host: digest of colour's committed block (layout colour/main.c:260-364) ----
+static void mat3mul_d(const double *A, const double *B, double *C)
+{
+  for(int j = 0; j < 3; j++) for(int i = 0; i < 3; i++)
+    C[3 * j + i] = A[3 * j + 0] * B[i] + A[3 * j + 1] * B[3 + i] + A[3 * j + 2] * B[6 + i];
+}
+static const double M_cat16_Mi[9] = {1.86206786, -1.01125463, 0.14918677, 0.38752654, 0.62144744, -0.00897398, -0.01584150, -0.03412294, 1.04996444};
+static const double M_cat16_M[9]  = {0.401288, 0.650173, -0.051461, -0.250268, 1.204414, 0.045854, -0.002079, 0.048952, 0.953127};
+static const double M_2020_to_xyz[9] = {0.636958048301290991, 0.144616903586208406, 0.168880975164172054, 0.26270021201126692, 0.677998071518871148, 0.0593017164698619384, 4.9999999999999999e-17, 0.0280726930490874452, 1.06098505771079066};
+static const double M_xyz_to_2020[9] = {1.71665119, -0.35567078, -0.25336628, -0.66668435, 1.61648124, 0.01576855, 0.01763986, -0.04277061, 0.94210312};
+static const double M_709_to_2020[9] = {0.62750375, 0.32927542, 0.04330266, 0.06910828, 0.91951916, 0.0113596, 0.01639406, 0.08801125, 0.89538035};
+static const double M_adobe_to_2020[9] = {0.87736306, 0.07751751, 0.04516292, 0.0966218, 0.89152263, 0.01186405, 0.02291617, 0.04301452, 0.93367996};
+static const double M_p3d65_to_2020[9] = {0.75386031, 0.19861268, 0.04757049, 0.04575344, 0.94178472, 0.01247032, -0.00121501, 0.01760596, 0.98321971};
+static const double M_ap0_to_2020[9] = {1.51286139, -0.2589874, -0.22978603, -0.07903646, 1.17706683, -0.10075565, 0.00209124, -0.03114411, 0.95350416};
+static const double M_ap1_to_2020[9] = {1.03866457, -1.14744180e-02, -2.72327263e-02, -4.33683734e-04, 1.00062477, 1.01851049e-04, -5.64306018e-03, -2.23568741e-02, 1.02483276};
+static const double M_redwg_to_2020[9] = {1.180431, -0.094040, -0.086391, -0.028017, 1.311442, -0.283425, -0.074360, -0.362078, 1.436437};
+static const double M_ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+
+static double host_decode_trc(double v, uint32_t trc)
+{
+  switch(trc)
+  {
+    case 1: { const double a = 1.09929682680944, b = 0.018053968510807; return v > b * 4.5 ? pow((v + (a - 1)) / a, 2.2) : v / 4.5; }
+    case 2: return v > 0.04045 ? pow((v + 0.055) / 1.055, 2.4) : v / 12.92;
+    case 3: { const double m1 = 1305.0 / 8192.0, m2 = 2523.0 / 32.0, c1 = 107.0 / 128.0, c2 = 2413.0 / 128.0, c3 = 2392.0 / 128.0;
+              const double xp = pow(fmax(0.0, v), 1.0 / m2); return pow(fmax(xp - c1, 0.0) / fmax(c2 - c3 * xp, 1e-10), 1.0 / m1); }
+    case 4: return pow(v, 2.6);
+    case 5: { const double a = 0.17883277, b = 0.28466892, c = 0.55991073; return v <= 0.5 ? v * v / 3.0 : (exp((v - c) / a) + b) / 12.0; }
+    case 6: return pow(fmax(v, 0.0), 2.2);
+    default: return v;
+  }
+}
+
+static int colour_digest(const float *f, uint32_t size, colour_digest_t *d)
+{
+  if(size < 236 * 4) return vkb_set_error(VKB_ERR_BAD_ARG, "colour: committed params too small (%u bytes)", size);
+  const uint32_t *ii = (const uint32_t *)f;
+  const int off = 224;
+  memset(d, 0, sizeof(*d));
+  const uint32_t prim = ii[off + 5];
+  d->trc = ii[off + 6];
+  if(d->trc > 6) return vkb_set_error(VKB_ERR_BAD_ARG, "colour: trc %u (camera log curves) is outside the hot-path scope", d->trc);
+  double P[9];
+  switch(prim)
+  {
+    case 0: for(int j = 0; j < 3; j++) for(int i = 0; i < 3; i++) P[3 * j + i] = f[4 + 4 * i + j]; break; // column major upload
+    case 1: memcpy(P, M_709_to_2020, sizeof(P)); break;
+    case 2: memcpy(P, M_ident, sizeof(P)); break;
+    case 3: memcpy(P, M_adobe_to_2020, sizeof(P)); break;
+    case 4: memcpy(P, M_p3d65_to_2020, sizeof(P)); break;
+    case 5: memcpy(P, M_xyz_to_2020, sizeof(P)); break;
+    case 6: memcpy(P, M_ap0_to_2020, sizeof(P)); break;
+    case 7: memcpy(P, M_ap1_to_2020, sizeof(P)); break;
+    case 10: memcpy(P, M_redwg_to_2020, sizeof(P)); break;
+    default: return vkb_set_error(VKB_ERR_BAD_ARG, "colour: primaries %u (camera gamuts) are outside the hot-path scope", prim);
+  }
+  // cat16(rgb, src = 1, dst = mul.rgb): xyz_to_rec2020 * M16i * diag(cl_dst / cl_src) * M16 * rec2020_to_xyz (main-impl.glsl:49-67)
+  double MR[9], XM[9], D[9] = {0}, T0[9], T1[9], A[9];
+  mat3mul_d(M_cat16_M, M_2020_to_xyz, MR);
+  mat3mul_d(M_xyz_to_2020, M_cat16_Mi, XM);
+  for(int j = 0; j < 3; j++)
+  {
+    const double cs = MR[3 * j] + MR[3 * j + 1] + MR[3 * j + 2];
+    const double cd = MR[3 * j] * f[0] + MR[3 * j + 1] * f[1] + MR[3 * j + 2] * f[2];
+    D[4 * j] = cd / cs;
+  }
+  mat3mul_d(D, MR, T0);
+  mat3mul_d(XM, T0, T1);
+  mat3mul_d(T1, P, A);
+  for(int k = 0; k < 9; k++) d->A[k] = (float)A[k];
+  d->exposure = f[3];
+  const float clip = f[off + 7];
+  d->clip_t = 0.0f;
+  if(clip > 0.0f)
+  {
+    const double c = host_decode_trc(clip, d->trc);
+    double t = 1e30;
+    for(int j = 0; j < 3; j++) t = fmin(t, (A[3 * j] + A[3 * j + 1] + A[3 * j + 2]) * c);
+    d->clip_t = (float)t;
+    if(!(d->clip_t > 0.0f)) return vkb_set_error(VKB_ERR_BAD_ARG, "colour: non-positive highlight clip level");
+  }
+  d->N = ii[16] > 24 ? 24 : ii[16];
+  d->sat = f[off + 2];
+  for(int j = 0; j < 3; j++) for(int i = 0; i < 3; i++) d->rbf_P[3 * j + i] = f[20 + 4 * i + j];
+  memcpy(d->rbf_c, f + 32, sizeof(float) * 96);
+  memcpy(d->rbf_p, f + 128, sizeof(float) * 96);
+  return VKB_OK;
+}
+
+static int launch_chain(const vkb_launch_t *l, int n_ops, const uint32_t *ops)
+{
+  VKB_REQUIRE(l->num_conn >= 2 && n_ops >= 1 && n_ops <= 8);
+  const vkb_image_t *in = l->conn, *out = l->conn + 1;
+  VKB_REQUIRE(in->chan == 4 && in->format == VKB_TOKEN_F16 && out->chan == 4);
+  VKB_REQUIRE(out->format == VKB_TOKEN_F16 || out->format == VKB_TOKEN_F32);
+  pw_chain_t P;
+  memset(&P, 0, sizeof(P));
+  P.n_ops = n_ops;
+  P.out_f32 = out->format == VKB_TOKEN_F32;
+  const uint8_t *pp = (const uint8_t *)l->params;
+  uint32_t left = l->params_size;
+  for(int o = 0; o < n_ops; o++)
+  {
+    P.op[o] = ops[o];
+    uint32_t need = 0;
+    switch(ops[o])
+    {
+      case PW_CROP:
+        need = 20 * 4; VKB_REQUIRE(o == 0 && left >= need);
+        memcpy(&P.crop, pp, need); break;
+      case PW_COLOUR:
+      {
+        need = 242 * 4; if(left < need) need = left; // callers may pass the 236 floats the shader reads
+        const int r = colour_digest((const float *)pp, need, &P.colour);
+        if(r) return r;
+        break;
+      }
+      case PW_FILMCURV:
+        need = sizeof(filmcurv_params_t); VKB_REQUIRE(left >= need);
+        memcpy(&P.film, pp, need);
+        if(P.film.colour == 2) return vkb_set_error(VKB_ERR_BAD_ARG, "filmcurv: colour mode 2 (munsell lut) is outside the hot-path scope");
+        break;
+      case PW_GRADE:
+        need = sizeof(grade_params_t); VKB_REQUIRE(left >= need);
+        memcpy(&P.grade, pp, need); break;
+      default: return vkb_set_error(VKB_ERR_BAD_ARG, "pointwise chain: unknown op %u", ops[o]);
+    }
+    pp += need; left -= need;
+  }
+  if(P.op[0] != PW_CROP) VKB_REQUIRE(in->wd == out->wd && in->ht == out->ht);
+  dim3 block(32, 8), grid(vkb_cdiv(out->wd, 64), vkb_cdiv(out->ht, 8));
+  k_pointwise<<<grid, block, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, out->data, out->wd, out->ht, P);
+  VKB_CHECK_LAUNCH();
+  return VKB_OK;
+}
+
+static int launch_crop(const vkb_launch_t *l)     { const uint32_t op = PW_CROP;     return launch_chain(l, 1, &op); }
+static int launch_colour(const vkb_launch_t *l)   { const uint32_t op = PW_COLOUR;   return launch_chain(l, 1, &op); }
+static int launch_filmcurv(const vkb_launch_t *l) { const uint32_t op = PW_FILMCURV; return launch_chain(l, 1, &op); }
+static int launch_grade(const vkb_launch_t *l)    { const uint32_t op = PW_GRADE;    return launch_chain(l, 1, &op); }
+static int launch_pointw(const vkb_launch_t *l)
+{
+  VKB_REQUIRE(l->push_size >= 8);
+  const uint32_t *pc = (const uint32_t *)l->push;
+  VKB_REQUIRE(pc[0] >= 1 && pc[0] <= 7 && l->push_size >= 4 * (1 + pc[0]));
+  return launch_chain(l, pc[0], pc + 1);
+}
+VKB_REGISTER("crop", "main", launch_crop);
+VKB_REGISTER("colour", "main", launch_colour);
+VKB_REGISTER("filmcurv", "main", launch_filmcurv);
+VKB_REGISTER("grade", "main", launch_grade);
+VKB_REGISTER("b200", "pointw", launch_pointw);

@@ -1,0 +1,118 @@
+// graph layer of the C-ABI (include/vkdt_b200.h §3): thin extern "C" wrappers over the pipe model + executor.
+#include "pipe.h"
+#include "mlv.h"
+
+int vkb_plan_sink(dt_graph_t *g, int modid, uint32_t *wd, uint32_t *ht, void **dptr);
+uint64_t vkb_plan_pool_bytes(dt_graph_t *g);
+int dt_graph_plan(dt_graph_t *g, std::string *text);
+
+struct vkb_graph_t { dt_graph_t *g; };
+
+static int find_inst(dt_graph_t *g, const char *inst, bool source)
+{ // first module with that instance name whose connector 0 is a source / sink ("main" if inst is null)
+  const dt_token_t it = dt_token(inst && inst[0] ? inst : "main");
+  for(size_t m = 0; m < g->module.size(); m++)
+  {
+    const dt_module_t *mod = &g->module[m];
+    if(!mod->name || mod->inst != it || !mod->num_connectors) continue;
+    if(mod->connector[0].type == dt_token(source ? "source" : "sink") && mod->name != dt_token("display")) return (int)m;
+  }
+  return -1;
+}
+
+extern "C" {
+
+vkb_graph_t *vkb_graph_new(void)
+{
+  vkb_graph_t *h = new vkb_graph_t();
+  h->g = dt_graph_new();
+  return h;
+}
+void vkb_graph_free(vkb_graph_t *h)
+{
+  if(!h) return;
+  dt_graph_cleanup(h->g);
+  delete h;
+}
+int vkb_graph_read_config_ascii(vkb_graph_t *h, const char *filename)
+{
+  if(!h || !filename) return VKB_ERR_BAD_ARG;
+  return dt_graph_read_config_ascii(h->g, filename) ? vkb_set_error(VKB_ERR_IO, "could not read config '%s'", filename) : VKB_OK;
+}
+int vkb_graph_read_config_line(vkb_graph_t *h, const char *line)
+{ // 0 ok, > 0 warning (ignored by the reference's reader), < 0 fatal (graph-io.c:297-298)
+  if(!h || !line) return VKB_ERR_BAD_ARG;
+  std::string s(line);
+  return dt_graph_read_config_line(h->g, &s[0]);
+}
+int vkb_graph_replace_display(vkb_graph_t *h, const char *sink_module)
+{
+  if(!h) return VKB_ERR_BAD_ARG;
+  const int m = dt_graph_replace_display(h->g, dt_token("main"), dt_token(sink_module && sink_module[0] ? sink_module : "o-pfm"));
+  if(m < 0) return vkb_set_error(VKB_ERR_GRAPH, "replace display failed (%d)", m);
+  dt_graph_disconnect_display_modules(h->g);
+  return VKB_OK;
+}
+static int set_source(vkb_graph_t *h, const char *inst, const void *data, const vkb_raw_params_t *p, int on_device)
+{
+  if(!h || !data || !p) return VKB_ERR_BAD_ARG;
+  const int m = find_inst(h->g, inst, true);
+  if(m < 0) return vkb_set_error(VKB_ERR_BAD_ARG, "no source module with instance '%s'", inst ? inst : "main");
+  if(p->packed_bpp && h->g->module[m].name != dt_token("i-mlv")) return vkb_set_error(VKB_ERR_BAD_ARG, "packed payloads go through i-mlv");
+  vkb_mem_source_t *s = &h->g->mem_source[m];
+  s->data = data; s->on_device = on_device; s->p = *p; s->valid = 1;
+  return VKB_OK;
+}
+int vkb_graph_set_source(vkb_graph_t *h, const char *inst, const void *data, const vkb_raw_params_t *p) { return set_source(h, inst, data, p, 0); }
+int vkb_graph_set_source_device(vkb_graph_t *h, const char *inst, const void *d, const vkb_raw_params_t *p) { return set_source(h, inst, d, p, 1); }
+int vkb_graph_set_sink_buffer(vkb_graph_t *h, const char *inst, void *dst, size_t bytes)
+{ // dst == NULL: keep the result on the device (no download, no file)
+  if(!h) return VKB_ERR_BAD_ARG;
+  const int m = find_inst(h->g, inst, false);
+  if(m < 0) return vkb_set_error(VKB_ERR_BAD_ARG, "no sink module with instance '%s'", inst ? inst : "main");
+  h->g->mem_sink[m] = vkb_mem_sink_t{ dst, bytes, 1 };
+  return VKB_OK;
+}
+int vkb_graph_sink_size(vkb_graph_t *h, const char *inst, uint32_t *wd, uint32_t *ht)
+{
+  if(!h) return VKB_ERR_BAD_ARG;
+  const int m = find_inst(h->g, inst, false);
+  if(m < 0) return vkb_set_error(VKB_ERR_BAD_ARG, "no sink module with instance '%s'", inst ? inst : "main");
+  return vkb_plan_sink(h->g, m, wd, ht, 0) ? vkb_set_error(VKB_ERR_GRAPH, "graph has not been run yet") : VKB_OK;
+}
+int vkb_graph_sink_device(vkb_graph_t *h, const char *inst, void **d_ptr)
+{
+  if(!h) return VKB_ERR_BAD_ARG;
+  const int m = find_inst(h->g, inst, false);
+  if(m < 0) return vkb_set_error(VKB_ERR_BAD_ARG, "no sink module with instance '%s'", inst ? inst : "main");
+  return vkb_plan_sink(h->g, m, 0, 0, d_ptr) ? vkb_set_error(VKB_ERR_GRAPH, "graph has not been run yet") : VKB_OK;
+}
+int vkb_graph_set_frame(vkb_graph_t *h, uint32_t frame) { if(!h) return VKB_ERR_BAD_ARG; h->g->frame = frame; return VKB_OK; }
+int vkb_graph_run(vkb_graph_t *h, int runflags) { if(!h) return VKB_ERR_BAD_ARG; return dt_graph_run(h->g, (uint32_t)runflags); }
+int vkb_graph_perf(vkb_graph_t *h, char *buf, size_t bufsize)
+{
+  if(!h || !buf || !bufsize) return VKB_ERR_BAD_ARG;
+  snprintf(buf, bufsize, "%s", h->g->perf_text.c_str());
+  int n = 0;
+  for(char c : h->g->perf_text) n += c == '\n';
+  return n;
+}
+int vkb_graph_dump_nodes(vkb_graph_t *h, char *buf, size_t bufsize)
+{
+  if(!h || !buf || !bufsize) return VKB_ERR_BAD_ARG;
+  const std::string s = dt_graph_dump_nodes(h->g);
+  snprintf(buf, bufsize, "%s", s.c_str());
+  return (int)s.size();
+}
+int vkb_graph_plan(vkb_graph_t *h, char *buf, size_t bufsize)
+{
+  if(!h) return VKB_ERR_BAD_ARG;
+  std::string s;
+  const int r = dt_graph_plan(h->g, &s);
+  if(r) return r;
+  if(buf && bufsize) snprintf(buf, bufsize, "%s", s.c_str());
+  return VKB_OK;
+}
+uint64_t vkb_graph_pool_bytes(vkb_graph_t *h) { return h ? vkb_plan_pool_bytes(h->g) : 0; }
+
+} // extern "C"

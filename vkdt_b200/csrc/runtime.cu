@@ -1,0 +1,118 @@
+// runtime + dispatch layers of the C-ABI (include/vkdt_b200.h §1, §2).
+// replaces src/qvk (device selection, queues) and the (name, kernel) -> pipeline lookup of src/pipe/graph.c:304-343
+// with a static registry of CUDA launchers.  there is no CPU fallback: without a device every call fails.
+#include "vkb_internal.h"
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+
+#define VKB_MAX_KERNELS 128
+struct kernel_entry_t { vkb_token_t name, kernel; vkb_kernel_fn fn; };
+static kernel_entry_t *g_kernels() { static kernel_entry_t k[VKB_MAX_KERNELS]; return k; }
+static int &g_kernel_cnt() { static int n = 0; return n; }
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+static int g_device = -1;
+
+extern "C" vkb_token_t vkb_token(const char *str)
+{ // src/pipe/token.h:39-56: up to 8 chars, little endian, zero padded
+  vkb_token_t t = 0;
+  for(int i = 0; i < 8 && str && str[i]; i++) t |= (vkb_token_t)(uint8_t)str[i] << (8 * i);
+  return t;
+}
+
+void vkb_register_kernel(const char *name, const char *kernel, vkb_kernel_fn fn)
+{
+  if(g_kernel_cnt() >= VKB_MAX_KERNELS) return;
+  g_kernels()[g_kernel_cnt()++] = { vkb_token(name), vkb_token(kernel), fn };
+}
+vkb_kernel_fn vkb_find_kernel(vkb_token_t name, vkb_token_t kernel)
+{
+  for(int i = 0; i < g_kernel_cnt(); i++)
+    if(g_kernels()[i].name == name && g_kernels()[i].kernel == kernel) return g_kernels()[i].fn;
+  return 0;
+}
+int vkb_set_error(int code, const char *fmt, ...)
+{
+  va_list ap; va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+void vkb_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+extern "C" {
+
+const char *vkb_last_error(void) { return g_err; }
+const char *vkb_version(void) { return "vkdt_b200 0.1 (sm_100a)"; }
+
+int vkb_device_count(void)
+{
+  int n = 0;
+  if(cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int vkb_init(int device_id)
+{
+  const int n = vkb_device_count();
+  if(n <= 0) return vkb_set_error(VKB_ERR_NO_DEVICE, "no CUDA device: vkdt_b200 has no CPU fallback");
+  if(device_id < 0) device_id = 0;
+  if(device_id >= n) return vkb_set_error(VKB_ERR_BAD_ARG, "device %d out of range (%d devices)", device_id, n);
+  cudaError_t e = cudaSetDevice(device_id);
+  if(e != cudaSuccess) return vkb_set_error(VKB_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  cudaFree(0);
+  g_device = device_id;
+  return VKB_OK;
+}
+void vkb_cleanup(void) { g_device = -1; }
+
+static int need_device(void)
+{
+  if(g_device >= 0) return VKB_OK;
+  return vkb_init(0);
+}
+
+#define CU(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) return vkb_set_error(VKB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while(0)
+
+int vkb_malloc(void **dptr, size_t bytes) { int r = need_device(); if(r) return r; CU(cudaMalloc(dptr, bytes)); return VKB_OK; }
+int vkb_free(void *dptr) { CU(cudaFree(dptr)); return VKB_OK; }
+int vkb_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream)
+{ CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream)); return VKB_OK; }
+int vkb_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream)
+{ CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream)); return VKB_OK; }
+int vkb_stream_sync(void *stream) { CU(cudaStreamSynchronize((cudaStream_t)stream)); return VKB_OK; }
+int vkb_host_alloc(void **hptr, size_t bytes) { int r = need_device(); if(r) return r; CU(cudaHostAlloc(hptr, bytes, cudaHostAllocDefault)); return VKB_OK; }
+int vkb_host_free(void *hptr) { CU(cudaFreeHost(hptr)); return VKB_OK; }
+
+int vkb_dispatch(vkb_token_t name, vkb_token_t kernel, uint32_t wd, uint32_t ht, uint32_t dp,
+                 const void *push, uint32_t push_size, const void *params, uint32_t params_size,
+                 const vkb_image_t *conn, uint32_t num_conn, void *stream)
+{
+  int r = need_device();
+  if(r) return r;
+  vkb_kernel_fn fn = vkb_find_kernel(name, kernel);
+  if(!fn)
+  {
+    char a[9] = {0}, b[9] = {0};
+    memcpy(a, &name, 8); memcpy(b, &kernel, 8);
+    return vkb_set_error(VKB_ERR_UNKNOWN_KERNEL, "no kernel registered for (%s, %s)", a, b);
+  }
+  for(uint32_t i = 0; i < num_conn; i++)
+    if(conn[i].data && conn[i].layers == 0) return vkb_set_error(VKB_ERR_BAD_ARG, "connector %u has zero layers", i);
+  vkb_launch_t l = { wd, ht, dp, push, push_size, params, params_size, conn, num_conn, (cudaStream_t)stream };
+  return fn(&l);
+}
+
+int vkb_kernel_count(void) { return g_kernel_cnt(); }
+int vkb_kernel_name(int idx, vkb_token_t *name, vkb_token_t *kernel)
+{
+  if(idx < 0 || idx >= g_kernel_cnt()) return VKB_ERR_BAD_ARG;
+  *name = g_kernels()[idx].name; *kernel = g_kernels()[idx].kernel;
+  return VKB_OK;
+}
+uint64_t vkb_launch_count(void) { return g_launches.load(); }
+void vkb_launch_count_reset(void) { g_launches.store(0); }
+
+} // extern "C"
