@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py — the raw->display hot path on N B200s (one process per GPU).
+
+metric: MP/s of the default darkroom graph (i-raw -> denoise -> hilite -> demosaic -> crop -> colour -> filmcurv ->
+llap -> grade -> o-pfm, bin/default-darkroom.i-raw) on synthetic 61 MP Bayer stills (BASELINE.json configs[1]).
+a "step" is one full pass of the graph over one still.  stills are independent units: with N > 1 every rank develops
+its own stills (weak scaling, no data-path collective; torch.distributed is used for the barrier and max-over-ranks only).
+
+  value      whole-job MP/s, input mosaic already resident in HBM, result left in HBM (kernel path only, CUDA events)
+  e2e        same metric through the reference-facing C-ABI graph call with HOST buffers: pinned H2D of the u16 mosaic and
+             D2H of the rgba f32 sink image inside the timed region
+  roofline   dominant kernel: unique bytes in+out of the launch / its average CUDA-event duration vs measured HBM copy peak
+  cpu_baseline / --impl reference: the CPU restatement of the reference's algorithm (oracle, OpenMP, all host cores) on a
+             bounded crop of the same workload.  the reference's own Vulkan pipeline cannot be built here.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (width, height, source module, packed bpp)
+    "still61": (9504, 6336, "i-raw", 0),
+    "still24": (6000, 4000, "i-raw", 0),
+    "mlv4k": (4096, 2160, "i-mlv", 14),
+}
+WB = (2.0, 1.0, 1.5)
+CAM = (0.8, 0.15, 0.05, 0.1, 0.85, 0.05, 0.02, 0.18, 0.8)
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag, self.proc = gpu, [], False, None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def oracle_cfg(O, w, h, strength):
+    d = O.darkroom_defaults(w, h)
+    for k in range(3):
+        d.whitebalance[k] = WB[k]
+    for k in range(9):
+        d.cam_to_rec2020[k] = CAM[k]
+    d.denoise.strength = strength
+    d.noise_a, d.noise_b = 100.0, 2.0
+    return d
+
+
+def cpu_reference_rate(sample_wh, steps, warmup, strength):
+    """times the oracle (CPU port of the reference's algorithm, OpenMP over all host cores) on a bounded crop."""
+    from oracle import oracle_py as O
+    from vkdt_b200 import synth
+    w, h = sample_wh
+    raw = synth.mosaic(w, h, seed=0x5EED0000)
+    d = oracle_cfg(O, w, h, strength)
+    ow, oh = O.darkroom_out_size(d)
+    for _ in range(warmup):
+        O.darkroom_run(d, raw)
+    t0 = time.time()
+    for _ in range(steps):
+        O.darkroom_run(d, raw)
+    dt = (time.time() - t0) / max(1, steps)
+    return (w * h) / dt / 1e6, dt, os.cpu_count()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="still61", choices=sorted(WORKLOADS))
+    ap.add_argument("--denoise", type=float, default=None, help="denoise:strength (default: 0.4 once the wavelet kernels are built, else 0)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    W, H, src, bpp = WORKLOADS[args.workload]
+    mp = W * H / 1e6
+
+    if args.impl == "reference":
+        # the reference's own CPU-side implementation of the path = the oracle port (vkdt-cli needs vulkan + glslang: absent)
+        if rank != 0:
+            return 0
+        strength = args.denoise if args.denoise is not None else 0.0
+        sample = (2376, 1584)  # 1/16 of the 61 MP frame, same graph
+        rate, dt, cores = cpu_reference_rate(sample, max(1, min(args.steps, 5)), max(1, min(args.warmup, 1)), strength)
+        print(json.dumps({
+            "impl": "reference", "metric": "MP/s raw->display graph", "value": round(rate, 3), "unit": "MP/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s %dx%d bayer 14-bit, default darkroom graph, denoise strength %.2f" % (args.workload, W, H, strength)},
+            "cpu_baseline": {"value": round(rate, 3), "unit": "MP/s", "cores": cores, "kind": "port",
+                             "sample": "%dx%d crop of the workload, %d timed passes of the CPU oracle (OpenMP)" % (sample[0], sample[1], max(1, min(args.steps, 5)))},
+            "e2e": {"value": round(rate, 3), "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from vkdt_b200 import api, synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (vkdt_b200 has no CPU path)")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    api.init(local_rank)
+    have_wavelet = ("denoise", "doub") in api.kernels()
+    strength = args.denoise if args.denoise is not None else (0.4 if have_wavelet else 0.0)
+
+    # ---- synthetic input: a few distinct stills per rank, cycled (deterministic seeds per SURVEY §8d) ----
+    nstills = 2
+    raws = [synth.mosaic(W, H, seed=0x5EED0000 + rank * 1000 + i, wb=WB) for i in range(nstills)]
+    if bpp:
+        payload = [synth.pack_bits_fast14(r) for r in raws]
+        in_bytes = (W * H * bpp + 7) // 8
+    else:
+        payload = raws
+        in_bytes = W * H * 2
+    rp = api.raw_params(W, H, wb=WB, cam_to_rec2020=CAM, noise_a=100.0, noise_b=2.0, packed_bpp=bpp)
+    # pinned host staging for the e2e leg, device copies for the kernel leg
+    host_in = []
+    for p in payload:
+        hp = api.host_alloc(p.nbytes + 64)
+        C = api.C
+        C.memmove(hp, p.ctypes.data, p.nbytes)
+        host_in.append(hp)
+    dev_in = []
+    for p in payload:
+        dp = api.dev_alloc(p.nbytes + 256)
+        api.check(api.lib.vkb_memcpy_h2d(dp, p.ctypes.data, p.nbytes, None))
+        dev_in.append(dp)
+    api.check(api.lib.vkb_stream_sync(None))
+
+    def make_graph():
+        g = api.Graph(cfg_text=api.DARKROOM_CFG.format(src=src))
+        g.set_device(local_rank)
+        if strength > 0:
+            g.line("param:denoise:01:strength:%g" % strength)
+        return g
+
+    # ---- leg 1: kernel path, input resident in HBM, sink left in HBM ----
+    g = make_graph()
+    g.set_source(dev_in[0], rp, device=True)
+    g.set_sink_buffer(None, 0)
+    g.run()                              # builds the plan, allocates the pool
+    ow, oh = g.sink_size()
+    out_bytes = ow * oh * 16
+    stream = g.stream()
+    FR = api.RUN_RECORD
+    for i in range(args.warmup):
+        g.set_source(dev_in[i % nstills], rp, device=True)
+        g.run(FR | api.RUN_UPLOAD)
+    api.check(api.lib.vkb_stream_sync(api.C.c_void_p(stream)))
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    api.lib.vkb_launch_count_reset()
+    e0, e1 = api.Event(), api.Event()
+    per_kernel = {}
+    e0.record(stream)
+    for i in range(args.steps):
+        g.set_source(dev_in[i % nstills], rp, device=True)
+        g.run(FR | api.RUN_UPLOAD | (api.RUN_WAIT if i == args.steps - 1 or i % 4 == 3 else 0))
+        if i == args.steps - 1 or i % 4 == 3:      # per-launch events are valid after a synchronised run
+            for label, ms, nbytes in g.perf_entries():
+                a = per_kernel.setdefault(label, [0.0, 0, nbytes])
+                a[0] += ms; a[1] += 1
+    e1.record(stream)
+    e1.sync()
+    torch.cuda.synchronize()
+    launches = api.launch_count()
+    t_kernel_ms = e0.elapsed_ms(e1)
+    if world > 1:
+        t = torch.tensor([t_kernel_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_kernel_ms = float(t.item())
+    clocks = sampler.stop()
+
+    # ---- leg 2: end to end through the C-ABI with host buffers ----
+    g2 = make_graph()
+    host_out = api.host_alloc(out_bytes)
+    g2.set_source(host_in[0], rp)
+    g2.set_sink_buffer(host_out, out_bytes)
+    g2.run()
+    FE = api.RUN_RECORD | api.RUN_UPLOAD | api.RUN_DOWNLOAD | api.RUN_WAIT
+    for i in range(max(1, args.warmup)):
+        g2.set_source(host_in[i % nstills], rp)
+        g2.run(FE)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    s2 = g2.stream()
+    f0, f1 = api.Event(), api.Event()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.time()
+    f0.record(s2)
+    for i in range(e2e_steps):
+        g2.set_source(host_in[i % nstills], rp)
+        g2.run(FE)
+    f1.record(s2)
+    f1.sync()
+    t_e2e_ms = max(f0.elapsed_ms(f1), (time.time() - t0) * 1e3)
+    if world > 1:
+        t = torch.tensor([t_e2e_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e_ms = float(t.item())
+    checksum = float(np.frombuffer((api.C.c_float * 4).from_address(host_out), dtype=np.float32).sum())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel ----
+    pk, pk_kind = peaks()
+    top = max(per_kernel.items(), key=lambda kv: kv[1][0])
+    top_label, (top_ms_sum, top_n, top_bytes) = top
+    top_ms = top_ms_sum / top_n
+    achieved = top_bytes / (top_ms * 1e-3) / 1e9
+    total_ms = sum(v[0] / v[1] for v in per_kernel.values())
+    graph_alg_bytes = in_bytes + out_bytes
+    roof = {"bound": "hbm", "kernel": top_label, "achieved": round(achieved, 1), "peak": pk["hbm_gbs"], "peak_kind": pk_kind + " copy bandwidth",
+            "unit": "GB/s", "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": None,
+            "algorithmic_bytes_per_launch": top_bytes, "avg_launch_ms": round(top_ms, 4),
+            "share_of_step": round(top_ms / total_ms, 4),
+            "graph": {"algorithmic_bytes_per_step": graph_alg_bytes, "achieved_gbs": round(graph_alg_bytes / (t_kernel_ms / args.steps * 1e-3) / 1e9, 1),
+                      "frac": round(graph_alg_bytes / (t_kernel_ms / args.steps * 1e-3) / 1e9 / pk["hbm_gbs"], 4)},
+            "kernels": {k: {"ms": round(v[0] / v[1], 4), "gbs": round(v[2] / (v[0] / v[1] * 1e-3) / 1e9, 1)} for k, v in
+                        sorted(per_kernel.items(), key=lambda kv: -kv[1][0])[:12]}}
+    line = {
+        "metric": "MP/s raw->display graph", "value": round(world * args.steps * mp / (t_kernel_ms * 1e-3), 2), "unit": "MP/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t_kernel_ms / args.steps, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: %dx%d bayer rggb 14-bit still (%.1f MP), default darkroom graph incl. hilite + llap + grade, "
+                               "denoise strength %.2f, sink rgba f32 %dx%d" % (args.workload, W, H, mp, strength, ow, oh),
+                   "timing": "inputs and intermediates (%.0f MB pool) exceed the 126 MB L2; %d distinct stills cycled" % (g.pool_bytes() / 1e6, nstills),
+                   "parallelism": "independent stills per GPU, no collective", "edges": "f16 at every reference edge (strict)"},
+        "e2e": {"value": round(world * e2e_steps * mp / (t_e2e_ms * 1e-3), 2), "unit": "MP/s", "h2d_bytes_per_step": in_bytes,
+                "d2h_bytes_per_step": out_bytes, "ms_per_step": round(t_e2e_ms / e2e_steps, 3), "steps": e2e_steps, "checksum": checksum},
+        "gpu_launches": int(launches), "launches_per_step": int(launches // max(1, args.steps)),
+        "clocks": clocks, "roofline": roof, "pool_bytes": g.pool_bytes(),
+    }
+    if not args.no_cpu_baseline:
+        sample = (2376, 1584)
+        rate, dt, cores = cpu_reference_rate(sample, 3, 1, strength)
+        line["cpu_baseline"] = {"value": round(rate, 3), "unit": "MP/s", "cores": cores, "kind": "port",
+                                "sample": "%dx%d crop of the workload, 3 timed passes of the CPU oracle (OpenMP), %.2f s each" % (sample[0], sample[1], dt)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -59,6 +59,12 @@ VKB_API int  vkb_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stre
 VKB_API int  vkb_stream_sync(void *stream);
 VKB_API int  vkb_host_alloc(void **hptr, size_t bytes);  /* pinned host staging, the "mapped" pointer of read_source/write_sink */
 VKB_API int  vkb_host_free(void *hptr);
+/* device timestamps on a stream (the reference times nodes with vulkan timestamp queries, src/pipe/graph.c:96-109) */
+VKB_API int  vkb_event_create(void **ev);
+VKB_API int  vkb_event_record(void *ev, void *stream);
+VKB_API int  vkb_event_sync(void *ev);
+VKB_API int  vkb_event_elapsed_ms(void *ev0, void *ev1, float *ms);
+VKB_API int  vkb_event_destroy(void *ev);
 
 /* ---- 2. dispatch ---- */
 /* one connector image as a kernel sees it (dt_connector_t + dt_connector_image_t, src/pipe/connector.h:156-210) */
@@ -136,7 +142,9 @@ VKB_API int  vkb_graph_dump_nodes(vkb_graph_t *g, char *buf, size_t bufsize); /*
 /* device-resident variant for kernel-only timing: source already in HBM, sink left in HBM */
 VKB_API int  vkb_graph_set_source_device(vkb_graph_t *g, const char *inst, const void *d_data, const vkb_raw_params_t *p);
 VKB_API int  vkb_graph_sink_device(vkb_graph_t *g, const char *inst, void **d_ptr);
-VKB_API uint64_t vkb_graph_pool_bytes(vkb_graph_t *g);                      /* -d mem: peak pooled HBM */
+VKB_API uint64_t vkb_graph_pool_bytes(vkb_graph_t *g);
+VKB_API void *vkb_graph_stream(vkb_graph_t *g);                            /* the cudaStream_t the graph launches on (after the first run) */
+VKB_API int   vkb_graph_set_device(vkb_graph_t *g, int device);             /* one graph per GPU: frame-parallel / band-split drivers */                      /* -d mem: peak pooled HBM */
 
 #ifdef __cplusplus
 }

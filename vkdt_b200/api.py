@@ -39,11 +39,12 @@ lib.vkb_dispatch.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c
 
 # every symbol include/vkdt_b200.h declares (checked by tests/test_cabi.py)
 DECLARED = """vkb_token vkb_init vkb_cleanup vkb_device_count vkb_last_error vkb_version vkb_malloc vkb_free
-vkb_memcpy_h2d vkb_memcpy_d2h vkb_stream_sync vkb_host_alloc vkb_host_free vkb_dispatch vkb_kernel_count
+vkb_memcpy_h2d vkb_memcpy_d2h vkb_stream_sync vkb_host_alloc vkb_host_free vkb_event_create vkb_event_record
+vkb_event_sync vkb_event_elapsed_ms vkb_event_destroy vkb_dispatch vkb_kernel_count
 vkb_kernel_name vkb_launch_count vkb_launch_count_reset vkb_graph_new vkb_graph_free vkb_graph_read_config_ascii
 vkb_graph_read_config_line vkb_graph_replace_display vkb_graph_set_source vkb_graph_set_sink_buffer
 vkb_graph_sink_size vkb_graph_set_frame vkb_graph_run vkb_graph_plan vkb_graph_perf vkb_graph_dump_nodes
-vkb_graph_set_source_device vkb_graph_sink_device vkb_graph_pool_bytes""".split()
+vkb_graph_set_source_device vkb_graph_sink_device vkb_graph_pool_bytes vkb_graph_stream vkb_graph_set_device""".split()
 
 
 def token(s):
@@ -111,6 +112,57 @@ lib.vkb_graph_pool_bytes.argtypes = [C.c_void_p]
 lib.vkb_graph_pool_bytes.restype = C.c_uint64
 lib.vkb_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
 lib.vkb_host_free.argtypes = [C.c_void_p]
+lib.vkb_graph_stream.argtypes = [C.c_void_p]
+lib.vkb_graph_stream.restype = C.c_void_p
+lib.vkb_graph_set_device.argtypes = [C.c_void_p, C.c_int]
+lib.vkb_event_create.argtypes = [C.POINTER(C.c_void_p)]
+lib.vkb_event_record.argtypes = [C.c_void_p, C.c_void_p]
+lib.vkb_event_sync.argtypes = [C.c_void_p]
+lib.vkb_event_elapsed_ms.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+lib.vkb_event_destroy.argtypes = [C.c_void_p]
+lib.vkb_malloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+lib.vkb_free.argtypes = [C.c_void_p]
+lib.vkb_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+lib.vkb_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+lib.vkb_stream_sync.argtypes = [C.c_void_p]
+
+
+class Event:
+    def __init__(self):
+        self.e = C.c_void_p()
+        check(lib.vkb_event_create(C.byref(self.e)))
+
+    def record(self, stream):
+        check(lib.vkb_event_record(self.e, C.c_void_p(stream)))
+
+    def sync(self):
+        check(lib.vkb_event_sync(self.e))
+
+    def elapsed_ms(self, later):
+        ms = C.c_float()
+        check(lib.vkb_event_elapsed_ms(self.e, later.e, C.byref(ms)))
+        return ms.value
+
+
+def host_alloc(nbytes):
+    """pinned host memory as a ctypes pointer value (free with host_free)."""
+    p = C.c_void_p()
+    check(lib.vkb_host_alloc(C.byref(p), nbytes))
+    return p.value
+
+
+def host_free(ptr):
+    check(lib.vkb_host_free(C.c_void_p(ptr)))
+
+
+def dev_alloc(nbytes):
+    p = C.c_void_p()
+    check(lib.vkb_malloc(C.byref(p), nbytes))
+    return p.value
+
+
+def dev_free(ptr):
+    check(lib.vkb_free(C.c_void_p(ptr)))
 
 # the reference's bin/default-darkroom.i-raw / .i-mlv module and connection lines (gui coordinates dropped)
 DARKROOM_CFG = """module:{src}:main
@@ -200,6 +252,24 @@ class Graph:
         b = C.create_string_buffer(1 << 18)
         lib.vkb_graph_dump_nodes(self.h, b, len(b))
         return b.value.decode()
+
+    def stream(self):
+        return lib.vkb_graph_stream(self.h) or 0
+
+    def set_device(self, dev):
+        check(lib.vkb_graph_set_device(self.h, dev))
+
+    def perf_entries(self):
+        """[(label, ms, unique bytes in+out)] of the last synchronised run."""
+        out = []
+        for l in self.perf().splitlines():
+            if l.startswith("[perf] total") or not l.startswith("[perf]"):
+                continue
+            label, rest = l[7:].split(":\t", 1) if ":\t" in l else (l, "")
+            f = rest.split("\t")
+            if len(f) >= 2:
+                out.append((label.strip(), float(f[0].split()[0]), int(f[1].split()[0])))
+        return out
 
     def pool_bytes(self):
         return int(lib.vkb_graph_pool_bytes(self.h))

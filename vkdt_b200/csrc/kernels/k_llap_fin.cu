@@ -1,0 +1,134 @@
+// finest level of the local laplacian pyramid, fused with llap/colour.comp and (optionally) grade/main.comp:
+//   out = grade( recolour( expand(coarse) + blend of the two laplacians bracketing the local grey value ) )
+// (llap/assemble.comp:52-88, llap/colour.comp:17-37, grade/main.comp:21-62).
+// B200 shape: the three gauss_expand()s a pixel needs read 5x5 coarse texels each from planes that depend on the
+// pixel's grey value.  a CTA of 32x8 output pixels stages the 20x8 coarse window of ALL 12 planes (11 gamma layers +
+// the collapsed coarse level) in shared memory once (7.5 global loads per pixel instead of ~60 with per-tap address
+// mirroring), and evaluates sample_soft's 3x3 bilinear taps in their separable form [1 1 2 1 1]/6 | [2 1 1 2]/6.
+// the separable sum differs from the shader's 9-tap order by fp32 rounding only (~1e-7), far below the f16 store
+// that follows; nothing downstream of this kernel feeds a pyramid level, so the difference cannot compound.
+// level-0 gamma layers are never read: curve() is recomputed from the input pixel and rounded to f16 in registers.
+#include "pointwise.cuh"
+#include <string.h>
+
+#define NUM_GAMMA 10
+#define NL (NUM_GAMMA + 1)
+#define FT_W 20
+#define FT_H 8
+
+struct llap_params_t { float sigma, shadows, hilights, clarity; };
+struct llapfin_t { llap_params_t p; int first; int have_grade; int out_f32; grade_params_t grade; };
+
+VKB_DEV float gamma_from_i(int i) { return (float)i / (NUM_GAMMA - 1.0f); }
+VKB_DEV float llap_curve(float x, float g, const llap_params_t &p)
+{ // llap/curve.comp:40-63
+  const float c = x - g;
+  float val;
+  const float ssigma = c > 0.0f ? p.sigma : -p.sigma;
+  const float shadhi = c > 0.0f ? p.shadows : p.hilights;
+  if(fabsf(c) > 2 * p.sigma) val = g + ssigma + shadhi * (c - ssigma);
+  else
+  {
+    const float t = clampf(c / (2.0f * ssigma), 0.0f, 1.0f);
+    const float t2 = t * t;
+    const float mt = 1.0f - t;
+    val = g + ssigma * 2.0f * mt * t + t2 * (ssigma + ssigma * shadhi);
+  }
+  val += p.clarity * c * expf(-c * c / (2.0f * p.sigma * p.sigma / 3.0f));
+  return val;
+}
+
+template <bool F32, bool GRADE>
+__global__ void __launch_bounds__(256) k_llap_final2(const uint2 *__restrict__ in, const __half *__restrict__ coarse,
+    const __half *__restrict__ l1, int cw, int ch, void *__restrict__ outv, int ow, int oh, const __grid_constant__ llapfin_t P)
+{
+  __shared__ float tile[NL + 1][FT_H][FT_W + 1];
+  const int cx0 = blockIdx.x * 16 - 2, cy0 = blockIdx.y * 4 - 2;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const size_t p1 = (size_t)cw * ch;
+  const bool big = cw >= 24 && ch >= 12;
+  for(int t = tid; t < (NL + 1) * FT_H * FT_W; t += 256)
+  {
+    const int pl = t / (FT_H * FT_W), rem = t - pl * (FT_H * FT_W), r = rem / FT_W, c = rem - r * FT_W;
+    const int gx = big ? mirror1(cx0 + c, cw) : mirrori(cx0 + c, cw), gy = big ? mirror1(cy0 + r, ch) : mirrori(cy0 + r, ch);
+    const __half *src = pl < NL ? l1 + pl * p1 : (P.first ? l1 + NUM_GAMMA * p1 : coarse);
+    tile[pl][r][c] = __half2float(__ldg(src + (size_t)gy * cw + gx));
+  }
+  __syncthreads();
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if(x >= ow || y >= oh) return;
+  const float4 px = ld_rgba(in, ow, x, y);
+  const float grey = lum2020(clampf(px.x, -1000.0f, 1000.0f), clampf(px.y, -1000.0f, 1000.0f), clampf(px.z, -1000.0f, 1000.0f));
+  // separable sample_soft weights over texels k-2..k+2 (tile column lx-2..lx+2)
+  const int lx = (x >> 1) - cx0, ly = (y >> 1) - cy0;
+  const bool ox = x & 1, oy = y & 1;
+  const float wx[5] = { ox ? 0.0f : 0.5f, ox ? 1.0f : 0.5f, ox ? 0.5f : 1.0f, 0.5f, ox ? 1.0f : 0.5f };
+  const float wy[5] = { oy ? 0.0f : 0.5f, oy ? 1.0f : 0.5f, oy ? 0.5f : 1.0f, 0.5f, oy ? 1.0f : 0.5f };
+  const float v = f16r(grey);
+  int hi = 1;
+  for(; hi < NUM_GAMMA - 1 && gamma_from_i(hi) <= v; hi++);
+  const int lo = hi - 1;
+  float e[3];
+  const int planes[3] = { NL, lo, hi };
+#pragma unroll
+  for(int q = 0; q < 3; q++)
+  {
+    const float (*T)[FT_W + 1] = tile[planes[q]];
+    float acc = 0.0f;
+#pragma unroll
+    for(int r = 0; r < 5; r++)
+    {
+      const float *row = T[ly - 2 + r] + lx - 2;
+      const float h = row[0] * wx[0] + row[1] * wx[1] + row[2] * wx[2] + row[3] * wx[3] + row[4] * wx[4];
+      acc += h * wy[r];
+    }
+    e[q] = acc / 9.0f;
+  }
+  const float glo = gamma_from_i(lo), ghi = gamma_from_i(hi);
+  const float a = clampf((v - glo) / (ghi - glo), 0.0f, 1.0f);
+  const float lap0 = f16r(llap_curve(grey, glo, P.p)) - e[1];
+  const float lap1 = f16r(llap_curve(grey, ghi, P.p)) - e[2];
+  float l = f16r(e[0] + lap0 * (1.0f - a) + lap1 * a);
+  // llap/colour.comp:17-37
+  const float yo = fmaxf(lum2020(px.x, px.y, px.z), 1e-8f);
+  if(l < yo) l = yo * expf(1.0f * (l - yo));
+  f3 c = { fmaxf(0.0f, px.x * l / yo), fmaxf(0.0f, px.y * l / yo), fmaxf(0.0f, px.z * l / yo) };
+  if(GRADE)
+  {
+    c = { f16r(c.x), f16r(c.y), f16r(c.z) };
+    c = grade_px(c, P.grade);
+  }
+  if(F32) reinterpret_cast<float4 *>(outv)[(size_t)y * ow + x] = make_float4(c.x, c.y, c.z, 1.0f);
+  else st_rgba(reinterpret_cast<uint2 *>(outv), ow, x, y, make_float4(c.x, c.y, c.z, 1.0f));
+}
+
+// conn: [0] input rgba f16, [1] coarse y f16 (level 1 assembled; ignored when first), [2] level-1 stack x11, [3] output rgba f16|f32
+// push: { u32 first; u32 have_grade }.  params: llap params (16 B) followed by grade params (76 B) when have_grade
+static int launch_llapfin2(const vkb_launch_t *l)
+{
+  VKB_REQUIRE(l->num_conn >= 4 && l->push_size >= 8 && l->params_size >= sizeof(llap_params_t));
+  const uint32_t *pc = (const uint32_t *)l->push;
+  const vkb_image_t *in = l->conn, *coarse = l->conn + 1, *l1 = l->conn + 2, *out = l->conn + 3;
+  VKB_REQUIRE(in->chan == 4 && in->format == VKB_TOKEN_F16 && l1->layers == NL && out->chan == 4);
+  VKB_REQUIRE(in->wd == out->wd && in->ht == out->ht);
+  VKB_REQUIRE(l1->wd == (in->wd - 1) / 2 + 1 && l1->ht == (in->ht - 1) / 2 + 1);
+  VKB_REQUIRE(out->format == VKB_TOKEN_F16 || out->format == VKB_TOKEN_F32);
+  llapfin_t P;
+  memset(&P, 0, sizeof(P));
+  memcpy(&P.p, l->params, sizeof(llap_params_t));
+  P.first = pc[0]; P.have_grade = pc[1]; P.out_f32 = out->format == VKB_TOKEN_F32;
+  if(P.have_grade)
+  {
+    VKB_REQUIRE(l->params_size >= sizeof(llap_params_t) + sizeof(grade_params_t));
+    memcpy(&P.grade, (const uint8_t *)l->params + sizeof(llap_params_t), sizeof(grade_params_t));
+  }
+  const dim3 grid(vkb_cdiv(out->wd, 32), vkb_cdiv(out->ht, 8)), block(32, 8);
+#define GO(F, G) k_llap_final2<F, G><<<grid, block, 0, l->stream>>>((const uint2 *)in->data, (const __half *)coarse->data, \
+      (const __half *)l1->data, l1->wd, l1->ht, out->data, out->wd, out->ht, P)
+  if(P.out_f32) { if(P.have_grade) GO(true, true); else GO(true, false); }
+  else          { if(P.have_grade) GO(false, true); else GO(false, false); }
+#undef GO
+  VKB_CHECK_LAUNCH();
+  return VKB_OK;
+}
+VKB_REGISTER("b200", "llapfin", launch_llapfin2);

@@ -25,6 +25,33 @@ struct pw_chain_t
 
 VKB_DEV f3 round3(f3 c) { return { f16r(c.x), f16r(c.y), f16r(c.z) }; }
 
+// compile-time specialisations of the common chains: the op sequence is a template parameter pack, so the loop
+// below unrolls into straight-line code (the generic runtime-switch kernel needed 104 registers).
+template <int O0, int O1, int O2, int O3, bool F32, bool ROT>
+__global__ void __launch_bounds__(256) k_pointwise_t(const uint2 *__restrict__ in, int iw, int ih,
+    void *__restrict__ outv, int ow, int oh, const __grid_constant__ pw_chain_t P)
+{
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if(x >= ow || y >= oh) return;
+  constexpr int ops[4] = { O0, O1, O2, O3 };
+  constexpr int n = (O0 != 0) + (O1 != 0) + (O2 != 0) + (O3 != 0);
+  float4 px;
+  if(O0 == PW_CROP) px = crop_fetch<ROT>(in, iw, ih, x, y, P.crop);
+  else px = ld_rgba(in, iw, x, y);
+  f3 c = { px.x, px.y, px.z };
+  if(O0 == PW_CROP && n > 1) c = round3(c);
+#pragma unroll
+  for(int o = (O0 == PW_CROP ? 1 : 0); o < n; o++)
+  {
+    if(ops[o] == PW_COLOUR)        c = colour_px(c, P.colour);
+    else if(ops[o] == PW_FILMCURV) c = filmcurv_px(c, P.film);
+    else if(ops[o] == PW_GRADE)    c = grade_px(c, P.grade);
+    if(o < n - 1) c = round3(c);
+  }
+  if(F32) reinterpret_cast<float4 *>(outv)[(size_t)y * ow + x] = make_float4(c.x, c.y, c.z, 1.0f);
+  else st_rgba(reinterpret_cast<uint2 *>(outv), ow, x, y, make_float4(c.x, c.y, c.z, 1.0f));
+}
+
 __global__ void __launch_bounds__(256) k_pointwise(const uint2 *__restrict__ in, int iw, int ih,
     void *__restrict__ outv, int ow, int oh, const __grid_constant__ pw_chain_t P)
 {
@@ -37,7 +64,7 @@ __global__ void __launch_bounds__(256) k_pointwise(const uint2 *__restrict__ in,
     if(x >= ow) continue;
     float4 px;
     int first = 0;
-    if(P.op[0] == PW_CROP) { px = crop_fetch(in, iw, ih, x, y, P.crop); first = 1; }
+    if(P.op[0] == PW_CROP) { px = P.crop.r[0] != 1.0f ? crop_fetch<true>(in, iw, ih, x, y, P.crop) : crop_fetch<false>(in, iw, ih, x, y, P.crop); first = 1; }
     else px = ld_rgba(in, iw, min(x, iw - 1), min(y, ih - 1));
     f3 c = { px.x, px.y, px.z };
     // every edge between two modules is an f16 image in the reference: round in registers where it would store
@@ -184,8 +211,29 @@ static int launch_chain(const vkb_launch_t *l, int n_ops, const uint32_t *ops)
     pp += need; left -= need;
   }
   if(P.op[0] != PW_CROP) VKB_REQUIRE(in->wd == out->wd && in->ht == out->ht);
-  dim3 block(32, 8), grid(vkb_cdiv(out->wd, 64), vkb_cdiv(out->ht, 8));
+  dim3 block(32, 8), grid(vkb_cdiv(out->wd, 64), vkb_cdiv(out->ht, 8)), grid1(vkb_cdiv(out->wd, 32), vkb_cdiv(out->ht, 8));
+  const int sig = P.op[0] | (P.op[1] << 4) | (P.op[2] << 8) | (P.op[3] << 12) | (n_ops > 4 ? 1 << 20 : 0);
+#define PW_CASE(A, B, C, D) \
+  case ((A) | ((B) << 4) | ((C) << 8) | ((D) << 12)): \
+    if((A) == PW_CROP && P.crop.r[0] != 1.0f) goto generic; /* rotation / perspective: catmull-rom gather, generic kernel */ \
+    if(P.out_f32) k_pointwise_t<A, B, C, D, true, false><<<grid1, block, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, out->data, out->wd, out->ht, P); \
+    else k_pointwise_t<A, B, C, D, false, false><<<grid1, block, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, out->data, out->wd, out->ht, P); \
+    break;
+  switch(sig)
+  {
+    PW_CASE(PW_CROP, PW_COLOUR, PW_FILMCURV, 0)
+    PW_CASE(PW_CROP, PW_COLOUR, PW_FILMCURV, PW_GRADE)
+    PW_CASE(PW_COLOUR, PW_FILMCURV, 0, 0)
+    PW_CASE(PW_CROP, PW_COLOUR, 0, 0)
+    PW_CASE(PW_CROP, 0, 0, 0)
+    PW_CASE(PW_COLOUR, 0, 0, 0)
+    PW_CASE(PW_FILMCURV, 0, 0, 0)
+    PW_CASE(PW_GRADE, 0, 0, 0)
+    default:
+    generic:
   k_pointwise<<<grid, block, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, out->data, out->wd, out->ht, P);
+  }
+#undef PW_CASE
   VKB_CHECK_LAUNCH();
   return VKB_OK;
 }

@@ -54,7 +54,9 @@ VKB_DEV float4 catmull_rom_rgba(const uint2 *__restrict__ tex, int w, int h, flo
   return res;
 }
 
-// crop/main.comp:20-57: output pixel (x,y) -> input texel
+// crop/main.comp:20-57: output pixel (x,y) -> input texel.  ROT is the shader's `params.r0 != 1.0` branch, hoisted
+// to a template parameter by the launcher (it is uniform): the catmull-rom path costs ~200 registers when inlined.
+template <bool ROT>
 VKB_DEV float4 crop_fetch(const uint2 *__restrict__ in, int iw, int ih, int x, int y, const crop_committed_t &c)
 {
   const float tsx = (float)iw, tsy = (float)ih;
@@ -70,7 +72,7 @@ VKB_DEV float4 crop_fetch(const uint2 *__restrict__ in, int iw, int ih, int x, i
   rdx /= tsx; rdy /= tsy;
   float4 rgba;
   if(rdx < 0.f || rdy < 0.f || rdx >= 1.f || rdy >= 1.f) rgba = make_float4(0, 0, 0, 0);
-  else if(c.r[0] != 1.0f) rgba = catmull_rom_rgba(in, iw, ih, rdx, rdy);
+  else if(ROT) rgba = catmull_rom_rgba(in, iw, ih, rdx, rdy);
   else rgba = ld_rgba_clamp(in, iw, ih, (int)(rdx * tsx), (int)(rdy * tsy));
   rgba.w = 1.0f;
   return rgba;

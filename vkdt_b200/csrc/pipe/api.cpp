@@ -5,6 +5,7 @@
 int vkb_plan_sink(dt_graph_t *g, int modid, uint32_t *wd, uint32_t *ht, void **dptr);
 uint64_t vkb_plan_pool_bytes(dt_graph_t *g);
 int dt_graph_plan(dt_graph_t *g, std::string *text);
+void *vkb_plan_stream(dt_graph_t *g);
 
 struct vkb_graph_t { dt_graph_t *g; };
 
@@ -113,6 +114,8 @@ int vkb_graph_plan(vkb_graph_t *h, char *buf, size_t bufsize)
   if(buf && bufsize) snprintf(buf, bufsize, "%s", s.c_str());
   return VKB_OK;
 }
+void *vkb_graph_stream(vkb_graph_t *h) { return h ? vkb_plan_stream(h->g) : 0; }
+int vkb_graph_set_device(vkb_graph_t *h, int device) { if(!h) return VKB_ERR_BAD_ARG; h->g->device = device; return VKB_OK; }
 uint64_t vkb_graph_pool_bytes(vkb_graph_t *h) { return h ? vkb_plan_pool_bytes(h->g) : 0; }
 
 } // extern "C"

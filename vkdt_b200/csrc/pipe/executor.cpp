@@ -491,6 +491,16 @@ int dt_graph_run(dt_graph_t *g, uint32_t run)
       p->buf[s.buf_upload].external = (void *)g->mem_source[s.modid].data;
       continue;
     }
+    {
+      const vkb_mem_source_t *ms = s.modid < (int)g->mem_source.size() && g->mem_source[s.modid].valid ? &g->mem_source[s.modid] : 0;
+      const uint32_t swd = g->node[s.nodeid].connector[0].roi.wd;
+      if(ms && (s.packed_bpp || swd == ms->p.width))
+      { // the caller's buffer already has the staging layout: copy straight from it (pinned if it came from vkb_host_alloc)
+        const size_t payload = s.packed_bpp ? ((size_t)ms->p.width * ms->p.height * s.packed_bpp + 7) / 8 : s.bytes;
+        cudaMemcpyAsync(buf_ptr(p, s.buf_upload), ms->data, payload, cudaMemcpyHostToDevice, p->stream);
+        continue;
+      }
+    }
     if(!mod->so->read_source) return vkb_set_error(VKB_ERR_GRAPH, "source module %s has no read_source", dt_token_string(mod->name).c_str());
     cudaStreamSynchronize(p->stream); // staging is reused
     dt_read_source_params_t rp = { &g->node[s.nodeid], 0, 0 };
@@ -558,7 +568,11 @@ int dt_graph_run(dt_graph_t *g, uint32_t run)
       {
         cudaEventElapsedTime(&p->launch[i].ms, p->ev[i], p->ev[i+1]);
         total += p->launch[i].ms;
-        snprintf(b, sizeof(b), "[perf] %-60s:\t%8.3f ms\n", p->launch[i].label.c_str(), p->launch[i].ms);
+        size_t bytes = 0; // unique bytes in + out of this launch
+        std::set<int> seen;
+        for(const plan_img_t &im : p->launch[i].conn) if(im.buf >= 0 && seen.insert(im.buf).second)
+          bytes += (size_t)im.wd * im.ht * im.chan * im.layers * (im.format == dt_token("f32") ? 4 : 2);
+        snprintf(b, sizeof(b), "[perf] %-60s:\t%8.3f ms\t%12zu B\n", p->launch[i].label.c_str(), p->launch[i].ms, bytes);
         g->perf_text += b;
       }
       snprintf(b, sizeof(b), "[perf] total time:\t%8.3f ms\n", total);

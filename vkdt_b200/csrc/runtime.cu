@@ -105,6 +105,12 @@ int vkb_dispatch(vkb_token_t name, vkb_token_t kernel, uint32_t wd, uint32_t ht,
   return fn(&l);
 }
 
+int vkb_event_create(void **ev) { int r = need_device(); if(r) return r; cudaEvent_t e; CU(cudaEventCreate(&e)); *ev = (void *)e; return VKB_OK; }
+int vkb_event_record(void *ev, void *stream) { CU(cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)stream)); return VKB_OK; }
+int vkb_event_sync(void *ev) { CU(cudaEventSynchronize((cudaEvent_t)ev)); return VKB_OK; }
+int vkb_event_elapsed_ms(void *ev0, void *ev1, float *ms) { CU(cudaEventElapsedTime(ms, (cudaEvent_t)ev0, (cudaEvent_t)ev1)); return VKB_OK; }
+int vkb_event_destroy(void *ev) { CU(cudaEventDestroy((cudaEvent_t)ev)); return VKB_OK; }
+
 int vkb_kernel_count(void) { return g_kernel_cnt(); }
 int vkb_kernel_name(int idx, vkb_token_t *name, vkb_token_t *kernel)
 {
