@@ -219,34 +219,45 @@ def main():
     clocks = sampler.stop()
 
     # ---- leg 2: end to end through the C-ABI with host buffers ----
-    g2 = make_graph()
-    host_out = api.host_alloc(out_bytes)
-    g2.set_source(host_in[0], rp)
-    g2.set_sink_buffer(host_out, out_bytes)
-    g2.run()
-    FE = api.RUN_RECORD | api.RUN_UPLOAD | api.RUN_DOWNLOAD | api.RUN_WAIT
-    for i in range(max(1, args.warmup)):
-        g2.set_source(host_in[i % nstills], rp)
-        g2.run(FE)
+    # two graph instances (each with its own pool, stream and pinned sink) ping-pong: while one frame's 962 MB result
+    # drains over PCIe the next frame uploads and computes.  every frame still pays its full H2D + kernels + D2H.
+    NG = 2
+    gs, host_out = [], []
+    for k in range(NG):
+        gk = make_graph()
+        ho = api.host_alloc(out_bytes)
+        gk.set_source(host_in[0], rp)
+        gk.set_sink_buffer(ho, out_bytes)
+        gk.run()
+        gs.append(gk); host_out.append(ho)
+    FE = api.RUN_RECORD | api.RUN_UPLOAD | api.RUN_DOWNLOAD
+    for i in range(max(2, args.warmup)):
+        gs[i % NG].set_source(host_in[i % nstills], rp)
+        gs[i % NG].run(FE | api.RUN_WAIT)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    s2 = g2.stream()
+    e2e_steps = max(4, min(args.steps, 12))
     f0, f1 = api.Event(), api.Event()
-    e2e_steps = max(3, min(args.steps, 10))
     t0 = time.time()
-    f0.record(s2)
+    f0.record(gs[0].stream())
     for i in range(e2e_steps):
-        g2.set_source(host_in[i % nstills], rp)
-        g2.run(FE)
-    f1.record(s2)
+        gk = gs[i % NG]
+        if i >= NG:
+            gk.run(api.RUN_WAIT)          # frame i-NG has fully landed in host memory before its buffers are reused
+        gk.set_source(host_in[i % nstills], rp)
+        gk.run(FE)
+    for k in range(NG):
+        gs[k].run(api.RUN_WAIT)
+    t_wall_ms = (time.time() - t0) * 1e3
+    f1.record(gs[0].stream())
     f1.sync()
-    t_e2e_ms = max(f0.elapsed_ms(f1), (time.time() - t0) * 1e3)
+    t_e2e_ms = max(f0.elapsed_ms(f1), t_wall_ms)
     if world > 1:
         t = torch.tensor([t_e2e_ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e_ms = float(t.item())
-    checksum = float(np.frombuffer((api.C.c_float * 4).from_address(host_out), dtype=np.float32).sum())
+    checksum = float(np.frombuffer((api.C.c_float * 4).from_address(host_out[(e2e_steps - 1) % NG]), dtype=np.float32).sum())
 
     if rank != 0:
         if world > 1:

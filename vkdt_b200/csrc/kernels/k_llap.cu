@@ -16,10 +16,31 @@ struct llap_params_t { float sigma, shadows, hilights, clarity; };
 
 VKB_DEV float gamma_from_i(int i) { return (float)i / (NUM_GAMMA - 1.0f); }
 VKB_DEV int gamma_hi_from_v(float v)
-{
+{ // llap.glsl:17-22 without a loop of divisions: 1 + #{ i in 1..8 : i/9 <= v }, the i/9 fold to constants
   int hi = 1;
-  for(; hi < NUM_GAMMA - 1 && gamma_from_i(hi) <= v; hi++);
+#pragma unroll
+  for(int i = 1; i < NUM_GAMMA - 1; i++) hi += ((float)i / (NUM_GAMMA - 1.0f) <= v) ? 1 : 0;
   return hi;
+}
+// curve() with its two divisions by per-launch constants turned into multiplications by their reciprocals
+// (inv2s = 1/(2 sigma), invd = 1/(2 sigma^2/3)): <= 1 ulp of difference in t and in the exponent, the value is
+// rounded to f16 right after.  the level-0 stack costs 10 of these per input pixel, the divisions were a third of it.
+VKB_DEV float llap_curve_k(float x, float g, const llap_params_t &p, float inv2s, float invd)
+{
+  const float c = x - g;
+  float val;
+  const float ssigma = c > 0.0f ? p.sigma : -p.sigma;
+  const float shadhi = c > 0.0f ? p.shadows : p.hilights;
+  if(fabsf(c) > 2 * p.sigma) val = g + ssigma + shadhi * (c - ssigma);
+  else
+  {
+    const float t = clampf(fabsf(c) * inv2s, 0.0f, 1.0f);
+    const float t2 = t * t;
+    const float mt = 1.0f - t;
+    val = g + ssigma * 2.0f * mt * t + t2 * (ssigma + ssigma * shadhi);
+  }
+  val += p.clarity * c * __expf(-c * c * invd);
+  return val;
 }
 VKB_DEV float llap_curve(float x, float g, const llap_params_t &p)
 {
@@ -35,7 +56,8 @@ VKB_DEV float llap_curve(float x, float g, const llap_params_t &p)
     const float mt = 1.0f - t;
     val = g + ssigma * 2.0f * mt * t + t2 * (ssigma + ssigma * shadhi);
   }
-  val += p.clarity * c * expf(-c * c / (2.0f * p.sigma * p.sigma / 3.0f));
+  // the gaussian term is a few % of val at most: __expf's ~1e-6 relative error on it stays below an fp32 ulp of val
+  val += p.clarity * c * __expf(-c * c / (2.0f * p.sigma * p.sigma / 3.0f));
   return val;
 }
 VKB_DEV float llap_grey(float4 px)
@@ -53,6 +75,7 @@ __global__ void __launch_bounds__(256) k_llap_reduce0(const uint2 *__restrict__ 
   __shared__ __half tile[NL][R0_TH][R0_TW + 1];
   const int tx0 = blockIdx.x * 64 - 1, ty0 = blockIdx.y * 16 - 1;
   const int tid = threadIdx.y * 32 + threadIdx.x;
+  const float inv2s = 1.0f / (2.0f * p.sigma), invd = 1.0f / (2.0f * p.sigma * p.sigma / 3.0f);
   for(int t = tid; t < R0_TW * R0_TH; t += 256)
   {
     const int lx = t % R0_TW, ly = t / R0_TW;
@@ -60,7 +83,7 @@ __global__ void __launch_bounds__(256) k_llap_reduce0(const uint2 *__restrict__ 
     const int gx = big ? mirror1(tx0 + lx, iw) : mirrori(tx0 + lx, iw), gy = big ? mirror1(ty0 + ly, ih) : mirrori(ty0 + ly, ih);
     const float y = llap_grey(ld_rgba(in, iw, gx, gy));
 #pragma unroll
-    for(int g = 0; g < NUM_GAMMA; g++) tile[g][ly][lx] = __float2half_rn(llap_curve(y, gamma_from_i(g), p));
+    for(int g = 0; g < NUM_GAMMA; g++) tile[g][ly][lx] = __float2half_rn(llap_curve_k(y, gamma_from_i(g), p, inv2s, invd));
     tile[NUM_GAMMA][ly][lx] = __float2half_rn(y);
   }
   __syncthreads();

@@ -20,6 +20,33 @@ struct llap_params_t { float sigma, shadows, hilights, clarity; };
 struct llapfin_t { llap_params_t p; int first; int have_grade; int out_f32; grade_params_t grade; };
 
 VKB_DEV float gamma_from_i(int i) { return (float)i / (NUM_GAMMA - 1.0f); }
+// llap.glsl:17-22 gamma_hi_from_v without the loop of divisions: 1 + #{ i in 1..8 : i/9 <= v } (the i/9 are compile time constants)
+VKB_DEV int gamma_hi(float v)
+{
+  int hi = 1;
+#pragma unroll
+  for(int i = 1; i < NUM_GAMMA - 1; i++) hi += ((float)i / (NUM_GAMMA - 1.0f) <= v) ? 1 : 0;
+  return hi;
+}
+// curve() with the two divisions by per-launch constants turned into multiplications (1 ulp of difference in t and
+// in the exponent; the result is rounded to f16 right after).  k.x = 1/(2 sigma), k.y = 1/(2 sigma^2 / 3)
+VKB_DEV float llap_curve_k(float x, float g, const llap_params_t &p, float inv2s, float invd)
+{
+  const float c = x - g;
+  float val;
+  const float ssigma = c > 0.0f ? p.sigma : -p.sigma;
+  const float shadhi = c > 0.0f ? p.shadows : p.hilights;
+  if(fabsf(c) > 2 * p.sigma) val = g + ssigma + shadhi * (c - ssigma);
+  else
+  {
+    const float t = clampf(fabsf(c) * inv2s, 0.0f, 1.0f);
+    const float t2 = t * t;
+    const float mt = 1.0f - t;
+    val = g + ssigma * 2.0f * mt * t + t2 * (ssigma + ssigma * shadhi);
+  }
+  val += p.clarity * c * __expf(-c * c * invd);
+  return val;
+}
 VKB_DEV float llap_curve(float x, float g, const llap_params_t &p)
 { // llap/curve.comp:40-63
   const float c = x - g;
@@ -34,7 +61,8 @@ VKB_DEV float llap_curve(float x, float g, const llap_params_t &p)
     const float mt = 1.0f - t;
     val = g + ssigma * 2.0f * mt * t + t2 * (ssigma + ssigma * shadhi);
   }
-  val += p.clarity * c * expf(-c * c / (2.0f * p.sigma * p.sigma / 3.0f));
+  // the gaussian term is < 3% of val: __expf's 1e-6 relative error on it is below an fp32 ulp of val
+  val += p.clarity * c * __expf(-c * c / (2.0f * p.sigma * p.sigma / 3.0f));
   return val;
 }
 
@@ -102,6 +130,125 @@ __global__ void __launch_bounds__(256) k_llap_final2(const uint2 *__restrict__ i
   else st_rgba(reinterpret_cast<uint2 *>(outv), ow, x, y, make_float4(c.x, c.y, c.z, 1.0f));
 }
 
+// ---- 2x2 output pixels per thread ----
+// the four pixels (2k, 2k+1) x (2m, 2m+1) expand the same 5x5 coarse texels around (k, m); with the usual case of all
+// four picking the same pair of gamma layers one 5x5 window per plane serves four outputs, and the separable row sums
+// (even weights [1 1 2 1 1]/2, odd weights [0 2 1 1 2]/2) are shared between the two columns / rows.
+// only the gamma layers the CTA's pixels actually select (+ the collapsed coarse level) are staged in shared memory.
+#define F3_W 36
+#define F3_H 12
+VKB_DEV void expand4(const float (*T)[F3_W + 1], int lx, int ly, float &ee, float &oe, float &eo, float &oo)
+{ // ee: x even y even, oe: x odd y even, eo: x even y odd, oo: both odd
+  float he[5], ho[5];
+#pragma unroll
+  for(int r = 0; r < 5; r++)
+  {
+    const float *row = T[ly - 2 + r] + lx - 2;
+    const float t0 = row[0], t1 = row[1], t2 = row[2], t3 = row[3], t4 = row[4];
+    he[r] = 0.5f * (t0 + t1) + t2 + 0.5f * (t3 + t4);
+    ho[r] = t1 + 0.5f * (t2 + t3) + t4;
+  }
+  ee = (0.5f * (he[0] + he[1]) + he[2] + 0.5f * (he[3] + he[4])) / 9.0f;
+  oe = (0.5f * (ho[0] + ho[1]) + ho[2] + 0.5f * (ho[3] + ho[4])) / 9.0f;
+  eo = (he[1] + 0.5f * (he[2] + he[3]) + he[4]) / 9.0f;
+  oo = (ho[1] + 0.5f * (ho[2] + ho[3]) + ho[4]) / 9.0f;
+}
+
+template <bool F32, bool GRADE>
+__global__ void __launch_bounds__(256) k_llap_final4(const uint2 *__restrict__ in, const __half *__restrict__ coarse,
+    const __half *__restrict__ l1, int cw, int ch, void *__restrict__ outv, int ow, int oh, const __grid_constant__ llapfin_t P)
+{
+  __shared__ float tile[NL + 1][F3_H][F3_W + 1];
+  __shared__ int s_pmin, s_pmax;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  if(tid == 0) { s_pmin = NUM_GAMMA; s_pmax = 0; }
+  const int kx = blockIdx.x * 32 + threadIdx.x, ky = blockIdx.y * 8 + threadIdx.y;
+  const int cx0 = blockIdx.x * 32 - 2, cy0 = blockIdx.y * 8 - 2;
+  const size_t p1 = (size_t)cw * ch;
+  // 1) the four input pixels, their grey value and gamma bracket
+  float4 px[4]; float grey[4], v[4]; int hi[4];
+  int mylo = NUM_GAMMA, myhi = 0;
+#pragma unroll
+  for(int q = 0; q < 4; q++)
+  {
+    const int x = 2 * kx + (q & 1), y = 2 * ky + (q >> 1);
+    hi[q] = -1;
+    if(x < ow && y < oh)
+    {
+      px[q] = ld_rgba(in, ow, x, y);
+      grey[q] = lum2020(clampf(px[q].x, -1000.0f, 1000.0f), clampf(px[q].y, -1000.0f, 1000.0f), clampf(px[q].z, -1000.0f, 1000.0f));
+      v[q] = f16r(grey[q]);
+      const int h = gamma_hi(v[q]);
+      hi[q] = h;
+      mylo = min(mylo, h - 1); myhi = max(myhi, h);
+    }
+  }
+  __syncthreads();
+  mylo = __reduce_min_sync(0xffffffffu, mylo); myhi = __reduce_max_sync(0xffffffffu, myhi);
+  if(threadIdx.x == 0) { atomicMin(&s_pmin, mylo); atomicMax(&s_pmax, myhi); }
+  __syncthreads();
+  const int pmin = s_pmin, pmax = s_pmax;
+  // 2) stage the needed planes: gamma layers pmin..pmax and the coarse level (slot NL)
+  const bool big = cw >= 40 && ch >= 16;
+  const int nplanes = pmax >= pmin ? pmax - pmin + 2 : 0;
+  // each thread owns <= 2 texel positions of the 36x12 window; the mirrored offset is computed once and reused per plane
+#pragma unroll
+  for(int e = 0; e < 2; e++)
+  {
+    const int t = tid + e * 256;
+    if(t >= F3_H * F3_W) break;
+    const int r = t / F3_W, c = t - r * F3_W;
+    const int gx = big ? mirror1(cx0 + c, cw) : mirrori(cx0 + c, cw), gy = big ? mirror1(cy0 + r, ch) : mirrori(cy0 + r, ch);
+    const size_t off = (size_t)gy * cw + gx;
+    if(nplanes) tile[NL][r][c] = __half2float(__ldg((P.first ? l1 + NUM_GAMMA * p1 : coarse) + off));
+    for(int pl = pmin; pl <= pmax; pl++) tile[pl][r][c] = __half2float(__ldg(l1 + pl * p1 + off));
+  }
+  __syncthreads();
+  if(hi[0] < 0) return; // whole 2x2 outside the image
+  const float inv2s = 1.0f / (2.0f * P.p.sigma), invd = 1.0f / (2.0f * P.p.sigma * P.p.sigma / 3.0f);
+  const int lx = kx - cx0, ly = ky - cy0;
+  float res[4], e0[4], e1[4];
+  expand4(tile[NL], lx, ly, res[0], res[1], res[2], res[3]);
+  const bool same = (hi[1] < 0 || hi[1] == hi[0]) && (hi[2] < 0 || hi[2] == hi[0]) && (hi[3] < 0 || hi[3] == hi[0]);
+  if(same)
+  {
+    expand4(tile[hi[0] - 1], lx, ly, e0[0], e0[1], e0[2], e0[3]);
+    expand4(tile[hi[0]],     lx, ly, e1[0], e1[1], e1[2], e1[3]);
+  }
+  else
+  {
+#pragma unroll
+    for(int q = 0; q < 4; q++) if(hi[q] >= 0)
+    {
+      float t[4];
+      expand4(tile[hi[q] - 1], lx, ly, t[0], t[1], t[2], t[3]); e0[q] = t[q];
+      expand4(tile[hi[q]],     lx, ly, t[0], t[1], t[2], t[3]); e1[q] = t[q];
+    }
+  }
+#pragma unroll
+  for(int q = 0; q < 4; q++)
+  {
+    if(hi[q] < 0) continue;
+    const int x = 2 * kx + (q & 1), y = 2 * ky + (q >> 1);
+    const float glo = gamma_from_i(hi[q] - 1), ghi = gamma_from_i(hi[q]);
+    const float a = clampf(__fdividef(v[q] - glo, ghi - glo), 0.0f, 1.0f);
+    const float lap0 = f16r(llap_curve_k(grey[q], glo, P.p, inv2s, invd)) - e0[q];
+    const float lap1 = f16r(llap_curve_k(grey[q], ghi, P.p, inv2s, invd)) - e1[q];
+    float l = f16r(res[q] + lap0 * (1.0f - a) + lap1 * a);
+    const float yo = fmaxf(lum2020(px[q].x, px[q].y, px[q].z), 1e-8f);
+    if(l < yo) l = yo * __expf(l - yo);
+    const float ratio = __fdividef(l, yo); // nothing downstream but one f16/f32 store: 2 ulp is plenty
+    f3 c = { fmaxf(0.0f, px[q].x * ratio), fmaxf(0.0f, px[q].y * ratio), fmaxf(0.0f, px[q].z * ratio) };
+    if(GRADE)
+    {
+      c = { f16r(c.x), f16r(c.y), f16r(c.z) };
+      c = grade_px(c, P.grade);
+    }
+    if(F32) reinterpret_cast<float4 *>(outv)[(size_t)y * ow + x] = make_float4(c.x, c.y, c.z, 1.0f);
+    else st_rgba(reinterpret_cast<uint2 *>(outv), ow, x, y, make_float4(c.x, c.y, c.z, 1.0f));
+  }
+}
+
 // conn: [0] input rgba f16, [1] coarse y f16 (level 1 assembled; ignored when first), [2] level-1 stack x11, [3] output rgba f16|f32
 // push: { u32 first; u32 have_grade }.  params: llap params (16 B) followed by grade params (76 B) when have_grade
 static int launch_llapfin2(const vkb_launch_t *l)
@@ -122,8 +269,8 @@ static int launch_llapfin2(const vkb_launch_t *l)
     VKB_REQUIRE(l->params_size >= sizeof(llap_params_t) + sizeof(grade_params_t));
     memcpy(&P.grade, (const uint8_t *)l->params + sizeof(llap_params_t), sizeof(grade_params_t));
   }
-  const dim3 grid(vkb_cdiv(out->wd, 32), vkb_cdiv(out->ht, 8)), block(32, 8);
-#define GO(F, G) k_llap_final2<F, G><<<grid, block, 0, l->stream>>>((const uint2 *)in->data, (const __half *)coarse->data, \
+  const dim3 grid(vkb_cdiv(out->wd, 64), vkb_cdiv(out->ht, 16)), block(32, 8);
+#define GO(F, G) k_llap_final4<F, G><<<grid, block, 0, l->stream>>>((const uint2 *)in->data, (const __half *)coarse->data, \
       (const __half *)l1->data, l1->wd, l1->ht, out->data, out->wd, out->ht, P)
   if(P.out_f32) { if(P.have_grade) GO(true, true); else GO(true, false); }
   else          { if(P.have_grade) GO(false, true); else GO(false, false); }

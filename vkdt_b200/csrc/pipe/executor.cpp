@@ -484,7 +484,7 @@ int dt_graph_run(dt_graph_t *g, uint32_t run)
   for(const plan_source_t &s : p->source)
   {
     dt_module_t *mod = &g->module[s.modid];
-    const bool want = (run & VKB_RUN_UPLOAD_SOURCE) || (mod->flags & s_module_request_read_source);
+    const bool want = (run & VKB_RUN_UPLOAD_SOURCE) || ((run & VKB_RUN_RECORD_CMD_BUF) && (mod->flags & s_module_request_read_source));
     if(!want) continue;
     if(s.external)
     { // caller owned device memory: just repoint
@@ -555,7 +555,9 @@ int dt_graph_run(dt_graph_t *g, uint32_t run)
       }
     }
   }
-  if(run & (VKB_RUN_WAIT_DONE | VKB_RUN_DOWNLOAD_SINK))
+  // downloads into caller memory are asynchronous until a run carries WAIT_DONE (two graphs can then ping-pong:
+  // the D2H of one frame overlaps the upload + kernels of the next)
+  if(run & VKB_RUN_WAIT_DONE)
   {
     cudaError_t e = cudaStreamSynchronize(p->stream);
     if(e != cudaSuccess) return vkb_set_error(VKB_ERR_CUDA, "graph run failed: %s", cudaGetErrorString(e));
