@@ -171,8 +171,11 @@ static inline void o_store1(oimg_t *im, int x, int y, float v, int f16)
 }
 
 /* ---- glsl builtins ---- */
-static inline float o_min(float a, float b) { return a < b ? a : b; }   /* glsl min: b<a ? b : a; NaN handling not relied on */
-static inline float o_max(float a, float b) { return a > b ? a : b; }
+/* glsl leaves min/max with a NaN operand undefined; GPUs (and llvm's minnum/maxnum) return the non-NaN operand.
+ * it matters: evd2x2's sqrt() of a discriminant that rounds below zero yields NaN in flat regions, and the
+ * shaders' max(1e-9, exp(NaN)) / clamp(NaN, ..) then fall back to finite values (denoise/cov.glsl:116-133). */
+static inline float o_min(float a, float b) { return fminf(a, b); }
+static inline float o_max(float a, float b) { return fmaxf(a, b); }
 static inline float o_clamp(float x, float a, float b) { return o_min(o_max(x, a), b); }
 static inline float o_mix(float a, float b, float t) { return a * (1.0f - t) + b * t; }
 static inline float o_smoothstep(float e0, float e1, float x)

@@ -110,10 +110,10 @@ def test_cfg_params_and_errors():
     g.line("param:denoise:01:strength:0.4")
     raw = np.zeros((256, 256), np.uint16)
     g.set_source(raw.ctypes.data, api.raw_params(256, 256))
-    with pytest.raises(api.VkbError):   # wavelet kernels are registered only once built: until then this must fail loudly, not fall back
-        if ("denoise", "doub") in api.kernels():
-            raise api.VkbError(0, "kernels present")
-        g.plan()
+    text = g.plan()    # strength > 0 switches the module to the wavelet nodes (denoise/main.c:227-326)
+    for k in ("denoise_half", "denoise_downcov", "denoise_down", "denoise_assemble", "denoise_doub"):
+        assert k in text, k
+    assert text.count("denoise_down [") == 3 and "denoise_noop" not in text
 
 
 def test_unconnected_graph_is_an_error():

@@ -14,15 +14,17 @@ WB = (2.0, 1.0, 1.5)
 CAM = (0.8, 0.15, 0.05, 0.1, 0.85, 0.05, 0.02, 0.18, 0.8)
 
 
-def _oracle_cfg(O, w, h, llap=True, grade=True):
+def _oracle_cfg(O, w, h, llap=True, grade=True, strength=0.0, noise=(1.0, 1.0)):
     d = O.darkroom_defaults(w, h)
+    d.denoise.strength = strength
+    d.noise_a, d.noise_b = noise
     for k in range(3): d.whitebalance[k] = WB[k]
     for k in range(9): d.cam_to_rec2020[k] = CAM[k]
     d.enable_llap, d.enable_grade = int(llap), int(grade)
     return d
 
 
-def _run_graph(gpu, raw, src="i-raw", packed=False, extra=()):
+def _run_graph(gpu, raw, src="i-raw", packed=False, extra=(), noise=(1.0, 1.0)):
     h, w = raw.shape
     g = gpu.Graph(cfg_text=gpu.DARKROOM_CFG.format(src=src))
     for l in extra:
@@ -30,10 +32,10 @@ def _run_graph(gpu, raw, src="i-raw", packed=False, extra=()):
     if packed:
         words = synth.pack_bits_fast14(raw) if raw.size % 8 == 0 else synth.pack_bits(raw, 14)
         buf = np.zeros(words.size + 64, dtype=np.uint16); buf[:words.size] = words
-        g.set_source(buf.ctypes.data, gpu.raw_params(w, h, wb=WB, cam_to_rec2020=CAM, packed_bpp=14))
+        g.set_source(buf.ctypes.data, gpu.raw_params(w, h, wb=WB, cam_to_rec2020=CAM, packed_bpp=14, noise_a=noise[0], noise_b=noise[1]))
     else:
         buf = np.ascontiguousarray(raw)
-        g.set_source(buf.ctypes.data, gpu.raw_params(w, h, wb=WB, cam_to_rec2020=CAM))
+        g.set_source(buf.ctypes.data, gpu.raw_params(w, h, wb=WB, cam_to_rec2020=CAM, noise_a=noise[0], noise_b=noise[1]))
     g.set_sink_buffer(None, 0)           # size unknown before the first run: keep on device, then fetch
     g.run()
     ow, oh = g.sink_size()
@@ -61,6 +63,21 @@ def test_darkroom_end_to_end(gpu, oracle, dims, src, packed):
     assert p >= 60.0, p
     assert (err > 1e-3).mean() <= 1e-5 and err.max() <= 2e-3, (err.max(), float((err > 1e-3).mean()))
     assert (err > 5e-4).mean() < 2e-3
+
+
+@pytest.mark.parametrize("dims", [(512, 384), (644, 486)])
+def test_darkroom_with_wavelet_denoise(gpu, oracle, dims):
+    """BASELINE config 2: the full graph with denoise:strength 0.4 (noise profile a=100, b=2 of the synthetic sensor)."""
+    w, h = dims
+    raw = synth.mosaic(w, h, seed=13)
+    want = oracle.darkroom_run(_oracle_cfg(oracle, w, h, strength=0.4, noise=(100.0, 2.0)), raw)
+    got, g = _run_graph(gpu, raw, extra=("param:denoise:01:strength:0.4",), noise=(100.0, 2.0))
+    err = np.abs(got[..., :3] - want[..., :3])
+    p = psnr(got[..., :3], want[..., :3])
+    print("denoise on: max abs %.3g, psnr %.1f dB\n%s" % (err.max(), p, g.perf()))
+    assert "denoise_downcov" in g.perf() and "denoise_doub" in g.perf()
+    assert p >= 60.0, p
+    assert (err > 1e-3).mean() <= 1e-4 and err.max() <= 5e-3, (err.max(), float((err > 1e-3).mean()))
 
 
 def test_graph_without_display_fails(gpu):

@@ -285,3 +285,75 @@ def test_llap_module(gpu, oracle, dims, with_grade):
     got = to_host(plans.llap(gpu, to_dev_f16(a), w, h, (0.12, 1.0, 1.0, 0.2), grade=gbytes, out_f32=with_grade))
     err = np.abs(got[..., :3] - want[..., :3])
     assert err.max() < 2e-3 and psnr(got[..., :3], want[..., :3]) > 66.0, (err.max(), psnr(got[..., :3], want[..., :3]))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# wavelet denoise (denoise:strength > 0)
+def _denoise_push(kind, wb, black, white, crop, filters, na, nb, level=0, block=2):
+    b = [np.float32(black) / np.float32(65535.0)] * 4
+    w = [np.float32(white) / np.float32(65535.0)] * 4
+    head = fbits(*wb) + fbits(*b) + fbits(*w)
+    if kind == "half":
+        return head + ibits(*crop) + ubits(filters)
+    if kind == "down":
+        return head + ibits(0, 0, 0, 0) + fbits(na, nb) + ibits(level) + ubits(block)
+    if kind == "assemble":
+        return head + ibits(0, 0, 0, 0) + fbits(na, nb) + ubits(filters)
+    if kind == "doub":
+        return head + ibits(*crop) + ubits(filters) + fbits(na, nb) + ibits(0) + fbits(0, 0, 0, 0)
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("dims,na,nb", [((256, 192), 100.0, 2.0), ((260, 196), 1e-5, 1e-4)])
+def test_denoise_wavelet_kernels(gpu, oracle, dims, na, nb):
+    """kernel by kernel, each fed with the oracle's previous stage; the second case uses tiny noise parameters so that the
+    edge weights of down.comp:83-92 are not saturated."""
+    O = oracle
+    w, h = dims
+    raw = _raw(w, h, seed=9)
+    F = 0x5d5d5d5d
+    wb = (2.0, 1.0, 1.5, 1.0)
+    src = raw.astype(np.float32) / np.float32(65535.0)
+    b4 = O.f4(*([np.float32(2048) / np.float32(65535)] * 4)); w4 = O.f4(*([np.float32(15000) / np.float32(65535)] * 4))
+    dp = O.DenoiseParams(0.4, 0.6, 1.0, 0.0, (C.c_float * 4)(0, 0, 0, 0), 1)
+    par = bytes(dp)
+    hw, hh = w // 2, h // 2
+    I = gpu.image
+    d_raw = to_dev_u16(raw)
+    # half
+    half, hi_ = O.new_img(hh, hw, 4)
+    O.lib().o_denoise_half(C.byref(O.img(src)), C.byref(hi_), O.i4(0, 0, w, h), w4, C.c_uint32(F))
+    d_half = dev_f16(hh, hw, 4)
+    gpu.dispatch("denoise", "half", [I(d_raw, w, h, 1, "ui16"), I(d_half, hw, hh, 4, "f16")], _denoise_push("half", wb, 2048, 15000, (0, 0, w, h), F, na, nb), par)
+    assert f16_ulp_diff(to_host(d_half), half).max() == 0
+    # downcov
+    dn = [O.new_img(hh, hw, 4) for _ in range(4)]
+    cov, ci = O.new_img(hh, hw, 4)
+    O.lib().o_denoise_downcov(C.byref(hi_), C.byref(dn[0][1]), C.byref(ci))
+    d_dn0 = dev_f16(hh, hw, 4); d_cov = dev_f16(hh, hw, 4)
+    gpu.dispatch("denoise", "downcov", [I(to_dev_f16(half), hw, hh, 4, "f16"), I(d_dn0, hw, hh, 4, "f16"), I(d_cov, hw, hh, 4, "f16")],
+                 _denoise_push("down", wb, 2048, 15000, None, F, na, nb, 0, 2), par)
+    assert_close_mixed(to_host(d_cov), cov, 4, 1e-4, 0.90, "denoise downcov cov", max_outliers=1e-3, hard_atol=1.0)
+    assert_close_mixed(to_host(d_dn0), dn[0][0], 3, 1e-5, 0.90, "denoise downcov", max_outliers=1e-3, hard_atol=5e-3)
+    # down levels 1..3
+    for lv in range(1, 4):
+        O.lib().o_denoise_down(C.byref(dn[lv - 1][1]), C.byref(dn[lv][1]), C.byref(dp), b4, w4, C.c_float(na), C.c_float(nb), lv, C.c_uint32(2))
+        d_out = dev_f16(hh, hw, 4)
+        gpu.dispatch("denoise", "down", [I(to_dev_f16(dn[lv - 1][0]), hw, hh, 4, "f16"), I(d_out, hw, hh, 4, "f16")],
+                     _denoise_push("down", wb, 2048, 15000, None, F, na, nb, lv, 2), par)
+        assert_close_mixed(to_host(d_out), dn[lv][0], 2, 1e-6, 0.95, "denoise down level %d" % lv, max_outliers=1e-4)
+    # assemble
+    asm, ai = O.new_img(hh, hw, 4)
+    O.lib().o_denoise_assemble(C.byref(hi_), C.byref(dn[0][1]), C.byref(dn[1][1]), C.byref(dn[2][1]), C.byref(dn[3][1]), C.byref(ai), C.byref(dp),
+                               O.f4(*wb), b4, w4, C.c_float(na), C.c_float(nb), C.c_uint32(F))
+    d_asm = dev_f16(hh, hw, 4)
+    gpu.dispatch("denoise", "assemble", [I(to_dev_f16(half), hw, hh, 4, "f16")] + [I(to_dev_f16(dn[k][0]), hw, hh, 4, "f16") for k in range(4)] +
+                 [I(d_asm, hw, hh, 4, "f16")], _denoise_push("assemble", wb, 2048, 15000, None, F, na, nb), par)
+    assert_close_mixed(to_host(d_asm), asm, 3, 1e-5, 0.90, "denoise assemble", max_outliers=1e-4)
+    # doub
+    out, oi = O.new_img(h, w, 1)
+    O.lib().o_denoise_doub(C.byref(O.img(src)), C.byref(ai), C.byref(hi_), C.byref(oi), C.byref(dp), O.i4(0, 0, w, h), b4, w4, C.c_float(na), C.c_float(nb), C.c_uint32(F))
+    d_o = dev_f16(h, w)
+    gpu.dispatch("denoise", "doub", [I(d_raw, w, h, 1, "ui16"), I(to_dev_f16(asm), hw, hh, 4, "f16"), I(to_dev_f16(half), hw, hh, 4, "f16"),
+                                     I(d_o, w, h, 1, "f16")], _denoise_push("doub", wb, 2048, 15000, (0, 0, w, h), F, na, nb), par)
+    assert_close_mixed(to_host(d_o), out, 2, 1e-6, 0.95, "denoise doub", max_outliers=1e-4)

@@ -1,0 +1,381 @@
+// noise-profile driven wavelet denoise on the mosaic (denoise:strength > 0).
+// replaces src/pipe/modules/denoise/{half,downcov,down,assemble,doub}.comp, cov.glsl, noise.glsl
+// (wired by denoise/main.c:227-326): half-size rgb -> structure-tensor guided blur (level 0) -> three edge-aware
+// "flower" levels written in the quadrant-swizzled layout that turns the same taps into an a-trous wavelet ->
+// soft-shrunk reassembly -> per-CFA-colour residual shrink on the full-resolution mosaic.
+// all intermediates live at 1/block^2 resolution; the full-res `doub` is the only HBM-heavy kernel (2+2 B/px + coarse reads).
+// compiled with --fmad=false: downcov picks between two covariance estimates by comparing determinants and rejects
+// hot pixels by a threshold — discontinuous decisions that must fall like in the fp32 restatement.
+#include "common.cuh"
+#include <string.h>
+
+struct denoise_params_t { float strength, luma, detail, pad; float edges[4]; int gainmap; };      // denoise/params
+struct dn_push_half_t { float wb[4], black[4], white[4]; int32_t crop[4]; uint32_t filters; };     // main.c:284-289
+struct dn_push_down_t { float wb[4], black[4], white[4]; int32_t crop[4]; float noise_a, noise_b; int32_t level; uint32_t block; }; // :244-253
+struct dn_push_asm_t  { float wb[4], black[4], white[4]; int32_t crop[4]; float noise_a, noise_b; uint32_t filters; };             // :266-274
+struct dn_push_doub_t { float wb[4], black[4], white[4]; int32_t crop[4]; uint32_t filters; float noise_a, noise_b; int32_t gainmap; float map_os[4]; }; // :301-308
+
+// noise.glsl:1-11
+VKB_DEV void noise_sigma(float a, float b, float black, float white, const float *edges, float val, float *sig)
+{
+  const float s = sqrtf(a + fmaxf(0.0f, (val - black) / (white - black)) * b);
+#pragma unroll
+  for(int k = 0; k < 3; k++) sig[k] = clampf(exp2f(12.0f * edges[k] + edges[3]) * s, 1e-3f, 1e3f);
+}
+VKB_DEV void swizzle(int x, int y, int w, int h, int &ox, int &oy)
+{ // downcov.comp:52-53, down.comp:103-104
+  ox = x / 2 + ((x & 1) * (w + 1)) / 2;
+  oy = y / 2 + ((y & 1) * (h + 1)) / 2;
+}
+
+// ---- half: cfa block -> rgb (half.comp:24-74); input is the ui16 source sampled as UNORM ----
+__global__ void __launch_bounds__(256) k_denoise_half(const uint16_t *__restrict__ in, int iw, int ih,
+    uint2 *__restrict__ out, int ow, int oh, int cx, int cy, float white, int xtrans)
+{
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if(x >= ow || y >= oh) return;
+  float4 rgba;
+#define RAW(X, Y) ((float)__ldg(in + (size_t)clampi((Y), 0, ih - 1) * iw + clampi((X), 0, iw - 1)) / 65535.0f)
+  if(xtrans)
+  {
+    float c[9];
+#pragma unroll
+    for(int i = 0; i < 3; i++)
+#pragma unroll
+      for(int j = 0; j < 3; j++) c[3 * i + j] = RAW(cx + 3 * x + i, cy + 3 * y + j);
+    const float col0 = (c[1] + c[7]) * 0.5f, col1 = (c[3] + c[5]) * 0.5f;
+    if(((x + y + cx + cy) & 1) > 0) { rgba.x = col0; rgba.z = col1; }
+    else                            { rgba.z = col0; rgba.x = col1; }
+    rgba.y = (c[0] + c[2] + c[4] + c[6] + c[8]) * 1.0f / 5.0f;
+    rgba.w = 1.0f;
+  }
+  else
+  { // textureGather at the block centre: x=(0,1) y=(1,1) z=(1,0) w=(0,0), mirrored repeat
+    const int x0 = mirrori(cx + 2 * x, iw), x1 = mirrori(cx + 2 * x + 1, iw), y0 = mirrori(cy + 2 * y, ih), y1 = mirrori(cy + 2 * y + 1, ih);
+    float gx = (float)__ldg(in + (size_t)y1 * iw + x0) / 65535.0f, gy = (float)__ldg(in + (size_t)y1 * iw + x1) / 65535.0f;
+    float gz = (float)__ldg(in + (size_t)y0 * iw + x1) / 65535.0f, gw = (float)__ldg(in + (size_t)y0 * iw + x0) / 65535.0f;
+    if(gx >= white) gx = gz;
+    if(gz >= white) gz = gx;
+    rgba = make_float4(gw, (gx + gz) / 2.0f, gy, 1.0f);
+  }
+#undef RAW
+  st_rgba(out, ow, x, y, rgba);
+}
+
+// ---- downcov: level 0, structure tensor guided blur (downcov.comp:41-62, cov.glsl:21-138) ----
+__global__ void __launch_bounds__(128) k_denoise_downcov(const uint2 *__restrict__ in, int w, int h,
+    uint2 *__restrict__ out, uint2 *__restrict__ covimg)
+{
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 4 + threadIdx.y;
+  if(x >= w || y >= h) return;
+  float lum[25];
+  int xi[5], yi[5];
+#pragma unroll
+  for(int k = 0; k < 5; k++) { xi[k] = mirrori(x - 2 + k, w); yi[k] = mirrori(y - 2 + k, h); }
+  float mwx = 0, mwy = 0, mbx = 0, mby = 0, smw = 0, smb = 0;
+#pragma unroll
+  for(int j = 0; j < 5; j++)
+#pragma unroll
+    for(int i = 0; i < 5; i++)
+    {
+      const float4 t = ld_rgba(in, w, xi[i], yi[j]);
+      const float px = lum2020(t.x, t.y, t.z);
+      lum[5 * j + i] = px;
+      const float fi = (float)(i - 2), fj = (float)(j - 2);
+      mwx += fi * px * 1.0f; mwy += fj * px * 1.0f;
+      smw += px * 1.0f;
+      mbx += fi / px * 1.0f; mby += fj / px * 1.0f;
+      smb += 1.0f / px * 1.0f;
+    }
+  mwx /= smw; mwy /= smw; mbx /= smb; mby /= smb;
+  float Sw0 = 0, Sw1 = 0, Sw2 = 0, Sw3 = 0, Sb0 = 0, Sb1 = 0, Sb2 = 0, Sb3 = 0, sw = 0, sb = 0, mean_b = 0;
+#pragma unroll
+  for(int j = 0; j < 5; j++)
+#pragma unroll
+    for(int i = 0; i < 5; i++)
+    {
+      const float px = lum[5 * j + i];
+      mean_b += px / 25.0f;
+      float p2 = px * px * 1.0f;
+      float p0 = (float)(i - 2) - mwx, p1 = (float)(j - 2) - mwy;
+      Sw0 += p2 * p0 * p0; Sw1 += p2 * p0 * p1; Sw2 += p2 * p1 * p0; Sw3 += p2 * p1 * p1;
+      sw += p2;
+      p0 = (float)(i - 2) - mbx; p1 = (float)(j - 2) - mby;
+      p2 = 1.0f / (px * px) * 1.0f;
+      Sb0 += p2 * p0 * p0; Sb1 += p2 * p0 * p1; Sb2 += p2 * p1 * p0; Sb3 += p2 * p1 * p1;
+      sb += p2;
+    }
+  Sw0 /= sw; Sw1 /= sw; Sw2 /= sw; Sw3 /= sw;
+  Sb0 /= sb; Sb1 /= sb; Sb2 /= sb; Sb3 /= sb;
+  const bool usew = (Sw0 * Sw3 - Sw1 * Sw2) < (Sb0 * Sb3 - Sb1 * Sb2);
+  float e0, e1, v0x, v0y, v1x, v1y;
+  evd2x2(usew ? Sw0 : Sb0, usew ? Sw2 : Sb2, usew ? Sw3 : Sb3, e0, e1, v0x, v0y, v1x, v1y);
+  e1 *= 0.05f;
+  e0 = clampf(e0, 0.01f, 25.0f); e1 = clampf(e1, 0.01f, 25.0f);
+  st_rgba(covimg, w, x, y, make_float4(e0, e1, v0x, v0y));
+  float r = 0, g = 0, b = 0, wt = 0;
+#pragma unroll
+  for(int j = 0; j < 5; j++)
+#pragma unroll
+    for(int i = 0; i < 5; i++)
+    {
+      const float4 t = ld_rgba(in, w, xi[i], yi[j]);
+      if(t.x > 2.0f * mean_b) continue; // hot pixels
+      const float fi = (float)(i - 2), fj = (float)(j - 2);
+      const float q0 = fi * v0x + fj * v0y, q1 = fi * v1x + fj * v1y;
+      const float wgt = fmaxf(1e-9f, expf(-0.5f * (q0 / e0 * q0 + q1 / e1 * q1)));
+      r += wgt * t.x; g += wgt * t.y; b += wgt * t.z;
+      wt += wgt;
+    }
+  const float iw_ = fmaxf(wt, 1e-8f);
+  float edge = clampf(75.0f * fmaxf(0.0f, e1 - 0.09f), 0.0f, 1.0f);
+  edge = smoothstepf(0.4f, 0.75f, edge);
+  edge = clampf(0.02f + edge, 0.0f, 1.0f);
+  int ox, oy; swizzle(x, y, w, h, ox, oy);
+  st_rgba(out, w, ox, oy, make_float4(r / iw_, g / iw_, b / iw_, edge));
+}
+
+VKB_DEV float gamma08(float f) { return f < 0.0f ? f : powf(f, 0.8f); } // feeds 1/sigma-scaled differences: keep full accuracy
+
+// ---- down: levels 1..3, 5 tap flower with edge stopping (down.comp:59-107) ----
+__global__ void __launch_bounds__(256) k_denoise_down(const uint2 *__restrict__ in, int w, int h, uint2 *__restrict__ out,
+    denoise_params_t p, float black, float white, float noise_a, float noise_b, float lv, float blk)
+{
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if(x >= w || y >= h) return;
+  const float t = 0.2f;
+  const float4 c0 = ld_rgba(in, w, x, y);
+  float sigma[3], sum[3], wgt[3], wc[3], g0[3];
+  noise_sigma(noise_a, noise_b, black, white, p.edges, c0.x, sigma);
+  const float cc[3] = { c0.x, c0.y, c0.z };
+#pragma unroll
+  for(int k = 0; k < 3; k++)
+  {
+    sum[k] = t * cc[k]; wgt[k] = t;
+    sigma[k] = lv * sigma[k] / blk;
+    wc[k] = 1.0f / sigma[k];
+    g0[k] = gamma08(cc[k]);
+  }
+  // taps at (+1.2,+0.4) (-1.2,-0.4) (+0.4,-1.2) (-0.4,+1.2) from the texel centre: base texel and bilinear fraction
+  const int   bx[4] = { x + 1, x - 2, x,     x - 1 }, by[4] = { y,    y - 1, y - 2, y + 1 };
+  const float ax[4] = { 0.2f,  0.8f,  0.4f,  0.6f  }, ay[4] = { 0.4f, 0.6f,  0.8f,  0.2f  };
+#pragma unroll
+  for(int o = 0; o < 4; o++)
+  {
+    const float4 col = bilin_rgba(in, w, h, bx[o], by[o], ax[o], ay[o]);
+    const float c[3] = { col.x, col.y, col.z };
+#pragma unroll
+    for(int k = 0; k < 3; k++)
+    {
+      const float e = clampf(1.0f - 0.5f * (wc[k] * fabsf(gamma08(c[k]) - g0[k])), 0.0f, 1.0f);
+      const float ww = e * (1.0f - t) / 4.0f;
+      sum[k] += ww * c[k];
+      wgt[k] += ww;
+    }
+  }
+  int ox, oy; swizzle(x, y, w, h, ox, oy);
+  st_rgba(out, w, ox, oy, make_float4(sum[0] / wgt[0], sum[1] / wgt[1], sum[2] / wgt[2], 1.0f));
+}
+
+struct asm_consts_t { float rgb_to_yuv[9], yuv_to_rgb[9]; float wb[3], black[3], white[3]; float noise_a, noise_b, blk, thrs0; };
+
+// ---- assemble: wavelet shrinkage over the 4 detail bands (assemble.comp:43-165) ----
+__global__ void __launch_bounds__(256) k_denoise_assemble(const uint2 *__restrict__ s0, const uint2 *__restrict__ s1, const uint2 *__restrict__ s2,
+    const uint2 *__restrict__ s3, const uint2 *__restrict__ s4, uint2 *__restrict__ out, int w, int h,
+    const __grid_constant__ denoise_params_t p, const __grid_constant__ asm_consts_t K)
+{
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if(x >= w || y >= h) return;
+  const int szx = w + 1, szy = h + 1;
+  const float4 orig = ld_rgba(s0, w, x, y);
+  float d[5][3] = { { orig.x, orig.y, orig.z } };
+  int ex = x, ey = y;
+  const uint2 *s[5] = { s0, s1, s2, s3, s4 };
+#pragma unroll
+  for(int l = 1; l <= 4; l++)
+  {
+    ex = ex / 2 + ((ex & 1) * szx) / 2;
+    ey = ey / 2 + ((ey & 1) * szy) / 2;
+    const float4 v = ld_rgba_clamp(s[l], w, h, ex, ey);
+    d[l][0] = v.x; d[l][1] = v.y; d[l][2] = v.z;
+  }
+  float sigma[3];
+  noise_sigma(K.noise_a, K.noise_b, K.black[1], K.white[1], p.edges, fmaxf(d[2][0], 0.0f), sigma);
+  const float bb[4] = { 0.7000f / K.blk, 0.4900f / K.blk, 0.3430f / K.blk, 0.2401f / K.blk };
+  float down4[3] = { d[4][0], d[4][1], d[4][2] }, len[4];
+#pragma unroll
+  for(int l = 0; l < 4; l++)
+  {
+#pragma unroll
+    for(int k = 0; k < 3; k++) d[l][k] = (d[l][k] - d[l + 1][k]) / (sigma[k] * bb[l]);
+    len[l] = sqrtf(d[l][0] * d[l][0] + d[l][1] * d[l][1] + d[l][2] * d[l][2]);
+  }
+  const float slope = ((len[3] - len[0]) / 3.0f + (len[2] - len[1]) / 1.0f + (len[1] - len[0]) / 1.0f
+      + (len[3] - len[2]) / 1.0f + (len[2] - len[0]) / 2.0f + (len[3] - len[1]) / 2.0f) / 6.0f;
+  float test = fmaxf(0.0f, -slope);
+  test = fmaxf(0.0f, 1.0f - test);
+  test = powf(test, 16.0f);
+  test = clampf(1.5f * test, 0.0f, 1.0f);
+#pragma unroll
+  for(int l = 3; l >= 0; l--)
+  {
+    const float thrs = fabsf(d[l][0]) > 10.0f ? 10000.0f : K.thrs0;
+#pragma unroll
+    for(int k = 0; k < 3; k++)
+    {
+      const float a = fabsf(d[l][k]);
+      const float tt = fminf(1.0f, a / (2.0f * thrs));
+      down4[k] += sigma[k] * bb[l] * signf(d[l][k]) * mixf(fmaxf(a - thrs, 0.0f), a, tt);
+    }
+  }
+  float v[3], vo[3], yuv[3], yuvo[3], rgb[3];
+  const float og[3] = { orig.x, orig.y, orig.z };
+#pragma unroll
+  for(int k = 0; k < 3; k++)
+  {
+    v[k]  = (down4[k] - K.black[k]) / (K.white[k] - K.black[k]) * K.wb[k];
+    vo[k] = (og[k]    - K.black[k]) / (K.white[k] - K.black[k]) * K.wb[k];
+  }
+#pragma unroll
+  for(int j = 0; j < 3; j++)
+  {
+    yuv[j]  = K.rgb_to_yuv[3 * j] * v[0]  + K.rgb_to_yuv[3 * j + 1] * v[1]  + K.rgb_to_yuv[3 * j + 2] * v[2];
+    yuvo[j] = K.rgb_to_yuv[3 * j] * vo[0] + K.rgb_to_yuv[3 * j + 1] * vo[1] + K.rgb_to_yuv[3 * j + 2] * vo[2];
+  }
+  yuv[0] = mixf(yuvo[0], yuv[0], p.luma);
+#pragma unroll
+  for(int j = 0; j < 3; j++) rgb[j] = K.yuv_to_rgb[3 * j] * yuv[0] + K.yuv_to_rgb[3 * j + 1] * yuv[1] + K.yuv_to_rgb[3 * j + 2] * yuv[2];
+  st_rgba(out, w, x, y, make_float4(rgb[0] / K.wb[0] * (K.white[0] - K.black[0]) + K.black[0],
+                                    rgb[1] / K.wb[1] * (K.white[1] - K.black[1]) + K.black[1],
+                                    rgb[2] / K.wb[2] * (K.white[2] - K.black[2]) + K.black[2], test));
+}
+
+// ---- doub: per-colour residual shrink on the full resolution mosaic (doub.comp:35-115) ----
+__global__ void __launch_bounds__(256) k_denoise_doub(const uint16_t *__restrict__ in, int iw, int ih,
+    const uint2 *__restrict__ crs0, const uint2 *__restrict__ crs1, int cw, int ch, __half *__restrict__ out, int ow, int oh,
+    const __grid_constant__ denoise_params_t p, const __grid_constant__ dn_push_doub_t P)
+{
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if(x >= ow || y >= oh) return;
+  // texture(img_crs, (ipos+0.5)/imageSize(out)): ideal sampler, coordinates in double
+  const double ux = ((double)x + 0.5) / (double)ow * (double)cw - 0.5, uy = ((double)y + 0.5) / (double)oh * (double)ch - 0.5;
+  const double fx = floor(ux), fy = floor(uy);
+  const float ax = (float)(ux - fx), ay = (float)(uy - fy);
+  const float4 upsm = bilin_rgba(crs0, cw, ch, (int)fx, (int)fy, ax, ay);
+  const float4 down = bilin_rgba(crs1, cw, ch, (int)fx, (int)fy, ax, ay);
+  float black = P.black[1], white = P.white[1], crs = upsm.y, crs1v = down.y;
+  float T = 0.5f * p.strength * upsm.w, blendw = p.luma;
+  const int xt = P.filters == 9;
+  const int col = xt ? xtrans_colour(x, y) : bayer_colour(x, y);
+  if(col != 1)
+  {
+    black = col == 0 ? P.black[0] : P.black[2]; white = col == 0 ? P.white[0] : P.white[2];
+    crs = col == 0 ? upsm.x : upsm.z; crs1v = col == 0 ? down.x : down.z; blendw = 1.0f;
+    if(xt) T /= fmaxf(1e-4f, upsm.w);
+  }
+  float sigma[3];
+  noise_sigma(P.noise_a, P.noise_b, black, white, p.edges, crs, sigma);
+  float val = (float)__ldg(in + (size_t)mirrori(y + P.crop[1], ih) * iw + mirrori(x + P.crop[0], iw)) / 65535.0f;
+  blendw = 0.5f * (blendw + 1.0f);
+  if(val < white)
+  {
+    const float wav = (val - crs1v) / fmaxf(sigma[0] + sigma[2], 1e-8f);
+    const float tt = fminf(1.0f, wav / fmaxf(2.0f * T, 1e-8f));
+    float uw = powf(fminf(1.0f, 1.0f * upsm.w), 4.0f);
+    uw = 1.0f - (1.0f - uw) * p.detail;
+    val = mixf(val, fmaxf(0.0f, crs + sigma[1] * signf(wav) * mixf(fmaxf(0.0f, fabsf(wav) - T), fabsf(wav), tt)), uw * blendw);
+  }
+  val = fmaxf(0.0f, (val - black) / (white - black));
+  out[(size_t)y * ow + x] = __float2half_rn(val);
+}
+
+static inline dim3 grid2d(unsigned w, unsigned h, unsigned by = 8) { return dim3(vkb_cdiv(w, 32), vkb_cdiv(h, by)); }
+static const dim3 blk2d(32, 8);
+
+// conn: [0] input ui16 raw, [1] output rgba f16 (1/block res)
+static int launch_half(const vkb_launch_t *l)
+{
+  VKB_REQUIRE(l->num_conn >= 2 && l->push_size >= sizeof(dn_push_half_t));
+  const dn_push_half_t *pc = (const dn_push_half_t *)l->push;
+  const vkb_image_t *in = l->conn, *out = l->conn + 1;
+  VKB_REQUIRE(in->format == VKB_TOKEN_UI16 && in->chan == 1 && out->chan == 4 && out->format == VKB_TOKEN_F16);
+  k_denoise_half<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint16_t *)in->data, in->wd, in->ht, (uint2 *)out->data,
+      out->wd, out->ht, pc->crop[0], pc->crop[1], pc->white[1], pc->filters == 9);
+  VKB_CHECK_LAUNCH();
+  return VKB_OK;
+}
+VKB_REGISTER("denoise", "half", launch_half);
+
+// conn: [0] input rgba f16, [1] output rgba f16 (swizzled), [2] cov rgba f16
+static int launch_downcov(const vkb_launch_t *l)
+{
+  VKB_REQUIRE(l->num_conn >= 3);
+  const vkb_image_t *in = l->conn, *out = l->conn + 1, *cov = l->conn + 2;
+  VKB_REQUIRE(in->chan == 4 && out->chan == 4 && cov->chan == 4 && in->wd == out->wd && in->ht == out->ht && cov->wd == in->wd);
+  k_denoise_downcov<<<grid2d(out->wd, out->ht, 4), dim3(32, 4), 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, (uint2 *)out->data, (uint2 *)cov->data);
+  VKB_CHECK_LAUNCH();
+  return VKB_OK;
+}
+VKB_REGISTER("denoise", "downcov", launch_downcov);
+
+// conn: [0] input rgba f16 (swizzled previous level), [1] output rgba f16
+static int launch_down(const vkb_launch_t *l)
+{
+  VKB_REQUIRE(l->num_conn >= 2 && l->push_size >= sizeof(dn_push_down_t) && l->params_size >= sizeof(denoise_params_t) - 4);
+  const dn_push_down_t *pc = (const dn_push_down_t *)l->push;
+  const vkb_image_t *in = l->conn, *out = l->conn + 1;
+  VKB_REQUIRE(in->chan == 4 && out->chan == 4 && in->wd == out->wd && in->ht == out->ht);
+  VKB_REQUIRE(pc->level >= 0); // the level < 0 branch (response()) is dead in the reference wiring
+  denoise_params_t p; memset(&p, 0, sizeof(p)); memcpy(&p, l->params, l->params_size < sizeof(p) ? l->params_size : sizeof(p));
+  const float blk = pc->block == 3 ? 2.23607f : (pc->block == 2 ? 1.414213f : 1.0f);
+  k_denoise_down<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, (uint2 *)out->data,
+      p, pc->black[1], pc->white[1], pc->noise_a, pc->noise_b, powf(0.7f, (float)pc->level), blk);
+  VKB_CHECK_LAUNCH();
+  return VKB_OK;
+}
+VKB_REGISTER("denoise", "down", launch_down);
+
+static void mat3mul(const float *A, const float *B, float *C)
+{
+  for(int j = 0; j < 3; j++) for(int i = 0; i < 3; i++) C[3 * j + i] = A[3 * j + 0] * B[0 + i] + A[3 * j + 1] * B[3 + i] + A[3 * j + 2] * B[6 + i];
+}
+// conn: [0..4] s0..s4 rgba f16, [5] output rgba f16
+static int launch_assemble(const vkb_launch_t *l)
+{
+  VKB_REQUIRE(l->num_conn >= 6 && l->push_size >= sizeof(dn_push_asm_t) && l->params_size >= sizeof(denoise_params_t) - 4);
+  const dn_push_asm_t *pc = (const dn_push_asm_t *)l->push;
+  const vkb_image_t *c = l->conn, *out = l->conn + 5;
+  for(int k = 0; k < 5; k++) VKB_REQUIRE(c[k].chan == 4 && c[k].wd == out->wd && c[k].ht == out->ht);
+  denoise_params_t p; memset(&p, 0, sizeof(p)); memcpy(&p, l->params, l->params_size < sizeof(p) ? l->params_size : sizeof(p));
+  static const float rec709_to_yuv[9] = {0.299f, 0.587f, 0.114f, -0.147f, -0.289f, 0.436f, 0.615f, -0.515f, -0.100f};
+  static const float yuv_to_rec709[9] = {1.0f, -3.94570707e-05f, 1.13982797f, 1.0f, -3.94610164e-01f, -5.80500316e-01f, 1.0f, 2.03199968f, -4.81376263e-04f};
+  static const float rec2020_to_rec709[9] = {1.66022677f, -0.58754761f, -0.07283825f, -0.12455334f, 1.13292605f, -0.00834963f, -0.01815514f, -0.10060303f, 1.11899817f};
+  static const float rec709_to_rec2020[9] = {0.62750375f, 0.32927542f, 0.04330266f, 0.06910828f, 0.91951916f, 0.0113596f, 0.01639406f, 0.08801125f, 0.89538035f};
+  asm_consts_t K;
+  mat3mul(rec709_to_yuv, rec2020_to_rec709, K.rgb_to_yuv);
+  mat3mul(rec709_to_rec2020, yuv_to_rec709, K.yuv_to_rgb);
+  for(int k = 0; k < 3; k++) { K.wb[k] = pc->wb[k]; K.black[k] = pc->black[k]; K.white[k] = pc->white[k]; }
+  K.noise_a = pc->noise_a; K.noise_b = pc->noise_b;
+  K.blk = pc->filters == 0u ? 1.0f : (pc->filters == 9u ? 2.23607f : 1.414213f);
+  K.thrs0 = powf(p.strength, 4.0f);
+  k_denoise_assemble<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint2 *)c[0].data, (const uint2 *)c[1].data, (const uint2 *)c[2].data,
+      (const uint2 *)c[3].data, (const uint2 *)c[4].data, (uint2 *)out->data, out->wd, out->ht, p, K);
+  VKB_CHECK_LAUNCH();
+  return VKB_OK;
+}
+VKB_REGISTER("denoise", "assemble", launch_assemble);
+
+// conn: [0] orig ui16 raw, [1] crs0 (assembled) rgba f16, [2] crs1 (half) rgba f16, [3] output mosaic f16, [4] gainmap (ignored)
+static int launch_doub(const vkb_launch_t *l)
+{
+  VKB_REQUIRE(l->num_conn >= 4 && l->push_size >= sizeof(dn_push_doub_t) && l->params_size >= sizeof(denoise_params_t) - 4);
+  const vkb_image_t *in = l->conn, *c0 = l->conn + 1, *c1 = l->conn + 2, *out = l->conn + 3;
+  VKB_REQUIRE(in->format == VKB_TOKEN_UI16 && c0->chan == 4 && c1->chan == 4 && c0->wd == c1->wd && out->chan == 1 && out->format == VKB_TOKEN_F16);
+  denoise_params_t p; memset(&p, 0, sizeof(p)); memcpy(&p, l->params, l->params_size < sizeof(p) ? l->params_size : sizeof(p));
+  dn_push_doub_t P; memcpy(&P, l->push, sizeof(P));
+  k_denoise_doub<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint16_t *)in->data, in->wd, in->ht, (const uint2 *)c0->data,
+      (const uint2 *)c1->data, c0->wd, c0->ht, (__half *)out->data, out->wd, out->ht, p, P);
+  VKB_CHECK_LAUNCH();
+  return VKB_OK;
+}
+VKB_REGISTER("denoise", "doub", launch_doub);
