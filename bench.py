@@ -122,7 +122,7 @@ def main():
         # the reference's own CPU-side implementation of the path = the oracle port (vkdt-cli needs vulkan + glslang: absent)
         if rank != 0:
             return 0
-        strength = args.denoise if args.denoise is not None else 0.0
+        strength = args.denoise if args.denoise is not None else 0.4
         sample = (2376, 1584)  # 1/16 of the 61 MP frame, same graph
         rate, dt, cores = cpu_reference_rate(sample, max(1, min(args.steps, 5)), max(1, min(args.warmup, 1)), strength)
         print(json.dumps({

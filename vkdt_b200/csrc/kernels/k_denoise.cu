@@ -82,10 +82,12 @@ __global__ void __launch_bounds__(128) k_denoise_downcov(const uint2 *__restrict
       const float px = lum2020(t.x, t.y, t.z);
       lum[5 * j + i] = px;
       const float fi = (float)(i - 2), fj = (float)(j - 2);
-      mwx += fi * px * 1.0f; mwy += fj * px * 1.0f;
-      smw += px * 1.0f;
-      mbx += fi / px * 1.0f; mby += fj / px * 1.0f;
-      smb += 1.0f / px * 1.0f;
+      mwx += fi * px; mwy += fj * px;
+      smw += px;
+      // fi / px == fi * (1 / px) bit for bit when fi is 0, +-1 or +-2: scaling a correctly rounded quotient by a power of two is exact
+      const float rcp = 1.0f / px;
+      mbx += fi * rcp; mby += fj * rcp;
+      smb += rcp;
     }
   mwx /= smw; mwy /= smw; mbx /= smb; mby /= smb;
   float Sw0 = 0, Sw1 = 0, Sw2 = 0, Sw3 = 0, Sb0 = 0, Sb1 = 0, Sb2 = 0, Sb3 = 0, sw = 0, sb = 0, mean_b = 0;
@@ -96,12 +98,12 @@ __global__ void __launch_bounds__(128) k_denoise_downcov(const uint2 *__restrict
     {
       const float px = lum[5 * j + i];
       mean_b += px / 25.0f;
-      float p2 = px * px * 1.0f;
+      float p2 = px * px;
       float p0 = (float)(i - 2) - mwx, p1 = (float)(j - 2) - mwy;
       Sw0 += p2 * p0 * p0; Sw1 += p2 * p0 * p1; Sw2 += p2 * p1 * p0; Sw3 += p2 * p1 * p1;
       sw += p2;
       p0 = (float)(i - 2) - mbx; p1 = (float)(j - 2) - mby;
-      p2 = 1.0f / (px * px) * 1.0f;
+      p2 = 1.0f / (px * px);
       Sb0 += p2 * p0 * p0; Sb1 += p2 * p0 * p1; Sb2 += p2 * p1 * p0; Sb3 += p2 * p1 * p1;
       sb += p2;
     }
@@ -114,6 +116,7 @@ __global__ void __launch_bounds__(128) k_denoise_downcov(const uint2 *__restrict
   e0 = clampf(e0, 0.01f, 25.0f); e1 = clampf(e1, 0.01f, 25.0f);
   st_rgba(covimg, w, x, y, make_float4(e0, e1, v0x, v0y));
   float r = 0, g = 0, b = 0, wt = 0;
+  const float ie0 = 1.0f / e0, ie1 = 1.0f / e1;
 #pragma unroll
   for(int j = 0; j < 5; j++)
 #pragma unroll
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(128) k_denoise_downcov(const uint2 *__restrict
       if(t.x > 2.0f * mean_b) continue; // hot pixels
       const float fi = (float)(i - 2), fj = (float)(j - 2);
       const float q0 = fi * v0x + fj * v0y, q1 = fi * v1x + fj * v1y;
-      const float wgt = fmaxf(1e-9f, expf(-0.5f * (q0 / e0 * q0 + q1 / e1 * q1)));
+      const float wgt = fmaxf(1e-9f, __expf(-0.5f * (q0 * ie0 * q0 + q1 * ie1 * q1)));
       r += wgt * t.x; g += wgt * t.y; b += wgt * t.z;
       wt += wgt;
     }
@@ -135,7 +138,8 @@ __global__ void __launch_bounds__(128) k_denoise_downcov(const uint2 *__restrict
   st_rgba(out, w, ox, oy, make_float4(r / iw_, g / iw_, b / iw_, edge));
 }
 
-VKB_DEV float gamma08(float f) { return f < 0.0f ? f : powf(f, 0.8f); } // feeds 1/sigma-scaled differences: keep full accuracy
+// x^0.8 on the SFU: ~1e-6 relative, i.e. <= 1e-4 in the [0,1] edge weight even at the 1e-3 noise floor of noise.glsl
+VKB_DEV float gamma08(float f) { return f < 0.0f ? f : __powf(f, 0.8f); }
 
 // ---- down: levels 1..3, 5 tap flower with edge stopping (down.comp:59-107) ----
 __global__ void __launch_bounds__(256) k_denoise_down(const uint2 *__restrict__ in, int w, int h, uint2 *__restrict__ out,
@@ -214,7 +218,7 @@ __global__ void __launch_bounds__(256) k_denoise_assemble(const uint2 *__restric
       + (len[3] - len[2]) / 1.0f + (len[2] - len[0]) / 2.0f + (len[3] - len[1]) / 2.0f) / 6.0f;
   float test = fmaxf(0.0f, -slope);
   test = fmaxf(0.0f, 1.0f - test);
-  test = powf(test, 16.0f);
+  test = test * test; test = test * test; test = test * test; test = test * test; // pow(test, 16)
   test = clampf(1.5f * test, 0.0f, 1.0f);
 #pragma unroll
   for(int l = 3; l >= 0; l--)
@@ -281,7 +285,7 @@ __global__ void __launch_bounds__(256) k_denoise_doub(const uint16_t *__restrict
   {
     const float wav = (val - crs1v) / fmaxf(sigma[0] + sigma[2], 1e-8f);
     const float tt = fminf(1.0f, wav / fmaxf(2.0f * T, 1e-8f));
-    float uw = powf(fminf(1.0f, 1.0f * upsm.w), 4.0f);
+    float uw = fminf(1.0f, 1.0f * upsm.w); uw = uw * uw; uw = uw * uw; // pow(.., 4)
     uw = 1.0f - (1.0f - uw) * p.detail;
     val = mixf(val, fmaxf(0.0f, crs + sigma[1] * signf(wav) * mixf(fmaxf(0.0f, fabsf(wav) - T), fabsf(wav), tt)), uw * blendw);
   }
