@@ -102,51 +102,9 @@ def cpu_reference_rate(sample_wh, steps, warmup, strength):
     return (w * h) / dt / 1e6, dt, os.cpu_count()
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="still61", choices=sorted(WORKLOADS))
-    ap.add_argument("--denoise", type=float, default=None, help="denoise:strength (default: 0.4 once the wavelet kernels are built, else 0)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    W, H, src, bpp = WORKLOADS[args.workload]
-    mp = W * H / 1e6
 
-    if args.impl == "reference":
-        # the reference's own CPU-side implementation of the path = the oracle port (vkdt-cli needs vulkan + glslang: absent)
-        if rank != 0:
-            return 0
-        strength = args.denoise if args.denoise is not None else 0.4
-        sample = (2376, 1584)  # 1/16 of the 61 MP frame, same graph
-        rate, dt, cores = cpu_reference_rate(sample, max(1, min(args.steps, 5)), max(1, min(args.warmup, 1)), strength)
-        print(json.dumps({
-            "impl": "reference", "metric": "MP/s raw->display graph", "value": round(rate, 3), "unit": "MP/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s %dx%d bayer 14-bit, default darkroom graph, denoise strength %.2f" % (args.workload, W, H, strength)},
-            "cpu_baseline": {"value": round(rate, 3), "unit": "MP/s", "cores": cores, "kind": "port",
-                             "sample": "%dx%d crop of the workload, %d timed passes of the CPU oracle (OpenMP)" % (sample[0], sample[1], max(1, min(args.steps, 5)))},
-            "e2e": {"value": round(rate, 3), "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
-        return 0
-
-    import torch
-    import torch.distributed as dist
-    from vkdt_b200 import api, synth
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (vkdt_b200 has no CPU path)")
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    torch.cuda.set_device(local_rank)
-    api.init(local_rank)
-    have_wavelet = ("denoise", "doub") in api.kernels()
-    strength = args.denoise if args.denoise is not None else (0.4 if have_wavelet else 0.0)
-
+def run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, src, bpp, strength, steps, warmup, sample_clocks=True):
+    """both legs (kernel path with HBM-resident input, end to end with host buffers) of one workload on this rank."""
     # ---- synthetic input: a few distinct stills per rank, cycled (deterministic seeds per SURVEY §8d) ----
     nstills = 2
     raws = [synth.mosaic(W, H, seed=0x5EED0000 + rank * 1000 + i, wb=WB) for i in range(nstills)]
@@ -187,12 +145,13 @@ def main():
     out_bytes = ow * oh * 16
     stream = g.stream()
     FR = api.RUN_RECORD
-    for i in range(args.warmup):
+    for i in range(warmup):
         g.set_source(dev_in[i % nstills], rp, device=True)
         g.run(FR | api.RUN_UPLOAD)
     api.check(api.lib.vkb_stream_sync(api.C.c_void_p(stream)))
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if sample_clocks:
+        sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -200,10 +159,10 @@ def main():
     e0, e1 = api.Event(), api.Event()
     per_kernel = {}
     e0.record(stream)
-    for i in range(args.steps):
+    for i in range(steps):
         g.set_source(dev_in[i % nstills], rp, device=True)
-        g.run(FR | api.RUN_UPLOAD | (api.RUN_WAIT if i == args.steps - 1 or i % 4 == 3 else 0))
-        if i == args.steps - 1 or i % 4 == 3:      # per-launch events are valid after a synchronised run
+        g.run(FR | api.RUN_UPLOAD | (api.RUN_WAIT if i == steps - 1 or i % 4 == 3 else 0))
+        if i == steps - 1 or i % 4 == 3:      # per-launch events are valid after a synchronised run
             for label, ms, nbytes in g.perf_entries():
                 a = per_kernel.setdefault(label, [0.0, 0, nbytes])
                 a[0] += ms; a[1] += 1
@@ -216,7 +175,8 @@ def main():
         t = torch.tensor([t_kernel_ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_kernel_ms = float(t.item())
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sample_clocks else None
+    pool_bytes = g.pool_bytes()
 
     # ---- leg 2: end to end through the C-ABI with host buffers ----
     # two graph instances (each with its own pool, stream and pinned sink) ping-pong: while one frame's 962 MB result
@@ -231,13 +191,13 @@ def main():
         gk.run()
         gs.append(gk); host_out.append(ho)
     FE = api.RUN_RECORD | api.RUN_UPLOAD | api.RUN_DOWNLOAD
-    for i in range(max(2, args.warmup)):
+    for i in range(max(2, warmup)):
         gs[i % NG].set_source(host_in[i % nstills], rp)
         gs[i % NG].run(FE | api.RUN_WAIT)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    e2e_steps = max(4, min(args.steps, 12))
+    e2e_steps = max(4, min(steps, 12))
     f0, f1 = api.Event(), api.Event()
     t0 = time.time()
     f0.record(gs[0].stream())
@@ -259,6 +219,70 @@ def main():
         t_e2e_ms = float(t.item())
     checksum = float(np.frombuffer((api.C.c_float * 4).from_address(host_out[(e2e_steps - 1) % NG]), dtype=np.float32).sum())
 
+    for hp in host_in + host_out:
+        api.host_free(hp)
+    for dp in dev_in:
+        api.dev_free(dp)
+    for gk in gs + [g]:
+        gk.close()
+    return dict(t_kernel_ms=t_kernel_ms, t_e2e_ms=t_e2e_ms, e2e_steps=e2e_steps, launches=launches, per_kernel=per_kernel, clocks=clocks,
+                in_bytes=in_bytes, out_bytes=out_bytes, ow=ow, oh=oh, pool_bytes=pool_bytes, checksum=checksum, nstills=nstills)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="still61", choices=sorted(WORKLOADS))
+    ap.add_argument("--denoise", type=float, default=None, help="denoise:strength (default: 0.4 once the wavelet kernels are built, else 0)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mlv", action="store_true", help="skip the extra MLV 4K frames/s measurement")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    W, H, src, bpp = WORKLOADS[args.workload]
+    mp = W * H / 1e6
+
+    if args.impl == "reference":
+        # the reference's own CPU-side implementation of the path = the oracle port (vkdt-cli needs vulkan + glslang: absent)
+        if rank != 0:
+            return 0
+        strength = args.denoise if args.denoise is not None else 0.4
+        sample = (2376, 1584)  # 1/16 of the 61 MP frame, same graph
+        rate, dt, cores = cpu_reference_rate(sample, max(1, min(args.steps, 5)), max(1, min(args.warmup, 1)), strength)
+        print(json.dumps({
+            "impl": "reference", "metric": "MP/s raw->display graph", "value": round(rate, 3), "unit": "MP/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s %dx%d bayer 14-bit, default darkroom graph, denoise strength %.2f" % (args.workload, W, H, strength)},
+            "cpu_baseline": {"value": round(rate, 3), "unit": "MP/s", "cores": cores, "kind": "port",
+                             "sample": "%dx%d crop of the workload, %d timed passes of the CPU oracle (OpenMP)" % (sample[0], sample[1], max(1, min(args.steps, 5)))},
+            "e2e": {"value": round(rate, 3), "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from vkdt_b200 import api, synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (vkdt_b200 has no CPU path)")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    api.init(local_rank)
+    have_wavelet = ("denoise", "doub") in api.kernels()
+    strength = args.denoise if args.denoise is not None else (0.4 if have_wavelet else 0.0)
+
+    mlv_W, mlv_H, mlv_src, mlv_bpp = WORKLOADS["mlv4k"]
+    R = run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, src, bpp, strength, args.steps, args.warmup)
+    M = None
+    if args.workload != "mlv4k" and not args.no_mlv:
+        M = run_workload(api, synth, torch, dist, args, rank, world, local_rank, mlv_W, mlv_H, mlv_src, mlv_bpp, strength,
+                         max(8, min(2 * args.steps, 40)), 3, sample_clocks=False)
+    t_kernel_ms, t_e2e_ms, e2e_steps, launches, per_kernel, clocks = R["t_kernel_ms"], R["t_e2e_ms"], R["e2e_steps"], R["launches"], R["per_kernel"], R["clocks"]
+    in_bytes, out_bytes, ow, oh, checksum, nstills = R["in_bytes"], R["out_bytes"], R["ow"], R["oh"], R["checksum"], R["nstills"]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -286,13 +310,19 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s: %dx%d bayer rggb 14-bit still (%.1f MP), default darkroom graph incl. hilite + llap + grade, "
                                "denoise strength %.2f, sink rgba f32 %dx%d" % (args.workload, W, H, mp, strength, ow, oh),
-                   "timing": "inputs and intermediates (%.0f MB pool) exceed the 126 MB L2; %d distinct stills cycled" % (g.pool_bytes() / 1e6, nstills),
+                   "timing": "inputs and intermediates (%.0f MB pool) exceed the 126 MB L2; %d distinct stills cycled" % (R["pool_bytes"] / 1e6, nstills),
                    "parallelism": "independent stills per GPU, no collective", "edges": "f16 at every reference edge (strict)"},
         "e2e": {"value": round(world * e2e_steps * mp / (t_e2e_ms * 1e-3), 2), "unit": "MP/s", "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": out_bytes, "ms_per_step": round(t_e2e_ms / e2e_steps, 3), "steps": e2e_steps, "checksum": checksum},
         "gpu_launches": int(launches), "launches_per_step": int(launches // max(1, args.steps)),
-        "clocks": clocks, "roofline": roof, "pool_bytes": g.pool_bytes(),
+        "clocks": clocks, "roofline": roof, "pool_bytes": R["pool_bytes"],
     }
+    if M:
+        msteps = max(8, min(2 * args.steps, 40))
+        line["mlv4k"] = {"workload": "MLV 4096x2160 14-bit packed frames, default darkroom graph, frame f -> rank f mod N",
+                         "frames_per_s": round(world * msteps / (M["t_kernel_ms"] * 1e-3), 1), "ms_per_frame": round(M["t_kernel_ms"] / msteps, 3),
+                         "e2e_frames_per_s": round(world * M["e2e_steps"] / (M["t_e2e_ms"] * 1e-3), 1),
+                         "h2d_bytes_per_frame": M["in_bytes"], "d2h_bytes_per_frame": M["out_bytes"], "n_gpus": world}
     if not args.no_cpu_baseline:
         sample = (2376, 1584)
         rate, dt, cores = cpu_reference_rate(sample, 3, 1, strength)

@@ -104,3 +104,33 @@ def test_node_list_matches_reference_structure(gpu, oracle):
         assert k in dot, k
     perf = g.perf()
     assert "b200_pointw (crop+colour+filmcurv)" in perf and "llapfin (assemble+colour+grade)" in perf
+
+
+def test_imlv_file_source_and_cli(gpu, oracle, tmp_path):
+    """the vkdt-cli compatible driver on an MLV file + cfg on disk: parse, unpack on the device, develop, write the PFM
+    (o-pfm/main.c:8-42) and compare with the oracle.  frame 1 through `--config frames:2`."""
+    import os
+    import subprocess
+    w, h = 512, 386
+    frames = [synth.mosaic(w, h, seed=21), synth.mosaic(w, h, seed=22)]
+    synth.write_mlv(str(tmp_path / "clip.mlv"), frames, black=2048, white=15000)
+    cfg = tmp_path / "clip.cfg"
+    cfg.write_text(gpu.DARKROOM_CFG.format(src="i-mlv") + "param:i-mlv:main:filename:clip.mlv\n")
+    cli = os.path.join(os.path.dirname(gpu.LIB_PATH), "vkdt-b200-cli")
+    out = str(tmp_path / "dev")
+    r = subprocess.run([cli, "-g", str(cfg), "--format", "o-pfm", "--filename", out, "-d", "perf", "--config", "frames:2"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "[perf] total time" in r.stdout and "b200_rawnoop" in r.stdout
+    for f in range(2):
+        data = open("%s_%04d.pfm" % (out, f), "rb").read()
+        assert data.startswith(b"PF\n")
+        hdr_end = data.index(b"\n", data.index(b"-1.0")) + 1
+        dims = data.split(b"\n")[1].split()
+        ow, oh = int(dims[0]), int(dims[1])
+        got = np.frombuffer(data[hdr_end:], dtype=np.float32).reshape(oh, ow, 3)
+        d = oracle.darkroom_defaults(w, h)          # i-mlv without IDNT: identity matrix, wb 1, noise 1/1 (i-mlv/main.c:119-141)
+        want = oracle.darkroom_run(d, frames[f])
+        assert want.shape[:2] == (oh, ow)
+        err = np.abs(got - want[..., :3])
+        assert psnr(got, want[..., :3]) >= 60.0 and err.max() <= 2e-3 and (err > 1e-3).mean() <= 1e-5, (f, err.max())
