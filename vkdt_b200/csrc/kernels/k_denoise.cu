@@ -16,11 +16,16 @@ struct dn_push_asm_t  { float wb[4], black[4], white[4]; int32_t crop[4]; float 
 struct dn_push_doub_t { float wb[4], black[4], white[4]; int32_t crop[4]; uint32_t filters; float noise_a, noise_b; int32_t gainmap; float map_os[4]; }; // :301-308
 
 // noise.glsl:1-11
-VKB_DEV void noise_sigma(float a, float b, float black, float white, const float *edges, float val, float *sig)
+// `escale[k]` = exp2(12*edges[k] + edges[3]) is a function of the module params only: evaluated once per launch on the host
+VKB_DEV void noise_sigma(float a, float b, float black, float white, const float *escale, float val, float *sig)
 {
   const float s = sqrtf(a + fmaxf(0.0f, (val - black) / (white - black)) * b);
 #pragma unroll
-  for(int k = 0; k < 3; k++) sig[k] = clampf(exp2f(12.0f * edges[k] + edges[3]) * s, 1e-3f, 1e3f);
+  for(int k = 0; k < 3; k++) sig[k] = clampf(escale[k] * s, 1e-3f, 1e3f);
+}
+static void host_escale(denoise_params_t *p)
+{ // overwrite edges[0..2] in the kernel's copy of the params with the scale factors
+  for(int k = 0; k < 3; k++) p->edges[k] = exp2f(12.0f * p->edges[k] + p->edges[3]);
 }
 VKB_DEV void swizzle(int x, int y, int w, int h, int &ox, int &oy)
 { // downcov.comp:52-53, down.comp:103-104
@@ -63,24 +68,35 @@ __global__ void __launch_bounds__(256) k_denoise_half(const uint16_t *__restrict
 }
 
 // ---- downcov: level 0, structure tensor guided blur (downcov.comp:41-62, cov.glsl:21-138) ----
-__global__ void __launch_bounds__(128) k_denoise_downcov(const uint2 *__restrict__ in, int w, int h,
+// a CTA of 32x8 outputs stages its 36x12 input window once in shared memory as (r, g, b, luminance) floats: the three
+// 5x5 passes of response() then read LDS.128 instead of 75 mirrored 8-byte global loads + conversions + luminance
+// dot products per pixel.  arithmetic per pixel is unchanged (same order, IEEE divisions) so the covariance choice and
+// the hot pixel test fall exactly like in the restatement.
+#define DC_W 36
+#define DC_H 12
+__global__ void __launch_bounds__(256) k_denoise_downcov(const uint2 *__restrict__ in, int w, int h,
     uint2 *__restrict__ out, uint2 *__restrict__ covimg)
 {
-  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 4 + threadIdx.y;
+  __shared__ float4 tile[DC_H][DC_W];
+  const int tx0 = blockIdx.x * 32 - 2, ty0 = blockIdx.y * 8 - 2;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  for(int t = tid; t < DC_W * DC_H; t += 256)
+  {
+    const int r = t / DC_W, c = t - r * DC_W;
+    const float4 v = ld_rgba(in, w, mirrori(tx0 + c, w), mirrori(ty0 + r, h));
+    tile[r][c] = make_float4(v.x, v.y, v.z, lum2020(v.x, v.y, v.z));
+  }
+  __syncthreads();
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
   if(x >= w || y >= h) return;
-  float lum[25];
-  int xi[5], yi[5];
-#pragma unroll
-  for(int k = 0; k < 5; k++) { xi[k] = mirrori(x - 2 + k, w); yi[k] = mirrori(y - 2 + k, h); }
+  const int lx = threadIdx.x, ly = threadIdx.y; // tile coords of tap (-2,-2)
   float mwx = 0, mwy = 0, mbx = 0, mby = 0, smw = 0, smb = 0;
 #pragma unroll
   for(int j = 0; j < 5; j++)
 #pragma unroll
     for(int i = 0; i < 5; i++)
     {
-      const float4 t = ld_rgba(in, w, xi[i], yi[j]);
-      const float px = lum2020(t.x, t.y, t.z);
-      lum[5 * j + i] = px;
+      const float px = tile[ly + j][lx + i].w;
       const float fi = (float)(i - 2), fj = (float)(j - 2);
       mwx += fi * px; mwy += fj * px;
       smw += px;
@@ -96,7 +112,7 @@ __global__ void __launch_bounds__(128) k_denoise_downcov(const uint2 *__restrict
 #pragma unroll
     for(int i = 0; i < 5; i++)
     {
-      const float px = lum[5 * j + i];
+      const float px = tile[ly + j][lx + i].w;
       mean_b += px / 25.0f;
       float p2 = px * px;
       float p0 = (float)(i - 2) - mwx, p1 = (float)(j - 2) - mwy;
@@ -122,7 +138,7 @@ __global__ void __launch_bounds__(128) k_denoise_downcov(const uint2 *__restrict
 #pragma unroll
     for(int i = 0; i < 5; i++)
     {
-      const float4 t = ld_rgba(in, w, xi[i], yi[j]);
+      const float4 t = tile[ly + j][lx + i];
       if(t.x > 2.0f * mean_b) continue; // hot pixels
       const float fi = (float)(i - 2), fj = (float)(j - 2);
       const float q0 = fi * v0x + fj * v0y, q1 = fi * v1x + fj * v1y;
@@ -262,11 +278,20 @@ __global__ void __launch_bounds__(256) k_denoise_doub(const uint16_t *__restrict
   const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
   if(x >= ow || y >= oh) return;
   // texture(img_crs, (ipos+0.5)/imageSize(out)): ideal sampler, coordinates in double
-  const double ux = ((double)x + 0.5) / (double)ow * (double)cw - 0.5, uy = ((double)y + 0.5) / (double)oh * (double)ch - 0.5;
-  const double fx = floor(ux), fy = floor(uy);
-  const float ax = (float)(ux - fx), ay = (float)(uy - fy);
-  const float4 upsm = bilin_rgba(crs0, cw, ch, (int)fx, (int)fy, ax, ay);
-  const float4 down = bilin_rgba(crs1, cw, ch, (int)fx, (int)fy, ax, ay);
+  int bx, by; float ax, ay;
+  if(ow == 2 * cw && oh == 2 * ch)
+  { // (x+0.5)/2 - 0.5 = x/2 - 0.25: even x -> texel x/2-1 + 0.75, odd x -> texel (x-1)/2 + 0.25, exactly
+    bx = (x >> 1) - ((x & 1) ? 0 : 1); ax = (x & 1) ? 0.25f : 0.75f;
+    by = (y >> 1) - ((y & 1) ? 0 : 1); ay = (y & 1) ? 0.25f : 0.75f;
+  }
+  else
+  {
+    const double ux = ((double)x + 0.5) / (double)ow * (double)cw - 0.5, uy = ((double)y + 0.5) / (double)oh * (double)ch - 0.5;
+    const double fx = floor(ux), fy = floor(uy);
+    bx = (int)fx; by = (int)fy; ax = (float)(ux - fx); ay = (float)(uy - fy);
+  }
+  const float4 upsm = bilin_rgba(crs0, cw, ch, bx, by, ax, ay);
+  const float4 down = bilin_rgba(crs1, cw, ch, bx, by, ax, ay);
   float black = P.black[1], white = P.white[1], crs = upsm.y, crs1v = down.y;
   float T = 0.5f * p.strength * upsm.w, blendw = p.luma;
   const int xt = P.filters == 9;
@@ -316,7 +341,7 @@ static int launch_downcov(const vkb_launch_t *l)
   VKB_REQUIRE(l->num_conn >= 3);
   const vkb_image_t *in = l->conn, *out = l->conn + 1, *cov = l->conn + 2;
   VKB_REQUIRE(in->chan == 4 && out->chan == 4 && cov->chan == 4 && in->wd == out->wd && in->ht == out->ht && cov->wd == in->wd);
-  k_denoise_downcov<<<grid2d(out->wd, out->ht, 4), dim3(32, 4), 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, (uint2 *)out->data, (uint2 *)cov->data);
+  k_denoise_downcov<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, (uint2 *)out->data, (uint2 *)cov->data);
   VKB_CHECK_LAUNCH();
   return VKB_OK;
 }
@@ -332,6 +357,7 @@ static int launch_down(const vkb_launch_t *l)
   VKB_REQUIRE(pc->level >= 0); // the level < 0 branch (response()) is dead in the reference wiring
   denoise_params_t p; memset(&p, 0, sizeof(p)); memcpy(&p, l->params, l->params_size < sizeof(p) ? l->params_size : sizeof(p));
   const float blk = pc->block == 3 ? 2.23607f : (pc->block == 2 ? 1.414213f : 1.0f);
+  host_escale(&p);
   k_denoise_down<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, (uint2 *)out->data,
       p, pc->black[1], pc->white[1], pc->noise_a, pc->noise_b, powf(0.7f, (float)pc->level), blk);
   VKB_CHECK_LAUNCH();
@@ -362,6 +388,7 @@ static int launch_assemble(const vkb_launch_t *l)
   K.noise_a = pc->noise_a; K.noise_b = pc->noise_b;
   K.blk = pc->filters == 0u ? 1.0f : (pc->filters == 9u ? 2.23607f : 1.414213f);
   K.thrs0 = powf(p.strength, 4.0f);
+  host_escale(&p);
   k_denoise_assemble<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint2 *)c[0].data, (const uint2 *)c[1].data, (const uint2 *)c[2].data,
       (const uint2 *)c[3].data, (const uint2 *)c[4].data, (uint2 *)out->data, out->wd, out->ht, p, K);
   VKB_CHECK_LAUNCH();
@@ -377,6 +404,7 @@ static int launch_doub(const vkb_launch_t *l)
   VKB_REQUIRE(in->format == VKB_TOKEN_UI16 && c0->chan == 4 && c1->chan == 4 && c0->wd == c1->wd && out->chan == 1 && out->format == VKB_TOKEN_F16);
   denoise_params_t p; memset(&p, 0, sizeof(p)); memcpy(&p, l->params, l->params_size < sizeof(p) ? l->params_size : sizeof(p));
   dn_push_doub_t P; memcpy(&P, l->push, sizeof(P));
+  host_escale(&p);
   k_denoise_doub<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint16_t *)in->data, in->wd, in->ht, (const uint2 *)c0->data,
       (const uint2 *)c1->data, c0->wd, c0->ht, (__half *)out->data, out->wd, out->ht, p, P);
   VKB_CHECK_LAUNCH();

@@ -234,24 +234,35 @@ __global__ void __launch_bounds__(256) k_llap_assemble_tiled(const __half *__res
     const __half *__restrict__ l1, int cw, int ch, __half *__restrict__ out, int ow, int oh, int first)
 {
   __shared__ float tile[NL + 1][AT_H][AT_W + 1];
+  __shared__ int s_pmin, s_pmax;
   const int cx0 = blockIdx.x * 16 - 2, cy0 = blockIdx.y * 4 - 2;
   const int tid = threadIdx.y * 32 + threadIdx.x;
   const size_t p0 = (size_t)ow * oh, p1 = (size_t)cw * ch;
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  const bool inside = x < ow && y < oh;
+  // which gamma layers does this CTA need?  only those (plus the collapsed coarse level) are staged
+  if(tid == 0) { s_pmin = NUM_GAMMA; s_pmax = 0; }
+  float v = 0.0f; int hi = 1;
+  if(inside) { v = ld_h(l0 + NUM_GAMMA * p0, ow, x, y); hi = gamma_hi_from_v(v); }
+  __syncthreads();
+  const int wlo = __reduce_min_sync(0xffffffffu, inside ? hi - 1 : NUM_GAMMA), whi = __reduce_max_sync(0xffffffffu, inside ? hi : 0);
+  if(threadIdx.x == 0) { atomicMin(&s_pmin, wlo); atomicMax(&s_pmax, whi); }
+  __syncthreads();
+  const int pmin = s_pmin, pmax = s_pmax;
   const bool big = cw >= 24 && ch >= 12;
-  for(int t = tid; t < (NL + 1) * AT_H * AT_W; t += 256)
+  if(tid < AT_H * AT_W)
   {
-    const int pl = t / (AT_H * AT_W), rem = t - pl * (AT_H * AT_W), r = rem / AT_W, c = rem - r * AT_W;
+    const int r = tid / AT_W, c = tid - r * AT_W;
     const int gx = big ? mirror1(cx0 + c, cw) : mirrori(cx0 + c, cw), gy = big ? mirror1(cy0 + r, ch) : mirrori(cy0 + r, ch);
-    const __half *src = pl < NL ? l1 + pl * p1 : (first ? l1 + NUM_GAMMA * p1 : coarse);
-    tile[pl][r][c] = __half2float(__ldg(src + (size_t)gy * cw + gx));
+    const size_t off = (size_t)gy * cw + gx;
+    tile[NL][r][c] = __half2float(__ldg((first ? l1 + NUM_GAMMA * p1 : coarse) + off));
+    for(int pl = pmin; pl <= pmax; pl++) tile[pl][r][c] = __half2float(__ldg(l1 + pl * p1 + off));
   }
   __syncthreads();
-  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-  if(x >= ow || y >= oh) return;
+  if(!inside) return;
   const soft_local_t sx = soft_local(x, cx0), sy = soft_local(y, cy0);
   const float res = gauss_expand_tile(tile[NL], sx, sy);
-  const float v = ld_h(l0 + NUM_GAMMA * p0, ow, x, y);
-  const int hi = gamma_hi_from_v(v), lo = hi - 1;
+  const int lo = hi - 1;
   const float glo = gamma_from_i(lo), ghi = gamma_from_i(hi);
   const float a = clampf((v - glo) / (ghi - glo), 0.0f, 1.0f);
   const float lap0 = ld_h(l0 + lo * p0, ow, x, y) - gauss_expand_tile(tile[lo], sx, sy);

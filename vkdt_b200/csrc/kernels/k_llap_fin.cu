@@ -154,6 +154,21 @@ VKB_DEV void expand4(const float (*T)[F3_W + 1], int lx, int ly, float &ee, floa
   oo = (ho[1] + 0.5f * (ho[2] + ho[3]) + ho[4]) / 9.0f;
 }
 
+VKB_DEV float expand1(const float (*T)[F3_W + 1], int lx, int ly, int q)
+{ // one output of the 2x2 (q&1: x odd, q>>1: y odd): used when the four pixels bracket different gamma layers
+  const bool ox = q & 1, oy = q >> 1;
+  const float wx[5] = { ox ? 0.0f : 0.5f, ox ? 1.0f : 0.5f, ox ? 0.5f : 1.0f, 0.5f, ox ? 1.0f : 0.5f };
+  const float wy[5] = { oy ? 0.0f : 0.5f, oy ? 1.0f : 0.5f, oy ? 0.5f : 1.0f, 0.5f, oy ? 1.0f : 0.5f };
+  float acc = 0.0f;
+#pragma unroll
+  for(int r = 0; r < 5; r++)
+  {
+    const float *row = T[ly - 2 + r] + lx - 2;
+    acc += (row[0] * wx[0] + row[1] * wx[1] + row[2] * wx[2] + row[3] * wx[3] + row[4] * wx[4]) * wy[r];
+  }
+  return acc / 9.0f;
+}
+
 template <bool F32, bool GRADE>
 __global__ void __launch_bounds__(256) k_llap_final4(const uint2 *__restrict__ in, const __half *__restrict__ coarse,
     const __half *__restrict__ l1, int cw, int ch, void *__restrict__ outv, int ow, int oh, const __grid_constant__ llapfin_t P)
@@ -220,9 +235,8 @@ __global__ void __launch_bounds__(256) k_llap_final4(const uint2 *__restrict__ i
 #pragma unroll
     for(int q = 0; q < 4; q++) if(hi[q] >= 0)
     {
-      float t[4];
-      expand4(tile[hi[q] - 1], lx, ly, t[0], t[1], t[2], t[3]); e0[q] = t[q];
-      expand4(tile[hi[q]],     lx, ly, t[0], t[1], t[2], t[3]); e1[q] = t[q];
+      e0[q] = expand1(tile[hi[q] - 1], lx, ly, q);
+      e1[q] = expand1(tile[hi[q]],     lx, ly, q);
     }
   }
 #pragma unroll
