@@ -134,3 +134,29 @@ def test_imlv_file_source_and_cli(gpu, oracle, tmp_path):
         assert want.shape[:2] == (oh, ow)
         err = np.abs(got - want[..., :3])
         assert psnr(got, want[..., :3]) >= 60.0 and err.max() <= 2e-3 and (err > 1e-3).mean() <= 1e-5, (f, err.max())
+
+
+@pytest.mark.parametrize("strength", [0.0, 0.4])
+def test_xtrans_end_to_end(gpu, oracle, strength):
+    """BASELINE config 3: X-Trans mosaic (canonical 6x6 phase) through denoise + X-Trans demosaic and the rest of the graph."""
+    w, h = 516, 408
+    raw = synth.mosaic(w, h, seed=31, xtrans=True)
+    d = _oracle_cfg(oracle, w, h, strength=strength, noise=(100.0, 2.0))
+    d.filters = 9
+    want = oracle.darkroom_run(d, raw)
+    g = gpu.Graph(cfg_text=gpu.DARKROOM_CFG.format(src="i-raw"))
+    if strength > 0:
+        assert g.line("param:denoise:01:strength:%g" % strength) == 0
+    buf = np.ascontiguousarray(raw)
+    g.set_source(buf.ctypes.data, gpu.raw_params(w, h, wb=WB, cam_to_rec2020=CAM, filters=9, noise_a=100.0, noise_b=2.0))
+    g.set_sink_buffer(None, 0)
+    g.run()
+    ow, oh = g.sink_size()
+    out = np.zeros((oh, ow, 4), dtype=np.float32)
+    g.set_sink_buffer(out.ctypes.data, out.nbytes)
+    g.run(gpu.RUN_RECORD | gpu.RUN_UPLOAD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT)
+    assert out.shape == want.shape
+    err = np.abs(out[..., :3] - want[..., :3])
+    p = psnr(out[..., :3], want[..., :3])
+    print("xtrans strength %.1f: max abs %.3g psnr %.1f" % (strength, err.max(), p))
+    assert p >= 60.0 and (err > 1e-3).mean() <= 1e-4 and err.max() <= 5e-3, (err.max(), p)

@@ -357,3 +357,48 @@ def test_denoise_wavelet_kernels(gpu, oracle, dims, na, nb):
     gpu.dispatch("denoise", "doub", [I(d_raw, w, h, 1, "ui16"), I(to_dev_f16(asm), hw, hh, 4, "f16"), I(to_dev_f16(half), hw, hh, 4, "f16"),
                                      I(d_o, w, h, 1, "f16")], _denoise_push("doub", wb, 2048, 15000, (0, 0, w, h), F, na, nb), par)
     assert_close_mixed(to_host(d_o), out, 2, 1e-6, 0.95, "denoise doub", max_outliers=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# x-trans (filters == 9): BASELINE config 3.  same kernels, block = 3 branches.
+XT = 9
+
+
+@pytest.mark.parametrize("dims", [(258, 192), (132, 102)])
+def test_xtrans_hilite_and_demosaic_kernels(gpu, oracle, dims):
+    O = oracle
+    w, h = dims
+    m = _mosaic_f16(O, w, h, seed=4, xtrans=True)
+    hp = O.HiliteParams(0.985, 0.3, 0.6)
+    par = fbits(0.985, 0.3, 0.6); push = fbits(1, 1, 1, 1) + ubits(XT)
+    I = gpu.image
+    mi = O.img(m)
+    d_m = to_dev_f16(m)
+    hw, hh = w // 3, h // 3
+    # hilite half / doub on the 3x3 blocks
+    half, hi_ = O.new_img(hh, hw, 4)
+    O.lib().o_hilite_half(C.byref(mi), C.byref(hi_), C.byref(hp), C.c_uint32(XT))
+    d_half = dev_f16(hh, hw, 4)
+    gpu.dispatch("hilite", "half", [I(d_m, w, h, 1, "f16"), I(d_half, hw, hh, 4, "f16")], push, par)
+    assert f16_ulp_diff(to_host(d_half), half).max() <= 1
+    want, wi = O.new_img(h, w, 1)
+    O.lib().o_hilite_module(C.byref(mi), C.byref(wi), C.byref(hp), O.f4(1, 1, 1, 1), C.c_uint32(XT))
+    got = to_host(plans.hilite(gpu, d_m, w, h, (0.985, 0.3, 0.6), filters=XT))
+    assert np.abs(got - want).max() < 2e-3 and psnr(got, want) > 70.0
+    # demosaic
+    cov, ci = O.new_img(hh, hw, 4); green, gi = O.new_img(h, w, 1); rgb, ri = O.new_img(h, w, 4)
+    O.lib().o_demosaic_gauss(C.byref(mi), C.byref(ci), C.c_uint32(XT))
+    O.lib().o_demosaic_splat(C.byref(mi), C.byref(ci), C.byref(gi), C.c_uint32(XT))
+    O.lib().o_demosaic_fix(C.byref(mi), C.byref(gi), C.byref(ci), C.byref(ri), C.c_uint32(XT), 0)
+    d_cov = dev_f16(hh, hw, 4)
+    gpu.dispatch("demosaic", "gauss", [I(None, 0, 0, 1, "f16"), I(d_m, w, h, 1, "f16"), I(d_cov, hw, hh, 4, "f16")], push)
+    gc = to_host(d_cov)
+    same = (gc[..., 2:] == cov[..., 2:]).all(axis=-1)
+    assert same.mean() > 0.999
+    d_green = dev_f16(h, w)
+    gpu.dispatch("demosaic", "splat", [I(d_m, w, h, 1, "f16"), I(to_dev_f16(cov), hw, hh, 4, "f16"), I(d_green, w, h, 1, "f16")], push)
+    assert_f16_close(to_host(d_green), green, 2, 0.97, "xtrans splat")
+    d_rgb = dev_f16(h, w, 4)
+    gpu.dispatch("demosaic", "fix", [I(d_m, w, h, 1, "f16"), I(to_dev_f16(green), w, h, 1, "f16"), I(to_dev_f16(cov), hw, hh, 4, "f16"),
+                                     I(d_rgb, w, h, 4, "f16")], push, ibits(0, 0))
+    assert_f16_close(to_host(d_rgb), rgb, 2, 0.97, "xtrans fix")

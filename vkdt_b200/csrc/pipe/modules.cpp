@@ -199,7 +199,8 @@ static void iraw_roi_out(dt_graph_t *g, dt_module_t *mod)
   const int block = p->filters == 9u ? 3 : (p->filters ? 2 : 1);
   mod->connector[0].roi.full_wd = (p->width / block) * block;
   mod->connector[0].roi.full_ht = (p->height / block) * block;
-  if(p->filters && p->filters != 9u) mod->connector[0].chan = dt_token("rggb"); // i-raw/main.c:226
+  // i-raw/main.c:221-226: one channel for any cfa (bayer and x-trans), rgba only for 3-component raws
+  mod->connector[0].chan = p->filters ? dt_token("rggb") : dt_token("rgba");
 }
 static int iraw_read_source(dt_module_t *mod, void *mapped, dt_read_source_params_t *p)
 { // i-raw/main.c:281-297: row copy of the aligned window into the mapped staging buffer
