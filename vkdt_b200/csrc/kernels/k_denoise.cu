@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(256) k_denoise_half(const uint16_t *__restrict
 // the hot pixel test fall exactly like in the restatement.
 #define DC_W 36
 #define DC_H 12
-__global__ void __launch_bounds__(256) k_denoise_downcov(const uint2 *__restrict__ in, int w, int h,
+__global__ void __launch_bounds__(256, 3) k_denoise_downcov(const uint2 *__restrict__ in, int w, int h,
     uint2 *__restrict__ out, uint2 *__restrict__ covimg)
 {
   __shared__ float4 tile[DC_H][DC_W];

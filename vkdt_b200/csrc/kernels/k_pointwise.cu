@@ -16,6 +16,7 @@ struct pw_chain_t
 {
   int n_ops;
   int op[8];
+  int shift, sx, sy;   // crop resolved to an integer translation on the host (the default 3 px micro-crop)
   int out_f32;
   crop_committed_t crop;
   filmcurv_params_t film;
@@ -36,7 +37,11 @@ __global__ void __launch_bounds__(256) k_pointwise_t(const uint2 *__restrict__ i
   constexpr int ops[4] = { O0, O1, O2, O3 };
   constexpr int n = (O0 != 0) + (O1 != 0) + (O2 != 0) + (O3 != 0);
   float4 px;
-  if(O0 == PW_CROP) px = crop_fetch<ROT>(in, iw, ih, x, y, P.crop);
+  if(O0 == PW_CROP)
+  {
+    if(ROT) { px = ld_rgba_clamp(in, iw, ih, x + P.sx, y + P.sy); px.w = 1.0f; } // host proved the gather is an integer shift
+    else px = crop_fetch<false>(in, iw, ih, x, y, P.crop);
+  }
   else px = ld_rgba(in, iw, x, y);
   f3 c = { px.x, px.y, px.z };
   if(O0 == PW_CROP && n > 1) c = round3(c);
@@ -211,11 +216,38 @@ static int launch_chain(const vkb_launch_t *l, int n_ops, const uint32_t *ops)
     pp += need; left -= need;
   }
   if(P.op[0] != PW_CROP) VKB_REQUIRE(in->wd == out->wd && in->ht == out->ht);
+  else if(P.crop.r[0] == 1.0f)
+  { // is crop/main.comp's gather (crop offset, rotation, homography, texelFetch(ivec2(rd*size))) a pure integer translation?
+    // evaluate the transform in double on a 3x3 grid of output pixels; every sample must land within 1/4 texel of the
+    // centre of texel (x + sx, y + sy) (the shader's fp32 error is ~1e-3 texels) and inside the input.
+    const crop_committed_t &c = P.crop;
+    const double tsx = in->wd, tsy = in->ht;
+    bool ok = true; long sx = 0, sy = 0;
+    for(int j = 0; j < 3 && ok; j++) for(int i = 0; i < 3 && ok; i++)
+    {
+      const double x = i * 0.5 * (out->wd - 1), y = j * 0.5 * (out->ht - 1);
+      double xx = floor(x) + 0.5 + (double)c.crop[0] * tsx, yy = floor(y) + 0.5 + (double)c.crop[2] * tsy;
+      const double dx = xx - tsx * .5, dy = yy - tsy * .5;
+      xx = c.r[0] * dx + c.r[2] * dy + tsx * .5; yy = c.r[1] * dx + c.r[3] * dy + tsy * .5;
+      const double hx = c.H[0] * xx + c.H[4] * yy + c.H[8], hy = c.H[1] * xx + c.H[5] * yy + c.H[9], hz = c.H[2] * xx + c.H[6] * yy + c.H[10];
+      const double u = hx / hz, v = hy / hz;
+      const long tx = (long)floor(u), ty = (long)floor(v);
+      if(fabs(u - (tx + 0.5)) > 0.25 || fabs(v - (ty + 0.5)) > 0.25 || tx < 0 || ty < 0 || tx >= (long)in->wd || ty >= (long)in->ht) ok = false;
+      const long ex = tx - (long)floor(x), ey = ty - (long)floor(y);
+      if(i == 0 && j == 0) { sx = ex; sy = ey; }
+      else if(ex != sx || ey != sy) ok = false;
+    }
+    if(ok) { P.shift = 1; P.sx = (int)sx; P.sy = (int)sy; }
+  }
   dim3 block(32, 8), grid(vkb_cdiv(out->wd, 64), vkb_cdiv(out->ht, 8)), grid1(vkb_cdiv(out->wd, 32), vkb_cdiv(out->ht, 8));
   const int sig = P.op[0] | (P.op[1] << 4) | (P.op[2] << 8) | (P.op[3] << 12) | (n_ops > 4 ? 1 << 20 : 0);
 #define PW_CASE(A, B, C, D) \
   case ((A) | ((B) << 4) | ((C) << 8) | ((D) << 12)): \
     if((A) == PW_CROP && P.crop.r[0] != 1.0f) goto generic; /* rotation / perspective: catmull-rom gather, generic kernel */ \
+    if((A) == PW_CROP && P.shift) { \
+      if(P.out_f32) k_pointwise_t<A, B, C, D, true, true><<<grid1, block, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, out->data, out->wd, out->ht, P); \
+      else k_pointwise_t<A, B, C, D, false, true><<<grid1, block, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, out->data, out->wd, out->ht, P); \
+      break; } \
     if(P.out_f32) k_pointwise_t<A, B, C, D, true, false><<<grid1, block, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, out->data, out->wd, out->ht, P); \
     else k_pointwise_t<A, B, C, D, false, false><<<grid1, block, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, out->data, out->wd, out->ht, P); \
     break;

@@ -208,7 +208,7 @@ VKB_DEV f3 adjust_colour_dng(f3 col0, f3 col1)
   if(col0.z > col0.y) { SWP(col0.z, col0.y) SWP(col1.z, col1.y) fx = true; }
   if(col0.y > col0.x) { SWP(col0.x, col0.y) SWP(col1.x, col1.y) fy = true; }
   if(col0.z > col0.y) { SWP(col0.z, col0.y) SWP(col1.z, col1.y) fz = true; }
-  col1.y = mixf(col1.z, col1.x, (col0.y - col0.z + 1e-6f) / (col0.x - col0.z + 1e-6f));
+  col1.y = mixf(col1.z, col1.x, __fdividef(col0.y - col0.z + 1e-6f, col0.x - col0.z + 1e-6f)); // blend factor: 2 ulp is plenty
   if(fz) SWP(col1.z, col1.y)
   if(fy) SWP(col1.x, col1.y)
   if(fx) SWP(col1.z, col1.y)
