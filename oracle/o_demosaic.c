@@ -27,6 +27,45 @@ void o_demosaic_down(const oimg_t *in, oimg_t *out, uint32_t filters)
   }
 }
 
+/* demosaic/halfsize.comp:15-52 */
+void o_demosaic_halfsize(const oimg_t *in, oimg_t *out, uint32_t filters)
+{
+#pragma omp parallel for schedule(static)
+  for(int y = 0; y < out->h; y++) for(int x = 0; x < out->w; x++)
+  {
+    float rgba[4];
+    if(filters == 9)
+    {
+      float c[9];
+      for(int i = 0; i < 3; i++) for(int j = 0; j < 3; j++) c[3*i+j] = o_fetch1(in, 3*x + i, 3*y + j);
+      rgba[1] = (c[0] + c[2] + c[4] + c[6] + c[8]) * 1.0f / 5.0f;
+      const float col0 = (c[1] + c[7]) * 0.5f, col1 = (c[3] + c[5]) * .5f;
+      if(((x + y) & 1) > 0) { rgba[0] = col0; rgba[2] = col1; }
+      else                  { rgba[2] = col0; rgba[0] = col1; }
+      rgba[3] = 1.0f; /* left undefined by the shader */
+    }
+    else
+    {
+      float c[4];
+      o_gather(in, 2.0 * (x + .5) / (double)in->w, 2.0 * (y + .5) / (double)in->h, c);
+      rgba[0] = c[3]; rgba[1] = (c[0] + c[2]) / 2.0f; rgba[2] = c[1]; rgba[3] = 1.0f;
+    }
+    o_store4(out, x, y, rgba, 1);
+  }
+}
+
+/* shared/resample.comp:26-40 (returns after the catmull rom lookup) */
+void o_resample(const oimg_t *in, oimg_t *out)
+{
+#pragma omp parallel for schedule(static)
+  for(int y = 0; y < out->h; y++) for(int x = 0; x < out->w; x++)
+  {
+    float res[4];
+    o_sample_catmull_rom(in, ((float)x + 0.5f) / (float)out->w, ((float)y + 0.5f) / (float)out->h, res);
+    o_store4(out, x, y, res, 1);
+  }
+}
+
 /* demosaic/gauss.comp:17-126 */
 void o_demosaic_gauss(const oimg_t *orig, oimg_t *out, uint32_t filters)
 {

@@ -57,6 +57,15 @@ void o_hilite_module(const oimg_t *in, oimg_t *out, const o_hilite_params_t *p, 
 void o_demosaic_module(const oimg_t *in, oimg_t *out, const o_demosaic_params_t *p, uint32_t filters)
 {
   const int block = filters == 9 ? 3 : 2;
+  if(p->method == 2)
+  { /* demosaic/main.c:93-112: half size; out is ((w+1)/2, (h+1)/2), resampled when the block is not 2 */
+    if(out->w == in->w / block && out->h == in->h / block) { o_demosaic_halfsize(in, out, filters); return; }
+    oimg_t half = o_img_alloc(in->w / block, in->h / block, 4);
+    o_demosaic_halfsize(in, &half, filters);
+    o_resample(&half, out);
+    o_img_free(&half);
+    return;
+  }
   oimg_t cov = o_img_alloc(in->w / block, in->h / block, 4);
   oimg_t green = o_img_alloc(in->w, in->h, 1);
   o_demosaic_gauss(in, &cov, filters);
@@ -118,7 +127,8 @@ void o_darkroom_defaults(o_darkroom_t *d, uint32_t width, uint32_t height)
 
 void o_darkroom_out_size(const o_darkroom_t *d, uint32_t *out_w, uint32_t *out_h)
 {
-  const uint32_t w = d->crop_aabb[2] - d->crop_aabb[0], h = d->crop_aabb[3] - d->crop_aabb[1];
+  uint32_t w = d->crop_aabb[2] - d->crop_aabb[0], h = d->crop_aabb[3] - d->crop_aabb[1];
+  if(d->demosaic.method == 2) { w = (w + 1) / 2; h = (h + 1) / 2; } /* demosaic/main.c:29-33 */
   o_crop_roi_out(d->orientation, w, h, d->crop.crop, &d->crop.rotate, out_w, out_h);
 }
 
@@ -144,7 +154,8 @@ int o_darkroom_run(const o_darkroom_t *d, const uint16_t *raw, float *out, int s
   o_img_free(&den);
   if(stage == 2) { copy_out(&hil, stage_out); o_img_free(&hil); return 0; }
 
-  oimg_t dem = o_img_alloc(cw, ch, 4);
+  const int dw = d->demosaic.method == 2 ? (cw + 1) / 2 : cw, dh = d->demosaic.method == 2 ? (ch + 1) / 2 : ch;
+  oimg_t dem = o_img_alloc(dw, dh, 4);
   o_demosaic_module(&hil, &dem, &d->demosaic, d->filters);
   o_img_free(&hil);
   if(stage == 3) { copy_out(&dem, stage_out); o_img_free(&dem); return 0; }
@@ -152,7 +163,7 @@ int o_darkroom_run(const o_darkroom_t *d, const uint16_t *raw, float *out, int s
   uint32_t ow, oh;
   o_darkroom_out_size(d, &ow, &oh);
   float fc[20];
-  o_crop_commit(d->orientation, cw, ch, d->crop.perspect, d->crop.crop, &d->crop.rotate, fc);
+  o_crop_commit(d->orientation, dw, dh, d->crop.perspect, d->crop.crop, &d->crop.rotate, fc);
   oimg_t crp = o_img_alloc(ow, oh, 4);
   o_crop_main(&dem, &crp, fc);
   o_img_free(&dem);

@@ -48,6 +48,8 @@ void o_hilite_doub(const oimg_t *in, const oimg_t *coarse, oimg_t *out, const o_
 
 /* demosaic */
 void o_demosaic_down(const oimg_t *in, oimg_t *out, uint32_t filters);
+void o_demosaic_halfsize(const oimg_t *in, oimg_t *out, uint32_t filters);
+void o_resample(const oimg_t *in, oimg_t *out);
 void o_demosaic_gauss(const oimg_t *orig, oimg_t *out, uint32_t filters);
 void o_demosaic_splat(const oimg_t *in, const oimg_t *gauss, oimg_t *out, uint32_t filters);
 void o_demosaic_fix(const oimg_t *in, const oimg_t *green, const oimg_t *cov, oimg_t *out, uint32_t filters, int fixup);

@@ -160,3 +160,31 @@ def test_xtrans_end_to_end(gpu, oracle, strength):
     p = psnr(out[..., :3], want[..., :3])
     print("xtrans strength %.1f: max abs %.3g psnr %.1f" % (strength, err.max(), p))
     assert p >= 60.0 and (err > 1e-3).mean() <= 1e-4 and err.max() <= 5e-3, (err.max(), p)
+
+
+@pytest.mark.parametrize("xtrans", [False, True])
+def test_halfsize_demosaic(gpu, oracle, xtrans):
+    """demosaic:method 2 (demosaic/main.c:93-112): half-size output; x-trans adds a real shared/resample node (3 -> 2)."""
+    w, h = (516, 408) if xtrans else (512, 420)
+    raw = synth.mosaic(w, h, seed=41, xtrans=xtrans)
+    d = _oracle_cfg(oracle, w, h)
+    d.demosaic.method = 2
+    if xtrans:
+        d.filters = 9
+    want = oracle.darkroom_run(d, raw)
+    g = gpu.Graph(cfg_text=gpu.DARKROOM_CFG.format(src="i-raw"))
+    assert g.line("param:demosaic:01:method:2") == 0
+    buf = np.ascontiguousarray(raw)
+    g.set_source(buf.ctypes.data, gpu.raw_params(w, h, wb=WB, cam_to_rec2020=CAM, filters=9 if xtrans else 0x5d5d5d5d))
+    g.set_sink_buffer(None, 0)
+    g.run()
+    ow, oh = g.sink_size()
+    assert (oh, ow) == want.shape[:2]
+    out = np.zeros((oh, ow, 4), dtype=np.float32)
+    g.set_sink_buffer(out.ctypes.data, out.nbytes)
+    g.run(gpu.RUN_RECORD | gpu.RUN_UPLOAD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT)
+    perf = g.perf()
+    assert "demosaic_halfsize" in perf and ("shared_resample" in perf) == xtrans
+    err = np.abs(out[..., :3] - want[..., :3])
+    p = psnr(out[..., :3], want[..., :3])
+    assert p >= 60.0 and (err > 1e-3).mean() <= 1e-4 and err.max() <= 5e-3, (err.max(), p)

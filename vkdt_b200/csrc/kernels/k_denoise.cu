@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(256) k_denoise_down(const uint2 *__restrict__ 
   st_rgba(out, w, ox, oy, make_float4(sum[0] / wgt[0], sum[1] / wgt[1], sum[2] / wgt[2], 1.0f));
 }
 
-struct asm_consts_t { float rgb_to_yuv[9], yuv_to_rgb[9]; float wb[3], black[3], white[3]; float noise_a, noise_b, blk, thrs0; };
+struct asm_consts_t { float rgb_to_yuv[9], yuv_to_rgb[9]; float wb[3], black[3], white[3]; float noise_a, noise_b, blk, thrs0, i2thrs0; float inorm[3], denorm[3]; };
 
 // ---- assemble: wavelet shrinkage over the 4 detail bands (assemble.comp:43-165) ----
 __global__ void __launch_bounds__(256) k_denoise_assemble(const uint2 *__restrict__ s0, const uint2 *__restrict__ s1, const uint2 *__restrict__ s2,
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(256) k_denoise_assemble(const uint2 *__restric
   for(int l = 0; l < 4; l++)
   {
 #pragma unroll
-    for(int k = 0; k < 3; k++) d[l][k] = (d[l][k] - d[l + 1][k]) / (sigma[k] * bb[l]);
+    for(int k = 0; k < 3; k++) d[l][k] = (d[l][k] - d[l + 1][k]) * __frcp_rn(sigma[k] * bb[l]);
     len[l] = sqrtf(d[l][0] * d[l][0] + d[l][1] * d[l][1] + d[l][2] * d[l][2]);
   }
   const float slope = ((len[3] - len[0]) / 3.0f + (len[2] - len[1]) / 1.0f + (len[1] - len[0]) / 1.0f
@@ -239,12 +239,13 @@ __global__ void __launch_bounds__(256) k_denoise_assemble(const uint2 *__restric
 #pragma unroll
   for(int l = 3; l >= 0; l--)
   {
-    const float thrs = fabsf(d[l][0]) > 10.0f ? 10000.0f : K.thrs0;
+    const bool big = fabsf(d[l][0]) > 10.0f;
+    const float thrs = big ? 10000.0f : K.thrs0, i2t = big ? 0.5f / 10000.0f : K.i2thrs0;
 #pragma unroll
     for(int k = 0; k < 3; k++)
     {
       const float a = fabsf(d[l][k]);
-      const float tt = fminf(1.0f, a / (2.0f * thrs));
+      const float tt = fminf(1.0f, a * i2t);
       down4[k] += sigma[k] * bb[l] * signf(d[l][k]) * mixf(fmaxf(a - thrs, 0.0f), a, tt);
     }
   }
@@ -253,8 +254,8 @@ __global__ void __launch_bounds__(256) k_denoise_assemble(const uint2 *__restric
 #pragma unroll
   for(int k = 0; k < 3; k++)
   {
-    v[k]  = (down4[k] - K.black[k]) / (K.white[k] - K.black[k]) * K.wb[k];
-    vo[k] = (og[k]    - K.black[k]) / (K.white[k] - K.black[k]) * K.wb[k];
+    v[k]  = (down4[k] - K.black[k]) * K.inorm[k];
+    vo[k] = (og[k]    - K.black[k]) * K.inorm[k];
   }
 #pragma unroll
   for(int j = 0; j < 3; j++)
@@ -265,9 +266,7 @@ __global__ void __launch_bounds__(256) k_denoise_assemble(const uint2 *__restric
   yuv[0] = mixf(yuvo[0], yuv[0], p.luma);
 #pragma unroll
   for(int j = 0; j < 3; j++) rgb[j] = K.yuv_to_rgb[3 * j] * yuv[0] + K.yuv_to_rgb[3 * j + 1] * yuv[1] + K.yuv_to_rgb[3 * j + 2] * yuv[2];
-  st_rgba(out, w, x, y, make_float4(rgb[0] / K.wb[0] * (K.white[0] - K.black[0]) + K.black[0],
-                                    rgb[1] / K.wb[1] * (K.white[1] - K.black[1]) + K.black[1],
-                                    rgb[2] / K.wb[2] * (K.white[2] - K.black[2]) + K.black[2], test));
+  st_rgba(out, w, x, y, make_float4(rgb[0] * K.denorm[0] + K.black[0], rgb[1] * K.denorm[1] + K.black[1], rgb[2] * K.denorm[2] + K.black[2], test));
 }
 
 // ---- doub: per-colour residual shrink on the full resolution mosaic (doub.comp:35-115) ----
@@ -388,6 +387,12 @@ static int launch_assemble(const vkb_launch_t *l)
   K.noise_a = pc->noise_a; K.noise_b = pc->noise_b;
   K.blk = pc->filters == 0u ? 1.0f : (pc->filters == 9u ? 2.23607f : 1.414213f);
   K.thrs0 = powf(p.strength, 4.0f);
+  K.i2thrs0 = 1.0f / (2.0f * K.thrs0);
+  for(int k = 0; k < 3; k++)
+  { // per-launch constants: wb/(white-black) and its inverse, computed in double
+    K.inorm[k]  = (float)((double)K.wb[k] / ((double)K.white[k] - (double)K.black[k]));
+    K.denorm[k] = (float)(((double)K.white[k] - (double)K.black[k]) / (double)K.wb[k]);
+  }
   host_escale(&p);
   k_denoise_assemble<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint2 *)c[0].data, (const uint2 *)c[1].data, (const uint2 *)c[2].data,
       (const uint2 *)c[3].data, (const uint2 *)c[4].data, (uint2 *)out->data, out->wd, out->ht, p, K);

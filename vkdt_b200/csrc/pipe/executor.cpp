@@ -278,7 +278,7 @@ static int build_plan(dt_graph_t *g, bool with_device)
         B.consumers[{n, 1}].clear();
         B.consumed[n] = 1;
       }
-      else { delete p; return vkb_set_error(VKB_ERR_GRAPH, "shared/resample with a scale factor is outside the hot path"); }
+      // otherwise a real resample: generic (shared, resample) launch below
     }
     if(is_node(nd, "demosaic", "down"))
     { // dead: gauss.comp never samples it

@@ -508,10 +508,25 @@ static void demosaic_create_nodes(dt_graph_t *graph, dt_module_t *module)
   const int method = dt_module_param_int(module, 1)[0];
   const float scale = (float)module->connector[0].roi.wd / (float)module->connector[1].roi.wd;
   const int halfsize = (scale >= 1.5 * block) || (method == 2);
-  if(halfsize || method == 1)
-  {
-    fprintf(stderr, "[vkdt_b200] demosaic: method %d / half size output is not built yet (SURVEY §8 a6); using gaussian splats at full size\n", method);
+  if(halfsize)
+  { // demosaic/main.c:93-112
+    const int id_half = dt_node_add(graph, module, "demosaic", "halfsize", roi_half.wd, roi_half.ht, 1, sizeof(pc), pc, 2,
+        "input",  "read",  "rggb", "*",   dt_no_roi,
+        "output", "write", "rgba", "f16", &roi_half);
+    dt_connector_copy(graph, module, 0, id_half, 0);
+    if(block != scale)
+    { // resample to get to the rest of the resolution, only if block != scale
+      const int id_resample = dt_node_add(graph, module, "shared", "resample", module->connector[1].roi.wd, module->connector[1].roi.ht, 1, 0, 0, 2,
+          "input",  "read",  "rgba", "f16", dt_no_roi,
+          "output", "write", "rgba", "f16", &module->connector[1].roi);
+      CONN(dt_node_connect(graph, id_half, 1, id_resample, 0));
+      dt_connector_copy(graph, module, 1, id_resample, 1);
+    }
+    else dt_connector_copy(graph, module, 1, id_half, 1);
+    return;
   }
+  if(method == 1)
+    fprintf(stderr, "[vkdt_b200] demosaic: method 1 (RCD) is not built yet (SURVEY §8 a6); using gaussian splats\n");
   const int id_down = dt_node_add(graph, module, "demosaic", "down", wd / block, ht / block, 1, sizeof(pc), pc, 2,
       "input", "read", "rggb", "*", dt_no_roi,
       "output", "write", "y", "f16", &roi_half);
