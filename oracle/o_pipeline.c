@@ -53,6 +53,9 @@ void o_hilite_module(const oimg_t *in, oimg_t *out, const o_hilite_params_t *p, 
   for(int l = 0; l <= L; l++) o_img_free(&lvl[l]);
 }
 
+/* white balance pushed to rcd_fill (img_param->whitebalance of demosaic's input, demosaic/main.c:89-90); set by the caller */
+float o_demosaic_wb[4] = { 1.0f, 1.0f, 1.0f, 1.0f };
+
 /* demosaic/main.c:159-202, method 0 (1:1 shared/resample node is the identity and elided) */
 void o_demosaic_module(const oimg_t *in, oimg_t *out, const o_demosaic_params_t *p, uint32_t filters)
 {
@@ -64,6 +67,14 @@ void o_demosaic_module(const oimg_t *in, oimg_t *out, const o_demosaic_params_t 
     o_demosaic_halfsize(in, &half, filters);
     o_resample(&half, out);
     o_img_free(&half);
+    return;
+  }
+  if(p->method == 1 && filters != 9)
+  { /* demosaic/main.c:116-156: RCD.  wb travels in the unused tail of the params struct (see o_darkroom_run) */
+    oimg_t vh = o_img_alloc(in->w, in->h, 1), pq = o_img_alloc(in->w / 2, in->h, 1), lp = o_img_alloc(in->w / 2, in->h, 1);
+    o_rcd_conv(in, &vh, &pq, &lp);
+    o_rcd_fill(in, &vh, &pq, &lp, out, o_demosaic_wb);
+    o_img_free(&vh); o_img_free(&pq); o_img_free(&lp);
     return;
   }
   oimg_t cov = o_img_alloc(in->w / block, in->h / block, 4);
@@ -156,6 +167,7 @@ int o_darkroom_run(const o_darkroom_t *d, const uint16_t *raw, float *out, int s
 
   const int dw = d->demosaic.method == 2 ? (cw + 1) / 2 : cw, dh = d->demosaic.method == 2 ? (ch + 1) / 2 : ch;
   oimg_t dem = o_img_alloc(dw, dh, 4);
+  for(int k = 0; k < 4; k++) o_demosaic_wb[k] = d->whitebalance[k];
   o_demosaic_module(&hil, &dem, &d->demosaic, d->filters);
   o_img_free(&hil);
   if(stage == 3) { copy_out(&dem, stage_out); o_img_free(&dem); return 0; }

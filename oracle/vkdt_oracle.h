@@ -50,6 +50,8 @@ void o_hilite_doub(const oimg_t *in, const oimg_t *coarse, oimg_t *out, const o_
 void o_demosaic_down(const oimg_t *in, oimg_t *out, uint32_t filters);
 void o_demosaic_halfsize(const oimg_t *in, oimg_t *out, uint32_t filters);
 void o_resample(const oimg_t *in, oimg_t *out);
+void o_rcd_conv(const oimg_t *cfa, oimg_t *vh, oimg_t *pq, oimg_t *lp);
+void o_rcd_fill(const oimg_t *cfa, const oimg_t *vh, const oimg_t *pq, const oimg_t *lp, oimg_t *out, const float *wb);
 void o_demosaic_gauss(const oimg_t *orig, oimg_t *out, uint32_t filters);
 void o_demosaic_splat(const oimg_t *in, const oimg_t *gauss, oimg_t *out, uint32_t filters);
 void o_demosaic_fix(const oimg_t *in, const oimg_t *green, const oimg_t *cov, oimg_t *out, uint32_t filters, int fixup);

@@ -188,3 +188,31 @@ def test_halfsize_demosaic(gpu, oracle, xtrans):
     err = np.abs(out[..., :3] - want[..., :3])
     p = psnr(out[..., :3], want[..., :3])
     assert p >= 60.0 and (err > 1e-3).mean() <= 1e-4 and err.max() <= 5e-3, (err.max(), p)
+
+
+@pytest.mark.parametrize("dims", [(512, 420), (646, 412)])
+def test_rcd_demosaic(gpu, oracle, dims):
+    """demosaic:method 1 (RCD, demosaic/main.c:116-156) against the tiling-independent restatement (oracle/o_rcd.c)."""
+    w, h = dims
+    raw = synth.mosaic(w, h, seed=51)
+    d = _oracle_cfg(oracle, w, h)
+    d.demosaic.method = 1
+    dem_want = oracle.darkroom_run(d, raw, 3)
+    want = oracle.darkroom_run(d, raw)
+    g = gpu.Graph(cfg_text=gpu.DARKROOM_CFG.format(src="i-raw"))
+    assert g.line("param:demosaic:01:method:1") == 0
+    buf = np.ascontiguousarray(raw)
+    g.set_source(buf.ctypes.data, gpu.raw_params(w, h, wb=WB, cam_to_rec2020=CAM))
+    g.set_sink_buffer(None, 0)
+    g.run()
+    ow, oh = g.sink_size()
+    out = np.zeros((oh, ow, 4), dtype=np.float32)
+    g.set_sink_buffer(out.ctypes.data, out.nbytes)
+    g.run(gpu.RUN_RECORD | gpu.RUN_UPLOAD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT)
+    perf = g.perf()
+    assert "demosaic_rcd_conv" in perf and "demosaic_rcd_fill" in perf and "demosaic_splat" not in perf
+    assert np.isfinite(dem_want).all()
+    err = np.abs(out[..., :3] - want[..., :3])
+    p = psnr(out[..., :3], want[..., :3])
+    print("rcd: max abs %.3g psnr %.1f" % (err.max(), p))
+    assert p >= 60.0 and (err > 1e-3).mean() <= 1e-4 and err.max() <= 5e-3, (err.max(), p)

@@ -525,8 +525,38 @@ static void demosaic_create_nodes(dt_graph_t *graph, dt_module_t *module)
     else dt_connector_copy(graph, module, 1, id_half, 1);
     return;
   }
-  if(method == 1)
-    fprintf(stderr, "[vkdt_b200] demosaic: method 1 (RCD) is not built yet (SURVEY §8 a6); using gaussian splats\n");
+  if(method == 1 && block == 2)
+  { // bayer with RCD (demosaic/main.c:116-156).  the reference sizes rcd_fill's dispatch in 64x32 shared memory tiles;
+    // our kernel tiles internally, the node keeps the image extent
+    dt_roi_t hr = module->connector[0].roi;
+    hr.wd /= 2;
+    const int id_conv = dt_node_add(graph, module, "demosaic", "rcd_conv", wd, ht, 1, 0, 0, 4,
+        "cfa", "read",  "*", "*",   dt_no_roi,
+        "vh",  "write", "r", "f16", &module->connector[0].roi,
+        "pq",  "write", "r", "f16", &hr,
+        "lp",  "write", "r", "f16", &hr);
+    const int id_fill = dt_node_add(graph, module, "demosaic", "rcd_fill", wd, ht, 1, sizeof(pc), pc, 5,
+        "cfa", "read", "*", "*", dt_no_roi,
+        "vh",  "read", "*", "*", dt_no_roi,
+        "pq",  "read", "*", "*", dt_no_roi,
+        "lp",  "read", "*", "*", dt_no_roi,
+        "output", "write", "rgba", "f16", &module->connector[0].roi);
+    CONN(dt_node_connect_named(graph, id_conv, "vh", id_fill, "vh"));
+    CONN(dt_node_connect_named(graph, id_conv, "pq", id_fill, "pq"));
+    CONN(dt_node_connect_named(graph, id_conv, "lp", id_fill, "lp"));
+    dt_connector_copy(graph, module, 0, id_conv, 0);
+    dt_connector_copy(graph, module, 0, id_fill, 0);
+    if(module->connector[1].roi.marker & s_roi_mark_hard)
+    {
+      const int id_resample = dt_node_add(graph, module, "shared", "resample", module->connector[1].roi.wd, module->connector[1].roi.ht, 1, 0, 0, 2,
+          "input",  "read",  "rgba", "f16", dt_no_roi,
+          "output", "write", "rgba", "f16", &module->connector[1].roi);
+      CONN(dt_node_connect(graph, id_fill, 4, id_resample, 0));
+      dt_connector_copy(graph, module, 1, id_resample, 1);
+    }
+    else dt_connector_copy(graph, module, 1, id_fill, 4);
+    return;
+  }
   const int id_down = dt_node_add(graph, module, "demosaic", "down", wd / block, ht / block, 1, sizeof(pc), pc, 2,
       "input", "read", "rggb", "*", dt_no_roi,
       "output", "write", "y", "f16", &roi_half);
