@@ -128,6 +128,10 @@ typedef struct vkb_raw_params_t
   uint32_t packed_bpp;         /* 0: `data` is u16 per pixel; 10/12/14: MLV style packed bit stream, unpacked on the device */
 } vkb_raw_params_t;
 VKB_API int  vkb_graph_set_source(vkb_graph_t *g, const char *inst, const void *data, const vkb_raw_params_t *p);
+/* what `param:i-raw:main:filename:<file>.dng` resolves to (uncompressed 16-bit cfa dng only): the image parameters the
+ * reference's loader hands to the graph (i-raw/rawloader-c/lib.rs:137-279, i-raw/main.c:138-256) and the cfa offset of
+ * the emitted window.  no GPU needed. */
+VKB_API int  vkb_dng_info(const char *filename, vkb_raw_params_t *p, uint32_t *cfa_off_x, uint32_t *cfa_off_y);
 /* redirect a sink (o-pfm:main ...) into caller memory instead of a file: rgba f32, wd*ht*16 bytes */
 VKB_API int  vkb_graph_set_sink_buffer(vkb_graph_t *g, const char *inst, void *dst, size_t bytes);
 VKB_API int  vkb_graph_sink_size(vkb_graph_t *g, const char *inst, uint32_t *wd, uint32_t *ht);

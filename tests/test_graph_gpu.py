@@ -216,3 +216,45 @@ def test_rcd_demosaic(gpu, oracle, dims):
     p = psnr(out[..., :3], want[..., :3])
     print("rcd: max abs %.3g psnr %.1f" % (err.max(), p))
     assert p >= 60.0 and (err > 1e-3).mean() <= 1e-4 and err.max() <= 5e-3, (err.max(), p)
+
+
+@pytest.mark.parametrize("cfa,xtrans", [(((1, 2), (0, 1)), False), (None, True)])
+def test_iraw_dng_file_source(gpu, oracle, tmp_path, cfa, xtrans):
+    """`param:i-raw:main:filename:x.dng`: the file path of the source module (uncompressed cfa dng).  the stored cfa
+    phase is off the canonical one, so the module has to emit the aligned window (i-raw/main.c:283-288)."""
+    w, h = 531, 402
+    if xtrans:
+        stored = np.roll(synth.XTRANS, (-4, -1), axis=(0, 1))
+    else:
+        stored = np.array(cfa)
+    full = np.zeros((h, w), np.uint16)
+    fn = str(tmp_path / "still.dng")
+    # build the file around an aligned mosaic so that the expected window is known
+    p0 = None
+    synth.write_dng(fn, full, cfa=stored, black=2048, white=15000, neutral=(0.5, 1.0, 2.0 / 3.0), color_matrix=CAM)
+    p0, ox, oy = gpu.dng_info(fn)
+    ww, hh = p0.width, p0.height
+    win = synth.mosaic(ww, hh, seed=23, xtrans=xtrans)
+    full[oy:oy + hh, ox:ox + ww] = win
+    synth.write_dng(fn, full, cfa=stored, black=2048, white=15000, neutral=(0.5, 1.0, 2.0 / 3.0), color_matrix=CAM)
+    g = gpu.Graph(cfg_text=gpu.DARKROOM_CFG.format(src="i-raw"))
+    assert g.line("param:i-raw:main:filename:%s" % fn) == 0
+    assert g.line("param:i-raw:main:noise a:100.0") == 0 and g.line("param:i-raw:main:noise b:2.0") == 0
+    g.set_sink_buffer(None, 0)
+    g.run()
+    ow, oh = g.sink_size()
+    got = np.zeros((oh, ow, 4), dtype=np.float32)
+    g.set_sink_buffer(got.ctypes.data, got.nbytes)
+    g.run(gpu.RUN_RECORD | gpu.RUN_UPLOAD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT)
+    d = oracle.darkroom_defaults(ww, hh)
+    d.filters = 9 if xtrans else d.filters
+    d.noise_a, d.noise_b = 100.0, 2.0
+    for k in range(4): d.whitebalance[k] = p0.whitebalance[k]
+    for k in range(9): d.cam_to_rec2020[k] = p0.cam_to_rec2020[k]
+    for k in range(4): d.crop_aabb[k] = p0.crop_aabb[k]
+    want = oracle.darkroom_run(d, win)
+    assert got.shape == want.shape
+    err = np.abs(got[..., :3] - want[..., :3])
+    p = psnr(got[..., :3], want[..., :3])
+    print("max abs %.3g psnr %.1f" % (err.max(), p))
+    assert p >= 60.0 and (err > 1e-3).mean() <= 1e-5 and err.max() <= 2e-3

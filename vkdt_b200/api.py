@@ -44,7 +44,7 @@ vkb_event_sync vkb_event_elapsed_ms vkb_event_destroy vkb_dispatch vkb_kernel_co
 vkb_kernel_name vkb_launch_count vkb_launch_count_reset vkb_graph_new vkb_graph_free vkb_graph_read_config_ascii
 vkb_graph_read_config_line vkb_graph_replace_display vkb_graph_set_source vkb_graph_set_sink_buffer
 vkb_graph_sink_size vkb_graph_set_frame vkb_graph_run vkb_graph_plan vkb_graph_perf vkb_graph_dump_nodes
-vkb_graph_set_source_device vkb_graph_sink_device vkb_graph_pool_bytes vkb_graph_stream vkb_graph_set_device""".split()
+vkb_graph_set_source_device vkb_graph_sink_device vkb_graph_pool_bytes vkb_graph_stream vkb_graph_set_device vkb_dng_info""".split()
 
 
 def token(s):
@@ -115,6 +115,7 @@ lib.vkb_host_free.argtypes = [C.c_void_p]
 lib.vkb_graph_stream.argtypes = [C.c_void_p]
 lib.vkb_graph_stream.restype = C.c_void_p
 lib.vkb_graph_set_device.argtypes = [C.c_void_p, C.c_int]
+lib.vkb_dng_info.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
 lib.vkb_event_create.argtypes = [C.POINTER(C.c_void_p)]
 lib.vkb_event_record.argtypes = [C.c_void_p, C.c_void_p]
 lib.vkb_event_sync.argtypes = [C.c_void_p]
@@ -284,6 +285,14 @@ class Graph:
             self.close()
         except Exception:
             pass
+
+
+def dng_info(filename):
+    """(RawParams, cfa_off_x, cfa_off_y) of an uncompressed cfa dng, as i-raw resolves it.  Host only."""
+    p = RawParams()
+    ox, oy = C.c_uint32(0), C.c_uint32(0)
+    check(lib.vkb_dng_info(filename.encode(), C.byref(p), C.byref(ox), C.byref(oy)))
+    return p, ox.value, oy.value
 
 
 def raw_params(width, height, black=2048.0, white=15000.0, wb=(1.0, 1.0, 1.0), cam_to_rec2020=None, filters=0x5d5d5d5d,

@@ -1,5 +1,6 @@
 // graph layer of the C-ABI (include/vkdt_b200.h §3): thin extern "C" wrappers over the pipe model + executor.
 #include "pipe.h"
+#include "dng.h"
 #include "mlv.h"
 
 int vkb_plan_sink(dt_graph_t *g, int modid, uint32_t *wd, uint32_t *ht, void **dptr);
@@ -115,6 +116,13 @@ int vkb_graph_plan(vkb_graph_t *h, char *buf, size_t bufsize)
   return VKB_OK;
 }
 void *vkb_graph_stream(vkb_graph_t *h) { return h ? vkb_plan_stream(h->g) : 0; }
+int vkb_dng_info(const char *filename, vkb_raw_params_t *p, uint32_t *ox, uint32_t *oy)
+{
+  if(!filename || !p) return VKB_ERR_BAD_ARG;
+  dng_image_t img;
+  if(dng_read(filename, &img)) return VKB_ERR_IO;
+  return dng_raw_params(&img, p, ox, oy) ? VKB_ERR_BAD_ARG : VKB_OK;
+}
 int vkb_graph_set_device(vkb_graph_t *h, int device) { if(!h) return VKB_ERR_BAD_ARG; h->g->device = device; return VKB_OK; }
 uint64_t vkb_graph_pool_bytes(vkb_graph_t *h) { return h ? vkb_plan_pool_bytes(h->g) : 0; }
 

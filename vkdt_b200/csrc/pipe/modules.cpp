@@ -5,6 +5,8 @@
 // operation order because integer sizes fall out of float math (crop/main.c:270-274).
 #include "pipe.h"
 #include "mlv.h"
+#include "dng.h"
+#include <strings.h>
 #include <math.h>
 #include <stdlib.h>
 #include <stdarg.h>
@@ -113,6 +115,7 @@ static void parse_def(const module_def_t &d, dt_module_so_t *so)
   void m##_roi_in(dt_graph_t *, dt_module_t *); void m##_create_nodes(dt_graph_t *, dt_module_t *); void m##_commit(dt_graph_t *, dt_module_t *);
 
 static int  iraw_init(dt_module_t *);
+static void iraw_cleanup(dt_module_t *);
 static void iraw_roi_out(dt_graph_t *, dt_module_t *);
 static int  iraw_read_source(dt_module_t *, void *, dt_read_source_params_t *);
 static int  imlv_init(dt_module_t *);
@@ -149,7 +152,7 @@ static std::vector<dt_module_so_t> &registry()
     dt_module_so_t so = {};
     parse_def(d, &so);
     const std::string n = d.name;
-    if(n == "i-raw")    { so.init = iraw_init; so.modify_roi_out = iraw_roi_out; so.read_source = iraw_read_source; }
+    if(n == "i-raw")    { so.init = iraw_init; so.cleanup = iraw_cleanup; so.modify_roi_out = iraw_roi_out; so.read_source = iraw_read_source; }
     if(n == "i-mlv")    { so.init = imlv_init; so.cleanup = imlv_cleanup; so.modify_roi_out = imlv_roi_out; so.read_source = imlv_read_source; }
     if(n == "denoise")  { so.modify_roi_in = denoise_roi_in; so.modify_roi_out = denoise_roi_out; so.create_nodes = denoise_create_nodes; }
     if(n == "hilite")   { so.create_nodes = hilite_create_nodes; }
@@ -188,11 +191,65 @@ static void fill_img_param(dt_module_t *mod, const vkb_raw_params_t *p)
   ip->colour_primaries = 0; // s_colour_primaries_custom: use cam_to_rec2020
   ip->colour_trc = 0;       // linear
 }
-static int iraw_init(dt_module_t *mod) { mod->flags = s_module_request_read_source; return 0; }
+// file source: uncompressed 16-bit cfa dng (pipe/dng.cpp); camera formats proper stay with rawler / rawspeed
+struct iraw_file_t { std::string filename; dng_image_t img; vkb_raw_params_t p; uint32_t ox = 0, oy = 0; bool loaded = false; };
+static std::string resource_path(const dt_module_t *mod, const char *fname)
+{ // dt_graph_get_resource_filename: relative to the cfg's directory first
+  std::string path = fname;
+  if(fname[0] != '/' && mod->graph->searchpath[0])
+  {
+    std::string p2 = std::string(mod->graph->searchpath) + "/" + fname;
+    FILE *t = fopen(p2.c_str(), "rb");
+    if(t) { fclose(t); path = p2; }
+  }
+  return path;
+}
+static int iraw_load(dt_module_t *mod)
+{ // i-raw/main.c:60-100 (load_raw): decode once per filename
+  iraw_file_t *d = (iraw_file_t *)mod->data;
+  const char *fname = dt_module_param_string(mod, 0);
+  if(d->loaded && d->filename == fname) return 0;
+  d->loaded = false;
+  const std::string path = resource_path(mod, fname);
+  const size_t len = path.size();
+  if(len < 4 || strcasecmp(path.c_str() + len - 4, ".dng"))
+  { fprintf(stderr, "[i-raw] %s: only uncompressed dng files and in-memory sources are decoded here\n", path.c_str()); return 1; }
+  const int err = dng_read(path.c_str(), &d->img);
+  if(err) { fprintf(stderr, "[i-raw] failed to load raw file %s (%d)\n", path.c_str(), err); return 1; }
+  if(dng_raw_params(&d->img, &d->p, &d->ox, &d->oy)) return 1;
+  d->filename = fname;
+  d->loaded = true;
+  return 0;
+}
+static int iraw_init(dt_module_t *mod) { mod->data = new iraw_file_t(); mod->flags = s_module_request_read_source; return 0; }
+static void iraw_cleanup(dt_module_t *mod) { delete (iraw_file_t *)mod->data; mod->data = 0; }
 static void iraw_roi_out(dt_graph_t *g, dt_module_t *mod)
 {
   const int mid = (int)(mod - g->module.data());
-  if(mid < 0 || mid >= (int)g->mem_source.size() || !g->mem_source[mid].valid) return; // leaves full_wd == 0: graph run fails
+  if(mid < 0 || mid >= (int)g->mem_source.size() || !g->mem_source[mid].valid)
+  {
+    if(iraw_load(mod)) return; // leaves full_wd == 0: graph run fails
+    iraw_file_t *d = (iraw_file_t *)mod->data;
+    fill_img_param(mod, &d->p);
+    dt_image_params_t *ip = &mod->img_param;
+    snprintf(ip->maker, sizeof(ip->maker), "%s", d->img.make);
+    snprintf(ip->model, sizeof(ip->model), "%s", d->img.model);
+    ip->iso = d->img.iso;
+    // i-raw/main.c:172-199: noise profile from the parameters, else from nprof/<maker>-<model>-<iso>.nprof
+    const float na = dt_module_param_float(mod, 1)[0], nb = dt_module_param_float(mod, 2)[0];
+    ip->noise_a = na; ip->noise_b = nb;
+    if(na == 0.0f && nb == 0.0f)
+    {
+      char pname[512];
+      snprintf(pname, sizeof(pname), "nprof/%s-%s-%d.nprof", ip->maker, ip->model, (int)ip->iso);
+      FILE *f = fopen(resource_path(mod, pname).c_str(), "rb");
+      if(f) { float a = 0.0f, b = 0.0f; if(fscanf(f, "%g %g", &a, &b) == 2) { ip->noise_a = a; ip->noise_b = b; } fclose(f); }
+    }
+    mod->connector[0].roi.full_wd = d->p.width;  // already rounded to the cfa block
+    mod->connector[0].roi.full_ht = d->p.height;
+    mod->connector[0].chan = dt_token("rggb");
+    return;
+  }
   const vkb_raw_params_t *p = &g->mem_source[mid].p;
   fill_img_param(mod, p);
   // i-raw/main.c:156-157: dimensions rounded down to the cfa block
@@ -206,7 +263,16 @@ static int iraw_read_source(dt_module_t *mod, void *mapped, dt_read_source_param
 { // i-raw/main.c:281-297: row copy of the aligned window into the mapped staging buffer
   dt_graph_t *g = mod->graph;
   const int mid = (int)(mod - g->module.data());
-  if(mid >= (int)g->mem_source.size() || !g->mem_source[mid].valid || g->mem_source[mid].on_device) return 1;
+  if(mid >= (int)g->mem_source.size() || !g->mem_source[mid].valid)
+  { // file: window starting at the cfa offset (i-raw/main.c:283-288)
+    if(iraw_load(mod)) return 1;
+    const iraw_file_t *d = (const iraw_file_t *)mod->data;
+    const uint32_t wd = mod->connector[0].roi.full_wd, ht = mod->connector[0].roi.full_ht;
+    for(uint32_t j = 0; j < ht; j++)
+      memcpy((uint16_t *)mapped + (size_t)j * wd, d->img.pix.data() + (size_t)(j + d->oy) * d->img.width + d->ox, sizeof(uint16_t) * wd);
+    return 0;
+  }
+  if(g->mem_source[mid].on_device) return 1;
   const vkb_raw_params_t *rp = &g->mem_source[mid].p;
   const uint32_t wd = mod->connector[0].roi.full_wd, ht = mod->connector[0].roi.full_ht;
   const uint16_t *src = (const uint16_t *)g->mem_source[mid].data;

@@ -132,3 +132,85 @@ def write_mlv(filename, frames, bpp=14, black=BLACK, white=WHITE, fps=(24000, 10
             f.write(struct.pack("<4sIQIHHHHI", b"VIDF", 32 + len(payload), 10 + i, i, 0, 0, 0, 0, 0))
             f.write(payload)
     return filename
+
+
+def write_dng(filename, raw, cfa=((0, 1), (1, 2)), black=2048, white=15000, neutral=(0.5, 1.0, 0.6),
+              color_matrix=None, illuminant=21, active_area=None, make="b200", model="synth", iso=100,
+              orientation=1, big_endian=False):
+    """Write `raw` (h x w uint16) as an uncompressed 16-bit CFA DNG (TIFF/EP + DNG 1.4 tags, one strip, raw data in IFD0).
+    cfa: 2x2 or 6x6 nested sequence of 0 r / 1 g / 2 b as stored.  Test input for the i-raw file path."""
+    import struct
+    raw = np.ascontiguousarray(raw, dtype=np.uint16)
+    h, w = raw.shape
+    cfa = np.asarray(cfa, dtype=np.uint8)
+    dim = cfa.shape[0]
+    if color_matrix is None:
+        color_matrix = (0.9, -0.3, -0.1, -0.4, 1.2, 0.2, -0.1, 0.2, 0.7)
+    e = ">" if big_endian else "<"
+
+    def rat(vals, signed=False):
+        out = b""
+        for v in vals:
+            out += struct.pack(e + ("ii" if signed else "II"), int(round(v * 10000)), 10000)
+        return out
+
+    entries = []  # (tag, type, count, payload bytes)
+
+    def add(tag, typ, count, payload):
+        entries.append((tag, typ, count, payload))
+
+    def short(v): return struct.pack(e + "H", v)
+    def long_(v): return struct.pack(e + "I", v)
+    add(254, 4, 1, long_(0))
+    add(256, 4, 1, long_(w))
+    add(257, 4, 1, long_(h))
+    add(258, 3, 1, short(16))
+    add(259, 3, 1, short(1))
+    add(262, 3, 1, short(32803))
+    add(271, 2, len(make) + 1, make.encode() + b"\0")
+    add(272, 2, len(model) + 1, model.encode() + b"\0")
+    add(273, 4, 1, None)  # strip offset, patched below
+    add(274, 3, 1, short(orientation))
+    add(277, 3, 1, short(1))
+    add(278, 4, 1, long_(h))
+    add(279, 4, 1, long_(w * h * 2))
+    add(33421, 3, 2, short(dim) + short(dim))
+    add(33422, 1, dim * dim, cfa.tobytes())
+    add(34855, 3, 1, short(iso))
+    add(50706, 1, 4, bytes((1, 4, 0, 0)))
+    bl = np.broadcast_to(np.asarray(black, dtype=np.float64).ravel(), (4,)) if np.size(black) in (1, 4) else None
+    add(50713, 3, 2, short(2) + short(2))
+    add(50714, 5, 4, rat(bl))
+    add(50717, 4, 1, long_(int(white)))
+    add(50721, 10, 9, rat(color_matrix, True))
+    add(50728, 5, 3, rat(neutral))
+    add(50778, 3, 1, short(illuminant))
+    if active_area is not None:
+        add(50829, 4, 4, b"".join(long_(v) for v in active_area))
+    entries.sort(key=lambda t: t[0])
+    n = len(entries)
+    ifd_off = 8
+    extra_off = ifd_off + 2 + 12 * n + 4
+    extra = b""
+    body = b""
+    strip_patch = None
+    for tag, typ, count, payload in entries:
+        if payload is None:
+            strip_patch = len(body) + 8
+            payload = long_(0)
+        if len(payload) <= 4:
+            val = payload.ljust(4, b"\0")
+        else:
+            if (extra_off + len(extra)) & 1:
+                extra += b"\0"
+            val = long_(extra_off + len(extra))
+            extra += payload
+        body += struct.pack(e + "HHI", tag, typ, count) + val
+    if (extra_off + len(extra)) & 1:
+        extra += b"\0"
+    data_off = extra_off + len(extra)
+    body = body[:strip_patch] + long_(data_off) + body[strip_patch + 4:]
+    hdr = (b"MM" if big_endian else b"II") + struct.pack(e + "HI", 42, ifd_off)
+    pix = raw.astype(">u2" if big_endian else "<u2").tobytes()
+    with open(filename, "wb") as f:
+        f.write(hdr + struct.pack(e + "H", n) + body + long_(0) + extra + pix)
