@@ -229,14 +229,17 @@ def test_iraw_dng_file_source(gpu, oracle, tmp_path, cfa, xtrans):
         stored = np.array(cfa)
     full = np.zeros((h, w), np.uint16)
     fn = str(tmp_path / "still.dng")
+    # xyz -> camera matrix chosen so that the derived camera -> rec2020 matrix is the CAM of the other tests
+    x2r = np.array([[1.71665119, -0.35567078, -0.25336628], [-0.66668435, 1.61648124, 0.01576855], [0.01763986, -0.04277061, 0.94210312]])
+    cm = tuple((np.linalg.inv(np.array(CAM).reshape(3, 3)) @ x2r).ravel())
     # build the file around an aligned mosaic so that the expected window is known
     p0 = None
-    synth.write_dng(fn, full, cfa=stored, black=2048, white=15000, neutral=(0.5, 1.0, 2.0 / 3.0), color_matrix=CAM)
+    synth.write_dng(fn, full, cfa=stored, black=2048, white=15000, neutral=(0.5, 1.0, 2.0 / 3.0), color_matrix=cm)
     p0, ox, oy = gpu.dng_info(fn)
     ww, hh = p0.width, p0.height
     win = synth.mosaic(ww, hh, seed=23, xtrans=xtrans)
     full[oy:oy + hh, ox:ox + ww] = win
-    synth.write_dng(fn, full, cfa=stored, black=2048, white=15000, neutral=(0.5, 1.0, 2.0 / 3.0), color_matrix=CAM)
+    synth.write_dng(fn, full, cfa=stored, black=2048, white=15000, neutral=(0.5, 1.0, 2.0 / 3.0), color_matrix=cm)
     g = gpu.Graph(cfg_text=gpu.DARKROOM_CFG.format(src="i-raw"))
     assert g.line("param:i-raw:main:filename:%s" % fn) == 0
     assert g.line("param:i-raw:main:noise a:100.0") == 0 and g.line("param:i-raw:main:noise b:2.0") == 0

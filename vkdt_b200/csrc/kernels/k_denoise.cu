@@ -74,24 +74,28 @@ __global__ void __launch_bounds__(256) k_denoise_half(const uint16_t *__restrict
 // the hot pixel test fall exactly like in the restatement.
 #define DC_W 36
 #define DC_H 12
-__global__ void __launch_bounds__(256, 3) k_denoise_downcov(const uint2 *__restrict__ in, int w, int h,
+// the j loops stay rolled: 55 registers instead of 128, four CTAs per SM; the unrolled i loop gives the ILP
+__global__ void __launch_bounds__(256, 4) k_denoise_downcov(const uint2 *__restrict__ in, int w, int h,
     uint2 *__restrict__ out, uint2 *__restrict__ covimg)
 {
-  __shared__ float4 tile[DC_H][DC_W];
+  __shared__ float4 tile[DC_H][DC_W];  // r g b lum
+  __shared__ float4 tinv[DC_H][DC_W];  // 1/lum, 1/(lum*lum), lum/25, lum*lum: every tap's divisions, done once per input texel
   const int tx0 = blockIdx.x * 32 - 2, ty0 = blockIdx.y * 8 - 2;
   const int tid = threadIdx.y * 32 + threadIdx.x;
   for(int t = tid; t < DC_W * DC_H; t += 256)
   {
     const int r = t / DC_W, c = t - r * DC_W;
     const float4 v = ld_rgba(in, w, mirrori(tx0 + c, w), mirrori(ty0 + r, h));
-    tile[r][c] = make_float4(v.x, v.y, v.z, lum2020(v.x, v.y, v.z));
+    const float l = lum2020(v.x, v.y, v.z), l2 = l * l;
+    tile[r][c] = make_float4(v.x, v.y, v.z, l);
+    tinv[r][c] = make_float4(1.0f / l, 1.0f / l2, l / 25.0f, l2);
   }
   __syncthreads();
   const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
   if(x >= w || y >= h) return;
   const int lx = threadIdx.x, ly = threadIdx.y; // tile coords of tap (-2,-2)
   float mwx = 0, mwy = 0, mbx = 0, mby = 0, smw = 0, smb = 0;
-#pragma unroll
+#pragma unroll 1
   for(int j = 0; j < 5; j++)
 #pragma unroll
     for(int i = 0; i < 5; i++)
@@ -101,25 +105,25 @@ __global__ void __launch_bounds__(256, 3) k_denoise_downcov(const uint2 *__restr
       mwx += fi * px; mwy += fj * px;
       smw += px;
       // fi / px == fi * (1 / px) bit for bit when fi is 0, +-1 or +-2: scaling a correctly rounded quotient by a power of two is exact
-      const float rcp = 1.0f / px;
+      const float rcp = tinv[ly + j][lx + i].x;
       mbx += fi * rcp; mby += fj * rcp;
       smb += rcp;
     }
   mwx /= smw; mwy /= smw; mbx /= smb; mby /= smb;
   float Sw0 = 0, Sw1 = 0, Sw2 = 0, Sw3 = 0, Sb0 = 0, Sb1 = 0, Sb2 = 0, Sb3 = 0, sw = 0, sb = 0, mean_b = 0;
-#pragma unroll
+#pragma unroll 1
   for(int j = 0; j < 5; j++)
 #pragma unroll
     for(int i = 0; i < 5; i++)
     {
-      const float px = tile[ly + j][lx + i].w;
-      mean_b += px / 25.0f;
-      float p2 = px * px;
+      const float4 q = tinv[ly + j][lx + i];
+      mean_b += q.z;
+      float p2 = q.w;
       float p0 = (float)(i - 2) - mwx, p1 = (float)(j - 2) - mwy;
       Sw0 += p2 * p0 * p0; Sw1 += p2 * p0 * p1; Sw2 += p2 * p1 * p0; Sw3 += p2 * p1 * p1;
       sw += p2;
       p0 = (float)(i - 2) - mbx; p1 = (float)(j - 2) - mby;
-      p2 = 1.0f / (px * px);
+      p2 = q.y;
       Sb0 += p2 * p0 * p0; Sb1 += p2 * p0 * p1; Sb2 += p2 * p1 * p0; Sb3 += p2 * p1 * p1;
       sb += p2;
     }
@@ -133,7 +137,7 @@ __global__ void __launch_bounds__(256, 3) k_denoise_downcov(const uint2 *__restr
   st_rgba(covimg, w, x, y, make_float4(e0, e1, v0x, v0y));
   float r = 0, g = 0, b = 0, wt = 0;
   const float ie0 = 1.0f / e0, ie1 = 1.0f / e1;
-#pragma unroll
+#pragma unroll 1
   for(int j = 0; j < 5; j++)
 #pragma unroll
     for(int i = 0; i < 5; i++)
@@ -270,6 +274,32 @@ __global__ void __launch_bounds__(256) k_denoise_assemble(const uint2 *__restric
 }
 
 // ---- doub: per-colour residual shrink on the full resolution mosaic (doub.comp:35-115) ----
+// the per pixel part after the two coarse lookups: upsm_c / down_c are the pixel's own colour channel of crs0 / crs1, upw = crs0.w
+VKB_DEV float doub_shrink(float val, float upsm_c, float down_c, float upw, int col, bool xt,
+    const denoise_params_t &p, const dn_push_doub_t &P)
+{
+  float black = P.black[1], white = P.white[1];
+  float T = 0.5f * p.strength * upw, blendw = p.luma;
+  if(col != 1)
+  {
+    black = col == 0 ? P.black[0] : P.black[2]; white = col == 0 ? P.white[0] : P.white[2];
+    blendw = 1.0f;
+    if(xt) T /= fmaxf(1e-4f, upw);
+  }
+  float sigma[3];
+  noise_sigma(P.noise_a, P.noise_b, black, white, p.edges, upsm_c, sigma);
+  blendw = 0.5f * (blendw + 1.0f);
+  if(val < white)
+  {
+    const float wav = (val - down_c) / fmaxf(sigma[0] + sigma[2], 1e-8f);
+    const float tt = fminf(1.0f, wav / fmaxf(2.0f * T, 1e-8f));
+    float uw = fminf(1.0f, 1.0f * upw); uw = uw * uw; uw = uw * uw; // pow(.., 4)
+    uw = 1.0f - (1.0f - uw) * p.detail;
+    val = mixf(val, fmaxf(0.0f, upsm_c + sigma[1] * signf(wav) * mixf(fmaxf(0.0f, fabsf(wav) - T), fabsf(wav), tt)), uw * blendw);
+  }
+  return fmaxf(0.0f, (val - black) / (white - black));
+}
+
 __global__ void __launch_bounds__(256) k_denoise_doub(const uint16_t *__restrict__ in, int iw, int ih,
     const uint2 *__restrict__ crs0, const uint2 *__restrict__ crs1, int cw, int ch, __half *__restrict__ out, int ow, int oh,
     const __grid_constant__ denoise_params_t p, const __grid_constant__ dn_push_doub_t P)
@@ -291,30 +321,52 @@ __global__ void __launch_bounds__(256) k_denoise_doub(const uint16_t *__restrict
   }
   const float4 upsm = bilin_rgba(crs0, cw, ch, bx, by, ax, ay);
   const float4 down = bilin_rgba(crs1, cw, ch, bx, by, ax, ay);
-  float black = P.black[1], white = P.white[1], crs = upsm.y, crs1v = down.y;
-  float T = 0.5f * p.strength * upsm.w, blendw = p.luma;
-  const int xt = P.filters == 9;
+  const bool xt = P.filters == 9;
   const int col = xt ? xtrans_colour(x, y) : bayer_colour(x, y);
-  if(col != 1)
-  {
-    black = col == 0 ? P.black[0] : P.black[2]; white = col == 0 ? P.white[0] : P.white[2];
-    crs = col == 0 ? upsm.x : upsm.z; crs1v = col == 0 ? down.x : down.z; blendw = 1.0f;
-    if(xt) T /= fmaxf(1e-4f, upsm.w);
-  }
-  float sigma[3];
-  noise_sigma(P.noise_a, P.noise_b, black, white, p.edges, crs, sigma);
-  float val = (float)__ldg(in + (size_t)mirrori(y + P.crop[1], ih) * iw + mirrori(x + P.crop[0], iw)) / 65535.0f;
-  blendw = 0.5f * (blendw + 1.0f);
-  if(val < white)
-  {
-    const float wav = (val - crs1v) / fmaxf(sigma[0] + sigma[2], 1e-8f);
-    const float tt = fminf(1.0f, wav / fmaxf(2.0f * T, 1e-8f));
-    float uw = fminf(1.0f, 1.0f * upsm.w); uw = uw * uw; uw = uw * uw; // pow(.., 4)
-    uw = 1.0f - (1.0f - uw) * p.detail;
-    val = mixf(val, fmaxf(0.0f, crs + sigma[1] * signf(wav) * mixf(fmaxf(0.0f, fabsf(wav) - T), fabsf(wav), tt)), uw * blendw);
-  }
-  val = fmaxf(0.0f, (val - black) / (white - black));
-  out[(size_t)y * ow + x] = __float2half_rn(val);
+  const float val = (float)__ldg(in + (size_t)mirrori(y + P.crop[1], ih) * iw + mirrori(x + P.crop[0], iw)) / 65535.0f;
+  const float uc = col == 1 ? upsm.y : (col == 0 ? upsm.x : upsm.z), dc = col == 1 ? down.y : (col == 0 ? down.x : down.z);
+  out[(size_t)y * ow + x] = __float2half_rn(doub_shrink(val, uc, dc, upsm.w, col, xt, p, P));
+}
+
+// bayer, output exactly twice the coarse size: one thread per 2x2 block.  the four pixels' bilinear taps (fractions
+// .75/.25 on texels X-1..X+1) share one 3x3 window of each coarse image and each pixel only needs its own colour channel,
+// so a block costs 9+9 texel loads and 25 f16 conversions instead of 32 loads and 96 conversions.  per pixel the
+// expressions are those of bilin_rgba() term by term.
+__global__ void __launch_bounds__(256) k_denoise_doub_bayer(const uint16_t *__restrict__ in, int iw, int ih,
+    const uint2 *__restrict__ crs0, const uint2 *__restrict__ crs1, int cw, int ch, __half *__restrict__ out, int ow, int oh,
+    const __grid_constant__ denoise_params_t p, const __grid_constant__ dn_push_doub_t P)
+{
+  const int X = blockIdx.x * 32 + threadIdx.x, Y = blockIdx.y * 8 + threadIdx.y;
+  if(X >= cw || Y >= ch) return;
+  int xi[3], yi[3];
+#pragma unroll
+  for(int k = 0; k < 3; k++) { xi[k] = mirrori(X - 1 + k, cw); yi[k] = mirrori(Y - 1 + k, ch); }
+  // channel c of the window, as floats: [j][i]
+  float u[4][3][3], d[3][3][3];
+#pragma unroll
+  for(int j = 0; j < 3; j++)
+#pragma unroll
+    for(int i = 0; i < 3; i++)
+    {
+      const float4 a = ld_rgba(crs0, cw, xi[i], yi[j]), b = ld_rgba(crs1, cw, xi[i], yi[j]);
+      u[0][j][i] = a.x; u[1][j][i] = a.y; u[2][j][i] = a.z; u[3][j][i] = a.w;
+      d[0][j][i] = b.x; d[1][j][i] = b.y; d[2][j][i] = b.z;
+    }
+  // pixel (dx, dy) of the block: base texel index = dx/dy (0 or 1) in the window, fraction .75 (even) or .25 (odd)
+#define BIL(T, DX, DY) ((T[DY][DX] * (1.0f - AX(DX)) + T[DY][DX + 1] * AX(DX)) * (1.0f - AX(DY)) + (T[DY + 1][DX] * (1.0f - AX(DX)) + T[DY + 1][DX + 1] * AX(DX)) * AX(DY))
+#define AX(D) ((D) ? 0.25f : 0.75f)
+  const int ry0 = mirrori(2 * Y + P.crop[1], ih), ry1 = mirrori(2 * Y + 1 + P.crop[1], ih);
+  const int rx0 = mirrori(2 * X + P.crop[0], iw), rx1 = mirrori(2 * X + 1 + P.crop[0], iw);
+  const float v00 = (float)__ldg(in + (size_t)ry0 * iw + rx0) / 65535.0f, v10 = (float)__ldg(in + (size_t)ry0 * iw + rx1) / 65535.0f;
+  const float v01 = (float)__ldg(in + (size_t)ry1 * iw + rx0) / 65535.0f, v11 = (float)__ldg(in + (size_t)ry1 * iw + rx1) / 65535.0f;
+  const float o00 = doub_shrink(v00, BIL(u[0], 0, 0), BIL(d[0], 0, 0), BIL(u[3], 0, 0), 0, false, p, P); // r
+  const float o10 = doub_shrink(v10, BIL(u[1], 1, 0), BIL(d[1], 1, 0), BIL(u[3], 1, 0), 1, false, p, P); // g
+  const float o01 = doub_shrink(v01, BIL(u[1], 0, 1), BIL(d[1], 0, 1), BIL(u[3], 0, 1), 1, false, p, P); // g
+  const float o11 = doub_shrink(v11, BIL(u[2], 1, 1), BIL(d[2], 1, 1), BIL(u[3], 1, 1), 2, false, p, P); // b
+#undef BIL
+#undef AX
+  *reinterpret_cast<__half2 *>(out + (size_t)(2 * Y) * ow + 2 * X)     = __floats2half2_rn(o00, o10);
+  *reinterpret_cast<__half2 *>(out + (size_t)(2 * Y + 1) * ow + 2 * X) = __floats2half2_rn(o01, o11);
 }
 
 static inline dim3 grid2d(unsigned w, unsigned h, unsigned by = 8) { return dim3(vkb_cdiv(w, 32), vkb_cdiv(h, by)); }
@@ -410,6 +462,10 @@ static int launch_doub(const vkb_launch_t *l)
   denoise_params_t p; memset(&p, 0, sizeof(p)); memcpy(&p, l->params, l->params_size < sizeof(p) ? l->params_size : sizeof(p));
   dn_push_doub_t P; memcpy(&P, l->push, sizeof(P));
   host_escale(&p);
+  if(P.filters != 9u && P.filters != 0u && out->wd == 2 * c0->wd && out->ht == 2 * c0->ht)
+    k_denoise_doub_bayer<<<grid2d(c0->wd, c0->ht), blk2d, 0, l->stream>>>((const uint16_t *)in->data, in->wd, in->ht, (const uint2 *)c0->data,
+        (const uint2 *)c1->data, c0->wd, c0->ht, (__half *)out->data, out->wd, out->ht, p, P);
+  else
   k_denoise_doub<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint16_t *)in->data, in->wd, in->ht, (const uint2 *)c0->data,
       (const uint2 *)c1->data, c0->wd, c0->ht, (__half *)out->data, out->wd, out->ht, p, P);
   VKB_CHECK_LAUNCH();
