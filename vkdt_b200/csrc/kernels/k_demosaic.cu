@@ -9,30 +9,42 @@ int launch_bayer_splat(const vkb_launch_t *l);
 int launch_bayer_fix(const vkb_launch_t *l);
 
 // ---- gauss: green-only structure tensor per block -> (eval.xy, axis snapped evec) (gauss.comp:17-126) ----
+// the tap pattern is a compile time property of the cfa: both loops unroll completely and the taps stay in registers.
+// i / p and j / p are evaluated as i * (1 / p): i, j are in {-1, 0, 1, 2}, and scaling a correctly rounded quotient
+// by 0, +-1 or 2 is exact, so one division per tap serves all three sums bit for bit.
+template <bool xtrans>
 __global__ void __launch_bounds__(256) k_demosaic_gauss(const __half *__restrict__ orig, int iw, int ih,
-    uint2 *__restrict__ out, int ow, int oh, int xtrans)
+    uint2 *__restrict__ out, int ow, int oh)
 {
   const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
   if(x >= ow || y >= oh) return;
-  const int blk = xtrans ? 3 : 2, lo = xtrans ? 0 : -1;
+  constexpr int blk = xtrans ? 3 : 2, lo = xtrans ? 0 : -1;
   float px[16];
-  int n = 0;
   float mwx = 0, mwy = 0, mbx = 0, mby = 0, smw = 0, smb = 0;
-  for(int j = lo; j < 3; j++) for(int i = lo; i < 3; i++)
+  int xi[4], yi[4];
+#pragma unroll
+  for(int i = lo; i < 3; i++) { xi[i - lo] = mirror1(blk * x + i, iw); yi[i - lo] = mirror1(blk * y + i, ih); }
+#pragma unroll
+  for(int j = lo; j < 3; j++)
+#pragma unroll
+  for(int i = lo; i < 3; i++)
   {
     if(xtrans ? (((j + i) & 1) == 1) : (((j + i) & 1) != 1)) continue;
-    const float p = ld_h_mirror(orig, iw, ih, blk * x + i, blk * y + j);
-    px[n++] = p;
+    const float p = ld_h(orig, iw, xi[i - lo], yi[j - lo]);
+    px[4 * (j - lo) + (i - lo)] = p;
     mwx += (float)i * p; mwy += (float)j * p; smw += p;
-    mbx += (float)i / p; mby += (float)j / p; smb += 1.0f / p;
+    const float rcp = 1.0f / p;
+    mbx += (float)i * rcp; mby += (float)j * rcp; smb += rcp;
   }
   mwx /= smw; mwy /= smw; mbx /= smb; mby /= smb;
   float Sw0 = 0, Sw1 = 0, Sw2 = 0, Sw3 = 0, Sb0 = 0, Sb1 = 0, Sb2 = 0, Sb3 = 0, sw = 0, sb = 0;
-  n = 0;
-  for(int j = lo; j < 3; j++) for(int i = lo; i < 3; i++)
+#pragma unroll
+  for(int j = lo; j < 3; j++)
+#pragma unroll
+  for(int i = lo; i < 3; i++)
   {
     if(xtrans ? (((j + i) & 1) == 1) : (((j + i) & 1) != 1)) continue;
-    const float p = px[n++];
+    const float p = px[4 * (j - lo) + (i - lo)];
     float p2 = p * p;
     float p0 = (float)i - mwx, p1 = (float)j - mwy;
     Sw0 += p2 * p0 * p0; Sw1 += p2 * p0 * p1; Sw2 += p2 * p1 * p0; Sw3 += p2 * p1 * p1;
@@ -138,8 +150,12 @@ static int launch_demosaic_gauss(const vkb_launch_t *l)
   const demosaic_push_t *pc = (const demosaic_push_t *)l->push;
   const vkb_image_t *orig = l->conn + 1, *out = l->conn + 2;
   VKB_REQUIRE(orig->chan == 1 && orig->format == VKB_TOKEN_F16 && out->chan == 4 && out->format == VKB_TOKEN_F16);
-  k_demosaic_gauss<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const __half *)orig->data, orig->wd, orig->ht,
-      (uint2 *)out->data, out->wd, out->ht, pc->filters == 9);
+  if(pc->filters == 9)
+    k_demosaic_gauss<true><<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const __half *)orig->data, orig->wd, orig->ht,
+        (uint2 *)out->data, out->wd, out->ht);
+  else
+    k_demosaic_gauss<false><<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const __half *)orig->data, orig->wd, orig->ht,
+        (uint2 *)out->data, out->wd, out->ht);
   VKB_CHECK_LAUNCH();
   return VKB_OK;
 }

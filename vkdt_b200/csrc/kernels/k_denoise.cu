@@ -27,6 +27,7 @@ static void host_escale(denoise_params_t *p)
 { // overwrite edges[0..2] in the kernel's copy of the params with the scale factors
   for(int k = 0; k < 3; k++) p->edges[k] = exp2f(12.0f * p->edges[k] + p->edges[3]);
 }
+VKB_DEV float exp2f_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 VKB_DEV void swizzle(int x, int y, int w, int h, int &ox, int &oy)
 { // downcov.comp:52-53, down.comp:103-104
   ox = x / 2 + ((x & 1) * (w + 1)) / 2;
@@ -136,20 +137,28 @@ __global__ void __launch_bounds__(256, 4) k_denoise_downcov(const uint2 *__restr
   e0 = clampf(e0, 0.01f, 25.0f); e1 = clampf(e1, 0.01f, 25.0f);
   st_rgba(covimg, w, x, y, make_float4(e0, e1, v0x, v0y));
   float r = 0, g = 0, b = 0, wt = 0;
-  const float ie0 = 1.0f / e0, ie1 = 1.0f / e1;
+  // weight(i,j) = exp(-(q0^2/e0 + q1^2/e1)/2) with q = V^t (i,j) is exp2 of a quadratic form in (i,j): the three
+  // coefficients are set up once, a tap costs two adds and one ex2.  (continuous in the inputs: ~1e-6 relative on the
+  // weights, the blurred colour is rounded to f16 right after.)
+  const float ie0 = 1.0f / e0, ie1 = 1.0f / e1, k2 = -0.5f * 1.4426950408889634f;
+  const float qa = k2 * (v0x * v0x * ie0 + v1x * v1x * ie1), qc = k2 * (v0y * v0y * ie0 + v1y * v1y * ie1);
+  const float qb = 2.0f * k2 * (v0x * v0y * ie0 + v1x * v1y * ie1);
+  float ei[5], eb[5];
+#pragma unroll
+  for(int i = 0; i < 5; i++) { ei[i] = qa * (float)((i - 2) * (i - 2)); eb[i] = qb * (float)(i - 2); }
 #pragma unroll 1
   for(int j = 0; j < 5; j++)
+  {
+    const float fj = (float)(j - 2), ej = qc * fj * fj;
 #pragma unroll
     for(int i = 0; i < 5; i++)
     {
       const float4 t = tile[ly + j][lx + i];
-      if(t.x > 2.0f * mean_b) continue; // hot pixels
-      const float fi = (float)(i - 2), fj = (float)(j - 2);
-      const float q0 = fi * v0x + fj * v0y, q1 = fi * v1x + fj * v1y;
-      const float wgt = fmaxf(1e-9f, __expf(-0.5f * (q0 * ie0 * q0 + q1 * ie1 * q1)));
-      r += wgt * t.x; g += wgt * t.y; b += wgt * t.z;
+      const float wgt = t.x > 2.0f * mean_b ? 0.0f : fmaxf(1e-9f, exp2f_fast((ei[i] + ej) + eb[i] * fj)); // hot pixels get no weight
+      r = __fmaf_rn(wgt, t.x, r); g = __fmaf_rn(wgt, t.y, g); b = __fmaf_rn(wgt, t.z, b);
       wt += wgt;
     }
+  }
   const float iw_ = fmaxf(wt, 1e-8f);
   float edge = clampf(75.0f * fmaxf(0.0f, e1 - 0.09f), 0.0f, 1.0f);
   edge = smoothstepf(0.4f, 0.75f, edge);
@@ -188,6 +197,67 @@ __global__ void __launch_bounds__(256) k_denoise_down(const uint2 *__restrict__ 
   {
     const float4 col = bilin_rgba(in, w, h, bx[o], by[o], ax[o], ay[o]);
     const float c[3] = { col.x, col.y, col.z };
+#pragma unroll
+    for(int k = 0; k < 3; k++)
+    {
+      const float e = clampf(1.0f - 0.5f * (wc[k] * fabsf(gamma08(c[k]) - g0[k])), 0.0f, 1.0f);
+      const float ww = e * (1.0f - t) / 4.0f;
+      sum[k] += ww * c[k];
+      wgt[k] += ww;
+    }
+  }
+  int ox, oy; swizzle(x, y, w, h, ox, oy);
+  st_rgba(out, w, ox, oy, make_float4(sum[0] / wgt[0], sum[1] / wgt[1], sum[2] / wgt[2], 1.0f));
+}
+
+// same arithmetic, taps served from a CTA wide window of the packed f16 texels in shared memory: the 17 texels a pixel
+// reads sit at constant offsets from one base address, which removes the per tap mirroring and 64-bit address
+// arithmetic (a fifth of the instructions of the kernel above).  used when the image is larger than one window.
+#define DD_W 36
+#define DD_H 12
+VKB_DEV float4 unpack_rgba(uint2 v)
+{
+  const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&v.x)), b = __half22float2(*reinterpret_cast<const __half2 *>(&v.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__global__ void __launch_bounds__(256) k_denoise_down_tiled(const uint2 *__restrict__ in, int w, int h, uint2 *__restrict__ out,
+    denoise_params_t p, float black, float white, float noise_a, float noise_b, float lv, float blk)
+{
+  __shared__ uint2 tile[DD_H][DD_W];
+  const int tx0 = blockIdx.x * 32 - 2, ty0 = blockIdx.y * 8 - 2;
+  for(int t = threadIdx.y * 32 + threadIdx.x; t < DD_W * DD_H; t += 256)
+  {
+    const int r = t / DD_W, c = t - r * DD_W;
+    tile[r][c] = __ldg(in + (size_t)mirror1(ty0 + r, h) * w + mirror1(tx0 + c, w));
+  }
+  __syncthreads();
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if(x >= w || y >= h) return;
+  const int lx = threadIdx.x + 2, ly = threadIdx.y + 2;
+  const float t = 0.2f;
+  const float4 c0 = unpack_rgba(tile[ly][lx]);
+  float sigma[3], sum[3], wgt[3], wc[3], g0[3];
+  noise_sigma(noise_a, noise_b, black, white, p.edges, c0.x, sigma);
+  const float cc[3] = { c0.x, c0.y, c0.z };
+#pragma unroll
+  for(int k = 0; k < 3; k++)
+  {
+    sum[k] = t * cc[k]; wgt[k] = t;
+    sigma[k] = lv * sigma[k] / blk;
+    wc[k] = 1.0f / sigma[k];
+    g0[k] = gamma08(cc[k]);
+  }
+  constexpr int   bx[4] = { 1, -2, 0, -1 }, by[4] = { 0, -1, -2, 1 };
+  constexpr float ax[4] = { 0.2f,  0.8f,  0.4f,  0.6f  }, ay[4] = { 0.4f, 0.6f,  0.8f,  0.2f  };
+#pragma unroll
+  for(int o = 0; o < 4; o++)
+  {
+    const float4 t00 = unpack_rgba(tile[ly + by[o]][lx + bx[o]]),     t10 = unpack_rgba(tile[ly + by[o]][lx + bx[o] + 1]);
+    const float4 t01 = unpack_rgba(tile[ly + by[o] + 1][lx + bx[o]]), t11 = unpack_rgba(tile[ly + by[o] + 1][lx + bx[o] + 1]);
+    const float c[3] = {
+      (t00.x * (1.0f - ax[o]) + t10.x * ax[o]) * (1.0f - ay[o]) + (t01.x * (1.0f - ax[o]) + t11.x * ax[o]) * ay[o],
+      (t00.y * (1.0f - ax[o]) + t10.y * ax[o]) * (1.0f - ay[o]) + (t01.y * (1.0f - ax[o]) + t11.y * ax[o]) * ay[o],
+      (t00.z * (1.0f - ax[o]) + t10.z * ax[o]) * (1.0f - ay[o]) + (t01.z * (1.0f - ax[o]) + t11.z * ax[o]) * ay[o] };
 #pragma unroll
     for(int k = 0; k < 3; k++)
     {
@@ -409,6 +479,10 @@ static int launch_down(const vkb_launch_t *l)
   denoise_params_t p; memset(&p, 0, sizeof(p)); memcpy(&p, l->params, l->params_size < sizeof(p) ? l->params_size : sizeof(p));
   const float blk = pc->block == 3 ? 2.23607f : (pc->block == 2 ? 1.414213f : 1.0f);
   host_escale(&p);
+  if(in->wd >= DD_W && in->ht >= DD_H) // a window overhangs the image by less than its size: one reflection is enough
+    k_denoise_down_tiled<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, (uint2 *)out->data,
+        p, pc->black[1], pc->white[1], pc->noise_a, pc->noise_b, powf(0.7f, (float)pc->level), blk);
+  else
   k_denoise_down<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, (uint2 *)out->data,
       p, pc->black[1], pc->white[1], pc->noise_a, pc->noise_b, powf(0.7f, (float)pc->level), blk);
   VKB_CHECK_LAUNCH();

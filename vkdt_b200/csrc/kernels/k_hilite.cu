@@ -44,39 +44,61 @@ __global__ void __launch_bounds__(256) k_hilite_half(const __half *__restrict__ 
 }
 
 // ---- reduce: 5x5 binomial over unclipped pixels, desaturating near white (reduce.comp:21-60) ----
+#define HR_TW 67
+#define HR_TH 19
 __global__ void __launch_bounds__(256) k_hilite_reduce(const uint2 *__restrict__ in, int iw, int ih,
     uint2 *__restrict__ out, int ow, int oh, hilite_params_t p, float wbr, float wbg, float wbb)
 {
-  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-  if(x >= ow || y >= oh) return;
+  // everything the shader evaluates per tap except the binomial weight depends on the input texel alone (luminance,
+  // clip test, desaturated colour: seven divisions and two smoothsteps).  a CTA of 32x8 outputs evaluates it once per
+  // texel of its 67x19 input window into shared memory; the 25 tap loop below only accumulates, in the shader's order.
+  __shared__ float4 tile[HR_TH][HR_TW]; // desaturated r g b, luminance
+  __shared__ float  okay[HR_TH][HR_TW]; // 1 if no channel is clipped
   float white = p.white;
   if(!(white > 0.0f)) white = 1.0f;
-  const float w[5] = {1.0f / 16.0f, 4.0f / 16.0f, 6.0f / 16.0f, 4.0f / 16.0f, 1.0f / 16.0f};
-  const float sw[5] = {1.0f, 2.0f, 0.0f, -2.0f, -1.0f};
-  float ex = 0.0f, ey = 0.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f, wgt = 0.0f;
   const float ds = p.desat * p.desat;
-#pragma unroll
-  for(int jj = -2; jj <= 2; jj++)
-#pragma unroll
-    for(int ii = -2; ii <= 2; ii++)
+  const int tx0 = blockIdx.x * 64 - 2, ty0 = blockIdx.y * 16 - 2;
+  for(int t = threadIdx.y * 32 + threadIdx.x; t < HR_TW * HR_TH; t += 256)
+  {
+    const int r = t / HR_TW, c = t - r * HR_TW;
+    const float4 rgb = ld_rgba(in, iw, mirrori(tx0 + c, iw), mirrori(ty0 + r, ih));
+    float4 m = make_float4(0.0f, 0.0f, 0.0f, lum2020(rgb.x, rgb.y, rgb.z));
+    const bool ok = rgb.x < white && rgb.y < white && rgb.z < white;
+    if(ok)
     {
-      const float4 rgb = ld_rgba_mirror(in, iw, ih, 2 * x + ii, 2 * y + jj);
-      const float l = lum2020(rgb.x, rgb.y, rgb.z);
-      ex += w[jj + 2] * sw[ii + 2] * l;
-      ey += w[ii + 2] * sw[jj + 2] * l;
-      const float u = w[ii + 2] * w[jj + 2];
       const float rw = rgb.x * wbr, gw = rgb.y * wbg, bw = rgb.z * wbb;
       const float cmax = fmaxf(rw, fmaxf(gw, bw));
       const float cmin = fminf(rw, fminf(gw, bw));
       const float sat = (cmax - cmin) / fmaxf(1e-3f, cmax);
-      if(rgb.x < white && rgb.y < white && rgb.z < white)
+      const float s = smoothstepf(0.2f, 1.0f, fmaxf(rgb.x, fmaxf(rgb.y, rgb.z)) / white);
+      float tt = smoothstepf(0.15f, 0.9f, sat);
+      tt = clampf(5.0f * ds * ds * s * tt, 0.0f, 1.0f);
+      m.x = mixf(rgb.x, (cmax + cmin) / wbr * .5f, tt);
+      m.y = mixf(rgb.y, (cmax + cmin) / wbg * .5f, tt);
+      m.z = mixf(rgb.z, (cmax + cmin) / wbb * .5f, tt);
+    }
+    tile[r][c] = m;
+    okay[r][c] = ok ? 1.0f : 0.0f;
+  }
+  __syncthreads();
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if(x >= ow || y >= oh) return;
+  const float w[5] = {1.0f / 16.0f, 4.0f / 16.0f, 6.0f / 16.0f, 4.0f / 16.0f, 1.0f / 16.0f};
+  const float sw[5] = {1.0f, 2.0f, 0.0f, -2.0f, -1.0f};
+  float ex = 0.0f, ey = 0.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f, wgt = 0.0f;
+  const int lx = 2 * threadIdx.x, ly = 2 * threadIdx.y; // tile coords of tap (-2,-2)
+#pragma unroll
+  for(int jj = 0; jj < 5; jj++)
+#pragma unroll
+    for(int ii = 0; ii < 5; ii++)
+    {
+      const float4 m = tile[ly + jj][lx + ii];
+      ex += w[jj] * sw[ii] * m.w;
+      ey += w[ii] * sw[jj] * m.w;
+      const float u = w[ii] * w[jj];
+      if(okay[ly + jj][lx + ii] != 0.0f)
       {
-        const float s = smoothstepf(0.2f, 1.0f, fmaxf(rgb.x, fmaxf(rgb.y, rgb.z)) / white);
-        float t = smoothstepf(0.15f, 0.9f, sat);
-        t = clampf(5.0f * ds * ds * s * t, 0.0f, 1.0f);
-        cr += mixf(rgb.x, (cmax + cmin) / wbr * .5f, t) * u;
-        cg += mixf(rgb.y, (cmax + cmin) / wbg * .5f, t) * u;
-        cb += mixf(rgb.z, (cmax + cmin) / wbb * .5f, t) * u;
+        cr += m.x * u; cg += m.y * u; cb += m.z * u;
         wgt += u;
       }
     }

@@ -25,6 +25,9 @@ VKB_DEV int gamma_hi_from_v(float v)
 // curve() with its two divisions by per-launch constants turned into multiplications by their reciprocals
 // (inv2s = 1/(2 sigma), invd = 1/(2 sigma^2/3)): <= 1 ulp of difference in t and in the exponent, the value is
 // rounded to f16 right after.  the level-0 stack costs 10 of these per input pixel, the divisions were a third of it.
+// CLARITY = false: p.clarity == 0 (the default).  the gaussian term is then +-0 with the sign of c, and adding
+// 0 * c reproduces `val + 0 * c * exp(..)` bit for bit (signed zeros included) without the exponential.
+template <bool CLARITY>
 VKB_DEV float llap_curve_k(float x, float g, const llap_params_t &p, float inv2s, float invd)
 {
   const float c = x - g;
@@ -39,7 +42,8 @@ VKB_DEV float llap_curve_k(float x, float g, const llap_params_t &p, float inv2s
     const float mt = 1.0f - t;
     val = g + ssigma * 2.0f * mt * t + t2 * (ssigma + ssigma * shadhi);
   }
-  val += p.clarity * c * __expf(-c * c * invd);
+  if(CLARITY) val += p.clarity * c * __expf(-c * c * invd);
+  else        val += 0.0f * c;
   return val;
 }
 VKB_DEV float llap_curve(float x, float g, const llap_params_t &p)
@@ -69,10 +73,11 @@ VKB_DEV float llap_grey(float4 px)
 // block = 32x8 outputs, input tile (2*32+1) x (2*8+1) texels around them, 11 f16 values per texel in smem.
 #define R0_TW 65
 #define R0_TH 17
+template <bool CLARITY>
 __global__ void __launch_bounds__(256) k_llap_reduce0(const uint2 *__restrict__ in, int iw, int ih,
     __half *__restrict__ out, int ow, int oh, llap_params_t p)
 {
-  __shared__ __half tile[NL][R0_TH][R0_TW + 1];
+  __shared__ __align__(16) __half tile[NL][R0_TH][R0_TW + 1];
   const int tx0 = blockIdx.x * 64 - 1, ty0 = blockIdx.y * 16 - 1;
   const int tid = threadIdx.y * 32 + threadIdx.x;
   const float inv2s = 1.0f / (2.0f * p.sigma), invd = 1.0f / (2.0f * p.sigma * p.sigma / 3.0f);
@@ -83,7 +88,7 @@ __global__ void __launch_bounds__(256) k_llap_reduce0(const uint2 *__restrict__ 
     const int gx = big ? mirror1(tx0 + lx, iw) : mirrori(tx0 + lx, iw), gy = big ? mirror1(ty0 + ly, ih) : mirrori(ty0 + ly, ih);
     const float y = llap_grey(ld_rgba(in, iw, gx, gy));
 #pragma unroll
-    for(int g = 0; g < NUM_GAMMA; g++) tile[g][ly][lx] = __float2half_rn(llap_curve_k(y, gamma_from_i(g), p, inv2s, invd));
+    for(int g = 0; g < NUM_GAMMA; g++) tile[g][ly][lx] = __float2half_rn(llap_curve_k<CLARITY>(y, gamma_from_i(g), p, inv2s, invd));
     tile[NUM_GAMMA][ly][lx] = __float2half_rn(y);
   }
   __syncthreads();
@@ -98,7 +103,12 @@ __global__ void __launch_bounds__(256) k_llap_reduce0(const uint2 *__restrict__ 
 #pragma unroll
     for(int j = 0; j < 3; j++)
 #pragma unroll
-      for(int i = 0; i < 3; i++) t[j][i] = __half2float(tile[g][ly + j][lx + i]);
+      for(int i = 0; i < 3; i += 2)
+      { // lx is even and the rows are 66 halves long: (lx, lx+1) is one aligned 32-bit load
+        const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&tile[g][ly + j][lx + i]));
+        t[j][i] = f.x;
+        if(i == 0) t[j][1] = f.y;
+      }
     // sample_semisoft: four bilinear taps with weights 1/2, summed, / 4
     const float b00 = (t[0][0] * 0.5f + t[0][1] * 0.5f) * 0.5f + (t[1][0] * 0.5f + t[1][1] * 0.5f) * 0.5f;
     const float b10 = (t[0][1] * 0.5f + t[0][2] * 0.5f) * 0.5f + (t[1][1] * 0.5f + t[1][2] * 0.5f) * 0.5f;
@@ -314,8 +324,13 @@ static int launch_llapr0(const vkb_launch_t *l)
   const vkb_image_t *in = l->conn, *out = l->conn + 1;
   VKB_REQUIRE(in->chan == 4 && in->format == VKB_TOKEN_F16 && out->chan == 1 && out->layers == NL && out->format == VKB_TOKEN_F16);
   VKB_REQUIRE(out->wd == (in->wd - 1) / 2 + 1 && out->ht == (in->ht - 1) / 2 + 1);
-  k_llap_reduce0<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht,
-      (__half *)out->data, out->wd, out->ht, *(const llap_params_t *)l->params);
+  const llap_params_t *lp = (const llap_params_t *)l->params;
+  if(lp->clarity == 0.0f)
+    k_llap_reduce0<false><<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht,
+        (__half *)out->data, out->wd, out->ht, *lp);
+  else
+    k_llap_reduce0<true><<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht,
+        (__half *)out->data, out->wd, out->ht, *lp);
   VKB_CHECK_LAUNCH();
   return VKB_OK;
 }
