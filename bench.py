@@ -8,7 +8,7 @@ its own stills (weak scaling, no data-path collective; torch.distributed is used
 
   value      whole-job MP/s, input mosaic already resident in HBM, result left in HBM (kernel path only, CUDA events)
   e2e        same metric through the reference-facing C-ABI graph call with HOST buffers: pinned H2D of the u16 mosaic and
-             D2H of the rgba f32 sink image inside the timed region
+             D2H of the rgb f32 sink image (the PFM payload) inside the timed region
   roofline   dominant kernel: unique bytes in+out of the launch / its average CUDA-event duration vs measured HBM copy peak
   cpu_baseline / --impl reference: the CPU restatement of the reference's algorithm (oracle, OpenMP, all host cores) on a
              bounded crop of the same workload.  the reference's own Vulkan pipeline cannot be built here.
@@ -134,6 +134,7 @@ def run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, s
         g.set_device(local_rank)
         if strength > 0:
             g.line("param:denoise:01:strength:%g" % strength)
+        g.set_sink_layout(api.SINK_RGB_F32)   # the PFM payload (r g b f32, 12 B/px) is what o-pfm puts into the file
         return g
 
     # ---- leg 1: kernel path, input resident in HBM, sink left in HBM ----
@@ -142,7 +143,7 @@ def run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, s
     g.set_sink_buffer(None, 0)
     g.run()                              # builds the plan, allocates the pool
     ow, oh = g.sink_size()
-    out_bytes = ow * oh * 16
+    out_bytes = ow * oh * 12
     stream = g.stream()
     FR = api.RUN_RECORD
     for i in range(warmup):
@@ -179,7 +180,7 @@ def run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, s
     pool_bytes = g.pool_bytes()
 
     # ---- leg 2: end to end through the C-ABI with host buffers ----
-    # two graph instances (each with its own pool, stream and pinned sink) ping-pong: while one frame's 962 MB result
+    # two graph instances (each with its own pool, stream and pinned sink) ping-pong: while one frame's 722 MB result
     # drains over PCIe the next frame uploads and computes.  every frame still pays its full H2D + kernels + D2H.
     NG = 2
     gs, host_out = [], []
@@ -309,7 +310,7 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t_kernel_ms / args.steps, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s: %dx%d bayer rggb 14-bit still (%.1f MP), default darkroom graph incl. hilite + llap + grade, "
-                               "denoise strength %.2f, sink rgba f32 %dx%d" % (args.workload, W, H, mp, strength, ow, oh),
+                               "denoise strength %.2f, sink rgb f32 %dx%d (PFM payload, 12 B/px)" % (args.workload, W, H, mp, strength, ow, oh),
                    "timing": "inputs and intermediates (%.0f MB pool) exceed the 126 MB L2; %d distinct stills cycled" % (R["pool_bytes"] / 1e6, nstills),
                    "parallelism": "independent stills per GPU, no collective", "edges": "f16 at every reference edge (strict)"},
         "e2e": {"value": round(world * e2e_steps * mp / (t_e2e_ms * 1e-3), 2), "unit": "MP/s", "h2d_bytes_per_step": in_bytes,

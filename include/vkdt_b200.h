@@ -134,6 +134,14 @@ VKB_API int  vkb_graph_set_source(vkb_graph_t *g, const char *inst, const void *
 VKB_API int  vkb_dng_info(const char *filename, vkb_raw_params_t *p, uint32_t *cfa_off_x, uint32_t *cfa_off_y);
 /* redirect a sink (o-pfm:main ...) into caller memory instead of a file: rgba f32, wd*ht*16 bytes */
 VKB_API int  vkb_graph_set_sink_buffer(vkb_graph_t *g, const char *inst, void *dst, size_t bytes);
+/* layout of a sink's pixels, on the device and in the caller's buffer.  VKB_SINK_RGBA_F32 (default for memory sinks) is
+ * what the reference maps for write_sink (o-pfm/connectors: rgba f32, 16 B/px).  VKB_SINK_RGB_F32 is the PFM payload
+ * itself (o-pfm/main.c:36-40 writes r g b per pixel, 12 B/px): the last kernel of the graph stores it directly, which
+ * takes a quarter off the device->host transfer that bounds the end-to-end rate.  o-pfm file output always uses it.
+ * takes effect at the next vkb_graph_run with VKB_RUN_ALL. */
+#define VKB_SINK_RGBA_F32 0
+#define VKB_SINK_RGB_F32  1
+VKB_API int  vkb_graph_set_sink_layout(vkb_graph_t *g, const char *inst, int layout);
 VKB_API int  vkb_graph_sink_size(vkb_graph_t *g, const char *inst, uint32_t *wd, uint32_t *ht);
 VKB_API int  vkb_graph_set_frame(vkb_graph_t *g, uint32_t frame);
 VKB_API int  vkb_graph_run(vkb_graph_t *g, int runflags);                   /* dt_graph_run, src/pipe/graph.c:719 */

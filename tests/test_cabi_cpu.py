@@ -120,3 +120,21 @@ def test_unconnected_graph_is_an_error():
     g = api.Graph(cfg_text="module:i-raw:main\nmodule:display:main\n", sink=None)
     with pytest.raises(api.VkbError):
         g.plan()
+
+
+def test_plan_rgb_sink_layout():
+    """the PFM payload layout: fused producers store r g b themselves, anything else gets one repack launch."""
+    g = api.Graph(cfg_text=api.DARKROOM_CFG.format(src="i-raw"))
+    raw = np.zeros((384, 512), np.uint16)
+    g.set_source(raw.ctypes.data, api.raw_params(512, 384))
+    buf = np.zeros(16, np.float32)
+    g.set_sink_buffer(buf.ctypes.data, 0)
+    text = g.plan()
+    fin = [l for l in text.splitlines() if "llapfin" in l][0]
+    assert "x4x1:f32@" in fin and "pfmpack" not in text        # memory sinks default to the reference's rgba f32
+    g.set_sink_layout(api.SINK_RGB_F32)
+    text = g.plan()
+    fin = [l for l in text.splitlines() if "llapfin" in l][0]
+    assert "x3x1:f32@" in fin and "pfmpack" not in text
+    with pytest.raises(api.VkbError):
+        g.set_sink_layout(7)

@@ -261,3 +261,52 @@ def test_iraw_dng_file_source(gpu, oracle, tmp_path, cfa, xtrans):
     p = psnr(got[..., :3], want[..., :3])
     print("max abs %.3g psnr %.1f" % (err.max(), p))
     assert p >= 60.0 and (err > 1e-3).mean() <= 1e-5 and err.max() <= 2e-3
+
+
+NO_LLAP = ("module:llap:01\n", "connect:filmcurv:01:output:llap:01:input\nconnect:llap:01:output:grade:01:input\n")
+ONLY_COLOUR_CFG = """module:i-raw:main
+module:denoise:01
+module:hilite:01
+module:demosaic:01
+module:colour:01
+module:display:main
+connect:i-raw:main:output:denoise:01:input
+connect:denoise:01:output:hilite:01:input
+connect:hilite:01:output:demosaic:01:input
+connect:demosaic:01:output:colour:01:input
+connect:colour:01:output:display:main:input
+"""
+
+
+def _variant_cfg(gpu, variant):
+    cfg = gpu.DARKROOM_CFG.format(src="i-raw")
+    if variant == "no-llap":     # crop+colour+filmcurv+grade fuse into one pointwise launch that feeds the sink
+        cfg = cfg.replace(NO_LLAP[0], "").replace(NO_LLAP[1], "connect:filmcurv:01:output:grade:01:input\n")
+        cfg = "\n".join(l for l in cfg.splitlines() if not l.startswith("param:llap")) + "\n"
+    if variant == "colour-only":  # a plain node launch feeds the sink: the executor appends the repack launch
+        cfg = ONLY_COLOUR_CFG
+    return cfg
+
+
+@pytest.mark.parametrize("variant", ["default", "no-llap", "colour-only"])
+def test_sink_rgb_layout(gpu, variant):
+    """VKB_SINK_RGB_F32 (the PFM payload, 12 B/px) carries exactly the r g b of the rgba f32 sink image."""
+    w, h = 530, 412
+    raw = np.ascontiguousarray(synth.mosaic(w, h, seed=5))
+    outs = {}
+    for layout in (gpu.SINK_RGBA_F32, gpu.SINK_RGB_F32):
+        g = gpu.Graph(cfg_text=_variant_cfg(gpu, variant))
+        g.set_source(raw.ctypes.data, gpu.raw_params(w, h, wb=WB, cam_to_rec2020=CAM))
+        g.set_sink_layout(layout)
+        g.set_sink_buffer(None, 0)
+        g.run()
+        ow, oh = g.sink_size()
+        out = np.full((oh, ow, 4 if layout == gpu.SINK_RGBA_F32 else 3), -7.0, dtype=np.float32)
+        g.set_sink_buffer(out.ctypes.data, out.nbytes)
+        g.run(gpu.RUN_RECORD | gpu.RUN_UPLOAD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT)
+        outs[layout] = out
+        perf = g.perf()
+        assert ("pfmpack" in perf) == (variant == "colour-only" and layout == gpu.SINK_RGB_F32), perf
+    a, b = outs[gpu.SINK_RGBA_F32], outs[gpu.SINK_RGB_F32]
+    assert a.shape[:2] == b.shape[:2] and np.isfinite(b).all() and (a[..., 3] == 1.0).all()
+    assert np.array_equal(a[..., :3], b)

@@ -44,7 +44,7 @@ vkb_event_sync vkb_event_elapsed_ms vkb_event_destroy vkb_dispatch vkb_kernel_co
 vkb_kernel_name vkb_launch_count vkb_launch_count_reset vkb_graph_new vkb_graph_free vkb_graph_read_config_ascii
 vkb_graph_read_config_line vkb_graph_replace_display vkb_graph_set_source vkb_graph_set_sink_buffer
 vkb_graph_sink_size vkb_graph_set_frame vkb_graph_run vkb_graph_plan vkb_graph_perf vkb_graph_dump_nodes
-vkb_graph_set_source_device vkb_graph_sink_device vkb_graph_pool_bytes vkb_graph_stream vkb_graph_set_device vkb_dng_info""".split()
+vkb_graph_set_source_device vkb_graph_sink_device vkb_graph_pool_bytes vkb_graph_stream vkb_graph_set_device vkb_dng_info vkb_graph_set_sink_layout""".split()
 
 
 def token(s):
@@ -91,6 +91,7 @@ def launch_count():
 
 # ---- graph layer -------------------------------------------------------------------------------------------
 RUN_ALL = -1
+SINK_RGBA_F32, SINK_RGB_F32 = 0, 1
 RUN_ROI, RUN_CREATE_NODES, RUN_ALLOC, RUN_RECORD, RUN_UPLOAD, RUN_DOWNLOAD, RUN_WAIT = 1, 2, 4, 8, 16, 32, 64
 
 lib.vkb_graph_new.restype = C.c_void_p
@@ -115,6 +116,7 @@ lib.vkb_host_free.argtypes = [C.c_void_p]
 lib.vkb_graph_stream.argtypes = [C.c_void_p]
 lib.vkb_graph_stream.restype = C.c_void_p
 lib.vkb_graph_set_device.argtypes = [C.c_void_p, C.c_int]
+lib.vkb_graph_set_sink_layout.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
 lib.vkb_dng_info.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
 lib.vkb_event_create.argtypes = [C.POINTER(C.c_void_p)]
 lib.vkb_event_record.argtypes = [C.c_void_p, C.c_void_p]
@@ -225,6 +227,10 @@ class Graph:
 
     def set_sink_buffer(self, ptr, nbytes, inst="main"):
         check(lib.vkb_graph_set_sink_buffer(self.h, inst.encode(), C.c_void_p(ptr) if ptr else None, nbytes))
+
+    def set_sink_layout(self, layout, inst="main"):
+        """SINK_RGBA_F32 (16 B/px, the reference's mapped sink buffer) or SINK_RGB_F32 (12 B/px, the PFM payload)."""
+        check(lib.vkb_graph_set_sink_layout(self.h, inst.encode(), layout))
 
     def run(self, flags=RUN_ALL):
         check(lib.vkb_graph_run(self.h, flags))

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) k_llap_final2(const uint2 *__restrict__ i
     c = { f16r(c.x), f16r(c.y), f16r(c.z) };
     c = grade_px(c, P.grade);
   }
-  if(F32) reinterpret_cast<float4 *>(outv)[(size_t)y * ow + x] = make_float4(c.x, c.y, c.z, 1.0f);
+  if(F32) st_sink_f32(outv, ow, x, y, c.x, c.y, c.z, P.out_f32);
   else st_rgba(reinterpret_cast<uint2 *>(outv), ow, x, y, make_float4(c.x, c.y, c.z, 1.0f));
 }
 
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(256) k_llap_final4(const uint2 *__restrict__ i
       c = { f16r(c.x), f16r(c.y), f16r(c.z) };
       c = grade_px(c, P.grade);
     }
-    if(F32) reinterpret_cast<float4 *>(outv)[(size_t)y * ow + x] = make_float4(c.x, c.y, c.z, 1.0f);
+    if(F32) st_sink_f32(outv, ow, x, y, c.x, c.y, c.z, P.out_f32);
     else st_rgba(reinterpret_cast<uint2 *>(outv), ow, x, y, make_float4(c.x, c.y, c.z, 1.0f));
   }
 }
@@ -270,14 +270,15 @@ static int launch_llapfin2(const vkb_launch_t *l)
   VKB_REQUIRE(l->num_conn >= 4 && l->push_size >= 8 && l->params_size >= sizeof(llap_params_t));
   const uint32_t *pc = (const uint32_t *)l->push;
   const vkb_image_t *in = l->conn, *coarse = l->conn + 1, *l1 = l->conn + 2, *out = l->conn + 3;
-  VKB_REQUIRE(in->chan == 4 && in->format == VKB_TOKEN_F16 && l1->layers == NL && out->chan == 4);
+  VKB_REQUIRE(in->chan == 4 && in->format == VKB_TOKEN_F16 && l1->layers == NL);
   VKB_REQUIRE(in->wd == out->wd && in->ht == out->ht);
   VKB_REQUIRE(l1->wd == (in->wd - 1) / 2 + 1 && l1->ht == (in->ht - 1) / 2 + 1);
   VKB_REQUIRE(out->format == VKB_TOKEN_F16 || out->format == VKB_TOKEN_F32);
+  VKB_REQUIRE(out->chan == 4 || (out->chan == 3 && out->format == VKB_TOKEN_F32)); // 3: packed rgb f32 sink (VKB_SINK_RGB_F32)
   llapfin_t P;
   memset(&P, 0, sizeof(P));
   memcpy(&P.p, l->params, sizeof(llap_params_t));
-  P.first = pc[0]; P.have_grade = pc[1]; P.out_f32 = out->format == VKB_TOKEN_F32;
+  P.first = pc[0]; P.have_grade = pc[1]; P.out_f32 = out->format == VKB_TOKEN_F32 ? (out->chan == 3 ? 2 : 1) : 0;
   if(P.have_grade)
   {
     VKB_REQUIRE(l->params_size >= sizeof(llap_params_t) + sizeof(grade_params_t));

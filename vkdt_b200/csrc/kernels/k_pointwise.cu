@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) k_pointwise_t(const uint2 *__restrict__ i
     else if(ops[o] == PW_GRADE)    c = grade_px(c, P.grade);
     if(o < n - 1) c = round3(c);
   }
-  if(F32) reinterpret_cast<float4 *>(outv)[(size_t)y * ow + x] = make_float4(c.x, c.y, c.z, 1.0f);
+  if(F32) st_sink_f32(outv, ow, x, y, c.x, c.y, c.z, P.out_f32);
   else st_rgba(reinterpret_cast<uint2 *>(outv), ow, x, y, make_float4(c.x, c.y, c.z, 1.0f));
 }
 
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) k_pointwise(const uint2 *__restrict__ in,
       else if(P.op[o] == PW_GRADE)    c = grade_px(c, P.grade);
       if(o < P.n_ops - 1) c = round3(c);
     }
-    if(P.out_f32) reinterpret_cast<float4 *>(outv)[(size_t)y * ow + x] = make_float4(c.x, c.y, c.z, 1.0f);
+    if(P.out_f32) st_sink_f32(outv, ow, x, y, c.x, c.y, c.z, P.out_f32);
     else st_rgba(reinterpret_cast<uint2 *>(outv), ow, x, y, make_float4(c.x, c.y, c.z, 1.0f));
   }
 }
@@ -179,12 +179,13 @@ static int launch_chain(const vkb_launch_t *l, int n_ops, const uint32_t *ops)
 {
   VKB_REQUIRE(l->num_conn >= 2 && n_ops >= 1 && n_ops <= 8);
   const vkb_image_t *in = l->conn, *out = l->conn + 1;
-  VKB_REQUIRE(in->chan == 4 && in->format == VKB_TOKEN_F16 && out->chan == 4);
+  VKB_REQUIRE(in->chan == 4 && in->format == VKB_TOKEN_F16);
   VKB_REQUIRE(out->format == VKB_TOKEN_F16 || out->format == VKB_TOKEN_F32);
+  VKB_REQUIRE(out->chan == 4 || (out->chan == 3 && out->format == VKB_TOKEN_F32)); // 3: packed rgb f32 sink (VKB_SINK_RGB_F32)
   pw_chain_t P;
   memset(&P, 0, sizeof(P));
   P.n_ops = n_ops;
-  P.out_f32 = out->format == VKB_TOKEN_F32;
+  P.out_f32 = out->format == VKB_TOKEN_F32 ? (out->chan == 3 ? 2 : 1) : 0;
   const uint8_t *pp = (const uint8_t *)l->params;
   uint32_t left = l->params_size;
   for(int o = 0; o < n_ops; o++)

@@ -1,0 +1,26 @@
+// sink side helpers of the executor.
+// (b200, pfmpack): rgba f32 -> packed rgb f32, the PFM payload (o-pfm/main.c:36-40).  only launched when the producer of
+// the sink image is not one of the fused kernels that store r g b themselves (k_llap_fin.cu, k_pointwise.cu).
+#include "common.cuh"
+
+__global__ void __launch_bounds__(256) k_pfmpack(const float4 *__restrict__ in, float *__restrict__ out, size_t n)
+{
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if(i >= n) return;
+  const float4 v = __ldg(in + i);
+  out[3 * i] = v.x; out[3 * i + 1] = v.y; out[3 * i + 2] = v.z;
+}
+
+// conn: [0] rgba f32, [1] rgb f32 (chan 3)
+static int launch_pfmpack(const vkb_launch_t *l)
+{
+  VKB_REQUIRE(l->num_conn >= 2);
+  const vkb_image_t *in = l->conn, *out = l->conn + 1;
+  VKB_REQUIRE(in->chan == 4 && in->format == VKB_TOKEN_F32 && out->chan == 3 && out->format == VKB_TOKEN_F32);
+  VKB_REQUIRE(in->wd == out->wd && in->ht == out->ht);
+  const size_t n = (size_t)in->wd * in->ht;
+  k_pfmpack<<<(unsigned)((n + 255) / 256), 256, 0, l->stream>>>((const float4 *)in->data, (float *)out->data, n);
+  VKB_CHECK_LAUNCH();
+  return VKB_OK;
+}
+VKB_REGISTER("b200", "pfmpack", launch_pfmpack);

@@ -72,7 +72,16 @@ int vkb_graph_set_sink_buffer(vkb_graph_t *h, const char *inst, void *dst, size_
   if(!h) return VKB_ERR_BAD_ARG;
   const int m = find_inst(h->g, inst, false);
   if(m < 0) return vkb_set_error(VKB_ERR_BAD_ARG, "no sink module with instance '%s'", inst ? inst : "main");
-  h->g->mem_sink[m] = vkb_mem_sink_t{ dst, bytes, 1 };
+  const int layout = h->g->mem_sink[m].layout;
+  h->g->mem_sink[m] = vkb_mem_sink_t{ dst, bytes, 1, layout };
+  return VKB_OK;
+}
+int vkb_graph_set_sink_layout(vkb_graph_t *h, const char *inst, int layout)
+{
+  if(!h || (layout != VKB_SINK_RGBA_F32 && layout != VKB_SINK_RGB_F32)) return VKB_ERR_BAD_ARG;
+  const int m = find_inst(h->g, inst, false);
+  if(m < 0) return vkb_set_error(VKB_ERR_BAD_ARG, "no sink module with instance '%s'", inst ? inst : "main");
+  h->g->mem_sink[m].layout = layout;
   return VKB_OK;
 }
 int vkb_graph_sink_size(vkb_graph_t *h, const char *inst, uint32_t *wd, uint32_t *ht)

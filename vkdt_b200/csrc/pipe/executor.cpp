@@ -34,7 +34,7 @@ struct plan_launch_t
   float ms = 0.0f;
 };
 struct plan_source_t { int modid; int nodeid; int buf_upload; size_t bytes; int packed_bpp; int external; };
-struct plan_sink_t   { int modid; int nodeid; int buf; size_t bytes; uint32_t wd, ht; };
+struct plan_sink_t   { int modid; int nodeid; int buf; size_t bytes; uint32_t wd, ht; int rgb; };
 
 struct vkb_plan_t
 {
@@ -361,7 +361,41 @@ static int build_plan(dt_graph_t *g, bool with_device)
       const plan_img_t in = B.img_in(n, 0);
       s.modid = modid; s.nodeid = n; s.buf = in.buf; s.wd = in.wd; s.ht = in.ht;
       s.bytes = (size_t)in.wd * in.ht * in.chan * (in.format == dt_token("f32") ? 4 : 2);
-      if(in.buf >= 0) p->buf[in.buf].pinned_live = 1;
+      s.rgb = 0;
+      // packed rgb f32 (the PFM payload): asked for by the caller, or implied by o-pfm writing a file
+      const vkb_mem_sink_t *msk = modid < (int)g->mem_sink.size() ? &g->mem_sink[modid] : 0;
+      const bool to_file = !(msk && msk->valid) && nd->module->name == dt_token("o-pfm");
+      if(in.buf >= 0 && in.chan == 4 && in.format == dt_token("f32") && (to_file || (msk && msk->layout == VKB_SINK_RGB_F32)))
+      {
+        // the launch that writes this buffer: if it is one of the fused kernels it stores r g b directly
+        bool fused = false;
+        for(int li = (int)p->launch.size() - 1; li >= 0 && !fused; li--)
+        {
+          plan_launch_t &pl = p->launch[li];
+          int ci = -1;
+          for(size_t c = 0; c < pl.conn.size(); c++) if(pl.conn[c].buf == in.buf) ci = (int)c;
+          if(ci < 0) continue;
+          if(pl.name == dt_token("b200") && ((pl.kernel == dt_token("llapfin") && ci == 3) || (pl.kernel == dt_token("pointw") && ci == 1)))
+          { pl.conn[ci].chan = 3; fused = true; }
+          break;
+        }
+        if(!fused)
+        { // any other producer: one repack launch behind it
+          plan_buf_t b;
+          b.bytes = (((size_t)in.wd * in.ht * 12 + 255) / 256) * 256 + 256;
+          p->buf.push_back(b);
+          plan_launch_t l;
+          l.name = dt_token("b200"); l.kernel = dt_token("pfmpack"); l.wd = in.wd; l.ht = in.ht; l.dp = 1;
+          l.conn.push_back(in);
+          l.conn.push_back(plan_img_t{ (int)p->buf.size() - 1, in.wd, in.ht, 3, 1, dt_token("f32") });
+          l.label = dt_token_string(nd->module->name) + " b200_pfmpack (rgba -> rgb)";
+          B.add_launch(l);
+          s.buf = l.conn[1].buf;
+        }
+        s.bytes = (size_t)in.wd * in.ht * 12;
+        s.rgb = 1;
+      }
+      if(s.buf >= 0) p->buf[s.buf].pinned_live = 1;
       p->sink.push_back(s);
       continue;
     }

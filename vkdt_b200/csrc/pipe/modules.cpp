@@ -979,13 +979,8 @@ static void opfm_write_sink(dt_module_t *module, void *buf, dt_write_sink_params
   while((len + 1 + off) & 0xf) off++;
   while(off-- > 0) fputc('0', f);
   fputc('\n', f);
-  // rgb only: gather rows into a buffer instead of one fwrite per pixel
-  std::vector<float> row((size_t)width * 3);
-  for(int j = 0; j < height; j++)
-  {
-    const float *src = pf + (size_t)4 * j * width;
-    for(int i = 0; i < width; i++) { row[3*i] = src[4*i]; row[3*i+1] = src[4*i+1]; row[3*i+2] = src[4*i+2]; }
-    fwrite(row.data(), sizeof(float), row.size(), f);
-  }
+  // the executor hands a file sink the payload as the file wants it (r g b per pixel, VKB_SINK_RGB_F32): the last
+  // kernel stored it that way, so this is one write instead of the reference's fwrite per pixel (o-pfm/main.c:36-40)
+  fwrite(pf, sizeof(float), (size_t)3 * width * height, f);
   fclose(f);
 }

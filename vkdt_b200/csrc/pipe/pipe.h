@@ -177,7 +177,7 @@ struct dt_node_t
 
 // in-memory source / sink redirection (vkb_graph_set_source / vkb_graph_set_sink_buffer)
 struct vkb_mem_source_t { const void *data; int on_device; vkb_raw_params_t p; int valid; };
-struct vkb_mem_sink_t   { void *dst; size_t bytes; int valid; };
+struct vkb_mem_sink_t   { void *dst; size_t bytes; int valid; int layout; }; // layout: VKB_SINK_RGBA_F32 | VKB_SINK_RGB_F32
 
 struct vkb_plan_t; // executor.cpp
 
