@@ -182,7 +182,7 @@ def run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, s
     # ---- leg 2: end to end through the C-ABI with host buffers ----
     # two graph instances (each with its own pool, stream and pinned sink) ping-pong: while one frame's 722 MB result
     # drains over PCIe the next frame uploads and computes.  every frame still pays its full H2D + kernels + D2H.
-    NG = 2
+    NG = max(2, int(os.environ.get('VKB_E2E_GRAPHS', '2')))
     gs, host_out = [], []
     for k in range(NG):
         gk = make_graph()

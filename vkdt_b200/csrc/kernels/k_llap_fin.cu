@@ -170,7 +170,7 @@ VKB_DEV float expand1(const float (*T)[F3_W + 1], int lx, int ly, int q)
 }
 
 template <bool F32, bool GRADE>
-__global__ void __launch_bounds__(256) k_llap_final4(const uint2 *__restrict__ in, const __half *__restrict__ coarse,
+__global__ void __launch_bounds__(256, 3) k_llap_final4(const uint2 *__restrict__ in, const __half *__restrict__ coarse,
     const __half *__restrict__ l1, int cw, int ch, void *__restrict__ outv, int ow, int oh, const __grid_constant__ llapfin_t P)
 {
   __shared__ float tile[NL + 1][F3_H][F3_W + 1];
@@ -223,6 +223,8 @@ __global__ void __launch_bounds__(256) k_llap_final4(const uint2 *__restrict__ i
   const float inv2s = 1.0f / (2.0f * P.p.sigma), invd = 1.0f / (2.0f * P.p.sigma * P.p.sigma / 3.0f);
   const int lx = kx - cx0, ly = ky - cy0;
   float res[4], e0[4], e1[4];
+  float oc[6]; // packed rgb sink: the thread's two pixels of a row, stored by the warp together
+  __shared__ __align__(16) float stage[8][196];
   expand4(tile[NL], lx, ly, res[0], res[1], res[2], res[3]);
   const bool same = (hi[1] < 0 || hi[1] == hi[0]) && (hi[2] < 0 || hi[2] == hi[0]) && (hi[3] < 0 || hi[3] == hi[0]);
   if(same)
@@ -242,7 +244,8 @@ __global__ void __launch_bounds__(256) k_llap_final4(const uint2 *__restrict__ i
 #pragma unroll
   for(int q = 0; q < 4; q++)
   {
-    if(hi[q] < 0) continue;
+    if(hi[q] >= 0)
+    {
     const int x = 2 * kx + (q & 1), y = 2 * ky + (q >> 1);
     const float glo = gamma_from_i(hi[q] - 1), ghi = gamma_from_i(hi[q]);
     const float a = clampf(__fdividef(v[q] - glo, ghi - glo), 0.0f, 1.0f);
@@ -258,8 +261,16 @@ __global__ void __launch_bounds__(256) k_llap_final4(const uint2 *__restrict__ i
       c = { f16r(c.x), f16r(c.y), f16r(c.z) };
       c = grade_px(c, P.grade);
     }
-    if(F32) st_sink_f32(outv, ow, x, y, c.x, c.y, c.z, P.out_f32);
+    if(F32 && P.out_f32 == 2) { oc[3 * (q & 1)] = c.x; oc[3 * (q & 1) + 1] = c.y; oc[3 * (q & 1) + 2] = c.z; }
+    else if(F32) st_sink_f32(outv, ow, x, y, c.x, c.y, c.z, P.out_f32);
     else st_rgba(reinterpret_cast<uint2 *>(outv), ow, x, y, make_float4(c.x, c.y, c.z, 1.0f));
+    }
+    if(F32 && (q & 1) && P.out_f32 == 2)
+    { // end of a row: the lanes left of the image border are the ones still here (hi[0] >= 0), contiguous from lane 0
+      const int x0 = blockIdx.x * 64, left = ow - x0, y = 2 * ky + (q >> 1);
+      if(y < oh) st_rgb_coop<6>(stage[threadIdx.y], reinterpret_cast<float *>(outv) + ((size_t)y * ow + x0) * 3, threadIdx.x,
+          min(32, (left + 1) >> 1), oc, 3 * min(64, left));
+    }
   }
 }
 

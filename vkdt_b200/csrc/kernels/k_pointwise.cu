@@ -53,7 +53,14 @@ __global__ void __launch_bounds__(256) k_pointwise_t(const uint2 *__restrict__ i
     else if(ops[o] == PW_GRADE)    c = grade_px(c, P.grade);
     if(o < n - 1) c = round3(c);
   }
-  if(F32) st_sink_f32(outv, ow, x, y, c.x, c.y, c.z, P.out_f32);
+  if(F32 && P.out_f32 == 2)
+  { // packed rgb sink: the lanes with x < ow are still here, contiguous from lane 0
+    __shared__ __align__(16) float stage[8][100];
+    const int x0 = blockIdx.x * 32, nl = min(32, ow - x0);
+    const float v[3] = { c.x, c.y, c.z };
+    st_rgb_coop<3>(stage[threadIdx.y], reinterpret_cast<float *>(outv) + ((size_t)y * ow + x0) * 3, threadIdx.x, nl, v, 3 * nl);
+  }
+  else if(F32) st_sink_f32(outv, ow, x, y, c.x, c.y, c.z, P.out_f32);
   else st_rgba(reinterpret_cast<uint2 *>(outv), ow, x, y, make_float4(c.x, c.y, c.z, 1.0f));
 }
 
