@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(256) k_denoise_doub(const uint16_t *__restrict
 // .75/.25 on texels X-1..X+1) share one 3x3 window of each coarse image and each pixel only needs its own colour channel,
 // so a block costs 9+9 texel loads and 25 f16 conversions instead of 32 loads and 96 conversions.  per pixel the
 // expressions are those of bilin_rgba() term by term.
-__global__ void __launch_bounds__(256) k_denoise_doub_bayer(const uint16_t *__restrict__ in, int iw, int ih,
+__global__ void __launch_bounds__(256, 4) k_denoise_doub_bayer(const uint16_t *__restrict__ in, int iw, int ih,
     const uint2 *__restrict__ crs0, const uint2 *__restrict__ crs1, int cw, int ch, __half *__restrict__ out, int ow, int oh,
     const __grid_constant__ denoise_params_t p, const __grid_constant__ dn_push_doub_t P)
 {

@@ -46,14 +46,16 @@ __global__ void __launch_bounds__(256) k_hilite_half(const __half *__restrict__ 
 // ---- reduce: 5x5 binomial over unclipped pixels, desaturating near white (reduce.comp:21-60) ----
 #define HR_TW 67
 #define HR_TH 19
+#define HR_COL(c) ((((c) & 1) * 34) + ((c) >> 1))
 __global__ void __launch_bounds__(256) k_hilite_reduce(const uint2 *__restrict__ in, int iw, int ih,
     uint2 *__restrict__ out, int ow, int oh, hilite_params_t p, float wbr, float wbg, float wbb)
 {
   // everything the shader evaluates per tap except the binomial weight depends on the input texel alone (luminance,
   // clip test, desaturated colour: seven divisions and two smoothsteps).  a CTA of 32x8 outputs evaluates it once per
   // texel of its 67x19 input window into shared memory; the 25 tap loop below only accumulates, in the shader's order.
-  __shared__ float4 tile[HR_TH][HR_TW]; // desaturated r g b, luminance
-  __shared__ float  okay[HR_TH][HR_TW]; // 1 if no channel is clipped
+  // columns are stored even ones first, odd ones behind (HR_COL): a warp's taps 2*lane+ii then hit consecutive words
+  __shared__ float4 tile[HR_TH][HR_TW + 1]; // desaturated r g b, luminance
+  __shared__ float  okay[HR_TH][HR_TW + 1]; // 1 if no channel is clipped
   float white = p.white;
   if(!(white > 0.0f)) white = 1.0f;
   const float ds = p.desat * p.desat;
@@ -77,8 +79,8 @@ __global__ void __launch_bounds__(256) k_hilite_reduce(const uint2 *__restrict__
       m.y = mixf(rgb.y, (cmax + cmin) / wbg * .5f, tt);
       m.z = mixf(rgb.z, (cmax + cmin) / wbb * .5f, tt);
     }
-    tile[r][c] = m;
-    okay[r][c] = ok ? 1.0f : 0.0f;
+    tile[r][HR_COL(c)] = m;
+    okay[r][HR_COL(c)] = ok ? 1.0f : 0.0f;
   }
   __syncthreads();
   const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
@@ -92,11 +94,11 @@ __global__ void __launch_bounds__(256) k_hilite_reduce(const uint2 *__restrict__
 #pragma unroll
     for(int ii = 0; ii < 5; ii++)
     {
-      const float4 m = tile[ly + jj][lx + ii];
+      const float4 m = tile[ly + jj][HR_COL(lx + ii)];
       ex += w[jj] * sw[ii] * m.w;
       ey += w[ii] * sw[jj] * m.w;
       const float u = w[ii] * w[jj];
-      if(okay[ly + jj][lx + ii] != 0.0f)
+      if(okay[ly + jj][HR_COL(lx + ii)] != 0.0f)
       {
         cr += m.x * u; cg += m.y * u; cb += m.z * u;
         wgt += u;
