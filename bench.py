@@ -103,6 +103,23 @@ def cpu_reference_rate(sample_wh, steps, warmup, strength):
 
 
 
+def ncu_traffic(label, key="bytes_per_launch"):
+    """dram bytes per launch (or SM issue-slot utilisation) of this kernel from the committed ncu --set full capture
+    (profiles/rNN_traffic.json), or None."""
+    import glob
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r*_traffic.json")))
+    if not files:
+        return None
+    try:
+        tr = json.load(open(files[-1]))[key]
+    except (OSError, ValueError, KeyError):
+        return None
+    for k, v in tr.items():
+        if k in label:
+            return int(v) if key == "bytes_per_launch" else round(float(v), 1)
+    return None
+
+
 def run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, src, bpp, strength, steps, warmup, sample_clocks=True):
     """both legs (kernel path with HBM-resident input, end to end with host buffers) of one workload on this rank."""
     # ---- synthetic input: a few distinct stills per rank, cycled (deterministic seeds per SURVEY §8d) ----
@@ -298,7 +315,9 @@ def main():
     total_ms = sum(v[0] / v[1] for v in per_kernel.values())
     graph_alg_bytes = in_bytes + out_bytes
     roof = {"bound": "hbm", "kernel": top_label, "achieved": round(achieved, 1), "peak": pk["hbm_gbs"], "peak_kind": pk_kind + " copy bandwidth",
-            "unit": "GB/s", "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": None,
+            "unit": "GB/s", "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": ncu_traffic(top_label),
+            "sm_issue_pct": ncu_traffic(top_label, "sm_issue_pct"),
+            "note": "instruction bound, not HBM bound: see sm_issue_pct (ncu smsp__issue_active of this kernel) and DESIGN.md section 3",
             "algorithmic_bytes_per_launch": top_bytes, "avg_launch_ms": round(top_ms, 4),
             "share_of_step": round(top_ms / total_ms, 4),
             "graph": {"algorithmic_bytes_per_step": graph_alg_bytes, "achieved_gbs": round(graph_alg_bytes / (t_kernel_ms / args.steps * 1e-3) / 1e9, 1),

@@ -13,6 +13,7 @@ if strength > 0:
 d = api.dev_alloc(raw.nbytes + 256)
 api.check(api.lib.vkb_memcpy_h2d(d, raw.ctypes.data, raw.nbytes, None)); api.check(api.lib.vkb_stream_sync(None))
 g.set_source(d, api.raw_params(W, H, wb=(2.0, 1.0, 1.5), noise_a=100.0, noise_b=2.0), device=True)
+g.set_sink_layout(api.SINK_RGB_F32)  # as bench.py: the PFM payload
 g.set_sink_buffer(None, 0)
 g.run()
 for _ in range(3):
