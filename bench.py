@@ -31,6 +31,8 @@ WORKLOADS = {
     "still61": (9504, 6336, "i-raw", 0),
     "still24": (6000, 4000, "i-raw", 0),
     "mlv4k": (4096, 2160, "i-mlv", 14),
+    "xtrans26": (6240, 4152, "i-raw", 0),     # BASELINE config 3 (x-trans: filters 9)
+    "still201": (16384, 12288, "i-raw", 0),   # BASELINE config 5 on ONE GPU (the band split is not built)
 }
 WB = (2.0, 1.0, 1.5)
 CAM = (0.8, 0.15, 0.05, 0.1, 0.85, 0.05, 0.02, 0.18, 0.8)
@@ -123,15 +125,21 @@ def ncu_traffic(label, key="bytes_per_launch"):
 def run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, src, bpp, strength, steps, warmup, sample_clocks=True):
     """both legs (kernel path with HBM-resident input, end to end with host buffers) of one workload on this rank."""
     # ---- synthetic input: a few distinct stills per rank, cycled (deterministic seeds per SURVEY §8d) ----
-    nstills = 2
-    raws = [synth.mosaic(W, H, seed=0x5EED0000 + rank * 1000 + i, wb=WB) for i in range(nstills)]
+    xtrans = args.workload == "xtrans26" and src == "i-raw"
+    big = W * H > 100e6
+    nstills = 1 if big else 2
+    if big:   # a 4x4 tiling of a 12.6 MP synthetic still: same statistics, generated in seconds
+        raws = [np.ascontiguousarray(np.tile(synth.mosaic(W // 4, H // 4, seed=0x5EED0000 + rank * 1000 + i, wb=WB), (4, 4))) for i in range(nstills)]
+    else:
+        raws = [synth.mosaic(W, H, seed=0x5EED0000 + rank * 1000 + i, wb=WB, xtrans=xtrans) for i in range(nstills)]
     if bpp:
         payload = [synth.pack_bits_fast14(r) for r in raws]
         in_bytes = (W * H * bpp + 7) // 8
     else:
         payload = raws
         in_bytes = W * H * 2
-    rp = api.raw_params(W, H, wb=WB, cam_to_rec2020=CAM, noise_a=100.0, noise_b=2.0, packed_bpp=bpp)
+    rp = api.raw_params(W, H, wb=WB, cam_to_rec2020=CAM, noise_a=100.0, noise_b=2.0, packed_bpp=bpp,
+                        **({"filters": 9} if xtrans else {}))
     # pinned host staging for the e2e leg, device copies for the kernel leg
     host_in = []
     for p in payload:
@@ -328,8 +336,9 @@ def main():
         "metric": "MP/s raw->display graph", "value": round(world * args.steps * mp / (t_kernel_ms * 1e-3), 2), "unit": "MP/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t_kernel_ms / args.steps, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: %dx%d bayer rggb 14-bit still (%.1f MP), default darkroom graph incl. hilite + llap + grade, "
-                               "denoise strength %.2f, sink rgb f32 %dx%d (PFM payload, 12 B/px)" % (args.workload, W, H, mp, strength, ow, oh),
+        "config": {"workload": "%s: %dx%d %s 14-bit still (%.1f MP), default darkroom graph incl. hilite + llap + grade, "
+                               "denoise strength %.2f, sink rgb f32 %dx%d (PFM payload, 12 B/px)" % (
+                                   args.workload, W, H, "x-trans" if args.workload == "xtrans26" else "bayer rggb", mp, strength, ow, oh),
                    "timing": "inputs and intermediates (%.0f MB pool) exceed the 126 MB L2; %d distinct stills cycled" % (R["pool_bytes"] / 1e6, nstills),
                    "parallelism": "independent stills per GPU, no collective", "edges": "f16 at every reference edge (strict)"},
         "e2e": {"value": round(world * e2e_steps * mp / (t_e2e_ms * 1e-3), 2), "unit": "MP/s", "h2d_bytes_per_step": in_bytes,

@@ -364,7 +364,7 @@ def test_denoise_wavelet_kernels(gpu, oracle, dims, na, nb):
 XT = 9
 
 
-@pytest.mark.parametrize("dims", [(258, 192), (132, 102)])
+@pytest.mark.parametrize("dims", [(258, 192), (132, 102), (261, 195)])
 def test_xtrans_hilite_and_demosaic_kernels(gpu, oracle, dims):
     O = oracle
     w, h = dims

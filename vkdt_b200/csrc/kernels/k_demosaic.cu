@@ -7,6 +7,8 @@
 struct demosaic_push_t { float wb[4]; uint32_t filters; };
 int launch_bayer_splat(const vkb_launch_t *l);
 int launch_bayer_fix(const vkb_launch_t *l);
+int launch_xtrans_splat(const vkb_launch_t *l);
+int launch_xtrans_fix(const vkb_launch_t *l);
 
 // ---- gauss: green-only structure tensor per block -> (eval.xy, axis snapped evec) (gauss.comp:17-126) ----
 // the tap pattern is a compile time property of the cfa: both loops unroll completely and the taps stay in registers.
@@ -169,6 +171,7 @@ static int launch_demosaic_splat(const vkb_launch_t *l)
   const vkb_image_t *in = l->conn, *g = l->conn + 1, *out = l->conn + 2;
   VKB_REQUIRE(in->chan == 1 && g->chan == 4 && out->chan == 1 && in->wd == out->wd && in->ht == out->ht);
   if(pc->filters != 9) return launch_bayer_splat(l); // one thread per shifted 2x2 block, k_demosaic_bayer.cu
+  return launch_xtrans_splat(l); // one thread per 3x3 block, k_demosaic_xtrans.cu
   k_demosaic_splat<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const __half *)in->data, in->wd, in->ht,
       (const uint2 *)g->data, g->wd, g->ht, (__half *)out->data, pc->filters == 9);
   VKB_CHECK_LAUNCH();
@@ -184,6 +187,7 @@ static int launch_demosaic_fix(const vkb_launch_t *l)
   const vkb_image_t *in = l->conn, *g = l->conn + 1, *cov = l->conn + 2, *out = l->conn + 3;
   VKB_REQUIRE(in->chan == 1 && g->chan == 1 && cov->chan == 4 && out->chan == 4 && in->wd == out->wd && g->wd == out->wd);
   if(pc->filters != 9 && ((const int32_t *)l->params)[0] <= 0) return launch_bayer_fix(l); // radius 1 fast path
+  if(pc->filters == 9 && ((const int32_t *)l->params)[0] <= 0) return launch_xtrans_fix(l); // radius 2: one thread per 3x3 block, k_demosaic_xtrans.cu
   k_demosaic_fix<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const __half *)in->data, (const __half *)g->data, in->wd, in->ht,
       (const uint2 *)cov->data, cov->wd, cov->ht, (uint2 *)out->data, pc->filters == 9, ((const int32_t *)l->params)[0]);
   VKB_CHECK_LAUNCH();
