@@ -104,6 +104,8 @@ enum
   VKB_RUN_UPLOAD_SOURCE  = 1 << 4,
   VKB_RUN_DOWNLOAD_SINK  = 1 << 5,
   VKB_RUN_WAIT_DONE      = 1 << 6,
+  VKB_RUN_PERF           = 1 << 7,  /* ours: time every launch with its own event pair (-d perf, vkb_graph_perf); costs ~1 us of
+                                       stream idle per launch, so frame loops leave it off */
   VKB_RUN_ALL            = -1,
 };
 

@@ -17,7 +17,7 @@ g.set_sink_layout(api.SINK_RGB_F32)  # as bench.py: the PFM payload
 g.set_sink_buffer(None, 0)
 g.run()
 for _ in range(3):
-    g.run(api.RUN_RECORD | api.RUN_UPLOAD | api.RUN_WAIT)
+    g.run(api.RUN_RECORD | api.RUN_UPLOAD | api.RUN_WAIT | api.RUN_PERF)
 tot = 0.0
 for label, ms, nb in g.perf_entries():
     tot += ms

@@ -41,7 +41,7 @@ def _run_graph(gpu, raw, src="i-raw", packed=False, extra=(), noise=(1.0, 1.0)):
     ow, oh = g.sink_size()
     out = np.zeros((oh, ow, 4), dtype=np.float32)
     g.set_sink_buffer(out.ctypes.data, out.nbytes)
-    g.run(gpu.RUN_RECORD | gpu.RUN_UPLOAD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT)
+    g.run(gpu.RUN_RECORD | gpu.RUN_UPLOAD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT | gpu.RUN_PERF)
     return out, g
 
 
@@ -154,7 +154,7 @@ def test_xtrans_end_to_end(gpu, oracle, strength):
     ow, oh = g.sink_size()
     out = np.zeros((oh, ow, 4), dtype=np.float32)
     g.set_sink_buffer(out.ctypes.data, out.nbytes)
-    g.run(gpu.RUN_RECORD | gpu.RUN_UPLOAD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT)
+    g.run(gpu.RUN_RECORD | gpu.RUN_UPLOAD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT | gpu.RUN_PERF)
     assert out.shape == want.shape
     err = np.abs(out[..., :3] - want[..., :3])
     p = psnr(out[..., :3], want[..., :3])
@@ -182,7 +182,7 @@ def test_halfsize_demosaic(gpu, oracle, xtrans):
     assert (oh, ow) == want.shape[:2]
     out = np.zeros((oh, ow, 4), dtype=np.float32)
     g.set_sink_buffer(out.ctypes.data, out.nbytes)
-    g.run(gpu.RUN_RECORD | gpu.RUN_UPLOAD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT)
+    g.run(gpu.RUN_RECORD | gpu.RUN_UPLOAD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT | gpu.RUN_PERF)
     perf = g.perf()
     assert "demosaic_halfsize" in perf and ("shared_resample" in perf) == xtrans
     err = np.abs(out[..., :3] - want[..., :3])
@@ -208,7 +208,7 @@ def test_rcd_demosaic(gpu, oracle, dims):
     ow, oh = g.sink_size()
     out = np.zeros((oh, ow, 4), dtype=np.float32)
     g.set_sink_buffer(out.ctypes.data, out.nbytes)
-    g.run(gpu.RUN_RECORD | gpu.RUN_UPLOAD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT)
+    g.run(gpu.RUN_RECORD | gpu.RUN_UPLOAD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT | gpu.RUN_PERF)
     perf = g.perf()
     assert "demosaic_rcd_conv" in perf and "demosaic_rcd_fill" in perf and "demosaic_splat" not in perf
     assert np.isfinite(dem_want).all()
@@ -248,7 +248,7 @@ def test_iraw_dng_file_source(gpu, oracle, tmp_path, cfa, xtrans):
     ow, oh = g.sink_size()
     got = np.zeros((oh, ow, 4), dtype=np.float32)
     g.set_sink_buffer(got.ctypes.data, got.nbytes)
-    g.run(gpu.RUN_RECORD | gpu.RUN_UPLOAD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT)
+    g.run(gpu.RUN_RECORD | gpu.RUN_UPLOAD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT | gpu.RUN_PERF)
     d = oracle.darkroom_defaults(ww, hh)
     d.filters = 9 if xtrans else d.filters
     d.noise_a, d.noise_b = 100.0, 2.0
@@ -303,7 +303,7 @@ def test_sink_rgb_layout(gpu, variant):
         ow, oh = g.sink_size()
         out = np.full((oh, ow, 4 if layout == gpu.SINK_RGBA_F32 else 3), -7.0, dtype=np.float32)
         g.set_sink_buffer(out.ctypes.data, out.nbytes)
-        g.run(gpu.RUN_RECORD | gpu.RUN_UPLOAD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT)
+        g.run(gpu.RUN_RECORD | gpu.RUN_UPLOAD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT | gpu.RUN_PERF)
         outs[layout] = out
         perf = g.perf()
         assert ("pfmpack" in perf) == (variant == "colour-only" and layout == gpu.SINK_RGB_F32), perf

@@ -92,7 +92,7 @@ def launch_count():
 # ---- graph layer -------------------------------------------------------------------------------------------
 RUN_ALL = -1
 SINK_RGBA_F32, SINK_RGB_F32 = 0, 1
-RUN_ROI, RUN_CREATE_NODES, RUN_ALLOC, RUN_RECORD, RUN_UPLOAD, RUN_DOWNLOAD, RUN_WAIT = 1, 2, 4, 8, 16, 32, 64
+RUN_ROI, RUN_CREATE_NODES, RUN_ALLOC, RUN_RECORD, RUN_UPLOAD, RUN_DOWNLOAD, RUN_WAIT, RUN_PERF = 1, 2, 4, 8, 16, 32, 64, 128
 
 lib.vkb_graph_new.restype = C.c_void_p
 lib.vkb_graph_free.argtypes = [C.c_void_p]

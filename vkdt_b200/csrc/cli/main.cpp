@@ -85,7 +85,7 @@ int main(int argc, char *argv[])
       snprintf(fn, sizeof(fn), "param:%s:main:filename:%s_%04d", format, filename, f);
       vkb_graph_read_config_line(g, fn);
     }
-    int flags = f == 0 ? VKB_RUN_ALL : (VKB_RUN_RECORD_CMD_BUF | VKB_RUN_UPLOAD_SOURCE | VKB_RUN_DOWNLOAD_SINK | VKB_RUN_WAIT_DONE);
+    int flags = f == 0 ? VKB_RUN_ALL : (VKB_RUN_RECORD_CMD_BUF | VKB_RUN_UPLOAD_SOURCE | VKB_RUN_DOWNLOAD_SINK | VKB_RUN_WAIT_DONE | (perf ? VKB_RUN_PERF : 0));
     if(last_only && f < frames - 1) flags &= ~VKB_RUN_DOWNLOAD_SINK;
     err = vkb_graph_run(g, flags);
     if(err) fprintf(stderr, "[cli] frame %d: %s\n", f, vkb_last_error());

@@ -560,12 +560,12 @@ int dt_graph_run(dt_graph_t *g, uint32_t run)
       }
       conn.clear();
       for(const plan_img_t &im : l.conn) conn.push_back(vkb_image_t{ buf_ptr(p, im.buf), im.wd, im.ht, im.chan, im.layers, im.format });
-      cudaEventRecord(p->ev[i], p->stream);
+      if(run & VKB_RUN_PERF) cudaEventRecord(p->ev[i], p->stream);
       r = vkb_dispatch(l.name, l.kernel, l.wd, l.ht, l.dp, l.push.data(), (uint32_t)l.push.size(), params.data(), (uint32_t)params.size(),
           conn.data(), (uint32_t)conn.size(), p->stream);
       if(r) return r;
     }
-    cudaEventRecord(p->ev[p->launch.size()], p->stream);
+    if(run & VKB_RUN_PERF) cudaEventRecord(p->ev[p->launch.size()], p->stream);
   }
   if(run & VKB_RUN_DOWNLOAD_SINK)
   {
@@ -595,7 +595,7 @@ int dt_graph_run(dt_graph_t *g, uint32_t run)
   {
     cudaError_t e = cudaStreamSynchronize(p->stream);
     if(e != cudaSuccess) return vkb_set_error(VKB_ERR_CUDA, "graph run failed: %s", cudaGetErrorString(e));
-    if(run & VKB_RUN_RECORD_CMD_BUF)
+    if((run & VKB_RUN_RECORD_CMD_BUF) && (run & VKB_RUN_PERF))
     { // -d perf (graph.c:881-933)
       char b[256];
       g->perf_text.clear();
