@@ -310,3 +310,29 @@ def test_sink_rgb_layout(gpu, variant):
     a, b = outs[gpu.SINK_RGBA_F32], outs[gpu.SINK_RGB_F32]
     assert a.shape[:2] == b.shape[:2] and np.isfinite(b).all() and (a[..., 3] == 1.0).all()
     assert np.array_equal(a[..., :3], b)
+
+
+@pytest.mark.parametrize("dims", [(36, 36), (70, 50), (200, 18), (18, 130), (98, 66)])
+@pytest.mark.parametrize("strength", [0.0, 0.4])
+def test_small_and_ragged_frames(gpu, oracle, dims, strength):
+    """frames smaller than one CTA window in one or both directions: every tiled kernel has to fall back to (or agree
+    with) general mirroring, the pyramids bottom out after a few levels, crop's micro-crop rule switches off (<= 400)."""
+    w, h = dims
+    raw = synth.mosaic(w, h, seed=77)
+    want = oracle.darkroom_run(_oracle_cfg(oracle, w, h, strength=strength, noise=(100.0, 2.0)), raw)
+    extra = ("param:denoise:01:strength:%g" % strength,) if strength > 0 else ()
+    got, g = _run_graph(gpu, raw, extra=extra, noise=(100.0, 2.0))
+    assert got.shape == want.shape
+    assert np.isfinite(got[..., :3]).all()
+    err = np.abs(got[..., :3] - want[..., :3])
+    p = psnr(got[..., :3], want[..., :3])
+    print("%dx%d strength %.1f: max abs %.3g psnr %.1f" % (w, h, strength, err.max(), p))
+    assert p >= 60.0 and err.max() <= 2e-3 and (err > 1e-3).mean() <= 1e-3
+
+
+def test_empty_source_is_an_error(gpu):
+    g = gpu.Graph(cfg_text=gpu.DARKROOM_CFG.format(src="i-raw"))
+    raw = np.zeros((2, 2), np.uint16)
+    g.set_source(raw.ctypes.data, gpu.raw_params(0, 0))
+    with pytest.raises(gpu.VkbError):
+        g.run()
