@@ -78,6 +78,15 @@ def build(ref=True):
         subprocess.run(["make", "-C", _HERE, "-s", "ref"], check=True)
 
 
+def set_threads(n=None):
+    """OpenMP threads of the restatement; returns the count in effect.  torchrun exports OMP_NUM_THREADS=1 to its
+    workers, which would silently turn the "all host cores" CPU baseline into a single-threaded one."""
+    lib()
+    gomp = C.CDLL("libgomp.so.1")
+    gomp.omp_set_num_threads(int(n or os.cpu_count() or 1))
+    return int(gomp.omp_get_max_threads())
+
+
 def lib():
     global _lib
     if _lib is None:
