@@ -264,6 +264,13 @@ def test_crop_and_fused_chain(gpu, oracle, dims, persp, rot):
     gpu.dispatch("b200", "pointw", [gpu.image(d_a, w, h, 4, "f16"), gpu.image(d_out2, ow, oh, 4, "f16")], ubits(3, 1, 2, 3),
                  fc.tobytes() + fcol.tobytes() + bytes(d.filmcurv))
     assert_close_mixed(to_host(d_out2)[..., :3], c2[..., :3], 3, 4e-6, 0.90, "fused crop+colour+filmcurv", max_outliers=2e-5)
+    if rot == 1337.0 and not persp:
+        # the straight-line kernel the default parameters select against the node by node kernels with f16 images between
+        # them (crop above, then colour, then filmcurv): the fused graph is value-compatible with the unfused one
+        d_c = dev_f16(oh, ow, 4); d_f = dev_f16(oh, ow, 4)
+        gpu.dispatch("colour", "main", [gpu.image(d_out, ow, oh, 4, "f16"), gpu.image(d_c, ow, oh, 4, "f16")], b"", fcol.tobytes())
+        gpu.dispatch("filmcurv", "main", [gpu.image(d_c, ow, oh, 4, "f16"), gpu.image(d_f, ow, oh, 4, "f16")], b"", bytes(d.filmcurv))
+        assert f16_ulp_diff(to_host(d_out2)[..., :3], to_host(d_f)[..., :3]).max() == 0
 
 
 @pytest.mark.parametrize("dims", [(506, 384), (253, 191), (64, 40)])

@@ -182,6 +182,80 @@ static int colour_digest(const float *f, uint32_t size, colour_digest_t *d)
   return VKB_OK;
 }
 
+// the default darkroom chain with default-shaped parameters, as straight-line code: crop as an integer shift,
+// colour = matrix * exposure (no trc decode, no clipping, no rbf, saturation 1), filmcurv colour mode 3 (per channel
+// weibull curve + dng hue preservation).  the launcher checks those conditions; every other combination keeps the
+// kernels above.  same device functions, same f16 roundings: values are identical to k_pointwise_t, the difference is
+// ~100 instead of ~190 issued instructions per pixel (the uniform parameter tests and the dead paths' register
+// pressure), which is what decides the speed of this kernel.
+// weibull_cdf() of pointwise.cuh on the bare SFU instructions.  __powf / __expf expand to the same ex2.approx / lg2.approx
+// but wrap each in a denormal guard (compare, scale, unscale: 4 instructions instead of 1); arguments here are >= 1e-7 * il
+// and a result below 2^-126 only ever enters 1 - x, so flushing it changes nothing.
+VKB_DEV float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+VKB_DEV float lg2_ftz(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+VKB_DEV float weibull_cdf_ftz(float x, float il, float k)
+{
+  const float p = ex2_ftz(k * lg2_ftz(fmaxf(x, 1e-7f) * il));   // __powf(x * il, k)
+  return 1.0f - ex2_ftz(-p * 1.4426950408889634f);               // __expf(-p)
+}
+#define PW_NPX 4
+template <bool F32>
+__global__ void __launch_bounds__(256) k_pointwise_dflt(const uint2 *__restrict__ in, int iw, int ih,
+    void *__restrict__ outv, int ow, int oh, const __grid_constant__ pw_chain_t P)
+{
+  // PW_NPX pixels per thread, 32 apart: all loads are issued before the first dependent instruction, which keeps
+  // enough bytes in flight per SM for HBM latency (one 8 byte load per thread does not: 2.7 TB/s)
+  const int y = blockIdx.y * 8 + threadIdx.y;
+  if(y >= oh) return;
+  uint2 raw[PW_NPX];
+#pragma unroll
+  for(int q = 0; q < PW_NPX; q++)
+  {
+    const int x = (blockIdx.x * PW_NPX + q) * 32 + threadIdx.x;
+    if(x < ow) raw[q] = __ldg(in + (size_t)(y + P.sy) * iw + x + P.sx); // inside the input for every output pixel: proven on the host
+  }
+#pragma unroll
+  for(int q = 0; q < PW_NPX; q++)
+  {
+  const int x = (blockIdx.x * PW_NPX + q) * 32 + threadIdx.x;
+  if(x >= ow) continue;
+  const float4 px = h4_to_f4(raw[q]);
+  // crop's output edge is f16: the fetched texel already is
+  const colour_digest_t &C = P.colour;
+  f3 o = { C.A[0] * px.x + C.A[1] * px.y + C.A[2] * px.z,
+           C.A[3] * px.x + C.A[4] * px.y + C.A[5] * px.z,
+           C.A[6] * px.x + C.A[7] * px.y + C.A[8] * px.z };
+  o.x *= C.exposure; o.y *= C.exposure; o.z *= C.exposure;
+  o.x = clampf(o.x, -65535.0f, 65535.0f); o.y = clampf(o.y, -65535.0f, 65535.0f); o.z = clampf(o.z, -65535.0f, 65535.0f);
+  o = round3(o);
+  const float il = fmaxf(5e-3f, P.film.light), k = fmaxf(1e-4f, P.film.contrast);
+  const f3 col0 = { o.x + P.film.bias, o.y + P.film.bias, o.z + P.film.bias };
+  // adjust_colour_dng(col0, curve(col0)) (shared.glsl:371-387) sorts the channels by col0, keeps the curve values of the
+  // largest and smallest and replaces the middle one by a blend of those two: the middle channel's own curve value
+  // is never used.  sorting col0 first (same comparisons, same tie breaking) and evaluating the curve on the sorted
+  // maximum and minimum gives bit-identical results with two curve evaluations instead of three and half the selects.
+  float s0 = col0.x, s1 = col0.y, s2 = col0.z, t;
+  const bool fx = s2 > s1; if(fx) { t = s2; s2 = s1; s1 = t; }
+  const bool fy = s1 > s0; if(fy) { t = s0; s0 = s1; s1 = t; }
+  const bool fz = s2 > s1; if(fz) { t = s2; s2 = s1; s1 = t; }
+  float r0 = weibull_cdf_ftz(s0, il, k), r2 = weibull_cdf_ftz(s2, il, k);
+  float r1 = mixf(r2, r0, __fdividef(s1 - s2 + 1e-6f, s0 - s2 + 1e-6f));
+  if(fz) { t = r2; r2 = r1; r1 = t; }
+  if(fy) { t = r0; r0 = r1; r1 = t; }
+  if(fx) { t = r2; r2 = r1; r1 = t; }
+  const f3 c = { r0, r1, r2 };
+  if(F32 && P.out_f32 == 2)
+  {
+    __shared__ float stage[8][96];
+    const int x0 = (blockIdx.x * PW_NPX + q) * 32, nl = min(32, ow - x0);
+    const float v[3] = { c.x, c.y, c.z };
+    st_rgb_coop<3>(stage[threadIdx.y], reinterpret_cast<float *>(outv) + ((size_t)y * ow + x0) * 3, threadIdx.x, nl, v, 3 * nl);
+  }
+  else if(F32) st_sink_f32(outv, ow, x, y, c.x, c.y, c.z, P.out_f32);
+  else st_rgba(reinterpret_cast<uint2 *>(outv), ow, x, y, make_float4(c.x, c.y, c.z, 1.0f));
+  }
+}
+
 static int launch_chain(const vkb_launch_t *l, int n_ops, const uint32_t *ops)
 {
   VKB_REQUIRE(l->num_conn >= 2 && n_ops >= 1 && n_ops <= 8);
@@ -249,6 +323,15 @@ static int launch_chain(const vkb_launch_t *l, int n_ops, const uint32_t *ops)
   }
   dim3 block(32, 8), grid(vkb_cdiv(out->wd, 64), vkb_cdiv(out->ht, 8)), grid1(vkb_cdiv(out->wd, 32), vkb_cdiv(out->ht, 8));
   const int sig = P.op[0] | (P.op[1] << 4) | (P.op[2] << 8) | (P.op[3] << 12) | (n_ops > 4 ? 1 << 20 : 0);
+  if(sig == (PW_CROP | (PW_COLOUR << 4) | (PW_FILMCURV << 8)) && P.shift && P.colour.trc == 0 && !(P.colour.clip_t > 0.0f) &&
+     P.colour.N == 0 && P.colour.sat == 1.0f && P.film.colour == 3)
+  { // the default darkroom parameters: straight-line kernel
+    const dim3 gridn(vkb_cdiv(out->wd, 32 * PW_NPX), vkb_cdiv(out->ht, 8));
+    if(P.out_f32) k_pointwise_dflt<true><<<gridn, block, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, out->data, out->wd, out->ht, P);
+    else          k_pointwise_dflt<false><<<gridn, block, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, out->data, out->wd, out->ht, P);
+    VKB_CHECK_LAUNCH();
+    return VKB_OK;
+  }
 #define PW_CASE(A, B, C, D) \
   case ((A) | ((B) << 4) | ((C) << 8) | ((D) << 12)): \
     if((A) == PW_CROP && P.crop.r[0] != 1.0f) goto generic; /* rotation / perspective: catmull-rom gather, generic kernel */ \
