@@ -27,7 +27,6 @@ static void host_escale(denoise_params_t *p)
 { // overwrite edges[0..2] in the kernel's copy of the params with the scale factors
   for(int k = 0; k < 3; k++) p->edges[k] = exp2f(12.0f * p->edges[k] + p->edges[3]);
 }
-VKB_DEV float exp2f_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 VKB_DEV void swizzle(int x, int y, int w, int h, int &ox, int &oy)
 { // downcov.comp:52-53, down.comp:103-104
   ox = x / 2 + ((x & 1) * (w + 1)) / 2;
@@ -154,7 +153,7 @@ __global__ void __launch_bounds__(256, 4) k_denoise_downcov(const uint2 *__restr
     for(int i = 0; i < 5; i++)
     {
       const float4 t = tile[ly + j][lx + i];
-      const float wgt = t.x > 2.0f * mean_b ? 0.0f : fmaxf(1e-9f, exp2f_fast((ei[i] + ej) + eb[i] * fj)); // hot pixels get no weight
+      const float wgt = t.x > 2.0f * mean_b ? 0.0f : fmaxf(1e-9f, ex2_ftz((ei[i] + ej) + eb[i] * fj)); // hot pixels get no weight
       r = __fmaf_rn(wgt, t.x, r); g = __fmaf_rn(wgt, t.y, g); b = __fmaf_rn(wgt, t.z, b);
       wt += wgt;
     }
@@ -168,7 +167,7 @@ __global__ void __launch_bounds__(256, 4) k_denoise_downcov(const uint2 *__restr
 }
 
 // x^0.8 on the SFU: ~1e-6 relative, i.e. <= 1e-4 in the [0,1] edge weight even at the 1e-3 noise floor of noise.glsl
-VKB_DEV float gamma08(float f) { return f < 0.0f ? f : __powf(f, 0.8f); }
+VKB_DEV float gamma08(float f) { return f < 0.0f ? f : pow_ftz(f, 0.8f); }
 
 // ---- down: levels 1..3, 5 tap flower with edge stopping (down.comp:59-107) ----
 __global__ void __launch_bounds__(256) k_denoise_down(const uint2 *__restrict__ in, int w, int h, uint2 *__restrict__ out,

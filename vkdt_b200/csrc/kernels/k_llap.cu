@@ -42,7 +42,7 @@ VKB_DEV float llap_curve_k(float x, float g, const llap_params_t &p, float inv2s
     const float mt = 1.0f - t;
     val = g + ssigma * 2.0f * mt * t + t2 * (ssigma + ssigma * shadhi);
   }
-  if(CLARITY) val += p.clarity * c * __expf(-c * c * invd);
+  if(CLARITY) val += p.clarity * c * exp_ftz(-c * c * invd);
   else        val += 0.0f * c;
   return val;
 }
@@ -61,7 +61,7 @@ VKB_DEV float llap_curve(float x, float g, const llap_params_t &p)
     val = g + ssigma * 2.0f * mt * t + t2 * (ssigma + ssigma * shadhi);
   }
   // the gaussian term is a few % of val at most: __expf's ~1e-6 relative error on it stays below an fp32 ulp of val
-  val += p.clarity * c * __expf(-c * c / (2.0f * p.sigma * p.sigma / 3.0f));
+  val += p.clarity * c * exp_ftz(-c * c / (2.0f * p.sigma * p.sigma / 3.0f));
   return val;
 }
 VKB_DEV float llap_grey(float4 px)

@@ -44,7 +44,7 @@ VKB_DEV float llap_curve_k(float x, float g, const llap_params_t &p, float inv2s
     const float mt = 1.0f - t;
     val = g + ssigma * 2.0f * mt * t + t2 * (ssigma + ssigma * shadhi);
   }
-  val += p.clarity * c * __expf(-c * c * invd);
+  val += p.clarity * c * exp_ftz(-c * c * invd);
   return val;
 }
 VKB_DEV float llap_curve(float x, float g, const llap_params_t &p)
@@ -62,7 +62,7 @@ VKB_DEV float llap_curve(float x, float g, const llap_params_t &p)
     val = g + ssigma * 2.0f * mt * t + t2 * (ssigma + ssigma * shadhi);
   }
   // the gaussian term is < 3% of val: __expf's 1e-6 relative error on it is below an fp32 ulp of val
-  val += p.clarity * c * __expf(-c * c / (2.0f * p.sigma * p.sigma / 3.0f));
+  val += p.clarity * c * exp_ftz(-c * c / (2.0f * p.sigma * p.sigma / 3.0f));
   return val;
 }
 
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(256, 3) k_llap_final4(const uint2 *__restrict_
     const float lap1 = f16r(llap_curve_k(grey[q], ghi, P.p, inv2s, invd)) - e1[q];
     float l = f16r(res[q] + lap0 * (1.0f - a) + lap1 * a);
     const float yo = fmaxf(lum2020(px[q].x, px[q].y, px[q].z), 1e-8f);
-    if(l < yo) l = yo * __expf(l - yo);
+    if(l < yo) l = yo * exp_ftz(l - yo);
     const float ratio = __fdividef(l, yo); // nothing downstream but one f16/f32 store: 2 ulp is plenty
     f3 c = { fmaxf(0.0f, px[q].x * ratio), fmaxf(0.0f, px[q].y * ratio), fmaxf(0.0f, px[q].z * ratio) };
     if(GRADE)

@@ -191,8 +191,6 @@ static int colour_digest(const float *f, uint32_t size, colour_digest_t *d)
 // weibull_cdf() of pointwise.cuh on the bare SFU instructions.  __powf / __expf expand to the same ex2.approx / lg2.approx
 // but wrap each in a denormal guard (compare, scale, unscale: 4 instructions instead of 1); arguments here are >= 1e-7 * il
 // and a result below 2^-126 only ever enters 1 - x, so flushing it changes nothing.
-VKB_DEV float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-VKB_DEV float lg2_ftz(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 VKB_DEV float weibull_cdf_ftz(float x, float il, float k)
 {
   const float p = ex2_ftz(k * lg2_ftz(fmaxf(x, 1e-7f) * il));   // __powf(x * il, k)

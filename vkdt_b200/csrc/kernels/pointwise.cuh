@@ -6,8 +6,8 @@
 #pragma once
 #include "common.cuh"
 
-#define PW_POW(x, y) __powf((x), (y))
-#define PW_EXP(x)    __expf((x))
+#define PW_POW(x, y) pow_ftz((x), (y))
+#define PW_EXP(x)    exp_ftz((x))
 
 // ---- parameter blocks, same byte layout as the reference's uniform blocks ----
 struct crop_committed_t { float H[12]; float r[4]; float crop[4]; };                     // crop/main.c:311-335
