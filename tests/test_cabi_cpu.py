@@ -138,3 +138,22 @@ def test_plan_rgb_sink_layout():
     assert "x3x1:f32@" in fin and "pfmpack" not in text
     with pytest.raises(api.VkbError):
         g.set_sink_layout(7)
+
+
+def test_plan_ipfm_source_and_onull_sink(tmp_path):
+    """i-pfm uploads f32 and converts once (b200:cvt16); o-null is a sink that keeps the last module's f16 image."""
+    from vkdt_b200 import synth
+    fn = str(tmp_path / "x.pfm")
+    synth.write_pfm(fn, np.random.default_rng(0).random((40, 64, 3), dtype=np.float32))
+    cfg = ("module:i-pfm:main\nmodule:filmcurv:01\nmodule:o-null:main\n"
+           "connect:i-pfm:main:output:filmcurv:01:input\nconnect:filmcurv:01:output:o-null:main:input\n"
+           "param:i-pfm:main:filename:%s\n" % fn)
+    g = api.Graph(cfg_text=cfg, sink=None)
+    text = g.plan()
+    assert "b200_cvt16" in text and "filmcurv_main" in text and "sink o-null 64x40" in text
+    assert "64x40x4x1:f32@" in text and "pfmpack" not in text
+    mono = str(tmp_path / "y.pfm")
+    synth.write_pfm(mono, np.zeros((8, 12), np.float32))
+    g = api.Graph(cfg_text=cfg.replace(fn, mono), sink=None)
+    # single channel ("Pf") files upload one float per pixel (the chain's kernels then refuse the 1-channel image at launch)
+    assert "12x8x1x1:f32@" in g.plan()

@@ -336,3 +336,50 @@ def test_empty_source_is_an_error(gpu):
     g.set_source(raw.ctypes.data, gpu.raw_params(0, 0))
     with pytest.raises(gpu.VkbError):
         g.run()
+
+
+TAIL_CFG = """module:i-pfm:main
+module:filmcurv:01
+module:llap:01
+module:grade:01
+module:display:main
+connect:i-pfm:main:output:filmcurv:01:input
+connect:filmcurv:01:output:llap:01:input
+connect:llap:01:output:grade:01:input
+connect:grade:01:output:display:main:input
+param:llap:01:sigma:0.12
+param:llap:01:shadows:1
+param:llap:01:hilights:1
+param:llap:01:clarity:0.2
+"""
+
+
+def test_ipfm_stage_isolation(gpu, oracle, tmp_path):
+    """feed an intermediate image (the oracle's colour output, written as a pfm like o-pfm would) through
+    i-pfm into the tail of the graph (filmcurv -> llap -> grade) and compare with the oracle's end result."""
+    w, h = 512, 384
+    raw = synth.mosaic(w, h, seed=19)
+    d = _oracle_cfg(oracle, w, h)
+    want = oracle.darkroom_run(d, raw)
+    mid = oracle.darkroom_run(d, raw, stage=5)          # colour output, an f16 image in the reference
+    fn = str(tmp_path / "colour.pfm")
+    synth.write_pfm(fn, mid)
+    g = gpu.Graph(cfg_text=TAIL_CFG)
+    assert g.line("param:i-pfm:main:filename:%s" % fn) == 0
+    g.set_sink_buffer(None, 0)
+    g.run()
+    ow, oh = g.sink_size()
+    assert (oh, ow) == want.shape[:2]
+    got = np.zeros((oh, ow, 4), dtype=np.float32)
+    g.set_sink_buffer(got.ctypes.data, got.nbytes)
+    g.run(gpu.RUN_RECORD | gpu.RUN_UPLOAD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT | gpu.RUN_PERF)
+    assert "cvt16" in g.perf()
+    err = np.abs(got[..., :3] - want[..., :3])
+    p = psnr(got[..., :3], want[..., :3])
+    print("tail of the graph from a pfm: max abs %.3g psnr %.1f" % (err.max(), p))
+    assert p >= 60.0 and err.max() <= 2e-3 and (err > 1e-3).mean() <= 1e-5
+    # a missing file leaves the graph without a source
+    g2 = gpu.Graph(cfg_text=TAIL_CFG)
+    g2.line("param:i-pfm:main:filename:%s" % str(tmp_path / "nope.pfm"))
+    with pytest.raises(gpu.VkbError):
+        g2.run()

@@ -24,3 +24,25 @@ static int launch_pfmpack(const vkb_launch_t *l)
   return VKB_OK;
 }
 VKB_REGISTER("b200", "pfmpack", launch_pfmpack);
+
+// (b200, cvt16): f32 -> f16 element by element, behind an f32 source (i-pfm) whose consumers read f16 edges
+__global__ void __launch_bounds__(256) k_cvt16(const float2 *__restrict__ in, __half2 *__restrict__ out, size_t n2, const float *__restrict__ in1, __half *__restrict__ out1, size_t n)
+{
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if(i < n2) { const float2 v = __ldg(in + i); out[i] = __floats2half2_rn(v.x, v.y); }
+  if(i == 0 && (n & 1)) out1[n - 1] = __float2half_rn(in1[n - 1]);
+}
+
+// conn: [0] f32 image, [1] f16 image of the same shape
+static int launch_cvt16(const vkb_launch_t *l)
+{
+  VKB_REQUIRE(l->num_conn >= 2);
+  const vkb_image_t *in = l->conn, *out = l->conn + 1;
+  VKB_REQUIRE(in->format == VKB_TOKEN_F32 && out->format == VKB_TOKEN_F16 && in->wd == out->wd && in->ht == out->ht && in->chan == out->chan);
+  const size_t n = (size_t)in->wd * in->ht * in->chan;
+  if(!n) return VKB_OK;
+  k_cvt16<<<(unsigned)((n / 2 + 256) / 256), 256, 0, l->stream>>>((const float2 *)in->data, (__half2 *)out->data, n / 2, (const float *)in->data, (__half *)out->data, n);
+  VKB_CHECK_LAUNCH();
+  return VKB_OK;
+}
+VKB_REGISTER("b200", "cvt16", launch_cvt16);

@@ -349,6 +349,22 @@ static int build_plan(dt_graph_t *g, bool with_device)
           B.add_launch(l);
         }
       }
+      else if(nd->connector[0].format == dt_token("f32") || (nd->module->num_connectors > 0 && nd->module->connector[0].format == dt_token("f32")))
+      { // f32 sources (i-pfm): the kernels of this path read f16 edges.  upload as is, convert once on the device and let
+        // every consumer see the f16 image (lossless for images that were f16 before they became a pfm file)
+        const uint32_t chan = (uint32_t)dt_connector_channels(nd->connector);
+        s.bytes = (size_t)wd * ht * chan * 4;
+        plan_buf_t ub; ub.bytes = s.bytes + 256;
+        p->buf.push_back(ub);
+        s.buf_upload = (int)p->buf.size() - 1;
+        g->node[n].connector[0].format = dt_token("f16");
+        plan_launch_t l;
+        l.name = dt_token("b200"); l.kernel = dt_token("cvt16"); l.wd = wd; l.ht = ht; l.dp = 1;
+        l.conn.push_back(plan_img_t{ s.buf_upload, wd, ht, chan, 1, dt_token("f32") });
+        l.conn.push_back(B.img_out(n, 0));
+        l.label = dt_token_string(nd->module->name) + " b200_cvt16 (f32 -> f16)";
+        B.add_launch(l);
+      }
       else { s.buf_upload = out; s.bytes = conn_bytes(nd->connector); }
       p->buf[s.buf_upload].first = -1; // written by the upload, before launch 0
       if(s.external) p->buf[s.buf_upload].external = (void *)ms->data;

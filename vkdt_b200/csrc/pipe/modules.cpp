@@ -19,6 +19,7 @@ struct module_def_t { const char *name; const char *connectors; const char *para
 static const module_def_t g_defs[] = {
   { "i-raw",    "output:source:*:ui16", "filename:string:256:test.cr2\nnoise a:float:1:0.0\nnoise b:float:1:0.0\nstartid:int:1:0" },
   { "i-mlv",    "output:source:rggb:ui16", "filename:string:256:test.mlv" },
+  { "i-pfm",    "output:source:rgba:f32", "filename:string:256:test.pfm\nstartid:int:1:0\nnoise a:float:1:0.0\nnoise b:float:1:0.0" },
   { "denoise",  "input:read:*:*\noutput:write:&input:*",
                 "strength:float:1:0.0\nluma:float:1:0.6\ndetail:float:1:1.0\npad:float:1:0\nedges:float:4:0:0:0:0\ngainmap:int:1:1" },
   { "hilite",   "input:read:*:*\noutput:write:&input:*", "white:float:1:0.985\ndesat:float:1:0.3\nsoft:float:1:0.6" },
@@ -118,6 +119,10 @@ static int  iraw_init(dt_module_t *);
 static void iraw_cleanup(dt_module_t *);
 static void iraw_roi_out(dt_graph_t *, dt_module_t *);
 static int  iraw_read_source(dt_module_t *, void *, dt_read_source_params_t *);
+static int  ipfm_init(dt_module_t *);
+static void ipfm_cleanup(dt_module_t *);
+static void ipfm_roi_out(dt_graph_t *, dt_module_t *);
+static int  ipfm_read_source(dt_module_t *, void *, dt_read_source_params_t *);
 static int  imlv_init(dt_module_t *);
 static void imlv_cleanup(dt_module_t *);
 static void imlv_roi_out(dt_graph_t *, dt_module_t *);
@@ -153,6 +158,7 @@ static std::vector<dt_module_so_t> &registry()
     parse_def(d, &so);
     const std::string n = d.name;
     if(n == "i-raw")    { so.init = iraw_init; so.cleanup = iraw_cleanup; so.modify_roi_out = iraw_roi_out; so.read_source = iraw_read_source; }
+    if(n == "i-pfm")    { so.init = ipfm_init; so.cleanup = ipfm_cleanup; so.modify_roi_out = ipfm_roi_out; so.read_source = ipfm_read_source; }
     if(n == "i-mlv")    { so.init = imlv_init; so.cleanup = imlv_cleanup; so.modify_roi_out = imlv_roi_out; so.read_source = imlv_read_source; }
     if(n == "denoise")  { so.modify_roi_in = denoise_roi_in; so.modify_roi_out = denoise_roi_out; so.create_nodes = denoise_create_nodes; }
     if(n == "hilite")   { so.create_nodes = hilite_create_nodes; }
@@ -278,6 +284,81 @@ static int iraw_read_source(dt_module_t *mod, void *mapped, dt_read_source_param
   const uint16_t *src = (const uint16_t *)g->mem_source[mid].data;
   if(wd == rp->width) memcpy(mapped, src, sizeof(uint16_t) * (size_t)wd * ht);
   else for(uint32_t j = 0; j < ht; j++) memcpy((uint16_t *)mapped + (size_t)j * wd, src + (size_t)j * rp->width, sizeof(uint16_t) * wd);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// i-pfm (i-pfm/main.c:38-166): rgb ("PF") or single channel ("Pf") float images, e.g. an intermediate image another
+// vkdt wrote with o-pfm: lets every stage of the path be run and compared in isolation.
+// the executor converts the uploaded f32 image to the f16 edge format the kernels read (b200:cvt16).
+struct ipfm_t { std::string filename; FILE *f = 0; uint32_t width = 0, height = 0; int channels = 3; long data_begin = 0; };
+static int ipfm_init(dt_module_t *mod) { mod->data = new ipfm_t(); return 0; }
+static void ipfm_cleanup(dt_module_t *mod)
+{
+  ipfm_t *p = (ipfm_t *)mod->data;
+  if(p) { if(p->f) fclose(p->f); delete p; }
+  mod->data = 0;
+}
+static int ipfm_read_header(dt_module_t *mod)
+{ // i-pfm/main.c:38-101
+  ipfm_t *p = (ipfm_t *)mod->data;
+  const char *fname = dt_module_param_string(mod, 0);
+  if(p->f && p->filename == fname) return 0;
+  if(p->f) fclose(p->f);
+  p->filename.clear();
+  p->f = fopen(resource_path(mod, fname).c_str(), "rb");
+  if(!p->f) { fprintf(stderr, "[i-pfm] could not load file `%s'!\n", fname); return 1; }
+  int wd = 0, ht = 0;
+  p->channels = 3;
+  if(fscanf(p->f, "PF\n%d %d\n%*[^\n]", &wd, &ht) != 2)
+  {
+    rewind(p->f);
+    if(fscanf(p->f, "Pf\n%d %d\n%*[^\n]", &wd, &ht) != 2 || wd <= 0 || ht <= 0) { fclose(p->f); p->f = 0; fprintf(stderr, "[i-pfm] `%s' is not a pfm file\n", fname); return 1; }
+    p->channels = 1;
+  }
+  if(wd <= 0 || ht <= 0 || fgetc(p->f) == EOF) { fclose(p->f); p->f = 0; return 1; }
+  p->width = wd; p->height = ht;
+  p->data_begin = ftell(p->f);
+  p->filename = fname;
+  return 0;
+}
+static void ipfm_roi_out(dt_graph_t *g, dt_module_t *mod)
+{
+  dt_image_params_t *ip = &mod->img_param;
+  if(ipfm_read_header(mod))
+  { // i-pfm/main.c:147-152: a 32x32 placeholder keeps the graph alive in the gui; a cli run has nothing to show for it
+    mod->connector[0].roi.full_wd = 0; mod->connector[0].roi.full_ht = 0;
+    return;
+  }
+  const ipfm_t *p = (const ipfm_t *)mod->data;
+  memset(ip, 0, sizeof(*ip));
+  for(int k = 0; k < 4; k++) { ip->black[k] = 0.0f; ip->white[k] = 65535.0f; ip->whitebalance[k] = 1.0f; }
+  ip->crop_aabb[2] = p->width; ip->crop_aabb[3] = p->height;
+  ip->noise_a = dt_module_param_float(mod, 2)[0];
+  ip->noise_b = dt_module_param_float(mod, 3)[0];
+  ip->filters = 0;
+  ip->colour_primaries = 2; // s_colour_primaries_2020
+  ip->colour_trc = 0;       // linear
+  ip->cam_to_rec2020[0] = ip->cam_to_rec2020[4] = ip->cam_to_rec2020[8] = 1.0f;
+  mod->connector[0].chan = p->channels == 1 ? dt_token("y") : dt_token("rgba");
+  mod->connector[0].roi.full_wd = p->width;
+  mod->connector[0].roi.full_ht = p->height;
+}
+static int ipfm_read_source(dt_module_t *mod, void *mapped, dt_read_source_params_t *)
+{ // i-pfm/main.c:103-118 (read_plain): rgb -> rgba with alpha 1, rows in file order
+  if(ipfm_read_header(mod)) return 1;
+  ipfm_t *p = (ipfm_t *)mod->data;
+  fseek(p->f, p->data_begin, SEEK_SET);
+  float *out = (float *)mapped;
+  const size_t n = (size_t)p->width * p->height;
+  if(p->channels == 1) return fread(out, sizeof(float), n, p->f) == n ? 0 : 1;
+  std::vector<float> row((size_t)p->width * 3);
+  for(uint32_t j = 0; j < p->height; j++)
+  {
+    if(fread(row.data(), sizeof(float), row.size(), p->f) != row.size()) return 1;
+    float *o = out + (size_t)4 * j * p->width;
+    for(uint32_t i = 0; i < p->width; i++) { o[4*i] = row[3*i]; o[4*i+1] = row[3*i+1]; o[4*i+2] = row[3*i+2]; o[4*i+3] = 1.0f; }
+  }
   return 0;
 }
 

@@ -214,3 +214,17 @@ def write_dng(filename, raw, cfa=((0, 1), (1, 2)), black=2048, white=15000, neut
     pix = raw.astype(">u2" if big_endian else "<u2").tobytes()
     with open(filename, "wb") as f:
         f.write(hdr + struct.pack(e + "H", n) + body + long_(0) + extra + pix)
+
+
+def write_pfm(filename, img):
+    """(H,W,3|4) or (H,W) float32 -> PFM as o-pfm writes it (o-pfm/main.c:27-40: header padded with '0' so that the data
+    starts 16-byte aligned, rows top to bottom, scale -1.0 = little endian)."""
+    img = np.asarray(img, dtype=np.float32)
+    h, w = img.shape[:2]
+    hdr = ("PF\n%d %d\n-1.0" if img.ndim == 3 else "Pf\n%d %d\n-1.0") % (w, h)
+    pad = 0
+    while (len(hdr) + 1 + pad) & 0xf:
+        pad += 1
+    with open(filename, "wb") as f:
+        f.write((hdr + "0" * pad + "\n").encode())
+        f.write(np.ascontiguousarray(img[..., :3] if img.ndim == 3 else img).astype("<f4").tobytes())
