@@ -73,7 +73,7 @@ with open(out + tag + "_summary.md", "w") as f:
     cnt = collections.Counter(names[step:step + period])
     for n, v in sorted(ncu_share.items(), key=lambda kv: -kv[1]):
         lab = LABEL.get(n, n)
-        e = [x["ms"] for k, x in ev.items() if lab in k]
+        e = [x["ms"] for k, x in ev.items() if lab in k.split()]
         f.write("| %s | %d | %.1f | %.3f | %s |\n" % (n, cnt[n], v, v / ncu_total, ("%.3f" % e[0]) if e else "-"))
     f.write("\nncu total of the step %.3f ms (sum of serialised launches); bench ms_per_step %.3f; dominant kernel share per bench %.3f.\n" % (
         ncu_total / 1e3, bench["ms_per_step"], bench["roofline"]["share_of_step"]))
