@@ -17,7 +17,10 @@
 #define FT_H 8
 
 struct llap_params_t { float sigma, shadows, hilights, clarity; };
-struct llapfin_t { llap_params_t p; int first; int have_grade; int out_f32; grade_params_t grade; };
+// everything below `grade` is a function of the launch's parameters only and is evaluated once on the host with the same
+// fp32 operations the kernel used to repeat per pixel (1/(2 sigma), 1/(2 sigma^2/3); grade: lift, 1 - lift, gain, offset, 1/gamma)
+struct llapfin_t { llap_params_t p; int first; int have_grade; int out_f32; grade_params_t grade;
+                   float inv2s, invd; float g_lift[3], g_oml[3], g_gain[3], g_off[3], g_ig[3]; };
 
 VKB_DEV float gamma_from_i(int i) { return (float)i / (NUM_GAMMA - 1.0f); }
 // llap.glsl:17-22 gamma_hi_from_v without the loop of divisions: 1 + #{ i in 1..8 : i/9 <= v } (the i/9 are compile time constants)
@@ -169,14 +172,33 @@ VKB_DEV float expand1(const float (*T)[F3_W + 1], int lx, int ly, int q)
   return acc / 9.0f;
 }
 
+// grade/main.comp:21-40 (mode 0) on the host-evaluated constants of llapfin_t: same operations, same order as grade_px()
+VKB_DEV f3 grade_px_digest(f3 c, const llapfin_t &P)
+{
+  if(P.grade.mode != 0) return grade_px(c, P.grade);
+  float v[3] = { c.x, c.y, c.z };
+#pragma unroll
+  for(int k = 0; k < 3; k++)
+  {
+    float t = P.g_gain[k] * v[k];
+    t = t * P.g_oml[k] + P.g_lift[k];
+    t = fmaxf(t, 0.0f);
+    t = (P.g_ig[k] == 1.0f) ? t : PW_POW(t, P.g_ig[k]);
+    v[k] = t + P.g_off[k];
+  }
+  return { v[0], v[1], v[2] };
+}
+
 template <bool F32, bool GRADE>
 __global__ void __launch_bounds__(256, 3) k_llap_final4(const uint2 *__restrict__ in, const __half *__restrict__ coarse,
     const __half *__restrict__ l1, int cw, int ch, void *__restrict__ outv, int ow, int oh, const __grid_constant__ llapfin_t P)
 {
   __shared__ float tile[NL + 1][F3_H][F3_W + 1];
   __shared__ int s_pmin, s_pmax;
+  __shared__ float s_gamma[NUM_GAMMA]; // i / 9: the bracket values by index, instead of a division per pixel and bracket
   const int tid = threadIdx.y * 32 + threadIdx.x;
   if(tid == 0) { s_pmin = NUM_GAMMA; s_pmax = 0; }
+  if(tid < NUM_GAMMA) s_gamma[tid] = gamma_from_i(tid);
   const int kx = blockIdx.x * 32 + threadIdx.x, ky = blockIdx.y * 8 + threadIdx.y;
   const int cx0 = blockIdx.x * 32 - 2, cy0 = blockIdx.y * 8 - 2;
   const size_t p1 = (size_t)cw * ch;
@@ -220,7 +242,7 @@ __global__ void __launch_bounds__(256, 3) k_llap_final4(const uint2 *__restrict_
   }
   __syncthreads();
   if(hi[0] < 0) return; // whole 2x2 outside the image
-  const float inv2s = 1.0f / (2.0f * P.p.sigma), invd = 1.0f / (2.0f * P.p.sigma * P.p.sigma / 3.0f);
+  const float inv2s = P.inv2s, invd = P.invd;
   const int lx = kx - cx0, ly = ky - cy0;
   float res[4], e0[4], e1[4];
   float oc[6]; // packed rgb sink: the thread's two pixels of a row, stored by the warp together
@@ -247,7 +269,7 @@ __global__ void __launch_bounds__(256, 3) k_llap_final4(const uint2 *__restrict_
     if(hi[q] >= 0)
     {
     const int x = 2 * kx + (q & 1), y = 2 * ky + (q >> 1);
-    const float glo = gamma_from_i(hi[q] - 1), ghi = gamma_from_i(hi[q]);
+    const float glo = s_gamma[hi[q] - 1], ghi = s_gamma[hi[q]];
     const float a = clampf(__fdividef(v[q] - glo, ghi - glo), 0.0f, 1.0f);
     const float lap0 = f16r(llap_curve_k(grey[q], glo, P.p, inv2s, invd)) - e0[q];
     const float lap1 = f16r(llap_curve_k(grey[q], ghi, P.p, inv2s, invd)) - e1[q];
@@ -259,7 +281,7 @@ __global__ void __launch_bounds__(256, 3) k_llap_final4(const uint2 *__restrict_
     if(GRADE)
     {
       c = { f16r(c.x), f16r(c.y), f16r(c.z) };
-      c = grade_px(c, P.grade);
+      c = grade_px_digest(c, P);
     }
     if(F32 && P.out_f32 == 2) { oc[3 * (q & 1)] = c.x; oc[3 * (q & 1) + 1] = c.y; oc[3 * (q & 1) + 2] = c.z; }
     else if(F32) st_sink_f32(outv, ow, x, y, c.x, c.y, c.z, P.out_f32);
@@ -290,10 +312,20 @@ static int launch_llapfin2(const vkb_launch_t *l)
   memset(&P, 0, sizeof(P));
   memcpy(&P.p, l->params, sizeof(llap_params_t));
   P.first = pc[0]; P.have_grade = pc[1]; P.out_f32 = out->format == VKB_TOKEN_F32 ? (out->chan == 3 ? 2 : 1) : 0;
+  P.inv2s = 1.0f / (2.0f * P.p.sigma); P.invd = 1.0f / (2.0f * P.p.sigma * P.p.sigma / 3.0f);
   if(P.have_grade)
   {
     VKB_REQUIRE(l->params_size >= sizeof(llap_params_t) + sizeof(grade_params_t));
     memcpy(&P.grade, (const uint8_t *)l->params + sizeof(llap_params_t), sizeof(grade_params_t));
+    const grade_params_t &q = P.grade;
+    for(int k = 0; k < 3; k++)
+    { // grade_px(): lift, gam, gain, off and the two expressions that only depend on them
+      const volatile float lift = q.lift[k] + q.lift[3], gam = fmaxf(q.gamma[k] + q.gamma[3], 1e-6f);
+      P.g_lift[k] = lift; P.g_oml[k] = 1.0f - lift;
+      P.g_gain[k] = fmaxf(q.gain[k] + q.gain[3], 0.0f);
+      P.g_off[k]  = q.off[k] + q.off[3];
+      P.g_ig[k]   = 1.0f / gam;
+    }
   }
   const dim3 grid(vkb_cdiv(out->wd, 64), vkb_cdiv(out->ht, 16)), block(32, 8);
 #define GO(F, G) k_llap_final4<F, G><<<grid, block, 0, l->stream>>>((const uint2 *)in->data, (const __half *)coarse->data, \
