@@ -224,10 +224,18 @@ __global__ void __launch_bounds__(256) k_denoise_down_tiled(const uint2 *__restr
 {
   __shared__ uint2 tile[DD_H][DD_W];
   const int tx0 = blockIdx.x * 32 - 2, ty0 = blockIdx.y * 8 - 2;
-  for(int t = threadIdx.y * 32 + threadIdx.x; t < DD_W * DD_H; t += 256)
+  // thread (tx, ty) stages rows ty, ty + 8 and columns tx, tx + 32 of the window: no division, one mirror per row / column
   {
-    const int r = t / DD_W, c = t - r * DD_W;
-    tile[r][c] = __ldg(in + (size_t)mirror1(ty0 + r, h) * w + mirror1(tx0 + c, w));
+    const int c0 = threadIdx.x, c1 = threadIdx.x + 32, r0 = threadIdx.y, r1 = threadIdx.y + 8;
+    const int gx0 = mirror1(tx0 + c0, w), gx1 = c1 < DD_W ? mirror1(tx0 + c1, w) : 0;
+    const size_t gy0 = (size_t)mirror1(ty0 + r0, h) * w, gy1 = r1 < DD_H ? (size_t)mirror1(ty0 + r1, h) * w : 0;
+    tile[r0][c0] = __ldg(in + gy0 + gx0);
+    if(c1 < DD_W) tile[r0][c1] = __ldg(in + gy0 + gx1);
+    if(r1 < DD_H)
+    {
+      tile[r1][c0] = __ldg(in + gy1 + gx0);
+      if(c1 < DD_W) tile[r1][c1] = __ldg(in + gy1 + gx1);
+    }
   }
   __syncthreads();
   const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
