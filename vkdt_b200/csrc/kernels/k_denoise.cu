@@ -278,7 +278,8 @@ __global__ void __launch_bounds__(256) k_denoise_down_tiled(const uint2 *__restr
   st_rgba(out, w, ox, oy, make_float4(sum[0] / wgt[0], sum[1] / wgt[1], sum[2] / wgt[2], 1.0f));
 }
 
-struct asm_consts_t { float rgb_to_yuv[9], yuv_to_rgb[9]; float wb[3], black[3], white[3]; float noise_a, noise_b, blk, thrs0, i2thrs0; float inorm[3], denorm[3]; };
+struct asm_consts_t { float rgb_to_yuv[9], yuv_to_rgb[9]; float wb[3], black[3], white[3]; float noise_a, noise_b, blk, thrs0, i2thrs0; float inorm[3], denorm[3];
+                      float bb[4], ibb[4]; }; // 0.7^(l+1) / blk and its reciprocal: launch constants, evaluated on the host
 
 // ---- assemble: wavelet shrinkage over the 4 detail bands (assemble.comp:43-165) ----
 __global__ void __launch_bounds__(256) k_denoise_assemble(const uint2 *__restrict__ s0, const uint2 *__restrict__ s1, const uint2 *__restrict__ s2,
@@ -302,13 +303,14 @@ __global__ void __launch_bounds__(256) k_denoise_assemble(const uint2 *__restric
   }
   float sigma[3];
   noise_sigma(K.noise_a, K.noise_b, K.black[1], K.white[1], p.edges, fmaxf(d[2][0], 0.0f), sigma);
-  const float bb[4] = { 0.7000f / K.blk, 0.4900f / K.blk, 0.3430f / K.blk, 0.2401f / K.blk };
+  const float bb[4] = { K.bb[0], K.bb[1], K.bb[2], K.bb[3] };
+  const float isig[3] = { __frcp_rn(sigma[0]), __frcp_rn(sigma[1]), __frcp_rn(sigma[2]) };
   float down4[3] = { d[4][0], d[4][1], d[4][2] }, len[4];
 #pragma unroll
   for(int l = 0; l < 4; l++)
   {
 #pragma unroll
-    for(int k = 0; k < 3; k++) d[l][k] = (d[l][k] - d[l + 1][k]) * __frcp_rn(sigma[k] * bb[l]);
+    for(int k = 0; k < 3; k++) d[l][k] = (d[l][k] - d[l + 1][k]) * (isig[k] * K.ibb[l]); // 1/(sigma bb) as a product of reciprocals: 3 instead of 12
     len[l] = sqrtf(d[l][0] * d[l][0] + d[l][1] * d[l][1] + d[l][2] * d[l][2]);
   }
   const float slope = ((len[3] - len[0]) / 3.0f + (len[2] - len[1]) / 1.0f + (len[1] - len[0]) / 1.0f
@@ -520,6 +522,7 @@ static int launch_assemble(const vkb_launch_t *l)
   K.noise_a = pc->noise_a; K.noise_b = pc->noise_b;
   K.blk = pc->filters == 0u ? 1.0f : (pc->filters == 9u ? 2.23607f : 1.414213f);
   K.thrs0 = powf(p.strength, 4.0f);
+  { const float pw[4] = { 0.7000f, 0.4900f, 0.3430f, 0.2401f }; for(int l = 0; l < 4; l++) { K.bb[l] = pw[l] / K.blk; K.ibb[l] = 1.0f / K.bb[l]; } }
   K.i2thrs0 = 1.0f / (2.0f * K.thrs0);
   for(int k = 0; k < 3; k++)
   { // per-launch constants: wb/(white-black) and its inverse, computed in double

@@ -120,13 +120,23 @@ __global__ void __launch_bounds__(256) k_hilite_assemble(const uint2 *__restrict
   const float w[5] = {1.0f / 16.0f, 4.0f / 16.0f, 6.0f / 16.0f, 4.0f / 16.0f, 1.0f / 16.0f};
   const int ix = x / 2, iy = y / 2, dx = x & 1, dy = y & 1;
   float ur = 0.0f, ug = 0.0f, ub = 0.0f, wgt = 0.0f;
-  for(int ii = dx ? 0 : -1; ii <= 1; ii++) for(int jj = dy ? 0 : -1; jj <= 1; jj++)
+  // same taps in the same order (ii outer, jj inner), unrolled over the full -1..1 range with the odd pixels' missing
+  // first tap predicated off: the weights become selects between constants instead of indexed loads from a local array
+#pragma unroll
+  for(int ii = -1; ii <= 1; ii++)
   {
-    const float4 rgb = ld_rgba_mirror(coarse, cw, ch, ix + ii, iy + jj);
-    const float wy = dy ? w[2 * jj + 1] : w[2 * jj + 2];
-    const float wx = dx ? w[2 * ii + 1] : w[2 * ii + 2];
-    ur += rgb.x * wy * wx; ug += rgb.y * wy * wx; ub += rgb.z * wy * wx;
-    wgt += wy * wx;
+    if(ii < 0 && dx) continue;
+    const float wx = ii < 0 ? w[0] : (ii == 0 ? (dx ? w[1] : w[2]) : (dx ? w[3] : w[4]));
+    const int cx = mirror1(ix + ii, cw);
+#pragma unroll
+    for(int jj = -1; jj <= 1; jj++)
+    {
+      if(jj < 0 && dy) continue;
+      const float wy = jj < 0 ? w[0] : (jj == 0 ? (dy ? w[1] : w[2]) : (dy ? w[3] : w[4]));
+      const float4 rgb = ld_rgba(coarse, cw, cx, mirror1(iy + jj, ch));
+      ur += rgb.x * wy * wx; ug += rgb.y * wy * wx; ub += rgb.z * wy * wx;
+      wgt += wy * wx;
+    }
   }
   if(wgt == 0.0f) { ur = 0.0f; ug = 1.0f; ub = 1.0f; }
   else { ur /= wgt; ug /= wgt; ub /= wgt; }
