@@ -226,7 +226,7 @@ def run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, s
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    e2e_steps = max(4, min(steps, 12 if out_bytes > 400e6 else 60))
+    e2e_steps = max(4, min(steps, 12 if out_bytes > 400e6 else 200))
     f0, f1 = api.Event(), api.Event()
     t0 = time.time()
     f0.record(gs[0].stream())
@@ -325,7 +325,7 @@ def main():
     M = None
     if args.workload != "mlv4k" and not args.no_mlv:
         M = run_workload(api, synth, torch, dist, args, rank, world, local_rank, mlv_W, mlv_H, mlv_src, mlv_bpp, strength,
-                         max(8, min(2 * args.steps, 40)), 3, sample_clocks=False)
+                         max(40, min(10 * args.steps, 200)), 3, sample_clocks=False)
     t_kernel_ms, t_e2e_ms, e2e_steps, launches, per_kernel, clocks = R["t_kernel_ms"], R["t_e2e_ms"], R["e2e_steps"], R["launches"], R["per_kernel"], R["clocks"]
     in_bytes, out_bytes, ow, oh, checksum, nstills = R["in_bytes"], R["out_bytes"], R["ow"], R["oh"], R["checksum"], R["nstills"]
     if rank != 0:
