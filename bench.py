@@ -366,7 +366,7 @@ def main():
         "clocks": clocks, "roofline": roof, "pool_bytes": R["pool_bytes"],
     }
     if M:
-        msteps = max(8, min(2 * args.steps, 40))
+        msteps = max(40, min(10 * args.steps, 200))
         line["mlv4k"] = {"workload": "MLV 4096x2160 14-bit packed frames, default darkroom graph, frame f -> rank f mod N",
                          "frames_per_s": round(world * msteps / (M["t_kernel_ms"] * 1e-3), 1), "ms_per_frame": round(M["t_kernel_ms"] / msteps, 3),
                          "e2e_frames_per_s": round(world * M["e2e_steps"] / (M["t_e2e_ms"] * 1e-3), 1),
