@@ -1,7 +1,7 @@
 """ad-hoc: feed the oracle's stage k output to the CUDA stage k+1 and report where they part."""
 import sys, ctypes as C
 import numpy as np
-sys.path.insert(0, "."); sys.path.insert(0, "tests")
+sys.path.insert(0, "."); sys.path.insert(0, "tests")  # run from the repo root: python tests/tools/debug_stages.py W H
 from vkdt_b200 import api, synth
 from oracle import oracle_py as O
 import plans
