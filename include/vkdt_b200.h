@@ -134,6 +134,10 @@ VKB_API int  vkb_graph_set_source(vkb_graph_t *g, const char *inst, const void *
  * reference's loader hands to the graph (i-raw/rawloader-c/lib.rs:137-279, i-raw/main.c:138-256) and the cfa offset of
  * the emitted window.  no GPU needed. */
 VKB_API int  vkb_dng_info(const char *filename, vkb_raw_params_t *p, uint32_t *cfa_off_x, uint32_t *cfa_off_y);
+/* the lossless jpeg (LJ92) decoder behind lossless MLV clips, replaces lj92_open + lj92_decode of the reference's vendored
+ * liblj92 (i-mlv/video_mlv.c:236-250): headers into width/height/bits/components, and, when `out` is not NULL,
+ * width*height*components samples in scan order into out[0..count).  host only, bit exact. */
+VKB_API int  vkb_lj92_decode(const uint8_t *data, size_t size, uint16_t *out, size_t count, int *width, int *height, int *bits, int *components);
 /* redirect a sink (o-pfm:main ...) into caller memory instead of a file: rgba f32, wd*ht*16 bytes */
 VKB_API int  vkb_graph_set_sink_buffer(vkb_graph_t *g, const char *inst, void *dst, size_t bytes);
 /* layout of a sink's pixels, on the device and in the caller's buffer.  VKB_SINK_RGBA_F32 (default for memory sinks) is

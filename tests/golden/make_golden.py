@@ -36,6 +36,65 @@ def mlv_goldens():
         print("mlv golden", bpp, out.shape, len(payload))
 
 
+def lj92_goldens():
+    """lossless jpeg: (1) a stream written by the REFERENCE's own encoder (liblj92 lj92_encode) and decoded by its decoder,
+    (2) streams of our test encoder (all predictors, 1 and 2 components) decoded by the reference's decoder, (3) a lossless
+    MLV clip read through the reference's mlv_get_frame.  pins vkb_lj92_decode / the i-mlv lossless path bit exactly."""
+    import ctypes as C
+    R = O.ref_lib()
+    assert R is not None, "oracle/_ref/libmlvref.so missing: run `make -C oracle ref` where /root/reference exists"
+    R.lj92_open.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 4
+    R.lj92_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    R.lj92_close.argtypes = [C.c_void_p]
+    R.lj92_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+
+    def ref_decode(stream):
+        buf = (C.c_uint8 * len(stream)).from_buffer_copy(stream)
+        hdl = C.c_void_p()
+        w, h, b, c = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        assert R.lj92_open(C.byref(hdl), buf, len(stream), C.byref(w), C.byref(h), C.byref(b), C.byref(c)) == 0
+        out = np.zeros((h.value, w.value * c.value), dtype=np.uint16)
+        assert R.lj92_decode(hdl, out.ctypes.data_as(C.c_void_p), out.size, 0, None, 0) == 0
+        R.lj92_close(hdl)
+        return out, b.value, c.value
+
+    rng = np.random.default_rng(0x1A92)
+    streams, expected, notes = [], [], []
+    # (1) reference encoder
+    w, h, bits = 96, 40, 14
+    img = (synth.mosaic(w, h, seed=5) & 0x3fff).astype(np.uint16)
+    enc, n = C.c_void_p(), C.c_int()
+    assert R.lj92_encode(img.ctypes.data_as(C.c_void_p), w, h, bits, w, 0, None, 0, C.byref(enc), C.byref(n)) == 0
+    s = C.string_at(enc, n.value)
+    out, b, c = ref_decode(s)
+    assert (out == img).all() and b == bits
+    streams.append(np.frombuffer(s, np.uint8)); expected.append(out); notes.append("reference encoder, %d bit" % bits)
+    # (2) our test encoder, decoded by the reference.  multi-component streams only with predictor 1 (what Canon's encoder
+    # writes): for predictors 2..7 the vendored liblj92's row loops assume one component and deviate from T.81
+    for bits, comps, pred, lengths in [(14, 1, 1, None), (14, 2, 1, None), (12, 1, 4, None), (14, 2, 1, [2, 3, 3, 3, 4, 4, 4, 5, 5, 6, 6, 7, 8, 9, 10, 11, 12]),
+                                       (14, 1, 6, [2, 3, 3, 3, 4, 4, 4, 5, 5, 6, 6, 7, 8, 9, 10, 11, 12]),
+                                       (14, 1, 7, None), (10, 1, 5, None), (14, 1, 2, None), (14, 1, 3, None)]:
+        img = rng.integers(0, 1 << bits, (20, 36)).astype(np.uint16)
+        img[2:9, 4:30] = (np.arange(26)[None, :] * 5 + 300) & ((1 << bits) - 1)
+        s = synth.lj92_encode(img, bits, comps, pred, lengths)
+        out, b, c = ref_decode(s)
+        assert (out == img).all() and b == bits and c == comps, (bits, comps, pred)
+        streams.append(np.frombuffer(s, np.uint8)); expected.append(out); notes.append("test encoder bits %d comps %d predictor %d" % (bits, comps, pred))
+    # (3) lossless clip through the reference's mlv reader
+    yy, xx = np.mgrid[0:34, 0:64]
+    pix = (2048 + 37 * xx + 11 * yy + rng.integers(0, 16, (34, 64))).astype(np.uint16)   # smooth: compresses below the packed size
+    with tempfile.TemporaryDirectory() as td:
+        fn = os.path.join(td, "l.mlv")
+        synth.write_mlv(fn, [pix, pix[::-1].copy()], bpp=14, lossless=True)
+        f0, info = O.ref_mlv_decode(fn, 0)
+        f1, _ = O.ref_mlv_decode(fn, 1)
+        clip = np.frombuffer(open(fn, "rb").read(), np.uint8)
+    assert (f0 == pix).all() and (f1 == pix[::-1]).all()
+    np.savez_compressed(os.path.join(HERE, "lj92.npz"), clip=clip, clip_frames=np.stack([f0, f1]), notes=np.array(notes),
+                        **{"stream_%d" % i: s for i, s in enumerate(streams)}, **{"expected_%d" % i: e for i, e in enumerate(expected)})
+    print("lj92 goldens:", len(streams), "streams + lossless clip", clip.size, "bytes")
+
+
 def darkroom_goldens():
     w, h = 168, 126
     raw = synth.mosaic(w, h, seed=77)
@@ -52,4 +111,5 @@ def darkroom_goldens():
 
 if __name__ == "__main__":
     mlv_goldens()
+    lj92_goldens()
     darkroom_goldens()

@@ -454,3 +454,33 @@ def test_full_size_61mp_properties(gpu):
     diff = np.abs(s[512:-512, 512:-512] - a[64 + 512:-512, 64 + 512:-512])
     print("translation: median %.3g, 99.9%% %.3g" % (np.median(diff), np.quantile(diff[::7, ::7], 0.999)))
     assert np.median(diff) < 2.5e-4                               # (3)
+
+
+def test_lossless_mlv_clip(gpu, tmp_path):
+    """a lossless (LJ92) clip develops to exactly what the same frames give as an uncompressed 14-bit clip."""
+    w, h = 512, 258
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = synth.mosaic(w, h, seed=3).astype(np.int64)
+    frames = [np.clip((base // 16) * 16 + ((xx + 3 * yy + k) & 7), 0, 16383).astype(np.uint16) for k in range(2)]   # compressible
+    outs = {}
+    for lossless in (False, True):
+        fn = str(tmp_path / ("l.mlv" if lossless else "u.mlv"))
+        synth.write_mlv(fn, frames, bpp=14, lossless=lossless)
+        g = gpu.Graph(cfg_text=gpu.DARKROOM_CFG.format(src="i-mlv"))
+        assert g.line("param:i-mlv:main:filename:%s" % fn) == 0
+        g.set_sink_buffer(None, 0)
+        g.run()
+        ow, oh = g.sink_size()
+        res = []
+        for f in range(2):
+            out = np.zeros((oh, ow, 4), dtype=np.float32)
+            g.set_sink_buffer(out.ctypes.data, out.nbytes)
+            g.set_frame(f)
+            g.run(gpu.RUN_RECORD | gpu.RUN_UPLOAD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT | gpu.RUN_PERF)
+            res.append(out)
+        perf = g.perf()
+        assert ("unpack" in perf or "rawnoop" in perf) == (not lossless)
+        outs[lossless] = res
+    for f in range(2):
+        assert np.isfinite(outs[True][f]).all() and np.array_equal(outs[True][f], outs[False][f])
+    assert not np.array_equal(outs[True][0], outs[True][1])

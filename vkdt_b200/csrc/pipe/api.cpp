@@ -1,6 +1,7 @@
 // graph layer of the C-ABI (include/vkdt_b200.h §3): thin extern "C" wrappers over the pipe model + executor.
 #include "pipe.h"
 #include "dng.h"
+#include "lj92.h"
 #include "mlv.h"
 
 int vkb_plan_sink(dt_graph_t *g, int modid, uint32_t *wd, uint32_t *ht, void **dptr);
@@ -131,6 +132,13 @@ int vkb_dng_info(const char *filename, vkb_raw_params_t *p, uint32_t *ox, uint32
   dng_image_t img;
   if(dng_read(filename, &img)) return VKB_ERR_IO;
   return dng_raw_params(&img, p, ox, oy) ? VKB_ERR_BAD_ARG : VKB_OK;
+}
+int vkb_lj92_decode(const uint8_t *data, size_t size, uint16_t *out, size_t count, int *w, int *h, int *bits, int *comps)
+{
+  if(!data || !size) return VKB_ERR_BAD_ARG;
+  if(lj92_info(data, size, w, h, bits, comps)) return vkb_set_error(VKB_ERR_IO, "not a lossless jpeg stream this decoder handles");
+  if(out && lj92_decode(data, size, out, count)) return vkb_set_error(VKB_ERR_IO, "lossless jpeg stream is corrupt or the output buffer too small");
+  return VKB_OK;
 }
 int vkb_graph_set_device(vkb_graph_t *h, int device) { if(!h) return VKB_ERR_BAD_ARG; h->g->device = device; return VKB_OK; }
 uint64_t vkb_graph_pool_bytes(vkb_graph_t *h) { return h ? vkb_plan_pool_bytes(h->g) : 0; }

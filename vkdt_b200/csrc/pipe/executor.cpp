@@ -302,7 +302,7 @@ static int build_plan(dt_graph_t *g, bool with_device)
       if(nd->module->name == dt_token("i-mlv"))
       {
         if(ms) s.packed_bpp = ms->p.packed_bpp;
-        else s.packed_bpp = ((mlv_clip_t *)nd->module->data)->bpp;
+        else s.packed_bpp = ((mlv_clip_t *)nd->module->data)->lossless ? 0 : ((mlv_clip_t *)nd->module->data)->bpp;
       }
       s.external = ms && ms->on_device;
       const int out = B.out_buf(n, 0);

@@ -1,4 +1,5 @@
 #include "mlv.h"
+#include "lj92.h"
 #include <string.h>
 #include <algorithm>
 
@@ -78,8 +79,8 @@ int mlv_open(mlv_clip_t *c, const char *filename)
     pos += bsize;
   }
   if(!have_mlvi || !have_rawi || c->frames.empty() || !c->width || !c->height) { fclose(f); c->frames.clear(); return 1; }
-  if(c->video_class & 0x20) { fclose(f); c->frames.clear(); fprintf(stderr, "[i-mlv] lossless (LJ92) clips are not supported yet\n"); return 1; }
-  if(c->bpp != 10 && c->bpp != 12 && c->bpp != 14) { fclose(f); c->frames.clear(); fprintf(stderr, "[i-mlv] unsupported bit depth %u\n", c->bpp); return 1; }
+  c->lossless = (c->video_class & 0x20) != 0; // MLV_VIDEO_CLASS_FLAG_LJ92 (video_mlv.c:227)
+  if(!c->lossless && c->bpp != 10 && c->bpp != 12 && c->bpp != 14) { fclose(f); c->frames.clear(); fprintf(stderr, "[i-mlv] unsupported bit depth %u\n", c->bpp); return 1; }
   std::stable_sort(c->frames.begin(), c->frames.end(), [](const mlv_frame_t &a, const mlv_frame_t &b) { return a.timestamp < b.timestamp; });
   if(c->frame_count == 0 || c->frame_count > c->frames.size()) c->frame_count = (uint32_t)c->frames.size();
   c->file = f;
@@ -96,4 +97,18 @@ int mlv_read_packed(mlv_clip_t *c, uint32_t idx, void *dst)
   if(fread(dst, 1, payload, c->file) != payload) return 1;
   memset((uint8_t *)dst + payload, 0, total - payload);
   return 0;
+}
+
+// lossless clips: the frame is one lossless jpeg stream; decoded on the host (video_mlv.c:224-251 does the same with
+// liblj92) straight into the staging buffer as width*height u16
+int mlv_read_lossless(mlv_clip_t *c, uint32_t idx, uint16_t *dst)
+{
+  if(!c->file || idx >= c->frames.size() || !c->lossless) return 1;
+  std::vector<uint8_t> buf(c->frames[idx].payload_size);
+  fseek(c->file, (long)c->frames[idx].payload_offset, SEEK_SET);
+  if(buf.empty() || fread(buf.data(), 1, buf.size(), c->file) != buf.size()) return 1;
+  int w = 0, h = 0, bits = 0, comps = 0;
+  if(lj92_info(buf.data(), buf.size(), &w, &h, &bits, &comps)) return 1;
+  if((size_t)w * h * comps != (size_t)c->width * c->height) { fprintf(stderr, "[i-mlv] lossless frame is %dx%dx%d, clip says %ux%u\n", w, h, comps, c->width, c->height); return 1; }
+  return lj92_decode(buf.data(), buf.size(), dst, (size_t)c->width * c->height);
 }

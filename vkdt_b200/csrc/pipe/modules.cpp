@@ -438,6 +438,7 @@ static int imlv_read_source(dt_module_t *mod, void *mapped, dt_read_source_param
   mlv_clip_t *c = (mlv_clip_t *)mod->data;
   uint32_t frame = g->frame;
   if(frame >= c->frame_count) frame = c->frame_count - 1; // i-mlv/main.c:82
+  if(c->lossless) return mlv_read_lossless(c, frame, (uint16_t *)mapped); // host decode like the reference, uploaded as plain u16
   return mlv_read_packed(c, frame, mapped);
 }
 

@@ -112,11 +112,13 @@ def pack_bits_fast14(pix):
 RAWI_SIZE = 4 + 4 + 8 + 2 + 2 + 160
 
 
-def write_mlv(filename, frames, bpp=14, black=BLACK, white=WHITE, fps=(24000, 1000), camera_name=None):
-    """frames: list of (H,W) uint16 arrays. writes MLVI + RAWI [+ IDNT] + VIDF*N (uncompressed)."""
+def write_mlv(filename, frames, bpp=14, black=BLACK, white=WHITE, fps=(24000, 1000), camera_name=None, lossless=False):
+    """frames: list of (H,W) uint16 arrays. writes MLVI + RAWI [+ IDNT] + VIDF*N, uncompressed (packed bits) or, with
+    lossless=True, one lossless jpeg stream per frame (MLV_VIDEO_CLASS_FLAG_LJ92, two interleaved components like
+    Magic Lantern writes them)."""
     h, w = frames[0].shape
     with open(filename, "wb") as f:
-        f.write(struct.pack("<4sI8sQHHIHHIIII", b"MLVI", 52, b"v2.0\0\0\0\0", 0x1234, 0, 1, 0, 1, 0,
+        f.write(struct.pack("<4sI8sQHHIHHIIII", b"MLVI", 52, b"v2.0\0\0\0\0", 0x1234, 0, 1, 0, 0x21 if lossless else 1, 0,
                             len(frames), 0, fps[0], fps[1]))
         raw_info = struct.pack("<II3iiiii4i4i2iii18ii", 1, 0, h, w, w * bpp // 8, w * h * bpp // 8, bpp, black, white,
                                0, 0, w, h, 0, 0, h, w, 0, 0, 0x02010100, 21, *([0] * 18), 1100)
@@ -127,8 +129,14 @@ def write_mlv(filename, frames, bpp=14, black=BLACK, white=WHITE, fps=(24000, 10
             f.write(struct.pack("<4sIQ32sI32s", b"IDNT", 4 + 4 + 8 + 32 + 4 + 32, 2, name, 0x80000285, b""))
         for i, fr in enumerate(frames):
             assert fr.shape == (h, w)
-            words = pack_bits_fast14(fr) if (bpp == 14 and fr.size % 8 == 0) else pack_bits(fr, bpp)
-            payload = words[:(w * h * bpp // 8 + 1) // 2].tobytes()[: w * h * bpp // 8]
+            if lossless:
+                payload = lj92_encode(fr, bits=bpp, components=2 if w % 2 == 0 else 1, predictor=1,
+                                      lengths=[2, 3, 3, 3, 4, 4, 4, 5, 5, 6, 6, 7, 8, 9, 10, 11, 12])
+                # the reference reads the stream into a buffer of the UNCOMPRESSED frame size (video_mlv.c:215)
+                assert len(payload) <= w * h * bpp // 8, "lossless frame larger than the packed one: use smoother test data"
+            else:
+                words = pack_bits_fast14(fr) if (bpp == 14 and fr.size % 8 == 0) else pack_bits(fr, bpp)
+                payload = words[:(w * h * bpp // 8 + 1) // 2].tobytes()[: w * h * bpp // 8]
             f.write(struct.pack("<4sIQIHHHHI", b"VIDF", 32 + len(payload), 10 + i, i, 0, 0, 0, 0, 0))
             f.write(payload)
     return filename
@@ -228,3 +236,68 @@ def write_pfm(filename, img):
     with open(filename, "wb") as f:
         f.write((hdr + "0" * pad + "\n").encode())
         f.write(np.ascontiguousarray(img[..., :3] if img.ndim == 3 else img).astype("<f4").tobytes())
+
+
+def lj92_encode(img, bits=14, components=1, predictor=1, lengths=None):
+    """(H,W) uint16 -> lossless jpeg (T.81 annex H) byte stream.  components 2 packs pairs of columns into interleaved
+    components the way Magic Lantern's lossless MLV frames do (frame width W = X * components).  Test helper: plain python,
+    use small images.  lengths: code length per difference category 0..16 (default: a fixed 5-bit code for all 17)."""
+    import struct
+    img = np.asarray(img, dtype=np.int64)
+    h, wtot = img.shape
+    assert wtot % components == 0
+    x = wtot // components
+    lengths = list(lengths) if lengths is not None else [5] * 17
+    assert len(lengths) == 17
+    order = sorted(range(17), key=lambda s: (lengths[s], s))
+    counts = [sum(1 for s in range(17) if lengths[s] == l) for l in range(1, 17)]
+    codes, code, prev = {}, 0, lengths[order[0]]
+    for s in order:            # canonical code assignment, T.81 annex C
+        code <<= lengths[s] - prev
+        prev = lengths[s]
+        codes[s] = (code, lengths[s])
+        code += 1
+    out = bytearray(b"\xff\xd8")
+    out += b"\xff\xc4" + struct.pack(">H", 2 + 17 + 17) + bytes([0]) + bytes(counts) + bytes(order)
+    out += b"\xff\xc3" + struct.pack(">HBHHB", 8 + 3 * components, bits, h, x, components)
+    for c in range(components):
+        out += bytes([c + 1, 0x11, 0])
+    out += b"\xff\xda" + struct.pack(">HB", 6 + 2 * components, components)
+    for c in range(components):
+        out += bytes([c + 1, 0x00])
+    out += bytes([predictor, 0, 0])
+    acc, nbits = 0, 0
+    body = bytearray()
+
+    def put(v, n):
+        nonlocal acc, nbits
+        acc = (acc << n) | (v & ((1 << n) - 1)); nbits += n
+        while nbits >= 8:
+            b = (acc >> (nbits - 8)) & 0xff
+            body.append(b)
+            if b == 0xff:
+                body.append(0)
+            nbits -= 8
+    nc = components
+    for y in range(h):
+        for i in range(wtot):
+            xx = i // nc
+            if y == 0:
+                pred = (1 << (bits - 1)) if xx == 0 else img[y, i - nc]
+            elif xx == 0:
+                pred = img[y - 1, i]
+            else:
+                ra, rb, rc = int(img[y, i - nc]), int(img[y - 1, i]), int(img[y - 1, i - nc])
+                pred = [ra, rb, rc, ra + rb - rc, ra + ((rb - rc) >> 1), rb + ((ra - rc) >> 1), (ra + rb) >> 1][predictor - 1]
+            d = (int(img[y, i]) - int(pred)) & 0xffff
+            if d >= 32768:
+                d -= 65536
+            if d == -32768:
+                d = 32768
+            ssss = 16 if d == 32768 else (abs(d)).bit_length()
+            put(*codes[ssss])
+            if 0 < ssss < 16:
+                put(d if d >= 0 else d + (1 << ssss) - 1, ssss)
+    if nbits:
+        put((1 << (8 - nbits)) - 1, 8 - nbits)      # pad with ones
+    return bytes(out + body + b"\xff\xd9")
