@@ -15,7 +15,7 @@ int launch_xtrans_fix(const vkb_launch_t *l);
 // i / p and j / p are evaluated as i * (1 / p): i, j are in {-1, 0, 1, 2}, and scaling a correctly rounded quotient
 // by 0, +-1 or 2 is exact, so one division per tap serves all three sums bit for bit.
 template <bool xtrans>
-__global__ void __launch_bounds__(256) k_demosaic_gauss(const __half *__restrict__ orig, int iw, int ih,
+__global__ void __launch_bounds__(256, 5) k_demosaic_gauss(const __half *__restrict__ orig, int iw, int ih,
     uint2 *__restrict__ out, int ow, int oh)
 {
   const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;

@@ -22,7 +22,7 @@ VKB_DEV float splat_weight(float e0, float e1, float cz, float cw, int i, int j)
   return clampf(expf(-0.5f * (of0 / e0 * of0 + of1 / e1 * of1)), 1e-4f, 1.0f);
 }
 
-__global__ void __launch_bounds__(256) k_bayer_splat(const __half *__restrict__ in, int w, int h,
+__global__ void __launch_bounds__(256, 6) k_bayer_splat(const __half *__restrict__ in, int w, int h,
     const uint2 *__restrict__ gauss, int gw, int gh, __half *__restrict__ out)
 {
   const int b = blockIdx.x * 32 + threadIdx.x, c = blockIdx.y * 8 + threadIdx.y;
@@ -83,7 +83,7 @@ VKB_DEV float fixw(float e0, float e1, float cz, float cw, int i, int j)
   return clampf(expf(-0.5f * (of0 / e0 * of0 + of1 / e1 * of1)), 1e-3f, 1.0f);
 }
 
-__global__ void __launch_bounds__(256) k_bayer_fix(const __half *__restrict__ in, const __half *__restrict__ green, int w, int h,
+__global__ void __launch_bounds__(256, 5) k_bayer_fix(const __half *__restrict__ in, const __half *__restrict__ green, int w, int h,
     const uint2 *__restrict__ covimg, int gw, int gh, uint2 *__restrict__ out)
 {
   const int b = blockIdx.x * 32 + threadIdx.x, c = blockIdx.y * 8 + threadIdx.y;

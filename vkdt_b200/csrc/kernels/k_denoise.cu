@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) k_denoise_half(const uint16_t *__restrict
 #define DC_W 36
 #define DC_H 12
 // the j loops stay rolled: 55 registers instead of 128, four CTAs per SM; the unrolled i loop gives the ILP
-__global__ void __launch_bounds__(256, 4) k_denoise_downcov(const uint2 *__restrict__ in, int w, int h,
+__global__ void __launch_bounds__(256, 5) k_denoise_downcov(const uint2 *__restrict__ in, int w, int h,
     uint2 *__restrict__ out, uint2 *__restrict__ covimg)
 {
   __shared__ float4 tile[DC_H][DC_W];  // r g b lum
@@ -219,7 +219,7 @@ VKB_DEV float4 unpack_rgba(uint2 v)
   const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&v.x)), b = __half22float2(*reinterpret_cast<const __half2 *>(&v.y));
   return make_float4(a.x, a.y, b.x, b.y);
 }
-__global__ void __launch_bounds__(256) k_denoise_down_tiled(const uint2 *__restrict__ in, int w, int h, uint2 *__restrict__ out,
+__global__ void __launch_bounds__(256, 6) k_denoise_down_tiled(const uint2 *__restrict__ in, int w, int h, uint2 *__restrict__ out,
     denoise_params_t p, float black, float white, float noise_a, float noise_b, float lv, float blk)
 {
   __shared__ uint2 tile[DD_H][DD_W];
@@ -282,7 +282,7 @@ struct asm_consts_t { float rgb_to_yuv[9], yuv_to_rgb[9]; float wb[3], black[3],
                       float bb[4], ibb[4]; }; // 0.7^(l+1) / blk and its reciprocal: launch constants, evaluated on the host
 
 // ---- assemble: wavelet shrinkage over the 4 detail bands (assemble.comp:43-165) ----
-__global__ void __launch_bounds__(256) k_denoise_assemble(const uint2 *__restrict__ s0, const uint2 *__restrict__ s1, const uint2 *__restrict__ s2,
+__global__ void __launch_bounds__(256, 5) k_denoise_assemble(const uint2 *__restrict__ s0, const uint2 *__restrict__ s1, const uint2 *__restrict__ s2,
     const uint2 *__restrict__ s3, const uint2 *__restrict__ s4, uint2 *__restrict__ out, int w, int h,
     const __grid_constant__ denoise_params_t p, const __grid_constant__ asm_consts_t K)
 {
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(256) k_denoise_doub(const uint16_t *__restrict
 // .75/.25 on texels X-1..X+1) share one 3x3 window of each coarse image and each pixel only needs its own colour channel,
 // so a block costs 9+9 texel loads and 25 f16 conversions instead of 32 loads and 96 conversions.  per pixel the
 // expressions are those of bilin_rgba() term by term.
-__global__ void __launch_bounds__(256, 4) k_denoise_doub_bayer(const uint16_t *__restrict__ in, int iw, int ih,
+__global__ void __launch_bounds__(256, 5) k_denoise_doub_bayer(const uint16_t *__restrict__ in, int iw, int ih,
     const uint2 *__restrict__ crs0, const uint2 *__restrict__ crs1, int cw, int ch, __half *__restrict__ out, int ow, int oh,
     const __grid_constant__ denoise_params_t p, const __grid_constant__ dn_push_doub_t P)
 {

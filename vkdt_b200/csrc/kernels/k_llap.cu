@@ -74,7 +74,7 @@ VKB_DEV float llap_grey(float4 px)
 #define R0_TW 65
 #define R0_TH 17
 template <bool CLARITY>
-__global__ void __launch_bounds__(256) k_llap_reduce0(const uint2 *__restrict__ in, int iw, int ih,
+__global__ void __launch_bounds__(256, 6) k_llap_reduce0(const uint2 *__restrict__ in, int iw, int ih,
     __half *__restrict__ out, int ow, int oh, llap_params_t p)
 {
   __shared__ __align__(16) __half tile[NL][R0_TH][R0_TW + 1];
@@ -351,6 +351,7 @@ VKB_REGISTER("llap", "reduce", launch_llap_reduce);
 
 // conn: [0] coarse y f16 (ignored when push.first), [1] currlo x11 (fine), [2] currhi x11 (coarse), [3] fine out y f16
 // push: { u32 num_gamma; u32 first } (llap/main.c:66,92)
+int launch_llap_assemble4(const vkb_launch_t *l, int first);
 static int launch_llap_assemble(const vkb_launch_t *l)
 {
   VKB_REQUIRE(l->num_conn >= 4 && l->push_size >= 8);
@@ -360,6 +361,7 @@ static int launch_llap_assemble(const vkb_launch_t *l)
   VKB_REQUIRE(l0->wd == out->wd && l0->ht == out->ht);
   VKB_REQUIRE(pc[1] || (coarse->wd == l1->wd && coarse->ht == l1->ht));
   VKB_REQUIRE(l1->wd == (out->wd - 1) / 2 + 1 && l1->ht == (out->ht - 1) / 2 + 1);
+  if(out->wd >= 80 && out->ht >= 32) return launch_llap_assemble4(l, (int)pc[1]); // one thread per 2x2 pixels, k_llap_asm4.cu
   if(out->wd >= 64 && out->ht >= 16)
     k_llap_assemble_tiled<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const __half *)coarse->data, (const __half *)l0->data,
         (const __half *)l1->data, l1->wd, l1->ht, (__half *)out->data, out->wd, out->ht, (int)pc[1]);

@@ -190,7 +190,7 @@ VKB_DEV f3 grade_px_digest(f3 c, const llapfin_t &P)
 }
 
 template <bool F32, bool GRADE>
-__global__ void __launch_bounds__(256, 3) k_llap_final4(const uint2 *__restrict__ in, const __half *__restrict__ coarse,
+__global__ void __launch_bounds__(256, 4) k_llap_final4(const uint2 *__restrict__ in, const __half *__restrict__ coarse,
     const __half *__restrict__ l1, int cw, int ch, void *__restrict__ outv, int ow, int oh, const __grid_constant__ llapfin_t P)
 {
   __shared__ float tile[NL + 1][F3_H][F3_W + 1];
