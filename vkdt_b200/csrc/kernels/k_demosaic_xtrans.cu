@@ -41,7 +41,7 @@ VKB_DEV float xt_splat_px(const __half *__restrict__ in, int w, int h, const uin
   return g / fmaxf(1e-8f, wg);
 }
 
-__global__ void __launch_bounds__(128) k_xtrans_splat(const __half *__restrict__ in, int w, int h,
+__global__ void __launch_bounds__(128, 8) k_xtrans_splat(const __half *__restrict__ in, int w, int h,
     const uint2 *__restrict__ gauss, int gw, int gh, __half *__restrict__ out)
 {
   const int X = blockIdx.x * 32 + threadIdx.x, Y = blockIdx.y * 4 + threadIdx.y;
@@ -106,7 +106,7 @@ VKB_DEV float4 xt_fix_px(const __half *__restrict__ in, const __half *__restrict
   return make_float4(rgb[0] / fmaxf(1e-8f, wt[0]), rgb[1] / fmaxf(1e-8f, wt[1]), rgb[2] / fmaxf(1e-8f, wt[2]), 1.0f);
 }
 
-__global__ void __launch_bounds__(128) k_xtrans_fix(const __half *__restrict__ in, const __half *__restrict__ green, int w, int h,
+__global__ void __launch_bounds__(128, 6) k_xtrans_fix(const __half *__restrict__ in, const __half *__restrict__ green, int w, int h,
     const uint2 *__restrict__ covimg, int gw, int gh, uint2 *__restrict__ out)
 {
   const int X = blockIdx.x * 32 + threadIdx.x, Y = blockIdx.y * 4 + threadIdx.y;
