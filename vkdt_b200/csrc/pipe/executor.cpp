@@ -32,7 +32,10 @@ struct plan_launch_t
   std::vector<plan_img_t> conn;
   std::string label;
   float ms = 0.0f;
+  std::vector<uint8_t> arg_params;  // this run's arguments (filled by dt_graph_run)
+  std::vector<vkb_image_t> arg_conn;
 };
+struct plan_graph_t { cudaGraphExec_t exec = 0; uint64_t hash = 0; int launches = 0; }; // one captured frame
 struct plan_source_t { int modid; int nodeid; int buf_upload; size_t bytes; int packed_bpp; int external; };
 struct plan_sink_t   { int modid; int nodeid; int buf; size_t bytes; uint32_t wd, ht; int rgb; };
 
@@ -48,6 +51,8 @@ struct vkb_plan_t
   void *staging_down = 0; size_t staging_down_bytes = 0; // pinned host
   cudaStream_t stream = 0;
   std::vector<cudaEvent_t> ev;
+  std::vector<plan_graph_t> graphs = std::vector<plan_graph_t>(4); // small cache keyed by the fingerprint of the launch arguments
+  unsigned graph_next = 0;
 };
 
 static void plan_free(vkb_plan_t *p)
@@ -57,6 +62,7 @@ static void plan_free(vkb_plan_t *p)
   if(p->staging_up) cudaFreeHost(p->staging_up);
   if(p->staging_down) cudaFreeHost(p->staging_down);
   for(cudaEvent_t e : p->ev) cudaEventDestroy(e);
+  for(plan_graph_t &cg : p->graphs) if(cg.exec) cudaGraphExecDestroy(cg.exec);
   if(p->stream) cudaStreamDestroy(p->stream);
   delete p;
 }
@@ -561,27 +567,79 @@ int dt_graph_run(dt_graph_t *g, uint32_t run)
   {
     // commit_params for every module in traversal order (graph-run-modules.h:5-31)
     for(int m : p->modid) if(g->module[m].so->commit_params) g->module[m].so->commit_params(g, &g->module[m]);
-    std::vector<uint8_t> params;
-    std::vector<vkb_image_t> conn;
+    // launch arguments of this run, and their fingerprint: every byte a kernel can see (parameters, push constants,
+    // image pointers and shapes)
+    uint64_t hash = 1469598103934665603ull;
+    auto mix = [&hash](const void *d, size_t n) { const uint8_t *b = (const uint8_t *)d; for(size_t k = 0; k < n; k++) { hash ^= b[k]; hash *= 1099511628211ull; } };
     for(size_t i = 0; i < p->launch.size(); i++)
     {
       plan_launch_t &l = p->launch[i];
-      params.clear();
+      l.arg_params.clear();
       for(int m : l.param_mods)
       {
         const dt_module_t *mod = &g->module[m];
         const uint8_t *src = mod->committed_param_size ? mod->committed_param : mod->param;
         const int sz = mod->committed_param_size ? mod->committed_param_size : mod->param_size;
-        params.insert(params.end(), src, src + sz);
+        l.arg_params.insert(l.arg_params.end(), src, src + sz);
       }
-      conn.clear();
-      for(const plan_img_t &im : l.conn) conn.push_back(vkb_image_t{ buf_ptr(p, im.buf), im.wd, im.ht, im.chan, im.layers, im.format });
-      if(run & VKB_RUN_PERF) cudaEventRecord(p->ev[i], p->stream);
-      r = vkb_dispatch(l.name, l.kernel, l.wd, l.ht, l.dp, l.push.data(), (uint32_t)l.push.size(), params.data(), (uint32_t)params.size(),
-          conn.data(), (uint32_t)conn.size(), p->stream);
-      if(r) return r;
+      l.arg_conn.clear();
+      for(const plan_img_t &im : l.conn) l.arg_conn.push_back(vkb_image_t{ buf_ptr(p, im.buf), im.wd, im.ht, im.chan, im.layers, im.format });
+      mix(l.arg_params.data(), l.arg_params.size());
+      mix(l.push.data(), l.push.size());
+      for(const vkb_image_t &im : l.arg_conn) { mix(&im.data, sizeof(im.data)); mix(&im.wd, 4); mix(&im.ht, 4); mix(&im.chan, 4); mix(&im.layers, 4); mix(&im.format, sizeof(im.format)); }
     }
-    if(run & VKB_RUN_PERF) cudaEventRecord(p->ev[p->launch.size()], p->stream);
+    auto dispatch_all = [&](bool events) -> int {
+      for(size_t i = 0; i < p->launch.size(); i++)
+      {
+        plan_launch_t &l = p->launch[i];
+        if(events) cudaEventRecord(p->ev[i], p->stream);
+        const int rr = vkb_dispatch(l.name, l.kernel, l.wd, l.ht, l.dp, l.push.data(), (uint32_t)l.push.size(), l.arg_params.data(), (uint32_t)l.arg_params.size(),
+            l.arg_conn.data(), (uint32_t)l.arg_conn.size(), p->stream);
+        if(rr) return rr;
+      }
+      if(events) cudaEventRecord(p->ev[p->launch.size()], p->stream);
+      return 0;
+    };
+    // frame loops replay a CUDA graph: the launch sequence of a frame is captured once per distinct set of arguments
+    // (a clip ping-ponging between two device buffers has two) and re-launched as one unit, which takes the ~60 kernel
+    // launches and their dependency latencies off the host and the stream front end.  -d perf runs stay plain launches.
+    static const bool no_graph = getenv("VKB_NO_CUDA_GRAPH") != 0;
+    if((run & VKB_RUN_PERF) || no_graph) { r = dispatch_all((run & VKB_RUN_PERF) != 0); if(r) return r; }
+    else
+    {
+      plan_graph_t *hit = 0;
+      for(plan_graph_t &cg : p->graphs) if(cg.exec && cg.hash == hash) hit = &cg;
+      if(!hit)
+      {
+        const uint64_t before = vkb_launch_count();
+        if(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+        { cudaGetLastError(); r = dispatch_all(false); if(r) return r; }
+        else
+        {
+          r = dispatch_all(false);
+          cudaGraph_t cap = 0;
+          const cudaError_t e = cudaStreamEndCapture(p->stream, &cap);
+          if(r) { if(cap) cudaGraphDestroy(cap); return r; }
+          if(e != cudaSuccess || !cap) return vkb_set_error(VKB_ERR_CUDA, "stream capture failed: %s", cudaGetErrorString(e));
+          plan_graph_t &slot = p->graphs[p->graph_next++ % p->graphs.size()];
+          if(slot.exec) cudaGraphExecDestroy(slot.exec);
+          slot.exec = 0;
+          const cudaError_t e2 = cudaGraphInstantiate(&slot.exec, cap, 0);
+          cudaGraphDestroy(cap);
+          if(e2 != cudaSuccess) { slot.exec = 0; return vkb_set_error(VKB_ERR_CUDA, "graph instantiation failed: %s", cudaGetErrorString(e2)); }
+          slot.hash = hash;
+          slot.launches = (int)(vkb_launch_count() - before);
+          vkb_count_launch(-slot.launches); // counted again below, when the captured launches actually run
+          hit = &slot;
+        }
+      }
+      if(hit)
+      {
+        const cudaError_t e = cudaGraphLaunch(hit->exec, p->stream);
+        if(e != cudaSuccess) return vkb_set_error(VKB_ERR_CUDA, "graph launch failed: %s", cudaGetErrorString(e));
+        vkb_count_launch(hit->launches);
+      }
+    }
   }
   if(run & VKB_RUN_DOWNLOAD_SINK)
   {
