@@ -484,3 +484,38 @@ def test_lossless_mlv_clip(gpu, tmp_path):
     for f in range(2):
         assert np.isfinite(outs[True][f]).all() and np.array_equal(outs[True][f], outs[False][f])
     assert not np.array_equal(outs[True][0], outs[True][1])
+
+
+def test_cuda_graph_replay_matches_plain_launches(gpu):
+    """frame loops replay a captured CUDA graph (no VKB_RUN_PERF); -d perf runs launch kernel by kernel.  same pixels, and a
+    parameter or source change between frames is picked up (new fingerprint -> new capture)."""
+    w, h = 530, 412
+    raws = [np.ascontiguousarray(synth.mosaic(w, h, seed=s)) for s in (5, 6)]
+    g = gpu.Graph(cfg_text=gpu.DARKROOM_CFG.format(src="i-raw"))
+    g.line("param:denoise:01:strength:0.4")
+    rp = gpu.raw_params(w, h, wb=WB, cam_to_rec2020=CAM, noise_a=100.0, noise_b=2.0)
+    g.set_source(raws[0].ctypes.data, rp)
+    g.set_sink_buffer(None, 0)
+    g.run()
+    ow, oh = g.sink_size()
+    FR = gpu.RUN_RECORD | gpu.RUN_UPLOAD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT
+
+    def frame(raw, flags):
+        out = np.zeros((oh, ow, 4), dtype=np.float32)
+        g.set_source(raw.ctypes.data, rp)
+        g.set_sink_buffer(out.ctypes.data, out.nbytes)
+        g.run(flags)
+        return out
+
+    plain = [frame(r, FR | gpu.RUN_PERF) for r in raws]
+    n0 = gpu.launch_count()
+    replay = [frame(raws[i % 2], FR) for i in range(6)]           # capture once, replay five times (host source: same pointers)
+    per_frame = (gpu.launch_count() - n0) // 6
+    assert per_frame == len(g.perf_entries()), (per_frame, len(g.perf_entries()))   # replayed launches are counted
+    for i, out in enumerate(replay):
+        assert np.array_equal(out, plain[i % 2])
+    assert not np.array_equal(plain[0], plain[1])
+    assert g.line("param:colour:01:exposure:0.5") == 0            # a parameter change must not replay the stale graph
+    brighter = frame(raws[0], FR)
+    assert brighter[..., :3].mean() > 1.2 * plain[0][..., :3].mean()
+    assert np.array_equal(frame(raws[0], FR | gpu.RUN_PERF), brighter)

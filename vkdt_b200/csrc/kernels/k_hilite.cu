@@ -60,9 +60,11 @@ __global__ void __launch_bounds__(256) k_hilite_reduce(const uint2 *__restrict__
   if(!(white > 0.0f)) white = 1.0f;
   const float ds = p.desat * p.desat;
   const int tx0 = blockIdx.x * 64 - 2, ty0 = blockIdx.y * 16 - 2;
-  for(int t = threadIdx.y * 32 + threadIdx.x; t < HR_TW * HR_TH; t += 256)
+  // only the part of the window the CTA's valid outputs read: the last levels of the pyramid are a few pixels large
+  const int need_w = min(HR_TW, 2 * (ow - (int)blockIdx.x * 32) + 3), need_h = min(HR_TH, 2 * (oh - (int)blockIdx.y * 8) + 3);
+  for(int t = threadIdx.y * 32 + threadIdx.x; t < need_w * need_h; t += 256)
   {
-    const int r = t / HR_TW, c = t - r * HR_TW;
+    const int r = t / need_w, c = t - r * need_w;
     const float4 rgb = ld_rgba(in, iw, mirrori(tx0 + c, iw), mirrori(ty0 + r, ih));
     float4 m = make_float4(0.0f, 0.0f, 0.0f, lum2020(rgb.x, rgb.y, rgb.z));
     const bool ok = rgb.x < white && rgb.y < white && rgb.z < white;

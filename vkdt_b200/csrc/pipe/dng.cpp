@@ -76,6 +76,7 @@ int dng_read(const char *filename, dng_image_t *img)
   if(!raw) return 3;
   if(!find(t, raw, 256, &e)) return 4; img->width = (uint32_t)value(t, e, 0);
   if(!find(t, raw, 257, &e)) return 4; img->height = (uint32_t)value(t, e, 0);
+  if(!img->width || !img->height || (uint64_t)img->width * img->height > (1ull << 31)) return 4; // nothing a sensor produces
   if(find(t, raw, 258, &e) && (int)value(t, e, 0) != 16) { fprintf(stderr, "[i-raw] dng: only 16 bits per sample are supported\n"); return 5; }
   if(find(t, raw, 259, &e) && (int)value(t, e, 0) != 1)  { fprintf(stderr, "[i-raw] dng: only uncompressed data is supported\n"); return 5; }
   if(find(t, raw, 277, &e) && (int)value(t, e, 0) != 1)  { fprintf(stderr, "[i-raw] dng: only one sample per pixel (cfa) is supported\n"); return 5; }
