@@ -78,8 +78,8 @@ __global__ void __launch_bounds__(256) k_denoise_half(const uint16_t *__restrict
 __global__ void __launch_bounds__(256, 5) k_denoise_downcov(const uint2 *__restrict__ in, int w, int h,
     uint2 *__restrict__ out, uint2 *__restrict__ covimg)
 {
-  __shared__ float4 tile[DC_H][DC_W];  // r g b lum
-  __shared__ float4 tinv[DC_H][DC_W];  // 1/lum, 1/(lum*lum), lum/25, lum*lum: every tap's divisions, done once per input texel
+  __shared__ float4 tile[DC_H][DC_W];  // r g b lum/25
+  __shared__ float4 tinv[DC_H][DC_W];  // lum, 1/lum | lum*lum, 1/(lum*lum): every tap's divisions, done once per input texel
   const int tx0 = blockIdx.x * 32 - 2, ty0 = blockIdx.y * 8 - 2;
   const int tid = threadIdx.y * 32 + threadIdx.x;
   for(int t = tid; t < DC_W * DC_H; t += 256)
@@ -87,46 +87,59 @@ __global__ void __launch_bounds__(256, 5) k_denoise_downcov(const uint2 *__restr
     const int r = t / DC_W, c = t - r * DC_W;
     const float4 v = ld_rgba(in, w, mirrori(tx0 + c, w), mirrori(ty0 + r, h));
     const float l = lum2020(v.x, v.y, v.z), l2 = l * l;
-    tile[r][c] = make_float4(v.x, v.y, v.z, l);
-    tinv[r][c] = make_float4(1.0f / l, 1.0f / l2, l / 25.0f, l2);
+    tile[r][c] = make_float4(v.x, v.y, v.z, l / 25.0f);
+    tinv[r][c] = make_float4(l, 1.0f / l, l2, 1.0f / l2);
   }
   __syncthreads();
   const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
   if(x >= w || y >= h) return;
   const int lx = threadIdx.x, ly = threadIdx.y; // tile coords of tap (-2,-2)
-  float mwx = 0, mwy = 0, mbx = 0, mby = 0, smw = 0, smb = 0;
+  // the "white" (weights lum, lum^2) and "black" (weights 1/lum, 1/lum^2) estimates of cov.glsl run through identical
+  // arithmetic: they travel as the two lanes of packed fp32 pairs (FMUL2 / FFMA2), one instruction for both.
+  // lane lo = white, lane hi = black.
+  f2 MX = pk2(0.0f, 0.0f), MY = MX, SM = MX;
 #pragma unroll 1
   for(int j = 0; j < 5; j++)
+  {
+    const float fj = (float)(j - 2);
+    const f2 FJ = pk2(fj, fj);
 #pragma unroll
     for(int i = 0; i < 5; i++)
     {
-      const float px = tile[ly + j][lx + i].w;
-      const float fi = (float)(i - 2), fj = (float)(j - 2);
-      mwx += fi * px; mwy += fj * px;
-      smw += px;
-      // fi / px == fi * (1 / px) bit for bit when fi is 0, +-1 or +-2: scaling a correctly rounded quotient by a power of two is exact
-      const float rcp = tinv[ly + j][lx + i].x;
-      mbx += fi * rcp; mby += fj * rcp;
-      smb += rcp;
+      const float fi = (float)(i - 2);
+      // (lum, 1/lum).  fi / px == fi * (1 / px) bit for bit when fi is 0, +-1 or +-2: scaling a correctly rounded quotient by a power of two is exact
+      const f2 L = *reinterpret_cast<const f2 *>(&tinv[ly + j][lx + i].x);
+      MX = add2(MX, mul2(pk2(fi, fi), L));
+      MY = add2(MY, mul2(FJ, L));
+      SM = add2(SM, L);
     }
-  mwx /= smw; mwy /= smw; mbx /= smb; mby /= smb;
-  float Sw0 = 0, Sw1 = 0, Sw2 = 0, Sw3 = 0, Sb0 = 0, Sb1 = 0, Sb2 = 0, Sb3 = 0, sw = 0, sb = 0, mean_b = 0;
+  }
+  const float smw = lo2(SM), smb = hi2(SM);
+  const float mwx = lo2(MX) / smw, mwy = lo2(MY) / smw, mbx = hi2(MX) / smb, mby = hi2(MY) / smb;
+  // the products run packed; the sums of products stay scalar: ptxas contracts a packed multiply into a following packed
+  // add (FFMA2) whatever --fmad says, and a fused sum would not round like the restatement's
+  f2 SS = pk2(0.0f, 0.0f);
+  float Sw0 = 0, Sw1 = 0, Sw2 = 0, Sw3 = 0, Sb0 = 0, Sb1 = 0, Sb2 = 0, Sb3 = 0, mean_b = 0;
+  f2 P0[5];
+#pragma unroll
+  for(int i = 0; i < 5; i++) P0[i] = pk2((float)(i - 2) - mwx, (float)(i - 2) - mbx);
 #pragma unroll 1
   for(int j = 0; j < 5; j++)
+  {
+    const f2 P1 = pk2((float)(j - 2) - mwy, (float)(j - 2) - mby);
 #pragma unroll
     for(int i = 0; i < 5; i++)
     {
-      const float4 q = tinv[ly + j][lx + i];
-      mean_b += q.z;
-      float p2 = q.w;
-      float p0 = (float)(i - 2) - mwx, p1 = (float)(j - 2) - mwy;
-      Sw0 += p2 * p0 * p0; Sw1 += p2 * p0 * p1; Sw2 += p2 * p1 * p0; Sw3 += p2 * p1 * p1;
-      sw += p2;
-      p0 = (float)(i - 2) - mbx; p1 = (float)(j - 2) - mby;
-      p2 = q.y;
-      Sb0 += p2 * p0 * p0; Sb1 += p2 * p0 * p1; Sb2 += p2 * p1 * p0; Sb3 += p2 * p1 * p1;
-      sb += p2;
+      mean_b += tile[ly + j][lx + i].w;
+      const f2 Q = *reinterpret_cast<const f2 *>(&tinv[ly + j][lx + i].z); // (lum^2, 1/lum^2)
+      const f2 T0 = mul2(Q, P0[i]), T1 = mul2(Q, P1);
+      const f2 A = mul2(T0, P0[i]), B = mul2(T0, P1), C = mul2(T1, P0[i]), D = mul2(T1, P1);
+      Sw0 += lo2(A); Sw1 += lo2(B); Sw2 += lo2(C); Sw3 += lo2(D);
+      Sb0 += hi2(A); Sb1 += hi2(B); Sb2 += hi2(C); Sb3 += hi2(D);
+      SS = add2(SS, Q);
     }
+  }
+  const float sw = lo2(SS), sb = hi2(SS);
   Sw0 /= sw; Sw1 /= sw; Sw2 /= sw; Sw3 /= sw;
   Sb0 /= sb; Sb1 /= sb; Sb2 /= sb; Sb3 /= sb;
   const bool usew = (Sw0 * Sw3 - Sw1 * Sw2) < (Sb0 * Sb3 - Sb1 * Sb2);
