@@ -21,8 +21,12 @@ __global__ void __launch_bounds__(256, 5) k_demosaic_gauss(const __half *__restr
   const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
   if(x >= ow || y >= oh) return;
   constexpr int blk = xtrans ? 3 : 2, lo = xtrans ? 0 : -1;
-  float px[16];
-  float mwx = 0, mwy = 0, mbx = 0, mby = 0, smw = 0, smb = 0;
+  // the "white" (weights p, p^2) and "black" (weights 1/p, 1/p^2) estimates go through identical arithmetic: they run as
+  // the two lanes of packed fp32 pairs (FMUL2 / FFMA2; lane lo = white, hi = black), like in denoise's downcov.
+  // first moments: i, j are 0, +-1, 2, the products are exact, so the fused multiply-add ptxas makes of them rounds like
+  // the separate operations.  second moments: inexact products, multiplied packed and summed as scalars, unfused.
+  f2 px[16];
+  f2 MX = pk2(0.0f, 0.0f), MY = MX, SM = MX;
   int xi[4], yi[4];
 #pragma unroll
   for(int i = lo; i < 3; i++) { xi[i - lo] = mirror1(blk * x + i, iw); yi[i - lo] = mirror1(blk * y + i, ih); }
@@ -33,29 +37,33 @@ __global__ void __launch_bounds__(256, 5) k_demosaic_gauss(const __half *__restr
   {
     if(xtrans ? (((j + i) & 1) == 1) : (((j + i) & 1) != 1)) continue;
     const float p = ld_h(orig, iw, xi[i - lo], yi[j - lo]);
-    px[4 * (j - lo) + (i - lo)] = p;
-    mwx += (float)i * p; mwy += (float)j * p; smw += p;
-    const float rcp = 1.0f / p;
-    mbx += (float)i * rcp; mby += (float)j * rcp; smb += rcp;
+    const f2 L = pk2(p, 1.0f / p);
+    px[4 * (j - lo) + (i - lo)] = L;
+    MX = add2(MX, mul2(pk2((float)i, (float)i), L));
+    MY = add2(MY, mul2(pk2((float)j, (float)j), L));
+    SM = add2(SM, L);
   }
-  mwx /= smw; mwy /= smw; mbx /= smb; mby /= smb;
-  float Sw0 = 0, Sw1 = 0, Sw2 = 0, Sw3 = 0, Sb0 = 0, Sb1 = 0, Sb2 = 0, Sb3 = 0, sw = 0, sb = 0;
+  const float smw = lo2(SM), smb = hi2(SM);
+  const float mwx = lo2(MX) / smw, mwy = lo2(MY) / smw, mbx = hi2(MX) / smb, mby = hi2(MY) / smb;
+  float Sw0 = 0, Sw1 = 0, Sw2 = 0, Sw3 = 0, Sb0 = 0, Sb1 = 0, Sb2 = 0, Sb3 = 0;
+  f2 SS = pk2(0.0f, 0.0f);
 #pragma unroll
   for(int j = lo; j < 3; j++)
 #pragma unroll
   for(int i = lo; i < 3; i++)
   {
     if(xtrans ? (((j + i) & 1) == 1) : (((j + i) & 1) != 1)) continue;
-    const float p = px[4 * (j - lo) + (i - lo)];
-    float p2 = p * p;
-    float p0 = (float)i - mwx, p1 = (float)j - mwy;
-    Sw0 += p2 * p0 * p0; Sw1 += p2 * p0 * p1; Sw2 += p2 * p1 * p0; Sw3 += p2 * p1 * p1;
-    sw += p2;
-    p0 = (float)i - mbx; p1 = (float)j - mby;
-    p2 = 1.0f / p2;
-    Sb0 += p2 * p0 * p0; Sb1 += p2 * p0 * p1; Sb2 += p2 * p1 * p0; Sb3 += p2 * p1 * p1;
-    sb += p2;
+    const float p = lo2(px[4 * (j - lo) + (i - lo)]);
+    const float p2 = p * p;
+    const f2 Q = pk2(p2, 1.0f / p2);
+    const f2 P0 = pk2((float)i - mwx, (float)i - mbx), P1 = pk2((float)j - mwy, (float)j - mby);
+    const f2 T0 = mul2(Q, P0), T1 = mul2(Q, P1);
+    const f2 A = mul2(T0, P0), B = mul2(T0, P1), C = mul2(T1, P0), D = mul2(T1, P1);
+    Sw0 += lo2(A); Sw1 += lo2(B); Sw2 += lo2(C); Sw3 += lo2(D);
+    Sb0 += hi2(A); Sb1 += hi2(B); Sb2 += hi2(C); Sb3 += hi2(D);
+    SS = add2(SS, Q);
   }
+  const float sw = lo2(SS), sb = hi2(SS);
   Sw0 /= sw; Sw1 /= sw; Sw2 /= sw; Sw3 /= sw;
   Sb0 /= sb; Sb1 /= sb; Sb2 /= sb; Sb3 /= sb;
   const bool usew = (Sw0 * Sw3 - Sw1 * Sw2) < (Sb0 * Sb3 - Sb1 * Sb2);
