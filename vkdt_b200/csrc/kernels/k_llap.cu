@@ -317,6 +317,7 @@ __global__ void __launch_bounds__(256) k_llap_final(const uint2 *__restrict__ in
 static inline dim3 grid2d(unsigned w, unsigned h, unsigned z = 1) { return dim3(vkb_cdiv(w, 32), vkb_cdiv(h, 8), z); }
 static const dim3 blk2d(32, 8);
 
+int launch_llapr0_packed(const vkb_launch_t *l);
 // conn: [0] input rgba f16 (level 0), [1] output y f16 x 11 layers (level 1).  params: llap params
 static int launch_llapr0(const vkb_launch_t *l)
 {
@@ -325,6 +326,7 @@ static int launch_llapr0(const vkb_launch_t *l)
   VKB_REQUIRE(in->chan == 4 && in->format == VKB_TOKEN_F16 && out->chan == 1 && out->layers == NL && out->format == VKB_TOKEN_F16);
   VKB_REQUIRE(out->wd == (in->wd - 1) / 2 + 1 && out->ht == (in->ht - 1) / 2 + 1);
   const llap_params_t *lp = (const llap_params_t *)l->params;
+  if(!getenv("VKB_LLAPR0_SCALAR")) return launch_llapr0_packed(l); // two layers per packed fp32 instruction, k_llap_r0.cu
   if(lp->clarity == 0.0f)
     k_llap_reduce0<false><<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht,
         (__half *)out->data, out->wd, out->ht, *lp);
