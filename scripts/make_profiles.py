@@ -35,7 +35,7 @@ ev = bench["roofline"]["kernels"]
 LABEL = {"k_denoise_half": "denoise_half", "k_denoise_downcov": "denoise_downcov", "k_denoise_down_tiled": "denoise_down", "k_denoise_down": "denoise_down",
          "k_denoise_assemble": "denoise_assemble", "k_denoise_doub_bayer": "denoise_doub", "k_hilite_half": "hilite_half", "k_hilite_reduce": "hilite_reduce",
          "k_hilite_assemble": "hilite_assemble", "k_hilite_doub": "hilite_doub", "k_demosaic_gauss<0>": "demosaic_gauss", "k_bayer_splat": "demosaic_splat",
-         "k_bayer_fix": "demosaic_fix", "k_llap_reduce0<1>": "b200_llapr0", "k_llap_reduce": "llap_reduce", "k_llap_assemble_tiled": "llap_assemble",
+         "k_bayer_fix": "demosaic_fix", "k_llap_reduce0<1>": "b200_llapr0", "k_llap_reduce0_p<1>": "b200_llapr0", "k_llap_reduce": "llap_reduce", "k_llap_assemble_tiled": "llap_assemble",
          "k_llap_assemble": "llap_assemble", "k_llap_assemble4": "llap_assemble", "k_llap_final4<1, 1>": "b200_llapfin", "k_pointwise_t<1, 2, 3, 0, 0, 1>": "b200_pointw"}
 
 # ---- per launch table of the full capture ----
