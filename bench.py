@@ -362,7 +362,7 @@ def main():
                    "parallelism": "independent stills per GPU, no collective", "edges": "f16 at every reference edge (strict)"},
         "e2e": {"value": round(world * e2e_steps * mp / (t_e2e_ms * 1e-3), 2), "unit": "MP/s", "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": out_bytes, "ms_per_step": round(t_e2e_ms / e2e_steps, 3), "steps": e2e_steps, "checksum": checksum},
-        "gpu_launches": int(launches), "launches_per_step": int(launches // max(1, args.steps)),
+        "gpu_launches": int(launches) * world, "launches_per_step": int(launches // max(1, args.steps)),  # every rank launches the same sequence
         "clocks": clocks, "roofline": roof, "pool_bytes": R["pool_bytes"],
     }
     if M:
