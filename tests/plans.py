@@ -41,7 +41,7 @@ def demosaic(api, d_in, w, h, filters=0x5d5d5d5d, fixup=0):
     return out, cov, green
 
 
-def llap(api, d_in, w, h, params, grade=None, out_f32=False):
+def llap(api, d_in, w, h, params, grade=None, out_f32=False, final_kernel="llapfin"):
     """d_in: rgba f16 (h,w,4). params = (sigma, shadows, hilights, clarity); grade: 19-value tuple packed bytes or None."""
     I = api.image
     par = fbits(*params)
@@ -60,7 +60,7 @@ def llap(api, d_in, w, h, params, grade=None, out_f32=False):
         coarse = out
     out = dev_f32(h, w) if out_f32 else dev_f16(h, w, 4)
     first = 1 if nl == 2 else 0
-    api.dispatch("b200", "llapfin", [I(d_in, w, h, 4, "f16"), I(coarse, *lv[1], 1, "f16"), I(stacks[1], *lv[1], 1, "f16", layers=11),
+    api.dispatch("b200", final_kernel, [I(d_in, w, h, 4, "f16"), I(coarse, *lv[1], 1, "f16"), I(stacks[1], *lv[1], 1, "f16", layers=11),
                                      I(out, w, h, 4, "f32" if out_f32 else "f16")], ubits(first, 1 if grade else 0),
                  par + (grade or b""))
     return out

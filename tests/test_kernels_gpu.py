@@ -294,6 +294,18 @@ def test_llap_module(gpu, oracle, dims, with_grade):
     assert err.max() < 2e-3 and psnr(got[..., :3], want[..., :3]) > 66.0, (err.max(), psnr(got[..., :3], want[..., :3]))
 
 
+def test_llapfin_against_the_exact_order_kernel(gpu):
+    """(b200, llapfin) expands the coarse level with separable sums and runs two layers per packed instruction;
+    (b200, llapfinx) is the per pixel kernel in the shader's 9-tap order.  they may differ by fp32 rounding before the
+    f16 store, i.e. by one f16 ulp at a small fraction of the pixels, nowhere by more than two."""
+    w, h = 506, 384
+    d_in = to_dev_f16(_rgb_image(w, h, scale=0.9))
+    a = to_host(plans.llap(gpu, d_in, w, h, (0.12, 1.0, 1.0, 0.2)))
+    b = to_host(plans.llap(gpu, d_in, w, h, (0.12, 1.0, 1.0, 0.2), final_kernel="llapfinx"))
+    ulp = f16_ulp_diff(a[..., :3], b[..., :3])
+    assert ulp.max() <= 2 and (ulp > 0).mean() < 2e-3, (int(ulp.max()), float((ulp > 0).mean()))
+
+
 # ---------------------------------------------------------------------------------------------------------
 # wavelet denoise (denoise:strength > 0)
 def _denoise_push(kind, wb, black, white, crop, filters, na, nb, level=0, block=2):

@@ -13,8 +13,6 @@
 
 #define NUM_GAMMA 10
 #define NL (NUM_GAMMA + 1)
-#define FT_W 20
-#define FT_H 8
 
 struct llap_params_t { float sigma, shadows, hilights, clarity; };
 // everything below `grade` is a function of the launch's parameters only and is evaluated once on the host with the same
@@ -67,70 +65,6 @@ VKB_DEV float llap_curve(float x, float g, const llap_params_t &p)
   // the gaussian term is < 3% of val: __expf's 1e-6 relative error on it is below an fp32 ulp of val
   val += p.clarity * c * exp_ftz(-c * c / (2.0f * p.sigma * p.sigma / 3.0f));
   return val;
-}
-
-template <bool F32, bool GRADE>
-__global__ void __launch_bounds__(256) k_llap_final2(const uint2 *__restrict__ in, const __half *__restrict__ coarse,
-    const __half *__restrict__ l1, int cw, int ch, void *__restrict__ outv, int ow, int oh, const __grid_constant__ llapfin_t P)
-{
-  __shared__ float tile[NL + 1][FT_H][FT_W + 1];
-  const int cx0 = blockIdx.x * 16 - 2, cy0 = blockIdx.y * 4 - 2;
-  const int tid = threadIdx.y * 32 + threadIdx.x;
-  const size_t p1 = (size_t)cw * ch;
-  const bool big = cw >= 24 && ch >= 12;
-  for(int t = tid; t < (NL + 1) * FT_H * FT_W; t += 256)
-  {
-    const int pl = t / (FT_H * FT_W), rem = t - pl * (FT_H * FT_W), r = rem / FT_W, c = rem - r * FT_W;
-    const int gx = big ? mirror1(cx0 + c, cw) : mirrori(cx0 + c, cw), gy = big ? mirror1(cy0 + r, ch) : mirrori(cy0 + r, ch);
-    const __half *src = pl < NL ? l1 + pl * p1 : (P.first ? l1 + NUM_GAMMA * p1 : coarse);
-    tile[pl][r][c] = __half2float(__ldg(src + (size_t)gy * cw + gx));
-  }
-  __syncthreads();
-  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-  if(x >= ow || y >= oh) return;
-  const float4 px = ld_rgba(in, ow, x, y);
-  const float grey = lum2020(clampf(px.x, -1000.0f, 1000.0f), clampf(px.y, -1000.0f, 1000.0f), clampf(px.z, -1000.0f, 1000.0f));
-  // separable sample_soft weights over texels k-2..k+2 (tile column lx-2..lx+2)
-  const int lx = (x >> 1) - cx0, ly = (y >> 1) - cy0;
-  const bool ox = x & 1, oy = y & 1;
-  const float wx[5] = { ox ? 0.0f : 0.5f, ox ? 1.0f : 0.5f, ox ? 0.5f : 1.0f, 0.5f, ox ? 1.0f : 0.5f };
-  const float wy[5] = { oy ? 0.0f : 0.5f, oy ? 1.0f : 0.5f, oy ? 0.5f : 1.0f, 0.5f, oy ? 1.0f : 0.5f };
-  const float v = f16r(grey);
-  int hi = 1;
-  for(; hi < NUM_GAMMA - 1 && gamma_from_i(hi) <= v; hi++);
-  const int lo = hi - 1;
-  float e[3];
-  const int planes[3] = { NL, lo, hi };
-#pragma unroll
-  for(int q = 0; q < 3; q++)
-  {
-    const float (*T)[FT_W + 1] = tile[planes[q]];
-    float acc = 0.0f;
-#pragma unroll
-    for(int r = 0; r < 5; r++)
-    {
-      const float *row = T[ly - 2 + r] + lx - 2;
-      const float h = row[0] * wx[0] + row[1] * wx[1] + row[2] * wx[2] + row[3] * wx[3] + row[4] * wx[4];
-      acc += h * wy[r];
-    }
-    e[q] = acc / 9.0f;
-  }
-  const float glo = gamma_from_i(lo), ghi = gamma_from_i(hi);
-  const float a = clampf((v - glo) / (ghi - glo), 0.0f, 1.0f);
-  const float lap0 = f16r(llap_curve(grey, glo, P.p)) - e[1];
-  const float lap1 = f16r(llap_curve(grey, ghi, P.p)) - e[2];
-  float l = f16r(e[0] + lap0 * (1.0f - a) + lap1 * a);
-  // llap/colour.comp:17-37
-  const float yo = fmaxf(lum2020(px.x, px.y, px.z), 1e-8f);
-  if(l < yo) l = yo * expf(1.0f * (l - yo));
-  f3 c = { fmaxf(0.0f, px.x * l / yo), fmaxf(0.0f, px.y * l / yo), fmaxf(0.0f, px.z * l / yo) };
-  if(GRADE)
-  {
-    c = { f16r(c.x), f16r(c.y), f16r(c.z) };
-    c = grade_px(c, P.grade);
-  }
-  if(F32) st_sink_f32(outv, ow, x, y, c.x, c.y, c.z, P.out_f32);
-  else st_rgba(reinterpret_cast<uint2 *>(outv), ow, x, y, make_float4(c.x, c.y, c.z, 1.0f));
 }
 
 // ---- 2x2 output pixels per thread ----
