@@ -147,9 +147,10 @@ __global__ void __launch_bounds__(256) k_hilite_assemble(const uint2 *__restrict
   const float sr = fine.x / fmaxf(0.001f, ur);
   const float sg = fine.y / fmaxf(0.001f, ug);
   const float sb = fine.z / fmaxf(0.001f, ub);
-  const float wr = expf(ur - fmaxf(ug, ub));
-  const float wg = expf(ug - fmaxf(ur, ub));
-  const float wb = expf(ub - fmaxf(ur, ug));
+  // blend weights, continuous: the SFU exponential (2 ulp) instead of the ~40 instruction libm one, three times per pixel
+  const float wr = exp_ftz(ur - fmaxf(ug, ub));
+  const float wg = exp_ftz(ug - fmaxf(ur, ub));
+  const float wb = exp_ftz(ub - fmaxf(ur, ug));
   const float scale = (sr * wr + sg * wg + sb * wb) / (wr + wg + wb);
   float t = p.soft;
   if(fine.x >= white || fine.y >= white || fine.z >= white) t = 1.0f;
