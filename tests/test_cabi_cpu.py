@@ -157,3 +157,32 @@ def test_plan_ipfm_source_and_onull_sink(tmp_path):
     g = api.Graph(cfg_text=cfg.replace(fn, mono), sink=None)
     # single channel ("Pf") files upload one float per pixel (the chain's kernels then refuse the 1-channel image at launch)
     assert "12x8x1x1:f32@" in g.plan()
+
+
+@pytest.mark.parametrize("crop,rot", [((0.25, 0.75, 0.25, 0.75), 0.0), ((0.1, 0.9, 0.2, 0.7), 0.0), ((0.0, 1.0, 0.0, 1.0), 90.0),
+                                      ((0.05, 0.95, 0.05, 0.95), 7.5), ((1.0, 3.0, 3.0, 7.0), 1337.0)])
+def test_crop_roi_follows_the_reference_arithmetic(oracle, crop, rot):
+    """the sink size falls out of crop's float math (crop/main.c:228-275): same numbers as the oracle's restatement for
+    explicit crop windows, a quarter turn, a free rotation and the magic defaults; paramsub edits one element."""
+    w, h = 1200, 802
+    g = api.Graph(cfg_text=api.DARKROOM_CFG.format(src="i-raw"))
+    assert g.line("param:crop:01:crop:%g:%g:%g:%g" % crop) == 0
+    assert g.line("param:crop:01:rotate:%g" % rot) == 0
+    raw = np.zeros((h, w), np.uint16)
+    g.set_source(raw.ctypes.data, api.raw_params(w, h))
+    g.set_sink_buffer(np.zeros(4, np.float32).ctypes.data, 0)
+    text = g.plan()
+    d = oracle.darkroom_defaults(w, h)
+    for k in range(4):
+        d.crop.crop[k] = crop[k]
+    d.crop.rotate = rot
+    ow, oh = oracle.darkroom_out_size(d)
+    assert "sink o-pfm %dx%d" % (ow, oh) in text, (ow, oh, [l for l in text.splitlines() if l.startswith("sink")])
+    if rot == 0.0:
+        assert g.line("paramsub:crop:01:crop:1:2:%g" % 0.5) == 0    # module:inst:param:beg:end:values: element 1 (right edge) only
+        d.crop.crop[1] = 0.5
+        ow2, oh2 = oracle.darkroom_out_size(d)
+        assert "sink o-pfm %dx%d" % (ow2, oh2) in g.plan() and oh2 == oh and ow2 != ow
+        assert g.line("param:crop:01:crop:0.5:0.5:0.2:0.7") == 0      # a window without area must not plan
+        with pytest.raises(api.VkbError):
+            g.plan()

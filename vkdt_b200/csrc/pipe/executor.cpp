@@ -384,6 +384,12 @@ static int build_plan(dt_graph_t *g, bool with_device)
       s.modid = modid; s.nodeid = n; s.buf = in.buf; s.wd = in.wd; s.ht = in.ht;
       s.bytes = (size_t)in.wd * in.ht * in.chan * (in.format == dt_token("f32") ? 4 : 2);
       s.rgb = 0;
+      if(in.buf >= 0 && (in.wd == 0 || in.ht == 0 || (uint64_t)in.wd * in.ht > (1ull << 32)))
+      { // e.g. a crop window with no area: the reference signals failure by an empty roi (graph-run-modules.h:652-666)
+        plan_free(p);
+        return vkb_set_error(VKB_ERR_GRAPH, "sink %s:%s would receive a %ux%u image", dt_token_string(nd->module->name).c_str(),
+            dt_token_string(nd->module->inst).c_str(), in.wd, in.ht);
+      }
       // packed rgb f32 (the PFM payload): asked for by the caller, or implied by o-pfm writing a file
       const vkb_mem_sink_t *msk = modid < (int)g->mem_sink.size() ? &g->mem_sink[modid] : 0;
       const bool to_file = !(msk && msk->valid) && nd->module->name == dt_token("o-pfm");
