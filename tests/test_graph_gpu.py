@@ -519,3 +519,22 @@ def test_cuda_graph_replay_matches_plain_launches(gpu):
     brighter = frame(raws[0], FR)
     assert brighter[..., :3].mean() > 1.2 * plain[0][..., :3].mean()
     assert np.array_equal(frame(raws[0], FR | gpu.RUN_PERF), brighter)
+
+
+@pytest.mark.parametrize("crop,rot", [((0.1, 0.9, 0.2, 0.7), 0.0), ((0.05, 0.95, 0.05, 0.95), 7.5), ((0.0, 1.0, 0.0, 1.0), 90.0)])
+def test_crop_window_and_rotation_end_to_end(gpu, oracle, crop, rot):
+    """non-default crop: an off-grid window (still an integer shift), a free rotation (catmull-rom resampling in the generic
+    pointwise kernel) and a quarter turn, through the whole graph."""
+    w, h = 640, 482
+    raw = synth.mosaic(w, h, seed=29)
+    d = _oracle_cfg(oracle, w, h)
+    for k in range(4):
+        d.crop.crop[k] = crop[k]
+    d.crop.rotate = rot
+    want = oracle.darkroom_run(d, raw)
+    got, g = _run_graph(gpu, raw, extra=("param:crop:01:crop:%g:%g:%g:%g" % crop, "param:crop:01:rotate:%g" % rot))
+    assert got.shape == want.shape
+    err = np.abs(got[..., :3] - want[..., :3])
+    p = psnr(got[..., :3], want[..., :3])
+    print("crop %s rot %g: %s max abs %.3g psnr %.1f" % (crop, rot, got.shape, err.max(), p))
+    assert p >= 60.0 and (err > 1e-3).mean() <= 1e-4 and err.max() <= 4e-3
