@@ -538,3 +538,59 @@ def test_crop_window_and_rotation_end_to_end(gpu, oracle, crop, rot):
     p = psnr(got[..., :3], want[..., :3])
     print("crop %s rot %g: %s max abs %.3g psnr %.1f" % (crop, rot, got.shape, err.max(), p))
     assert p >= 60.0 and (err > 1e-3).mean() <= 1e-4 and err.max() <= 4e-3
+
+
+def _set(obj, path, val):
+    *head, last = path.split(".")
+    for k in head:
+        obj = getattr(obj, k)
+    if isinstance(val, (tuple, list)):
+        arr = getattr(obj, last)
+        for i, v in enumerate(val):
+            arr[i] = v
+    else:
+        setattr(obj, last, val)
+
+
+VARIANTS = {
+    # name: ([cfg lines], [(oracle field, value)])
+    "exposure+sat":   (["param:colour:01:exposure:0.7", "param:colour:01:sat:1.3"], [("colour.exposure", 0.7), ("colour.sat", 1.3)]),
+    "filmcurv-perch": (["param:filmcurv:01:colour:1", "param:filmcurv:01:light:1.4", "param:filmcurv:01:contrast:1.2"],
+                       [("filmcurv.colour", 1), ("filmcurv.light", 1.4), ("filmcurv.contrast", 1.2)]),
+    "filmcurv-ucs":   (["param:filmcurv:01:colour:0"], [("filmcurv.colour", 0)]),
+    "filmcurv-agx":   (["param:filmcurv:01:colour:4"], [("filmcurv.colour", 4)]),
+    "filmcurv-oklab": (["param:filmcurv:01:colour:5", "param:filmcurv:01:bias:0.01"], [("filmcurv.colour", 5), ("filmcurv.bias", 0.01)]),
+    "llap-flat":      (["param:llap:01:clarity:0", "param:llap:01:shadows:0.8", "param:llap:01:hilights:1.2"],
+                       [("llap.clarity", 0.0), ("llap.shadows", 0.8), ("llap.hilights", 1.2)]),
+    "hilite":         (["param:hilite:01:white:0.9", "param:hilite:01:desat:0.6", "param:hilite:01:soft:0.2"],
+                       [("hilite.white", 0.9), ("hilite.desat", 0.6), ("hilite.soft", 0.2)]),
+    "demosaic-fixup": (["param:demosaic:01:colour:1"], [("demosaic.colour", 1)]),
+    "grade-cdl":      (["param:grade:01:lift:0.01:0:0.02:0", "param:grade:01:gamma:1.1:1:0.9:0", "param:grade:01:gain:1.05:1:0.95:0.02", "param:grade:01:offset:0:0.01:0:0"],
+                       [("grade.lift", (0.01, 0, 0.02, 0)), ("grade.gamma", (1.1, 1, 0.9, 0)), ("grade.gain", (1.05, 1, 0.95, 0.02)), ("grade.offset", (0, 0.01, 0, 0))]),
+    "grade-zones":    (["param:grade:01:mode:1", "param:grade:01:gain:1.1:1:1:0", "param:grade:01:lift:0.02:0:0:0"],
+                       [("grade.mode", 1), ("grade.gain", (1.1, 1, 1, 0)), ("grade.lift", (0.02, 0, 0, 0))]),
+    "denoise-knobs":  (["param:denoise:01:strength:0.8", "param:denoise:01:luma:0.3", "param:denoise:01:detail:0.5"],
+                       [("denoise.strength", 0.8), ("denoise.luma", 0.3), ("denoise.detail", 0.5)]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(VARIANTS))
+def test_parameter_variants_end_to_end(gpu, oracle, name):
+    """non-default parameters route through the kernels the default graph does not touch (generic pointwise chains, the
+    other tone curve colour modes, grade's zone mode, demosaic with the wider fix-up radius, llap without clarity)."""
+    lines, fields = VARIANTS[name]
+    w, h = 512, 384
+    raw = synth.mosaic(w, h, seed=37)
+    d = _oracle_cfg(oracle, w, h, noise=(100.0, 2.0))
+    for path, val in fields:
+        _set(d, path, val)
+    want = oracle.darkroom_run(d, raw)
+    got, g = _run_graph(gpu, raw, extra=tuple(lines), noise=(100.0, 2.0))
+    assert got.shape == want.shape and np.isfinite(got[..., :3]).all()
+    err = np.abs(got[..., :3] - want[..., :3])
+    p = psnr(got[..., :3], want[..., :3])
+    print("%s: max abs %.3g psnr %.1f, > 1e-3: %.2e" % (name, err.max(), p, (err > 1e-3).mean()))
+    # the oklab mode scales the pixel by a ratio of luminances (filmcurv/main.comp:150-166): next to black the ratio
+    # amplifies an input ulp a hundredfold at a handful of pixels
+    cap = 5e-2 if name == "filmcurv-oklab" else 4e-3
+    assert p >= 60.0 and (err > 1e-3).mean() <= 1e-4 and err.max() <= cap
