@@ -569,6 +569,10 @@ VARIANTS = {
                        [("grade.lift", (0.01, 0, 0.02, 0)), ("grade.gamma", (1.1, 1, 0.9, 0)), ("grade.gain", (1.05, 1, 0.95, 0.02)), ("grade.offset", (0, 0.01, 0, 0))]),
     "grade-zones":    (["param:grade:01:mode:1", "param:grade:01:gain:1.1:1:1:0", "param:grade:01:lift:0.02:0:0:0"],
                        [("grade.mode", 1), ("grade.gain", (1.1, 1, 1, 0)), ("grade.lift", (0.02, 0, 0, 0))]),
+    "colour-rbf":     (["param:colour:01:mode:1", "param:colour:01:cnt:4", "param:colour:01:rbmap:0.3333:0.3333:0.3333:0.3333:0.3333:0.3333:0.5:0.25:0.25:0.55:0.22:0.23:0.25:0.5:0.25:0.24:0.53:0.23:0.25:0.25:0.5:0.23:0.27:0.5"],
+                       [("colour.mode", 1), ("colour.cnt", 4), ("colour.rbmap", (0.3333, 0.3333, 0.3333, 0.3333, 0.3333, 0.3333, 0.5, 0.25, 0.25, 0.55, 0.22, 0.23, 0.25, 0.5, 0.25, 0.24, 0.53, 0.23, 0.25, 0.25, 0.5, 0.23, 0.27, 0.5))]),
+    "colour-rec709":  (["param:colour:01:matrix:3"], [("colour.matrix", 3)]),
+    "colour-clip":    (["param:colour:01:clip:1", "param:colour:01:clipmax:0.8"], [("colour.clip", 1), ("colour.clipmax", 0.8)]),
     "denoise-knobs":  (["param:denoise:01:strength:0.8", "param:denoise:01:luma:0.3", "param:denoise:01:detail:0.5"],
                        [("denoise.strength", 0.8), ("denoise.luma", 0.3), ("denoise.detail", 0.5)]),
 }
