@@ -72,6 +72,7 @@ int mlv_open(mlv_clip_t *c, const char *filename)
       fr.timestamp = rd64(b + 8);
       fr.frame_number = rd32(b + 16);
       const uint32_t space = rd32(b + 28);
+      if(space > bsize - 32) { pos += bsize; continue; } // frameSpace larger than the block: not a frame we can trust
       fr.payload_offset = pos + 32 + space;
       fr.payload_size = bsize - 32 - space;
       c->frames.push_back(fr);
@@ -80,6 +81,7 @@ int mlv_open(mlv_clip_t *c, const char *filename)
   }
   if(!have_mlvi || !have_rawi || c->frames.empty() || !c->width || !c->height) { fclose(f); c->frames.clear(); return 1; }
   c->lossless = (c->video_class & 0x20) != 0; // MLV_VIDEO_CLASS_FLAG_LJ92 (video_mlv.c:227)
+  if(c->lossless && (c->bpp < 8 || c->bpp > 16)) { fclose(f); c->frames.clear(); fprintf(stderr, "[i-mlv] implausible bit depth %u\n", c->bpp); return 1; }
   if(!c->lossless && c->bpp != 10 && c->bpp != 12 && c->bpp != 14) { fclose(f); c->frames.clear(); fprintf(stderr, "[i-mlv] unsupported bit depth %u\n", c->bpp); return 1; }
   std::stable_sort(c->frames.begin(), c->frames.end(), [](const mlv_frame_t &a, const mlv_frame_t &b) { return a.timestamp < b.timestamp; });
   if(c->frame_count == 0 || c->frame_count > c->frames.size()) c->frame_count = (uint32_t)c->frames.size();
