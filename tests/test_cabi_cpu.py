@@ -186,3 +186,15 @@ def test_crop_roi_follows_the_reference_arithmetic(oracle, crop, rot):
         assert g.line("param:crop:01:crop:0.5:0.5:0.2:0.7") == 0      # a window without area must not plan
         with pytest.raises(api.VkbError):
             g.plan()
+
+
+def test_cyclic_connections_are_an_error_not_a_hang():
+    cfg = ("module:i-raw:main\nmodule:crop:01\nmodule:colour:01\nmodule:filmcurv:01\nmodule:display:main\n"
+           "connect:i-raw:main:output:crop:01:input\nconnect:crop:01:output:colour:01:input\nconnect:colour:01:output:filmcurv:01:input\n"
+           "connect:filmcurv:01:output:colour:01:input\nconnect:filmcurv:01:output:display:main:input\n")
+    g = api.Graph(cfg_text=cfg)
+    raw = np.zeros((64, 96), np.uint16)
+    g.set_source(raw.ctypes.data, api.raw_params(96, 64))
+    with pytest.raises(api.VkbError) as e:
+        g.plan()
+    assert e.value.code == -6 and "sink" in str(e.value)

@@ -128,3 +128,36 @@ def test_parsers_under_address_and_ub_sanitizer(tmp_path):
         for k in range(0, len(files), 64):
             r = subprocess.run([exe, kind] + files[k:k + 64], capture_output=True, text=True, timeout=300)
             assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_config_grammar_survives_garbage():
+    """graph-io style lines with mangled tokens, counts and numbers: warnings or errors, never a crash; the graph still plans."""
+    rng = np.random.default_rng(9)
+    base = api.DARKROOM_CFG.format(src="i-raw").splitlines() + [
+        "param:crop:01:crop:0.1:0.9:0.1:0.9", "paramsub:crop:01:crop:1:2:0.5", "paraminc:colour:01:exposure:0:1:0.25",
+        "param:colour:01:rbmap:" + ":".join(["0.5"] * 144), "param:i-raw:main:filename:/nonexistent/file.dng", "frames:10", "fps:24"]
+    alphabet = list(b":0123456789.-+eE abcxyz\t#%\xff\x00")
+    g = api.Graph(cfg_text=api.DARKROOM_CFG.format(src="i-raw"))
+    for _ in range(4000):
+        line = bytearray(base[rng.integers(0, len(base))].encode())
+        for _ in range(rng.integers(1, 6)):
+            k = rng.integers(0, 4)
+            if k == 0 and line:
+                line[rng.integers(0, len(line))] = alphabet[rng.integers(0, len(alphabet))]
+            elif k == 1:
+                i = rng.integers(0, len(line) + 1)
+                line[i:i] = bytes(rng.choice(alphabet, rng.integers(1, 40)).tolist())
+            elif k == 2 and line:
+                del line[rng.integers(0, len(line)):]
+            else:
+                line += b":" + str(rng.integers(-2**40, 2**40)).encode()
+        api.lib.vkb_graph_read_config_line(g.h, bytes(line).replace(b"\x00", b"?"))
+    raw = np.zeros((64, 96), np.uint16)
+    g.set_source(raw.ctypes.data, api.raw_params(96, 64))
+    try:                      # whatever the mangled lines wired up (self loops, cycles, dangling inputs): an error or a plan
+        g.plan()
+    except api.VkbError:
+        pass
+    g2 = api.Graph(cfg_text=api.DARKROOM_CFG.format(src="i-raw"))
+    g2.set_source(raw.ctypes.data, api.raw_params(96, 64))
+    assert "sink o-pfm" in g2.plan()

@@ -704,7 +704,7 @@ int dt_graph_run_modules(dt_graph_t *g, std::vector<int> &modid)
 {
   modid.clear();
   traverse_post(g->module, [](const dt_module_t &m) { return m.inst == dt_token("main"); }, modid);
-  if(modid.empty()) return VKB_ERR_GRAPH;
+  if(modid.empty()) return vkb_set_error(VKB_ERR_GRAPH, "no module reaches a main sink (display:main / o-*:main): nothing to run, or the connections form a cycle");
   const int cnt = (int)modid.size();
   int main_input_module = -1;
   for(int i = 0; i < cnt; i++)
