@@ -198,3 +198,17 @@ def test_cyclic_connections_are_an_error_not_a_hang():
     with pytest.raises(api.VkbError) as e:
         g.plan()
     assert e.value.code == -6 and "sink" in str(e.value)
+
+
+def test_plan_from_mlv_files(tmp_path):
+    """the container reader on well-formed clips: uncompressed -> packed upload + device unpack, lossless -> u16 upload."""
+    from vkdt_b200 import synth
+    yy, xx = np.mgrid[0:66, 0:128]
+    pix = (2048 + 31 * xx + 17 * yy).astype(np.uint16)
+    for lossless, want in ((False, "packed 14"), (True, "packed 0")):
+        fn = str(tmp_path / ("l.mlv" if lossless else "u.mlv"))
+        synth.write_mlv(fn, [pix, pix, pix], bpp=14, lossless=lossless, camera_name="Canon EOS 5D Mark III")
+        g = api.Graph(cfg_text=api.DARKROOM_CFG.format(src="i-mlv"))
+        assert g.line("param:i-mlv:main:filename:%s" % fn) == 0
+        text = g.plan()
+        assert want in text and "sink o-pfm 128x66" in text, text[-300:]   # no micro-crop below 400 px (crop/main.c:194-224)
