@@ -212,3 +212,25 @@ def test_plan_from_mlv_files(tmp_path):
         assert g.line("param:i-mlv:main:filename:%s" % fn) == 0
         text = g.plan()
         assert want in text and "sink o-pfm 128x66" in text, text[-300:]   # no micro-crop below 400 px (crop/main.c:194-224)
+
+
+def test_cli_dump_nodes_without_a_gpu(tmp_path):
+    """`vkdt-b200-cli -g x.cfg --dump-nodes` (graph-print.h:76) only needs the host half: cfg file next to a dng, searchpath
+    resolution of the relative filename, node layer as graphviz."""
+    import os
+    import subprocess
+    from vkdt_b200 import synth
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "vkdt_b200", "vkdt-b200-cli")
+    if not os.path.exists(cli):
+        pytest.skip("cli not built")
+    synth.write_dng(str(tmp_path / "img.dng"), np.zeros((402, 600), np.uint16))
+    cfg = tmp_path / "img.dng.cfg"
+    cfg.write_text(api.DARKROOM_CFG.format(src="i-raw") + "param:i-raw:main:filename:img.dng\n")
+    r = subprocess.run([cli, "-g", str(cfg), "--dump-nodes"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.lstrip().startswith("digraph") and "hilite_reduce" in r.stdout and "llap_curve" in r.stdout and "o-pfm_main" in r.stdout
+    r = subprocess.run([cli, "-g", str(tmp_path / "missing.cfg"), "--dump-nodes"], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0
+    r = subprocess.run([cli, "--bogus"], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "usage" in r.stderr
