@@ -134,6 +134,11 @@ VKB_API int  vkb_graph_set_source(vkb_graph_t *g, const char *inst, const void *
  * reference's loader hands to the graph (i-raw/rawloader-c/lib.rs:137-279, i-raw/main.c:138-256) and the cfa offset of
  * the emitted window.  no GPU needed. */
 VKB_API int  vkb_dng_info(const char *filename, vkb_raw_params_t *p, uint32_t *cfa_off_x, uint32_t *cfa_off_y);
+/* the uniform block a module's commit_params() produces for the current graph (crop/main.c:277-345: 20 floats,
+ * colour/main.c:219-365: 242 floats; modules without commit_params: their raw parameter block): runs the host-side
+ * module passes like vkb_graph_plan, then commit_params of that module.  *size: bytes available in, bytes written out.
+ * no GPU needed; what the kernels are handed as `params`. */
+VKB_API int  vkb_graph_committed_params(vkb_graph_t *g, const char *module, const char *inst, void *out, size_t *size);
 /* the lossless jpeg (LJ92) decoder behind lossless MLV clips, replaces lj92_open + lj92_decode of the reference's vendored
  * liblj92 (i-mlv/video_mlv.c:236-250): headers into width/height/bits/components, and, when `out` is not NULL,
  * width*height*components samples in scan order into out[0..count).  host only, bit exact. */

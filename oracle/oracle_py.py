@@ -109,6 +109,54 @@ def ref_lib():
     return _ref
 
 
+_href = None
+
+
+def ref_host_lib():
+    """the HOST side of the reference's crop/main.c and colour/main.c, compiled in place by `make -C oracle ref`
+    (oracle/ref_crop_shim.c, ref_colour_shim.c); None when it was never built."""
+    global _href
+    if _href is None:
+        path = os.path.join(_HERE, "_ref", "libhostref.so")
+        if not os.path.exists(path):
+            return None
+        _href = C.CDLL(path)
+    return _href
+
+
+def ref_crop(orientation, in_w, in_h, perspect, crop, rotate):
+    """the reference's crop modify_roi_out + commit_params: (out_w, out_h, committed[20])."""
+    ow, oh, f = C.c_uint32(), C.c_uint32(), (C.c_float * 20)()
+    ref_host_lib().ref_crop(C.c_uint32(orientation), C.c_uint32(in_w), C.c_uint32(in_h), (C.c_float * 8)(*perspect), (C.c_float * 4)(*crop),
+                            C.c_float(rotate), C.byref(ow), C.byref(oh), f)
+    return ow.value, oh.value, np.array(list(f), dtype=np.float32)
+
+
+def crop_oracle(orientation, in_w, in_h, perspect, crop, rotate):
+    """the oracle's restatement of the same: (out_w, out_h, committed[20])."""
+    ow, oh, f = C.c_uint32(), C.c_uint32(), np.zeros(20, np.float32)
+    cr, rot = (C.c_float * 4)(*crop), C.c_float(rotate)
+    lib().o_crop_roi_out(C.c_uint32(orientation), C.c_uint32(in_w), C.c_uint32(in_h), cr, C.byref(rot), C.byref(ow), C.byref(oh))
+    lib().o_crop_commit(C.c_uint32(orientation), C.c_uint32(in_w), C.c_uint32(in_h), (C.c_float * 8)(*perspect), cr, C.byref(rot), fptr(f))
+    return ow.value, oh.value, f
+
+
+def ref_colour_commit(params_bytes, img_wb, cam_to_rec2020, primaries, trc):
+    """the reference's colour commit_params on a raw parameter block: (committed[242], white written back[4])."""
+    f, wbo = (C.c_float * 256)(), (C.c_float * 4)()
+    n = ref_host_lib().ref_colour_commit(params_bytes, C.c_uint32(len(params_bytes)), (C.c_float * 4)(*img_wb), (C.c_float * 9)(*cam_to_rec2020),
+                                         C.c_int(primaries), C.c_int(trc), wbo, f)
+    return np.array(list(f), dtype=np.float32)[:n], np.array(list(wbo), dtype=np.float32)
+
+
+def colour_commit_oracle(params_bytes, img_wb, cam_to_rec2020, primaries, trc):
+    p = ColourParams.from_buffer_copy(params_bytes)
+    pwb = (C.c_float * 4)(*[p.white[k] for k in range(4)])
+    f = np.zeros(256, np.float32)
+    lib().o_colour_commit(C.byref(p), pwb, (C.c_float * 4)(*img_wb), (C.c_float * 9)(*cam_to_rec2020), C.c_int(primaries), C.c_int(trc), fptr(f))
+    return f[:242], np.array(list(pwb), dtype=np.float32)
+
+
 def img(a):
     """wrap a float32 numpy array (h,w) or (h,w,4) as oimg_t (keeps a reference to the array)."""
     a = np.ascontiguousarray(a, dtype=np.float32)

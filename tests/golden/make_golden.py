@@ -95,6 +95,51 @@ def lj92_goldens():
     print("lj92 goldens:", len(streams), "streams + lossless clip", clip.size, "bytes")
 
 
+def host_goldens():
+    """crop and colour parameter blocks from the REFERENCE's own crop/main.c and colour/main.c (host side, compiled in place:
+    oracle/_ref/libhostref.so).  pins o_crop_roi_out / o_crop_commit / o_colour_commit and the product's module callbacks."""
+    assert O.ref_host_lib() is not None, "oracle/_ref/libhostref.so missing: run `make -C oracle ref` where /root/reference exists"
+    rng = np.random.default_rng(0xC0107)
+    crop_in, crop_out = [], []
+    for t in range(300):
+        w, h = int(rng.integers(20, 9000)), int(rng.integers(20, 9000))
+        ori = int(rng.choice([0, 1, 3, 6, 8]))
+        if t % 3 == 0:
+            crop = (1.0, 3.0, 3.0, 7.0)
+        else:
+            a, b = sorted(rng.random(2)); c, d = sorted(rng.random(2))
+            crop = (float(a), float(b) + 0.01, float(c), float(d) + 0.01)
+        rot = float(rng.choice([1337.0, 0.0, 90.0, 180.0, 270.0, float(rng.uniform(-30, 30))]))
+        persp = np.array([0.25, 0.25, 0.75, 0.25, 0.75, 0.75, 0.25, 0.75]) + (0 if t % 4 == 0 else rng.uniform(-0.05, 0.05, 8))
+        inp = np.array([ori, w, h, *persp, *crop, rot], dtype=np.float64)
+        ow, oh, f = O.ref_crop(ori, w, h, [float(np.float32(x)) for x in persp], crop, rot)
+        o2 = O.crop_oracle(ori, w, h, [float(np.float32(x)) for x in persp], crop, rot)
+        assert (ow, oh) == o2[:2] and np.array_equal(f.view(np.uint32), o2[2].view(np.uint32)), "oracle crop differs from the reference"
+        crop_in.append(inp); crop_out.append(np.concatenate([[ow, oh], f.astype(np.float64)]))
+    col_par, col_img, col_out = [], [], []
+    for t in range(120):
+        d = O.darkroom_defaults(64, 64)
+        p = d.colour
+        p.exposure = float(rng.uniform(-2, 2)); p.sat = float(rng.choice([1.0, rng.uniform(0, 2)]))
+        p.matrix = int(rng.choice([0, 1, 2, 3, 4, 5])); p.gamut = int(rng.integers(0, 3)); p.clip = int(rng.integers(0, 2)); p.clipmax = float(rng.uniform(0.5, 2))
+        p.temp = float(rng.choice([6504.0, 0.0, rng.uniform(2000, 10000)])); p.picked = int(rng.integers(0, 2))
+        for k in range(9): p.mat[k] = float(rng.uniform(-1, 1.5))
+        for k in range(4): p.white[k] = float(rng.choice([0.0, rng.uniform(0.2, 1.0)]))
+        p.mode = int(rng.integers(0, 2)); p.cnt = int(rng.integers(0, 25))
+        for k in range(144): p.rbmap[k] = float(rng.uniform(0.05, 0.9))
+        wb = [float(np.float32(rng.uniform(0.5, 3))), 1.0, float(np.float32(rng.uniform(0.5, 3))), 1.0]
+        cam = [float(np.float32(x)) for x in (np.eye(3) + rng.uniform(-0.3, 0.3, (3, 3))).ravel()]
+        prim, trc = (0, 0) if t < 80 else (int(rng.choice([1, 2, 3, 4, 5, 6, 7])), int(rng.choice([0, 1, 2, 3, 4, 5, 6])))
+        raw = bytes(p)
+        f, wbo = O.ref_colour_commit(raw, wb, cam, prim, trc)
+        f2, wbo2 = O.colour_commit_oracle(raw, wb, cam, prim, trc)
+        assert np.array_equal(np.nan_to_num(f, nan=-7.0), np.nan_to_num(f2, nan=-7.0)) and np.array_equal(wbo, wbo2), "oracle colour commit differs from the reference"
+        col_par.append(np.frombuffer(raw, np.uint8)); col_img.append(np.array(wb + cam + [prim, trc], np.float64)); col_out.append(np.concatenate([f, wbo]))
+    np.savez_compressed(os.path.join(HERE, "host_ref.npz"), crop_in=np.array(crop_in), crop_out=np.array(crop_out),
+                        colour_params=np.array(col_par), colour_img=np.array(col_img), colour_out=np.array(col_out, dtype=np.float32))
+    print("host goldens:", len(crop_in), "crop cases,", len(col_par), "colour cases")
+
+
 def darkroom_goldens():
     w, h = 168, 126
     raw = synth.mosaic(w, h, seed=77)
@@ -112,4 +157,5 @@ def darkroom_goldens():
 if __name__ == "__main__":
     mlv_goldens()
     lj92_goldens()
+    host_goldens()
     darkroom_goldens()

@@ -44,7 +44,7 @@ vkb_event_sync vkb_event_elapsed_ms vkb_event_destroy vkb_dispatch vkb_kernel_co
 vkb_kernel_name vkb_launch_count vkb_launch_count_reset vkb_graph_new vkb_graph_free vkb_graph_read_config_ascii
 vkb_graph_read_config_line vkb_graph_replace_display vkb_graph_set_source vkb_graph_set_sink_buffer
 vkb_graph_sink_size vkb_graph_set_frame vkb_graph_run vkb_graph_plan vkb_graph_perf vkb_graph_dump_nodes
-vkb_graph_set_source_device vkb_graph_sink_device vkb_graph_pool_bytes vkb_graph_stream vkb_graph_set_device vkb_dng_info vkb_graph_set_sink_layout vkb_lj92_decode""".split()
+vkb_graph_set_source_device vkb_graph_sink_device vkb_graph_pool_bytes vkb_graph_stream vkb_graph_set_device vkb_dng_info vkb_graph_set_sink_layout vkb_lj92_decode vkb_graph_committed_params""".split()
 
 
 def token(s):
@@ -117,6 +117,7 @@ lib.vkb_graph_stream.argtypes = [C.c_void_p]
 lib.vkb_graph_stream.restype = C.c_void_p
 lib.vkb_graph_set_device.argtypes = [C.c_void_p, C.c_int]
 lib.vkb_graph_set_sink_layout.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+lib.vkb_graph_committed_params.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p]
 lib.vkb_lj92_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 lib.vkb_dng_info.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
 lib.vkb_event_create.argtypes = [C.POINTER(C.c_void_p)]
@@ -232,6 +233,14 @@ class Graph:
     def set_sink_layout(self, layout, inst="main"):
         """SINK_RGBA_F32 (16 B/px, the reference's mapped sink buffer) or SINK_RGB_F32 (12 B/px, the PFM payload)."""
         check(lib.vkb_graph_set_sink_layout(self.h, inst.encode(), layout))
+
+    def committed_params(self, module, inst="01"):
+        """float32 view of the uniform block commit_params() of that module produces for the current graph (host only)."""
+        import numpy as np
+        buf = np.zeros(4096, dtype=np.uint8)
+        n = C.c_size_t(buf.nbytes)
+        check(lib.vkb_graph_committed_params(self.h, module.encode(), inst.encode(), buf.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return buf[:n.value].view(np.float32).copy()
 
     def set_frame(self, frame):
         check(lib.vkb_graph_set_frame(self.h, int(frame)))

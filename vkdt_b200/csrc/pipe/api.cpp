@@ -125,6 +125,23 @@ int vkb_graph_plan(vkb_graph_t *h, char *buf, size_t bufsize)
   if(buf && bufsize) snprintf(buf, bufsize, "%s", s.c_str());
   return VKB_OK;
 }
+int vkb_graph_committed_params(vkb_graph_t *h, const char *module, const char *inst, void *out, size_t *size)
+{
+  if(!h || !module || !inst || !out || !size) return VKB_ERR_BAD_ARG;
+  std::string s;
+  const int r = dt_graph_plan(h->g, &s); // module passes: roi + img_param of every module on the path
+  if(r) return r;
+  const int m = dt_module_get(h->g, dt_token(module), dt_token(inst));
+  if(m < 0) return vkb_set_error(VKB_ERR_BAD_ARG, "no module %s:%s", module, inst);
+  dt_module_t *mod = &h->g->module[m];
+  if(mod->so->commit_params) mod->so->commit_params(h->g, mod);
+  const uint8_t *src = mod->committed_param_size ? mod->committed_param : mod->param;
+  const size_t n = mod->committed_param_size ? (size_t)mod->committed_param_size : (size_t)mod->param_size;
+  if(*size < n) return vkb_set_error(VKB_ERR_BAD_ARG, "buffer too small: %zu < %zu", *size, n);
+  memcpy(out, src, n);
+  *size = n;
+  return VKB_OK;
+}
 void *vkb_graph_stream(vkb_graph_t *h) { return h ? vkb_plan_stream(h->g) : 0; }
 int vkb_dng_info(const char *filename, vkb_raw_params_t *p, uint32_t *ox, uint32_t *oy)
 {
