@@ -139,6 +139,11 @@ VKB_API int  vkb_dng_info(const char *filename, vkb_raw_params_t *p, uint32_t *c
  * module passes like vkb_graph_plan, then commit_params of that module.  *size: bytes available in, bytes written out.
  * no GPU needed; what the kernels are handed as `params`. */
 VKB_API int  vkb_graph_committed_params(vkb_graph_t *g, const char *module, const char *inst, void *out, size_t *size);
+/* the module and node layer as text: per module on the path its image parameters, parameter block and connectors, and every
+ * node its create_nodes() made (dispatch size, push constants, connector formats / sizes / wiring).  the detailed sibling of
+ * vkb_graph_dump_nodes (graph-print.h:76); oracle/ref_nodes_driver.h writes the same text from the reference's own
+ * <module>/main.c, which is how the tests pin the node graph.  runs the module passes only, no GPU needed. */
+VKB_API int  vkb_graph_describe(vkb_graph_t *g, char *buf, size_t bufsize);
 /* the lossless jpeg (LJ92) decoder behind lossless MLV clips, replaces lj92_open + lj92_decode of the reference's vendored
  * liblj92 (i-mlv/video_mlv.c:236-250): headers into width/height/bits/components, and, when `out` is not NULL,
  * width*height*components samples in scan order into out[0..count).  host only, bit exact. */

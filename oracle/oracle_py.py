@@ -239,3 +239,54 @@ def ref_mlv_decode(filename, frame=0):
     if r.ref_mlv_decode(filename.encode(), C.c_uint64(frame), out.ctypes.data_as(C.POINTER(C.c_uint16))):
         raise RuntimeError("reference mlv_get_frame failed")
     return out, dict(width=w, height=h, bpp=info[2], black=info[3], white=info[4], frames=info[5])
+
+
+class RefNodesIn(C.Structure):
+    _fields_ = [("in_full_wd", C.c_uint32), ("in_full_ht", C.c_uint32), ("filters", C.c_uint32), ("black", C.c_float * 4), ("white", C.c_float * 4),
+                ("wb", C.c_float * 4), ("crop_aabb", C.c_uint32 * 4), ("noise_a", C.c_float), ("noise_b", C.c_float), ("in_chan", C.c_char_p),
+                ("in_format", C.c_char_p), ("out_chan", C.c_char_p), ("out_format", C.c_char_p), ("out_marker", C.c_uint32), ("moddir", C.c_char_p), ("param", C.c_char_p), ("param_size", C.c_uint32)]
+
+
+def parse_described_modules(text):
+    """split the text of vkb_graph_describe / ref_nodes_* into {module name: block} (blocks keep their lines)."""
+    blocks, cur = {}, None
+    for ln in text.splitlines():
+        if ln.startswith("module "):
+            cur = ln.split()[1]
+            blocks[cur] = []
+        if cur is not None:
+            blocks[cur].append(ln)
+    return blocks
+
+
+def _img_fields(module_line):
+    """image parameters of a `module` line as the bits the reference harness takes."""
+    kv = dict(t.split("=") for t in module_line.split() if "=" in t)
+    f32 = lambda s: [float(np.array([int(x, 16)], np.uint32).view(np.float32)[0]) for x in s.split(",")]
+    return dict(filters=int(kv["filters"]), black=f32(kv["black"]), white=f32(kv["white"]), wb=f32(kv["wb"]), crop=[int(x) for x in kv["crop"].split(",")], noise=f32(kv["noise"]))
+
+
+def ref_nodes(module, prev_block, block, refdir="/root/reference", img_line=None):
+    """run the reference's own <module>/main.c (roi callbacks + create_nodes) on what the product's describe() says enters the
+    module: `prev_block` = lines of the module feeding it (image parameters, output connector), `block` = the module's own lines
+    (parameter block, negotiated output channels / format / request strength).  `img_line`: the image parameters the module
+    copies in its roi pass when they are not the feeding module's final ones (a reference `imgout` line).
+    returns (the reference's text for the module, its imgout line)."""
+    ip = _img_fields(img_line or prev_block[0])
+    prev_out = [ln.split() for ln in prev_block if ln.startswith(" mconn") and ln.split()[2].split(":")[1] in ("write", "source")][0]
+    _, _, pchan, pfmt = prev_out[2].split(":")
+    pfw, pfh = prev_out[3][4:].split("/")[0].split("x")
+    out = [ln.split() for ln in block if ln.startswith(" mconn") and ln.split()[2].startswith("output:")][0]
+    blob = bytes.fromhex([ln for ln in block if ln.startswith(" params")][0].split()[1] if len([ln for ln in block if ln.startswith(" params")][0].split()) > 1 else "")
+    a = RefNodesIn(int(pfw), int(pfh), ip["filters"], (C.c_float * 4)(*ip["black"]), (C.c_float * 4)(*ip["white"]), (C.c_float * 4)(*ip["wb"]),
+                   (C.c_uint32 * 4)(*ip["crop"]), ip["noise"][0], ip["noise"][1], pchan.encode(), pfmt.encode(), out[2].split(":")[2].encode(), out[2].split(":")[3].encode(), int(out[4][2:]),
+                   os.path.join(refdir, "src/pipe/modules", module).encode(), blob, len(blob))
+    buf = C.create_string_buffer(1 << 18)
+    fn = getattr(ref_host_lib(), "ref_nodes_" + module)
+    fn.restype = C.c_int
+    n = fn(C.byref(a), buf, len(buf))
+    assert n > 0, "ref_nodes_%s failed: %d" % (module, n)
+    text = buf.value.decode()
+    first, rest = text.split("\n", 1)
+    assert first.startswith("imgout ")
+    return rest, first

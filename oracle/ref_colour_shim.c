@@ -14,9 +14,9 @@
 #include <stdlib.h>
 #include <string.h>
 
-/* symbols create_nodes / write_sink of the module would bind to in a real vkdt: never reached from commit_params */
+/* a symbol write_sink of the module would bind to in a real vkdt: never reached from commit_params.
+ * (dt_node_connect comes from the reference's connector.c, linked into the same library) */
 qvk_t qvk;
-int dt_node_connect(dt_graph_t *graph, int n0, int c0, int n1, int c1) { return 0; }
 
 /* p: the module's parameter block in the order of colour/params (exposure sat picked matrix gamut clip clipmax temp
  * white[4] mat[9] mode cnt rbmap[144] import[8]) = o_colour_params_t.  clut / picked / abney / spectra unconnected. */

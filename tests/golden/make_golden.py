@@ -4,6 +4,8 @@
 
  - mlv_unpack_{10,12,14}.npz: seeded pixels packed into an MLV file and decoded by the REFERENCE's own
    video_mlv.c (oracle/_ref/libmlvref.so).  pins the oracle's o_mlv_unpack and the CUDA unpack kernel bit exactly.
+ - host_ref.npz: crop / colour parameter blocks from the REFERENCE's own crop/main.c and colour/main.c (oracle/_ref/libhostref.so).
+ - host_nodes.json.gz: node graphs of denoise / hilite / demosaic / llap / filmcurv from the REFERENCE's own create_nodes (same library).
  - darkroom_*.npz: outputs of the CPU oracle for the default darkroom graph on a small synthetic frame.  these pin
    the oracle against accidental edits (the float path has no reference-made vectors: parity unpinned).
 """
@@ -140,6 +142,59 @@ def host_goldens():
     print("host goldens:", len(crop_in), "crop cases,", len(col_par), "colour cases")
 
 
+NODE_CASES = [  # (cfg lines, width, height, raw parameters)
+    ([], 512, 384, {}),
+    (["param:denoise:01:strength:0.4"], 512, 384, dict(wb=(2.0, 1.0, 1.5), noise_a=100.0, noise_b=2.0)),
+    (["param:denoise:01:strength:0.4"], 516, 390, dict(filters=9, wb=(2.0, 1.0, 1.5), noise_a=100.0, noise_b=2.0)),
+    ([], 516, 390, dict(filters=9)),
+    (["param:demosaic:01:method:1"], 512, 384, {}),
+    (["param:demosaic:01:method:2"], 512, 384, {}),
+    (["param:demosaic:01:method:2"], 516, 390, dict(filters=9)),
+    (["param:denoise:01:strength:0.4"], 1030, 778, dict(crop_aabb=(8, 4, 1000, 700), black=1024.0, white=16000.0)),
+    ([], 1030, 778, dict(crop_aabb=(8, 4, 1000, 700), black=1024.0, white=16000.0)),
+    ([], 6000, 4000, {}),
+    (["param:denoise:01:strength:0.4", "param:demosaic:01:method:1"], 9504, 6336, dict(wb=(2.0, 1.0, 1.5))),
+    (["param:denoise:01:strength:0.4"], 6240, 4152, dict(filters=9, wb=(2.0, 1.0, 1.5))),
+    ([], 4096, 2160, dict(wb=(2.0, 1.0, 1.5))),
+    (["param:denoise:01:strength:0.4"], 16384, 12288, {}),
+    ([], 38, 26, {}),
+    (["param:denoise:01:strength:0.2"], 70, 50, {}),
+]
+NODE_MODULES = ("denoise", "hilite", "demosaic", "llap", "filmcurv")
+
+
+def reference_nodes(lines, w, h, kw):
+    """{module: text} from the REFERENCE's own create_nodes (oracle/_ref/libhostref.so) for the modules of the default darkroom
+    graph that build nodes, fed with what the product's vkb_graph_describe says enters each module."""
+    from vkdt_b200 import api
+    g = api.Graph(cfg_text=api.DARKROOM_CFG.format(src="i-raw"))
+    for ln in lines:
+        assert g.line(ln) == 0, ln
+    raw = np.zeros((h, w), np.uint16)
+    g.set_source(raw.ctypes.data, api.raw_params(w, h, **kw))
+    blocks = O.parse_described_modules(g.describe())
+    names, img, out = list(blocks), None, {}
+    for i, m in enumerate(names):
+        if m not in NODE_MODULES:
+            img = None
+            continue
+        out[m], img = O.ref_nodes(m, blocks[names[i - 1]], blocks[m], img_line=img)
+    return out
+
+
+def node_goldens():
+    """the node graphs of denoise / hilite / demosaic / llap / filmcurv as the REFERENCE's own <module>/main.c builds them (roi
+    callbacks + create_nodes compiled in place, oracle/ref_nodes_shim.c): node and kernel names, dispatch sizes, push constants,
+    connector channels / formats / sizes and the wiring.  pins the product's module callbacks (tests/test_host_ref_cpu.py)."""
+    import json
+    assert O.ref_host_lib() is not None, "oracle/_ref/libhostref.so missing: run `make -C oracle ref` where /root/reference exists"
+    cases = [dict(lines=ln, w=w, h=h, raw=kw, modules=reference_nodes(ln, w, h, kw)) for ln, w, h, kw in NODE_CASES]
+    import gzip
+    with gzip.GzipFile(os.path.join(HERE, "host_nodes.json.gz"), "wb", mtime=0) as f:
+        f.write(json.dumps(cases, indent=0).encode())
+    print("node goldens:", len(cases), "graphs,", sum(len(c["modules"]) for c in cases), "module node lists")
+
+
 def darkroom_goldens():
     w, h = 168, 126
     raw = synth.mosaic(w, h, seed=77)
@@ -158,4 +213,5 @@ if __name__ == "__main__":
     mlv_goldens()
     lj92_goldens()
     host_goldens()
+    node_goldens()
     darkroom_goldens()

@@ -7,6 +7,7 @@
 int vkb_plan_sink(dt_graph_t *g, int modid, uint32_t *wd, uint32_t *ht, void **dptr);
 uint64_t vkb_plan_pool_bytes(dt_graph_t *g);
 int dt_graph_plan(dt_graph_t *g, std::string *text);
+int dt_graph_run_modules(dt_graph_t *g, std::vector<int> &modid);
 void *vkb_plan_stream(dt_graph_t *g);
 
 struct vkb_graph_t { dt_graph_t *g; };
@@ -115,6 +116,17 @@ int vkb_graph_dump_nodes(vkb_graph_t *h, char *buf, size_t bufsize)
   const std::string s = dt_graph_dump_nodes(h->g);
   snprintf(buf, bufsize, "%s", s.c_str());
   return (int)s.size();
+}
+int vkb_graph_describe(vkb_graph_t *h, char *buf, size_t bufsize)
+{
+  if(!h || !buf || !bufsize) return VKB_ERR_BAD_ARG;
+  std::vector<int> modid;
+  const int r = dt_graph_run_modules(h->g, modid); // module passes only: roi out, roi in, create nodes
+  if(r) return r;
+  const std::string s = dt_graph_describe(h->g, modid);
+  if(s.size() + 1 > bufsize) return vkb_set_error(VKB_ERR_BAD_ARG, "buffer too small: %zu < %zu", bufsize, s.size() + 1);
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return VKB_OK;
 }
 int vkb_graph_plan(vkb_graph_t *h, char *buf, size_t bufsize)
 {

@@ -197,7 +197,8 @@ static int connect_generic(std::vector<T> &el, int m0, int c0, int m1, int c1)
   return 0;
 }
 int dt_module_connect(dt_graph_t *g, int m0, int c0, int m1, int c1) { return connect_generic<dt_module_t, true>(g->module, m0, c0, m1, c1); }
-// the node layer does not renegotiate formats: nodes declare what they read (connector.c node flavour)
+// the node layer (connector.c node flavour): wildcards on either side take the other side's channels / format
+// (connector.inc:94-106); a mismatch of declared formats is not an error here, nodes declare what they read
 int dt_node_connect(dt_graph_t *g, int n0, int c0, int n1, int c1)
 {
   if(n1 < 0 || n1 >= (int)g->node.size() || n0 < 0 || n0 >= (int)g->node.size()) return 1;
@@ -206,8 +207,17 @@ int dt_node_connect(dt_graph_t *g, int n0, int c0, int n1, int c1)
   dt_connector_t *cn1 = g->node[n1].connector + c1, *cn0 = g->node[n0].connector + c0;
   if(!dt_connector_input(cn1)) return 3;
   if(!dt_connector_output(cn0)) return 9;
+  if(cn1->chan == dt_token("*")) cn1->chan = cn0->chan;
+  if(cn0->chan == dt_token("*")) cn0->chan = cn1->chan;
+  if(cn1->chan == dt_token("*")) cn1->chan = dt_token("rgba");
+  if(cn0->chan == dt_token("*")) cn0->chan = dt_token("rgba");
+  if(cn1->format == dt_token("*")) cn1->format = cn0->format;
+  if(cn0->format == dt_token("*")) cn0->format = cn1->format;
+  if(cn1->format == dt_token("*")) cn1->format = dt_token("f16");
+  if(cn0->format == dt_token("*")) cn0->format = dt_token("f16");
   cn1->connected = dt_cid(n0, c0);
   cn1->associated = s_cid_unset;
+  cn0->associated = s_cid_unset;
   cn1->array_length = cn0->array_length;
   cn1->roi = cn0->roi;
   if(dt_connector_owner(cn0)) cn0->connected.i++;
@@ -789,5 +799,64 @@ std::string dt_graph_dump_nodes(dt_graph_t *g)
     }
   }
   s += "}\n";
+  return s;
+}
+
+// the module and node layer as text, one block per module on the path in execution order: image parameters as they leave
+// the module, its connectors, and every node it created with dispatch size, push constants and the connectors' formats,
+// sizes and wiring (node ids local to the module; "mod.c": copied from module connector c, "nK.c": node connection).
+// what create_nodes of the reference builds for the same module is written in the same form by oracle/ref_nodes_driver.h,
+// and tests/test_host_ref_cpu.py compares the two line by line.  also lists each module's parameter block.
+static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+std::string dt_graph_describe(dt_graph_t *g, const std::vector<int> &modid)
+{
+  std::string s;
+  char b[1024];
+  for(int mi : modid)
+  {
+    const dt_module_t *m = &g->module[mi];
+    const dt_image_params_t *ip = &m->img_param;
+    snprintf(b, sizeof(b), "module %s filters=%u black=%08x,%08x,%08x,%08x white=%08x,%08x,%08x,%08x wb=%08x,%08x,%08x,%08x crop=%u,%u,%u,%u noise=%08x,%08x\n",
+        dt_token_string(m->name).c_str(), ip->filters, f2u(ip->black[0]), f2u(ip->black[1]), f2u(ip->black[2]), f2u(ip->black[3]),
+        f2u(ip->white[0]), f2u(ip->white[1]), f2u(ip->white[2]), f2u(ip->white[3]),
+        f2u(ip->whitebalance[0]), f2u(ip->whitebalance[1]), f2u(ip->whitebalance[2]), f2u(ip->whitebalance[3]),
+        ip->crop_aabb[0], ip->crop_aabb[1], ip->crop_aabb[2], ip->crop_aabb[3], f2u(ip->noise_a), f2u(ip->noise_b));
+    s += b;
+    s += " params ";
+    for(int k = 0; k < m->param_size; k++) { snprintf(b, sizeof(b), "%02x", m->param[k]); s += b; }
+    s += "\n";
+    for(int i = 0; i < m->num_connectors; i++)
+    {
+      const dt_connector_t *c = m->connector + i;
+      snprintf(b, sizeof(b), " mconn %d %s:%s:%s:%s roi=%ux%u/%ux%u m=%u bypass=%d\n", i, dt_token_string(c->name).c_str(), dt_token_string(c->type).c_str(),
+          dt_token_string(c->chan).c_str(), dt_token_string(c->format).c_str(), c->roi.full_wd, c->roi.full_ht, c->roi.wd, c->roi.ht, c->roi.marker, dt_cid_unset(c->bypass) ? -1 : c->bypass.c);
+      s += b;
+    }
+    int first = -1;
+    for(size_t n = 0; n < g->node.size(); n++) if(g->node[n].module == m) { first = (int)n; break; }
+    for(size_t n = 0; n < g->node.size(); n++)
+    {
+      const dt_node_t *nd = &g->node[n];
+      if(nd->module != m) continue;
+      snprintf(b, sizeof(b), " node %d %s:%s %ux%ux%u pc=%d:", (int)n - first, dt_token_string(nd->name).c_str(), dt_token_string(nd->kernel).c_str(), nd->wd, nd->ht, nd->dp, (int)nd->push_constant_size);
+      s += b;
+      for(size_t k = 0; k < nd->push_constant_size / 4; k++) { uint32_t w; memcpy(&w, nd->push_constant + 4 * k, 4); snprintf(b, sizeof(b), "%s%08x", k ? "," : "", w); s += b; }
+      s += "\n";
+      for(int i = 0; i < nd->num_connectors; i++)
+      {
+        const dt_connector_t *c = nd->connector + i;
+        snprintf(b, sizeof(b), "  conn %d %s:%s:%s:%s roi=%ux%u/%ux%u al=%d ", i, dt_token_string(c->name).c_str(), dt_token_string(c->type).c_str(),
+            dt_token_string(c->chan).c_str(), dt_token_string(c->format).c_str(), c->roi.full_wd, c->roi.full_ht, c->roi.wd, c->roi.ht, c->array_length);
+        s += b;
+        const bool copied = !dt_cid_unset(c->associated) && (dt_connector_input(c) ||
+            (m->connector[c->associated.c].associated.i == (int)n && m->connector[c->associated.c].associated.c == i));
+        if(copied) snprintf(b, sizeof(b), "mod.%d\n", c->associated.c);
+        else if(dt_connector_input(c) && c->connected.i >= 0) snprintf(b, sizeof(b), "n%d.%d\n", c->connected.i - first, c->connected.c);
+        else if(dt_connector_input(c)) snprintf(b, sizeof(b), "open\n");
+        else snprintf(b, sizeof(b), "own\n");
+        s += b;
+      }
+    }
+  }
   return s;
 }

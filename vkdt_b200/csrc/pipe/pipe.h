@@ -218,6 +218,7 @@ int  dt_graph_replace_display(dt_graph_t *g, dt_token_t inst, dt_token_t mod);
 void dt_graph_disconnect_display_modules(dt_graph_t *g);
 int  dt_graph_run(dt_graph_t *g, uint32_t runflags);
 std::string dt_graph_dump_nodes(dt_graph_t *g);
+std::string dt_graph_describe(dt_graph_t *g, const std::vector<int> &modid);
 
 dt_module_so_t *dt_module_so_get(dt_token_t name);   // registry (global.c:442)
 
