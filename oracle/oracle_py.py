@@ -290,3 +290,19 @@ def ref_nodes(module, prev_block, block, refdir="/root/reference", img_line=None
     first, rest = text.split("\n", 1)
     assert first.startswith("imgout ")
     return rest, first
+
+
+def ref_graph_describe(w, h, lines=(), raw=None, sink="o-pfm", refdir="/root/reference", cfg="bin/default-darkroom.i-raw"):
+    """the reference's own module pass (config reader, dt_graph_replace_display, roi out / roi in / create nodes, commit_params;
+    oracle/ref_graph_shim.c) over one of its .cfg files with a w x h source: text in the form of vkb_graph_describe."""
+    raw = dict(raw or {})
+    wb = list(raw.get("wb", (1.0, 1.0, 1.0))) + [1.0]
+    crop = raw.get("crop_aabb") or (0, 0, w, h)
+    a = RefNodesIn(w, h, raw.get("filters", 0x5d5d5d5d), (C.c_float * 4)(*[raw.get("black", 2048.0)] * 4), (C.c_float * 4)(*[raw.get("white", 15000.0)] * 4),
+                   (C.c_float * 4)(*wb[:4]), (C.c_uint32 * 4)(*crop), raw.get("noise_a", 1.0), raw.get("noise_b", 1.0), b"", b"", b"", b"", 0, b"", b"", 0)
+    buf = C.create_string_buffer(1 << 21)
+    fn = ref_host_lib().ref_graph_describe
+    fn.restype = C.c_int
+    n = fn(os.path.join(refdir, "src/pipe").encode(), os.path.join(refdir, cfg).encode(), "\n".join(lines).encode(), sink.encode(), C.byref(a), buf, len(buf))
+    assert n > 0, "ref_graph_describe failed: %d" % n
+    return buf.value.decode()

@@ -78,6 +78,7 @@ static int ref_nodes_run(const char *name, const ref_nodes_in_t *in, ref_init_t 
   src->graph = graph; src->name = dt_token("i-src"); src->inst = dt_token("main");
   src->num_connectors = 1;
   src->connector[0] = (dt_connector_t){ .name = dt_token("output"), .type = dt_token("source"), .chan = dt_token(in->in_chan), .format = dt_token(in->in_format) };
+  src->connector[0].array_length = 1;
   src->connector[0].roi = (dt_roi_t){ .full_wd = in->in_full_wd, .full_ht = in->in_full_ht, .wd = in->in_full_wd, .ht = in->in_full_ht };
   for(int k = 0; k < 4; k++) { src->img_param.black[k] = in->black[k]; src->img_param.white[k] = in->white[k]; src->img_param.whitebalance[k] = in->wb[k]; src->img_param.crop_aabb[k] = in->crop_aabb[k]; }
   src->img_param.filters = in->filters; src->img_param.noise_a = in->noise_a; src->img_param.noise_b = in->noise_b;
@@ -92,7 +93,7 @@ static int ref_nodes_run(const char *name, const ref_nodes_in_t *in, ref_init_t 
     if(!tok[3]) continue;
     dt_connector_t *cn = mod->connector + mod->num_connectors++;
     *cn = (dt_connector_t){ .name = dt_token(tok[0]), .type = dt_token(tok[1]), .chan = dt_token(tok[2]), .format = dt_token(tok[3]) };
-    cn->connected = s_cid_unset; cn->associated = s_cid_unset; cn->bypass = s_cid_unset;
+    cn->connected = s_cid_unset; cn->associated = s_cid_unset; cn->bypass = s_cid_unset; cn->array_length = 1; /* module.c:73 */
     if(cn->type == dt_token("write")) cn->connected.i = cn->connected.c = 0;
   }
   fclose(f);

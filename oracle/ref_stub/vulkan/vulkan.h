@@ -21,3 +21,14 @@ typedef struct { char layerName[256]; uint32_t specVersion, implementationVersio
 typedef void (*PFN_vkCmdPushDescriptorSetKHR)(void);
 typedef struct { int dummy; } VkAccelerationStructureGeometryKHR;
 typedef struct { int dummy; } VkAccelerationStructureBuildGeometryInfoKHR;
+/* the module pass of the graph (graph-run-modules.h) builds a descriptor set layout and waits on a semaphore in between its
+ * host-side work: the types and constants those lines mention */
+#define VK_NULL_HANDLE 0
+#define VK_STRUCTURE_TYPE_SEMAPHORE_WAIT_INFO 1
+#define VK_STRUCTURE_TYPE_DESCRIPTOR_SET_LAYOUT_CREATE_INFO 2
+#define VK_SHADER_STAGE_ALL 0x7fffffff
+#define VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER 6
+#define VK_DESCRIPTOR_SET_LAYOUT_CREATE_UPDATE_AFTER_BIND_POOL_BIT 2
+typedef struct { uint32_t binding; int descriptorType; uint32_t descriptorCount; VkFlags stageFlags; const void *pImmutableSamplers; } VkDescriptorSetLayoutBinding;
+typedef struct { int sType; const void *pNext; VkFlags flags; uint32_t bindingCount; const VkDescriptorSetLayoutBinding *pBindings; } VkDescriptorSetLayoutCreateInfo;
+typedef struct { int sType; const void *pNext; VkFlags flags; uint32_t semaphoreCount; const VkSemaphore *pSemaphores; const uint64_t *pValues; } VkSemaphoreWaitInfo;

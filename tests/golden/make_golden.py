@@ -6,6 +6,8 @@
    video_mlv.c (oracle/_ref/libmlvref.so).  pins the oracle's o_mlv_unpack and the CUDA unpack kernel bit exactly.
  - host_ref.npz: crop / colour parameter blocks from the REFERENCE's own crop/main.c and colour/main.c (oracle/_ref/libhostref.so).
  - host_nodes.json.gz: node graphs of denoise / hilite / demosaic / llap / filmcurv from the REFERENCE's own create_nodes (same library).
+ - host_graph.json.gz: the whole module pass (config reader, roi negotiation, nodes, committed parameters) of the REFERENCE's own
+   graph code over its own default darkroom config (same library).
  - darkroom_*.npz: outputs of the CPU oracle for the default darkroom graph on a small synthetic frame.  these pin
    the oracle against accidental edits (the float path has no reference-made vectors: parity unpinned).
 """
@@ -195,6 +197,32 @@ def node_goldens():
     print("node goldens:", len(cases), "graphs,", sum(len(c["modules"]) for c in cases), "module node lists")
 
 
+GRAPH_CASES = NODE_CASES + [  # parameter lines travel through the reference's own config reader (graph-io.c) here
+    (["param:crop:01:rotate:7.5", "param:crop:01:crop:0.1:0.9:0.2:0.8"], 600, 400, {}),
+    (["param:crop:01:rotate:90"], 600, 400, dict(wb=(2.0, 1.0, 1.5))),
+    (["param:crop:01:perspect:0.2:0.25:0.8:0.2:0.75:0.8:0.25:0.75", "param:denoise:01:strength:0.3"], 804, 602, {}),
+    (["param:colour:01:exposure:0.75", "param:colour:01:sat:1.25", "param:colour:01:matrix:1", "param:colour:01:temp:4500"], 512, 384, dict(wb=(2.2, 1.0, 1.4))),
+    (["param:colour:01:matrix:2", "param:colour:01:mat:1.1:-0.05:-0.05:0.02:0.9:0.08:0.0:-0.1:1.1", "param:colour:01:clip:1"], 512, 384, dict(wb=(1.9, 1.0, 1.7))),
+    (["param:filmcurv:01:light:2.5", "param:filmcurv:01:contrast:1.4", "param:filmcurv:01:colour:1", "param:llap:01:clarity:0.5", "param:llap:01:sigma:0.2",
+      "param:grade:01:gain:1.1:1.0:0.9:1.0", "param:hilite:01:white:0.9", "param:denoise:01:luma:0.3", "param:demosaic:01:colour:1"], 516, 390, dict(filters=9)),
+]
+
+
+def graph_goldens():
+    """the module pass of the REFERENCE's own graph code over its own bin/default-darkroom.i-raw (oracle/ref_graph_shim.c: global.c,
+    module.c, graph-io.c, connector.c, graph-export.c, graph-run-modules.h and the seven module main.c files compiled in place; only
+    i-raw is a stand-in): every module on the path with image parameters, parameter block, connectors incl. negotiated sizes and
+    request strengths, nodes, push constants, wiring and the committed uniform blocks.  pins the product's config reader, roi
+    negotiation, module callbacks and commit_params (tests/test_host_ref_cpu.py)."""
+    import gzip
+    import json
+    assert O.ref_host_lib() is not None, "oracle/_ref/libhostref.so missing: run `make -C oracle ref` where /root/reference exists"
+    cases = [dict(lines=ln, w=w, h=h, raw=kw, text=O.ref_graph_describe(w, h, ln, kw)) for ln, w, h, kw in GRAPH_CASES]
+    with gzip.GzipFile(os.path.join(HERE, "host_graph.json.gz"), "wb", mtime=0) as f:
+        f.write(json.dumps(cases, indent=0).encode())
+    print("graph goldens:", len(cases), "graphs,", sum(c["text"].count("\n") for c in cases), "lines")
+
+
 def darkroom_goldens():
     w, h = 168, 126
     raw = synth.mosaic(w, h, seed=77)
@@ -214,4 +242,5 @@ if __name__ == "__main__":
     lj92_goldens()
     host_goldens()
     node_goldens()
+    graph_goldens()
     darkroom_goldens()

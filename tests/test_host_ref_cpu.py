@@ -214,3 +214,88 @@ def test_live_reference_nodes_random(oracle):
             if module == "filmcurv":
                 continue
             assert _documented_deviations(module, _blocks(text)[module], case) == mine[module], (case, module)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the whole module pass: config reader, display replacement, roi out / roi in negotiation (sizes AND request strengths),
+# create_nodes of every module, repointing through the module layer and commit_params, against the REFERENCE's own graph code
+# run over its own bin/default-darkroom.i-raw (tests/golden/host_graph.json.gz, oracle/ref_graph_shim.c)
+GRAPHS = json.loads(gzip.open(os.path.join(os.path.dirname(__file__), "golden", "host_graph.json.gz")).read())
+
+
+def _graph_text_product(case):
+    g = api.Graph(cfg_text=api.DARKROOM_CFG.format(src="i-raw"))
+    assert g.line("param:i-raw:main:filename:none.raw") == 0   # the last line of the reference's default-darkroom.i-raw
+    for ln in case["lines"]:
+        assert g.line(ln) == 0, ln
+    buf = np.zeros((case["h"], case["w"]), np.uint16)
+    kw = dict(case["raw"])
+    for k in ("wb", "crop_aabb"):
+        if k in kw:
+            kw[k] = tuple(kw[k])
+    g.set_source(buf.ctypes.data, api.raw_params(case["w"], case["h"], **kw))
+    return g.describe().splitlines()
+
+
+def _graph_text_reference(case, text):
+    """the reference's text with the four documented deviations applied (see _documented_deviations)"""
+    lines, out, skip, module = text.splitlines(), [], False, ""
+    for ln in lines:
+        if ln.startswith("module "):
+            module, skip = ln.split()[1], False
+        if ln.startswith(" node "):
+            skip = module == "filmcurv" and ln.split()[2] in ("OpenDRT:hist", "filmcurv:dspy")
+            if module == "filmcurv" and ln.split()[2] == "filmcurv:main":
+                ln = re.sub(r"^ node \d+", " node 0", ln)
+        elif not ln.startswith("  conn "):
+            skip = False
+        if not skip:
+            out.append(ln)
+    fixed, start = [], 0
+    for i in range(len(out) + 1):   # per module, for the rewrites that need to know the node
+        if i == len(out) or (out[i].startswith("module ") and i > start):
+            fixed += _documented_deviations(out[start].split()[1], out[start:i], case)
+            start = i
+    return fixed
+
+
+def test_product_module_pass_matches_reference_graph_code():
+    for case in GRAPHS:
+        ref = _graph_text_reference(case, case["text"])
+        got = _graph_text_product(case)
+        assert len(ref) == len(got), (case["lines"], case["w"], case["h"], len(ref), len(got))
+        bad = [(a[:200], b[:200]) for a, b in zip(ref, got) if a != b]
+        assert not bad, (case["lines"], case["w"], case["h"], bad[:3])
+    assert len(GRAPHS) >= 20
+
+
+def test_live_reference_graph_random(oracle):
+    """the same on random sizes and parameters against the compiled reference, where it exists (the build container)."""
+    if oracle.ref_host_lib() is None or not hasattr(oracle.ref_host_lib(), "ref_graph_describe") or not os.path.isdir("/root/reference/src/pipe/modules"):
+        pytest.skip("oracle/_ref/libhostref.so or /root/reference not present")
+    rng = np.random.default_rng(1017)
+    for t in range(30):
+        xtrans = t % 3 == 2
+        blk = 6 if xtrans else 2
+        w, h = int(rng.integers(6, 900)) * blk, int(rng.integers(6, 600)) * blk
+        lines = []
+        if t % 2:
+            lines.append("param:denoise:01:strength:%g" % rng.uniform(0.05, 1.0))
+        if not xtrans and t % 4 == 0:
+            lines.append("param:demosaic:01:method:%d" % rng.integers(1, 3))
+        if t % 5 == 1:
+            lines.append("param:crop:01:rotate:%g" % rng.choice([0.0, 90.0, 180.0, 270.0, rng.uniform(-20, 20)]))
+        if t % 5 == 3:
+            a, b = sorted(rng.uniform(0, 1, 2)); c, d = sorted(rng.uniform(0, 1, 2))
+            lines.append("param:crop:01:crop:%g:%g:%g:%g" % (a, b + 0.05, c, d + 0.05))
+        if t % 7 == 2:
+            lines += ["param:colour:01:exposure:%g" % rng.uniform(-2, 2), "param:colour:01:matrix:%d" % rng.integers(0, 3), "param:colour:01:temp:%g" % rng.uniform(2500, 9000)]
+        raw = dict(black=float(rng.integers(0, 4096)), white=float(rng.integers(8000, 65535)), wb=(float(rng.uniform(1, 3)), 1.0, float(rng.uniform(1, 3))),
+                   noise_a=float(rng.uniform(0.1, 200)), noise_b=float(rng.uniform(0.1, 4)))
+        if xtrans:
+            raw["filters"] = 9
+        case = dict(lines=lines, w=w, h=h, raw=raw)
+        ref = _graph_text_reference(case, oracle.ref_graph_describe(w, h, lines, raw))
+        got = _graph_text_product(case)
+        bad = [(a[:200], b[:200]) for a, b in zip(ref, got) if a != b]
+        assert len(ref) == len(got) and not bad, (case, len(ref), len(got), bad[:3])

@@ -116,7 +116,7 @@ int dt_module_add(dt_graph_t *g, dt_token_t name, dt_token_t inst)
   memset(mod, 0, sizeof(*mod));
   mod->so = so; mod->name = name; mod->inst = inst; mod->graph = g;
   mod->num_connectors = (int)so->connector.size();
-  for(int c = 0; c < mod->num_connectors; c++) mod->connector[c] = so->connector[c];
+  for(int c = 0; c < mod->num_connectors; c++) { mod->connector[c] = so->connector[c]; mod->connector[c].array_length = 1; } // module.c:73
   int psize = 0;
   for(const dt_ui_param_t &p : so->param) psize += (int)p.def.size();
   mod->param = g->params_pool.data() + g->params_end;
@@ -856,6 +856,14 @@ std::string dt_graph_describe(dt_graph_t *g, const std::vector<int> &modid)
         else snprintf(b, sizeof(b), "own\n");
         s += b;
       }
+    }
+    if(m->so->commit_params && m->committed_param_size)
+    { // the uniform block the kernels of this module are handed
+      dt_module_t *mw = &g->module[mi];
+      mw->so->commit_params(g, mw);
+      s += " committed ";
+      for(int k = 0; k < mw->committed_param_size; k++) { snprintf(b, sizeof(b), "%02x", mw->committed_param[k]); s += b; }
+      s += "\n";
     }
   }
   return s;
