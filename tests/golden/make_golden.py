@@ -208,6 +208,22 @@ GRAPH_CASES = NODE_CASES + [  # parameter lines travel through the reference's o
 ]
 
 
+MLV_CLIPS = {  # name: (width, height, bits, black, white, camera name in IDNT or None); cameras outside dcraw's adobe_coeff table
+    "plain14": (512, 384, 14, 2048, 15000, None),
+    "named12": (328, 246, 12, 512, 3900, "Synth Cam One"),
+}
+MLV_DIR = "/tmp/vkdt_b200_golden"   # the file name is part of i-mlv's parameter block: the tests write the clips to the same place
+
+
+def write_golden_clip(name):
+    w, h, bpp, black, white, camera = MLV_CLIPS[name]
+    os.makedirs(MLV_DIR, exist_ok=True)
+    fn = os.path.join(MLV_DIR, name + ".mlv")
+    pix = (synth.mosaic(w, h, seed=5) >> (14 - bpp)).astype(np.uint16)
+    synth.write_mlv(fn, [pix, pix[::-1].copy()], bpp=bpp, black=black, white=white, camera_name=camera)
+    return fn
+
+
 def graph_goldens():
     """the module pass of the REFERENCE's own graph code over its own bin/default-darkroom.i-raw (oracle/ref_graph_shim.c: global.c,
     module.c, graph-io.c, connector.c, graph-export.c, graph-run-modules.h and the seven module main.c files compiled in place; only
@@ -218,6 +234,11 @@ def graph_goldens():
     import json
     assert O.ref_host_lib() is not None, "oracle/_ref/libhostref.so missing: run `make -C oracle ref` where /root/reference exists"
     cases = [dict(lines=ln, w=w, h=h, raw=kw, text=O.ref_graph_describe(w, h, ln, kw)) for ln, w, h, kw in GRAPH_CASES]
+    # bin/default-darkroom.i-mlv with the reference's own i-mlv/main.c reading a clip: header -> image parameters -> colour's block
+    for name, (w, h, bpp, black, white, camera) in MLV_CLIPS.items():
+        fn = write_golden_clip(name)
+        lines = ["param:i-mlv:main:filename:" + fn] + (["param:denoise:01:strength:0.3"] if bpp == 12 else [])
+        cases.append(dict(lines=lines, w=w, h=h, raw={}, mlv=name, text=O.ref_graph_describe(w, h, lines, {}, cfg="bin/default-darkroom.i-mlv")))
     with gzip.GzipFile(os.path.join(HERE, "host_graph.json.gz"), "wb", mtime=0) as f:
         f.write(json.dumps(cases, indent=0).encode())
     print("graph goldens:", len(cases), "graphs,", sum(c["text"].count("\n") for c in cases), "lines")

@@ -12,6 +12,7 @@ pytestmark = pytest.mark.gpu
 
 WB = (2.0, 1.0, 1.5)
 CAM = (0.8, 0.15, 0.05, 0.1, 0.85, 0.05, 0.02, 0.18, 0.8)
+XYZ_TO_REC2020 = (1.7166511880, -0.3556707838, -0.2533662814, -0.6666843518, 1.6164812366, 0.0157685458, 0.0176398574, -0.0427706133, 0.9421031212)
 
 
 def _oracle_cfg(O, w, h, llap=True, grade=True, strength=0.0, noise=(1.0, 1.0)):
@@ -129,11 +130,15 @@ def test_imlv_file_source_and_cli(gpu, oracle, tmp_path):
         dims = data.split(b"\n")[1].split()
         ow, oh = int(dims[0]), int(dims[1])
         got = np.frombuffer(data[hdr_end:], dtype=np.float32).reshape(oh, ow, 3)
-        d = oracle.darkroom_defaults(w, h)          # i-mlv without IDNT: identity matrix, wb 1, noise 1/1 (i-mlv/main.c:119-141)
+        d = oracle.darkroom_defaults(w, h)          # i-mlv without IDNT: wb 1, noise 1/1 (i-mlv/main.c:119-141) and, for a camera that is
+        for k, v in enumerate(XYZ_TO_REC2020):      # not in the adobe table, camera rgb = xyz: cam_to_rec2020 = xyz_to_rec2020 (:165-201;
+            d.cam_to_rec2020[k] = v                 # pinned against the reference's own i-mlv/main.c in tests/test_host_ref_cpu.py)
         want = oracle.darkroom_run(d, frames[f])
         assert want.shape[:2] == (oh, ow)
         err = np.abs(got - want[..., :3])
-        assert psnr(got, want[..., :3]) >= 60.0 and err.max() <= 2e-3 and (err > 1e-3).mean() <= 1e-5, (f, err.max())
+        # gate of the full size configs: the xyz matrix drives some channels negative, where the tone curve's
+        # hue preserving ratio amplifies an f16 flip more than with the mild matrices of the other tests
+        assert psnr(got, want[..., :3]) >= 60.0 and err.max() <= 1e-2 and (err > 1e-3).mean() <= 1e-5, (f, err.max())
 
 
 @pytest.mark.parametrize("strength", [0.0, 0.4])

@@ -189,11 +189,7 @@ def test_live_reference_nodes_random(oracle):
     """the same comparison on random sizes / levels against the compiled reference, where it exists (the build container)."""
     if oracle.ref_host_lib() is None or not hasattr(oracle.ref_host_lib(), "ref_nodes_llap") or not os.path.isdir("/root/reference/src/pipe/modules"):
         pytest.skip("oracle/_ref/libhostref.so or /root/reference not present")
-    sys_path_golden = os.path.join(os.path.dirname(__file__), "golden")
-    import importlib.util
-    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(sys_path_golden, "make_golden.py"))
-    mg = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mg)
+    mg = _make_golden_module()
     rng = np.random.default_rng(20261017)
     for t in range(24):
         xtrans = t % 3 == 2
@@ -223,7 +219,27 @@ def test_live_reference_nodes_random(oracle):
 GRAPHS = json.loads(gzip.open(os.path.join(os.path.dirname(__file__), "golden", "host_graph.json.gz")).read())
 
 
+def _make_golden_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    return mg
+
+
+# the reference's bin/default-darkroom.i-mlv ends in llap (no grade): llap feeds the display and the histogram
+MLV_CFG = api.DARKROOM_CFG.format(src="i-mlv").replace("connect:llap:01:output:grade:01:input\n", "") \
+    .replace("connect:grade:01:output:display:main:input", "connect:llap:01:output:display:main:input") \
+    .replace("connect:grade:01:output:hist:01:input", "connect:llap:01:output:hist:01:input")
+
+
 def _graph_text_product(case):
+    if "mlv" in case:
+        _make_golden_module().write_golden_clip(case["mlv"])     # same pixels, same path as when the golden was made
+        g = api.Graph(cfg_text=MLV_CFG)
+        for ln in case["lines"]:
+            assert g.line(ln) == 0, ln
+        return g.describe().splitlines()
     g = api.Graph(cfg_text=api.DARKROOM_CFG.format(src="i-raw"))
     assert g.line("param:i-raw:main:filename:none.raw") == 0   # the last line of the reference's default-darkroom.i-raw
     for ln in case["lines"]:
@@ -266,7 +282,7 @@ def test_product_module_pass_matches_reference_graph_code():
         assert len(ref) == len(got), (case["lines"], case["w"], case["h"], len(ref), len(got))
         bad = [(a[:200], b[:200]) for a, b in zip(ref, got) if a != b]
         assert not bad, (case["lines"], case["w"], case["h"], bad[:3])
-    assert len(GRAPHS) >= 20
+    assert len(GRAPHS) >= 24 and sum("mlv" in c for c in GRAPHS) == 2
 
 
 def test_live_reference_graph_random(oracle):

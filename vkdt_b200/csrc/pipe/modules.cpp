@@ -413,8 +413,17 @@ static void imlv_roi_out(dt_graph_t *g, dt_module_t *mod)
   for(int k = 0; k < 4; k++) { ip->black[k] = b; ip->white[k] = w; ip->whitebalance[k] = 1.0f; }
   ip->filters = 0x5d5d5d5d; // i-mlv/main.c:127
   ip->crop_aabb[2] = c->width; ip->crop_aabb[3] = c->height;
-  ip->cam_to_rec2020[0] = ip->cam_to_rec2020[4] = ip->cam_to_rec2020[8] = 1.0f;
-  ip->noise_a = 1.0f; ip->noise_b = 1.0f; // :140-141; nprof lookup and adobe matrix table are outside the hot path
+  // :165-201: camera rgb -> xyz comes from dcraw's adobe_coeff table by camera name; a camera that is not in it gets the
+  // identity there, and the matrix handed on is xyz_to_rec2020 * identity (white balance 1: the row sums of the identity).
+  // the table itself is not built here, so every clip takes that branch (a named camera is told so once).
+  static const float xyz_to_rec2020[9] = {
+     1.7166511880f, -0.3556707838f, -0.2533662814f,
+    -0.6666843518f,  1.6164812366f,  0.0157685458f,
+     0.0176398574f, -0.0427706133f,  0.9421031212f };
+  for(int k = 0; k < 9; k++) ip->cam_to_rec2020[k] = xyz_to_rec2020[k];
+  static int told = 0;
+  if(c->camera_name[0] && !told++) fprintf(stderr, "[i-mlv] no colour matrix table: `%s' is developed with camera rgb = xyz\n", c->camera_name);
+  ip->noise_a = 1.0f; ip->noise_b = 1.0f; // :140-141; the nprof lookup is outside the hot path
   snprintf(ip->model, sizeof(ip->model), "%s", c->camera_name);
   snprintf(ip->maker, sizeof(ip->maker), "%s", c->camera_name);
   for(size_t i = 0; i < sizeof(ip->maker); i++) if(ip->maker[i] == ' ') ip->maker[i] = 0;
