@@ -144,6 +144,9 @@ VKB_API int  vkb_graph_committed_params(vkb_graph_t *g, const char *module, cons
  * vkb_graph_dump_nodes (graph-print.h:76); oracle/ref_nodes_driver.h writes the same text from the reference's own
  * <module>/main.c, which is how the tests pin the node graph.  runs the module passes only, no GPU needed. */
 VKB_API int  vkb_graph_describe(vkb_graph_t *g, char *buf, size_t bufsize);
+/* what the config lines read so far amount to (graph-io.c:232-315): "frames N", then one line per module in the order of
+ * creation, "<name>:<inst> <parameter block, hex> <input connector><<module>.<connector> ...".  host only. */
+VKB_API int  vkb_graph_state(vkb_graph_t *g, char *buf, size_t bufsize);
 /* the lossless jpeg (LJ92) decoder behind lossless MLV clips, replaces lj92_open + lj92_decode of the reference's vendored
  * liblj92 (i-mlv/video_mlv.c:236-250): headers into width/height/bits/components, and, when `out` is not NULL,
  * width*height*components samples in scan order into out[0..count).  host only, bit exact. */

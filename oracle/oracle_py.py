@@ -306,3 +306,14 @@ def ref_graph_describe(w, h, lines=(), raw=None, sink="o-pfm", refdir="/root/ref
     n = fn(os.path.join(refdir, "src/pipe").encode(), os.path.join(refdir, cfg).encode(), "\n".join(lines).encode(), sink.encode(), C.byref(a), buf, len(buf))
     assert n > 0, "ref_graph_describe failed: %d" % n
     return buf.value.decode()
+
+
+def ref_config_lines(lines, refdir="/root/reference", cfg="bin/default-darkroom.i-raw"):
+    """return codes of the reference's dt_graph_read_config_line for each line on top of `cfg`, and the resulting state text."""
+    codes = (C.c_int * max(1, len(lines)))()
+    buf = C.create_string_buffer(1 << 20)
+    fn = ref_host_lib().ref_config_lines
+    fn.restype = C.c_int
+    n = fn(os.path.join(refdir, "src/pipe").encode(), os.path.join(refdir, cfg).encode(), "\n".join(lines).encode(), codes, len(lines), buf, len(buf))
+    assert n == len(lines), "ref_config_lines failed: %d" % n
+    return list(codes)[:n], buf.value.decode()

@@ -66,10 +66,7 @@ static dt_module_so_t *so_get(const char *name)
   return 0;
 }
 
-/* cfgfile: a .cfg of the reference (bin/default-darkroom.i-raw); extra: more config lines, '\n' separated (may be 0);
- * basedir: <reference>/src/pipe (holds modules/); sink: module the display is replaced by, e.g. "o-pfm".
- * writes one block per module on the path, execution order.  returns bytes written, < 0 on failure. */
-int ref_graph_describe(const char *basedir, const char *cfgfile, const char *extra, const char *sink, const ref_nodes_in_t *in, char *out, int outsize)
+static int ref_pipe_init(const char *basedir)
 {
   static int inited = 0;
   if(!inited)
@@ -97,6 +94,15 @@ int ref_graph_describe(const char *basedir, const char *cfgfile, const char *ext
     { dt_module_so_t *so = so_get("i-mlv"); if(!so) return -10; so->init = imlv_ref_init; so->cleanup = imlv_ref_cleanup; so->modify_roi_out = imlv_ref_modify_roi_out; }
     inited = 1;
   }
+  return 0;
+}
+
+/* cfgfile: a .cfg of the reference (bin/default-darkroom.i-raw); extra: more config lines, '\n' separated (may be 0);
+ * basedir: <reference>/src/pipe (holds modules/); sink: module the display is replaced by, e.g. "o-pfm".
+ * writes one block per module on the path, execution order.  returns bytes written, < 0 on failure. */
+int ref_graph_describe(const char *basedir, const char *cfgfile, const char *extra, const char *sink, const ref_nodes_in_t *in, char *out, int outsize)
+{
+  { const int r = ref_pipe_init(basedir); if(r) return r; }
   ref_src = in;
   /* dt_graph_init (graph.c:34-56) without the device objects */
   dt_graph_t *g = calloc(1, sizeof(*g));
@@ -198,4 +204,54 @@ done:
   for(uint32_t m = 0; m < g->num_modules; m++) if(g->module[m].name && g->module[m].so && g->module[m].so->cleanup) g->module[m].so->cleanup(g->module + m);
   free(g->conn_image_pool); free(g->params_pool); free(g->node); free(g->module); free(g);
   return ret;
+}
+
+/* the reference's config grammar (graph-io.c:232-252 and the readers above it) line by line on top of a loaded .cfg: return
+ * code of dt_graph_read_config_line per line (0 ok, > 0 warning, < 0 fatal) into codes[], and afterwards frame count and the
+ * parameter block of every module as text ("<name>:<inst> <hex>"), so that what a line DID can be compared too. */
+int ref_config_lines(const char *basedir, const char *cfgfile, const char *lines, int *codes, int maxcodes, char *out, int outsize)
+{
+  { const int r = ref_pipe_init(basedir); if(r) return r; }
+  dt_graph_t *g = calloc(1, sizeof(*g));
+  g->frame_cnt = 1;
+  g->max_modules = 100; g->module = calloc(sizeof(dt_module_t), g->max_modules);
+  g->max_nodes = 16;    g->node = calloc(sizeof(dt_node_t), g->max_nodes);
+  g->params_max = 16u << 20; g->params_pool = calloc(1, g->params_max);
+  int n = -20;
+  if(!dt_graph_read_config_ascii(g, cfgfile))
+  {
+    n = 0;
+    char *copy = strdup(lines), *c = copy;
+    while(c && *c && n < maxcodes)
+    {
+      char *e = strchr(c, '\n'); if(e) *e++ = 0;
+      static char line[300000];
+      snprintf(line, sizeof(line), "%s", c);
+      codes[n++] = dt_graph_read_config_line(g, line);
+      c = e;
+    }
+    free(copy);
+    char *o = out; int left = outsize; char b0[9], b1[9];
+    ref_out(&o, &left, "frames %u\n", g->frame_cnt);
+    for(uint32_t m = 0; m < g->num_modules; m++)
+    {
+      dt_module_t *mod = g->module + m;
+      if(!mod->name) continue;
+      for(int p = 0; p < mod->so->num_params; p++) if(mod->so->param[p]->type == dt_token("string"))
+      {
+        char *str = (char *)mod->param + mod->so->param[p]->offset;
+        const int len = strnlen(str, mod->so->param[p]->cnt);
+        memset(str + len, 0, mod->so->param[p]->cnt - len);
+      }
+      ref_out(&o, &left, "%s:%s ", ref_tkn(mod->name, b0), ref_tkn(mod->inst, b1));
+      for(int k = 0; k < mod->param_size; k++) ref_out(&o, &left, "%02x", mod->param[k]);
+      for(int cc = 0; cc < mod->num_connectors; cc++) if(dt_connector_input(mod->connector + cc))
+        ref_out(&o, &left, " %s<%d.%d", ref_tkn(mod->connector[cc].name, b0), mod->connector[cc].connected.i, mod->connector[cc].connected.c);
+      ref_out(&o, &left, "\n");
+    }
+    if(left <= 0) n = -1;
+  }
+  for(uint32_t m = 0; m < g->num_modules; m++) if(g->module[m].name && g->module[m].so && g->module[m].so->cleanup) g->module[m].so->cleanup(g->module + m);
+  free(g->params_pool); free(g->node); free(g->module); free(g);
+  return n;
 }

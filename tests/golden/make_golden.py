@@ -8,6 +8,7 @@
  - host_nodes.json.gz: node graphs of denoise / hilite / demosaic / llap / filmcurv from the REFERENCE's own create_nodes (same library).
  - host_graph.json.gz: the whole module pass (config reader, roi negotiation, nodes, committed parameters) of the REFERENCE's own
    graph code over its own default darkroom config (same library).
+ - host_cfg.json.gz: return codes and effects of config lines from the REFERENCE's own graph-io.c (same library).
  - darkroom_*.npz: outputs of the CPU oracle for the default darkroom graph on a small synthetic frame.  these pin
    the oracle against accidental edits (the float path has no reference-made vectors: parity unpinned).
 """
@@ -244,6 +245,31 @@ def graph_goldens():
     print("graph goldens:", len(cases), "graphs,", sum(c["text"].count("\n") for c in cases), "lines")
 
 
+CFG_LINES = [
+    "param:colour:01:exposure:0.5", "param:crop:01:crop:0.1:0.9:0.2:0.8", "# comment", "param:nosuch:01:x:1", "param:colour:01:nosuch:1",
+    "param:colour:09:exposure:1", "frames:7", "fps:30", "bogus:line", "module:grade:02", "module:nosuch:01", "connect:grade:01:output:grade:02:input",
+    "connect:grade:01:nosuch:grade:02:input", "connect:nosuch:01:output:grade:02:input", "paramsub:colour:01:mat:4:0.5", "paramsub:colour:01:mat:40:0.5",
+    "param:colour:01:mat:1:2:3", "param:colour:01:exposure", "param:denoise:01:strength:abc", "param:llap:01:sigma:0.3:0.4", "", "param", "param:",
+    "connect:demosaic:01:output:colour:01:input", "connect:colour:01:output:colour:01:input", "connect:grade:01:output:crop:01:input",
+    "param:i-raw:main:filename:some/long name with spaces.dng", "param:colour:01:import:abcdefghijklmnop", "paraminc:colour:01:exposure:0:0.25",
+    "paramdec:colour:01:exposure:0:0.5", "module:grade:01", "param:grade:02:gain:2:2:2:2", "connect:-1:-1:-1:grade:02:input", "connect:hilite:01:output:grade:02:input",
+    "param:colour:01:rbmap:0.1:0.2:0.3:0.4:0.5:0.6", "paramsub:colour:01:rbmap:140:1:2:3:4:5:6:7:8", "param:colour:01:cnt:7", "param:colour:01:cnt:7.9", "param:colour:01:matrix:-3",
+    "module:llap:02:10:20", "connect:llap:02:output:llap:01:input", "connect:filmcurv:01:output:llap:02:input", "frames:-3", "frames:abc", "fps:", "param:crop:01:rotate:1e3",
+    "param:crop:01:rotate:nan", "param:hilite:01:white:0x10", "param:filmcurv:01:light: 2.5", "module:display:dspy", "connect:llap:02:output:display:dspy:input",
+]
+
+
+def cfg_goldens():
+    """the config grammar: return code of the REFERENCE's own dt_graph_read_config_line (graph-io.c compiled in place) for each of
+    CFG_LINES on top of its bin/default-darkroom.i-raw, and what they did (frame count, all parameter blocks, all connections)."""
+    import gzip
+    import json
+    codes, state = O.ref_config_lines(CFG_LINES)
+    with gzip.GzipFile(os.path.join(HERE, "host_cfg.json.gz"), "wb", mtime=0) as f:
+        f.write(json.dumps(dict(lines=CFG_LINES, codes=codes, state=state), indent=0).encode())
+    print("cfg goldens:", len(CFG_LINES), "lines, codes", sorted(set(codes)))
+
+
 def darkroom_goldens():
     w, h = 168, 126
     raw = synth.mosaic(w, h, seed=77)
@@ -264,4 +290,5 @@ if __name__ == "__main__":
     host_goldens()
     node_goldens()
     graph_goldens()
+    cfg_goldens()
     darkroom_goldens()

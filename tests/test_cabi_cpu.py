@@ -188,16 +188,20 @@ def test_crop_roi_follows_the_reference_arithmetic(oracle, crop, rot):
             g.plan()
 
 
-def test_cyclic_connections_are_an_error_not_a_hang():
+def test_cyclic_connections_are_refused_like_the_reference():
+    """a connection that would close a loop is refused with code 12 before anything is touched (connector.c:21-27, cycles.h:47-66):
+    a warning for the config reader, and the graph stays what it was."""
     cfg = ("module:i-raw:main\nmodule:crop:01\nmodule:colour:01\nmodule:filmcurv:01\nmodule:display:main\n"
            "connect:i-raw:main:output:crop:01:input\nconnect:crop:01:output:colour:01:input\nconnect:colour:01:output:filmcurv:01:input\n"
-           "connect:filmcurv:01:output:colour:01:input\nconnect:filmcurv:01:output:display:main:input\n")
+           "connect:filmcurv:01:output:display:main:input\n")
     g = api.Graph(cfg_text=cfg)
     raw = np.zeros((64, 96), np.uint16)
     g.set_source(raw.ctypes.data, api.raw_params(96, 64))
-    with pytest.raises(api.VkbError) as e:
-        g.plan()
-    assert e.value.code == -6 and "sink" in str(e.value)
+    before = g.plan()
+    assert g.line("connect:filmcurv:01:output:colour:01:input") == 12      # colour <- filmcurv <- colour
+    assert g.line("connect:colour:01:output:colour:01:input") == 12        # onto itself
+    assert g.line("connect:filmcurv:01:output:crop:01:input") == 12        # two modules upstream
+    assert g.plan() == before
 
 
 def test_plan_from_mlv_files(tmp_path):

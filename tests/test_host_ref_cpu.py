@@ -315,3 +315,54 @@ def test_live_reference_graph_random(oracle):
         got = _graph_text_product(case)
         bad = [(a[:200], b[:200]) for a, b in zip(ref, got) if a != b]
         assert len(ref) == len(got) and not bad, (case, len(ref), len(got), bad[:3])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the config grammar against the REFERENCE's own graph-io.c: return code per line (0 ok, > 0 warning, < 0 fatal) and the
+# state the lines leave behind (tests/golden/host_cfg.json.gz)
+CFG = json.loads(gzip.open(os.path.join(os.path.dirname(__file__), "golden", "host_cfg.json.gz")).read())
+
+
+def _product_cfg_lines(lines):
+    g = api.Graph(cfg_text=api.DARKROOM_CFG.format(src="i-raw") + "param:i-raw:main:filename:none.raw\n", sink=None)
+    return [g.line(ln) for ln in lines], g.state()
+
+
+def test_config_lines_match_reference_reader():
+    codes, state = _product_cfg_lines(CFG["lines"])
+    assert codes == CFG["codes"], [(ln, a, b) for ln, a, b in zip(CFG["lines"], CFG["codes"], codes) if a != b]
+    assert state.splitlines() == CFG["state"].splitlines()
+    assert 12 in codes and 4 in codes and 2 in codes and 1 in codes     # cycle, index out of range, no such parameter, no such module
+
+
+def test_keyframe_and_feedback_lines_warn():
+    """deliberate: the reference accepts these (0); keyframes and feedback connectors are outside the path, the product says so (1)
+    instead of silently developing something else."""
+    codes, _ = _product_cfg_lines(["module:grade:02", "keyframe:3:colour:01:exposure:0:1.5", "feedback:grade:01:output:grade:02:input"])
+    assert codes == [0, 1, 1]
+
+
+def test_live_config_line_fuzz(oracle):
+    if oracle.ref_host_lib() is None or not hasattr(oracle.ref_host_lib(), "ref_config_lines") or not os.path.isdir("/root/reference/src/pipe/modules"):
+        pytest.skip("oracle/_ref/libhostref.so or /root/reference not present")
+    rng = np.random.default_rng(77)
+    mods = ["colour:01", "crop:01", "llap:01", "grade:01", "denoise:01", "hilite:01", "demosaic:01", "filmcurv:01", "nosuch:01", "colour:02"]
+    pars = ["exposure", "crop", "sigma", "gain", "strength", "white", "method", "light", "mat", "rbmap", "rotate", "perspect", "nosuch", "clarity", "cnt"]
+    vals = ["0.5", "-1", "3", "1e-3", "abc", "", "7.25", "0", "2", "1e9"]
+    lines = []
+    for t in range(400):
+        kind = rng.integers(0, 6)
+        if kind < 3:
+            n = int(rng.integers(0, 6))
+            lines.append("param:%s:%s" % (rng.choice(mods), rng.choice(pars)) + "".join(":" + rng.choice(vals) for _ in range(n)))
+        elif kind == 3:
+            lines.append("paramsub:%s:%s:%d" % (rng.choice(mods), rng.choice(pars), rng.integers(0, 12)) + "".join(":" + rng.choice(vals) for _ in range(int(rng.integers(1, 4)))))
+        elif kind == 4:
+            a, b = rng.choice(mods[:8], 2)
+            lines.append("connect:%s:output:%s:input" % (a, b))
+        else:
+            lines.append("module:%s:%02d" % (rng.choice(["grade", "llap", "colour", "crop", "nosuch"]), rng.integers(1, 4)))
+    ref_codes, ref_state = oracle.ref_config_lines(lines)
+    codes, state = _product_cfg_lines(lines)
+    assert codes == ref_codes, [(ln, a, b) for ln, a, b in zip(lines, ref_codes, codes) if a != b][:5]
+    assert state.splitlines() == ref_state.splitlines(), [(a[:160], b[:160]) for a, b in zip(ref_state.splitlines(), state.splitlines()) if a != b][:3]

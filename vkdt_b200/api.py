@@ -44,7 +44,7 @@ vkb_event_sync vkb_event_elapsed_ms vkb_event_destroy vkb_dispatch vkb_kernel_co
 vkb_kernel_name vkb_launch_count vkb_launch_count_reset vkb_graph_new vkb_graph_free vkb_graph_read_config_ascii
 vkb_graph_read_config_line vkb_graph_replace_display vkb_graph_set_source vkb_graph_set_sink_buffer
 vkb_graph_sink_size vkb_graph_set_frame vkb_graph_run vkb_graph_plan vkb_graph_perf vkb_graph_dump_nodes
-vkb_graph_set_source_device vkb_graph_sink_device vkb_graph_pool_bytes vkb_graph_stream vkb_graph_set_device vkb_dng_info vkb_graph_set_sink_layout vkb_lj92_decode vkb_graph_committed_params vkb_graph_describe""".split()
+vkb_graph_set_source_device vkb_graph_sink_device vkb_graph_pool_bytes vkb_graph_stream vkb_graph_set_device vkb_dng_info vkb_graph_set_sink_layout vkb_lj92_decode vkb_graph_committed_params vkb_graph_describe vkb_graph_state""".split()
 
 
 def token(s):
@@ -118,6 +118,7 @@ lib.vkb_graph_stream.restype = C.c_void_p
 lib.vkb_graph_set_device.argtypes = [C.c_void_p, C.c_int]
 lib.vkb_graph_set_sink_layout.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
 lib.vkb_graph_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+lib.vkb_graph_state.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
 lib.vkb_graph_committed_params.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p]
 lib.vkb_lj92_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 lib.vkb_dng_info.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -278,6 +279,12 @@ class Graph:
         """module and node layer as text (host only): see vkb_graph_describe."""
         b = C.create_string_buffer(1 << 20)
         check(lib.vkb_graph_describe(self.h, b, len(b)))
+        return b.value.decode()
+
+    def state(self):
+        """frame count, parameter blocks and connections of all modules as text (host only): see vkb_graph_state."""
+        b = C.create_string_buffer(1 << 20)
+        check(lib.vkb_graph_state(self.h, b, len(b)))
         return b.value.decode()
 
     def stream(self):

@@ -117,6 +117,26 @@ int vkb_graph_dump_nodes(vkb_graph_t *h, char *buf, size_t bufsize)
   snprintf(buf, bufsize, "%s", s.c_str());
   return (int)s.size();
 }
+int vkb_graph_state(vkb_graph_t *h, char *buf, size_t bufsize)
+{
+  if(!h || !buf || !bufsize) return VKB_ERR_BAD_ARG;
+  std::string s;
+  char b[64];
+  snprintf(b, sizeof(b), "frames %u\n", h->g->frame_cnt);
+  s += b;
+  for(const dt_module_t &m : h->g->module)
+  {
+    if(!m.name) continue; // removed (module.c:dt_module_remove leaves a hole)
+    s += dt_token_string(m.name) + ":" + dt_token_string(m.inst) + " ";
+    for(int k = 0; k < m.param_size; k++) { snprintf(b, sizeof(b), "%02x", m.param[k]); s += b; }
+    for(int c = 0; c < m.num_connectors; c++) if(dt_connector_input(m.connector + c))
+    { snprintf(b, sizeof(b), " %s<%d.%d", dt_token_string(m.connector[c].name).c_str(), m.connector[c].connected.i, m.connector[c].connected.c); s += b; }
+    s += "\n";
+  }
+  if(s.size() + 1 > bufsize) return vkb_set_error(VKB_ERR_BAD_ARG, "buffer too small: %zu < %zu", bufsize, s.size() + 1);
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return VKB_OK;
+}
 int vkb_graph_describe(vkb_graph_t *h, char *buf, size_t bufsize)
 {
   if(!h || !buf || !bufsize) return VKB_ERR_BAD_ARG;

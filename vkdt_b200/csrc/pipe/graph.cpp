@@ -196,7 +196,34 @@ static int connect_generic(std::vector<T> &el, int m0, int c0, int m1, int c1)
   if(cn0->type == dt_token("write") || cn0->type == dt_token("source")) cn0->connected.i++;
   return 0;
 }
-int dt_module_connect(dt_graph_t *g, int m0, int c0, int m1, int c1) { return connect_generic<dt_module_t, true>(g->module, m0, c0, m1, c1); }
+// would feeding m1 from m0 close a loop?  (cycles.h:47-66: refused with code 12 before anything is touched.)  the graph so far
+// has none, so only the new edge can: it does iff m0 already depends on m1, found by walking m0's inputs upstream
+static bool connection_is_cyclic(const dt_graph_t *g, int m0, int m1)
+{
+  const int num = (int)g->module.size();
+  if(m0 < 0 || m1 < 0 || m0 >= num || m1 >= num) return false;
+  std::vector<char> seen(num, 0);
+  std::vector<int> todo(1, m0);
+  while(!todo.empty())
+  {
+    const int m = todo.back(); todo.pop_back();
+    if(m == m1) return true;
+    if(seen[m]) continue;
+    seen[m] = 1;
+    for(int c = 0; c < g->module[m].num_connectors; c++)
+    {
+      const dt_connector_t *cn = g->module[m].connector + c;
+      if(!dt_connector_input(cn) || (cn->flags & s_conn_feedback)) continue; // feedback edges carry last frame's data: no cycle
+      if(cn->connected.i >= 0 && cn->connected.i < num) todo.push_back(cn->connected.i);
+    }
+  }
+  return false;
+}
+int dt_module_connect(dt_graph_t *g, int m0, int c0, int m1, int c1)
+{
+  if(connection_is_cyclic(g, m0, m1)) return 12;
+  return connect_generic<dt_module_t, true>(g->module, m0, c0, m1, c1);
+}
 // the node layer (connector.c node flavour): wildcards on either side take the other side's channels / format
 // (connector.inc:94-106); a mismatch of declared formats is not an error here, nodes declare what they read
 int dt_node_connect(dt_graph_t *g, int n0, int c0, int n1, int c1)
@@ -375,8 +402,8 @@ static int read_param_values(dt_graph_t *g, char *line, dt_token_t name, dt_toke
 }
 int dt_graph_read_config_line(dt_graph_t *g, char *c)
 { // graph-io.c:232-254
-  if(c[0] == '#' || c[0] == 0) return 0;
-  const dt_token_t cmd = io_token(c);
+  if(c[0] == '#') return 0;
+  const dt_token_t cmd = io_token(c); // an empty line is an unknown command like any other: warning 1
   if(cmd == dt_token("module"))
   {
     const dt_token_t name = io_token(c), inst = io_token(c);
