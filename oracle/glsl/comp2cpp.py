@@ -1,0 +1,196 @@
+#!/usr/bin/env python3
+"""ORACLE — test infrastructure.  turns one of the reference's compute shaders into a C++ translation unit for glsl_shim.h.
+
+    comp2cpp.py <reference>/src/pipe/modules <module> <kernel> > _ref/shader_<module>_<kernel>.cpp
+
+The shader is read where it lies under /root/reference; the output goes to oracle/_ref/ (git-ignored), never into the repo.
+What happens to the source: `#version` / `#extension` lines dropped, includes and `#if` resolved by cpp, interface blocks
+(`layout(...) uniform`) become plain structs / image_t globals bound by the entry point below, `out` / `inout` parameters become
+references, array constructors become brace lists, floating literals get an `f` (a GLSL literal is fp32), and functions that
+main() never reaches are left out (so that a shader only needs the parts of shared.glsl it uses to compile).  the function
+bodies - the arithmetic - are untouched."""
+import os
+import re
+import subprocess
+import sys
+
+SCALAR = {"float": 4, "int": 4, "uint": 4, "vec2": 8, "vec3": 12, "vec4": 16, "ivec2": 8, "ivec4": 16, "mat3": 48}
+ALIGN = {"float": 4, "int": 4, "uint": 4, "vec2": 8, "vec3": 16, "vec4": 16, "ivec2": 8, "ivec4": 16, "mat3": 16}
+
+
+def inline_includes(path, search, seen):
+    """textual #include resolution (the shaders use GL_GOOGLE_include_directive), dropping #version / #extension lines"""
+    out = []
+    for ln in open(path).read().splitlines():
+        if re.match(r"\s*#\s*(version|extension)\b", ln):
+            continue
+        m = re.match(r'\s*#\s*include\s+"([^"]+)"', ln)
+        if m:
+            for d in [os.path.dirname(path)] + search:
+                cand = os.path.join(d, m.group(1))
+                if os.path.exists(cand):
+                    if ("#pragma once" in open(cand).read() or cand.endswith(".h")) and cand in seen:
+                        break
+                    seen.add(cand)
+                    out.append(inline_includes(cand, search, seen))
+                    break
+            else:
+                sys.exit("include not found: " + m.group(1))
+            continue
+        if re.match(r"\s*#\s*pragma\s+once", ln):
+            continue
+        out.append(ln)
+    return "\n".join(out)
+
+
+def preprocess(moddir, module, kernel):
+    src = inline_includes(os.path.join(moddir, module, kernel + ".comp"), [os.path.join(moddir, module), moddir, os.path.dirname(moddir)], set())
+    r = subprocess.run(["cpp", "-P", "-undef", "-nostdinc", "-x", "c", "-"], input=src, capture_output=True, text=True)
+    if r.returncode:
+        sys.exit("cpp failed: " + r.stderr[:2000])
+    return r.stdout
+
+
+def split_toplevel(text):
+    """top level declarations: text up to a ';' or a balanced {...} (plus a trailing instance name and ';') at depth 0"""
+    out, depth, start, i, n = [], 0, 0, 0, len(text)
+    while i < n:
+        c = text[i]
+        if c in "({[":
+            depth += 1
+        elif c in ")}]":
+            depth -= 1
+            if c == "}" and depth == 0:
+                j = i + 1
+                m = re.match(r"\s*\w*\s*(\[\s*\d*\s*\])?\s*;", text[j:])     # struct / interface block instance
+                head = text[start:i + 1]
+                if m and not re.search(r"\)\s*\{", head.split("{", 1)[0] + "{"):
+                    i = j + m.end() - 1
+                out.append(text[start:i + 1].strip())
+                start = i + 1
+        elif c == ";" and depth == 0:
+            out.append(text[start:i + 1].strip())
+            start = i + 1
+        i += 1
+    return [d for d in out if d]
+
+
+def std140(members):
+    off, res = 0, []
+    for typ, name, count in members:
+        size, align = SCALAR[typ], ALIGN[typ]
+        if count:
+            align = 16
+            stride = (size + 15) // 16 * 16
+            off = (off + align - 1) // align * align
+            res.append((typ, name, count, off, stride))
+            off += stride * count
+        else:
+            off = (off + align - 1) // align * align
+            res.append((typ, name, 0, off, size))
+            off += size
+    return res, off
+
+
+def fix_body(code):
+    code = re.sub(r"\b(?:in\s+)?(?:inout|out)\s+(\w+)\s+(\w+)", r"\1 &\2", code)           # out / inout parameters
+    code = re.sub(r"\b(\w+)\s*\[\s*\d*\s*\]\s*\(", lambda m: "{" if m.group(1) in SCALAR or m.group(1) == "mat3" else m.group(0), code)  # handled below
+    code = code.replace("^^", "!=")                                                          # logical xor of two bools
+    code = re.sub(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][-+]?\d+)?|\d+[eE][-+]?\d+)(?![\w.])", r"\1f", code)   # fp32 literals
+    code = re.sub(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][-+]?\d+)?)[lL][fF]\b", r"\1f", code)
+    return code
+
+
+def main():
+    moddir, module, kernel = sys.argv[1:4]
+    text = preprocess(moddir, module, kernel)
+    decls = split_toplevel(text)
+    blocks, images, funcs, others = [], [], {}, []
+    for d in decls:
+        if re.match(r"layout\s*\([^)]*\)\s*in\s*;", d):
+            continue
+        m = re.match(r"layout\s*\(([^)]*)\)\s*uniform\s+(\w+)\s*\{(.*)\}\s*(\w+)\s*;", d, re.S)
+        if m:
+            members = []
+            for mem in m.group(3).split(";"):
+                mem = mem.strip()
+                if not mem:
+                    continue
+                mm = re.match(r"(\w+)\s+(\w+)\s*(?:\[\s*(\d+)\s*\])?$", mem)
+                if not mm or mm.group(1) not in SCALAR:
+                    sys.exit("unsupported block member: " + mem)
+                members.append((mm.group(1), mm.group(2), int(mm.group(3) or 0)))
+            blocks.append(("push" if "push_constant" in m.group(1) else "params", m.group(2), m.group(4), members))
+            continue
+        m = re.match(r"layout\s*\(([^)]*)\)\s*uniform\s+(?:writeonly\s+|readonly\s+|coherent\s+)*(sampler2D|image2D)\s+(\w+)\s*(\[\s*\])?\s*;", d)
+        if m:
+            b = re.search(r"binding\s*=\s*(\d+)", m.group(1))
+            s = re.search(r"set\s*=\s*(\d+)", m.group(1))
+            if not s or int(s.group(1)) != 1:
+                sys.exit("unsupported descriptor set: " + d)
+            images.append((int(b.group(1)), m.group(3), bool(m.group(4))))
+            continue
+        if d.startswith("layout"):
+            sys.exit("unsupported interface: " + d[:120])
+        m = re.match(r"(?:const\s+)?[\w]+\s+(\w+)\s*\(([^)]*)\)\s*\{", d, re.S)
+        if m and d.endswith("}"):
+            funcs[m.group(1)] = d
+        else:
+            others.append(d)
+    if "main" not in funcs:
+        sys.exit("no main()")
+    # functions reachable from main()
+    keep, todo = set(), ["main"]
+    while todo:
+        f = todo.pop()
+        if f in keep:
+            continue
+        keep.add(f)
+        for name in set(re.findall(r"\b(\w+)\s*\(", funcs[f])):
+            if name in funcs and name not in keep:
+                todo.append(name)
+    used_text = "\n".join(funcs[f] for f in keep)
+    ns = "shader_%s_%s" % (re.sub(r"\W", "_", module), re.sub(r"\W", "_", kernel))
+    o = ['// generated by oracle/glsl/comp2cpp.py from %s/%s.comp of the reference: do not commit' % (module, kernel), '#include "glsl_shim.h"',
+         "namespace glsl { namespace %s {" % ns, "static uvec3 gl_GlobalInvocationID;"]
+    for kind, tname, inst, members in blocks:
+        o.append("struct %s { %s };" % (tname, " ".join("%s %s%s;" % (t, n, "[%d]" % c if c else "") for t, n, c in members)))
+        o.append("static %s %s;" % (tname, inst))
+    images.sort()
+    for b, name, arr in images:
+        o.append("static image_t %s%s;" % (name, "[64]" if arr else ""))
+    for d in others:   # global constants and structs, only those the kept functions mention
+        m = re.match(r"(?:const\s+)?(?:struct\s+)?\w+\s+(\w+)", d)
+        if m and re.search(r"\b%s\b" % re.escape(m.group(1)), used_text + "\n".join(x for x in others if x is not d)):
+            o.append(fix_body(d))
+    order = [f for f in funcs if f in keep]    # source order: callees are defined before their callers in GLSL
+    for f in order:
+        o.append(re.sub(r"void\s+main\s*\(", "static void shader_main(", fix_body(funcs[f]), count=1) if f == "main" else "static " + fix_body(funcs[f]))
+    o.append("}}")
+    o.append('extern "C" int %s(const void *params_blob, int params_size, const void *push_blob, int push_size, const glsl::image_t *imgs, const int *counts, int nbind, int wd, int ht, int dp)' % ns)
+    o.append("{ using namespace glsl; using namespace glsl::%s;" % ns)
+    for kind, tname, inst, members in blocks:
+        lay, total = std140(members)
+        src, size = ("push_blob", "push_size") if kind == "push" else ("params_blob", "params_size")
+        o.append("  if(%s < %d) return -1;" % (size, max(off + (stride * cnt if cnt else sz) for _, _, cnt, off, stride in lay for sz in [stride])))
+        for typ, name, cnt, off, stride in lay:
+            if cnt:
+                o.append("  for(int k = 0; k < %d; k++) memcpy(&%s.%s[k], (const char *)%s + %d + %d * k, %d);" % (cnt, inst, name, src, off, stride, SCALAR[typ]))
+            elif typ == "mat3":
+                o.append("  for(int k = 0; k < 3; k++) memcpy(&%s.%s[k], (const char *)%s + %d + 16 * k, 12);" % (inst, name, src, off))
+            else:
+                o.append("  memcpy(&%s.%s, (const char *)%s + %d, %d);" % (inst, name, src, off, SCALAR[typ]))
+    o.append("  if(nbind != %d) return -2;" % len(images))
+    o.append("  int at = 0;")
+    for i, (b, name, arr) in enumerate(images):
+        if arr:
+            o.append("  if(counts[%d] > 64) return -3; for(int k = 0; k < counts[%d]; k++) %s[k] = imgs[at + k]; at += counts[%d];" % (i, i, name, i))
+        else:
+            o.append("  %s = imgs[at]; at += counts[%d];" % (name, i))
+    o.append("  for(int z = 0; z < dp; z++) for(int y = 0; y < ht; y++) for(int x = 0; x < wd; x++) { gl_GlobalInvocationID = uvec3(x, y, z); shader_main(); }")
+    o.append("  return 0;\n}")
+    print("\n".join(o))
+
+
+if __name__ == "__main__":
+    main()

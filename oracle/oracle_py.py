@@ -317,3 +317,38 @@ def ref_config_lines(lines, refdir="/root/reference", cfg="bin/default-darkroom.
     n = fn(os.path.join(refdir, "src/pipe").encode(), os.path.join(refdir, cfg).encode(), "\n".join(lines).encode(), codes, len(lines), buf, len(buf))
     assert n == len(lines), "ref_config_lines failed: %d" % n
     return list(codes)[:n], buf.value.decode()
+
+
+# ---- the reference's own compute shaders, compiled as C++ (oracle/glsl/comp2cpp.py + glsl_shim.h -> oracle/_ref/libshaderref.so) ----
+class ShaderImage(C.Structure):
+    _fields_ = [("data", C.POINTER(C.c_float)), ("wd", C.c_int), ("ht", C.c_int), ("chan", C.c_int), ("f16", C.c_int)]
+
+
+_shader = None
+
+
+def ref_shader_lib():
+    global _shader
+    if _shader is None:
+        path = os.path.join(_HERE, "_ref", "libshaderref.so")
+        if not os.path.exists(path):
+            return None
+        _shader = C.CDLL(path)
+    return _shader
+
+
+def ref_shader(module, kernel, params, push, bindings, wd, ht, dp=1):
+    """run <module>/<kernel>.comp of the reference on the CPU, one invocation per (x, y, z) < (wd, ht, dp).
+    bindings: per descriptor binding of set 1 either (array, f16) or a list of those for an array connector; arrays are float32
+    (h, w) or (h, w, c), written in place for image2D bindings (f16: stores round to half precision)."""
+    flat, counts = [], []
+    for b in bindings:
+        items = b if isinstance(b, list) else [b]
+        counts.append(len(items))
+        for a, f16 in items:
+            assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+            flat.append(ShaderImage(a.ctypes.data_as(C.POINTER(C.c_float)), a.shape[1], a.shape[0], 1 if a.ndim == 2 else a.shape[2], int(f16)))
+    arr = (ShaderImage * len(flat))(*flat)
+    fn = getattr(ref_shader_lib(), "shader_%s_%s" % (module.replace("-", "_"), kernel))
+    r = fn(bytes(params), len(bytes(params)), bytes(push), len(bytes(push)), arr, (C.c_int * len(counts))(*counts), len(counts), wd, ht, dp)
+    assert r == 0, "shader_%s_%s failed: %d" % (module, kernel, r)

@@ -9,6 +9,7 @@
  - host_graph.json.gz: the whole module pass (config reader, roi negotiation, nodes, committed parameters) of the REFERENCE's own
    graph code over its own default darkroom config (same library).
  - host_cfg.json.gz: return codes and effects of config lines from the REFERENCE's own graph-io.c (same library).
+ - shader_ref.npz: outputs of the REFERENCE's own compute shaders compiled as C++ (oracle/glsl -> oracle/_ref/libshaderref.so).
  - darkroom_*.npz: outputs of the CPU oracle for the default darkroom graph on a small synthetic frame.  these pin
    the oracle against accidental edits (the float path has no reference-made vectors: parity unpinned).
 """
@@ -270,6 +271,21 @@ def cfg_goldens():
     print("cfg goldens:", len(CFG_LINES), "lines, codes", sorted(set(codes)))
 
 
+def shader_goldens():
+    """outputs of the REFERENCE's own compute shaders, compiled as C++ (oracle/glsl, oracle/_ref/libshaderref.so), on the seeded inputs
+    of tests/test_shader_ref_cpu.py: pins the oracle's float kernels where the reference is absent."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import test_shader_ref_cpu as T
+    assert O.ref_shader_lib() is not None, "oracle/_ref/libshaderref.so missing: run `make -C oracle ref` where /root/reference exists"
+    out = {}
+    for name, fn in T.cases(O).items():
+        _, got = fn()
+        for k, g in enumerate(got):
+            out["%s/%d" % (name, k)] = np.asarray(g, np.float32).astype(np.float16) if name.split()[0] not in ("grade.main",) else np.asarray(g, np.float32)
+    np.savez_compressed(os.path.join(HERE, "shader_ref.npz"), **out)
+    print("shader goldens:", len(out), "images from", len(T.cases(O)), "cases")
+
+
 def darkroom_goldens():
     w, h = 168, 126
     raw = synth.mosaic(w, h, seed=77)
@@ -291,4 +307,5 @@ if __name__ == "__main__":
     node_goldens()
     graph_goldens()
     cfg_goldens()
+    shader_goldens()
     darkroom_goldens()

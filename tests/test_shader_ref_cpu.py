@@ -1,0 +1,269 @@
+"""float kernels: the CPU oracle against the REFERENCE's own compute shaders, compiled as C++ (oracle/glsl/comp2cpp.py rewrites the
+interface declarations of <module>/<kernel>.comp where it lies under /root/reference, oracle/glsl/glsl_shim.h is the language
+runtime; `make -C oracle ref` -> oracle/_ref/libshaderref.so).  the arithmetic, its order and its constants are the shader's;
+every kernel here has to agree BIT FOR BIT with the oracle's restatement on seeded inputs (f16 valued, like the edges of the
+graph), image borders, clipped and negative values included.  tests/golden/shader_ref.npz holds the shaders' outputs for the
+same inputs (written by tests/golden/make_golden.py), so the pin also holds where the reference is absent."""
+import ctypes as C
+import os
+import numpy as np
+import pytest
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "shader_ref.npz")
+BAYER, XTRANS = 0x5d5d5d5d, 9
+
+
+def f16(a):
+    return np.ascontiguousarray(a.astype(np.float16).astype(np.float32))
+
+
+def mosaic(rng, w, h, hot=True):
+    m = rng.uniform(0.0, 1.1, (h, w))
+    m[h // 3:h // 2, w // 4:w // 2] = rng.uniform(0.95, 1.3, (h // 2 - h // 3, w // 2 - w // 4))   # a clipped region
+    if hot:
+        m[5, 7] = 4.0
+    return f16(m)
+
+
+def rgba(rng, w, h, lo=-0.05, hi=1.5):
+    a = rng.uniform(lo, hi, (h, w, 4))
+    a[..., 3] = 1.0
+    a[0, 0, :3] = [np.nan, 0.5, 0.2]
+    a[0, 1, :3] = 0.0
+    a[0, 2, :3] = [-1.0, -2.0, 3.0]
+    return f16(a)
+
+
+def push_wb(wb, filters, extra=()):
+    return np.array(list(wb), np.float32).tobytes() + np.array([filters] + list(extra), np.uint32).tobytes()
+
+
+def cases(O):
+    """name -> function returning (outputs of the oracle, outputs of the shader), each a list of float32 arrays"""
+    L = O.lib()
+    out = {}
+
+    def img_out(h, w, c):
+        return O.new_img(h, w, c)
+
+    def add(name):
+        def deco(fn):
+            out[name] = fn
+            return fn
+        return deco
+
+    for mode in (0, 1):
+        @add("grade.main mode %d" % mode)
+        def _(mode=mode):
+            rng = np.random.default_rng(10 + mode)
+            a = rgba(rng, 96, 64)
+            gp = O.GradeParams((C.c_float * 4)(0.01, 0.0, 0.02, 0.0), (C.c_float * 4)(1.1, 1.0, 0.9, 0.05), (C.c_float * 4)(1.0, 1.1, 0.95, 0.0), (C.c_float * 4)(0.0, 0.01, 0.0, 0.0), mode, 0.3, 0.4)
+            want, wi = img_out(64, 96, 4)
+            L.o_grade_main(C.byref(O.img(a)), C.byref(wi), C.byref(gp), 0)
+            got = np.zeros((64, 96, 4), np.float32)
+            O.ref_shader("grade", "main", bytes(gp), b"", [(a, 0), (got, 0)], 96, 64)
+            return [want], [got]
+
+    @add("llap.curve")
+    def _():
+        rng = np.random.default_rng(20)
+        a = rgba(rng, 96, 64)
+        lp = O.LlapParams(0.12, 0.8, 1.3, 0.4)
+        outs = [np.zeros((64, 96), np.float32) for _ in range(11)]
+        O.ref_shader("llap", "curve", bytes(lp), np.array([10], np.uint32).tobytes(), [(a, 0), [(o, 1) for o in outs]], 96, 64)
+        want = [img_out(64, 96, 1) for _ in range(11)]
+        L.o_llap_curve(C.byref(O.img(a)), (O.OImg * 11)(*[x[1] for x in want]), C.byref(lp))
+        return [x[0].reshape(64, 96) for x in want], outs
+
+    for (w, h) in ((96, 64), (37, 23)):
+        @add("llap.reduce %dx%d" % (w, h))
+        def _(w=w, h=h):
+            rng = np.random.default_rng(21)
+            ins = [f16(rng.uniform(0, 1.2, (h, w))) for _ in range(11)]
+            cw, ch = (w - 1) // 2 + 1, (h - 1) // 2 + 1
+            outs = [np.zeros((ch, cw), np.float32) for _ in range(11)]
+            O.ref_shader("llap", "reduce", bytes(O.LlapParams(0.12, 1, 1, 0.2)), b"", [[(i, 0) for i in ins], [(o, 1) for o in outs]], cw, ch, 11)
+            want = [img_out(ch, cw, 1) for _ in range(11)]
+            for i, x in zip(ins, want):     # the oracle's is one layer per call
+                L.o_llap_reduce(C.byref(O.img(i)), C.byref(x[1]))
+            return [x[0].reshape(ch, cw) for x in want], outs
+
+        for first in (0, 1):
+            @add("llap.assemble %dx%d first %d" % (w, h, first))
+            def _(w=w, h=h, first=first):
+                rng = np.random.default_rng(22 + first)
+                cw, ch = (w - 1) // 2 + 1, (h - 1) // 2 + 1
+                l0 = [f16(rng.uniform(0, 1.2, (h, w))) for _ in range(11)]
+                l1 = [f16(rng.uniform(0, 1.2, (ch, cw))) for _ in range(11)]
+                coarse = l1[10] if first else f16(rng.uniform(0, 1.2, (ch, cw)))
+                got = np.zeros((h, w), np.float32)
+                # with `first` the coarse input is a dummy binding (llap/main.c:84-86) and the shader reads l1[num_gamma] instead
+                O.ref_shader("llap", "assemble", b"", np.array([10, first], np.uint32).tobytes(), [(coarse, 0), [(i, 0) for i in l0], [(i, 0) for i in l1], (got, 1)], w, h)
+                want, wi = img_out(h, w, 1)
+                L.o_llap_assemble(C.byref(O.img(coarse)), (O.OImg * 11)(*[O.img(i) for i in l0]), (O.OImg * 11)(*[O.img(i) for i in l1]), C.byref(wi), first)
+                return [want.reshape(h, w)], [got]
+
+    @add("llap.colour")
+    def _():
+        rng = np.random.default_rng(24)
+        a, lum = rgba(rng, 96, 64), f16(rng.uniform(0, 1.2, (64, 96)))
+        want, wi = img_out(64, 96, 4)
+        L.o_llap_colour(C.byref(O.img(lum)), C.byref(O.img(a)), C.byref(wi), 1)
+        got = np.zeros((64, 96, 4), np.float32)
+        O.ref_shader("llap", "colour", bytes(O.LlapParams(0.12, 1, 1, 0.2)), b"", [(lum, 0), (a, 0), (got, 1)], 96, 64)
+        return [want], [got]
+
+    for filters, (w, h) in ((BAYER, (96, 64)), (XTRANS, (96, 66)), (BAYER, (38, 26))):
+        blk = 3 if filters == XTRANS else 2
+        tag = "%s %dx%d" % ("xtrans" if filters == XTRANS else "bayer", w, h)
+        hp = O.HiliteParams(0.9, 0.3, 0.6)
+        wb = (2.0, 1.0, 1.5, 1.0)
+
+        @add("hilite.half " + tag)
+        def _(filters=filters, w=w, h=h, blk=blk, hp=hp, wb=wb):
+            m = mosaic(np.random.default_rng(30), w, h)
+            want, wi = img_out(h // blk, w // blk, 4)
+            L.o_hilite_half(C.byref(O.img(m)), C.byref(wi), C.byref(hp), C.c_uint32(filters))
+            got = np.zeros((h // blk, w // blk, 4), np.float32)
+            O.ref_shader("hilite", "half", bytes(hp), push_wb(wb, filters), [(m, 0), (got, 1)], w // blk, h // blk)
+            return [want], [got]
+
+        @add("hilite.reduce " + tag)
+        def _(w=w // blk, h=h // blk, hp=hp, wb=wb, filters=filters):
+            a = rgba(np.random.default_rng(31), w, h, 0.0, 1.2)
+            a[..., 3] = f16(np.random.default_rng(32).uniform(0, 1, (h, w)))
+            cw, ch = (w - 1) // 2 + 1, (h - 1) // 2 + 1
+            want, wi = img_out(ch, cw, 4)
+            L.o_hilite_reduce(C.byref(O.img(a)), C.byref(wi), C.byref(hp), (C.c_float * 4)(*wb))
+            got = np.zeros((ch, cw, 4), np.float32)
+            O.ref_shader("hilite", "reduce", bytes(hp), push_wb(wb, filters), [(a, 0), (got, 1)], cw, ch)
+            return [want], [got]
+
+        @add("hilite.assemble " + tag)
+        def _(w=w // blk, h=h // blk, hp=hp, wb=wb, filters=filters):
+            rng = np.random.default_rng(33)
+            cw, ch = (w - 1) // 2 + 1, (h - 1) // 2 + 1
+            fine, coarse = rgba(rng, w, h, 0.0, 1.2), rgba(rng, cw, ch, 0.0, 1.2)
+            fine[..., 3] = f16(rng.uniform(0, 1, (h, w)))
+            coarse[..., 3] = f16(rng.uniform(0, 1, (ch, cw)))
+            want, wi = img_out(h, w, 4)
+            L.o_hilite_assemble(C.byref(O.img(fine)), C.byref(O.img(coarse)), C.byref(wi), C.byref(hp))
+            got = np.zeros((h, w, 4), np.float32)
+            O.ref_shader("hilite", "assemble", bytes(hp), push_wb(wb, filters, (0,)), [(fine, 0), (coarse, 0), (got, 1)], w, h)
+            return [want], [got]
+
+        @add("hilite.doub " + tag)
+        def _(filters=filters, w=w, h=h, blk=blk, hp=hp, wb=wb):
+            rng = np.random.default_rng(34)
+            m, coarse = mosaic(rng, w, h), rgba(rng, w // blk, h // blk, 0.0, 1.2)
+            want, wi = img_out(h, w, 1)
+            L.o_hilite_doub(C.byref(O.img(m)), C.byref(O.img(coarse)), C.byref(wi), C.byref(hp), C.c_uint32(filters))
+            got = np.zeros((h, w), np.float32)
+            O.ref_shader("hilite", "doub", bytes(hp), push_wb(wb, filters), [(m, 0), (coarse, 0), (got, 1)], w // blk, h // blk)
+            return [want.reshape(h, w)], [got]
+
+        @add("demosaic.down " + tag)
+        def _(filters=filters, w=w, h=h, blk=blk):
+            m = mosaic(np.random.default_rng(40), w, h)
+            want, wi = img_out(h // blk, w // blk, 1)
+            L.o_demosaic_down(C.byref(O.img(m)), C.byref(wi), C.c_uint32(filters))
+            got = np.zeros((h // blk, w // blk), np.float32)
+            O.ref_shader("demosaic", "down", b"", push_wb((1, 1, 1, 1), filters), [(m, 0), (got, 1)], w // blk, h // blk)
+            return [want.reshape(h // blk, w // blk)], [got]
+
+        @add("demosaic.halfsize " + tag)
+        def _(filters=filters, w=w, h=h, blk=blk):
+            m = mosaic(np.random.default_rng(41), w, h)
+            want, wi = img_out(h // blk, w // blk, 4)
+            L.o_demosaic_halfsize(C.byref(O.img(m)), C.byref(wi), C.c_uint32(filters))
+            got = np.zeros((h // blk, w // blk, 4), np.float32)
+            O.ref_shader("demosaic", "halfsize", b"", push_wb((1, 1, 1, 1), filters), [(m, 0), (got, 1)], w // blk, h // blk)
+            return [want], [got]
+
+        @add("demosaic.splat+fix " + tag)
+        def _(filters=filters, w=w, h=h, blk=blk):
+            rng = np.random.default_rng(42)
+            m = mosaic(rng, w, h, hot=False)
+            cov, ci = img_out(h // blk, w // blk, 4)
+            L.o_demosaic_gauss(C.byref(O.img(m)), C.byref(ci), C.c_uint32(filters))       # the oracle's covariance image feeds both
+            cov = np.ascontiguousarray(cov.reshape(h // blk, w // blk, 4))
+            wg, wgi = img_out(h, w, 1)
+            L.o_demosaic_splat(C.byref(O.img(m)), C.byref(O.img(cov)), C.byref(wgi), C.c_uint32(filters))
+            gg = np.zeros((h, w), np.float32)
+            O.ref_shader("demosaic", "splat", b"", push_wb((1, 1, 1, 1), filters), [(m, 0), (cov, 0), (gg, 1)], w, h)
+            res_o, res_s = [wg.reshape(h, w)], [gg]
+            green = np.ascontiguousarray(wg.reshape(h, w))
+            for fixup in (0, 1):
+                wo, woi = img_out(h, w, 4)
+                L.o_demosaic_fix(C.byref(O.img(m)), C.byref(O.img(green)), C.byref(O.img(cov)), C.byref(woi), C.c_uint32(filters), fixup)
+                go = np.zeros((h, w, 4), np.float32)
+                O.ref_shader("demosaic", "fix", np.array([fixup], np.int32).tobytes(), push_wb((1, 1, 1, 1), filters), [(m, 0), (green, 0), (cov, 0), (go, 1)], w, h)
+                res_o.append(wo)
+                res_s.append(go)
+            return res_o, res_s
+    return out
+
+
+def _same(a, b):
+    a, b = np.asarray(a, np.float32).ravel(), np.asarray(b, np.float32).ravel()
+    return a.shape == b.shape and np.array_equal(np.where(np.isnan(a), np.float32(-7), a).view(np.uint32), np.where(np.isnan(b), np.float32(-7), b).view(np.uint32))
+
+
+def _f16_ulps(a, b):
+    """distance in representable f16 values"""
+    def key(x):
+        u = x.astype(np.float16).view(np.uint16).astype(np.int32)
+        return np.where(u & 0x8000, 0x8000 - u, u)
+    return np.abs(key(a) - key(b))
+
+
+# kernels that FILTER (texture() at fractional coordinates): the shader computes its texture coordinates in fp32, the oracle is an
+# ideal sampler that carries them in double (oracle/o_common.h:122-143), so a weight can differ in its last bits and an
+# f16 store can then round the other way.  everything else is bit exact.
+SAMPLED = ("llap.reduce", "llap.assemble")
+
+
+def _report(name, want, got):
+    bad = []
+    for k, (a, b) in enumerate(zip(want, got)):
+        a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+        if name.startswith("demosaic.halfsize xtrans"):
+            a, b = a[..., :3], b[..., :3]       # the shader leaves alpha unwritten for x-trans (demosaic/halfsize.comp:20-33)
+        if _same(a, b):
+            continue
+        d = np.abs(a.astype(np.float64) - b.astype(np.float64)).ravel()
+        n = int((d > 0).sum() + (np.isnan(a) != np.isnan(b)).sum())
+        if name.startswith(SAMPLED) and np.array_equal(np.isnan(a), np.isnan(b)) and _f16_ulps(a, b).max() <= 1 and n <= 0.02 * d.size:
+            continue
+        bad.append("%s[%d]: %d of %d values differ, max abs %.3g" % (name, k, n, d.size, np.nanmax(d)))
+    return bad
+
+
+def test_oracle_matches_reference_shaders_live(oracle):
+    if oracle.ref_shader_lib() is None:
+        pytest.skip("oracle/_ref/libshaderref.so not built (needs /root/reference: make -C oracle ref)")
+    bad, n = [], 0
+    for name, fn in cases(oracle).items():
+        want, got = fn()
+        bad += _report(name, want, got)
+        n += len(want)
+    assert not bad, "\n".join(bad)
+    assert n >= 60
+
+
+def test_oracle_matches_reference_shader_goldens(oracle):
+    """the same against the shaders' outputs stored when the reference was present (inputs are seeded, so only outputs are stored)"""
+    G = np.load(GOLDEN)
+    bad, n = [], 0
+    real = oracle.ref_shader
+    try:
+        oracle.ref_shader = lambda *a, **k: None          # the shader side of each case stays zero: only the oracle side is used
+        for name, fn in cases(oracle).items():
+            want, _ = fn()
+            got = [G["%s/%d" % (name, k)] for k in range(len(want))]
+            bad += _report(name, want, [g.reshape(np.asarray(w).shape) for g, w in zip(got, want)])
+            n += len(want)
+    finally:
+        oracle.ref_shader = real
+    assert not bad, "\n".join(bad)
+    assert n >= 60
