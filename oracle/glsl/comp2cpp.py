@@ -14,8 +14,8 @@ import re
 import subprocess
 import sys
 
-SCALAR = {"float": 4, "int": 4, "uint": 4, "vec2": 8, "vec3": 12, "vec4": 16, "ivec2": 8, "ivec4": 16, "mat3": 48}
-ALIGN = {"float": 4, "int": 4, "uint": 4, "vec2": 8, "vec3": 16, "vec4": 16, "ivec2": 8, "ivec4": 16, "mat3": 16}
+SCALAR = {"float": 4, "int": 4, "uint": 4, "vec2": 8, "vec3": 12, "vec4": 16, "ivec2": 8, "ivec4": 16, "uvec4": 16, "mat3": 48}
+ALIGN = {"float": 4, "int": 4, "uint": 4, "vec2": 8, "vec3": 16, "vec4": 16, "ivec2": 8, "ivec4": 16, "uvec4": 16, "mat3": 16}
 
 
 def inline_includes(path, search, seen):
@@ -45,7 +45,8 @@ def inline_includes(path, search, seen):
 
 def preprocess(moddir, module, kernel):
     src = inline_includes(os.path.join(moddir, module, kernel + ".comp"), [os.path.join(moddir, module), moddir, os.path.dirname(moddir)], set())
-    r = subprocess.run(["cpp", "-P", "-undef", "-nostdinc", "-x", "c", "-"], input=src, capture_output=True, text=True)
+    # GL_core_profile: predefined by every GLSL compiler (matrices.h keys its column major mat3() form on it)
+    r = subprocess.run(["cpp", "-P", "-undef", "-nostdinc", "-DGL_core_profile=1", "-x", "c", "-"], input=src, capture_output=True, text=True)
     if r.returncode:
         sys.exit("cpp failed: " + r.stderr[:2000])
     return r.stdout
@@ -116,10 +117,12 @@ def main():
                 mem = mem.strip()
                 if not mem:
                     continue
-                mm = re.match(r"(\w+)\s+(\w+)\s*(?:\[\s*(\d+)\s*\])?$", mem)
-                if not mm or mm.group(1) not in SCALAR:
-                    sys.exit("unsupported block member: " + mem)
-                members.append((mm.group(1), mm.group(2), int(mm.group(3) or 0)))
+                typ, rest = mem.split(None, 1)
+                for one in rest.split(","):
+                    mm = re.match(r"(\w+)\s*(?:\[\s*(\d+)\s*\])?$", one.strip())
+                    if not mm or typ not in SCALAR:
+                        sys.exit("unsupported block member: " + mem)
+                    members.append((typ, mm.group(1), int(mm.group(2) or 0)))
             blocks.append(("push" if "push_constant" in m.group(1) else "params", m.group(2), m.group(4), members))
             continue
         m = re.match(r"layout\s*\(([^)]*)\)\s*uniform\s+(?:writeonly\s+|readonly\s+|coherent\s+)*(sampler2D|image2D)\s+(\w+)\s*(\[\s*\])?\s*;", d)
@@ -134,7 +137,7 @@ def main():
             sys.exit("unsupported interface: " + d[:120])
         m = re.match(r"(?:const\s+)?[\w]+\s+(\w+)\s*\(([^)]*)\)\s*\{", d, re.S)
         if m and d.endswith("}"):
-            funcs[m.group(1)] = d
+            funcs[m.group(1)] = (funcs[m.group(1)] + "\n" if m.group(1) in funcs else "") + d      # overloads travel together
         else:
             others.append(d)
     if "main" not in funcs:
@@ -149,6 +152,13 @@ def main():
         for name in set(re.findall(r"\b(\w+)\s*\(", funcs[f])):
             if name in funcs and name not in keep:
                 todo.append(name)
+    # a swizzle handed to a function with a single inout parameter: C++ cannot bind the proxy to a reference, go through a temporary
+    for f in list(keep):
+        m = re.match(r"[\w\s]*?\b(\w+)\s*\(\s*inout\s+(\w+)\s+\w+\s*\)", funcs[f])
+        if m:
+            name, typ = m.group(1), m.group(2)
+            for g in keep:
+                funcs[g] = re.sub(r"\b%s\s*\(\s*(\w+\.[xyzwrgba]{2,4})\s*\)\s*;" % name, r"{ %s _t = \1; %s(_t); \1 = _t; }" % (typ, name), funcs[g])
     used_text = "\n".join(funcs[f] for f in keep)
     ns = "shader_%s_%s" % (re.sub(r"\W", "_", module), re.sub(r"\W", "_", kernel))
     o = ['// generated by oracle/glsl/comp2cpp.py from %s/%s.comp of the reference: do not commit' % (module, kernel), '#include "glsl_shim.h"',
@@ -165,7 +175,7 @@ def main():
             o.append(fix_body(d))
     order = [f for f in funcs if f in keep]    # source order: callees are defined before their callers in GLSL
     for f in order:
-        o.append(re.sub(r"void\s+main\s*\(", "static void shader_main(", fix_body(funcs[f]), count=1) if f == "main" else "static " + fix_body(funcs[f]))
+        o.append(re.sub(r"void\s+main\s*\(", "static void shader_main(", fix_body(funcs[f]), count=1) if f == "main" else fix_body(funcs[f]))
     o.append("}}")
     o.append('extern "C" int %s(const void *params_blob, int params_size, const void *push_blob, int push_size, const glsl::image_t *imgs, const int *counts, int nbind, int wd, int ht, int dp)' % ns)
     o.append("{ using namespace glsl; using namespace glsl::%s;" % ns)

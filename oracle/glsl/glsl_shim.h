@@ -55,6 +55,7 @@ template<class V, int P, int... I> struct swz
   V &operator/=(float b) { for(int i = 0; i < N; i++) d[i] /= b; return *this; }
 
 struct vec2; struct vec3; struct vec4; struct ivec2; struct uvec3;
+template<class V, int P, int A, int B> struct iswz2 { int d[P]; operator V() const { return V(d[A], d[B]); } };
 
 struct vec2
 {
@@ -72,7 +73,7 @@ struct vec3
 {
   union { float d[3]; struct { float x, y, z; }; struct { float r, g, b; };
     swz<vec3, 3, 0, 1, 2> xyz, rgb; swz<vec3, 3, 2, 1, 0> zyx, bgr; swz<vec3, 3, 0, 0, 0> xxx, rrr; swz<vec3, 3, 1, 1, 1> yyy, ggg; swz<vec3, 3, 2, 2, 2> zzz, bbb;
-    swz<vec3, 3, 1, 2, 0> yzx, gbr; swz<vec3, 3, 2, 0, 1> zxy, brg; swz<vec4, 3, 1, 2, 1, 0> gbgr; swz<vec4, 3, 0, 1, 2, 2> rgbb; swz<vec4, 3, 0, 1, 1, 2> rggb; swz<vec2, 3, 2, 0> zx, br; swz<vec2, 3, 1, 0> yx, gr;
+    swz<vec3, 3, 1, 2, 0> yzx, gbr; swz<vec3, 3, 2, 0, 1> zxy, brg; swz<vec4, 3, 1, 2, 1, 0> gbgr; swz<vec4, 3, 0, 1, 2, 2> rgbb; swz<vec4, 3, 0, 1, 1, 2> rggb; swz<vec2, 3, 2, 0> zx, br; swz<vec2, 3, 1, 0> yx, gr; swz<vec2, 3, 2, 1> zy, bg;
     swz<vec2, 3, 0, 1> xy, rg; swz<vec2, 3, 1, 2> yz, gb; swz<vec2, 3, 0, 2> xz, rb; };
   vec3() : d{0, 0, 0} {}
   explicit vec3(float s) : d{s, s, s} {}
@@ -103,11 +104,11 @@ struct vec4
 };
 struct uvec3 { union { uint d[3]; struct { uint x, y, z; }; }; uvec3(uint a = 0, uint b = 0, uint c = 0) : d{a, b, c} {} };
 struct bvec2 { bool d[2]; };
-struct bvec3 { bool d[3]; };
+struct bvec3 { union { bool d[3]; struct { bool x, y, z; }; }; bvec3() : d{false, false, false} {} explicit bvec3(bool b) : d{b, b, b} {} bvec3(bool a, bool b, bool c) : d{a, b, c} {} };
 struct bvec4 { bool d[4]; };
 struct ivec2
 {
-  union { int d[2]; struct { int x, y; }; };
+  union { int d[2]; struct { int x, y; }; iswz2<ivec2, 2, 0, 1> xy; iswz2<ivec2, 2, 1, 0> yx; };
   ivec2() : d{0, 0} {}
   explicit ivec2(int s) : d{s, s} {}
   ivec2(int a, int b) : d{a, b} {}
@@ -129,6 +130,7 @@ struct ivec2
   // int vector with a float scalar or vector: the int side converts (GLSL implicit conversion)
   friend vec2 operator*(const ivec2 &a, float b) { return vec2((float)a.x * b, (float)a.y * b); }
   friend vec2 operator*(float a, const ivec2 &b) { return vec2(a * (float)b.x, a * (float)b.y); }
+  friend vec2 operator/(float a, const ivec2 &b) { return vec2(a / (float)b.x, a / (float)b.y); }
   friend vec2 operator/(const ivec2 &a, float b) { return vec2((float)a.x / b, (float)a.y / b); }
   friend vec2 operator+(const ivec2 &a, float b) { return vec2((float)a.x + b, (float)a.y + b); }
   friend vec2 operator+(float a, const ivec2 &b) { return vec2(a + (float)b.x, a + (float)b.y); }
@@ -179,9 +181,14 @@ inline float max(double a, float b) { return max((float)a, b); }
 inline float min(float a, double b) { return min(a, (float)b); }
 inline float clamp(float x, float lo, float hi) { return min(max(x, lo), hi); }
 inline int   clamp(int x, int lo, int hi) { return min(max(x, lo), hi); }
+inline uint  clamp(uint x, int lo, int hi) { return x < (uint)lo ? (uint)lo : (x > (uint)hi ? (uint)hi : x); }
+inline float clamp(float x, int lo, float hi) { return clamp(x, (float)lo, hi); }
+inline float clamp(float x, float lo, int hi) { return clamp(x, lo, (float)hi); }
+inline float clamp(float x, int lo, int hi) { return clamp(x, (float)lo, (float)hi); }
 inline vec2  clamp(const vec2 &x, float lo, float hi) { return min(max(x, lo), hi); }
 inline vec3  clamp(const vec3 &x, float lo, float hi) { return min(max(x, lo), hi); }
 inline vec4  clamp(const vec4 &x, float lo, float hi) { return min(max(x, lo), hi); }
+inline vec2  clamp(const vec2 &x, const vec2 &lo, const vec2 &hi) { return min(max(x, lo), hi); }
 inline vec3  clamp(const vec3 &x, const vec3 &lo, const vec3 &hi) { return min(max(x, lo), hi); }
 inline vec4  clamp(const vec4 &x, const vec4 &lo, const vec4 &hi) { return min(max(x, lo), hi); }
 inline ivec2 clamp(const ivec2 &x, const ivec2 &lo, const ivec2 &hi) { return ivec2(clamp(x.x, lo.x, hi.x), clamp(x.y, lo.y, hi.y)); }
@@ -206,7 +213,7 @@ inline bvec2 greaterThanEqual(const ivec2 &a, const ivec2 &b) { return bvec2{{a.
 inline bvec2 greaterThan(const ivec2 &a, const ivec2 &b) { return bvec2{{a.x > b.x, a.y > b.y}}; }
 inline bvec2 lessThan(const ivec2 &a, const ivec2 &b) { return bvec2{{a.x < b.x, a.y < b.y}}; }
 #define GLSL_CMP(F, OP) \
-  inline bvec3 F(const vec3 &a, const vec3 &b) { return bvec3{{a.d[0] OP b.d[0], a.d[1] OP b.d[1], a.d[2] OP b.d[2]}}; } \
+  inline bvec3 F(const vec3 &a, const vec3 &b) { return bvec3(a.d[0] OP b.d[0], a.d[1] OP b.d[1], a.d[2] OP b.d[2]); } \
   inline bvec4 F(const vec4 &a, const vec4 &b) { return bvec4{{a.d[0] OP b.d[0], a.d[1] OP b.d[1], a.d[2] OP b.d[2], a.d[3] OP b.d[3]}}; } \
   inline bvec2 F(const vec2 &a, const vec2 &b) { return bvec2{{a.d[0] OP b.d[0], a.d[1] OP b.d[1]}}; }
 GLSL_CMP(lessThan, <) GLSL_CMP(lessThanEqual, <=) GLSL_CMP(greaterThan, >) GLSL_CMP(greaterThanEqual, >=) GLSL_CMP(equal, ==)
@@ -217,6 +224,7 @@ inline bool all(const bvec4 &b) { return b.d[0] && b.d[1] && b.d[2] && b.d[3]; }
 inline vec3 mix(const vec3 &a, const vec3 &b, const bvec3 &t) { return vec3(t.d[0] ? b.d[0] : a.d[0], t.d[1] ? b.d[1] : a.d[1], t.d[2] ? b.d[2] : a.d[2]); }
 inline bool any(const bvec2 &b) { return b.d[0] || b.d[1]; }
 inline bool all(const bvec2 &b) { return b.d[0] && b.d[1]; }
+inline vec2 unpackHalf2x16(uint v) { uint16_t lo = (uint16_t)(v & 0xffffu), hi = (uint16_t)(v >> 16); _Float16 a, b; memcpy(&a, &lo, 2); memcpy(&b, &hi, 2); return vec2((float)a, (float)b); }
 inline bool isnan(float a) { return std::isnan(a); }
 inline bool isinf(float a) { return std::isinf(a); }
 
@@ -229,8 +237,22 @@ struct mat2
   vec2 &operator[](int i) { return c[i]; }
   friend vec2 operator*(const mat2 &m, const vec2 &v) { return m.c[0] * v.d[0] + m.c[1] * v.d[1]; }
   friend vec2 operator*(const vec2 &v, const mat2 &m) { return vec2(dot(v, m.c[0]), dot(v, m.c[1])); }
+  friend mat2 operator+(const mat2 &a, const mat2 &b) { return mat2(a.c[0] + b.c[0], a.c[1] + b.c[1]); }
+  friend mat2 operator-(const mat2 &a, const mat2 &b) { return mat2(a.c[0] - b.c[0], a.c[1] - b.c[1]); }
+  friend mat2 operator*(const mat2 &a, float b) { return mat2(a.c[0] * b, a.c[1] * b); }
+  friend mat2 operator*(float a, const mat2 &b) { return mat2(a * b.c[0], a * b.c[1]); }
+  friend mat2 operator/(const mat2 &a, float b) { return mat2(a.c[0] / b, a.c[1] / b); }
+  friend mat2 operator*(const mat2 &a, const mat2 &b) { return mat2(a * b.c[0], a * b.c[1]); }
+  mat2 &operator+=(const mat2 &b) { c[0] += b.c[0]; c[1] += b.c[1]; return *this; }
+  mat2 &operator*=(float b) { c[0] *= b; c[1] *= b; return *this; }
+  mat2 &operator/=(float b) { c[0] /= b; c[1] /= b; return *this; }
+  explicit mat2(float s) { c[0] = vec2(s, 0); c[1] = vec2(0, s); }
 };
-struct ivec4 { union { int d[4]; struct { int x, y, z, w; }; }; ivec4() : d{0, 0, 0, 0} {} int operator[](int i) const { return d[i]; } };
+inline float determinant(const mat2 &m) { return m.c[0].d[0] * m.c[1].d[1] - m.c[1].d[0] * m.c[0].d[1]; }
+inline mat2 outerProduct(const vec2 &c, const vec2 &r) { return mat2(c * r.d[0], c * r.d[1]); }
+inline mat2 transpose(const mat2 &m) { return mat2(vec2(m.c[0].d[0], m.c[1].d[0]), vec2(m.c[0].d[1], m.c[1].d[1])); }
+struct ivec4 { union { int d[4]; struct { int x, y, z, w; }; iswz2<ivec2, 4, 0, 1> xy; iswz2<ivec2, 4, 2, 3> zw; }; ivec4() : d{0, 0, 0, 0} {} int operator[](int i) const { return d[i]; } };
+struct uvec4 { union { uint d[4]; struct { uint x, y, z, w; }; }; uvec4() : d{0, 0, 0, 0} {} uint operator[](int i) const { return d[i]; } };
 struct mat3
 { // column major: m[c] is a column, mat3(c0, c1, c2)
   vec3 c[3];

@@ -9,7 +9,7 @@
  - host_graph.json.gz: the whole module pass (config reader, roi negotiation, nodes, committed parameters) of the REFERENCE's own
    graph code over its own default darkroom config (same library).
  - host_cfg.json.gz: return codes and effects of config lines from the REFERENCE's own graph-io.c (same library).
- - shader_ref.npz: outputs of the REFERENCE's own compute shaders compiled as C++ (oracle/glsl -> oracle/_ref/libshaderref.so).
+ - shader_ref.npz / shader_ref.json: outputs (images for the filtering kernels, sha256 digests for the bit exact ones) of the REFERENCE's own compute shaders compiled as C++ (oracle/glsl -> oracle/_ref/libshaderref.so).
  - darkroom_*.npz: outputs of the CPU oracle for the default darkroom graph on a small synthetic frame.  these pin
    the oracle against accidental edits (the float path has no reference-made vectors: parity unpinned).
 """
@@ -277,13 +277,21 @@ def shader_goldens():
     sys.path.insert(0, os.path.dirname(HERE))
     import test_shader_ref_cpu as T
     assert O.ref_shader_lib() is not None, "oracle/_ref/libshaderref.so missing: run `make -C oracle ref` where /root/reference exists"
-    out = {}
+    import json
+    arrays, digests = {}, {}
     for name, fn in T.cases(O).items():
         _, got = fn()
         for k, g in enumerate(got):
-            out["%s/%d" % (name, k)] = np.asarray(g, np.float32).astype(np.float16) if name.split()[0] not in ("grade.main",) else np.asarray(g, np.float32)
-    np.savez_compressed(os.path.join(HERE, "shader_ref.npz"), **out)
-    print("shader goldens:", len(out), "images from", len(T.cases(O)), "cases")
+            g = np.asarray(g, np.float32)
+            if name.startswith(T.SAMPLED):      # compared with a one ulp allowance: the values are needed (all f16 valued)
+                assert np.array_equal(g.astype(np.float16).astype(np.float32), g, equal_nan=True)
+                arrays["%s/%d" % (name, k)] = g.astype(np.float16)
+            else:                               # compared bit for bit: a digest is enough
+                digests["%s/%d" % (name, k)] = T.digest(name, g)
+    np.savez_compressed(os.path.join(HERE, "shader_ref.npz"), **arrays)
+    with open(os.path.join(HERE, "shader_ref.json"), "w") as f:
+        json.dump(digests, f, indent=0, sort_keys=True)
+    print("shader goldens:", len(arrays), "images +", len(digests), "digests from", len(T.cases(O)), "cases")
 
 
 def darkroom_goldens():

@@ -201,6 +201,148 @@ def cases(O):
                 res_o.append(wo)
                 res_s.append(go)
             return res_o, res_s
+    # ---- pointwise chain: crop, colour, filmcurv ------------------------------------------------------------------------
+    for mode in (0, 1, 3, 4, 5):                      # 2 (munsell) needs the lookup table input, not restated
+        @add("filmcurv.main mode %d" % mode)
+        def _(mode=mode):
+            a = rgba(np.random.default_rng(50 + mode), 96, 64, -0.02, 2.0)
+            fp = O.FilmcurvParams(2.5, 1.3, 0.01, mode, 1.1, 0.2, 0.1, -0.1, 0.05, 0.1)
+            res_o, res_s = [], []
+            for out16 in (1, 0):
+                want, wi = img_out(64, 96, 4)
+                L.o_filmcurv_main(C.byref(O.img(a)), C.byref(wi), C.byref(fp), out16)
+                got = np.zeros((64, 96, 4), np.float32)
+                O.ref_shader("filmcurv", "main", bytes(fp), b"", [(a, 0), (got, out16)], 96, 64)
+                res_o.append(want)
+                res_s.append(got)
+            return res_o, res_s
+
+    for k, (matrix, gamut, sat, clip, cnt, mode) in enumerate(((1, 0, 1.0, 0, 4, 0), (2, 0, 1.3, 1, 4, 0), (1, 0, 0.7, 0, 6, 1), (0, 0, 1.0, 0, 4, 0))):
+        @add("colour.main set %d" % k)
+        def _(k=k, matrix=matrix, gamut=gamut, sat=sat, clip=clip, cnt=cnt, mode=mode):
+            rng = np.random.default_rng(60 + k)
+            a = rgba(rng, 96, 64, -0.02, 2.0)
+            d = O.darkroom_defaults(64, 64)
+            p = d.colour
+            p.exposure, p.sat, p.matrix, p.gamut, p.clip, p.clipmax, p.cnt, p.mode = 0.4, sat, matrix, gamut, clip, 1.2, cnt, mode
+            for i, v in enumerate((1.1, -0.05, -0.05, 0.02, 0.9, 0.08, 0.0, -0.1, 1.1)):
+                p.mat[i] = v
+            if mode == 1:
+                for i in range(6 * cnt):
+                    p.rbmap[i] = float(rng.uniform(0.1, 0.8))
+            f, _wb = O.colour_commit_oracle(bytes(p), [2.1, 1.0, 1.6, 1.0], [0.8, 0.15, 0.05, 0.1, 0.85, 0.05, 0.02, 0.18, 0.8], 0, 0)
+            f = np.ascontiguousarray(f, np.float32)
+            res_o, res_s = [], []
+            for out16 in (1,):
+                want, wi = img_out(64, 96, 4)
+                L.o_colour_main(C.byref(O.img(a)), C.byref(wi), O.fptr(f), out16)
+                got = np.zeros((64, 96, 4), np.float32)
+                # clut / pick / abney / spectra / auto_temp are unconnected: the reference binds the input there as a dummy
+                O.ref_shader("colour", "main", f.tobytes(), np.zeros(3, np.int32).tobytes(), [(a, 0), (got, out16), (a, 0), (a, 0), (a, 0), (a, 0), (a, 0)], 96, 64)
+                res_o.append(want)
+                res_s.append(got)
+            return res_o, res_s
+
+    for k, (rot, crop, ori) in enumerate(((1337.0, (1.0, 3.0, 3.0, 7.0), 0), (90.0, (0.1, 0.9, 0.2, 0.8), 0), (7.5, (0.1, 0.9, 0.2, 0.8), 0), (1337.0, (1.0, 3.0, 3.0, 7.0), 6))):
+        @add("crop.main set %d" % k)
+        def _(k=k, rot=rot, crop=crop, ori=ori):
+            w, h = 500, 420                                        # > 400: the automatic 3 px micro crop is active
+            a = rgba(np.random.default_rng(70 + k), w, h, 0.0, 1.5)
+            persp = [0.25, 0.25, 0.75, 0.25, 0.75, 0.75, 0.25, 0.75]
+            ow, oh, f = O.crop_oracle(ori, w, h, persp, crop, rot)
+            want, wi = img_out(oh, ow, 4)
+            L.o_crop_main(C.byref(O.img(a)), C.byref(wi), O.fptr(f))
+            got = np.zeros((oh, ow, 4), np.float32)
+            blob = np.zeros(28, np.float32)                        # std140: mat3 H = three vec4 columns, then r0..r3, crop window
+            for c in range(3):
+                blob[4 * c:4 * c + 3] = f[4 * c:4 * c + 3]
+            blob[12:20] = f[12:20]
+            O.ref_shader("crop", "main", f.tobytes(), b"", [(a, 0), (got, 1)], ow, oh)
+            return [want], [got]
+
+    # ---- denoise -----------------------------------------------------------------------------------------------------------
+    for filters, (w, h), crop in ((BAYER, (96, 64), (0, 0, 96, 64)), (XTRANS, (96, 66), (0, 0, 96, 66)), (BAYER, (100, 68), (4, 2, 96, 62))):
+        blk = 3 if filters == XTRANS else 2
+        tag = "%s %dx%d" % ("xtrans" if filters == XTRANS else "bayer", w, h)
+        black, white = [2048.0 / 65535.0] * 4, [15000.0 / 65535.0] * 4
+        wb, na, nb = (2.0, 1.0, 1.5, 1.0), 100.0, 2.0
+        dp = O.DenoiseParams(0.4, 0.6, 1.0, 0.0, (C.c_float * 4)(0, 0, 0, 0), 1)
+        cw, ch = crop[2] - crop[0], crop[3] - crop[1]
+
+        def raw_unorm(seed, w=w, h=h):
+            rng = np.random.default_rng(seed)
+            v = rng.integers(1500, 16383, (h, w)).astype(np.float32)
+            v[h // 3:h // 2, w // 4:w // 2] = 16383
+            return np.ascontiguousarray((v / np.float32(65535.0)).astype(np.float32))
+
+        def f4(v):
+            return np.array(v, np.float32).tobytes()
+
+        def i4(v):
+            return np.array(v, np.int32).tobytes()
+
+        @add("denoise.noop " + tag)
+        def _(filters=filters, crop=crop, cw=cw, ch=ch, black=black, white=white, dp=dp, raw_unorm=raw_unorm, f4=f4, i4=i4):
+            m = raw_unorm(80)
+            want, wi = img_out(ch, cw, 1)
+            L.o_denoise_noop(C.byref(O.img(m)), C.byref(wi), (C.c_int * 4)(*crop), (C.c_float * 4)(*black), (C.c_float * 4)(*white))
+            got = np.zeros((ch, cw, 4), np.float32)
+            push = i4(crop) + f4(black) + f4(white) + f4([0, 0, 0, 0]) + np.array([filters], np.uint32).tobytes() + i4([0])
+            O.ref_shader("denoise", "noop", bytes(dp) + b"\0" * 12, push, [(m, 0), (got, 1), (m, 0)], cw, ch)
+            return [want.reshape(ch, cw)], [got[..., 0]]            # the shader stores (v, 0, 0, 1); consumers read .r
+
+        @add("denoise.half..doub " + tag)
+        def _(filters=filters, blk=blk, crop=crop, cw=cw, ch=ch, black=black, white=white, wb=wb, na=na, nb=nb, dp=dp, raw_unorm=raw_unorm, f4=f4, i4=i4):
+            m = raw_unorm(81)
+            hw, hh = cw // blk, ch // blk
+            fbits = np.array([filters], np.uint32).tobytes()
+            params = bytes(dp) + b"\0" * 12
+            head = f4(wb) + f4(black) + f4(white) + i4(crop)
+            cI, bI, wI, wbI = (C.c_int * 4)(*crop), (C.c_float * 4)(*black), (C.c_float * 4)(*white), (C.c_float * 4)(*wb)
+            res_o, res_s = [], []
+            # each stage: the oracle's output of the previous stage feeds both sides
+            half, hi = img_out(hh, hw, 4)
+            L.o_denoise_half(C.byref(O.img(m)), C.byref(hi), cI, wI, C.c_uint32(filters))
+            g = np.zeros((hh, hw, 4), np.float32)
+            O.ref_shader("denoise", "half", params, head + fbits, [(m, 0), (g, 1)], hw, hh)
+            res_o.append(half); res_s.append(g)
+            dn = [img_out(hh, hw, 4) for _ in range(4)]
+            cov, ci = img_out(hh, hw, 4)
+            L.o_denoise_downcov(C.byref(hi), C.byref(dn[0][1]), C.byref(ci))
+            g0, gc = np.zeros((hh, hw, 4), np.float32), np.zeros((hh, hw, 4), np.float32)
+            # the crop window travels in the push constants of half and doub only: for a mosaic the reference hands down / downcov / assemble zeros (denoise/main.c:230-262)
+            O.ref_shader("denoise", "downcov", params, head[:48] + i4([0, 0, 0, 0]) + f4([na, nb]) + i4([0, blk]), [(half, 0), (g0, 1), (gc, 1)], hw, hh)
+            res_o += [dn[0][0], cov]; res_s += [g0, gc]
+            for i in range(1, 4):
+                L.o_denoise_down(C.byref(dn[i - 1][1]), C.byref(dn[i][1]), C.byref(dp), bI, wI, C.c_float(na), C.c_float(nb), i, C.c_uint32(blk))
+                gi = np.zeros((hh, hw, 4), np.float32)
+                O.ref_shader("denoise", "down", params, head[:48] + i4([0, 0, 0, 0]) + f4([na, nb]) + i4([i, blk]), [(dn[i - 1][0], 0), (gi, 1)], hw, hh)
+                res_o.append(dn[i][0]); res_s.append(gi)
+            asm, ai = img_out(hh, hw, 4)
+            L.o_denoise_assemble(C.byref(hi), C.byref(dn[0][1]), C.byref(dn[1][1]), C.byref(dn[2][1]), C.byref(dn[3][1]), C.byref(ai), C.byref(dp), wbI, bI, wI,
+                                 C.c_float(na), C.c_float(nb), C.c_uint32(filters))
+            ga = np.zeros((hh, hw, 4), np.float32)
+            O.ref_shader("denoise", "assemble", params, head[:48] + i4([0, 0, 0, 0]) + f4([na, nb]) + fbits,
+                         [(half, 0), (dn[0][0], 0), (dn[1][0], 0), (dn[2][0], 0), (dn[3][0], 0), (ga, 1)], hw, hh)
+            res_o.append(asm); res_s.append(ga)
+            out, oi = img_out(ch, cw, 1)
+            L.o_denoise_doub(C.byref(O.img(m)), C.byref(ai), C.byref(hi), C.byref(oi), C.byref(dp), cI, bI, wI, C.c_float(na), C.c_float(nb), C.c_uint32(filters))
+            gd = np.zeros((ch, cw), np.float32)
+            O.ref_shader("denoise", "doub", params, head + fbits + f4([na, nb]) + i4([0]) + f4([0, 0, 0, 0]), [(m, 0), (asm, 0), (half, 0), (gd, 1), (half, 0)], cw, ch)
+            res_o.append(out.reshape(ch, cw)); res_s.append(gd)
+            return res_o, res_s
+
+    for filters, (w, h) in ((BAYER, (96, 64)), (XTRANS, (96, 66))):
+        @add("demosaic.gauss %s" % ("xtrans" if filters == XTRANS else "bayer"))
+        def _(filters=filters, w=w, h=h):
+            blk = 3 if filters == XTRANS else 2
+            m = mosaic(np.random.default_rng(43), w, h, hot=False)
+            want, wi = img_out(h // blk, w // blk, 4)
+            L.o_demosaic_gauss(C.byref(O.img(m)), C.byref(wi), C.c_uint32(filters))
+            got = np.zeros((h // blk, w // blk, 4), np.float32)
+            dummy = np.zeros((h // blk, w // blk), np.float32)
+            O.ref_shader("demosaic", "gauss", b"", push_wb((1, 1, 1, 1), filters), [(dummy, 0), (m, 0), (got, 1)], w // blk, h // blk)
+            return [want], [got]
     return out
 
 
@@ -220,7 +362,7 @@ def _f16_ulps(a, b):
 # kernels that FILTER (texture() at fractional coordinates): the shader computes its texture coordinates in fp32, the oracle is an
 # ideal sampler that carries them in double (oracle/o_common.h:122-143), so a weight can differ in its last bits and an
 # f16 store can then round the other way.  everything else is bit exact.
-SAMPLED = ("llap.reduce", "llap.assemble")
+SAMPLED = ("llap.reduce", "llap.assemble", "denoise.half..doub")
 
 
 def _report(name, want, got):
@@ -248,22 +390,39 @@ def test_oracle_matches_reference_shaders_live(oracle):
         bad += _report(name, want, got)
         n += len(want)
     assert not bad, "\n".join(bad)
-    assert n >= 60
+    assert n >= 110
+
+
+def digest(name, a):
+    """sha256 over the float32 bytes of what _report compares bit for bit (NaNs canonical, x-trans halfsize without its unwritten alpha)"""
+    import hashlib
+    a = np.asarray(a, np.float32)
+    if name.startswith("demosaic.halfsize xtrans"):
+        a = a[..., :3]
+    a = np.where(np.isnan(a), np.float32(-7), a).astype(np.float32)
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest() + " %s" % (a.shape,)
 
 
 def test_oracle_matches_reference_shader_goldens(oracle):
-    """the same against the shaders' outputs stored when the reference was present (inputs are seeded, so only outputs are stored)"""
+    """the same against what the shaders gave when the reference was present (the inputs are seeded): images for the filtering
+    kernels, sha256 digests for the bit exact ones (tests/golden/shader_ref.npz, shader_ref.json)"""
+    import json
     G = np.load(GOLDEN)
+    D = json.load(open(GOLDEN.replace(".npz", ".json")))
     bad, n = [], 0
     real = oracle.ref_shader
     try:
         oracle.ref_shader = lambda *a, **k: None          # the shader side of each case stays zero: only the oracle side is used
         for name, fn in cases(oracle).items():
             want, _ = fn()
-            got = [G["%s/%d" % (name, k)] for k in range(len(want))]
-            bad += _report(name, want, [g.reshape(np.asarray(w).shape) for g, w in zip(got, want)])
-            n += len(want)
+            for k, w in enumerate(want):
+                key = "%s/%d" % (name, k)
+                if name.startswith(SAMPLED):
+                    bad += _report(key, [w], [G[key].astype(np.float32).reshape(np.asarray(w).shape)])
+                elif digest(name, w) != D[key]:
+                    bad.append("%s: digest differs" % key)
+                n += 1
     finally:
         oracle.ref_shader = real
     assert not bad, "\n".join(bad)
-    assert n >= 60
+    assert n >= 110 and n == len(G.files) + len(D)
