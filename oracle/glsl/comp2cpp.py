@@ -95,7 +95,15 @@ def std140(members):
 
 def fix_body(code):
     code = re.sub(r"\b(?:in\s+)?(?:inout|out)\s+(\w+)\s+(\w+)", r"\1 &\2", code)           # out / inout parameters
-    code = re.sub(r"\b(\w+)\s*\[\s*\d*\s*\]\s*\(", lambda m: "{" if m.group(1) in SCALAR or m.group(1) == "mat3" else m.group(0), code)  # handled below
+    while True:                                                                                # array constructors: float[](a, b) -> {a, b}
+        m = re.search(r"\b(\w+)\s*\[\s*\d*\s*\]\s*\(", code)
+        if not m or not (m.group(1) in SCALAR or m.group(1) in ("mat2", "mat3")):
+            break
+        depth, j = 1, m.end()
+        while depth:
+            depth += {"(": 1, ")": -1}.get(code[j], 0)
+            j += 1
+        code = code[:m.start()] + "{" + code[m.end():j - 1] + "}" + code[j:]
     code = code.replace("^^", "!=")                                                          # logical xor of two bools
     code = re.sub(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][-+]?\d+)?|\d+[eE][-+]?\d+)(?![\w.])", r"\1f", code)   # fp32 literals
     code = re.sub(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][-+]?\d+)?)[lL][fF]\b", r"\1f", code)

@@ -5,11 +5,14 @@
  * and bench.py's cpu_baseline / --impl reference legs may load it (as the checker).
  *
  * Parity status: the MLV bit-unpack restatement is pinned against the reference's own compiled
- * code (oracle/_ref, built from src/pipe/modules/i-mlv/video_mlv.c).  The float kernels are
- * "parity unpinned": the reference's Vulkan/GLSL pipeline cannot be built or run in this
- * container (no vulkan headers/loader/ICD, no glslang) and the reference tree holds no golden
- * vectors for this path.  They are restated line by line from the .comp
- * sources cited at each function.
+ * code (oracle/_ref/libmlvref.so, built from src/pipe/modules/i-mlv/video_mlv.c); the host side
+ * (crop / colour parameter blocks, node graphs) against its own main.c files (libhostref.so); the
+ * float kernels against the reference's own compute shaders compiled as C++ (oracle/glsl,
+ * libshaderref.so, tests/test_shader_ref_cpu.py: bit exact, one f16 ulp on a few values for the
+ * kernels that filter at fractional coordinates).  demosaic/rcd_fill alone is "parity unpinned"
+ * (workgroup shared memory; restated from the .comp source, checked end to end only), and no
+ * Vulkan driver's output is available: the reference's pipeline cannot be run in this container
+ * (no vulkan headers/loader/ICD, no glslang) and its tree holds no golden images.
  *
  * Conventions that every restated kernel follows:
  *  - an image is w*h*c floats, c in {1,4}; a value stored through an f16 connector has been

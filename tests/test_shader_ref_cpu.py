@@ -343,6 +343,25 @@ def cases(O):
             dummy = np.zeros((h // blk, w // blk), np.float32)
             O.ref_shader("demosaic", "gauss", b"", push_wb((1, 1, 1, 1), filters), [(dummy, 0), (m, 0), (got, 1)], w // blk, h // blk)
             return [want], [got]
+    @add("demosaic.rcd_conv")
+    def _():
+        w, h = 96, 64
+        m = mosaic(np.random.default_rng(44), w, h, hot=False)
+        wo = [img_out(h, w, 1), img_out(h, w // 2, 1), img_out(h, w // 2, 1)]
+        L.o_rcd_conv(C.byref(O.img(m)), C.byref(wo[0][1]), C.byref(wo[1][1]), C.byref(wo[2][1]))
+        go = [np.zeros((h, w), np.float32), np.zeros((h, w // 2), np.float32), np.zeros((h, w // 2), np.float32)]
+        O.ref_shader("demosaic", "rcd_conv", b"", b"", [(m, 0), (go[0], 1), (go[1], 1), (go[2], 1)], w, h)
+        return [x[0].reshape(g.shape) for x, g in zip(wo, go)], go
+
+    for (ow, oh) in ((96, 64), (90, 60)):             # 1:1 (what vkdt-cli inserts behind demosaic) and a mild downscale
+        @add("shared.resample to %dx%d" % (ow, oh))
+        def _(ow=ow, oh=oh):
+            a = rgba(np.random.default_rng(45), 96, 64, 0.0, 1.5)
+            want, wi = img_out(oh, ow, 4)
+            L.o_resample(C.byref(O.img(a)), C.byref(wi))
+            got = np.zeros((oh, ow, 4), np.float32)
+            O.ref_shader("shared", "resample", b"", b"", [[(a, 0)], [(got, 1)]], ow, oh)
+            return [want], [got]
     return out
 
 
@@ -362,7 +381,7 @@ def _f16_ulps(a, b):
 # kernels that FILTER (texture() at fractional coordinates): the shader computes its texture coordinates in fp32, the oracle is an
 # ideal sampler that carries them in double (oracle/o_common.h:122-143), so a weight can differ in its last bits and an
 # f16 store can then round the other way.  everything else is bit exact.
-SAMPLED = ("llap.reduce", "llap.assemble", "denoise.half..doub")
+SAMPLED = ("llap.reduce", "llap.assemble", "denoise.half..doub", "shared.resample")
 
 
 def _report(name, want, got):
