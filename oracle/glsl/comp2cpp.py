@@ -114,9 +114,18 @@ def main():
     moddir, module, kernel = sys.argv[1:4]
     text = preprocess(moddir, module, kernel)
     decls = split_toplevel(text)
-    blocks, images, funcs, others = [], [], {}, []
+    blocks, images, funcs, others, local = [], [], {}, [], {"x": 8, "y": 8}
     for d in decls:
-        if re.match(r"layout\s*\([^)]*\)\s*in\s*;", d):
+        m = re.match(r"layout\s*\(([^)]*)\)\s*in\s*;", d)
+        if m:
+            for axis in "xy":
+                mm = re.search(r"local_size_%s\s*=\s*\(?\s*(\d+)" % axis, m.group(1))
+                if mm:
+                    local[axis] = int(mm.group(1))
+            continue
+        m = re.match(r"shared\s+(.*)", d, re.S)
+        if m:                                   # workgroup shared memory: one workgroup runs at a time, a plain global does
+            others.append("static " + m.group(1))
             continue
         m = re.match(r"layout\s*\(([^)]*)\)\s*uniform\s+(\w+)\s*\{(.*)\}\s*(\w+)\s*;", d, re.S)
         if m:
@@ -170,7 +179,7 @@ def main():
     used_text = "\n".join(funcs[f] for f in keep)
     ns = "shader_%s_%s" % (re.sub(r"\W", "_", module), re.sub(r"\W", "_", kernel))
     o = ['// generated by oracle/glsl/comp2cpp.py from %s/%s.comp of the reference: do not commit' % (module, kernel), '#include "glsl_shim.h"',
-         "namespace glsl { namespace %s {" % ns, "static uvec3 gl_GlobalInvocationID;"]
+         "namespace glsl { namespace %s {" % ns, "static thread_local uvec3 gl_GlobalInvocationID, gl_LocalInvocationID, gl_WorkGroupID;"]
     for kind, tname, inst, members in blocks:
         o.append("struct %s { %s };" % (tname, " ".join("%s %s%s;" % (t, n, "[%d]" % c if c else "") for t, n, c in members)))
         o.append("static %s %s;" % (tname, inst))
@@ -178,7 +187,7 @@ def main():
     for b, name, arr in images:
         o.append("static image_t %s%s;" % (name, "[64]" if arr else ""))
     for d in others:   # global constants and structs, only those the kept functions mention
-        m = re.match(r"(?:const\s+)?(?:struct\s+)?\w+\s+(\w+)", d)
+        m = re.match(r"(?:static\s+)?(?:const\s+)?(?:struct\s+)?\w+\s+(\w+)", d)
         if m and re.search(r"\b%s\b" % re.escape(m.group(1)), used_text + "\n".join(x for x in others if x is not d)):
             o.append(fix_body(d))
     order = [f for f in funcs if f in keep]    # source order: callees are defined before their callers in GLSL
@@ -205,7 +214,14 @@ def main():
             o.append("  if(counts[%d] > 64) return -3; for(int k = 0; k < counts[%d]; k++) %s[k] = imgs[at + k]; at += counts[%d];" % (i, i, name, i))
         else:
             o.append("  %s = imgs[at]; at += counts[%d];" % (name, i))
-    o.append("  for(int z = 0; z < dp; z++) for(int y = 0; y < ht; y++) for(int x = 0; x < wd; x++) { gl_GlobalInvocationID = uvec3(x, y, z); shader_main(); }")
+    if re.search(r"\bbarrier\s*\(", used_text):
+        # the reference dispatches ceil(wd / 8) x ceil(ht / 8) workgroups whatever the shader's local size is (record-cmd.h:377-380):
+        # nodes with other local sizes pre-scale wd / ht (demosaic/main.c:125-131)
+        o.append("  const int lx = %d, ly = %d;" % (local["x"], local["y"]))
+        o.append("  for(int gy = 0; gy < (ht + 7) / 8; gy++) for(int gx = 0; gx < (wd + 7) / 8; gx++)")
+        o.append("    run_workgroup(lx, ly, [gx, gy, lx, ly](int x, int y) { gl_WorkGroupID = uvec3(gx, gy, 0); gl_LocalInvocationID = uvec3(x, y, 0); gl_GlobalInvocationID = uvec3(gx * lx + x, gy * ly + y, 0); shader_main(); });")
+    else:
+        o.append("  for(int z = 0; z < dp; z++) for(int y = 0; y < ht; y++) for(int x = 0; x < wd; x++) { gl_GlobalInvocationID = uvec3(x, y, z); shader_main(); }")
     o.append("  return 0;\n}")
     print("\n".join(o))
 

@@ -10,9 +10,12 @@
 #include <cstring>
 #include <algorithm>
 #include <vector>
+#include <barrier>
+#include <thread>
 
 namespace glsl {
 typedef unsigned int uint;
+typedef _Float16 float16_t;   // GL_EXT_shader_explicit_arithmetic_types_float16: storage type of rcd_fill's shared memory tiles
 
 // ---- swizzles: a proxy that lives in a union with the vector's storage ------------------------------------------------
 template<class V, int P, int... I> struct swz
@@ -102,13 +105,13 @@ struct vec4
   vec4 &operator=(const vec4 &o) { for(int i = 0; i < 4; i++) d[i] = o.d[i]; return *this; }
   GLSL_VEC_OPS(vec4, 4)
 };
-struct uvec3 { union { uint d[3]; struct { uint x, y, z; }; }; uvec3(uint a = 0, uint b = 0, uint c = 0) : d{a, b, c} {} };
+struct uvec3 { union { uint d[3]; struct { uint x, y, z; }; iswz2<ivec2, 3, 0, 1> xy; }; uvec3(uint a = 0, uint b = 0, uint c = 0) : d{a, b, c} {} };
 struct bvec2 { bool d[2]; };
 struct bvec3 { union { bool d[3]; struct { bool x, y, z; }; }; bvec3() : d{false, false, false} {} explicit bvec3(bool b) : d{b, b, b} {} bvec3(bool a, bool b, bool c) : d{a, b, c} {} };
 struct bvec4 { bool d[4]; };
 struct ivec2
 {
-  union { int d[2]; struct { int x, y; }; iswz2<ivec2, 2, 0, 1> xy; iswz2<ivec2, 2, 1, 0> yx; };
+  union { int d[2]; struct { int x, y; }; struct { int r, g; }; iswz2<ivec2, 2, 0, 1> xy; iswz2<ivec2, 2, 1, 0> yx; };
   ivec2() : d{0, 0} {}
   explicit ivec2(int s) : d{s, s} {}
   ivec2(int a, int b) : d{a, b} {}
@@ -116,6 +119,10 @@ struct ivec2
   explicit ivec2(const vec2 &v) : d{(int)v.d[0], (int)v.d[1]} {}   // conversion truncates towards zero
   int &operator[](int i) { return d[i]; }
   int operator[](int i) const { return d[i]; }
+  ivec2 &operator+=(const ivec2 &b) { x += b.x; y += b.y; return *this; }
+  ivec2 &operator-=(const ivec2 &b) { x -= b.x; y -= b.y; return *this; }
+  ivec2 &operator*=(int b) { x *= b; y *= b; return *this; }
+  ivec2 &operator/=(int b) { x /= b; y /= b; return *this; }
   friend ivec2 operator+(const ivec2 &a, const ivec2 &b) { return ivec2(a.x + b.x, a.y + b.y); }
   friend ivec2 operator-(const ivec2 &a, const ivec2 &b) { return ivec2(a.x - b.x, a.y - b.y); }
   friend ivec2 operator*(const ivec2 &a, const ivec2 &b) { return ivec2(a.x * b.x, a.y * b.y); }
@@ -195,6 +202,7 @@ inline ivec2 clamp(const ivec2 &x, const ivec2 &lo, const ivec2 &hi) { return iv
 inline ivec2 max(const ivec2 &a, const ivec2 &b) { return ivec2(max(a.x, b.x), max(a.y, b.y)); }
 inline ivec2 min(const ivec2 &a, const ivec2 &b) { return ivec2(min(a.x, b.x), min(a.y, b.y)); }
 inline float mix(float a, float b, float t) { return a * (1.0f - t) + b * t; }
+inline float mix(float a, float b, bool t) { return t ? b : a; }
 inline vec2  mix(const vec2 &a, const vec2 &b, float t) { return a * (1.0f - t) + b * t; }
 inline vec3  mix(const vec3 &a, const vec3 &b, float t) { return a * (1.0f - t) + b * t; }
 inline vec4  mix(const vec4 &a, const vec4 &b, float t) { return a * (1.0f - t) + b * t; }
@@ -324,4 +332,17 @@ inline vec4 textureGather(const sampler2D &s, const vec2 &uv, int comp)
   return vec4(image_fetch(s, i0, j1).d[comp], image_fetch(s, i1, j1).d[comp], image_fetch(s, i1, j0).d[comp], image_fetch(s, i0, j0).d[comp]);
 }
 inline vec4 textureLod(const sampler2D &s, const vec2 &uv, float) { return texture(s, uv); }
+// ---- workgroups: shaders that call barrier() run one thread per invocation of a workgroup -------------------------------------
+inline thread_local std::barrier<> *current_barrier = 0;
+inline void barrier() { if(current_barrier) current_barrier->arrive_and_wait(); }
+inline void memoryBarrierShared() {}
+template<class F> inline void run_workgroup(int lx, int ly, F &&invocation)
+{ // invocation(local x, local y) sets the built-in ids and runs main(); a thread that returns early drops out of the barrier
+  std::barrier<> bar(lx * ly);
+  std::vector<std::thread> th;
+  th.reserve((size_t)lx * ly);
+  for(int y = 0; y < ly; y++) for(int x = 0; x < lx; x++)
+    th.emplace_back([&bar, &invocation, x, y]() { current_barrier = &bar; invocation(x, y); bar.arrive_and_drop(); });
+  for(std::thread &t : th) t.join();
+}
 } // namespace glsl

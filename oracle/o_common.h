@@ -9,8 +9,8 @@
  * (crop / colour parameter blocks, node graphs) against its own main.c files (libhostref.so); the
  * float kernels against the reference's own compute shaders compiled as C++ (oracle/glsl,
  * libshaderref.so, tests/test_shader_ref_cpu.py: bit exact, one f16 ulp on a few values for the
- * kernels that filter at fractional coordinates).  demosaic/rcd_fill alone is "parity unpinned"
- * (workgroup shared memory; restated from the .comp source, checked end to end only), and no
+ * kernels that filter at fractional coordinates; demosaic/rcd_fill away from the reference's
+ * tile seams, where its output depends on the tiling).  What stays unpinned: no
  * Vulkan driver's output is available: the reference's pipeline cannot be run in this container
  * (no vulkan headers/loader/ICD, no glslang) and its tree holds no golden images.
  *

@@ -353,6 +353,28 @@ def cases(O):
         O.ref_shader("demosaic", "rcd_conv", b"", b"", [(m, 0), (go[0], 1), (go[1], 1), (go[2], 1)], w, h)
         return [x[0].reshape(g.shape) for x, g in zip(wo, go)], go
 
+    @add("demosaic.rcd_fill")
+    def _():
+        w, h = 96, 64
+        m = mosaic(np.random.default_rng(46), w, h, hot=False)
+        planes = [img_out(h, w, 1), img_out(h, w // 2, 1), img_out(h, w // 2, 1)]
+        L.o_rcd_conv(C.byref(O.img(m)), C.byref(planes[0][1]), C.byref(planes[1][1]), C.byref(planes[2][1]))
+        wb = (2.0, 1.0, 1.5, 1.0)
+        want, wi = img_out(h, w, 4)
+        L.o_rcd_fill(C.byref(O.img(m)), C.byref(planes[0][1]), C.byref(planes[1][1]), C.byref(planes[2][1]), C.byref(wi), (C.c_float * 4)(*wb))
+        got = np.zeros((h, w, 4), np.float32)
+        # 58 x 26 px tiles of 32 x 32 invocations, dispatched as tiles * 8 (demosaic/main.c:125-131); runs one thread per invocation
+        O.ref_shader("demosaic", "rcd_fill", b"", push_wb(wb, BAYER), [(m, 0)] + [(np.ascontiguousarray(x[0].reshape(x[0].shape[0], -1)), 0) for x in planes] + [(got, 1)],
+                     (w + 57) // 58 * 8, (h + 25) // 26 * 8)
+        # the reference keeps 58 x 26 px of every 64 x 32 tile (DT_RCD_BORDER = 3) while the second and third step reach 4 px through
+        # the shared memory tile (rcd_fill.comp:96-99, 114-135): within 3 px of a tile seam, and within 6 px of the image border, its
+        # output depends on the tiling (reads beyond the tile wrap into neighbouring rows of the shared arrays).  the oracle and the
+        # product are tiling independent (deviation 5); everywhere else the two have to agree bit for bit
+        yy, xx = np.mgrid[0:h, 0:w]
+        keep = ((xx % 58 >= 3) & (xx % 58 < 55) & (yy % 26 >= 3) & (yy % 26 < 23) & (xx >= 6) & (xx < w - 6) & (yy >= 6) & (yy < h - 6))
+        assert keep.sum() > 3000
+        return [np.asarray(want).reshape(h, w, 4)[keep]], [got[keep]]
+
     for (ow, oh) in ((96, 64), (90, 60)):             # 1:1 (what vkdt-cli inserts behind demosaic) and a mild downscale
         @add("shared.resample to %dx%d" % (ow, oh))
         def _(ow=ow, oh=oh):
