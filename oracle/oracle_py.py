@@ -352,3 +352,90 @@ def ref_shader(module, kernel, params, push, bindings, wd, ht, dp=1):
     fn = getattr(ref_shader_lib(), "shader_%s_%s" % (module.replace("-", "_"), kernel))
     r = fn(bytes(params), len(bytes(params)), bytes(push), len(bytes(push)), arr, (C.c_int * len(counts))(*counts), len(counts), wd, ht, dp)
     assert r == 0, "shader_%s_%s failed: %d" % (module, kernel, r)
+
+
+def ref_pipeline_run(text, raw, trace=None):
+    """execute the REFERENCE's own node graph with the REFERENCE's own shaders, on the CPU: `text` is what ref_graph_describe() wrote
+    (module pass of the reference's graph code: nodes, dispatch sizes, push constants, connector formats, wiring, parameter and
+    committed blocks), every node runs <name>/<kernel>.comp through ref_shader() on images laid out as its connectors say (f16
+    connectors round on store).  raw: (h, w) uint16 mosaic, read by the first node's consumers as UNORM (x / 65535, allocate.h:72-81).
+    the module chain is linear (default darkroom graphs): a module's `input` is the output of the module before it.
+    returns the image the sink receives, (h, w, 4) float32.  trace: optional dict filled with {"module:kernel#node": outputs}."""
+    mods, cur, node = [], None, None
+    for ln in text.splitlines():
+        t = ln.split()
+        if ln.startswith("module "):
+            cur = dict(name=t[1], params=b"", committed=None, mconn=[], nodes=[])
+            mods.append(cur)
+        elif ln.startswith(" params"):
+            cur["params"] = bytes.fromhex(t[1]) if len(t) > 1 else b""
+        elif ln.startswith(" committed"):
+            cur["committed"] = bytes.fromhex(t[1])
+        elif ln.startswith(" mconn"):
+            name, typ, chan, fmt = t[2].split(":")
+            assert t[-1] == "bypass=-1", "bypassed modules are not handled"
+            cur["mconn"].append(dict(name=name, type=typ))
+        elif ln.startswith(" node"):
+            wd, ht, dp = [int(x) for x in t[3].split("x")]
+            pc = t[4].split(":", 1)[1]
+            node = dict(name=t[2], wd=wd, ht=ht, dp=dp, push=b"".join(int(x, 16).to_bytes(4, "little") for x in pc.split(",")) if pc else b"", conn=[], out=None)
+            cur["nodes"].append(node)
+        elif ln.startswith("  conn"):
+            name, typ, chan, fmt = t[2].split(":")
+            w, h = [int(x) for x in t[3].split("/")[1].split("x")]
+            nchan = 1 if chan in ("rggb", "rgbx", "ssbo") or len(chan) == 1 else (2 if len(chan) == 2 else 4)
+            node["conn"].append(dict(name=name, type=typ, chan=nchan, fmt=fmt, w=w, h=h, al=max(1, int(t[4][3:])), link=t[5], buf=None))
+    h, w = raw.shape
+    unorm = np.ascontiguousarray(raw.astype(np.float32) / np.float32(65535.0))
+
+    def module_output(mi):
+        """the node connector that carries module mi's output"""
+        oc = [i for i, c in enumerate(mods[mi]["mconn"]) if c["type"] in ("write", "source") and c["name"] == "output"][0]
+        for n in mods[mi]["nodes"]:
+            for c in n["conn"]:
+                if c["type"] in ("write", "source") and c["link"] == "mod.%d" % oc:
+                    return mi, n, c
+        raise AssertionError("module %s has no node on its output" % mods[mi]["name"])
+
+    def run(mi, n):
+        if n["out"] is not None:
+            return
+        n["out"] = True
+        m = mods[mi]
+        if n["name"] == "i-raw:main" or n["name"] == "i-mlv:main":
+            n["conn"][0]["buf"] = [unorm]
+            return
+        binds, first_input = [], None
+        for c in n["conn"]:
+            if c["type"] in ("write",):
+                c["buf"] = [np.zeros((c["h"], c["w"]) if c["chan"] == 1 else (c["h"], c["w"], c["chan"]), np.float32) for _ in range(c["al"])]
+                binds.append([(b, 0 if c["fmt"] == "f32" else 1) for b in c["buf"]])
+                continue
+            src = None
+            if c["link"].startswith("n"):
+                k, cc = [int(x) for x in c["link"][1:].split(".")]
+                run(mi, m["nodes"][k])
+                src = m["nodes"][k]["conn"][cc]["buf"]
+            elif c["link"].startswith("mod.") and m["mconn"][int(c["link"][4:])]["name"] == "input":
+                pm, pn, pc = module_output(mi - 1)
+                run(pm, pn)
+                src = pc["buf"]
+            if src is None:                       # unconnected lut / gainmap inputs: the reference binds a dummy (graph-run-nodes-allocate.h)
+                src = first_input
+            assert src is not None, (m["name"], n["name"], c["name"])
+            if first_input is None:
+                first_input = src
+            c["buf"] = src
+            binds.append([(b, 0) for b in src])
+        if n["name"].startswith("o-") or n["name"] == "display:main":
+            return
+        module, kernel = n["name"].split(":")
+        ref_shader(module, kernel, m["committed"] if m["committed"] is not None else m["params"] + b"\0" * 16, n["push"] + b"\0" * 16,
+                   [b if len(b) > 1 else b[0] for b in binds], n["wd"], n["ht"], n["dp"])
+        if trace is not None:
+            trace["%s#%d" % (n["name"], m["nodes"].index(n))] = [c["buf"] for c in n["conn"] if c["type"] == "write"]
+
+    sink = mods[-1]["nodes"][0]
+    run(len(mods) - 1, sink)
+    out = sink["conn"][0]["buf"][0]
+    return out

@@ -10,6 +10,7 @@
    graph code over its own default darkroom config (same library).
  - host_cfg.json.gz: return codes and effects of config lines from the REFERENCE's own graph-io.c (same library).
  - shader_ref.npz / shader_ref.json: outputs (images for the filtering kernels, sha256 digests for the bit exact ones) of the REFERENCE's own compute shaders compiled as C++ (oracle/glsl -> oracle/_ref/libshaderref.so).
+ - pipeline_ref.npz: the default darkroom graph end to end from the REFERENCE's own graph code + own shaders on the CPU.
  - darkroom_*.npz: outputs of the CPU oracle for the default darkroom graph on a small synthetic frame.  these pin
    the oracle against accidental edits (the float path has no reference-made vectors: parity unpinned).
 """
@@ -294,6 +295,17 @@ def shader_goldens():
     print("shader goldens:", len(arrays), "images +", len(digests), "digests from", len(T.cases(O)), "cases")
 
 
+def pipeline_goldens():
+    """what the sink receives when the REFERENCE's own graph code and own shaders run on the CPU (oracle.ref_graph_describe +
+    oracle.ref_pipeline_run): the default darkroom graph end to end, four configurations (tests/test_pipeline_ref_cpu.py)."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import test_pipeline_ref_cpu as T
+    out = {name: T.reference_output(O, name).astype(np.float32) for name in T.CASES}
+    np.savez_compressed(os.path.join(HERE, "pipeline_ref.npz"), **out)
+    for name in T.CASES:
+        print("pipeline golden", name, "vs oracle: max abs %.3g, psnr %.1f dB" % T.check(name, out[name], T.oracle_output(O, name)))
+
+
 def darkroom_goldens():
     w, h = 168, 126
     raw = synth.mosaic(w, h, seed=77)
@@ -316,4 +328,5 @@ if __name__ == "__main__":
     graph_goldens()
     cfg_goldens()
     shader_goldens()
+    pipeline_goldens()
     darkroom_goldens()
