@@ -78,3 +78,31 @@ def test_reference_pipeline_on_cpu_matches_oracle_live(oracle, name):
 @pytest.mark.parametrize("name", list(CASES))
 def test_reference_pipeline_golden_matches_oracle(oracle, name):
     check(name, np.load(GOLDEN)[name], oracle_output(oracle, name))
+
+
+VARIANTS = [  # (width, height, config lines, the same settings on the oracle's struct)
+    (504, 420, [], lambda d: None),                                   # > 400 px: crop's automatic 3 px micro crop is active -> 498 x 414
+    (240, 180, ["param:crop:01:rotate:7.5", "param:crop:01:crop:0.1:0.9:0.2:0.8"],
+     lambda d: (setattr(d.crop, "rotate", 7.5), [d.crop.crop.__setitem__(k, v) for k, v in enumerate((0.1, 0.9, 0.2, 0.8))])),
+    (240, 180, ["param:crop:01:rotate:90"], lambda d: setattr(d.crop, "rotate", 90.0)),          # quarter turn -> 239 x 180 out of float arithmetic
+    (240, 180, ["param:colour:01:exposure:0.7", "param:filmcurv:01:colour:1", "param:filmcurv:01:light:2.0", "param:llap:01:clarity:0.5"],
+     lambda d: (setattr(d.colour, "exposure", 0.7), setattr(d.filmcurv, "colour", 1), setattr(d.filmcurv, "light", 2.0), setattr(d.llap, "clarity", 0.5))),
+    (240, 180, ["param:demosaic:01:method:2"], lambda d: setattr(d.demosaic, "method", 2)),       # half size demosaic + resample
+]
+
+
+@pytest.mark.parametrize("k", range(len(VARIANTS)))
+def test_reference_pipeline_variants_live(oracle, k):
+    """sizes and parameters that change the graph's geometry or its kernels' branches, live against the compiled reference"""
+    if oracle.ref_shader_lib() is None or oracle.ref_host_lib() is None or not os.path.isdir("/root/reference/src/pipe/modules"):
+        pytest.skip("needs oracle/_ref/lib{host,shader}ref.so and /root/reference (make -C oracle ref)")
+    w, h, lines, setup = VARIANTS[k]
+    raw = synth.mosaic(w, h, seed=5)
+    ref = oracle.ref_pipeline_run(oracle.ref_graph_describe(w, h, lines, dict(wb=WB, noise_a=NOISE[0], noise_b=NOISE[1])), raw)[..., :3]
+    d = oracle.darkroom_defaults(w, h)
+    for c, v in enumerate(WB):
+        d.whitebalance[c] = v
+    d.noise_a, d.noise_b = NOISE
+    d.enable_grade = 1
+    setup(d)
+    check("variant %d" % k, ref, oracle.darkroom_run(d, raw)[..., :3])
