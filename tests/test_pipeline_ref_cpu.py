@@ -106,3 +106,22 @@ def test_reference_pipeline_variants_live(oracle, k):
     d.enable_grade = 1
     setup(d)
     check("variant %d" % k, ref, oracle.darkroom_run(d, raw)[..., :3])
+
+
+def test_reference_mlv_pipeline_live(oracle, tmp_path):
+    """bin/default-darkroom.i-mlv with the reference's own i-mlv/main.c reading the clip header (image parameters incl. the camera
+    matrix for a camera outside dcraw's table: xyz_to_rec2020) against the oracle configured the way tests/test_graph_gpu.py
+    configures it for the product's MLV file test."""
+    if oracle.ref_shader_lib() is None or oracle.ref_host_lib() is None or not os.path.isdir("/root/reference/src/pipe/modules"):
+        pytest.skip("needs oracle/_ref/lib{host,shader}ref.so and /root/reference (make -C oracle ref)")
+    w, h = 168, 126
+    raw = synth.mosaic(w, h, seed=21)
+    fn = str(tmp_path / "clip.mlv")
+    synth.write_mlv(fn, [raw], black=2048, white=15000)
+    text = oracle.ref_graph_describe(w, h, ["param:i-mlv:main:filename:" + fn], {}, cfg="bin/default-darkroom.i-mlv")
+    ref = oracle.ref_pipeline_run(text, raw)[..., :3]
+    d = oracle.darkroom_defaults(w, h)
+    for k, v in enumerate((1.7166511880, -0.3556707838, -0.2533662814, -0.6666843518, 1.6164812366, 0.0157685458, 0.0176398574, -0.0427706133, 0.9421031212)):
+        d.cam_to_rec2020[k] = v
+    d.enable_grade = 0                                  # the reference's i-mlv default graph ends in llap
+    check("mlv", ref, oracle.darkroom_run(d, raw)[..., :3])
