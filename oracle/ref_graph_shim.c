@@ -255,3 +255,24 @@ int ref_config_lines(const char *basedir, const char *cfgfile, const char *lines
   free(g->params_pool); free(g->node); free(g->module); free(g);
   return n;
 }
+
+/* the reference's own o-pfm write_sink (o-pfm/main.c:8-42) on a width x height rgba f32 buffer: writes <basename>.pfm */
+void opfm_ref_write_sink(dt_module_t *, void *, dt_write_sink_params_t *);
+int ref_write_pfm(const char *basename, const float *rgba, int width, int height)
+{
+  static dt_ui_param_t par;
+  static dt_module_so_t so;
+  dt_module_t *mod = calloc(1, sizeof(*mod));
+  char name[256];
+  snprintf(name, sizeof(name), "%s", basename);
+  memset(&so, 0, sizeof(so)); memset(&par, 0, sizeof(par));
+  par.name = dt_token("filename"); par.type = dt_token("string"); par.cnt = 256; par.offset = 0;
+  so.param[0] = &par; so.num_params = 1;
+  mod->so = &so; mod->param = (uint8_t *)name; mod->param_size = 256;
+  mod->num_connectors = 1;
+  mod->connector[0].roi.wd = mod->connector[0].roi.full_wd = width;
+  mod->connector[0].roi.ht = mod->connector[0].roi.full_ht = height;
+  opfm_ref_write_sink(mod, (void *)rgba, 0);
+  free(mod);
+  return 0;
+}

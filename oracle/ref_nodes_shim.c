@@ -16,6 +16,7 @@
 #define create_nodes   REF_CAT(REFMOD, ref_create_nodes)
 #define commit_params  REF_CAT(REFMOD, ref_commit_params)
 #define audio          REF_CAT(REFMOD, ref_audio)
+#define write_sink     REF_CAT(REFMOD, ref_write_sink)
 #include REFMAIN
 #include "ref_nodes_driver.h"
 
