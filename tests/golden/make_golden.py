@@ -12,7 +12,7 @@
  - shader_ref.npz / shader_ref.json: outputs (images for the filtering kernels, sha256 digests for the bit exact ones) of the REFERENCE's own compute shaders compiled as C++ (oracle/glsl -> oracle/_ref/libshaderref.so).
  - pipeline_ref.npz: the default darkroom graph end to end from the REFERENCE's own graph code + own shaders on the CPU.
  - darkroom_*.npz: outputs of the CPU oracle for the default darkroom graph on a small synthetic frame.  these pin
-   the oracle against accidental edits (the float path has no reference-made vectors: parity unpinned).
+   the oracle's whole graph against accidental edits (the reference-made vectors for the float path are shader_ref.* and pipeline_ref.npz).
 """
 import os
 import sys
