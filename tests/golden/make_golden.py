@@ -227,6 +227,21 @@ def write_golden_clip(name):
     return fn
 
 
+PFM_CFG = ("module:i-pfm:main\nmodule:colour:01\nmodule:filmcurv:01\nmodule:display:main\nconnect:i-pfm:main:output:colour:01:input\n"
+           "connect:colour:01:output:filmcurv:01:input\nconnect:filmcurv:01:output:display:main:input\nparam:i-pfm:main:filename:%s\n")
+
+
+def write_golden_pfm():
+    """an intermediate image as another vkdt would hand it over with o-pfm, and a cfg that develops it from colour on"""
+    os.makedirs(MLV_DIR, exist_ok=True)
+    fn = os.path.join(MLV_DIR, "mid.pfm")
+    synth.write_pfm(fn, np.random.default_rng(0).random((40, 64, 3), dtype=np.float32))
+    cfg = os.path.join(MLV_DIR, "pfm.cfg")
+    with open(cfg, "w") as f:
+        f.write(PFM_CFG % fn)
+    return fn, cfg
+
+
 def graph_goldens():
     """the module pass of the REFERENCE's own graph code over its own bin/default-darkroom.i-raw (oracle/ref_graph_shim.c: global.c,
     module.c, graph-io.c, connector.c, graph-export.c, graph-run-modules.h and the seven module main.c files compiled in place; only
@@ -242,6 +257,9 @@ def graph_goldens():
         fn = write_golden_clip(name)
         lines = ["param:i-mlv:main:filename:" + fn] + (["param:denoise:01:strength:0.3"] if bpp == 12 else [])
         cases.append(dict(lines=lines, w=w, h=h, raw={}, mlv=name, text=O.ref_graph_describe(w, h, lines, {}, cfg="bin/default-darkroom.i-mlv")))
+    # i-pfm (the reference's own i-pfm/main.c reading the header) in front of colour and filmcurv
+    fn, cfg = write_golden_pfm()
+    cases.append(dict(lines=[], w=64, h=40, raw={}, pfm=1, text=O.ref_graph_describe(64, 40, [], {}, cfg=cfg)))
     with gzip.GzipFile(os.path.join(HERE, "host_graph.json.gz"), "wb", mtime=0) as f:
         f.write(json.dumps(cases, indent=0).encode())
     print("graph goldens:", len(cases), "graphs,", sum(c["text"].count("\n") for c in cases), "lines")

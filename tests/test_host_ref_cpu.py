@@ -234,6 +234,10 @@ MLV_CFG = api.DARKROOM_CFG.format(src="i-mlv").replace("connect:llap:01:output:g
 
 
 def _graph_text_product(case):
+    if "pfm" in case:
+        mg = _make_golden_module()
+        fn, _cfg = mg.write_golden_pfm()
+        return api.Graph(cfg_text=mg.PFM_CFG % fn).describe().splitlines()
     if "mlv" in case:
         _make_golden_module().write_golden_clip(case["mlv"])     # same pixels, same path as when the golden was made
         g = api.Graph(cfg_text=MLV_CFG)
@@ -282,7 +286,7 @@ def test_product_module_pass_matches_reference_graph_code():
         assert len(ref) == len(got), (case["lines"], case["w"], case["h"], len(ref), len(got))
         bad = [(a[:200], b[:200]) for a, b in zip(ref, got) if a != b]
         assert not bad, (case["lines"], case["w"], case["h"], bad[:3])
-    assert len(GRAPHS) >= 24 and sum("mlv" in c for c in GRAPHS) == 2
+    assert len(GRAPHS) >= 25 and sum("mlv" in c for c in GRAPHS) == 2 and sum("pfm" in c for c in GRAPHS) == 1
 
 
 def test_live_reference_graph_random(oracle):

@@ -338,8 +338,7 @@ static void ipfm_roi_out(dt_graph_t *g, dt_module_t *mod)
   ip->noise_b = dt_module_param_float(mod, 3)[0];
   ip->filters = 0;
   ip->colour_primaries = 2; // s_colour_primaries_2020
-  ip->colour_trc = 0;       // linear
-  ip->cam_to_rec2020[0] = ip->cam_to_rec2020[4] = ip->cam_to_rec2020[8] = 1.0f;
+  ip->colour_trc = 0;       // linear; cam_to_rec2020 stays zero like in the reference (i-pfm/main.c:69-83): rec2020 input does not use it
   mod->connector[0].chan = p->channels == 1 ? dt_token("y") : dt_token("rgba");
   mod->connector[0].roi.full_wd = p->width;
   mod->connector[0].roi.full_ht = p->height;
