@@ -165,15 +165,7 @@ def test_product_node_graphs_match_reference():
         for module, text in case["modules"].items():
             ref = _documented_deviations(module, _blocks(text)[module], case)
             got = mine[module]
-            if module == "filmcurv":
-                # 3. the histogram / dspy nodes feed a gui widget only (filmcurv/main.c:18-36): not built.  the main node has to agree
-                rn = [n for n in _node_blocks(ref) if "filmcurv:main" in n[0]]
-                gn = [n for n in _node_blocks(got) if "filmcurv:main" in n[0]]
-                assert len(rn) == 1 and len(gn) == 1
-                assert re.sub(r"node \d+", "node", rn[0][0]) == re.sub(r"node \d+", "node", gn[0][0]) and rn[0][1] == gn[0][1], (case["lines"], module)
-                assert [l for l in ref if l.startswith(" mconn")] == [l for l in got if l.startswith(" mconn")]
-            else:
-                assert ref == got, (case["lines"], case["w"], case["h"], module, [(a, b) for a, b in zip(ref, got) if a != b][:4])
+            assert ref == got, (case["lines"], case["w"], case["h"], module, [(a, b) for a, b in zip(ref, got) if a != b][:4])
             checked += 1
     assert checked >= 75
 
@@ -207,8 +199,6 @@ def test_live_reference_nodes_random(oracle):
         case = dict(lines=lines, w=w, h=h, raw=raw)
         mine = _blocks(_describe(lines, w, h, raw))
         for module, text in mg.reference_nodes(lines, w, h, raw).items():
-            if module == "filmcurv":
-                continue
             assert _documented_deviations(module, _blocks(text)[module], case) == mine[module], (case, module)
 
 
@@ -258,19 +248,8 @@ def _graph_text_product(case):
 
 
 def _graph_text_reference(case, text):
-    """the reference's text with the four documented deviations applied (see _documented_deviations)"""
-    lines, out, skip, module = text.splitlines(), [], False, ""
-    for ln in lines:
-        if ln.startswith("module "):
-            module, skip = ln.split()[1], False
-        if ln.startswith(" node "):
-            skip = module == "filmcurv" and ln.split()[2] in ("OpenDRT:hist", "filmcurv:dspy")
-            if module == "filmcurv" and ln.split()[2] == "filmcurv:main":
-                ln = re.sub(r"^ node \d+", " node 0", ln)
-        elif not ln.startswith("  conn "):
-            skip = False
-        if not skip:
-            out.append(ln)
+    """the reference's text with the documented deviations applied (see _documented_deviations)"""
+    out = text.splitlines()
     fixed, start = [], 0
     for i in range(len(out) + 1):   # per module, for the rewrites that need to know the node
         if i == len(out) or (out[i].startswith("module ") and i > start):

@@ -990,12 +990,27 @@ static void filmcurv_roi_out(dt_graph_t *, dt_module_t *module)
   module->connector[1].roi = module->connector[0].roi;
 }
 static void filmcurv_create_nodes(dt_graph_t *graph, dt_module_t *module)
-{
+{ // filmcurv/main.c:12-38.  hist and dspy draw the curve widget of the gui: they hang off the `dspy` connector, which nothing
+  // on an export path reads, so the executor never reaches them (no kernel is built for them); they exist so that the node
+  // list is the reference's
+  const int wd = module->connector[0].roi.wd, ht = module->connector[0].roi.ht;
+  dt_roi_t hroi = {};
+  hroi.wd = 16 + 1; hroi.ht = 16;
+  const int id_hist = dt_node_add(graph, module, "OpenDRT", "hist", (wd + 15) / 16 * 8, (ht + 15) / 16 * 8, 1, 0, 0, 2,
+      "input",  "read",  "*",    "*",   dt_no_roi,
+      "hist",   "write", "ssbo", "u32", &hroi);
   const int id_main = dt_node_add(graph, module, "filmcurv", "main", module->connector[0].roi.wd, module->connector[0].roi.ht, 1, 0, 0, 2,
       "input",  "read",  "*",    "*",   dt_no_roi,
       "output", "write", "rgba", "f16", &module->connector[1].roi);
+  const int id_dspy = dt_node_add(graph, module, "filmcurv", "dspy", module->connector[2].roi.wd, module->connector[2].roi.ht, 1, 0, 0, 2,
+      "hist",   "read",  "ssbo", "u32", dt_no_roi,
+      "output", "write", "rgba", "f16", &module->connector[2].roi);
+  graph->node[id_hist].connector[1].flags |= s_conn_clear;
+  CONN(dt_node_connect_named(graph, id_hist, "hist", id_dspy, "hist"));
+  dt_connector_copy(graph, module, 0, id_hist, 0);
   dt_connector_copy(graph, module, 0, id_main, 0);
   dt_connector_copy(graph, module, 1, id_main, 1);
+  dt_connector_copy(graph, module, 2, id_dspy, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
