@@ -88,6 +88,17 @@ VKB_API int vkb_dispatch(vkb_token_t name, vkb_token_t kernel, uint32_t wd, uint
 VKB_API int vkb_kernel_count(void);
 VKB_API int vkb_kernel_name(int idx, vkb_token_t *name, vkb_token_t *kernel);
 /* kernels launched through vkb_dispatch / vkb_graph_run since the last reset (the bench's gpu_launches) */
+/* arithmetic mode of the kernels.  every kernel exists in two builds:
+ *   VKB_MODE_STRICT (default)  the arithmetic of the reference's shaders operation for operation: unfused multiply-adds, IEEE
+ *                              division and square root, exp / exp2 / log2 / pow with libm's results bit for bit (what the CPU
+ *                              oracle and the reference's shaders compiled as C++ compute)
+ *   VKB_MODE_FAST              the SFU's ex2 / lg2 / rcp approximations (~2 ulp) and fused multiply-adds, what a GPU driver makes
+ *                              of GLSL: within the path's tolerance (max abs 1e-3 on all but a 1e-5 tail), not bit compatible
+ * vkb_set_mode sets the process default (also: environment VKB_FAST=1), used by vkb_dispatch and by graphs created after it. */
+#define VKB_MODE_STRICT 0
+#define VKB_MODE_FAST   1
+VKB_API int  vkb_set_mode(int mode);
+VKB_API int  vkb_get_mode(void);
 VKB_API uint64_t vkb_launch_count(void);
 VKB_API void     vkb_launch_count_reset(void);
 
@@ -104,8 +115,11 @@ enum
   VKB_RUN_UPLOAD_SOURCE  = 1 << 4,
   VKB_RUN_DOWNLOAD_SINK  = 1 << 5,
   VKB_RUN_WAIT_DONE      = 1 << 6,
-  VKB_RUN_PERF           = 1 << 7,  /* ours: time every launch with its own event pair (-d perf, vkb_graph_perf); costs ~1 us of
-                                       stream idle per launch, so frame loops leave it off */
+  VKB_RUN_BEFORE_ACTIVE  = 1 << 7,  /* s_graph_run_before_active: a gui notion (active_module), accepted and without effect here */
+  VKB_RUN_PERF           = 1 << 16, /* ours, outside the reference's bits and never implied by VKB_RUN_ALL: time every launch with its
+                                       own event pair (-d perf, vkb_graph_perf) instead of replaying the captured CUDA graph; costs
+                                       ~1 us of stream idle per launch.  vkb_graph_set_perf() switches the same thing on per graph,
+                                       like the reference's `-d perf` log mask (src/pipe/graph.c:881) */
   VKB_RUN_ALL            = -1,
 };
 
@@ -166,6 +180,8 @@ VKB_API int  vkb_graph_set_frame(vkb_graph_t *g, uint32_t frame);
 VKB_API int  vkb_graph_run(vkb_graph_t *g, int runflags);                   /* dt_graph_run, src/pipe/graph.c:719 */
 /* -d perf equivalent (graph.c:881-933): per-kernel milliseconds of the last run; returns number of entries */
 VKB_API int  vkb_graph_perf(vkb_graph_t *g, char *buf, size_t bufsize);
+VKB_API int  vkb_graph_set_perf(vkb_graph_t *g, int on);
+VKB_API int  vkb_graph_set_mode(vkb_graph_t *g, int mode);                  /* VKB_MODE_STRICT | VKB_MODE_FAST, before the next run */
 /* host-side half of a run only (module passes, node rewrite/fusion, liveness + pool layout): needs no device.
  * writes the launch list as text: one line per kernel launch with its connector images and pool offsets */
 VKB_API int  vkb_graph_plan(vkb_graph_t *g, char *buf, size_t bufsize);

@@ -15,8 +15,21 @@ def f16_ulp_diff(a, b):
     return d
 
 
+def census(what, d, got=None, want=None):
+    """VKB_CENSUS=<file>: append one line per comparison (max f16 ulp, share of bit-identical values, max abs) - the per
+    kernel record of how far the strict kernels are from the restatement, kept under profiles/."""
+    import os
+    path = os.environ.get("VKB_CENSUS")
+    if not path:
+        return
+    mabs = float(np.nanmax(np.abs(np.asarray(got, dtype=np.float64) - np.asarray(want, dtype=np.float64)))) if got is not None else -1.0
+    with open(path, "a") as f:
+        f.write("%-44s max_ulp %3d  identical %.6f  differing %d of %d  max_abs %.3g\n" % (what, int(d.max()), float((d == 0).mean()), int((d != 0).sum()), d.size, mabs))
+
+
 def assert_f16_close(got, want, max_ulp=2, min_exact=0.98, what=""):
     d = f16_ulp_diff(got, want)
+    census(what, d, got, want)
     exact = float((d == 0).mean())
     assert d.max() <= max_ulp and exact >= min_exact, "%s: max ulp %d (allowed %d), bit-identical %.4f (needed %.4f)" % (
         what, int(d.max()), max_ulp, exact, min_exact)
@@ -31,6 +44,7 @@ def assert_close_mixed(got, want, ulps=3, atol=4e-6, min_exact=0.85, what="", ma
     got[both_nan] = 0.0; want[both_nan] = 0.0
     assert not (np.isnan(got) | np.isnan(want)).any(), "%s: NaN on one side only" % what
     d = f16_ulp_diff(got, want)
+    census(what, d, got, want)
     bad = (d > ulps) & (np.abs(got - want) > atol)
     exact = float((d == 0).mean())
     assert float(np.abs(got - want).max()) <= hard_atol, "%s: max abs %.3g" % (what, float(np.abs(got - want).max()))

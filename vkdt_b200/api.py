@@ -44,7 +44,7 @@ vkb_event_sync vkb_event_elapsed_ms vkb_event_destroy vkb_dispatch vkb_kernel_co
 vkb_kernel_name vkb_launch_count vkb_launch_count_reset vkb_graph_new vkb_graph_free vkb_graph_read_config_ascii
 vkb_graph_read_config_line vkb_graph_replace_display vkb_graph_set_source vkb_graph_set_sink_buffer
 vkb_graph_sink_size vkb_graph_set_frame vkb_graph_run vkb_graph_plan vkb_graph_perf vkb_graph_dump_nodes
-vkb_graph_set_source_device vkb_graph_sink_device vkb_graph_pool_bytes vkb_graph_stream vkb_graph_set_device vkb_dng_info vkb_graph_set_sink_layout vkb_lj92_decode vkb_graph_committed_params vkb_graph_describe vkb_graph_state""".split()
+vkb_graph_set_source_device vkb_graph_sink_device vkb_graph_pool_bytes vkb_graph_stream vkb_graph_set_device vkb_dng_info vkb_graph_set_sink_layout vkb_lj92_decode vkb_graph_committed_params vkb_graph_describe vkb_graph_state vkb_graph_set_perf vkb_set_mode vkb_get_mode vkb_graph_set_mode""".split()
 
 
 def token(s):
@@ -89,10 +89,22 @@ def launch_count():
     return int(lib.vkb_launch_count())
 
 
+MODE_STRICT, MODE_FAST = 0, 1
+
+
+def set_mode(mode):
+    """process default arithmetic mode of the kernels (MODE_STRICT: bit compatible with the CPU restatement; MODE_FAST: SFU)."""
+    return check(lib.vkb_set_mode(mode))
+
+
+def get_mode():
+    return int(lib.vkb_get_mode())
+
+
 # ---- graph layer -------------------------------------------------------------------------------------------
 RUN_ALL = -1
 SINK_RGBA_F32, SINK_RGB_F32 = 0, 1
-RUN_ROI, RUN_CREATE_NODES, RUN_ALLOC, RUN_RECORD, RUN_UPLOAD, RUN_DOWNLOAD, RUN_WAIT, RUN_PERF = 1, 2, 4, 8, 16, 32, 64, 128
+RUN_ROI, RUN_CREATE_NODES, RUN_ALLOC, RUN_RECORD, RUN_UPLOAD, RUN_DOWNLOAD, RUN_WAIT, RUN_PERF = 1, 2, 4, 8, 16, 32, 64, 1 << 16
 
 lib.vkb_graph_new.restype = C.c_void_p
 lib.vkb_graph_free.argtypes = [C.c_void_p]
@@ -108,6 +120,9 @@ lib.vkb_graph_set_frame.argtypes = [C.c_void_p, C.c_uint32]
 lib.vkb_graph_run.argtypes = [C.c_void_p, C.c_int]
 lib.vkb_graph_plan.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
 lib.vkb_graph_perf.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+lib.vkb_graph_set_perf.argtypes = [C.c_void_p, C.c_int]
+lib.vkb_graph_set_mode.argtypes = [C.c_void_p, C.c_int]
+lib.vkb_set_mode.argtypes = [C.c_int]
 lib.vkb_graph_dump_nodes.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
 lib.vkb_graph_pool_bytes.argtypes = [C.c_void_p]
 lib.vkb_graph_pool_bytes.restype = C.c_uint64
@@ -269,6 +284,12 @@ class Graph:
         b = C.create_string_buffer(1 << 16)
         lib.vkb_graph_perf(self.h, b, len(b))
         return b.value.decode()
+
+    def set_mode(self, mode):
+        check(lib.vkb_graph_set_mode(self.h, int(mode)))
+
+    def set_perf(self, on=True):
+        check(lib.vkb_graph_set_perf(self.h, int(on)))
 
     def dump_nodes(self):
         b = C.create_string_buffer(1 << 18)

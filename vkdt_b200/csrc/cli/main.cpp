@@ -56,6 +56,7 @@ int main(int argc, char *argv[])
   if(!dump && vkb_init(device)) { fprintf(stderr, "[cli] %s\n", vkb_last_error()); return 2; }
   vkb_graph_t *g = vkb_graph_new();
   vkb_graph_set_device(g, device);
+  vkb_graph_set_perf(g, perf);
   if(vkb_graph_read_config_ascii(g, cfg)) { fprintf(stderr, "[cli] %s\n", vkb_last_error()); return 3; }
   if(vkb_graph_replace_display(g, format)) { fprintf(stderr, "[cli] %s\n", vkb_last_error()); return 4; }
   if(config_start) for(int i = config_start; i < argc; i++) vkb_graph_read_config_line(g, argv[i]);
@@ -85,7 +86,7 @@ int main(int argc, char *argv[])
       snprintf(fn, sizeof(fn), "param:%s:main:filename:%s_%04d", format, filename, f);
       vkb_graph_read_config_line(g, fn);
     }
-    int flags = f == 0 ? VKB_RUN_ALL : (VKB_RUN_RECORD_CMD_BUF | VKB_RUN_UPLOAD_SOURCE | VKB_RUN_DOWNLOAD_SINK | VKB_RUN_WAIT_DONE | (perf ? VKB_RUN_PERF : 0));
+    int flags = f == 0 ? VKB_RUN_ALL : (VKB_RUN_RECORD_CMD_BUF | VKB_RUN_UPLOAD_SOURCE | VKB_RUN_DOWNLOAD_SINK | VKB_RUN_WAIT_DONE);
     if(last_only && f < frames - 1) flags &= ~VKB_RUN_DOWNLOAD_SINK;
     err = vkb_graph_run(g, flags);
     if(err) fprintf(stderr, "[cli] frame %d: %s\n", f, vkb_last_error());

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256) k_demosaic_splat(const __half *__restrict
     const float col = ld_h_clamp(in, w, h, px, py);
     const float of0 = cov.z * (float)i + cov.w * (float)j;
     const float of1 = -cov.w * (float)i + cov.z * (float)j;
-    float weight = clampf(expf(-0.5f * (of0 / e0 * of0 + of1 / e1 * of1)), 1e-4f, 1.0f);
+    float weight = clampf(m_exp(-0.5f * (of0 / e0 * of0 + of1 / e1 * of1)), 1e-4f, 1.0f);
     if(i == 0 && j == 0) weight = 666.0f;
     g += col * weight;
     wg += weight;
@@ -119,7 +119,7 @@ VKB_DEV float fix_gauss(float e0, float e1, float cz, float cw, int i, int j)
 {
   const float of0 = cz * (float)i + cw * (float)j;
   const float of1 = -cw * (float)i + cz * (float)j;
-  return clampf(expf(-0.5f * (of0 / e0 * of0 + of1 / e1 * of1)), 1e-3f, 1.0f);
+  return clampf(m_exp(-0.5f * (of0 / e0 * of0 + of1 / e1 * of1)), 1e-3f, 1.0f);
 }
 
 // ---- fix: red/blue by interpolating the ratio to green (fix.comp:25-135) ----
@@ -202,3 +202,5 @@ static int launch_demosaic_fix(const vkb_launch_t *l)
   return VKB_OK;
 }
 VKB_REGISTER("demosaic", "fix", launch_demosaic_fix);
+
+VKB_NS_END

@@ -19,7 +19,7 @@ VKB_DEV float splat_weight(float e0, float e1, float cz, float cw, int i, int j)
 { // splat.comp:33-37
   const float of0 = cz * (float)i + cw * (float)j;
   const float of1 = -cw * (float)i + cz * (float)j;
-  return clampf(expf(-0.5f * (of0 / e0 * of0 + of1 / e1 * of1)), 1e-4f, 1.0f);
+  return clampf(m_exp(-0.5f * (of0 / e0 * of0 + of1 / e1 * of1)), 1e-4f, 1.0f);
 }
 
 __global__ void __launch_bounds__(256, 6) k_bayer_splat(const __half *__restrict__ in, int w, int h,
@@ -80,7 +80,7 @@ VKB_DEV float fixw(float e0, float e1, float cz, float cw, int i, int j)
 { // fix.comp:16-23
   const float of0 = cz * (float)i + cw * (float)j;
   const float of1 = -cw * (float)i + cz * (float)j;
-  return clampf(expf(-0.5f * (of0 / e0 * of0 + of1 / e1 * of1)), 1e-3f, 1.0f);
+  return clampf(m_exp(-0.5f * (of0 / e0 * of0 + of1 / e1 * of1)), 1e-3f, 1.0f);
 }
 
 __global__ void __launch_bounds__(256, 5) k_bayer_fix(const __half *__restrict__ in, const __half *__restrict__ green, int w, int h,
@@ -169,3 +169,5 @@ int launch_bayer_fix(const vkb_launch_t *l)
   VKB_CHECK_LAUNCH();
   return VKB_OK;
 }
+
+VKB_NS_END

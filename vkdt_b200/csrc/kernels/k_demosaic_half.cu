@@ -66,3 +66,5 @@ static int launch_resample(const vkb_launch_t *l)
   return VKB_OK;
 }
 VKB_REGISTER("shared", "resample", launch_resample);
+
+VKB_NS_END

@@ -12,7 +12,7 @@ VKB_DEV float xt_weight(float e0, float e1, float cz, float cw, int i, int j, fl
 { // splat.comp:33-37 (lo = 1e-4), fix.comp:16-23 (lo = 1e-3)
   const float of0 = cz * (float)i + cw * (float)j;
   const float of1 = -cw * (float)i + cz * (float)j;
-  return clampf(expf(-0.5f * (of0 / e0 * of0 + of1 / e1 * of1)), lo, 1.0f);
+  return clampf(m_exp(-0.5f * (of0 / e0 * of0 + of1 / e1 * of1)), lo, 1.0f);
 }
 // the 13 distinct weights of a 5x5 window: index (j+2)*5 + (i+2), mirrored index 24 - idx
 #define XT_WEIGHTS(W, E0, E1, CZ, CW, LO) \
@@ -188,3 +188,5 @@ int launch_xtrans_fix(const vkb_launch_t *l)
   VKB_CHECK_LAUNCH();
   return VKB_OK;
 }
+
+VKB_NS_END

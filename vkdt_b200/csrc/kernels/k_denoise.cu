@@ -6,8 +6,8 @@
 // all intermediates live at 1/block^2 resolution; the full-res `doub` is the only HBM-heavy kernel (2+2 B/px + coarse reads).
 // compiled with --fmad=false: downcov picks between two covariance estimates by comparing determinants and rejects
 // hot pixels by a threshold — discontinuous decisions that must fall like in the fp32 restatement.
-#include "common.cuh"
 #include <string.h>
+#include "common.cuh"
 
 struct denoise_params_t { float strength, luma, detail, pad; float edges[4]; int gainmap; };      // denoise/params
 struct dn_push_half_t { float wb[4], black[4], white[4]; int32_t crop[4]; uint32_t filters; };     // main.c:284-289
@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(256, 5) k_denoise_downcov(const uint2 *__restr
   e0 = clampf(e0, 0.01f, 25.0f); e1 = clampf(e1, 0.01f, 25.0f);
   st_rgba(covimg, w, x, y, make_float4(e0, e1, v0x, v0y));
   float r = 0, g = 0, b = 0, wt = 0;
+#if VKB_FAST
   // weight(i,j) = exp(-(q0^2/e0 + q1^2/e1)/2) with q = V^t (i,j) is exp2 of a quadratic form in (i,j): the three
   // coefficients are set up once, a tap costs two adds and one ex2.  (continuous in the inputs: ~1e-6 relative on the
   // weights, the blurred colour is rounded to f16 right after.)
@@ -171,6 +172,26 @@ __global__ void __launch_bounds__(256, 5) k_denoise_downcov(const uint2 *__restr
       wt += wgt;
     }
   }
+#else
+  // cov.glsl:116-133 tap for tap: rotate the offset into the eigenbasis, libm's exponential, unfused accumulation
+#pragma unroll 1
+  for(int j = 0; j < 5; j++)
+  {
+    const float fj = (float)(j - 2);
+#pragma unroll
+    for(int i = 0; i < 5; i++)
+    {
+      const float fi = (float)(i - 2);
+      const float4 t = tile[ly + j][lx + i];
+      if(t.x > 2.0f * mean_b) continue; // hot pixels
+      const float x0 = fi * v0x + fj * v0y;
+      const float x1 = fi * v1x + fj * v1y;
+      const float wgt = fmaxf(1e-9f, m_exp(-0.5f * (x0 / e0 * x0 + x1 / e1 * x1)));
+      r += wgt * t.x; g += wgt * t.y; b += wgt * t.z;
+      wt += wgt;
+    }
+  }
+#endif
   const float iw_ = fmaxf(wt, 1e-8f);
   float edge = clampf(75.0f * fmaxf(0.0f, e1 - 0.09f), 0.0f, 1.0f);
   edge = smoothstepf(0.4f, 0.75f, edge);
@@ -180,7 +201,7 @@ __global__ void __launch_bounds__(256, 5) k_denoise_downcov(const uint2 *__restr
 }
 
 // x^0.8 on the SFU: ~1e-6 relative, i.e. <= 1e-4 in the [0,1] edge weight even at the 1e-3 noise floor of noise.glsl
-VKB_DEV float gamma08(float f) { return f < 0.0f ? f : pow_ftz(f, 0.8f); }
+VKB_DEV float gamma08(float f) { return f < 0.0f ? f : m_pow(f, 0.8f); }
 
 // ---- down: levels 1..3, 5 tap flower with edge stopping (down.comp:59-107) ----
 __global__ void __launch_bounds__(256) k_denoise_down(const uint2 *__restrict__ in, int w, int h, uint2 *__restrict__ out,
@@ -317,20 +338,30 @@ __global__ void __launch_bounds__(256, 5) k_denoise_assemble(const uint2 *__rest
   float sigma[3];
   noise_sigma(K.noise_a, K.noise_b, K.black[1], K.white[1], p.edges, fmaxf(d[2][0], 0.0f), sigma);
   const float bb[4] = { K.bb[0], K.bb[1], K.bb[2], K.bb[3] };
+#if VKB_FAST
   const float isig[3] = { __frcp_rn(sigma[0]), __frcp_rn(sigma[1]), __frcp_rn(sigma[2]) };
+#endif
   float down4[3] = { d[4][0], d[4][1], d[4][2] }, len[4];
 #pragma unroll
   for(int l = 0; l < 4; l++)
   {
 #pragma unroll
+#if VKB_FAST
     for(int k = 0; k < 3; k++) d[l][k] = (d[l][k] - d[l + 1][k]) * (isig[k] * K.ibb[l]); // 1/(sigma bb) as a product of reciprocals: 3 instead of 12
+#else
+    for(int k = 0; k < 3; k++) d[l][k] = (d[l][k] - d[l + 1][k]) / (sigma[k] * bb[l]);
+#endif
     len[l] = sqrtf(d[l][0] * d[l][0] + d[l][1] * d[l][1] + d[l][2] * d[l][2]);
   }
   const float slope = ((len[3] - len[0]) / 3.0f + (len[2] - len[1]) / 1.0f + (len[1] - len[0]) / 1.0f
       + (len[3] - len[2]) / 1.0f + (len[2] - len[0]) / 2.0f + (len[3] - len[1]) / 2.0f) / 6.0f;
   float test = fmaxf(0.0f, -slope);
   test = fmaxf(0.0f, 1.0f - test);
+#if VKB_FAST
   test = test * test; test = test * test; test = test * test; test = test * test; // pow(test, 16)
+#else
+  test = m_pow(test, 16.0f);
+#endif
   test = clampf(1.5f * test, 0.0f, 1.0f);
 #pragma unroll
   for(int l = 3; l >= 0; l--)
@@ -341,7 +372,11 @@ __global__ void __launch_bounds__(256, 5) k_denoise_assemble(const uint2 *__rest
     for(int k = 0; k < 3; k++)
     {
       const float a = fabsf(d[l][k]);
+#if VKB_FAST
       const float tt = fminf(1.0f, a * i2t);
+#else
+      const float tt = fminf(1.0f, a / (2.0f * thrs));
+#endif
       down4[k] += sigma[k] * bb[l] * signf(d[l][k]) * mixf(fmaxf(a - thrs, 0.0f), a, tt);
     }
   }
@@ -350,8 +385,13 @@ __global__ void __launch_bounds__(256, 5) k_denoise_assemble(const uint2 *__rest
 #pragma unroll
   for(int k = 0; k < 3; k++)
   {
+#if VKB_FAST
     v[k]  = (down4[k] - K.black[k]) * K.inorm[k];
     vo[k] = (og[k]    - K.black[k]) * K.inorm[k];
+#else
+    v[k]  = (down4[k] - K.black[k]) / (K.white[k] - K.black[k]) * K.wb[k];
+    vo[k] = (og[k]    - K.black[k]) / (K.white[k] - K.black[k]) * K.wb[k];
+#endif
   }
 #pragma unroll
   for(int j = 0; j < 3; j++)
@@ -362,7 +402,12 @@ __global__ void __launch_bounds__(256, 5) k_denoise_assemble(const uint2 *__rest
   yuv[0] = mixf(yuvo[0], yuv[0], p.luma);
 #pragma unroll
   for(int j = 0; j < 3; j++) rgb[j] = K.yuv_to_rgb[3 * j] * yuv[0] + K.yuv_to_rgb[3 * j + 1] * yuv[1] + K.yuv_to_rgb[3 * j + 2] * yuv[2];
+#if VKB_FAST
   st_rgba(out, w, x, y, make_float4(rgb[0] * K.denorm[0] + K.black[0], rgb[1] * K.denorm[1] + K.black[1], rgb[2] * K.denorm[2] + K.black[2], test));
+#else
+  st_rgba(out, w, x, y, make_float4(rgb[0] / K.wb[0] * (K.white[0] - K.black[0]) + K.black[0], rgb[1] / K.wb[1] * (K.white[1] - K.black[1]) + K.black[1],
+        rgb[2] / K.wb[2] * (K.white[2] - K.black[2]) + K.black[2], test));
+#endif
 }
 
 // ---- doub: per-colour residual shrink on the full resolution mosaic (doub.comp:35-115) ----
@@ -385,7 +430,11 @@ VKB_DEV float doub_shrink(float val, float upsm_c, float down_c, float upw, int 
   {
     const float wav = (val - down_c) / fmaxf(sigma[0] + sigma[2], 1e-8f);
     const float tt = fminf(1.0f, wav / fmaxf(2.0f * T, 1e-8f));
+#if VKB_FAST
     float uw = fminf(1.0f, 1.0f * upw); uw = uw * uw; uw = uw * uw; // pow(.., 4)
+#else
+    float uw = m_pow(fminf(1.0f, 1.0f * upw), 4.0f);
+#endif
     uw = 1.0f - (1.0f - uw) * p.detail;
     val = mixf(val, fmaxf(0.0f, upsm_c + sigma[1] * signf(wav) * mixf(fmaxf(0.0f, fabsf(wav) - T), fabsf(wav), tt)), uw * blendw);
   }
@@ -569,3 +618,5 @@ static int launch_doub(const vkb_launch_t *l)
   return VKB_OK;
 }
 VKB_REGISTER("denoise", "doub", launch_doub);
+
+VKB_NS_END

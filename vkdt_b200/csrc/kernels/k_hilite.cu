@@ -147,10 +147,10 @@ __global__ void __launch_bounds__(256) k_hilite_assemble(const uint2 *__restrict
   const float sr = fine.x / fmaxf(0.001f, ur);
   const float sg = fine.y / fmaxf(0.001f, ug);
   const float sb = fine.z / fmaxf(0.001f, ub);
-  // blend weights, continuous: the SFU exponential (2 ulp) instead of the ~40 instruction libm one, three times per pixel
-  const float wr = exp_ftz(ur - fmaxf(ug, ub));
-  const float wg = exp_ftz(ug - fmaxf(ur, ub));
-  const float wb = exp_ftz(ub - fmaxf(ur, ug));
+  // blend weights: libm's exponential bit for bit (strict) or the SFU one (fast, 2 ulp), three times per pixel
+  const float wr = m_exp(ur - fmaxf(ug, ub));
+  const float wg = m_exp(ug - fmaxf(ur, ub));
+  const float wb = m_exp(ub - fmaxf(ur, ug));
   const float scale = (sr * wr + sg * wg + sb * wb) / (wr + wg + wb);
   float t = p.soft;
   if(fine.x >= white || fine.y >= white || fine.z >= white) t = 1.0f;
@@ -186,9 +186,9 @@ __global__ void __launch_bounds__(256) k_hilite_doub(const __half *__restrict__ 
     const float sr = minr / fmaxf(0.001f, upsm.x);
     const float sg = ming / fmaxf(0.001f, upsm.y);
     const float sb = minb / fmaxf(0.001f, upsm.z);
-    const float wr = expf(upsm.x - fmaxf(upsm.y, upsm.z));
-    const float wg = expf(upsm.y - fmaxf(upsm.x, upsm.z));
-    const float wb = expf(upsm.z - fmaxf(upsm.x, upsm.y));
+    const float wr = m_exp(upsm.x - fmaxf(upsm.y, upsm.z));
+    const float wg = m_exp(upsm.y - fmaxf(upsm.x, upsm.z));
+    const float wb = m_exp(upsm.z - fmaxf(upsm.x, upsm.y));
     const float scale = (sr * wr + sg * wg + sb * wb) / (wr + wg + wb);
     const float maxr = fmaxf(c[1], c[7]), maxb = fmaxf(c[3], c[5]);
     const float maxg = fmaxf(fmaxf(fmaxf(c[0], c[2]), c[4]), fmaxf(c[6], c[8]));
@@ -217,9 +217,9 @@ __global__ void __launch_bounds__(256) k_hilite_doub(const __half *__restrict__ 
     const float sr = c[3] / fmaxf(0.001f, upsm.x);
     const float sg = ming / fmaxf(0.001f, upsm.y);
     const float sb = c[1] / fmaxf(0.001f, upsm.z);
-    const float wr = expf(upsm.x - fmaxf(upsm.y, upsm.z));
-    const float wg = expf(upsm.y - fmaxf(upsm.x, upsm.z));
-    const float wb = expf(upsm.z - fmaxf(upsm.x, upsm.y));
+    const float wr = m_exp(upsm.x - fmaxf(upsm.y, upsm.z));
+    const float wg = m_exp(upsm.y - fmaxf(upsm.x, upsm.z));
+    const float wb = m_exp(upsm.z - fmaxf(upsm.x, upsm.y));
     const float scale = (sr * wr + sg * wg + sb * wb) / (wr + wg + wb);
     const float maxrgb = fmaxf(fmaxf(c[0], c[1]), fmaxf(c[2], c[3]));
     if(maxrgb > softw)
@@ -303,3 +303,5 @@ static int launch_hilite_doub(const vkb_launch_t *l)
   return VKB_OK;
 }
 VKB_REGISTER("hilite", "doub", launch_hilite_doub);
+
+VKB_NS_END

@@ -6,8 +6,8 @@
 //  - (b200, llapfin) finest assemble + llap/colour.comp (+ grade) fused: level-0 laplacians are recomputed
 //    from the input pixel (curve() rounded to f16 in registers = the value the reference would have stored)
 // wiring: llap/main.c:31-105.  gamma/curve: llap/llap.glsl:3-22, llap/curve.comp:40-63.
-#include "pointwise.cuh"
 #include <string.h>
+#include "pointwise.cuh"
 
 #define NUM_GAMMA 10
 #define NL (NUM_GAMMA + 1)
@@ -27,27 +27,8 @@ VKB_DEV int gamma_hi_from_v(float v)
 // rounded to f16 right after.  the level-0 stack costs 10 of these per input pixel, the divisions were a third of it.
 // CLARITY = false: p.clarity == 0 (the default).  the gaussian term is then +-0 with the sign of c, and adding
 // 0 * c reproduces `val + 0 * c * exp(..)` bit for bit (signed zeros included) without the exponential.
-template <bool CLARITY>
-VKB_DEV float llap_curve_k(float x, float g, const llap_params_t &p, float inv2s, float invd)
-{
-  const float c = x - g;
-  float val;
-  const float ssigma = c > 0.0f ? p.sigma : -p.sigma;
-  const float shadhi = c > 0.0f ? p.shadows : p.hilights;
-  if(fabsf(c) > 2 * p.sigma) val = g + ssigma + shadhi * (c - ssigma);
-  else
-  {
-    const float t = clampf(fabsf(c) * inv2s, 0.0f, 1.0f);
-    const float t2 = t * t;
-    const float mt = 1.0f - t;
-    val = g + ssigma * 2.0f * mt * t + t2 * (ssigma + ssigma * shadhi);
-  }
-  if(CLARITY) val += p.clarity * c * exp_ftz(-c * c * invd);
-  else        val += 0.0f * c;
-  return val;
-}
 VKB_DEV float llap_curve(float x, float g, const llap_params_t &p)
-{
+{ // llap/curve.comp:40-63
   const float c = x - g;
   float val;
   const float ssigma = c > 0.0f ? p.sigma : -p.sigma;
@@ -60,8 +41,33 @@ VKB_DEV float llap_curve(float x, float g, const llap_params_t &p)
     const float mt = 1.0f - t;
     val = g + ssigma * 2.0f * mt * t + t2 * (ssigma + ssigma * shadhi);
   }
-  // the gaussian term is a few % of val at most: __expf's ~1e-6 relative error on it stays below an fp32 ulp of val
-  val += p.clarity * c * exp_ftz(-c * c / (2.0f * p.sigma * p.sigma / 3.0f));
+  val += p.clarity * c * m_exp(-c * c / (2.0f * p.sigma * p.sigma / 3.0f));
+  return val;
+}
+template <bool CLARITY>
+VKB_DEV float llap_curve_k(float x, float g, const llap_params_t &p, float inv2s, float invd)
+{
+#if !VKB_FAST
+  if(CLARITY) return llap_curve(x, g, p); // strict: the shader's divisions and libm's exponential
+#endif
+  const float c = x - g;
+  float val;
+  const float ssigma = c > 0.0f ? p.sigma : -p.sigma;
+  const float shadhi = c > 0.0f ? p.shadows : p.hilights;
+  if(fabsf(c) > 2 * p.sigma) val = g + ssigma + shadhi * (c - ssigma);
+  else
+  {
+#if VKB_FAST
+    const float t = clampf(fabsf(c) * inv2s, 0.0f, 1.0f);
+#else
+    const float t = clampf(c / (2.0f * ssigma), 0.0f, 1.0f);
+#endif
+    const float t2 = t * t;
+    const float mt = 1.0f - t;
+    val = g + ssigma * 2.0f * mt * t + t2 * (ssigma + ssigma * shadhi);
+  }
+  if(CLARITY) val += p.clarity * c * exp_ftz(-c * c * invd);
+  else        val += 0.0f * c;
   return val;
 }
 VKB_DEV float llap_grey(float4 px)
@@ -303,7 +309,7 @@ __global__ void __launch_bounds__(256) k_llap_final(const uint2 *__restrict__ in
   float l = f16r(res + lap0 * (1.0f - a) + lap1 * a);
   // llap/colour.comp:17-37
   const float yo = fmaxf(lum2020(px.x, px.y, px.z), 1e-8f);
-  if(l < yo) l = yo * expf(1.0f * (l - yo));
+  if(l < yo) l = yo * m_exp(1.0f * (l - yo));
   f3 c = { fmaxf(0.0f, px.x * l / yo), fmaxf(0.0f, px.y * l / yo), fmaxf(0.0f, px.z * l / yo) };
   if(P.have_grade)
   {
@@ -326,7 +332,9 @@ static int launch_llapr0(const vkb_launch_t *l)
   VKB_REQUIRE(in->chan == 4 && in->format == VKB_TOKEN_F16 && out->chan == 1 && out->layers == NL && out->format == VKB_TOKEN_F16);
   VKB_REQUIRE(out->wd == (in->wd - 1) / 2 + 1 && out->ht == (in->ht - 1) / 2 + 1);
   const llap_params_t *lp = (const llap_params_t *)l->params;
-  if(!getenv("VKB_LLAPR0_SCALAR")) return launch_llapr0_packed(l); // two layers per packed fp32 instruction, k_llap_r0.cu
+  // fast: two layers per packed fp32 instruction (k_llap_r0.cu: fused multiply-adds, reciprocals, the SFU exponential);
+  // strict: the scalar kernel below with the shader's curve operation for operation
+  if(VKB_FAST && !getenv("VKB_LLAPR0_SCALAR")) return launch_llapr0_packed(l);
   if(lp->clarity == 0.0f)
     k_llap_reduce0<false><<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht,
         (__half *)out->data, out->wd, out->ht, *lp);
@@ -401,3 +409,5 @@ static int launch_llapfin(const vkb_launch_t *l)
 }
 // the shader-order (9 tap) variant stays available for A/B checks; the executor uses k_llap_fin.cu's (b200, llapfin)
 VKB_REGISTER("b200", "llapfinx", launch_llapfin);
+
+VKB_NS_END

@@ -143,3 +143,5 @@ int launch_llap_assemble4(const vkb_launch_t *l, int first)
   VKB_CHECK_LAUNCH();
   return VKB_OK;
 }
+
+VKB_NS_END

@@ -8,8 +8,8 @@
 // the separable sum differs from the shader's 9-tap order by fp32 rounding only (~1e-7), far below the f16 store
 // that follows; nothing downstream of this kernel feeds a pyramid level, so the difference cannot compound.
 // level-0 gamma layers are never read: curve() is recomputed from the input pixel and rounded to f16 in registers.
-#include "pointwise.cuh"
 #include <string.h>
+#include "pointwise.cuh"
 
 #define NUM_GAMMA 10
 #define NL (NUM_GAMMA + 1)
@@ -63,7 +63,7 @@ VKB_DEV float llap_curve(float x, float g, const llap_params_t &p)
     val = g + ssigma * 2.0f * mt * t + t2 * (ssigma + ssigma * shadhi);
   }
   // the gaussian term is < 3% of val: __expf's 1e-6 relative error on it is below an fp32 ulp of val
-  val += p.clarity * c * exp_ftz(-c * c / (2.0f * p.sigma * p.sigma / 3.0f));
+  val += p.clarity * c * m_exp(-c * c / (2.0f * p.sigma * p.sigma / 3.0f));
   return val;
 }
 
@@ -104,6 +104,41 @@ VKB_DEV float expand1(const float (*T)[F3_W + 1], int lx, int ly, int q)
     acc += (row[0] * wx[0] + row[1] * wx[1] + row[2] * wx[2] + row[3] * wx[3] + row[4] * wx[4]) * wy[r];
   }
   return acc / 9.0f;
+}
+
+// strict build: sample_soft's nine bilinear taps in the shader's order (as k_llap_asm4.cu's expand_q), from the 5x5 window
+VKB_DEV constexpr int  tap_i0(int d, int t)   { return d ? (t == 0 ? 1 : (t == 1 ? 2 : 4)) : (t == 0 ? 0 : (t == 1 ? 2 : 3)); }
+VKB_DEV constexpr bool tap_half(int d, int t) { return d ? t == 1 : t != 1; }
+template <int DX, int DY>
+VKB_DEV float expand_q(const float (&W)[5][5])
+{
+  float r = 0.0f;
+#pragma unroll
+  for(int j = 0; j < 3; j++)
+#pragma unroll
+    for(int i = 0; i < 3; i++)
+    {
+      const int x0 = tap_i0(DX, i), y0 = tap_i0(DY, j);
+      float top = tap_half(DX, i) ? W[y0][x0] * 0.5f + W[y0][x0 + 1] * 0.5f : W[y0][x0];
+      float v;
+      if(tap_half(DY, j))
+      {
+        const float bot = tap_half(DX, i) ? W[y0 + 1][x0] * 0.5f + W[y0 + 1][x0 + 1] * 0.5f : W[y0 + 1][x0];
+        v = top * 0.5f + bot * 0.5f;
+      }
+      else v = top;
+      r += v;
+    }
+  return r / 9.0f;
+}
+VKB_DEV void expand4_exact(const float (*T)[F3_W + 1], int lx, int ly, float *t)
+{
+  float W[5][5];
+#pragma unroll
+  for(int r = 0; r < 5; r++)
+#pragma unroll
+    for(int c = 0; c < 5; c++) W[r][c] = T[ly - 2 + r][lx - 2 + c];
+  t[0] = expand_q<0, 0>(W); t[1] = expand_q<1, 0>(W); t[2] = expand_q<0, 1>(W); t[3] = expand_q<1, 1>(W);
 }
 
 // grade/main.comp:21-40 (mode 0) on the host-evaluated constants of llapfin_t: same operations, same order as grade_px()
@@ -181,6 +216,7 @@ __global__ void __launch_bounds__(256, 4) k_llap_final4(const uint2 *__restrict_
   float res[4], e0[4], e1[4];
   float oc[6]; // packed rgb sink: the thread's two pixels of a row, stored by the warp together
   __shared__ __align__(16) float stage[8][196];
+#if VKB_FAST
   expand4(tile[NL], lx, ly, res[0], res[1], res[2], res[3]);
   const bool same = (hi[1] < 0 || hi[1] == hi[0]) && (hi[2] < 0 || hi[2] == hi[0]) && (hi[3] < 0 || hi[3] == hi[0]);
   if(same)
@@ -197,6 +233,28 @@ __global__ void __launch_bounds__(256, 4) k_llap_final4(const uint2 *__restrict_
       e1[q] = expand1(tile[hi[q]],     lx, ly, q);
     }
   }
+#else
+  { // the collapsed coarse level, then every gamma layer one of the four pixels brackets, each in the shader's tap order
+    int hmin = NUM_GAMMA, hmax = 0;
+#pragma unroll
+    for(int q = 0; q < 4; q++) if(hi[q] >= 0) { hmin = min(hmin, hi[q]); hmax = max(hmax, hi[q]); }
+    for(int pl = hmin - 2; pl <= hmax; pl++)
+    {
+      float t[4];
+      expand4_exact(tile[pl == hmin - 2 ? NL : pl], lx, ly, t);
+#pragma unroll
+      for(int q = 0; q < 4; q++)
+      {
+        if(pl == hmin - 2) res[q] = t[q];
+        else
+        {
+          if(pl == hi[q] - 1) e0[q] = t[q];
+          if(pl == hi[q])     e1[q] = t[q];
+        }
+      }
+    }
+  }
+#endif
 #pragma unroll
   for(int q = 0; q < 4; q++)
   {
@@ -204,6 +262,7 @@ __global__ void __launch_bounds__(256, 4) k_llap_final4(const uint2 *__restrict_
     {
     const int x = 2 * kx + (q & 1), y = 2 * ky + (q >> 1);
     const float glo = s_gamma[hi[q] - 1], ghi = s_gamma[hi[q]];
+#if VKB_FAST
     const float a = clampf(__fdividef(v[q] - glo, ghi - glo), 0.0f, 1.0f);
     const float lap0 = f16r(llap_curve_k(grey[q], glo, P.p, inv2s, invd)) - e0[q];
     const float lap1 = f16r(llap_curve_k(grey[q], ghi, P.p, inv2s, invd)) - e1[q];
@@ -212,6 +271,16 @@ __global__ void __launch_bounds__(256, 4) k_llap_final4(const uint2 *__restrict_
     if(l < yo) l = yo * exp_ftz(l - yo);
     const float ratio = __fdividef(l, yo); // nothing downstream but one f16/f32 store: 2 ulp is plenty
     f3 c = { fmaxf(0.0f, px[q].x * ratio), fmaxf(0.0f, px[q].y * ratio), fmaxf(0.0f, px[q].z * ratio) };
+#else
+    // assemble.comp:66-87 and colour.comp:23-35 operation for operation
+    const float a = clampf((v[q] - glo) / (ghi - glo), 0.0f, 1.0f);
+    const float lap0 = f16r(llap_curve(grey[q], glo, P.p)) - e0[q];
+    const float lap1 = f16r(llap_curve(grey[q], ghi, P.p)) - e1[q];
+    float l = f16r(res[q] + lap0 * (1.0f - a) + lap1 * a);
+    const float yo = fmaxf(lum2020(px[q].x, px[q].y, px[q].z), 1e-8f);
+    if(l < yo) l = yo * m_exp(1.0f * (l - yo));
+    f3 c = { fmaxf(0.0f, px[q].x * l / yo), fmaxf(0.0f, px[q].y * l / yo), fmaxf(0.0f, px[q].z * l / yo) };
+#endif
     if(GRADE)
     {
       c = { f16r(c.x), f16r(c.y), f16r(c.z) };
@@ -271,3 +340,5 @@ static int launch_llapfin2(const vkb_launch_t *l)
   return VKB_OK;
 }
 VKB_REGISTER("b200", "llapfin", launch_llapfin2);
+
+VKB_NS_END

@@ -111,3 +111,5 @@ int launch_llapr0_packed(const vkb_launch_t *l)
   VKB_CHECK_LAUNCH();
   return VKB_OK;
 }
+
+VKB_NS_END

@@ -6,9 +6,9 @@
 //    back to back (crop: 20 floats committed, colour: 242 floats committed, filmcurv: 10 x 4 B, grade: 19 x 4 B)
 // replaces crop/main.comp, colour/main.comp, filmcurv/main.comp, grade/main.comp and the three HBM
 // round trips between them.
-#include "pointwise.cuh"
 #include <string.h>
 #include <math.h>
+#include "pointwise.cuh"
 
 enum { PW_CROP = 1, PW_COLOUR = 2, PW_FILMCURV = 3, PW_GRADE = 4 };
 
@@ -126,6 +126,26 @@ static double host_decode_trc(double v, uint32_t trc)
   }
 }
 
+// fp32 flavours for the strict build's launch constants (the host compiler neither contracts nor reassociates)
+static float host_decode_trc_f(float v, uint32_t trc)
+{
+  switch(trc)
+  {
+    case 1: { const float a = 1.09929682680944f, b = 0.018053968510807f; return v > b * 4.5f ? powf((v + (a - 1)) / a, 2.2f) : v / 4.5f; }
+    case 2: return v > 0.04045f ? powf((v + 0.055f) / 1.055f, 2.4f) : v / 12.92f;
+    case 3: { const float m1 = 1305.0f / 8192.0f, m2 = 2523.0f / 32.0f, c1 = 107.0f / 128.0f, c2 = 2413.0f / 128.0f, c3 = 2392.0f / 128.0f;
+              const float xp = powf(fmaxf(0.0f, v), 1.0f / m2); return powf(fmaxf(xp - c1, 0.0f) / fmaxf(c2 - c3 * xp, 1e-10f), 1.0f / m1); }
+    case 4: return powf(v, 2.6f);
+    case 5: { const float a = 0.17883277f, b = 0.28466892f, c = 0.55991073f; return v <= 0.5f ? v * v / 3.0f : (expf((v - c) / a) + b) / 12.0f; }
+    case 6: return powf(fmaxf(v, 0.0f), 2.2f);
+    default: return v;
+  }
+}
+static void host_mat3v_f(const float *M, const float *x, float *y)
+{
+  for(int j = 0; j < 3; j++) y[j] = M[3 * j + 0] * x[0] + M[3 * j + 1] * x[1] + M[3 * j + 2] * x[2];
+}
+
 static int colour_digest(const float *f, uint32_t size, colour_digest_t *d)
 {
   if(size < 236 * 4) return vkb_set_error(VKB_ERR_BAD_ARG, "colour: committed params too small (%u bytes)", size);
@@ -163,15 +183,46 @@ static int colour_digest(const float *f, uint32_t size, colour_digest_t *d)
   mat3mul_d(XM, T0, T1);
   mat3mul_d(T1, P, A);
   for(int k = 0; k < 9; k++) d->A[k] = (float)A[k];
+  { // the strict build's matrices: fp32, formed like the shader forms them (main-impl.glsl:49-67; oracle/o_colour.c cat16())
+    static const float fM16[9]  = {0.401288f, 0.650173f, -0.051461f, -0.250268f, 1.204414f, 0.045854f, -0.002079f, 0.048952f, 0.953127f};
+    static const float fM16i[9] = {1.86206786f, -1.01125463f, 0.14918677f, 0.38752654f, 0.62144744f, -0.00897398f, -0.01584150f, -0.03412294f, 1.04996444f};
+    static const float fR[9] = {0.636958048301290991f, 0.144616903586208406f, 0.168880975164172054f, 0.26270021201126692f, 0.677998071518871148f, 0.0593017164698619384f, 4.9999999999999999e-17f, 0.0280726930490874452f, 1.06098505771079066f};
+    static const float fX[9] = {1.71665119f, -0.35567078f, -0.25336628f, -0.66668435f, 1.61648124f, 0.01576855f, 0.01763986f, -0.04277061f, 0.94210312f};
+    volatile float t; // every product and sum rounded to fp32, in the restatement's order
+    for(int j = 0; j < 3; j++) for(int i = 0; i < 3; i++)
+    {
+      t = fM16[3 * j + 0] * fR[i]; float a = t; t = fM16[3 * j + 1] * fR[3 + i]; a = a + t; t = fM16[3 * j + 2] * fR[6 + i]; a = a + t; d->MR[3 * j + i] = a;
+      t = fX[3 * j + 0] * fM16i[i]; a = t; t = fX[3 * j + 1] * fM16i[3 + i]; a = a + t; t = fX[3 * j + 2] * fM16i[6 + i]; a = a + t; d->XM[3 * j + i] = a;
+    }
+    for(int j = 0; j < 3; j++)
+    {
+      t = d->MR[3 * j] * 1.0f; float cs = t; t = d->MR[3 * j + 1] * 1.0f; cs = cs + t; t = d->MR[3 * j + 2] * 1.0f; cs = cs + t;
+      t = d->MR[3 * j] * f[0]; float cd = t; t = d->MR[3 * j + 1] * f[1]; cd = cd + t; t = d->MR[3 * j + 2] * f[2]; cd = cd + t;
+      t = cd / cs; d->ratio[j] = t;
+    }
+    d->has_P = prim != 2;
+    for(int k = 0; k < 9; k++) d->P[k] = (float)P[k]; // the double constants above are the fp32 literals' decimal strings: exact round trip
+  }
   d->exposure = f[3];
   const float clip = f[off + 7];
   d->clip_t = 0.0f;
   if(clip > 0.0f)
   {
+#if VKB_FAST
     const double c = host_decode_trc(clip, d->trc);
     double t = 1e30;
     for(int j = 0; j < 3; j++) t = fmin(t, (A[3 * j] + A[3 * j + 1] + A[3 * j + 2]) * c);
     d->clip_t = (float)t;
+#else
+    // main-impl.glsl:241-247: the clip level runs through decode_colour and cat16 like a pixel, in fp32
+    float c[3], o[3];
+    c[0] = c[1] = c[2] = host_decode_trc_f(clip, d->trc);
+    if(d->has_P) { host_mat3v_f(d->P, c, o); memcpy(c, o, sizeof(c)); }
+    host_mat3v_f(d->MR, c, o);
+    for(int k = 0; k < 3; k++) o[k] *= d->ratio[k];
+    host_mat3v_f(d->XM, o, c);
+    d->clip_t = fminf(c[0], fminf(c[1], c[2]));
+#endif
     if(!(d->clip_t > 0.0f)) return vkb_set_error(VKB_ERR_BAD_ARG, "colour: non-positive highlight clip level");
   }
   d->N = ii[16] > 24 ? 24 : ii[16];
@@ -193,8 +244,12 @@ static int colour_digest(const float *f, uint32_t size, colour_digest_t *d)
 // and a result below 2^-126 only ever enters 1 - x, so flushing it changes nothing.
 VKB_DEV float weibull_cdf_ftz(float x, float il, float k)
 {
+#if VKB_FAST
   const float p = ex2_ftz(k * lg2_ftz(fmaxf(x, 1e-7f) * il));   // __powf(x * il, k)
   return 1.0f - ex2_ftz(-p * 1.4426950408889634f);               // __expf(-p)
+#else
+  return weibull_cdf(x, il, k);                                  // libm's powf and expf bit for bit
+#endif
 }
 #define PW_NPX 4
 template <bool F32>
@@ -220,9 +275,13 @@ __global__ void __launch_bounds__(256) k_pointwise_dflt(const uint2 *__restrict_
   const float4 px = h4_to_f4(raw[q]);
   // crop's output edge is f16: the fetched texel already is
   const colour_digest_t &C = P.colour;
+#if VKB_FAST
   f3 o = { C.A[0] * px.x + C.A[1] * px.y + C.A[2] * px.z,
            C.A[3] * px.x + C.A[4] * px.y + C.A[5] * px.z,
            C.A[6] * px.x + C.A[7] * px.y + C.A[8] * px.z };
+#else
+  f3 o = colour_matrices({ px.x, px.y, px.z }, C);
+#endif
   o.x *= C.exposure; o.y *= C.exposure; o.z *= C.exposure;
   o.x = clampf(o.x, -65535.0f, 65535.0f); o.y = clampf(o.y, -65535.0f, 65535.0f); o.z = clampf(o.z, -65535.0f, 65535.0f);
   o = round3(o);
@@ -237,7 +296,7 @@ __global__ void __launch_bounds__(256) k_pointwise_dflt(const uint2 *__restrict_
   const bool fy = s1 > s0; if(fy) { t = s0; s0 = s1; s1 = t; }
   const bool fz = s2 > s1; if(fz) { t = s2; s2 = s1; s1 = t; }
   float r0 = weibull_cdf_ftz(s0, il, k), r2 = weibull_cdf_ftz(s2, il, k);
-  float r1 = mixf(r2, r0, __fdividef(s1 - s2 + 1e-6f, s0 - s2 + 1e-6f));
+  float r1 = mixf(r2, r0, m_div(s1 - s2 + 1e-6f, s0 - s2 + 1e-6f));
   if(fz) { t = r2; r2 = r1; r1 = t; }
   if(fy) { t = r0; r0 = r1; r1 = t; }
   if(fx) { t = r2; r2 = r1; r1 = t; }
@@ -375,3 +434,5 @@ VKB_REGISTER("colour", "main", launch_colour);
 VKB_REGISTER("filmcurv", "main", launch_filmcurv);
 VKB_REGISTER("grade", "main", launch_grade);
 VKB_REGISTER("b200", "pointw", launch_pointw);
+
+VKB_NS_END

@@ -154,3 +154,5 @@ static int launch_rawnoop(const vkb_launch_t *l)
   return launch_unpack_t<true>(l, pi[0], pf[1], pf[2]);
 }
 VKB_REGISTER("b200", "rawnoop", launch_rawnoop);
+
+VKB_NS_END

@@ -214,3 +214,5 @@ static int launch_rcd_fill(const vkb_launch_t *l)
   return VKB_OK;
 }
 VKB_REGISTER("demosaic", "rcd_fill", launch_rcd_fill);
+
+VKB_NS_END

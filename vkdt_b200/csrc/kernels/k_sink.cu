@@ -46,3 +46,27 @@ static int launch_cvt16(const vkb_launch_t *l)
   return VKB_OK;
 }
 VKB_REGISTER("b200", "cvt16", launch_cvt16);
+
+// (b200, libm): the mode's transcendental functions element by element, for the tests that compare them with libm
+// (tests/test_libm_exact_gpu.py).  push: { u32 op }: 0 exp, 1 exp2, 2 log2, 3 pow(a, b).  conn: [0] a f32, [1] b f32, [2] out f32
+__global__ void __launch_bounds__(256) k_libm(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ out, size_t n, int op)
+{
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if(i >= n) return;
+  const float x = a[i], y = b[i];
+  out[i] = op == 0 ? m_exp(x) : (op == 1 ? m_exp2(x) : (op == 2 ? m_log2(x) : m_pow(x, y)));
+}
+static int launch_libm(const vkb_launch_t *l)
+{
+  VKB_REQUIRE(l->num_conn >= 3 && l->push_size >= 4);
+  const vkb_image_t *a = l->conn, *b = l->conn + 1, *out = l->conn + 2;
+  VKB_REQUIRE(a->format == VKB_TOKEN_F32 && b->format == VKB_TOKEN_F32 && out->format == VKB_TOKEN_F32);
+  const size_t n = (size_t)out->wd * out->ht * out->chan;
+  if(!n) return VKB_OK;
+  k_libm<<<(unsigned)((n + 255) / 256), 256, 0, l->stream>>>((const float *)a->data, (const float *)b->data, (float *)out->data, n, *(const int *)l->push);
+  VKB_CHECK_LAUNCH();
+  return VKB_OK;
+}
+VKB_REGISTER("b200", "libm", launch_libm);
+
+VKB_NS_END

@@ -1,13 +1,13 @@
 // per-pixel device functions of the pointwise modules: crop (gather front end), colour, filmcurv, grade.
 // restated from crop/main.comp:20-57, colour/main-impl.glsl:118-341, filmcurv/main.comp:68-166 +
 // params.glsl:15-34, grade/main.comp:21-62, shared.glsl:47-96,371-387, shared/dtucs.glsl:11-83,
-// colourspaces.glsl:2-78.  transcendentals use the SFU intrinsics (what GLSL pow/exp compile to on a GPU);
-// the chain is ALU-sensitive at ~250 Gpx/s, accurate libm versions would make it compute bound.
+// colourspaces.glsl:2-78.  transcendentals: m_pow / m_exp of common.cuh, i.e. libm's results bit for bit in the strict
+// build and the SFU intrinsics (what GLSL pow/exp compile to on a GPU) in the fast one.
 #pragma once
 #include "common.cuh"
 
-#define PW_POW(x, y) pow_ftz((x), (y))
-#define PW_EXP(x)    exp_ftz((x))
+#define PW_POW(x, y) m_pow((x), (y))
+#define PW_EXP(x)    m_exp((x))
 
 // ---- parameter blocks, same byte layout as the reference's uniform blocks ----
 struct crop_committed_t { float H[12]; float r[4]; float crop[4]; };                     // crop/main.c:311-335
@@ -16,6 +16,11 @@ struct grade_params_t { float lift[4], gamma[4], gain[4], off[4]; int mode; floa
 // colour: host side digest of the 242-float committed block (colour/main.c:260-364)
 struct colour_digest_t
 {
+  // strict build: the shader's own sequence per pixel (main-impl.glsl:152-198 decode_colour's primaries matrix, then
+  // cat16() :49-67 = XM * (diag(cd/cs) * (MR * rgb))), every matrix in fp32 exactly as the shader / restatement forms it
+  float P[9]; uint32_t has_P;   // primaries -> rec2020, row major (has_P == 0: rec2020 input, no multiplication)
+  float MR[9], XM[9], ratio[3]; // M16 * rec2020_to_xyz, xyz_to_rec2020 * M16i, cl_dst / cl_src
+  // fast build: all of it premultiplied on the host in double
   float A[9];        // row major: xyz_to_rec2020 * M16i * diag(cl_dst/cl_src) * M16 * rec2020_to_xyz * primaries
   float exposure;    // mul.w
   float clip_t;      // min channel of the processed clip colour, <= 0: no clipping
@@ -146,8 +151,8 @@ VKB_DEV float decode_trc(float v, uint32_t trc)
               return v > b * 4.5f ? PW_POW((v + (a - 1)) / a, 2.2f) : v / 4.5f; }
     case 2: return v > 0.04045f ? PW_POW((v + 0.055f) / 1.055f, 2.4f) : v / 12.92f;
     case 3: { const float m1 = 1305.0f / 8192.0f, m2 = 2523.0f / 32.0f, c1 = 107.0f / 128.0f, c2 = 2413.0f / 128.0f, c3 = 2392.0f / 128.0f;
-              const float xp = powf(fmaxf(0.0f, v), 1.0f / m2);
-              return powf(fmaxf(xp - c1, 0.0f) / fmaxf(c2 - c3 * xp, 1e-10f), 1.0f / m1); }
+              const float xp = PW_POW(fmaxf(0.0f, v), 1.0f / m2);
+              return PW_POW(fmaxf(xp - c1, 0.0f) / fmaxf(c2 - c3 * xp, 1e-10f), 1.0f / m1); }
     case 4: return PW_POW(v, 2.6f);
     case 5: { const float a = 0.17883277f, b = 0.28466892f, c = 0.55991073f;
               return v <= 0.5f ? v * v / 3.0f : (PW_EXP((v - c) / a) + b) / 12.0f; }
@@ -155,12 +160,27 @@ VKB_DEV float decode_trc(float v, uint32_t trc)
     default: return v;
   }
 }
+VKB_DEV f3 mat3v(const float *M, f3 v)
+{ // y = M x, row major, each row summed left to right (matrices.h / o_mat3mulv)
+  return { M[0] * v.x + M[1] * v.y + M[2] * v.z, M[3] * v.x + M[4] * v.y + M[5] * v.z, M[6] * v.x + M[7] * v.y + M[8] * v.z };
+}
+VKB_DEV f3 colour_matrices(f3 c, const colour_digest_t &p)
+{ // primaries -> rec2020, then cat16 (main-impl.glsl:49-67), operation for operation
+  if(p.has_P) c = mat3v(p.P, c);
+  f3 cl = mat3v(p.MR, c);
+  cl.x *= p.ratio[0]; cl.y *= p.ratio[1]; cl.z *= p.ratio[2];
+  return mat3v(p.XM, cl);
+}
 VKB_DEV f3 colour_px(f3 c, const colour_digest_t &p)
 {
   if(p.trc) { c.x = decode_trc(c.x, p.trc); c.y = decode_trc(c.y, p.trc); c.z = decode_trc(c.z, p.trc); }
+#if VKB_FAST
   f3 o = { p.A[0] * c.x + p.A[1] * c.y + p.A[2] * c.z,
            p.A[3] * c.x + p.A[4] * c.y + p.A[5] * c.z,
            p.A[6] * c.x + p.A[7] * c.y + p.A[8] * c.z };
+#else
+  f3 o = colour_matrices(c, p);
+#endif
   if(p.clip_t > 0.0f) { o.x = fminf(o.x, p.clip_t); o.y = fminf(o.y, p.clip_t); o.z = fminf(o.z, p.clip_t); }
   o.x *= p.exposure; o.y *= p.exposure; o.z *= p.exposure;
   if(p.N > 0)
@@ -208,7 +228,7 @@ VKB_DEV f3 adjust_colour_dng(f3 col0, f3 col1)
   if(col0.z > col0.y) { SWP(col0.z, col0.y) SWP(col1.z, col1.y) fx = true; }
   if(col0.y > col0.x) { SWP(col0.x, col0.y) SWP(col1.x, col1.y) fy = true; }
   if(col0.z > col0.y) { SWP(col0.z, col0.y) SWP(col1.z, col1.y) fz = true; }
-  col1.y = mixf(col1.z, col1.x, __fdividef(col0.y - col0.z + 1e-6f, col0.x - col0.z + 1e-6f)); // blend factor: 2 ulp is plenty
+  col1.y = mixf(col1.z, col1.x, m_div(col0.y - col0.z + 1e-6f, col0.x - col0.z + 1e-6f)); // blend factor (fast: 2 ulp is plenty)
   if(fz) SWP(col1.z, col1.y)
   if(fy) SWP(col1.x, col1.y)
   if(fx) SWP(col1.z, col1.y)
@@ -356,7 +376,7 @@ VKB_DEV f3 grade_px(f3 c, const grade_params_t &q)
   else
   {
     float L = fmaxf(v[0], 0.0f) * 0.2126f + fmaxf(v[1], 0.0f) * 0.7152f + fmaxf(v[2], 0.0f) * 0.0722f;
-    L = clampf(0.67f + __log2f(fmaxf(L, 1e-6f)) * 0.11f, 0.0f, 1.0f);
+    L = clampf(0.67f + m_log2(fmaxf(L, 1e-6f)) * 0.11f, 0.0f, 1.0f);
     const float sp = clampf(q.sh_pivot, 1e-3f, 1.0f - 1e-3f);
     const float hp = clampf(q.hi_pivot, sp + 1e-3f, 1.0f);
     const float w_s = 1.0f - smoothstepf(0.0f, sp, L);

@@ -110,6 +110,8 @@ int vkb_graph_perf(vkb_graph_t *h, char *buf, size_t bufsize)
   for(char c : h->g->perf_text) n += c == '\n';
   return n;
 }
+int vkb_graph_set_mode(vkb_graph_t *h, int mode) { if(!h || (mode != VKB_MODE_STRICT && mode != VKB_MODE_FAST)) return VKB_ERR_BAD_ARG; h->g->mode = mode; return VKB_OK; }
+int vkb_graph_set_perf(vkb_graph_t *h, int on) { if(!h) return VKB_ERR_BAD_ARG; h->g->perf = on != 0; return VKB_OK; }
 int vkb_graph_dump_nodes(vkb_graph_t *h, char *buf, size_t bufsize)
 {
   if(!h || !buf || !bufsize) return VKB_ERR_BAD_ARG;

@@ -373,6 +373,9 @@ static int build_plan(dt_graph_t *g, bool with_device)
       }
       else { s.buf_upload = out; s.bytes = conn_bytes(nd->connector); }
       p->buf[s.buf_upload].first = -1; // written by the upload, before launch 0
+      // a run without UPLOAD_SOURCE (parameters changed, same image) reads the source again: the reference keeps source
+      // connectors s_conn_protected for that (graph-run-nodes-allocate.h:959-963), here the upload buffer is never recycled
+      p->buf[s.buf_upload].pinned_live = 1;
       if(s.external) p->buf[s.buf_upload].external = (void *)ms->data;
       p->source.push_back(s);
       continue;
@@ -440,6 +443,10 @@ static int build_plan(dt_graph_t *g, bool with_device)
         const dt_node_t *nx = &g->node[cs[0].first];
         if(!is_pointwise(nx) || is_node(nx, "crop", "main") || cs[0].second != 0 || B.consumed[cs[0].first]) break;
         if(nx->connector[find_conn(nx, "output")].roi.wd != g->node[cur].connector[oc].roi.wd) break;
+        // the fused kernel holds one parameter block per op type: a second instance of a module starts a new launch
+        bool repeated = false;
+        for(int cn : chain) if(pw_op(&g->node[cn]) == pw_op(nx)) repeated = true;
+        if(repeated) break;
         chain.push_back(cs[0].first);
         cur = cs[0].first;
         if(chain.size() == 7) break;
@@ -534,6 +541,9 @@ int dt_graph_run(dt_graph_t *g, uint32_t run)
 {
   int r;
   if(vkb_device_count() <= 0) return vkb_set_error(VKB_ERR_NO_DEVICE, "no CUDA device: vkdt_b200 has no CPU fallback");
+  // per-launch timing is a property of the graph (vkb_graph_set_perf, the reference's -d perf log mask) or an explicit flag
+  // outside the reference's bits; s_graph_run_all (-1u, every bit set) never implies it
+  const bool perf = g->perf || (run != (uint32_t)VKB_RUN_ALL && (run & VKB_RUN_PERF));
   if((run & (VKB_RUN_ROI | VKB_RUN_CREATE_NODES | VKB_RUN_ALLOC)) || !g->plan || !g->plan->pool)
   {
     r = build_plan(g, true);
@@ -575,7 +585,7 @@ int dt_graph_run(dt_graph_t *g, uint32_t run)
     for(int m : p->modid) if(g->module[m].so->commit_params) g->module[m].so->commit_params(g, &g->module[m]);
     // launch arguments of this run, and their fingerprint: every byte a kernel can see (parameters, push constants,
     // image pointers and shapes)
-    uint64_t hash = 1469598103934665603ull;
+    uint64_t hash = 1469598103934665603ull ^ (uint64_t)g->mode;
     auto mix = [&hash](const void *d, size_t n) { const uint8_t *b = (const uint8_t *)d; for(size_t k = 0; k < n; k++) { hash ^= b[k]; hash *= 1099511628211ull; } };
     for(size_t i = 0; i < p->launch.size(); i++)
     {
@@ -599,8 +609,9 @@ int dt_graph_run(dt_graph_t *g, uint32_t run)
       {
         plan_launch_t &l = p->launch[i];
         if(events) cudaEventRecord(p->ev[i], p->stream);
-        const int rr = vkb_dispatch(l.name, l.kernel, l.wd, l.ht, l.dp, l.push.data(), (uint32_t)l.push.size(), l.arg_params.data(), (uint32_t)l.arg_params.size(),
-            l.arg_conn.data(), (uint32_t)l.arg_conn.size(), p->stream);
+        const vkb_launch_t kl = { l.wd, l.ht, l.dp, l.push.data(), (uint32_t)l.push.size(), l.arg_params.data(), (uint32_t)l.arg_params.size(),
+            l.arg_conn.data(), (uint32_t)l.arg_conn.size(), p->stream, -1, -1 };
+        const int rr = vkb_dispatch_launch(l.name, l.kernel, g->mode, &kl);
         if(rr) return rr;
       }
       if(events) cudaEventRecord(p->ev[p->launch.size()], p->stream);
@@ -610,7 +621,7 @@ int dt_graph_run(dt_graph_t *g, uint32_t run)
     // (a clip ping-ponging between two device buffers has two) and re-launched as one unit, which takes the ~60 kernel
     // launches and their dependency latencies off the host and the stream front end.  -d perf runs stay plain launches.
     static const bool no_graph = getenv("VKB_NO_CUDA_GRAPH") != 0;
-    if((run & VKB_RUN_PERF) || no_graph) { r = dispatch_all((run & VKB_RUN_PERF) != 0); if(r) return r; }
+    if(perf || no_graph) { r = dispatch_all(perf); if(r) return r; }
     else
     {
       plan_graph_t *hit = 0;
@@ -675,7 +686,7 @@ int dt_graph_run(dt_graph_t *g, uint32_t run)
   {
     cudaError_t e = cudaStreamSynchronize(p->stream);
     if(e != cudaSuccess) return vkb_set_error(VKB_ERR_CUDA, "graph run failed: %s", cudaGetErrorString(e));
-    if((run & VKB_RUN_RECORD_CMD_BUF) && (run & VKB_RUN_PERF))
+    if((run & VKB_RUN_RECORD_CMD_BUF) && perf)
     { // -d perf (graph.c:881-933)
       char b[256];
       g->perf_text.clear();

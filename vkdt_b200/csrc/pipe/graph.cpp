@@ -69,6 +69,8 @@ dt_graph_t *dt_graph_new()
   g->searchpath[0] = 0; g->basedir[0] = 0;
   g->plan = 0;
   g->device = 0;
+  g->perf = 0;
+  g->mode = vkb_default_mode();
   return g;
 }
 

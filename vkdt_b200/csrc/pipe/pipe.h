@@ -199,6 +199,8 @@ struct dt_graph_t
   std::vector<vkb_mem_sink_t>   mem_sink;
   std::string perf_text;
   int      device;
+  int      mode;                             // VKB_MODE_STRICT | VKB_MODE_FAST (vkb_graph_set_mode)
+  int      perf;                             // time every launch (vkb_graph_set_perf)
 };
 
 // ---- graph api (graph.h:176-194, module.c, connector.inc, graph-io.c) ----

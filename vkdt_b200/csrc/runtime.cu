@@ -5,10 +5,11 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <atomic>
 
-#define VKB_MAX_KERNELS 128
-struct kernel_entry_t { vkb_token_t name, kernel; vkb_kernel_fn fn; };
+#define VKB_MAX_KERNELS 256
+struct kernel_entry_t { vkb_token_t name, kernel; vkb_kernel_fn fn; int mode; };
 static kernel_entry_t *g_kernels() { static kernel_entry_t k[VKB_MAX_KERNELS]; return k; }
 static int &g_kernel_cnt() { static int n = 0; return n; }
 static thread_local char g_err[512] = "";
@@ -22,15 +23,22 @@ extern "C" vkb_token_t vkb_token(const char *str)
   return t;
 }
 
-void vkb_register_kernel(const char *name, const char *kernel, vkb_kernel_fn fn)
+static int &g_mode()
+{ // process default: strict, unless the environment asks for the fast build of the kernels
+  static int m = (getenv("VKB_FAST") && atoi(getenv("VKB_FAST")) != 0) ? VKB_MODE_FAST : VKB_MODE_STRICT;
+  return m;
+}
+int vkb_default_mode(void) { return g_mode(); }
+void vkb_register_kernel(const char *name, const char *kernel, vkb_kernel_fn fn, int mode)
 {
   if(g_kernel_cnt() >= VKB_MAX_KERNELS) return;
-  g_kernels()[g_kernel_cnt()++] = { vkb_token(name), vkb_token(kernel), fn };
+  g_kernels()[g_kernel_cnt()++] = { vkb_token(name), vkb_token(kernel), fn, mode };
 }
-vkb_kernel_fn vkb_find_kernel(vkb_token_t name, vkb_token_t kernel)
+vkb_kernel_fn vkb_find_kernel(vkb_token_t name, vkb_token_t kernel, int mode)
 {
+  if(mode < 0) mode = g_mode();
   for(int i = 0; i < g_kernel_cnt(); i++)
-    if(g_kernels()[i].name == name && g_kernels()[i].kernel == kernel) return g_kernels()[i].fn;
+    if(g_kernels()[i].name == name && g_kernels()[i].kernel == kernel && g_kernels()[i].mode == mode) return g_kernels()[i].fn;
   return 0;
 }
 int vkb_set_error(int code, const char *fmt, ...)
@@ -41,6 +49,21 @@ int vkb_set_error(int code, const char *fmt, ...)
   return code;
 }
 void vkb_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int vkb_dispatch_launch(vkb_token_t name, vkb_token_t kernel, int mode, const vkb_launch_t *l)
+{
+  if(g_device < 0) { const int r = vkb_init(0); if(r) return r; }
+  vkb_kernel_fn fn = vkb_find_kernel(name, kernel, mode);
+  if(!fn)
+  {
+    char a[9] = {0}, b[9] = {0};
+    memcpy(a, &name, 8); memcpy(b, &kernel, 8);
+    return vkb_set_error(VKB_ERR_UNKNOWN_KERNEL, "no kernel registered for (%s, %s)", a, b);
+  }
+  for(uint32_t i = 0; i < l->num_conn; i++)
+    if(l->conn[i].data && l->conn[i].layers == 0) return vkb_set_error(VKB_ERR_BAD_ARG, "connector %u has zero layers", i);
+  return fn(l);
+}
 
 extern "C" {
 
@@ -90,19 +113,8 @@ int vkb_dispatch(vkb_token_t name, vkb_token_t kernel, uint32_t wd, uint32_t ht,
                  const void *push, uint32_t push_size, const void *params, uint32_t params_size,
                  const vkb_image_t *conn, uint32_t num_conn, void *stream)
 {
-  int r = need_device();
-  if(r) return r;
-  vkb_kernel_fn fn = vkb_find_kernel(name, kernel);
-  if(!fn)
-  {
-    char a[9] = {0}, b[9] = {0};
-    memcpy(a, &name, 8); memcpy(b, &kernel, 8);
-    return vkb_set_error(VKB_ERR_UNKNOWN_KERNEL, "no kernel registered for (%s, %s)", a, b);
-  }
-  for(uint32_t i = 0; i < num_conn; i++)
-    if(conn[i].data && conn[i].layers == 0) return vkb_set_error(VKB_ERR_BAD_ARG, "connector %u has zero layers", i);
-  vkb_launch_t l = { wd, ht, dp, push, push_size, params, params_size, conn, num_conn, (cudaStream_t)stream };
-  return fn(&l);
+  vkb_launch_t l = { wd, ht, dp, push, push_size, params, params_size, conn, num_conn, (cudaStream_t)stream, -1, -1 };
+  return vkb_dispatch_launch(name, kernel, -1, &l);
 }
 
 int vkb_event_create(void **ev) { int r = need_device(); if(r) return r; cudaEvent_t e; CU(cudaEventCreate(&e)); *ev = (void *)e; return VKB_OK; }
@@ -111,13 +123,24 @@ int vkb_event_sync(void *ev) { CU(cudaEventSynchronize((cudaEvent_t)ev)); return
 int vkb_event_elapsed_ms(void *ev0, void *ev1, float *ms) { CU(cudaEventElapsedTime(ms, (cudaEvent_t)ev0, (cudaEvent_t)ev1)); return VKB_OK; }
 int vkb_event_destroy(void *ev) { CU(cudaEventDestroy((cudaEvent_t)ev)); return VKB_OK; }
 
-int vkb_kernel_count(void) { return g_kernel_cnt(); }
+// the strict set is what introspection lists (the fast set has the same names)
+int vkb_kernel_count(void) { int n = 0; for(int i = 0; i < g_kernel_cnt(); i++) n += g_kernels()[i].mode == VKB_MODE_STRICT; return n; }
 int vkb_kernel_name(int idx, vkb_token_t *name, vkb_token_t *kernel)
 {
-  if(idx < 0 || idx >= g_kernel_cnt()) return VKB_ERR_BAD_ARG;
-  *name = g_kernels()[idx].name; *kernel = g_kernels()[idx].kernel;
+  for(int i = 0; i < g_kernel_cnt(); i++) if(g_kernels()[i].mode == VKB_MODE_STRICT && idx-- == 0)
+  {
+    *name = g_kernels()[i].name; *kernel = g_kernels()[i].kernel;
+    return VKB_OK;
+  }
+  return VKB_ERR_BAD_ARG;
+}
+int vkb_set_mode(int mode)
+{
+  if(mode != VKB_MODE_STRICT && mode != VKB_MODE_FAST) return vkb_set_error(VKB_ERR_BAD_ARG, "mode %d: VKB_MODE_STRICT or VKB_MODE_FAST", mode);
+  g_mode() = mode;
   return VKB_OK;
 }
+int vkb_get_mode(void) { return g_mode(); }
 uint64_t vkb_launch_count(void) { return g_launches.load(); }
 void vkb_launch_count_reset(void) { g_launches.store(0); }
 

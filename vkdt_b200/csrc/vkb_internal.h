@@ -14,11 +14,27 @@ struct vkb_launch_t
   const void *params; uint32_t params_size;
   const vkb_image_t *conn; uint32_t num_conn;
   cudaStream_t stream;
+  // band split (executor.cpp): only rows [band_y0, band_y1) of the launcher's band image (the image
+  // its grid covers) are computed; every coordinate, mirror rule and size stays that of the whole image.  -1: everything.
+  int32_t band_y0, band_y1;
 };
 typedef int (*vkb_kernel_fn)(const vkb_launch_t *);
 
-void vkb_register_kernel(const char *name, const char *kernel, vkb_kernel_fn fn);
-vkb_kernel_fn vkb_find_kernel(vkb_token_t name, vkb_token_t kernel);
+// kernels exist in two builds, see kernels/common.cuh: mode 0 strict (default), 1 fast
+#ifndef VKB_FAST
+#define VKB_FAST 0
+#endif
+#if VKB_FAST
+#define VKB_NS_BEGIN namespace vkb_fast {
+#else
+#define VKB_NS_BEGIN namespace vkb_strict {
+#endif
+#define VKB_NS_END }
+void vkb_register_kernel(const char *name, const char *kernel, vkb_kernel_fn fn, int mode);
+vkb_kernel_fn vkb_find_kernel(vkb_token_t name, vkb_token_t kernel, int mode = -1); // mode < 0: the process default (vkb_set_mode)
+int vkb_default_mode(void);
+// what vkb_dispatch does, with an explicit mode and band (the graph executor's entry point)
+int vkb_dispatch_launch(vkb_token_t name, vkb_token_t kernel, int mode, const vkb_launch_t *l);
 int  vkb_set_error(int code, const char *fmt, ...);
 void vkb_count_launch(int n);
 
@@ -26,7 +42,7 @@ void vkb_count_launch(int n);
 #define VKB_TOKEN_F32  0x323366ull        /* "f32"  */
 #define VKB_TOKEN_UI16 0x36316975ull      /* "ui16" */
 
-struct vkb_registrar_t { vkb_registrar_t(const char *n, const char *k, vkb_kernel_fn f) { vkb_register_kernel(n, k, f); } };
+struct vkb_registrar_t { vkb_registrar_t(const char *n, const char *k, vkb_kernel_fn f) { vkb_register_kernel(n, k, f, VKB_FAST); } };
 #define VKB_REGISTER(name, kernel, fn) static vkb_registrar_t vkb_reg_##fn(name, kernel, fn)
 
 #define VKB_CHECK_LAUNCH() do { cudaError_t e_ = cudaGetLastError(); \
