@@ -324,6 +324,37 @@ def pipeline_goldens():
         print("pipeline golden", name, "vs oracle: max abs %.3g, psnr %.1f dB" % T.check(name, out[name], T.oracle_output(O, name)))
 
 
+def pipeline_goldens_2mp():
+    """the same reference pipeline on the CPU at 3 MP (2004 x 1500: bayer + denoise, x-trans + denoise; ~1 min of shader
+    emulation each).  the full output is 36 MB: the fixture keeps the lattice of every 8th pixel (offset 3) and the statistics of
+    the whole frame against the oracle (tests/test_reference_gpu.py compares the product on the lattice)."""
+    from oracle import oracle_py as O
+    import test_pipeline_ref_cpu as T
+    out = {}
+    for name, (w, h, xtrans, strength) in T.CASES_2MP.items():
+        raw = synth.mosaic(w, h, seed=77, xtrans=xtrans)
+        lines = ["param:denoise:01:strength:%g" % strength]
+        kw = dict(wb=T.WB, noise_a=T.NOISE[0], noise_b=T.NOISE[1])
+        if xtrans:
+            kw["filters"] = 9
+        ref = O.ref_pipeline_run(O.ref_graph_describe(w, h, lines, kw), raw)[..., :3].astype(np.float32)
+        d = O.darkroom_defaults(w, h)
+        for k, v in enumerate(T.WB):
+            d.whitebalance[k] = v
+        d.noise_a, d.noise_b = T.NOISE
+        d.denoise.strength = strength
+        d.filters = 9 if xtrans else d.filters
+        d.enable_grade = 1
+        want = O.darkroom_run(d, raw)[..., :3]
+        err = np.abs(ref.astype(np.float64) - want)
+        mse = float(np.mean(err ** 2))
+        stats = np.array([ref.shape[0], ref.shape[1], err.max(), 99.0 if mse == 0 else 10 * np.log10(1.0 / mse), (err > 1e-3).mean(), (err != 0).mean()])
+        print(name, ref.shape, "reference vs oracle over the whole frame: max abs %.3g psnr %.1f dB, > 1e-3: %.3g, differing: %.3g" % tuple(stats[2:]))
+        out[name] = ref[3::8, 3::8].copy()
+        out[name + "_stats"] = stats
+    np.savez_compressed(os.path.join(HERE, "pipeline_ref_2mp.npz"), **out)
+
+
 def darkroom_goldens():
     w, h = 168, 126
     raw = synth.mosaic(w, h, seed=77)
@@ -347,4 +378,6 @@ if __name__ == "__main__":
     cfg_goldens()
     shader_goldens()
     pipeline_goldens()
+    if "--big" in sys.argv:
+        pipeline_goldens_2mp()
     darkroom_goldens()

@@ -52,6 +52,35 @@ def assert_close_mixed(got, want, ulps=3, atol=4e-6, min_exact=0.85, what="", ma
         what, int(bad.sum()), int(d.max()), float(np.abs(got - want).max()), exact)
 
 
+def parity_gate(got, want, what="", max_abs=1e-3, min_psnr=60.0):
+    """BASELINE.json north_star, literally: float outputs within max-abs 1e-3 and PSNR >= 60 dB in linear rec2020.
+    (the strict kernels are bit compatible with the restatement: what is measured here is normally 0 and 99 dB; the census
+    file records it.)"""
+    got = np.asarray(got, dtype=np.float32); want = np.asarray(want, dtype=np.float32)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    both_nan = np.isnan(got) & np.isnan(want)
+    assert not (np.isnan(got) ^ np.isnan(want)).any(), "%s: NaN on one side only" % what
+    err = np.abs(np.where(both_nan, 0.0, got) - np.where(both_nan, 0.0, want))
+    p = psnr(np.where(both_nan, 0.0, got), np.where(both_nan, 0.0, want))
+    import os
+    path = os.environ.get("VKB_CENSUS")
+    if path:
+        with open(path, "a") as f:
+            f.write("%-44s graph: max_abs %.3g  psnr %.1f dB  differing %d of %d  > 1e-3: %d\n" % (what, float(err.max()), p, int((err != 0).sum()), err.size, int((err > 1e-3).sum())))
+    assert p >= min_psnr, "%s: psnr %.1f dB < %.1f" % (what, p, min_psnr)
+    assert float(err.max()) <= max_abs, "%s: max abs %.3g > %.3g (%d of %d values beyond it)" % (what, float(err.max()), max_abs, int((err > max_abs).sum()), err.size)
+    return float(err.max()), p
+
+
+def census_graph(what, got, want):
+    import os
+    path = os.environ.get("VKB_CENSUS")
+    if path:
+        err = np.abs(np.asarray(got, dtype=np.float64) - np.asarray(want, dtype=np.float64))
+        with open(path, "a") as f:
+            f.write("%-44s graph: max_abs %.3g  differing %d of %d  > 1e-3: %d\n" % (what, float(np.nanmax(err)), int((err != 0).sum()), err.size, int((err > 1e-3).sum())))
+
+
 def psnr(got, want, peak=1.0):
     got = np.asarray(got, dtype=np.float64); want = np.asarray(want, dtype=np.float64)
     mse = np.mean((got - want) ** 2)

@@ -5,7 +5,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from helpers import psnr
+from helpers import psnr, parity_gate
 from vkdt_b200 import synth
 
 pytestmark = pytest.mark.gpu
@@ -57,13 +57,13 @@ def test_darkroom_end_to_end(gpu, oracle, dims, src, packed):
     err = np.abs(got[..., :3] - want[..., :3])
     p = psnr(got[..., :3], want[..., :3])
     print("max abs %.3g, psnr %.1f dB, pool %.1f MB\n%s" % (err.max(), p, g.pool_bytes() / 1e6, g.perf()))
-    # gate (BASELINE.json north_star): PSNR >= 60 dB and max-abs <= 1e-3 in linear rec2020.
-    # every edge of the reference graph is an f16 image: where the CUDA exp/pow and libm differ in the last fp32 bit an
-    # f16 rounding flips (4.9e-4 in [0.5,1), 9.8e-4 in [1,2)), and llap's local contrast gain can stack two such flips
-    # to 3 ulp at isolated pixels.  so: <= 1e-3 on all but 1e-5 of the values, never above 2e-3.
-    assert p >= 60.0, p
-    assert (err > 1e-3).mean() <= 1e-5 and err.max() <= 2e-3, (err.max(), float((err > 1e-3).mean()))
+    # gate (BASELINE.json north_star): PSNR >= 60 dB and max-abs <= 1e-3 in linear rec2020, literally.  every edge of the
+    # reference graph is an f16 image, so the strict kernels reproduce the restatement's arithmetic operation for operation
+    # (libm's exp / pow bit for bit, no fused multiply-adds): no rounding can flip, nothing can stack through llap's pyramid
+    # or fall the other way at a discontinuous decision.
+    parity_gate(got[..., :3], want[..., :3], "darkroom %dx%d %s" % (w, h, src))
     assert (err > 5e-4).mean() < 2e-3
+
 
 
 @pytest.mark.parametrize("dims", [(512, 384), (644, 486)])
@@ -77,8 +77,8 @@ def test_darkroom_with_wavelet_denoise(gpu, oracle, dims):
     p = psnr(got[..., :3], want[..., :3])
     print("denoise on: max abs %.3g, psnr %.1f dB\n%s" % (err.max(), p, g.perf()))
     assert "denoise_downcov" in g.perf() and "denoise_doub" in g.perf()
-    assert p >= 60.0, p
-    assert (err > 1e-3).mean() <= 1e-4 and err.max() <= 5e-3, (err.max(), float((err > 1e-3).mean()))
+    parity_gate(got[..., :3], want[..., :3], "darkroom+denoise %dx%d" % (w, h))
+
 
 
 def test_graph_without_display_fails(gpu):
@@ -138,7 +138,7 @@ def test_imlv_file_source_and_cli(gpu, oracle, tmp_path):
         err = np.abs(got - want[..., :3])
         # gate of the full size configs: the xyz matrix drives some channels negative, where the tone curve's
         # hue preserving ratio amplifies an f16 flip more than with the mild matrices of the other tests
-        assert psnr(got, want[..., :3]) >= 60.0 and err.max() <= 1e-2 and (err > 1e-3).mean() <= 1e-5, (f, err.max())
+        parity_gate(got, want[..., :3], "i-mlv file + cli, frame %d" % f)
 
 
 @pytest.mark.parametrize("strength", [0.0, 0.4])
@@ -164,7 +164,7 @@ def test_xtrans_end_to_end(gpu, oracle, strength):
     err = np.abs(out[..., :3] - want[..., :3])
     p = psnr(out[..., :3], want[..., :3])
     print("xtrans strength %.1f: max abs %.3g psnr %.1f" % (strength, err.max(), p))
-    assert p >= 60.0 and (err > 1e-3).mean() <= 1e-4 and err.max() <= 5e-3, (err.max(), p)
+    parity_gate(out[..., :3], want[..., :3], "xtrans strength %.1f" % strength)
 
 
 @pytest.mark.parametrize("xtrans", [False, True])
@@ -192,7 +192,7 @@ def test_halfsize_demosaic(gpu, oracle, xtrans):
     assert "demosaic_halfsize" in perf and ("shared_resample" in perf) == xtrans
     err = np.abs(out[..., :3] - want[..., :3])
     p = psnr(out[..., :3], want[..., :3])
-    assert p >= 60.0 and (err > 1e-3).mean() <= 1e-4 and err.max() <= 5e-3, (err.max(), p)
+    parity_gate(out[..., :3], want[..., :3], "halfsize demosaic xtrans=%d" % int(xtrans))
 
 
 @pytest.mark.parametrize("dims", [(512, 420), (646, 412)])
@@ -220,7 +220,7 @@ def test_rcd_demosaic(gpu, oracle, dims):
     err = np.abs(out[..., :3] - want[..., :3])
     p = psnr(out[..., :3], want[..., :3])
     print("rcd: max abs %.3g psnr %.1f" % (err.max(), p))
-    assert p >= 60.0 and (err > 1e-3).mean() <= 1e-4 and err.max() <= 5e-3, (err.max(), p)
+    parity_gate(out[..., :3], want[..., :3], "rcd demosaic")
 
 
 @pytest.mark.parametrize("cfa,xtrans", [(((1, 2), (0, 1)), False), (None, True)])
@@ -265,7 +265,7 @@ def test_iraw_dng_file_source(gpu, oracle, tmp_path, cfa, xtrans):
     err = np.abs(got[..., :3] - want[..., :3])
     p = psnr(got[..., :3], want[..., :3])
     print("max abs %.3g psnr %.1f" % (err.max(), p))
-    assert p >= 60.0 and (err > 1e-3).mean() <= 1e-5 and err.max() <= 2e-3
+    parity_gate(got[..., :3], want[..., :3], "i-raw dng file")
 
 
 NO_LLAP = ("module:llap:01\n", "connect:filmcurv:01:output:llap:01:input\nconnect:llap:01:output:grade:01:input\n")
@@ -332,7 +332,7 @@ def test_small_and_ragged_frames(gpu, oracle, dims, strength):
     err = np.abs(got[..., :3] - want[..., :3])
     p = psnr(got[..., :3], want[..., :3])
     print("%dx%d strength %.1f: max abs %.3g psnr %.1f" % (w, h, strength, err.max(), p))
-    assert p >= 60.0 and err.max() <= 2e-3 and (err > 1e-3).mean() <= 1e-3
+    parity_gate(got[..., :3], want[..., :3], "small frame %dx%d strength %.1f" % (w, h, strength))
 
 
 def test_empty_source_is_an_error(gpu):
@@ -382,7 +382,7 @@ def test_ipfm_stage_isolation(gpu, oracle, tmp_path):
     err = np.abs(got[..., :3] - want[..., :3])
     p = psnr(got[..., :3], want[..., :3])
     print("tail of the graph from a pfm: max abs %.3g psnr %.1f" % (err.max(), p))
-    assert p >= 60.0 and err.max() <= 2e-3 and (err > 1e-3).mean() <= 1e-5
+    parity_gate(got[..., :3], want[..., :3], "i-pfm stage isolation")
     # a missing file leaves the graph without a source
     g2 = gpu.Graph(cfg_text=TAIL_CFG)
     g2.line("param:i-pfm:main:filename:%s" % str(tmp_path / "nope.pfm"))
@@ -390,30 +390,45 @@ def test_ipfm_stage_isolation(gpu, oracle, tmp_path):
         g2.run()
 
 
-@pytest.mark.parametrize("cfgname,dims,src,packed,strength", [
-    ("C1 24 MP bayer still", (6000, 4000), "i-raw", False, 0.4),
-    ("C4 MLV 4K frame", (4096, 2160), "i-mlv", True, 0.0),
+@pytest.mark.parametrize("cfgname,dims,src,packed,strength,xtrans", [
+    ("C1 24 MP bayer still", (6000, 4000), "i-raw", False, 0.4, False),
+    ("C2 61 MP bayer still (the bench workload)", (9504, 6336), "i-raw", False, 0.4, False),
+    ("C3 26 MP x-trans still", (6240, 4152), "i-raw", False, 0.4, True),
+    ("C4 MLV 4K frame", (4096, 2160), "i-mlv", True, 0.0, False),
 ])
-def test_baseline_configs_at_full_size(gpu, oracle, cfgname, dims, src, packed, strength):
-    """BASELINE.json configs at their real dimensions, whole graph against the oracle (the oracle needs ~10 s and a few GB
-    here; the 61 and 201 MP configs run the same code and are covered through bench.py and the properties below)."""
+def test_baseline_configs_at_full_size(gpu, oracle, cfgname, dims, src, packed, strength, xtrans):
+    """BASELINE.json configs 1-4 at their real dimensions, whole graph (denoise 0.4 + hilite + llap + grade for the stills)
+    against the oracle, with the north_star tolerance literally: max abs <= 1e-3, PSNR >= 60 dB.  the oracle needs 5-20 s and
+    up to ~12 GB of host memory per case.  (config 5, 201 MP: test_bands_gpu.py compares the band split with one GPU, which
+    runs the code tested here.)"""
     w, h = dims
-    raw = synth.mosaic(w, h, seed=101)
-    want = oracle.darkroom_run(_oracle_cfg(oracle, w, h, strength=strength, noise=(100.0, 2.0)), raw)
+    raw = synth.mosaic(w, h, seed=101, xtrans=xtrans)
+    d = _oracle_cfg(oracle, w, h, strength=strength, noise=(100.0, 2.0))
+    if xtrans:
+        d.filters = 9
+    want = oracle.darkroom_run(d, raw)
     extra = ("param:denoise:01:strength:%g" % strength,) if strength > 0 else ()
-    got, g = _run_graph(gpu, raw, src, packed, extra=extra, noise=(100.0, 2.0))
+    if xtrans:
+        buf = np.ascontiguousarray(raw)
+        g = gpu.Graph(cfg_text=gpu.DARKROOM_CFG.format(src=src))
+        for l in extra:
+            assert g.line(l) == 0
+        g.set_source(buf.ctypes.data, gpu.raw_params(w, h, wb=WB, cam_to_rec2020=CAM, noise_a=100.0, noise_b=2.0, filters=9))
+        g.set_sink_buffer(None, 0)
+        g.run()
+        ow, oh = g.sink_size()
+        got = np.zeros((oh, ow, 4), dtype=np.float32)
+        g.set_sink_buffer(got.ctypes.data, got.nbytes)
+        g.run(gpu.RUN_RECORD | gpu.RUN_UPLOAD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT)
+    else:
+        got, g = _run_graph(gpu, raw, src, packed, extra=extra, noise=(100.0, 2.0))
     assert got.shape == want.shape
     err = np.abs(got[..., :3] - want[..., :3])
-    p = psnr(got[..., :3], want[..., :3])
-    print("%s: %dx%d -> %dx%d max abs %.3g psnr %.1f dB, > 1e-3: %.2e of the values" % (cfgname, w, h, got.shape[1], got.shape[0], err.max(), p, (err > 1e-3).mean()))
     k = np.unravel_index(np.argmax(err), err.shape)
-    print("largest difference at %s: got %.6f want %.6f" % (k, got[..., :3][k], want[..., :3][k]))
-    assert p >= 60.0 and (err > 1e-3).mean() <= 1e-5
-    # with tens of millions of values a few hundred land where a discontinuous decision of the graph (demosaic's
-    # eigenvector snap, denoise's covariance pick and hot pixel test) sees an input one f16 ulp away from the oracle's and
-    # falls the other way: isolated pixels up to ~1 % off.  the gate: <= 1e-3 on all but 1e-5 of the values (measured
-    # 3.5e-6 at 24 MP), <= 2e-3 on all but 2e-6, nothing beyond 1e-2
-    assert (err > 2e-3).mean() <= 2e-6 and err.max() <= 1e-2
+    print("%s: %dx%d -> %dx%d max abs %.3g, differing values %d of %d; largest at %s: got %.6f want %.6f" % (
+        cfgname, w, h, got.shape[1], got.shape[0], err.max(), int((err != 0).sum()), err.size, k, got[..., :3][k], want[..., :3][k]))
+    parity_gate(got[..., :3], want[..., :3], cfgname)
+    g.close()
 
 
 def test_full_size_61mp_properties(gpu):
@@ -542,7 +557,7 @@ def test_crop_window_and_rotation_end_to_end(gpu, oracle, crop, rot):
     err = np.abs(got[..., :3] - want[..., :3])
     p = psnr(got[..., :3], want[..., :3])
     print("crop %s rot %g: %s max abs %.3g psnr %.1f" % (crop, rot, got.shape, err.max(), p))
-    assert p >= 60.0 and (err > 1e-3).mean() <= 1e-4 and err.max() <= 4e-3
+    parity_gate(got[..., :3], want[..., :3], "crop %s rot %g" % (crop, rot))
 
 
 def _set(obj, path, val):
@@ -599,7 +614,12 @@ def test_parameter_variants_end_to_end(gpu, oracle, name):
     err = np.abs(got[..., :3] - want[..., :3])
     p = psnr(got[..., :3], want[..., :3])
     print("%s: max abs %.3g psnr %.1f, > 1e-3: %.2e" % (name, err.max(), p, (err > 1e-3).mean()))
-    # the oklab mode scales the pixel by a ratio of luminances (filmcurv/main.comp:150-166): next to black the ratio
-    # amplifies an input ulp a hundredfold at a handful of pixels
-    cap = 5e-2 if name == "filmcurv-oklab" else 4e-3
-    assert p >= 60.0 and (err > 1e-3).mean() <= 1e-4 and err.max() <= cap
+    from helpers import census_graph
+    census_graph(name, got[..., :3], want[..., :3])
+    # the tone curve modes 0 / 4 / 5 go through sin / cos / atan2, where the device's functions are not libm's bit for bit
+    # (1-2 ulp); the oklab mode scales the pixel by a ratio of luminances (filmcurv/main.comp:150-166), which next to black
+    # amplifies such an ulp a hundredfold at a handful of pixels.  every other variant: the north_star gate, literally
+    if name == "filmcurv-oklab":
+        assert p >= 60.0 and (err > 1e-3).mean() <= 1e-4 and err.max() <= 5e-2
+    else:
+        parity_gate(got[..., :3], want[..., :3], "variant " + name)

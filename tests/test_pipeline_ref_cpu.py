@@ -23,6 +23,13 @@ CASES = {  # name: (width, height, x-trans, denoise strength, demosaic method)
 }
 
 
+GOLDEN_2MP = os.path.join(os.path.dirname(__file__), "golden", "pipeline_ref_2mp.npz")
+CASES_2MP = {  # name: (width, height, x-trans, denoise strength): 3 MP frames, kept as a lattice (make_golden.pipeline_goldens_2mp)
+    "bayer_denoise_3mp": (2004, 1500, False, 0.4),
+    "xtrans_denoise_3mp": (2004, 1500, True, 0.4),
+}
+
+
 def inputs(name):
     w, h, xtrans, strength, method = CASES[name]
     raw = synth.mosaic(w, h, seed=77, xtrans=xtrans)

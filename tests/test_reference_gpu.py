@@ -1,24 +1,23 @@
-"""the product against the REFERENCE's own pipeline output, without the oracle in between: tests/golden/pipeline_ref.npz holds
+"""the product against the REFERENCE's own pipeline output, without the oracle in between: tests/golden/pipeline_ref*.npz hold
 what the sink receives when the reference's own graph code (compiled in place) drives the reference's own compute shaders
 (compiled as C++) on the CPU (tests/test_pipeline_ref_cpu.py, tests/golden/make_golden.py).  same seeded mosaics, same config
-lines, through the C-ABI graph.  gate: PSNR >= 60 dB (BASELINE.json); max abs: every edge of the graph is an f16 image, the
-reference-on-CPU and the GPU each round a few values the other way (one f16 ulp is 9.8e-4 in [1, 2)), so <= 1e-3 is asked of
-99 % of the values and 4e-3 of all of them."""
+lines, through the C-ABI graph.  gate: BASELINE.json's, literally: PSNR >= 60 dB and max abs <= 1e-3 on the small frames (120 x 90:
+bayer, bayer + denoise, x-trans + denoise).  on the 3 MP frames (kept as a lattice of every 8th pixel) the reference's shaders,
+which compute their texture coordinates in fp32, themselves sit up to 4e-3 from the ideal sampler of the restatement at a
+handful of pixels (the fixture records that distance over the whole frame): there the product, which is
+bit compatible with the restatement, has to reproduce exactly that distance and no more."""
 import os
 import numpy as np
 import pytest
 
-from helpers import psnr
+from helpers import psnr, parity_gate
 from vkdt_b200 import synth
 import test_pipeline_ref_cpu as R
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["bayer", "bayer_denoise"])
-def test_product_matches_reference_pipeline(gpu, name):
-    want = np.load(R.GOLDEN)[name]
-    w, h, raw, lines, kw = R.inputs(name)
+def _develop(gpu, w, h, raw, lines, kw):
     g = gpu.Graph(cfg_text=gpu.DARKROOM_CFG.format(src="i-raw"))
     for ln in lines:
         assert g.line(ln) == 0, ln
@@ -30,10 +29,37 @@ def test_product_matches_reference_pipeline(gpu, name):
     out = np.zeros((oh, ow, 4), dtype=np.float32)
     g.set_sink_buffer(out.ctypes.data, out.nbytes)
     g.run(gpu.RUN_RECORD | gpu.RUN_UPLOAD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT)
-    got = out[..., :3]
+    g.close()
+    return out[..., :3]
+
+
+@pytest.mark.parametrize("name", ["bayer", "bayer_denoise", "xtrans_denoise"])
+def test_product_matches_reference_pipeline(gpu, name):
+    want = np.load(R.GOLDEN)[name]
+    w, h, raw, lines, kw = R.inputs(name)
+    got = _develop(gpu, w, h, raw, lines, kw)
     assert got.shape == want.shape, (got.shape, want.shape)
+    assert np.isfinite(got).all()
+    parity_gate(got, want, "vs reference pipeline: " + name)
+
+
+@pytest.mark.parametrize("name", sorted(R.CASES_2MP))
+def test_product_matches_reference_pipeline_3mp(gpu, name):
+    gold = np.load(R.GOLDEN_2MP)
+    want, stats = gold[name], gold[name + "_stats"]
+    w, h, xtrans, strength = R.CASES_2MP[name]
+    raw = synth.mosaic(w, h, seed=77, xtrans=xtrans)
+    kw = dict(wb=R.WB, noise_a=R.NOISE[0], noise_b=R.NOISE[1])
+    if xtrans:
+        kw["filters"] = 9
+    got = _develop(gpu, w, h, raw, ["param:denoise:01:strength:%g" % strength], kw)
+    assert got.shape[:2] == (int(stats[0]), int(stats[1])), (got.shape, stats[:2])
+    got = got[3::8, 3::8]
+    assert got.shape == want.shape and np.isfinite(got).all()
     err = np.abs(got.astype(np.float64) - want)
     p = psnr(got, want)
-    print("%s vs the reference pipeline: max abs %.3g, psnr %.1f dB, > 1e-3: %.3g" % (name, err.max(), p, float((err > 1e-3).mean())))
-    assert np.isfinite(got).all() and p >= 60.0, p
-    assert err.max() <= 4e-3 and (err > 1e-3).mean() <= 1e-2, (err.max(), float((err > 1e-3).mean()))
+    print("%s vs the reference pipeline (lattice of %d values): max abs %.3g, psnr %.1f dB, > 1e-3: %.3g; the reference vs the restatement over "
+          "the whole frame: max abs %.3g, psnr %.1f dB, > 1e-3: %.3g" % (name, err.size, err.max(), p, float((err > 1e-3).mean()), stats[2], stats[3], stats[4]))
+    # PSNR gate as stated; max abs: no further from the reference's shaders than the restatement itself is
+    assert p >= 60.0 and p >= stats[3] - 1.0, (p, stats[3])
+    assert err.max() <= max(1e-3, stats[2] * 1.0000001) and (err > 1e-3).mean() <= max(2e-5, 4.0 * stats[4]), (err.max(), stats[2], float((err > 1e-3).mean()), stats[4])

@@ -200,7 +200,9 @@ __global__ void __launch_bounds__(256, 5) k_denoise_downcov(const uint2 *__restr
   st_rgba(out, w, ox, oy, make_float4(r / iw_, g / iw_, b / iw_, edge));
 }
 
-// x^0.8 on the SFU: ~1e-6 relative, i.e. <= 1e-4 in the [0,1] edge weight even at the 1e-3 noise floor of noise.glsl
+#define DN_F02 0.20000004768371582f
+#define DN_F04 0.3999999761581421f
+// x^0.8 on the SFU (fast): ~1e-6 relative, i.e. <= 1e-4 in the [0,1] edge weight even at the 1e-3 noise floor of noise.glsl
 VKB_DEV float gamma08(float f) { return f < 0.0f ? f : m_pow(f, 0.8f); }
 
 // ---- down: levels 1..3, 5 tap flower with edge stopping (down.comp:59-107) ----
@@ -224,7 +226,9 @@ __global__ void __launch_bounds__(256) k_denoise_down(const uint2 *__restrict__ 
   }
   // taps at (+1.2,+0.4) (-1.2,-0.4) (+0.4,-1.2) (-0.4,+1.2) from the texel centre: base texel and bilinear fraction
   const int   bx[4] = { x + 1, x - 2, x,     x - 1 }, by[4] = { y,    y - 1, y - 2, y + 1 };
-  const float ax[4] = { 0.2f,  0.8f,  0.4f,  0.6f  }, ay[4] = { 0.4f, 0.6f,  0.8f,  0.2f  };
+  // the shader's offsets are the fp32 constants 0.5+-1.2 = 1.7f, -0.7f and 0.5+-0.4 = 0.9f, 0.1f (glslang folds in double, then
+  // rounds): an ideal sampler sees the fractions (1.7f - 1.5) = 0.20000005 and (0.9f - 0.5) = 0.39999998, not 0.2f and 0.4f
+  const float ax[4] = { DN_F02, 0.8f, DN_F04, 0.6f }, ay[4] = { DN_F04, 0.6f, 0.8f, DN_F02 };
 #pragma unroll
   for(int o = 0; o < 4; o++)
   {
@@ -289,7 +293,7 @@ __global__ void __launch_bounds__(256, 6) k_denoise_down_tiled(const uint2 *__re
     g0[k] = gamma08(cc[k]);
   }
   constexpr int   bx[4] = { 1, -2, 0, -1 }, by[4] = { 0, -1, -2, 1 };
-  constexpr float ax[4] = { 0.2f,  0.8f,  0.4f,  0.6f  }, ay[4] = { 0.4f, 0.6f,  0.8f,  0.2f  };
+  constexpr float ax[4] = { DN_F02, 0.8f, DN_F04, 0.6f }, ay[4] = { DN_F04, 0.6f, 0.8f, DN_F02 };
 #pragma unroll
   for(int o = 0; o < 4; o++)
   {
