@@ -191,6 +191,22 @@ VKB_API int  vkb_graph_set_source_device(vkb_graph_t *g, const char *inst, const
 VKB_API int  vkb_graph_sink_device(vkb_graph_t *g, const char *inst, void **d_ptr);
 VKB_API uint64_t vkb_graph_pool_bytes(vkb_graph_t *g);
 VKB_API void *vkb_graph_stream(vkb_graph_t *g);                            /* the cudaStream_t the graph launches on (after the first run) */
+/* band split: ONE frame developed by n GPUs of the box, each computing a horizontal band of every
+ * kernel launch; halo rows (stencils, pyramid neighbours, denoise's quadrant swizzle) are copied between the devices' pools
+ * with peer access (NVLink), pyramid levels below 32 rows per device are computed whole on every device.  the result is bit
+ * for bit the one GPU frame.  devices[] are CUDA device ordinals (the same ordinal may be listed more than once: the bands
+ * then share that GPU, which is how the one-GPU tests exercise the exchange).  needs a u16 mosaic source in memory (host or
+ * device) and the default darkroom graph's kernels (bayer, denoise on); anything else fails loudly at the next run.
+ * n <= 1 switches it off.  takes effect at the next vkb_graph_run with VKB_RUN_ALL. */
+VKB_API int   vkb_graph_set_bands(vkb_graph_t *g, int n, const int *devices);
+/* host only (no GPU needed): the band split as text, per launch and device slot the rows computed, the rows pulled and from
+ * which slot, the slots waited for; then the source rows uploaded and sink rows downloaded per slot */
+VKB_API int   vkb_graph_band_plan(vkb_graph_t *g, char *buf, size_t bufsize);
+/* bytes the devices pull from their peers per frame (all devices / the busiest one), number of copies and kernel launches */
+VKB_API int   vkb_graph_band_stats(vkb_graph_t *g, uint64_t *bytes_total, uint64_t *bytes_max_device, int *pulls, int *launches);
+/* device side timing of banded frames: mark(0) before, mark(1) after a span of runs; elapsed = the slowest device's span */
+VKB_API int   vkb_graph_band_mark(vkb_graph_t *g, int which);
+VKB_API int   vkb_graph_band_elapsed_ms(vkb_graph_t *g, float *ms);
 VKB_API int   vkb_graph_set_device(vkb_graph_t *g, int device);             /* one graph per GPU: frame-parallel / band-split drivers */                      /* -d mem: peak pooled HBM */
 
 #ifdef __cplusplus

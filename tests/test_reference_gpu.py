@@ -60,6 +60,7 @@ def test_product_matches_reference_pipeline_3mp(gpu, name):
     p = psnr(got, want)
     print("%s vs the reference pipeline (lattice of %d values): max abs %.3g, psnr %.1f dB, > 1e-3: %.3g; the reference vs the restatement over "
           "the whole frame: max abs %.3g, psnr %.1f dB, > 1e-3: %.3g" % (name, err.size, err.max(), p, float((err > 1e-3).mean()), stats[2], stats[3], stats[4]))
-    # PSNR gate as stated; max abs: no further from the reference's shaders than the restatement itself is
+    # PSNR gate as stated; max abs: no further from the reference's shaders than the restatement itself is on this lattice
+    # (stats[6..8]: the restatement's max abs / share beyond 1e-3 / share of differing values there)
     assert p >= 60.0 and p >= stats[3] - 1.0, (p, stats[3])
-    assert err.max() <= max(1e-3, stats[2] * 1.0000001) and (err > 1e-3).mean() <= max(2e-5, 4.0 * stats[4]), (err.max(), stats[2], float((err > 1e-3).mean()), stats[4])
+    assert err.max() <= max(1e-3, stats[6] * 1.0000001) and (err > 1e-3).mean() <= max(1e-5, stats[7] * 1.0000001), (err.max(), stats[6], float((err > 1e-3).mean()), stats[7])

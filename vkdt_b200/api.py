@@ -44,7 +44,7 @@ vkb_event_sync vkb_event_elapsed_ms vkb_event_destroy vkb_dispatch vkb_kernel_co
 vkb_kernel_name vkb_launch_count vkb_launch_count_reset vkb_graph_new vkb_graph_free vkb_graph_read_config_ascii
 vkb_graph_read_config_line vkb_graph_replace_display vkb_graph_set_source vkb_graph_set_sink_buffer
 vkb_graph_sink_size vkb_graph_set_frame vkb_graph_run vkb_graph_plan vkb_graph_perf vkb_graph_dump_nodes
-vkb_graph_set_source_device vkb_graph_sink_device vkb_graph_pool_bytes vkb_graph_stream vkb_graph_set_device vkb_dng_info vkb_graph_set_sink_layout vkb_lj92_decode vkb_graph_committed_params vkb_graph_describe vkb_graph_state vkb_graph_set_perf vkb_set_mode vkb_get_mode vkb_graph_set_mode""".split()
+vkb_graph_set_source_device vkb_graph_sink_device vkb_graph_pool_bytes vkb_graph_stream vkb_graph_set_device vkb_dng_info vkb_graph_set_sink_layout vkb_lj92_decode vkb_graph_committed_params vkb_graph_describe vkb_graph_state vkb_graph_set_perf vkb_set_mode vkb_get_mode vkb_graph_set_mode vkb_graph_set_bands vkb_graph_band_plan vkb_graph_band_stats vkb_graph_band_mark vkb_graph_band_elapsed_ms""".split()
 
 
 def token(s):
@@ -123,6 +123,11 @@ lib.vkb_graph_perf.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
 lib.vkb_graph_set_perf.argtypes = [C.c_void_p, C.c_int]
 lib.vkb_graph_set_mode.argtypes = [C.c_void_p, C.c_int]
 lib.vkb_set_mode.argtypes = [C.c_int]
+lib.vkb_graph_set_bands.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+lib.vkb_graph_band_plan.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+lib.vkb_graph_band_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+lib.vkb_graph_band_mark.argtypes = [C.c_void_p, C.c_int]
+lib.vkb_graph_band_elapsed_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
 lib.vkb_graph_dump_nodes.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
 lib.vkb_graph_pool_bytes.argtypes = [C.c_void_p]
 lib.vkb_graph_pool_bytes.restype = C.c_uint64
@@ -287,6 +292,29 @@ class Graph:
 
     def set_mode(self, mode):
         check(lib.vkb_graph_set_mode(self.h, int(mode)))
+
+    def set_bands(self, devices):
+        """band split of one frame over these CUDA devices (an ordinal may repeat: bands sharing a GPU)."""
+        arr = (C.c_int * len(devices))(*devices)
+        check(lib.vkb_graph_set_bands(self.h, len(devices), arr))
+
+    def band_plan(self):
+        b = C.create_string_buffer(1 << 22)
+        check(lib.vkb_graph_band_plan(self.h, b, len(b)))
+        return b.value.decode()
+
+    def band_stats(self):
+        t, m, np_, nk = C.c_uint64(), C.c_uint64(), C.c_int(), C.c_int()
+        check(lib.vkb_graph_band_stats(self.h, C.byref(t), C.byref(m), C.byref(np_), C.byref(nk)))
+        return dict(bytes_total=t.value, bytes_max_device=m.value, pulls=np_.value, launches=nk.value)
+
+    def band_mark(self, which):
+        check(lib.vkb_graph_band_mark(self.h, which))
+
+    def band_elapsed_ms(self):
+        ms = C.c_float()
+        check(lib.vkb_graph_band_elapsed_ms(self.h, C.byref(ms)))
+        return ms.value
 
     def set_perf(self, on=True):
         check(lib.vkb_graph_set_perf(self.h, int(on)))

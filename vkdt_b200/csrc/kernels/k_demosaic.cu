@@ -16,10 +16,10 @@ int launch_xtrans_fix(const vkb_launch_t *l);
 // by 0, +-1 or 2 is exact, so one division per tap serves all three sums bit for bit.
 template <bool xtrans>
 __global__ void __launch_bounds__(256, 5) k_demosaic_gauss(const __half *__restrict__ orig, int iw, int ih,
-    uint2 *__restrict__ out, int ow, int oh)
+    uint2 *__restrict__ out, int ow, int oh, const band_t bd)
 {
-  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-  if(x >= ow || y >= oh) return;
+  const int x = blockIdx.x * 32 + threadIdx.x, y = BAND_BY * 8 + threadIdx.y;
+  if(x >= ow || y >= oh || BAND_SKIP(y)) return;
   constexpr int blk = xtrans ? 3 : 2, lo = xtrans ? 0 : -1;
   // the "white" (weights p, p^2) and "black" (weights 1/p, 1/p^2) estimates go through identical arithmetic: they run as
   // the two lanes of packed fp32 pairs (FMUL2 / FFMA2; lane lo = white, hi = black), like in denoise's downcov.
@@ -160,12 +160,15 @@ static int launch_demosaic_gauss(const vkb_launch_t *l)
   const demosaic_push_t *pc = (const demosaic_push_t *)l->push;
   const vkb_image_t *orig = l->conn + 1, *out = l->conn + 2;
   VKB_REQUIRE(orig->chan == 1 && orig->format == VKB_TOKEN_F16 && out->chan == 4 && out->format == VKB_TOKEN_F16);
+  dim3 grid = grid2d(out->wd, out->ht);
+  const band_t bd = band_of(l, 1, 8, out->ht, &grid.y);
+  if(!grid.y) return VKB_OK;
   if(pc->filters == 9)
-    k_demosaic_gauss<true><<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const __half *)orig->data, orig->wd, orig->ht,
-        (uint2 *)out->data, out->wd, out->ht);
+    k_demosaic_gauss<true><<<grid, blk2d, 0, l->stream>>>((const __half *)orig->data, orig->wd, orig->ht,
+        (uint2 *)out->data, out->wd, out->ht, bd);
   else
-    k_demosaic_gauss<false><<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const __half *)orig->data, orig->wd, orig->ht,
-        (uint2 *)out->data, out->wd, out->ht);
+    k_demosaic_gauss<false><<<grid, blk2d, 0, l->stream>>>((const __half *)orig->data, orig->wd, orig->ht,
+        (uint2 *)out->data, out->wd, out->ht, bd);
   VKB_CHECK_LAUNCH();
   return VKB_OK;
 }

@@ -23,9 +23,9 @@ VKB_DEV float splat_weight(float e0, float e1, float cz, float cw, int i, int j)
 }
 
 __global__ void __launch_bounds__(256, 6) k_bayer_splat(const __half *__restrict__ in, int w, int h,
-    const uint2 *__restrict__ gauss, int gw, int gh, __half *__restrict__ out)
+    const uint2 *__restrict__ gauss, int gw, int gh, __half *__restrict__ out, const band_t bd)
 {
-  const int b = blockIdx.x * 32 + threadIdx.x, c = blockIdx.y * 8 + threadIdx.y;
+  const int b = blockIdx.x * 32 + threadIdx.x, c = BAND_BY * 8 + threadIdx.y;
   if(2 * b - 1 >= w || 2 * c - 1 >= h) return;
   const float4 cov = ld_rgba_clamp(gauss, gw, gh, b, c);
   const float e0 = clampf(cov.x, 0.01f, 25.0f), e1 = clampf(cov.y, 0.01f, 25.0f);
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256, 6) k_bayer_splat(const __half *__restrict
   { // the four pixels of the shifted block: (lx,ly) in {1,2}^2 of the 4x4 neighbourhood
     const int lx = 1 + (q & 1), ly = 1 + (q >> 1);
     const int x = x0 + lx, y = y0 + ly;
-    if(x < 0 || y < 0 || x >= w || y >= h) continue;
+    if(x < 0 || y < 0 || x >= w || y >= h || BAND_SKIP(y)) continue; // band rows are output rows here
     float g = 0.0f, wg = 0.0f;
     const bool green = ((x & 1) != (y & 1));
 #define M(I, J) (interior ? m[ly + (J)][lx + (I)] : splat_fetch(in, w, h, x + (I), y + (J)))
@@ -84,9 +84,9 @@ VKB_DEV float fixw(float e0, float e1, float cz, float cw, int i, int j)
 }
 
 __global__ void __launch_bounds__(256, 5) k_bayer_fix(const __half *__restrict__ in, const __half *__restrict__ green, int w, int h,
-    const uint2 *__restrict__ covimg, int gw, int gh, uint2 *__restrict__ out)
+    const uint2 *__restrict__ covimg, int gw, int gh, uint2 *__restrict__ out, const band_t bd)
 {
-  const int b = blockIdx.x * 32 + threadIdx.x, c = blockIdx.y * 8 + threadIdx.y;
+  const int b = blockIdx.x * 32 + threadIdx.x, c = BAND_BY * 8 + threadIdx.y;
   if(2 * b - 1 >= w || 2 * c - 1 >= h) return;
   float4 cov = ld_rgba_clamp(covimg, gw, gh, b, c);
   cov.x = clampf(cov.x, 1.0f, 49.f); cov.y = clampf(cov.y, 1.0f, 49.f);
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256, 5) k_bayer_fix(const __half *__restrict__
   {
     const int lx = 1 + (q & 1), ly = 1 + (q >> 1);
     const int x = x0 + lx, y = y0 + ly;
-    if(x < 0 || y < 0 || x >= w || y >= h) continue;
+    if(x < 0 || y < 0 || x >= w || y >= h || BAND_SKIP(y)) continue; // band rows are output rows here
     const float gc = g[ly][lx];
     float r = 0.0f, bl = 0.0f, wr = 0.0f, wb = 0.0f;
 #define TAP(ACC, WACC, I, J, WGT) { ACC += m[ly + (J)][lx + (I)] * (1e-4f + gc) / (1e-4f + g[ly + (J)][lx + (I)]) * (WGT); WACC += (WGT); }
@@ -152,11 +152,25 @@ __global__ void __launch_bounds__(256, 5) k_bayer_fix(const __half *__restrict__
   }
 }
 
+// band of the shifted block kernels: thread row c writes output rows 2c-1 and 2c, so rows [y0, y1) need c in
+// [y0 / 2, y1 / 2]; bd.y0 / bd.y1 stay OUTPUT rows and are tested per pixel
+static inline band_t band_shifted(const vkb_launch_t *l, int out_ht, unsigned *grid_y)
+{
+  band_t b = { 0, 0, out_ht };
+  if(l->band_y0 < 0) return b;
+  b.y0 = l->band_y0; b.y1 = l->band_y1 < out_ht ? l->band_y1 : out_ht;
+  const int c0 = b.y0 / 2, c1 = b.y1 / 2 + 1; // thread rows [c0, c1)
+  b.by0 = c0 / 8;
+  *grid_y = b.y1 > b.y0 ? (unsigned)((c1 + 7) / 8 - b.by0) : 0u;
+  return b;
+}
 int launch_bayer_splat(const vkb_launch_t *l)
 {
   const vkb_image_t *in = l->conn, *g = l->conn + 1, *out = l->conn + 2;
   dim3 grid(vkb_cdiv(out->wd / 2 + 1, 32), vkb_cdiv(out->ht / 2 + 1, 8));
-  k_bayer_splat<<<grid, dim3(32, 8), 0, l->stream>>>((const __half *)in->data, in->wd, in->ht, (const uint2 *)g->data, g->wd, g->ht, (__half *)out->data);
+  const band_t bd = band_shifted(l, out->ht, &grid.y);
+  if(!grid.y) return VKB_OK;
+  k_bayer_splat<<<grid, dim3(32, 8), 0, l->stream>>>((const __half *)in->data, in->wd, in->ht, (const uint2 *)g->data, g->wd, g->ht, (__half *)out->data, bd);
   VKB_CHECK_LAUNCH();
   return VKB_OK;
 }
@@ -164,8 +178,10 @@ int launch_bayer_fix(const vkb_launch_t *l)
 {
   const vkb_image_t *in = l->conn, *g = l->conn + 1, *cov = l->conn + 2, *out = l->conn + 3;
   dim3 grid(vkb_cdiv(out->wd / 2 + 1, 32), vkb_cdiv(out->ht / 2 + 1, 8));
+  const band_t bd = band_shifted(l, out->ht, &grid.y);
+  if(!grid.y) return VKB_OK;
   k_bayer_fix<<<grid, dim3(32, 8), 0, l->stream>>>((const __half *)in->data, (const __half *)g->data, in->wd, in->ht,
-      (const uint2 *)cov->data, cov->wd, cov->ht, (uint2 *)out->data);
+      (const uint2 *)cov->data, cov->wd, cov->ht, (uint2 *)out->data, bd);
   VKB_CHECK_LAUNCH();
   return VKB_OK;
 }

@@ -35,10 +35,10 @@ VKB_DEV void swizzle(int x, int y, int w, int h, int &ox, int &oy)
 
 // ---- half: cfa block -> rgb (half.comp:24-74); input is the ui16 source sampled as UNORM ----
 __global__ void __launch_bounds__(256) k_denoise_half(const uint16_t *__restrict__ in, int iw, int ih,
-    uint2 *__restrict__ out, int ow, int oh, int cx, int cy, float white, int xtrans)
+    uint2 *__restrict__ out, int ow, int oh, int cx, int cy, float white, int xtrans, const band_t bd)
 {
-  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-  if(x >= ow || y >= oh) return;
+  const int x = blockIdx.x * 32 + threadIdx.x, y = BAND_BY * 8 + threadIdx.y;
+  if(x >= ow || y >= oh || BAND_SKIP(y)) return;
   float4 rgba;
 #define RAW(X, Y) ((float)__ldg(in + (size_t)clampi((Y), 0, ih - 1) * iw + clampi((X), 0, iw - 1)) / 65535.0f)
   if(xtrans)
@@ -76,11 +76,11 @@ __global__ void __launch_bounds__(256) k_denoise_half(const uint16_t *__restrict
 #define DC_H 12
 // the j loops stay rolled: 55 registers instead of 128, four CTAs per SM; the unrolled i loop gives the ILP
 __global__ void __launch_bounds__(256, 5) k_denoise_downcov(const uint2 *__restrict__ in, int w, int h,
-    uint2 *__restrict__ out, uint2 *__restrict__ covimg)
+    uint2 *__restrict__ out, uint2 *__restrict__ covimg, const band_t bd)
 {
   __shared__ float4 tile[DC_H][DC_W];  // r g b lum/25
   __shared__ float4 tinv[DC_H][DC_W];  // lum, 1/lum | lum*lum, 1/(lum*lum): every tap's divisions, done once per input texel
-  const int tx0 = blockIdx.x * 32 - 2, ty0 = blockIdx.y * 8 - 2;
+  const int tx0 = blockIdx.x * 32 - 2, ty0 = BAND_BY * 8 - 2;
   const int tid = threadIdx.y * 32 + threadIdx.x;
   for(int t = tid; t < DC_W * DC_H; t += 256)
   {
@@ -91,8 +91,8 @@ __global__ void __launch_bounds__(256, 5) k_denoise_downcov(const uint2 *__restr
     tinv[r][c] = make_float4(l, 1.0f / l, l2, 1.0f / l2);
   }
   __syncthreads();
-  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-  if(x >= w || y >= h) return;
+  const int x = blockIdx.x * 32 + threadIdx.x, y = BAND_BY * 8 + threadIdx.y;
+  if(x >= w || y >= h || BAND_SKIP(y)) return;
   const int lx = threadIdx.x, ly = threadIdx.y; // tile coords of tap (-2,-2)
   // the "white" (weights lum, lum^2) and "black" (weights 1/lum, 1/lum^2) estimates of cov.glsl run through identical
   // arithmetic: they travel as the two lanes of packed fp32 pairs (FMUL2 / FFMA2), one instruction for both.
@@ -258,10 +258,10 @@ VKB_DEV float4 unpack_rgba(uint2 v)
   return make_float4(a.x, a.y, b.x, b.y);
 }
 __global__ void __launch_bounds__(256, 6) k_denoise_down_tiled(const uint2 *__restrict__ in, int w, int h, uint2 *__restrict__ out,
-    denoise_params_t p, float black, float white, float noise_a, float noise_b, float lv, float blk)
+    denoise_params_t p, float black, float white, float noise_a, float noise_b, float lv, float blk, const band_t bd)
 {
   __shared__ uint2 tile[DD_H][DD_W];
-  const int tx0 = blockIdx.x * 32 - 2, ty0 = blockIdx.y * 8 - 2;
+  const int tx0 = blockIdx.x * 32 - 2, ty0 = BAND_BY * 8 - 2;
   // thread (tx, ty) stages rows ty, ty + 8 and columns tx, tx + 32 of the window: no division, one mirror per row / column
   {
     const int c0 = threadIdx.x, c1 = threadIdx.x + 32, r0 = threadIdx.y, r1 = threadIdx.y + 8;
@@ -276,8 +276,8 @@ __global__ void __launch_bounds__(256, 6) k_denoise_down_tiled(const uint2 *__re
     }
   }
   __syncthreads();
-  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-  if(x >= w || y >= h) return;
+  const int x = blockIdx.x * 32 + threadIdx.x, y = BAND_BY * 8 + threadIdx.y;
+  if(x >= w || y >= h || BAND_SKIP(y)) return;
   const int lx = threadIdx.x + 2, ly = threadIdx.y + 2;
   const float t = 0.2f;
   const float4 c0 = unpack_rgba(tile[ly][lx]);
@@ -322,10 +322,10 @@ struct asm_consts_t { float rgb_to_yuv[9], yuv_to_rgb[9]; float wb[3], black[3],
 // ---- assemble: wavelet shrinkage over the 4 detail bands (assemble.comp:43-165) ----
 __global__ void __launch_bounds__(256, 5) k_denoise_assemble(const uint2 *__restrict__ s0, const uint2 *__restrict__ s1, const uint2 *__restrict__ s2,
     const uint2 *__restrict__ s3, const uint2 *__restrict__ s4, uint2 *__restrict__ out, int w, int h,
-    const __grid_constant__ denoise_params_t p, const __grid_constant__ asm_consts_t K)
+    const __grid_constant__ denoise_params_t p, const __grid_constant__ asm_consts_t K, const band_t bd)
 {
-  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-  if(x >= w || y >= h) return;
+  const int x = blockIdx.x * 32 + threadIdx.x, y = BAND_BY * 8 + threadIdx.y;
+  if(x >= w || y >= h || BAND_SKIP(y)) return;
   const int szx = w + 1, szy = h + 1;
   const float4 orig = ld_rgba(s0, w, x, y);
   float d[5][3] = { { orig.x, orig.y, orig.z } };
@@ -479,10 +479,10 @@ __global__ void __launch_bounds__(256) k_denoise_doub(const uint16_t *__restrict
 // expressions are those of bilin_rgba() term by term.
 __global__ void __launch_bounds__(256, 5) k_denoise_doub_bayer(const uint16_t *__restrict__ in, int iw, int ih,
     const uint2 *__restrict__ crs0, const uint2 *__restrict__ crs1, int cw, int ch, __half *__restrict__ out, int ow, int oh,
-    const __grid_constant__ denoise_params_t p, const __grid_constant__ dn_push_doub_t P)
+    const __grid_constant__ denoise_params_t p, const __grid_constant__ dn_push_doub_t P, const band_t bd)
 {
-  const int X = blockIdx.x * 32 + threadIdx.x, Y = blockIdx.y * 8 + threadIdx.y;
-  if(X >= cw || Y >= ch) return;
+  const int X = blockIdx.x * 32 + threadIdx.x, Y = BAND_BY * 8 + threadIdx.y;
+  if(X >= cw || Y >= ch || BAND_SKIP(Y)) return;
   int xi[3], yi[3];
 #pragma unroll
   for(int k = 0; k < 3; k++) { xi[k] = mirrori(X - 1 + k, cw); yi[k] = mirrori(Y - 1 + k, ch); }
@@ -524,8 +524,11 @@ static int launch_half(const vkb_launch_t *l)
   const dn_push_half_t *pc = (const dn_push_half_t *)l->push;
   const vkb_image_t *in = l->conn, *out = l->conn + 1;
   VKB_REQUIRE(in->format == VKB_TOKEN_UI16 && in->chan == 1 && out->chan == 4 && out->format == VKB_TOKEN_F16);
-  k_denoise_half<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint16_t *)in->data, in->wd, in->ht, (uint2 *)out->data,
-      out->wd, out->ht, pc->crop[0], pc->crop[1], pc->white[1], pc->filters == 9);
+  dim3 grid = grid2d(out->wd, out->ht);
+  const band_t bd = band_of(l, 1, 8, out->ht, &grid.y);
+  if(!grid.y) return VKB_OK;
+  k_denoise_half<<<grid, blk2d, 0, l->stream>>>((const uint16_t *)in->data, in->wd, in->ht, (uint2 *)out->data,
+      out->wd, out->ht, pc->crop[0], pc->crop[1], pc->white[1], pc->filters == 9, bd);
   VKB_CHECK_LAUNCH();
   return VKB_OK;
 }
@@ -537,7 +540,10 @@ static int launch_downcov(const vkb_launch_t *l)
   VKB_REQUIRE(l->num_conn >= 3);
   const vkb_image_t *in = l->conn, *out = l->conn + 1, *cov = l->conn + 2;
   VKB_REQUIRE(in->chan == 4 && out->chan == 4 && cov->chan == 4 && in->wd == out->wd && in->ht == out->ht && cov->wd == in->wd);
-  k_denoise_downcov<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, (uint2 *)out->data, (uint2 *)cov->data);
+  dim3 grid = grid2d(out->wd, out->ht);
+  const band_t bd = band_of(l, 1, 8, out->ht, &grid.y);
+  if(!grid.y) return VKB_OK;
+  k_denoise_downcov<<<grid, blk2d, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, (uint2 *)out->data, (uint2 *)cov->data, bd);
   VKB_CHECK_LAUNCH();
   return VKB_OK;
 }
@@ -555,8 +561,13 @@ static int launch_down(const vkb_launch_t *l)
   const float blk = pc->block == 3 ? 2.23607f : (pc->block == 2 ? 1.414213f : 1.0f);
   host_escale(&p);
   if(in->wd >= DD_W && in->ht >= DD_H) // a window overhangs the image by less than its size: one reflection is enough
-    k_denoise_down_tiled<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, (uint2 *)out->data,
-        p, pc->black[1], pc->white[1], pc->noise_a, pc->noise_b, powf(0.7f, (float)pc->level), blk);
+  {
+    dim3 grid = grid2d(out->wd, out->ht);
+    const band_t bd = band_of(l, 1, 8, out->ht, &grid.y);
+    if(!grid.y) return VKB_OK;
+    k_denoise_down_tiled<<<grid, blk2d, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, (uint2 *)out->data,
+        p, pc->black[1], pc->white[1], pc->noise_a, pc->noise_b, powf(0.7f, (float)pc->level), blk, bd);
+  }
   else
   k_denoise_down<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, (uint2 *)out->data,
       p, pc->black[1], pc->white[1], pc->noise_a, pc->noise_b, powf(0.7f, (float)pc->level), blk);
@@ -596,8 +607,11 @@ static int launch_assemble(const vkb_launch_t *l)
     K.denorm[k] = (float)(((double)K.white[k] - (double)K.black[k]) / (double)K.wb[k]);
   }
   host_escale(&p);
-  k_denoise_assemble<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint2 *)c[0].data, (const uint2 *)c[1].data, (const uint2 *)c[2].data,
-      (const uint2 *)c[3].data, (const uint2 *)c[4].data, (uint2 *)out->data, out->wd, out->ht, p, K);
+  dim3 grid = grid2d(out->wd, out->ht);
+  const band_t bd = band_of(l, 1, 8, out->ht, &grid.y);
+  if(!grid.y) return VKB_OK;
+  k_denoise_assemble<<<grid, blk2d, 0, l->stream>>>((const uint2 *)c[0].data, (const uint2 *)c[1].data, (const uint2 *)c[2].data,
+      (const uint2 *)c[3].data, (const uint2 *)c[4].data, (uint2 *)out->data, out->wd, out->ht, p, K, bd);
   VKB_CHECK_LAUNCH();
   return VKB_OK;
 }
@@ -613,8 +627,13 @@ static int launch_doub(const vkb_launch_t *l)
   dn_push_doub_t P; memcpy(&P, l->push, sizeof(P));
   host_escale(&p);
   if(P.filters != 9u && P.filters != 0u && out->wd == 2 * c0->wd && out->ht == 2 * c0->ht)
-    k_denoise_doub_bayer<<<grid2d(c0->wd, c0->ht), blk2d, 0, l->stream>>>((const uint16_t *)in->data, in->wd, in->ht, (const uint2 *)c0->data,
-        (const uint2 *)c1->data, c0->wd, c0->ht, (__half *)out->data, out->wd, out->ht, p, P);
+  {
+    dim3 grid = grid2d(c0->wd, c0->ht);
+    const band_t bd = band_of(l, 2, 8, c0->ht, &grid.y); // band image: the output mosaic, two rows per thread row
+    if(!grid.y) return VKB_OK;
+    k_denoise_doub_bayer<<<grid, blk2d, 0, l->stream>>>((const uint16_t *)in->data, in->wd, in->ht, (const uint2 *)c0->data,
+        (const uint2 *)c1->data, c0->wd, c0->ht, (__half *)out->data, out->wd, out->ht, p, P, bd);
+  }
   else
   k_denoise_doub<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint16_t *)in->data, in->wd, in->ht, (const uint2 *)c0->data,
       (const uint2 *)c1->data, c0->wd, c0->ht, (__half *)out->data, out->wd, out->ht, p, P);

@@ -8,10 +8,10 @@ struct hilite_push_t   { float wb[4]; uint32_t filters; };     // hilite/main.c:
 
 // ---- half: mosaic block -> rgb, clipped greens replaced (half.comp:24-72) ----
 __global__ void __launch_bounds__(256) k_hilite_half(const __half *__restrict__ in, int iw, int ih,
-    uint2 *__restrict__ out, int ow, int oh, float white, int xtrans)
+    uint2 *__restrict__ out, int ow, int oh, float white, int xtrans, const band_t bd)
 {
-  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-  if(x >= ow || y >= oh) return;
+  const int x = blockIdx.x * 32 + threadIdx.x, y = BAND_BY * 8 + threadIdx.y;
+  if(x >= ow || y >= oh || BAND_SKIP(y)) return;
   float4 rgba;
   if(xtrans)
   {
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) k_hilite_half(const __half *__restrict__ 
 #define HR_TH 19
 #define HR_COL(c) ((((c) & 1) * 34) + ((c) >> 1))
 __global__ void __launch_bounds__(256) k_hilite_reduce(const uint2 *__restrict__ in, int iw, int ih,
-    uint2 *__restrict__ out, int ow, int oh, hilite_params_t p, float wbr, float wbg, float wbb)
+    uint2 *__restrict__ out, int ow, int oh, hilite_params_t p, float wbr, float wbg, float wbb, const band_t bd)
 {
   // everything the shader evaluates per tap except the binomial weight depends on the input texel alone (luminance,
   // clip test, desaturated colour: seven divisions and two smoothsteps).  a CTA of 32x8 outputs evaluates it once per
@@ -59,9 +59,9 @@ __global__ void __launch_bounds__(256) k_hilite_reduce(const uint2 *__restrict__
   float white = p.white;
   if(!(white > 0.0f)) white = 1.0f;
   const float ds = p.desat * p.desat;
-  const int tx0 = blockIdx.x * 64 - 2, ty0 = blockIdx.y * 16 - 2;
+  const int tx0 = blockIdx.x * 64 - 2, ty0 = BAND_BY * 16 - 2;
   // only the part of the window the CTA's valid outputs read: the last levels of the pyramid are a few pixels large
-  const int need_w = min(HR_TW, 2 * (ow - (int)blockIdx.x * 32) + 3), need_h = min(HR_TH, 2 * (oh - (int)blockIdx.y * 8) + 3);
+  const int need_w = min(HR_TW, 2 * (ow - (int)blockIdx.x * 32) + 3), need_h = min(HR_TH, 2 * (oh - BAND_BY * 8) + 3);
   for(int t = threadIdx.y * 32 + threadIdx.x; t < need_w * need_h; t += 256)
   {
     const int r = t / need_w, c = t - r * need_w;
@@ -85,8 +85,8 @@ __global__ void __launch_bounds__(256) k_hilite_reduce(const uint2 *__restrict__
     okay[r][HR_COL(c)] = ok ? 1.0f : 0.0f;
   }
   __syncthreads();
-  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-  if(x >= ow || y >= oh) return;
+  const int x = blockIdx.x * 32 + threadIdx.x, y = BAND_BY * 8 + threadIdx.y;
+  if(x >= ow || y >= oh || BAND_SKIP(y)) return;
   const float w[5] = {1.0f / 16.0f, 4.0f / 16.0f, 6.0f / 16.0f, 4.0f / 16.0f, 1.0f / 16.0f};
   const float sw[5] = {1.0f, 2.0f, 0.0f, -2.0f, -1.0f};
   float ex = 0.0f, ey = 0.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f, wgt = 0.0f;
@@ -115,10 +115,10 @@ __global__ void __launch_bounds__(256) k_hilite_reduce(const uint2 *__restrict__
 
 // ---- assemble: expand coarse, rescale to the fine level's unclipped channels, blend (assemble.comp:23-118) ----
 __global__ void __launch_bounds__(256) k_hilite_assemble(const uint2 *__restrict__ fine_img, const uint2 *__restrict__ coarse,
-    int cw, int ch, uint2 *__restrict__ out, int ow, int oh, hilite_params_t p)
+    int cw, int ch, uint2 *__restrict__ out, int ow, int oh, hilite_params_t p, const band_t bd)
 {
-  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-  if(x >= ow || y >= oh) return;
+  const int x = blockIdx.x * 32 + threadIdx.x, y = BAND_BY * 8 + threadIdx.y;
+  if(x >= ow || y >= oh || BAND_SKIP(y)) return;
   const float w[5] = {1.0f / 16.0f, 4.0f / 16.0f, 6.0f / 16.0f, 4.0f / 16.0f, 1.0f / 16.0f};
   const int ix = x / 2, iy = y / 2, dx = x & 1, dy = y & 1;
   float ur = 0.0f, ug = 0.0f, ub = 0.0f, wgt = 0.0f;
@@ -166,11 +166,11 @@ __global__ void __launch_bounds__(256) k_hilite_assemble(const uint2 *__restrict
 
 // ---- doub: write reconstructed values back into the mosaic where it clips (doub.comp:22-121) ----
 __global__ void __launch_bounds__(256) k_hilite_doub(const __half *__restrict__ in, int iw, int ih,
-    const uint2 *__restrict__ coarse, int cw, int ch, __half *__restrict__ out, int ow, int oh, float white, int xtrans)
+    const uint2 *__restrict__ coarse, int cw, int ch, __half *__restrict__ out, int ow, int oh, float white, int xtrans, const band_t bd)
 {
-  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  const int x = blockIdx.x * 32 + threadIdx.x, y = BAND_BY * 8 + threadIdx.y;
   const int bw = xtrans ? ow / 3 : ow / 2, bh = xtrans ? oh / 3 : oh / 2;
-  if(x >= bw || y >= bh) return;
+  if(x >= bw || y >= bh || BAND_SKIP(y)) return;
   float4 upsm = ld_rgba_clamp(coarse, cw, ch, x, y);
   const float softw = 0.97f * white;
   if(xtrans)
@@ -253,8 +253,11 @@ static int launch_hilite_half(const vkb_launch_t *l)
   const hilite_push_t *pc = (const hilite_push_t *)l->push;
   const vkb_image_t *in = l->conn, *out = l->conn + 1;
   VKB_REQUIRE(in->format == VKB_TOKEN_F16 && in->chan == 1 && out->format == VKB_TOKEN_F16 && out->chan == 4);
-  k_hilite_half<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const __half *)in->data, in->wd, in->ht,
-      (uint2 *)out->data, out->wd, out->ht, ((const float *)l->params)[0], pc->filters == 9);
+  dim3 grid = grid2d(out->wd, out->ht);
+  const band_t bd = band_of(l, 1, 8, out->ht, &grid.y);
+  if(!grid.y) return VKB_OK;
+  k_hilite_half<<<grid, blk2d, 0, l->stream>>>((const __half *)in->data, in->wd, in->ht,
+      (uint2 *)out->data, out->wd, out->ht, ((const float *)l->params)[0], pc->filters == 9, bd);
   VKB_CHECK_LAUNCH();
   return VKB_OK;
 }
@@ -269,8 +272,11 @@ static int launch_hilite_reduce(const vkb_launch_t *l)
   VKB_REQUIRE(in->chan == 4 && out->chan == 4 && in->format == VKB_TOKEN_F16 && out->format == VKB_TOKEN_F16);
   float wb[3] = { pc->wb[0], pc->wb[1], pc->wb[2] };
   if(!(wb[0] * wb[0] + wb[1] * wb[1] + wb[2] * wb[2] > 1e-3f)) wb[0] = wb[1] = wb[2] = 1.0f;
-  k_hilite_reduce<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht,
-      (uint2 *)out->data, out->wd, out->ht, *(const hilite_params_t *)l->params, wb[0], wb[1], wb[2]);
+  dim3 grid = grid2d(out->wd, out->ht);
+  const band_t bd = band_of(l, 1, 8, out->ht, &grid.y);
+  if(!grid.y) return VKB_OK;
+  k_hilite_reduce<<<grid, blk2d, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht,
+      (uint2 *)out->data, out->wd, out->ht, *(const hilite_params_t *)l->params, wb[0], wb[1], wb[2], bd);
   VKB_CHECK_LAUNCH();
   return VKB_OK;
 }
@@ -282,8 +288,11 @@ static int launch_hilite_assemble(const vkb_launch_t *l)
   VKB_REQUIRE(l->num_conn >= 3 && l->params_size >= sizeof(hilite_params_t));
   const vkb_image_t *fine = l->conn, *coarse = l->conn + 1, *out = l->conn + 2;
   VKB_REQUIRE(fine->chan == 4 && coarse->chan == 4 && out->chan == 4 && fine->wd == out->wd && fine->ht == out->ht);
-  k_hilite_assemble<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint2 *)fine->data, (const uint2 *)coarse->data,
-      coarse->wd, coarse->ht, (uint2 *)out->data, out->wd, out->ht, *(const hilite_params_t *)l->params);
+  dim3 grid = grid2d(out->wd, out->ht);
+  const band_t bd = band_of(l, 1, 8, out->ht, &grid.y);
+  if(!grid.y) return VKB_OK;
+  k_hilite_assemble<<<grid, blk2d, 0, l->stream>>>((const uint2 *)fine->data, (const uint2 *)coarse->data,
+      coarse->wd, coarse->ht, (uint2 *)out->data, out->wd, out->ht, *(const hilite_params_t *)l->params, bd);
   VKB_CHECK_LAUNCH();
   return VKB_OK;
 }
@@ -297,8 +306,11 @@ static int launch_hilite_doub(const vkb_launch_t *l)
   const vkb_image_t *in = l->conn, *coarse = l->conn + 1, *out = l->conn + 2;
   VKB_REQUIRE(in->chan == 1 && coarse->chan == 4 && out->chan == 1 && out->format == VKB_TOKEN_F16);
   const int xt = pc->filters == 9;
-  k_hilite_doub<<<grid2d(out->wd / (xt ? 3 : 2), out->ht / (xt ? 3 : 2)), blk2d, 0, l->stream>>>((const __half *)in->data, in->wd, in->ht,
-      (const uint2 *)coarse->data, coarse->wd, coarse->ht, (__half *)out->data, out->wd, out->ht, ((const float *)l->params)[0], xt);
+  dim3 grid = grid2d(out->wd / (xt ? 3 : 2), out->ht / (xt ? 3 : 2));
+  const band_t bd = band_of(l, xt ? 3 : 2, 8, out->ht / (xt ? 3 : 2), &grid.y); // band image: the output mosaic, one cfa block row per thread row
+  if(!grid.y) return VKB_OK;
+  k_hilite_doub<<<grid, blk2d, 0, l->stream>>>((const __half *)in->data, in->wd, in->ht,
+      (const uint2 *)coarse->data, coarse->wd, coarse->ht, (__half *)out->data, out->wd, out->ht, ((const float *)l->params)[0], xt, bd);
   VKB_CHECK_LAUNCH();
   return VKB_OK;
 }

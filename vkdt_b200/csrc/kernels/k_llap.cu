@@ -81,10 +81,10 @@ VKB_DEV float llap_grey(float4 px)
 #define R0_TH 17
 template <bool CLARITY>
 __global__ void __launch_bounds__(256, 6) k_llap_reduce0(const uint2 *__restrict__ in, int iw, int ih,
-    __half *__restrict__ out, int ow, int oh, llap_params_t p)
+    __half *__restrict__ out, int ow, int oh, llap_params_t p, const band_t bd)
 {
   __shared__ __align__(16) __half tile[NL][R0_TH][R0_TW + 1];
-  const int tx0 = blockIdx.x * 64 - 1, ty0 = blockIdx.y * 16 - 1;
+  const int tx0 = blockIdx.x * 64 - 1, ty0 = BAND_BY * 16 - 1;
   const int tid = threadIdx.y * 32 + threadIdx.x;
   const float inv2s = 1.0f / (2.0f * p.sigma), invd = 1.0f / (2.0f * p.sigma * p.sigma / 3.0f);
   for(int t = tid; t < R0_TW * R0_TH; t += 256)
@@ -98,8 +98,8 @@ __global__ void __launch_bounds__(256, 6) k_llap_reduce0(const uint2 *__restrict
     tile[NUM_GAMMA][ly][lx] = __float2half_rn(y);
   }
   __syncthreads();
-  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-  if(x >= ow || y >= oh) return;
+  const int x = blockIdx.x * 32 + threadIdx.x, y = BAND_BY * 8 + threadIdx.y;
+  if(x >= ow || y >= oh || BAND_SKIP(y)) return;
   const int lx = 2 * threadIdx.x, ly = 2 * threadIdx.y; // tile coords of texel (2x-1, 2y-1)
   const size_t plane = (size_t)ow * oh;
 #pragma unroll
@@ -126,10 +126,10 @@ __global__ void __launch_bounds__(256, 6) k_llap_reduce0(const uint2 *__restrict
 
 // ---- reduce of coarse levels: blockIdx.z = layer ----
 __global__ void __launch_bounds__(256) k_llap_reduce(const __half *__restrict__ in, int iw, int ih,
-    __half *__restrict__ out, int ow, int oh)
+    __half *__restrict__ out, int ow, int oh, const band_t bd)
 {
-  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, g = blockIdx.z;
-  if(x >= ow || y >= oh) return;
+  const int x = blockIdx.x * 32 + threadIdx.x, y = BAND_BY * 8 + threadIdx.y, g = blockIdx.z;
+  if(x >= ow || y >= oh || BAND_SKIP(y)) return;
   const __half *src = in + (size_t)g * iw * ih;
   float t[3][3];
 #pragma unroll
@@ -335,12 +335,15 @@ static int launch_llapr0(const vkb_launch_t *l)
   // fast: two layers per packed fp32 instruction (k_llap_r0.cu: fused multiply-adds, reciprocals, the SFU exponential);
   // strict: the scalar kernel below with the shader's curve operation for operation
   if(VKB_FAST && !getenv("VKB_LLAPR0_SCALAR")) return launch_llapr0_packed(l);
+  dim3 grid = grid2d(out->wd, out->ht);
+  const band_t bd = band_of(l, 1, 8, out->ht, &grid.y);
+  if(!grid.y) return VKB_OK;
   if(lp->clarity == 0.0f)
-    k_llap_reduce0<false><<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht,
-        (__half *)out->data, out->wd, out->ht, *lp);
+    k_llap_reduce0<false><<<grid, blk2d, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht,
+        (__half *)out->data, out->wd, out->ht, *lp, bd);
   else
-    k_llap_reduce0<true><<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht,
-        (__half *)out->data, out->wd, out->ht, *lp);
+    k_llap_reduce0<true><<<grid, blk2d, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht,
+        (__half *)out->data, out->wd, out->ht, *lp, bd);
   VKB_CHECK_LAUNCH();
   return VKB_OK;
 }
@@ -352,8 +355,11 @@ static int launch_llap_reduce(const vkb_launch_t *l)
   VKB_REQUIRE(l->num_conn >= 2);
   const vkb_image_t *in = l->conn, *out = l->conn + 1;
   VKB_REQUIRE(in->chan == 1 && out->chan == 1 && in->layers == out->layers && in->format == VKB_TOKEN_F16 && out->format == VKB_TOKEN_F16);
-  k_llap_reduce<<<grid2d(out->wd, out->ht, out->layers), blk2d, 0, l->stream>>>((const __half *)in->data, in->wd, in->ht,
-      (__half *)out->data, out->wd, out->ht);
+  dim3 grid = grid2d(out->wd, out->ht, out->layers);
+  const band_t bd = band_of(l, 1, 8, out->ht, &grid.y);
+  if(!grid.y) return VKB_OK;
+  k_llap_reduce<<<grid, blk2d, 0, l->stream>>>((const __half *)in->data, in->wd, in->ht,
+      (__half *)out->data, out->wd, out->ht, bd);
   VKB_CHECK_LAUNCH();
   return VKB_OK;
 }
@@ -372,6 +378,7 @@ static int launch_llap_assemble(const vkb_launch_t *l)
   VKB_REQUIRE(pc[1] || (coarse->wd == l1->wd && coarse->ht == l1->ht));
   VKB_REQUIRE(l1->wd == (out->wd - 1) / 2 + 1 && l1->ht == (out->ht - 1) / 2 + 1);
   if(out->wd >= 80 && out->ht >= 32) return launch_llap_assemble4(l, (int)pc[1]); // one thread per 2x2 pixels, k_llap_asm4.cu
+  if(l->band_y0 >= 0 && !(l->band_y0 == 0 && l->band_y1 >= (int)out->ht)) return vkb_set_error(VKB_ERR_BAD_ARG, "llap assemble: levels this small run whole, not banded");
   if(out->wd >= 64 && out->ht >= 16)
     k_llap_assemble_tiled<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const __half *)coarse->data, (const __half *)l0->data,
         (const __half *)l1->data, l1->wd, l1->ht, (__half *)out->data, out->wd, out->ht, (int)pc[1]);

@@ -50,14 +50,14 @@ VKB_DEV float expand_q(const float (&W)[5][5])
 }
 
 __global__ void __launch_bounds__(256, 4) k_llap_assemble4(const __half *__restrict__ coarse, const __half *__restrict__ l0,
-    const __half *__restrict__ l1, int cw, int ch, __half *__restrict__ out, int ow, int oh, int first)
+    const __half *__restrict__ l1, int cw, int ch, __half *__restrict__ out, int ow, int oh, int first, const band_t bd)
 {
   __shared__ float tile[NL + 1][A4_H][A4_W + 1];
   __shared__ int s_pmin, s_pmax;
   const int tid = threadIdx.y * 32 + threadIdx.x;
   if(tid == 0) { s_pmin = NUM_GAMMA; s_pmax = 0; }
-  const int kx = blockIdx.x * 32 + threadIdx.x, ky = blockIdx.y * 8 + threadIdx.y;
-  const int cx0 = blockIdx.x * 32 - 2, cy0 = blockIdx.y * 8 - 2;
+  const int kx = blockIdx.x * 32 + threadIdx.x, ky = BAND_BY * 8 + threadIdx.y;
+  const int cx0 = blockIdx.x * 32 - 2, cy0 = BAND_BY * 8 - 2;
   const size_t p0 = (size_t)ow * oh, p1 = (size_t)cw * ch;
   float v[4]; int hi[4];
   int mylo = NUM_GAMMA, myhi = 0;
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256, 4) k_llap_assemble4(const __half *__restr
   {
     const int x = 2 * kx + (q & 1), y = 2 * ky + (q >> 1);
     hi[q] = -1;
-    if(x < ow && y < oh)
+    if(x < ow && y < oh && !BAND_SKIP(ky))
     {
       v[q] = ld_h(l0 + NUM_GAMMA * p0, ow, x, y);
       hi[q] = gamma_hi_from_v(v[q]);
@@ -138,8 +138,11 @@ __global__ void __launch_bounds__(256, 4) k_llap_assemble4(const __half *__restr
 int launch_llap_assemble4(const vkb_launch_t *l, int first)
 {
   const vkb_image_t *coarse = l->conn, *l0 = l->conn + 1, *l1 = l->conn + 2, *out = l->conn + 3;
-  k_llap_assemble4<<<dim3(vkb_cdiv(out->wd, 64), vkb_cdiv(out->ht, 16)), dim3(32, 8), 0, l->stream>>>((const __half *)coarse->data, (const __half *)l0->data,
-      (const __half *)l1->data, l1->wd, l1->ht, (__half *)out->data, out->wd, out->ht, first);
+  dim3 grid(vkb_cdiv(out->wd, 64), vkb_cdiv(out->ht, 16));
+  const band_t bd = band_of(l, 2, 8, (out->ht + 1) / 2, &grid.y); // band image: the fine output, two rows per thread row
+  if(!grid.y) return VKB_OK;
+  k_llap_assemble4<<<grid, dim3(32, 8), 0, l->stream>>>((const __half *)coarse->data, (const __half *)l0->data,
+      (const __half *)l1->data, l1->wd, l1->ht, (__half *)out->data, out->wd, out->ht, first, bd);
   VKB_CHECK_LAUNCH();
   return VKB_OK;
 }

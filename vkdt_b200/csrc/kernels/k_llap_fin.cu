@@ -160,7 +160,7 @@ VKB_DEV f3 grade_px_digest(f3 c, const llapfin_t &P)
 
 template <bool F32, bool GRADE>
 __global__ void __launch_bounds__(256, 4) k_llap_final4(const uint2 *__restrict__ in, const __half *__restrict__ coarse,
-    const __half *__restrict__ l1, int cw, int ch, void *__restrict__ outv, int ow, int oh, const __grid_constant__ llapfin_t P)
+    const __half *__restrict__ l1, int cw, int ch, void *__restrict__ outv, int ow, int oh, const __grid_constant__ llapfin_t P, const band_t bd)
 {
   __shared__ float tile[NL + 1][F3_H][F3_W + 1];
   __shared__ int s_pmin, s_pmax;
@@ -168,8 +168,8 @@ __global__ void __launch_bounds__(256, 4) k_llap_final4(const uint2 *__restrict_
   const int tid = threadIdx.y * 32 + threadIdx.x;
   if(tid == 0) { s_pmin = NUM_GAMMA; s_pmax = 0; }
   if(tid < NUM_GAMMA) s_gamma[tid] = gamma_from_i(tid);
-  const int kx = blockIdx.x * 32 + threadIdx.x, ky = blockIdx.y * 8 + threadIdx.y;
-  const int cx0 = blockIdx.x * 32 - 2, cy0 = blockIdx.y * 8 - 2;
+  const int kx = blockIdx.x * 32 + threadIdx.x, ky = BAND_BY * 8 + threadIdx.y;
+  const int cx0 = blockIdx.x * 32 - 2, cy0 = BAND_BY * 8 - 2;
   const size_t p1 = (size_t)cw * ch;
   // 1) the four input pixels, their grey value and gamma bracket
   float4 px[4]; float grey[4], v[4]; int hi[4];
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(256, 4) k_llap_final4(const uint2 *__restrict_
   {
     const int x = 2 * kx + (q & 1), y = 2 * ky + (q >> 1);
     hi[q] = -1;
-    if(x < ow && y < oh)
+    if(x < ow && y < oh && !BAND_SKIP(ky))
     {
       px[q] = ld_rgba(in, ow, x, y);
       grey[q] = lum2020(clampf(px[q].x, -1000.0f, 1000.0f), clampf(px[q].y, -1000.0f, 1000.0f), clampf(px[q].z, -1000.0f, 1000.0f));
@@ -330,9 +330,11 @@ static int launch_llapfin2(const vkb_launch_t *l)
       P.g_ig[k]   = 1.0f / gam;
     }
   }
-  const dim3 grid(vkb_cdiv(out->wd, 64), vkb_cdiv(out->ht, 16)), block(32, 8);
+  dim3 grid(vkb_cdiv(out->wd, 64), vkb_cdiv(out->ht, 16)), block(32, 8);
+  const band_t bd = band_of(l, 2, 8, (out->ht + 1) / 2, &grid.y); // band image: the output, two rows per thread row
+  if(!grid.y) return VKB_OK;
 #define GO(F, G) k_llap_final4<F, G><<<grid, block, 0, l->stream>>>((const uint2 *)in->data, (const __half *)coarse->data, \
-      (const __half *)l1->data, l1->wd, l1->ht, out->data, out->wd, out->ht, P)
+      (const __half *)l1->data, l1->wd, l1->ht, out->data, out->wd, out->ht, P, bd)
   if(P.out_f32) { if(P.have_grade) GO(true, true); else GO(true, false); }
   else          { if(P.have_grade) GO(false, true); else GO(false, false); }
 #undef GO

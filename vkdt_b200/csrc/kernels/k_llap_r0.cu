@@ -48,10 +48,10 @@ VKB_DEV f2 avg2(f2 a, f2 b) { const f2 h = pk2(0.5f, 0.5f); return add2(mul2(a, 
 
 template <bool CLARITY>
 __global__ void __launch_bounds__(256, 5) k_llap_reduce0_p(const uint2 *__restrict__ in, int iw, int ih,
-    __half *__restrict__ out, int ow, int oh, const llap_params_t p)
+    __half *__restrict__ out, int ow, int oh, const llap_params_t p, const band_t bd)
 {
   __shared__ __align__(16) __half2 tile[NP][R0_TH][R0_TW + 1];
-  const int tx0 = blockIdx.x * 64 - 1, ty0 = blockIdx.y * 16 - 1;
+  const int tx0 = blockIdx.x * 64 - 1, ty0 = BAND_BY * 16 - 1;
   const int tid = threadIdx.y * 32 + threadIdx.x;
   const float inv2s = 1.0f / (2.0f * p.sigma), invd = 1.0f / (2.0f * p.sigma * p.sigma / 3.0f);
   const bool big = iw >= 66 && ih >= 18; // the tile overhangs the image by < one tile: the cheap mirror is enough
@@ -70,8 +70,8 @@ __global__ void __launch_bounds__(256, 5) k_llap_reduce0_p(const uint2 *__restri
     tile[NP - 1][ly][lx] = __floats2half2_rn(y, 0.0f);
   }
   __syncthreads();
-  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-  if(x >= ow || y >= oh) return;
+  const int x = blockIdx.x * 32 + threadIdx.x, y = BAND_BY * 8 + threadIdx.y;
+  if(x >= ow || y >= oh || BAND_SKIP(y)) return;
   const int lx = 2 * threadIdx.x, ly = 2 * threadIdx.y; // tile coords of texel (2x-1, 2y-1)
   const size_t plane = (size_t)ow * oh;
   __half *o = out + (size_t)y * ow + x;
@@ -103,11 +103,13 @@ int launch_llapr0_packed(const vkb_launch_t *l)
 {
   const vkb_image_t *in = l->conn, *out = l->conn + 1;
   const llap_params_t *lp = (const llap_params_t *)l->params;
-  const dim3 grid(vkb_cdiv(out->wd, 32), vkb_cdiv(out->ht, 8)), block(32, 8);
+  dim3 grid(vkb_cdiv(out->wd, 32), vkb_cdiv(out->ht, 8)), block(32, 8);
+  const band_t bd = band_of(l, 1, 8, out->ht, &grid.y);
+  if(!grid.y) return VKB_OK;
   if(lp->clarity == 0.0f)
-    k_llap_reduce0_p<false><<<grid, block, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, (__half *)out->data, out->wd, out->ht, *lp);
+    k_llap_reduce0_p<false><<<grid, block, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, (__half *)out->data, out->wd, out->ht, *lp, bd);
   else
-    k_llap_reduce0_p<true><<<grid, block, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, (__half *)out->data, out->wd, out->ht, *lp);
+    k_llap_reduce0_p<true><<<grid, block, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, (__half *)out->data, out->wd, out->ht, *lp, bd);
   VKB_CHECK_LAUNCH();
   return VKB_OK;
 }

@@ -254,12 +254,12 @@ VKB_DEV float weibull_cdf_ftz(float x, float il, float k)
 #define PW_NPX 4
 template <bool F32>
 __global__ void __launch_bounds__(256) k_pointwise_dflt(const uint2 *__restrict__ in, int iw, int ih,
-    void *__restrict__ outv, int ow, int oh, const __grid_constant__ pw_chain_t P)
+    void *__restrict__ outv, int ow, int oh, const __grid_constant__ pw_chain_t P, const band_t bd)
 {
   // PW_NPX pixels per thread, 32 apart: all loads are issued before the first dependent instruction, which keeps
   // enough bytes in flight per SM for HBM latency (one 8 byte load per thread does not: 2.7 TB/s)
-  const int y = blockIdx.y * 8 + threadIdx.y;
-  if(y >= oh) return;
+  const int y = BAND_BY * 8 + threadIdx.y;
+  if(y >= oh || BAND_SKIP(y)) return;
   uint2 raw[PW_NPX];
 #pragma unroll
   for(int q = 0; q < PW_NPX; q++)
@@ -380,12 +380,17 @@ static int launch_chain(const vkb_launch_t *l, int n_ops, const uint32_t *ops)
   }
   dim3 block(32, 8), grid(vkb_cdiv(out->wd, 64), vkb_cdiv(out->ht, 8)), grid1(vkb_cdiv(out->wd, 32), vkb_cdiv(out->ht, 8));
   const int sig = P.op[0] | (P.op[1] << 4) | (P.op[2] << 8) | (P.op[3] << 12) | (n_ops > 4 ? 1 << 20 : 0);
+  if(l->band_y0 >= 0 && !(sig == (PW_CROP | (PW_COLOUR << 4) | (PW_FILMCURV << 8)) && P.shift && P.colour.trc == 0 && !(P.colour.clip_t > 0.0f) &&
+     P.colour.N == 0 && P.colour.sat == 1.0f && P.film.colour == 3))
+    return vkb_set_error(VKB_ERR_BAD_ARG, "pointwise chain: only the default parameter kernel runs banded");
   if(sig == (PW_CROP | (PW_COLOUR << 4) | (PW_FILMCURV << 8)) && P.shift && P.colour.trc == 0 && !(P.colour.clip_t > 0.0f) &&
      P.colour.N == 0 && P.colour.sat == 1.0f && P.film.colour == 3)
   { // the default darkroom parameters: straight-line kernel
-    const dim3 gridn(vkb_cdiv(out->wd, 32 * PW_NPX), vkb_cdiv(out->ht, 8));
-    if(P.out_f32) k_pointwise_dflt<true><<<gridn, block, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, out->data, out->wd, out->ht, P);
-    else          k_pointwise_dflt<false><<<gridn, block, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, out->data, out->wd, out->ht, P);
+    dim3 gridn(vkb_cdiv(out->wd, 32 * PW_NPX), vkb_cdiv(out->ht, 8));
+    const band_t bd = band_of(l, 1, 8, out->ht, &gridn.y);
+    if(!gridn.y) return VKB_OK;
+    if(P.out_f32) k_pointwise_dflt<true><<<gridn, block, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, out->data, out->wd, out->ht, P, bd);
+    else          k_pointwise_dflt<false><<<gridn, block, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, out->data, out->wd, out->ht, P, bd);
     VKB_CHECK_LAUNCH();
     return VKB_OK;
   }

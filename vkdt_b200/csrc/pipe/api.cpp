@@ -9,6 +9,10 @@ uint64_t vkb_plan_pool_bytes(dt_graph_t *g);
 int dt_graph_plan(dt_graph_t *g, std::string *text);
 int dt_graph_run_modules(dt_graph_t *g, std::vector<int> &modid);
 void *vkb_plan_stream(dt_graph_t *g);
+int vkb_plan_band_stats(dt_graph_t *g, uint64_t *total, uint64_t *max_dev, int *pulls, int *launches);
+int vkb_plan_band_mark(dt_graph_t *g, int which);
+int vkb_plan_band_elapsed(dt_graph_t *g, float *ms);
+int dt_graph_band_plan(dt_graph_t *g, std::string *text);
 
 struct vkb_graph_t { dt_graph_t *g; };
 
@@ -191,6 +195,27 @@ int vkb_lj92_decode(const uint8_t *data, size_t size, uint16_t *out, size_t coun
   if(out && lj92_decode(data, size, out, count)) return vkb_set_error(VKB_ERR_IO, "lossless jpeg stream is corrupt or the output buffer too small");
   return VKB_OK;
 }
+int vkb_graph_set_bands(vkb_graph_t *h, int n, const int *devices)
+{
+  if(!h || n < 0 || n > 64 || (n > 0 && !devices)) return VKB_ERR_BAD_ARG;
+  h->g->band_devices.assign(devices, devices + n);
+  if(n == 1) { h->g->device = devices[0]; h->g->band_devices.clear(); }
+  return VKB_OK;
+}
+int vkb_graph_band_plan(vkb_graph_t *h, char *buf, size_t bufsize)
+{
+  if(!h || !buf || !bufsize) return VKB_ERR_BAD_ARG;
+  std::string s;
+  const int r = dt_graph_band_plan(h->g, &s);
+  if(r) return r;
+  if(s.size() + 1 > bufsize) return vkb_set_error(VKB_ERR_BAD_ARG, "buffer too small: %zu < %zu", bufsize, s.size() + 1);
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return VKB_OK;
+}
+int vkb_graph_band_stats(vkb_graph_t *h, uint64_t *bytes_total, uint64_t *bytes_max_device, int *pulls, int *launches)
+{ if(!h) return VKB_ERR_BAD_ARG; return vkb_plan_band_stats(h->g, bytes_total, bytes_max_device, pulls, launches) ? vkb_set_error(VKB_ERR_GRAPH, "no band split planned") : VKB_OK; }
+int vkb_graph_band_mark(vkb_graph_t *h, int which) { if(!h) return VKB_ERR_BAD_ARG; return vkb_plan_band_mark(h->g, which); }
+int vkb_graph_band_elapsed_ms(vkb_graph_t *h, float *ms) { if(!h || !ms) return VKB_ERR_BAD_ARG; return vkb_plan_band_elapsed(h->g, ms); }
 int vkb_graph_set_device(vkb_graph_t *h, int device) { if(!h) return VKB_ERR_BAD_ARG; h->g->device = device; return VKB_OK; }
 uint64_t vkb_graph_pool_bytes(vkb_graph_t *h) { return h ? vkb_plan_pool_bytes(h->g) : 0; }
 

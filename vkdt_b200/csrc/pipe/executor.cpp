@@ -8,9 +8,14 @@
 // per-launch cudaEvent timing reproduces `-d perf` (graph.c:881-933).
 #include "pipe.h"
 #include "mlv.h"
+#include "bands.h"
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <map>
+#include <mutex>
 #include <set>
+#include <thread>
 
 int dt_graph_run_modules(dt_graph_t *g, std::vector<int> &modid);
 void dt_graph_node_order(dt_graph_t *g, std::vector<int> &nodeid);
@@ -39,6 +44,36 @@ struct plan_graph_t { cudaGraphExec_t exec = 0; uint64_t hash = 0; int launches 
 struct plan_source_t { int modid; int nodeid; int buf_upload; size_t bytes; int packed_bpp; int external; };
 struct plan_sink_t   { int modid; int nodeid; int buf; size_t bytes; uint32_t wd, ht; int rgb; };
 
+// ---- band split: one frame over several GPUs (build_bands below) ----
+struct band_pull_t { int src; int buf; int r0, r1; };              // rows [r0, r1) of buffer `buf` copied from device slot `src`
+struct band_step_t                                                  // what one device does for one launch of the plan
+{
+  std::vector<std::pair<int,int>> compute;                          // row intervals of the launch's band image (empty: nothing)
+  std::vector<band_pull_t> pulls;                                   // halo rows fetched from peers before the launch
+  std::vector<int> waits;                                           // device slots whose previous step must have completed
+};
+struct band_copy_t { int buf; int r0, r1; };
+struct band_dev_t
+{
+  int device = 0;
+  void *pool = 0;
+  cudaStream_t stream = 0;
+  std::vector<cudaEvent_t> ev;                                      // one per launch
+  std::vector<band_step_t> step;
+  std::vector<band_copy_t> upload, download;                        // source rows this device needs / sink rows it owns
+  size_t pulled_bytes = 0;                                          // per frame, over NVLink (or device to device in tests)
+  std::thread worker;
+  int rc = 0; char err[256] = {0};
+};
+struct vkb_bands_t
+{
+  std::vector<band_dev_t> dev;
+  std::mutex mtx; std::condition_variable cv;
+  uint64_t frame = 0, go = 0; int pending = 0, quit = 0; uint32_t runflags = 0;
+  std::vector<std::atomic<uint64_t>> issued;                        // per device: frame * 65536 + launches recorded so far
+  cudaEvent_t t0 = 0, t1 = 0;
+};
+
 struct vkb_plan_t
 {
   std::vector<plan_buf_t> buf;
@@ -53,11 +88,14 @@ struct vkb_plan_t
   std::vector<cudaEvent_t> ev;
   std::vector<plan_graph_t> graphs = std::vector<plan_graph_t>(4); // small cache keyed by the fingerprint of the launch arguments
   unsigned graph_next = 0;
+  vkb_bands_t *bands = 0;
 };
 
+static void bands_free(vkb_bands_t *b);
 static void plan_free(vkb_plan_t *p)
 {
   if(!p) return;
+  if(p->bands) { bands_free(p->bands); p->bands = 0; }
   if(p->pool) cudaFree(p->pool);
   if(p->staging_up) cudaFreeHost(p->staging_up);
   if(p->staging_down) cudaFreeHost(p->staging_down);
@@ -530,6 +568,372 @@ static int build_plan(dt_graph_t *g, bool with_device)
   return VKB_OK;
 }
 
+
+// ================================================================================================================
+// band split (BASELINE.json config 5): ONE frame developed by several GPUs.
+//
+// every device gets the same plan and the same pool layout for the WHOLE image (7.6 GB of 180 at 201 MP), so a buffer has
+// the same offset everywhere and every kernel keeps the coordinates, sizes and mirror rules of the one GPU run.  a device
+// computes only its rows of every launch (vkb_launch_t::band_y0/y1); rows of an input it does not hold (the halo of a
+// stencil, a pyramid level's neighbours, the other half of denoise's quadrant swizzle) are copied from the device that
+// computed them, over NVLink with peer access, into the same offset of its own pool right before the launch.  pyramid
+// levels with fewer than 32 rows per device are computed whole on every device (the first such level all-gathers its
+// input through the same mechanism).  all of it is planned here on the host: which rows a device computes per launch
+// (band_rows), which rows of which connector a launch reads for them (band_describe), hence the pulls; the result is
+// bit for bit the one GPU frame.  execution: one host thread per device issuing its steps, devices ordered by events:
+// a device waits for the peers it pulls from (read after write) and for the peers that pulled from it in the step before
+// (its pool recycles memory: write after read).
+// ================================================================================================================
+enum { BA_NONE = 0, BA_READ, BA_READ_SWZ, BA_WRITE, BA_WRITE_SWZ };
+struct band_acc_t { int kind, num, den, lo, hi; };     // BA_READ: rows [floor(y0 num/den) + lo, ceil(y1 num/den) + hi); BA_READ_SWZ: lo = depth
+struct band_desc_t
+{
+  int band_conn = -1;      // connector whose rows are the launch's band coordinate
+  int unit = 1;            // band boundaries are multiples of this
+  int from_owned = -1;     // >= 0: compute the rows of this input connector that the device computed itself (swizzled levels)
+  int edge = 0;            // rows within `edge` of the image border read up to edge + 6 rows from it (splat.comp:27-30)
+  band_acc_t acc[DT_MAX_CONNECTORS];
+};
+
+static bool band_describe(const plan_launch_t &l, band_desc_t &D)
+{
+  auto is = [&](const char *n, const char *k) { return l.name == dt_token(n) && l.kernel == dt_token(k); };
+  for(auto &a : D.acc) a = band_acc_t{ BA_NONE, 1, 1, 0, 0 };
+  auto R = [&](int c, int num, int den, int lo, int hi) { D.acc[c] = band_acc_t{ BA_READ, num, den, lo, hi }; };
+  auto W = [&](int c) { D.acc[c] = band_acc_t{ BA_WRITE, 1, 1, 0, 0 }; };
+  if(is("denoise", "half"))
+  { // half.comp: block (x, y) reads mosaic rows crop.y + 2y, + 2y + 1
+    const int cy = l.push.size() >= 56 ? ((const int32_t *)l.push.data())[13] : 0;
+    D.band_conn = 1; R(0, 2, 1, cy, cy); W(1);
+  }
+  else if(is("denoise", "downcov")) { D.band_conn = 0; R(0, 1, 1, -2, 2); D.acc[1] = band_acc_t{ BA_WRITE_SWZ, 1, 1, 0, 0 }; W(2); }
+  else if(is("denoise", "down"))    { D.band_conn = 0; D.from_owned = 0; R(0, 1, 1, -2, 2); D.acc[1] = band_acc_t{ BA_WRITE_SWZ, 1, 1, 0, 0 }; }
+  else if(is("denoise", "assemble"))
+  { // assemble.comp:56-70: scale l is read at the l times swizzled position
+    D.band_conn = 5; R(0, 1, 1, 0, 0);
+    for(int k = 1; k <= 4; k++) D.acc[k] = band_acc_t{ BA_READ_SWZ, 1, 1, k, 0 };
+    W(5);
+  }
+  else if(is("denoise", "doub"))
+  { // band image: the output mosaic.  bayer kernel: block Y = y / 2 reads coarse rows Y - 1 .. Y + 1
+    const int cy = l.push.size() >= 56 ? ((const int32_t *)l.push.data())[13] : 0;
+    D.band_conn = 3; D.unit = 2; R(0, 1, 1, cy, cy); R(1, 1, 2, -1, 1); R(2, 1, 2, -1, 1); W(3);
+  }
+  else if(is("hilite", "half"))     { D.band_conn = 1; R(0, 2, 1, 0, 0); W(1); }
+  else if(is("hilite", "reduce"))   { D.band_conn = 1; R(0, 2, 1, -2, 1); W(1); }
+  else if(is("hilite", "assemble")) { D.band_conn = 2; R(0, 1, 1, 0, 0); R(1, 1, 2, -1, 1); W(2); }
+  else if(is("hilite", "doub"))     { D.band_conn = 2; D.unit = 2; R(0, 1, 1, 0, 0); R(1, 1, 2, 0, 1); W(2); }
+  else if(is("demosaic", "gauss"))  { D.band_conn = 2; R(1, 2, 1, -1, 1); W(2); }
+  else if(is("demosaic", "splat"))  { D.band_conn = 2; D.unit = 2; D.edge = 2; R(0, 1, 1, -2, 2); R(1, 1, 2, 0, 1); W(2); }
+  else if(is("demosaic", "fix"))    { D.band_conn = 3; D.unit = 2; R(0, 1, 1, -2, 2); R(1, 1, 1, -2, 2); R(2, 1, 2, 0, 1); W(3); }
+  else if(is("b200", "pointw"))
+  { // crop resolved to an integer shift (the launcher refuses anything else in a band): the shift is at most the size difference
+    D.band_conn = 1; R(0, 1, 1, 0, (int)l.conn[0].ht - (int)l.conn[1].ht); W(1);
+  }
+  else if(is("b200", "llapr0"))     { D.band_conn = 1; R(0, 2, 1, -1, 0); W(1); }
+  else if(is("llap", "reduce"))     { D.band_conn = 1; R(0, 2, 1, -1, 0); W(1); }
+  else if(is("llap", "assemble"))   { D.band_conn = 3; D.unit = 2; R(0, 1, 2, -2, 2); R(1, 1, 1, 0, 0); R(2, 1, 2, -2, 2); W(3); }
+  else if(is("b200", "llapfin"))    { D.band_conn = 3; D.unit = 2; R(0, 1, 1, 0, 0); R(1, 1, 2, -2, 2); R(2, 1, 2, -2, 2); W(3); }
+  else return false;
+  return true;
+}
+
+static void bands_free(vkb_bands_t *b)
+{
+  if(!b) return;
+  { std::lock_guard<std::mutex> lk(b->mtx); b->quit = 1; }
+  b->cv.notify_all();
+  for(band_dev_t &d : b->dev) if(d.worker.joinable()) d.worker.join();
+  for(band_dev_t &d : b->dev)
+  {
+    cudaSetDevice(d.device);
+    for(cudaEvent_t e : d.ev) cudaEventDestroy(e);
+    if(d.stream) cudaStreamDestroy(d.stream);
+    if(d.pool) cudaFree(d.pool);
+  }
+  delete b;
+}
+
+// rows of an image of height hb that device slot d of n computes: the cut positions are those of the full resolution image
+// (multiples of 64 rows of the source) scaled to the image's pyramid level, so that a device's bands nest across levels
+static std::pair<int,int> band_rows(int hb, int hfull, int d, int n, int unit)
+{
+  if(hb < 32 * n) return { 0, hb };                                  // too small to split: every device computes it whole
+  int k = 0;
+  while(k < 20 && ((hfull >> (k + 1)) >= hb || std::abs((hfull >> (k + 1)) - hb) < std::abs((hfull >> k) - hb))) k++;
+  auto cut = [&](int i) -> int {
+    if(i <= 0) return 0;
+    if(i >= n) return hb;
+    const int yfull = (int)(((int64_t)hfull * i / n) / 64) * 64;
+    int c = yfull >> k;
+    c -= c % unit;
+    return std::min(std::max(c, 0), hb);
+  };
+  return { cut(d), cut(d + 1) };
+}
+
+static void band_worker(dt_graph_t *g, int d);
+
+// host half: what every device computes, pulls and waits for, per launch.  needs no device (vkb_graph_band_plan)
+static int plan_bands(dt_graph_t *g, vkb_bands_t **out)
+{
+  vkb_plan_t *p = g->plan;
+  const int n = (int)g->band_devices.size();
+  const int nl = (int)p->launch.size();
+  if(p->source.empty()) return vkb_set_error(VKB_ERR_GRAPH, "band split: no source");
+  const int hfull = (int)g->node[p->source[0].nodeid].connector[0].roi.ht;
+  vkb_bands_t *B = new vkb_bands_t();
+  B->dev.resize(n);
+  B->issued = std::vector<std::atomic<uint64_t>>(n);
+  for(int d = 0; d < n; d++) { B->dev[d].device = g->band_devices[d]; B->dev[d].step.resize(nl); B->issued[d].store(0); }
+  // buffer heights (rows) and row strides, from the images the launches bind
+  const int nb = (int)p->buf.size();
+  std::vector<int> bh(nb, 0);
+  for(const plan_launch_t &l : p->launch) for(const plan_img_t &im : l.conn) if(im.buf >= 0) bh[im.buf] = (int)im.ht;
+  std::vector<uint8_t> is_src(nb, 0);
+  for(const plan_source_t &s : p->source) { is_src[s.buf_upload] = s.external ? 2 : 1; bh[s.buf_upload] = std::max(bh[s.buf_upload], 1); }
+  // valid[b][d]: rows of buffer b device d holds; own[b][d]: rows it computed itself
+  std::vector<std::vector<rows_t>> valid(nb, std::vector<rows_t>(n)), own(nb, std::vector<rows_t>(n));
+  for(int b = 0; b < nb; b++) if(is_src[b] == 2) for(int d = 0; d < n; d++) valid[b][d].add(0, 1 << 30); // caller's device memory, read over peer access
+  std::vector<std::vector<rows_t>> up(nb, std::vector<rows_t>(n));
+  std::vector<std::vector<std::vector<int>>> pulled_from(nl, std::vector<std::vector<int>>(n)); // [l][src] -> devices that pulled from src at launch l
+  for(int li = 0; li < nl; li++)
+  {
+    const plan_launch_t &l = p->launch[li];
+    band_desc_t D;
+    if(!band_describe(l, D)) { bands_free(B); return vkb_set_error(VKB_ERR_GRAPH, "band split: kernel %s_%s has no band description (label %s)",
+        dt_token_string(l.name).c_str(), dt_token_string(l.kernel).c_str(), l.label.c_str()); }
+    const int hb = (int)l.conn[D.band_conn].ht;
+    // rows every device computes
+    std::vector<rows_t> comp(n);
+    for(int d = 0; d < n; d++)
+    {
+      if(D.from_owned >= 0 && hb >= 32 * n) comp[d] = own[l.conn[D.from_owned].buf][d];
+      else { const auto r = band_rows(hb, hfull, d, n, D.unit); comp[d].add(r.first, r.second); }
+    }
+    // reads -> pulls (against the state before this launch)
+    for(int d = 0; d < n; d++)
+    {
+      band_step_t &st = B->dev[d].step[li];
+      st.compute = comp[d].v;
+      for(size_t c = 0; c < l.conn.size(); c++)
+      {
+        const band_acc_t &a = D.acc[c];
+        const int b = l.conn[c].buf;
+        if(b < 0 || (a.kind != BA_READ && a.kind != BA_READ_SWZ)) continue;
+        const int hc = (int)l.conn[c].ht;
+        rows_t need;
+        if(a.kind == BA_READ)
+        {
+          for(auto &iv : comp[d].v)
+          {
+            const int r0 = (int)(((int64_t)iv.first * a.num) / a.den) + a.lo, r1 = (int)(((int64_t)iv.second * a.num + a.den - 1) / a.den) + a.hi;
+            need.add(r0, r1);
+            if(D.edge && iv.first <= D.edge) need.add(0, D.edge + 7);
+            if(D.edge && iv.second >= hb - D.edge) need.add(hc - D.edge - 7, hc);
+          }
+        }
+        else { need = comp[d]; for(int k = 0; k < a.lo; k++) need = band_swz_rows(need, hc); }
+        need = need.clipped(0, hc);
+        rows_t missing = need.minus(valid[b][d]);
+        if(missing.empty()) continue;
+        if(is_src[b] == 1) { up[b][d].add(missing); valid[b][d].add(missing); continue; } // host source: uploaded straight from the caller's buffer
+        for(int e = 0; e < n && !missing.empty(); e++)
+        {
+          if(e == d) continue;
+          const rows_t take = missing.intersect(own[b][e]);   // from the device that computed them (always complete one step earlier)
+          for(auto &iv : take.v)
+          {
+            st.pulls.push_back(band_pull_t{ e, b, iv.first, iv.second });
+            const plan_img_t &im = l.conn[c];
+            B->dev[d].pulled_bytes += (size_t)(iv.second - iv.first) * im.wd * im.chan * im.layers * (im.format == dt_token("f32") ? 4 : 2);
+          }
+          if(!take.empty())
+          {
+            if(std::find(st.waits.begin(), st.waits.end(), e) == st.waits.end()) st.waits.push_back(e);
+            if(std::find(pulled_from[li][e].begin(), pulled_from[li][e].end(), d) == pulled_from[li][e].end()) pulled_from[li][e].push_back(d);
+            missing = missing.minus(take);
+            valid[b][d].add(take);
+          }
+        }
+        if(!missing.empty())
+        {
+          bands_free(B);
+          return vkb_set_error(VKB_ERR_GRAPH, "band split: launch %d (%s) on device slot %d needs rows [%d, %d) of connector %zu that no device computed",
+              li, l.label.c_str(), d, missing.v[0].first, missing.v[0].second, c);
+        }
+      }
+      // write after read: whoever pulled from this device in the step before must be done before this device moves on
+      if(li > 0) for(int e : pulled_from[li - 1][d]) if(std::find(st.waits.begin(), st.waits.end(), e) == st.waits.end()) st.waits.push_back(e);
+    }
+    // writes
+    for(int d = 0; d < n; d++) for(size_t c = 0; c < l.conn.size(); c++)
+    {
+      const band_acc_t &a = D.acc[c];
+      const int b = l.conn[c].buf;
+      if(b < 0 || (a.kind != BA_WRITE && a.kind != BA_WRITE_SWZ)) continue;
+      const int hc = (int)l.conn[c].ht;
+      const rows_t w = (a.kind == BA_WRITE ? comp[d] : band_swz_rows(comp[d], hc)).clipped(0, hc);
+      valid[b][d].add(w); own[b][d].add(w);
+    }
+  }
+  for(int d = 0; d < n; d++)
+  {
+    for(const plan_source_t &s : p->source) if(!s.external) for(auto &iv : up[s.buf_upload][d].v) B->dev[d].upload.push_back(band_copy_t{ s.buf_upload, iv.first, iv.second });
+    for(const plan_sink_t &s : p->sink) if(s.buf >= 0) for(auto &iv : own[s.buf][d].v) B->dev[d].download.push_back(band_copy_t{ s.buf, iv.first, iv.second });
+  }
+  *out = B;
+  return VKB_OK;
+}
+
+static int build_bands(dt_graph_t *g)
+{
+  vkb_plan_t *p = g->plan;
+  vkb_bands_t *B = 0;
+  const int r = plan_bands(g, &B);
+  if(r) return r;
+  const int n = (int)B->dev.size(), nl = (int)p->launch.size();
+  // device side: pools, streams, events, peer access, workers
+  for(int d = 0; d < n; d++)
+  {
+    band_dev_t &bd = B->dev[d];
+    cudaError_t e = cudaSetDevice(bd.device);
+    if(e == cudaSuccess) e = cudaMalloc(&bd.pool, p->pool_bytes);
+    if(e != cudaSuccess) { const char *msg = cudaGetErrorString(e); bands_free(B); return vkb_set_error(VKB_ERR_OOM, "band split: pool of %zu bytes on device %d: %s", p->pool_bytes, bd.device, msg); }
+    cudaStreamCreateWithFlags(&bd.stream, cudaStreamNonBlocking);
+    bd.ev.resize(nl);
+    for(cudaEvent_t &ev : bd.ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    for(int o = 0; o < n; o++) if(B->dev[o].device != bd.device)
+    {
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, bd.device, B->dev[o].device);
+      if(!can) { bands_free(B); return vkb_set_error(VKB_ERR_CUDA, "band split: device %d cannot access device %d (no NVLink / PCIe peer path)", bd.device, B->dev[o].device); }
+      const cudaError_t pe = cudaDeviceEnablePeerAccess(B->dev[o].device, 0);
+      if(pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) { bands_free(B); return vkb_set_error(VKB_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(pe)); }
+      cudaGetLastError();
+    }
+  }
+  cudaSetDevice(B->dev[0].device);
+  cudaEventCreate(&B->t0); cudaEventCreate(&B->t1);
+  p->bands = B;
+  for(int d = 0; d < n; d++) B->dev[d].worker = std::thread(band_worker, g, d);
+  return VKB_OK;
+}
+
+static size_t band_row_bytes(const vkb_plan_t *p, int buf, uint32_t *layers, size_t *plane)
+{ // geometry of a buffer as its launches see it
+  for(const plan_launch_t &l : p->launch) for(const plan_img_t &im : l.conn) if(im.buf == buf)
+  {
+    const size_t rb = (size_t)im.wd * im.chan * (im.format == dt_token("f32") ? 4 : 2);
+    *layers = im.layers; *plane = rb * im.ht;
+    return rb;
+  }
+  *layers = 1; *plane = 0;
+  return 0;
+}
+
+static void band_worker(dt_graph_t *g, int d)
+{
+  vkb_plan_t *p = g->plan;
+  vkb_bands_t *B = p->bands;
+  band_dev_t &me = B->dev[d];
+  const int n = (int)B->dev.size(), nl = (int)p->launch.size();
+  uint64_t seen = 0;
+  cudaSetDevice(me.device);
+  for(;;)
+  {
+    uint32_t run; uint64_t frame;
+    {
+      std::unique_lock<std::mutex> lk(B->mtx);
+      B->cv.wait(lk, [&] { return B->quit || B->go > seen; });
+      if(B->quit) return;
+      seen = B->go; run = B->runflags; frame = B->frame;
+    }
+    me.rc = 0;
+    // the previous frame's last pulls out of this pool must have landed before the pool is written again
+    if(frame > 1) for(int e = 0; e < n; e++) if(e != d) cudaStreamWaitEvent(me.stream, B->dev[e].ev[nl - 1], 0);
+    if(run & VKB_RUN_UPLOAD_SOURCE) for(const plan_source_t &s : p->source) if(!s.external)
+    {
+      const vkb_mem_source_t *ms = s.modid < (int)g->mem_source.size() && g->mem_source[s.modid].valid ? &g->mem_source[s.modid] : 0;
+      if(!ms || s.packed_bpp) { me.rc = VKB_ERR_GRAPH; snprintf(me.err, sizeof(me.err), "band split: the source has to be a u16 mosaic in memory"); break; }
+      const size_t rb = (size_t)ms->p.width * 2;
+      for(const band_copy_t &c : me.upload) if(c.buf == s.buf_upload)
+        cudaMemcpyAsync((uint8_t *)me.pool + p->buf[c.buf].offset + rb * c.r0, (const uint8_t *)ms->data + rb * c.r0, rb * (c.r1 - c.r0), cudaMemcpyHostToDevice, me.stream);
+    }
+    if(run & VKB_RUN_RECORD_CMD_BUF) for(int li = 0; li < nl && !me.rc; li++)
+    {
+      const plan_launch_t &l = p->launch[li];
+      const band_step_t &st = me.step[li];
+      for(int e : st.waits)
+      { // the peer's record of its step li - 1 has to be issued before the wait on it is
+        const uint64_t want = frame * 65536 + (uint64_t)li;
+        while(B->issued[e].load(std::memory_order_acquire) < want) std::this_thread::yield();
+        cudaStreamWaitEvent(me.stream, B->dev[e].ev[li - 1], 0);
+      }
+      for(const band_pull_t &q : st.pulls)
+      {
+        uint32_t layers; size_t plane;
+        const size_t rb = band_row_bytes(p, q.buf, &layers, &plane);
+        const size_t off = p->buf[q.buf].offset + rb * q.r0, bytes = rb * (q.r1 - q.r0);
+        if(layers <= 1) cudaMemcpyAsync((uint8_t *)me.pool + off, (const uint8_t *)B->dev[q.src].pool + off, bytes, cudaMemcpyDefault, me.stream);
+        else cudaMemcpy2DAsync((uint8_t *)me.pool + off, plane, (const uint8_t *)B->dev[q.src].pool + off, plane, bytes, layers, cudaMemcpyDefault, me.stream);
+      }
+      std::vector<vkb_image_t> conn;
+      for(const plan_img_t &im : l.conn)
+      {
+        void *ptr = 0;
+        if(im.buf >= 0) ptr = p->buf[im.buf].external ? p->buf[im.buf].external : (void *)((uint8_t *)me.pool + p->buf[im.buf].offset);
+        conn.push_back(vkb_image_t{ ptr, im.wd, im.ht, im.chan, im.layers, im.format });
+      }
+      for(const auto &iv : st.compute)
+      {
+        const vkb_launch_t kl = { l.wd, l.ht, l.dp, l.push.data(), (uint32_t)l.push.size(), l.arg_params.data(), (uint32_t)l.arg_params.size(),
+            conn.data(), (uint32_t)conn.size(), me.stream, iv.first, iv.second };
+        const int rr = vkb_dispatch_launch(l.name, l.kernel, g->mode, &kl);
+        if(rr) { me.rc = rr; snprintf(me.err, sizeof(me.err), "%s", vkb_last_error()); break; }
+      }
+      cudaEventRecord(me.ev[li], me.stream);
+      B->issued[d].store(frame * 65536 + (uint64_t)li + 1, std::memory_order_release);
+    }
+    if(me.rc) B->issued[d].store(frame * 65536 + 65535, std::memory_order_release); // do not leave peers spinning
+    if(!me.rc && (run & VKB_RUN_DOWNLOAD_SINK)) for(const plan_sink_t &s : p->sink)
+    {
+      const vkb_mem_sink_t *ms = s.modid < (int)g->mem_sink.size() && g->mem_sink[s.modid].valid ? &g->mem_sink[s.modid] : 0;
+      if(!ms || !ms->dst) continue;
+      const size_t rb = s.bytes / s.ht;
+      for(const band_copy_t &c : me.download) if(c.buf == s.buf)
+        cudaMemcpyAsync((uint8_t *)ms->dst + rb * c.r0, (const uint8_t *)me.pool + p->buf[c.buf].offset + rb * c.r0, rb * (c.r1 - c.r0), cudaMemcpyDeviceToHost, me.stream);
+    }
+    if(!me.rc && (run & VKB_RUN_WAIT_DONE))
+    {
+      const cudaError_t e = cudaStreamSynchronize(me.stream);
+      if(e != cudaSuccess) { me.rc = VKB_ERR_CUDA; snprintf(me.err, sizeof(me.err), "band split: device %d: %s", me.device, cudaGetErrorString(e)); }
+    }
+    {
+      std::lock_guard<std::mutex> lk(B->mtx);
+      B->pending--;
+    }
+    B->cv.notify_all();
+  }
+}
+
+static int run_bands(dt_graph_t *g, uint32_t run)
+{
+  vkb_plan_t *p = g->plan;
+  vkb_bands_t *B = p->bands;
+  {
+    std::unique_lock<std::mutex> lk(B->mtx);
+    B->frame++; B->go++; B->runflags = run; B->pending = (int)B->dev.size();
+  }
+  B->cv.notify_all();
+  {
+    std::unique_lock<std::mutex> lk(B->mtx);
+    B->cv.wait(lk, [&] { return B->pending == 0; });
+  }
+  for(band_dev_t &d : B->dev) if(d.rc) return vkb_set_error(d.rc, "%s", d.err);
+  return VKB_OK;
+}
+
 static void *buf_ptr(const vkb_plan_t *p, int b)
 {
   if(b < 0) return 0;
@@ -544,13 +948,34 @@ int dt_graph_run(dt_graph_t *g, uint32_t run)
   // per-launch timing is a property of the graph (vkb_graph_set_perf, the reference's -d perf log mask) or an explicit flag
   // outside the reference's bits; s_graph_run_all (-1u, every bit set) never implies it
   const bool perf = g->perf || (run != (uint32_t)VKB_RUN_ALL && (run & VKB_RUN_PERF));
-  if((run & (VKB_RUN_ROI | VKB_RUN_CREATE_NODES | VKB_RUN_ALLOC)) || !g->plan || !g->plan->pool)
+  const bool banded = g->band_devices.size() > 1;   // one frame over several GPUs (vkb_graph_set_bands)
+  if((run & (VKB_RUN_ROI | VKB_RUN_CREATE_NODES | VKB_RUN_ALLOC)) || !g->plan || (banded ? !g->plan->bands : !g->plan->pool))
   {
-    r = build_plan(g, true);
+    r = build_plan(g, !banded);
     if(r) return r;
+    if(banded) { r = build_bands(g); if(r) { plan_free(g->plan); g->plan = 0; return r; } }
     run |= VKB_RUN_UPLOAD_SOURCE | VKB_RUN_RECORD_CMD_BUF;
   }
   vkb_plan_t *p = g->plan;
+  if(banded)
+  { // parameters are committed here, everything that touches a device happens in the per device workers
+    if(run & VKB_RUN_RECORD_CMD_BUF)
+    {
+      for(int m : p->modid) if(g->module[m].so->commit_params) g->module[m].so->commit_params(g, &g->module[m]);
+      for(plan_launch_t &l : p->launch)
+      {
+        l.arg_params.clear();
+        for(int m : l.param_mods)
+        {
+          const dt_module_t *mod = &g->module[m];
+          const uint8_t *src = mod->committed_param_size ? mod->committed_param : mod->param;
+          const int sz = mod->committed_param_size ? mod->committed_param_size : mod->param_size;
+          l.arg_params.insert(l.arg_params.end(), src, src + sz);
+        }
+      }
+    }
+    return run_bands(g, run);
+  }
   cudaSetDevice(g->device);
   // sources with s_module_request_read_source re-upload every run (graph-run-modules.h:573-587)
   for(const plan_source_t &s : p->source)
@@ -736,6 +1161,37 @@ int dt_graph_plan(dt_graph_t *g, std::string *text)
   return VKB_OK;
 }
 
+// host only: the band split as text, one line per launch and device slot (rows computed, rows pulled and from whom)
+int dt_graph_band_plan(dt_graph_t *g, std::string *text)
+{
+  if(g->band_devices.size() < 2) return vkb_set_error(VKB_ERR_BAD_ARG, "no band split set (vkb_graph_set_bands)");
+  int r = build_plan(g, false);
+  if(r) return r;
+  vkb_bands_t *B = 0;
+  r = plan_bands(g, &B);
+  if(r) return r;
+  char b[256];
+  const vkb_plan_t *p = g->plan;
+  for(size_t li = 0; li < p->launch.size(); li++) for(size_t d = 0; d < B->dev.size(); d++)
+  {
+    const band_step_t &st = B->dev[d].step[li];
+    snprintf(b, sizeof(b), "launch %2zu dev %zu %s_%s rows", li, d, dt_token_string(p->launch[li].name).c_str(), dt_token_string(p->launch[li].kernel).c_str());
+    *text += b;
+    for(auto &iv : st.compute) { snprintf(b, sizeof(b), " [%d,%d)", iv.first, iv.second); *text += b; }
+    for(auto &q : st.pulls) { snprintf(b, sizeof(b), " pull b%d[%d,%d)<-%d", q.buf, q.r0, q.r1, q.src); *text += b; }
+    for(int e : st.waits) { snprintf(b, sizeof(b), " wait %d", e); *text += b; }
+    *text += "\n";
+  }
+  for(size_t d = 0; d < B->dev.size(); d++)
+  {
+    for(auto &c : B->dev[d].upload)   { snprintf(b, sizeof(b), "upload dev %zu b%d[%d,%d)\n", d, c.buf, c.r0, c.r1); *text += b; }
+    for(auto &c : B->dev[d].download) { snprintf(b, sizeof(b), "download dev %zu b%d[%d,%d)\n", d, c.buf, c.r0, c.r1); *text += b; }
+    snprintf(b, sizeof(b), "dev %zu pulls %zu bytes per frame\n", d, B->dev[d].pulled_bytes); *text += b;
+  }
+  bands_free(B);
+  return VKB_OK;
+}
+
 // accessors used by the C-ABI
 int vkb_plan_sink(dt_graph_t *g, int modid, uint32_t *wd, uint32_t *ht, void **dptr)
 {
@@ -743,11 +1199,60 @@ int vkb_plan_sink(dt_graph_t *g, int modid, uint32_t *wd, uint32_t *ht, void **d
   for(const plan_sink_t &s : g->plan->sink) if(s.modid == modid)
   {
     if(wd) *wd = s.wd; if(ht) *ht = s.ht;
-    if(dptr) *dptr = buf_ptr(g->plan, s.buf);
+    if(dptr) *dptr = g->plan->bands ? (void *)((uint8_t *)g->plan->bands->dev[0].pool + g->plan->buf[s.buf].offset) : buf_ptr(g->plan, s.buf);
     return VKB_OK;
   }
   return VKB_ERR_BAD_ARG;
 }
 uint64_t vkb_plan_pool_bytes(dt_graph_t *g) { return g->plan ? g->plan->pool_bytes : 0; }
 int vkb_plan_launches(dt_graph_t *g) { return g->plan ? (int)g->plan->launch.size() : 0; }
-void *vkb_plan_stream(dt_graph_t *g) { return g->plan ? (void *)g->plan->stream : 0; }
+void *vkb_plan_stream(dt_graph_t *g) { return g->plan ? (g->plan->bands ? (void *)g->plan->bands->dev[0].stream : (void *)g->plan->stream) : 0; }
+// band split statistics: bytes pulled from peers per frame (sum over devices, and the largest single device)
+int vkb_plan_band_stats(dt_graph_t *g, uint64_t *total, uint64_t *max_dev, int *pulls, int *launches)
+{
+  if(!g->plan || !g->plan->bands) return VKB_ERR_GRAPH;
+  uint64_t t = 0, m = 0; int np = 0, nk = 0;
+  for(const band_dev_t &d : g->plan->bands->dev)
+  {
+    t += d.pulled_bytes; m = std::max<uint64_t>(m, d.pulled_bytes);
+    for(const band_step_t &st : d.step) { np += (int)st.pulls.size(); nk += (int)st.compute.size(); }
+  }
+  if(total) *total = t; if(max_dev) *max_dev = m; if(pulls) *pulls = np; if(launches) *launches = nk;
+  return VKB_OK;
+}
+// device side time of a span of banded frames: mark(0) / mark(1) record an event on every device's stream, elapsed() is the
+// largest per device span (all devices start together after a synchronising run)
+int vkb_plan_band_mark(dt_graph_t *g, int which)
+{
+  if(!g->plan || !g->plan->bands) return VKB_ERR_GRAPH;
+  vkb_bands_t *B = g->plan->bands;
+  static thread_local std::vector<cudaEvent_t> dummy;
+  for(band_dev_t &d : B->dev)
+  {
+    cudaSetDevice(d.device);
+    if(d.ev.size() < (size_t)g->plan->launch.size() + 2)
+    { // two timing events behind the per launch ones
+      cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+      d.ev.push_back(a); d.ev.push_back(b);
+    }
+    cudaEventRecord(d.ev[g->plan->launch.size() + (which ? 1 : 0)], d.stream);
+  }
+  return VKB_OK;
+}
+int vkb_plan_band_elapsed(dt_graph_t *g, float *ms)
+{
+  if(!g->plan || !g->plan->bands) return VKB_ERR_GRAPH;
+  float mx = 0.0f;
+  const size_t nl = g->plan->launch.size();
+  for(band_dev_t &d : g->plan->bands->dev)
+  {
+    if(d.ev.size() < nl + 2) return VKB_ERR_GRAPH;
+    cudaSetDevice(d.device);
+    cudaEventSynchronize(d.ev[nl + 1]);
+    float t = 0.0f;
+    if(cudaEventElapsedTime(&t, d.ev[nl], d.ev[nl + 1]) != cudaSuccess) return VKB_ERR_CUDA;
+    mx = std::max(mx, t);
+  }
+  *ms = mx;
+  return VKB_OK;
+}

@@ -199,6 +199,7 @@ struct dt_graph_t
   std::vector<vkb_mem_sink_t>   mem_sink;
   std::string perf_text;
   int      device;
+  std::vector<int> band_devices;             // > 1 entries: band split over these CUDA devices (vkb_graph_set_bands)
   int      mode;                             // VKB_MODE_STRICT | VKB_MODE_FAST (vkb_graph_set_mode)
   int      perf;                             // time every launch (vkb_graph_set_perf)
 };
