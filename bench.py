@@ -10,8 +10,13 @@ its own stills (weak scaling, no data-path collective; torch.distributed is used
   e2e        same metric through the reference-facing C-ABI graph call with HOST buffers: pinned H2D of the u16 mosaic and
              D2H of the rgb f32 sink image (the PFM payload) inside the timed region
   roofline   dominant kernel: unique bytes in+out of the launch / its average CUDA-event duration vs measured HBM copy peak
-  cpu_baseline / --impl reference: the CPU restatement of the reference's algorithm (oracle, OpenMP, all host cores) on a
-             bounded crop of the same workload.  the reference's own Vulkan pipeline cannot be built here.
+  cpu_baseline / --impl reference: the CPU restatement of the reference's algorithm (oracle, OpenMP, all host cores) on the
+             same full frame.  the reference's own Vulkan pipeline cannot be built or run here (no loader, ICD, glslang:
+             profiles/r02_vulkan_probe.txt, DESIGN.md).
+  fast       the kernel path again with the fast build of the kernels (SFU exp / pow, fused multiply-adds: round 1's
+             arithmetic).  the headline runs the strict build, which is bit compatible with the restatement.
+  bands      (N > 1, or --workload still201 --gpus N) BASELINE.json config 5: ONE 201 MP still split into bands over the N GPUs
+             of the box with halo exchange over NVLink peer access, driven by rank 0 (strong scaling of one frame).
 """
 import argparse
 import json
@@ -114,13 +119,21 @@ def oracle_cfg(O, w, h, strength):
     return d
 
 
-def cpu_reference_rate(sample_wh, steps, warmup, strength):
-    """times the oracle (CPU port of the reference's algorithm, OpenMP over all host cores) on a bounded crop."""
+def workload_name(name, W, H, mp, strength):
+    """one string for both arms (the driver compares config.workload of the two lines)."""
+    return "%s: %dx%d %s 14-bit still (%.1f MP), default darkroom graph incl. hilite + llap + grade, denoise strength %.2f" % (
+        name, W, H, "x-trans" if name == "xtrans26" else "bayer rggb", mp, strength)
+
+
+def cpu_reference_rate(sample_wh, steps, warmup, strength, xtrans=False):
+    """times the oracle (CPU port of the reference's algorithm, OpenMP over all host cores) on one frame of that size."""
     from oracle import oracle_py as O
     from vkdt_b200 import synth
     w, h = sample_wh
-    raw = synth.mosaic(w, h, seed=0x5EED0000)
+    raw = synth.mosaic(w, h, seed=0x5EED0000, xtrans=xtrans)
     d = oracle_cfg(O, w, h, strength)
+    if xtrans:
+        d.filters = 9
     ow, oh = O.darkroom_out_size(d)
     threads = O.set_threads(len(os.sched_getaffinity(0)))   # all host cores this process may use, whatever OMP_NUM_THREADS says
     for _ in range(warmup):
@@ -150,8 +163,10 @@ def ncu_traffic(label, key="bytes_per_launch"):
     return None
 
 
-def run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, src, bpp, strength, steps, warmup, sample_clocks=True):
-    """both legs (kernel path with HBM-resident input, end to end with host buffers) of one workload on this rank."""
+def run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, src, bpp, strength, steps, warmup, sample_clocks=True,
+                 mode=0, e2e=True):
+    """both legs (kernel path with HBM-resident input, end to end with host buffers) of one workload on this rank.
+    mode: api.MODE_STRICT (the headline) or api.MODE_FAST; e2e=False: kernel leg only."""
     # ---- synthetic input: a few distinct stills per rank, cycled (deterministic seeds per SURVEY §8d) ----
     xtrans = args.workload == "xtrans26" and src == "i-raw"
     big = W * H > 100e6
@@ -188,6 +203,7 @@ def run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, s
         if strength > 0:
             g.line("param:denoise:01:strength:%g" % strength)
         g.set_sink_layout(api.SINK_RGB_F32)   # the PFM payload (r g b f32, 12 B/px) is what o-pfm puts into the file
+        g.set_mode(mode)
         return g
 
     # ---- leg 1: kernel path, input resident in HBM, sink left in HBM ----
@@ -231,6 +247,14 @@ def run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, s
         t_kernel_ms = float(t.item())
     clocks = sampler.stop() if sample_clocks else None
     pool_bytes = g.pool_bytes()
+    if not e2e:
+        for hp in host_in:
+            api.host_free(hp)
+        for dp in dev_in:
+            api.dev_free(dp)
+        g.close()
+        return dict(t_kernel_ms=t_kernel_ms, launches=launches, per_kernel=per_kernel, clocks=clocks, in_bytes=in_bytes, out_bytes=out_bytes,
+                    ow=ow, oh=oh, pool_bytes=pool_bytes, nstills=nstills)
 
     # ---- leg 2: end to end through the C-ABI with host buffers ----
     # two graph instances (each with its own pool, stream and pinned sink) ping-pong: while one frame's 722 MB result
@@ -285,6 +309,95 @@ def run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, s
                 in_bytes=in_bytes, out_bytes=out_bytes, ow=ow, oh=oh, pool_bytes=pool_bytes, checksum=checksum, nstills=nstills)
 
 
+
+def run_bands(api, synth, devices, W, H, strength, steps, warmup, with_single=True):
+    """BASELINE.json config 5: ONE still split into horizontal bands over `devices` (vkb_graph_set_bands), halo rows pulled
+    between the devices' pools over NVLink peer access.  kernel leg: every device holds its source rows in its pool (uploaded
+    once), the sink stays in HBM; end to end: every device uploads its source rows from and downloads its sink rows into one
+    pinned host frame, inside the timed region.  times are device side: the slowest device's span (vkb_graph_band_elapsed_ms)."""
+    n = len(devices)
+    if W * H > 100e6:   # a 4x4 tiling of a 12.6 MP synthetic still: same statistics, generated in seconds
+        raw = np.ascontiguousarray(np.tile(synth.mosaic(W // 4, H // 4, seed=0x5EED0000, wb=WB), (4, 4)))
+    else:
+        raw = synth.mosaic(W, H, seed=0x5EED0000, wb=WB)
+    rp = api.raw_params(W, H, wb=WB, cam_to_rec2020=CAM, noise_a=100.0, noise_b=2.0)
+    host_in = api.host_alloc(raw.nbytes + 64)
+    api.C.memmove(host_in, raw.ctypes.data, raw.nbytes)
+
+    def graph(devs):
+        g = api.Graph(cfg_text=api.DARKROOM_CFG.format(src="i-raw"))
+        g.line("param:denoise:01:strength:%g" % strength)
+        g.set_sink_layout(api.SINK_RGB_F32)
+        if len(devs) > 1:
+            g.set_bands(devs)
+        else:
+            g.set_device(devs[0])
+        g.set_source(host_in, rp)
+        g.set_sink_buffer(None, 0)
+        g.run()
+        return g
+
+    g = graph(devices)
+    ow, oh = g.sink_size()
+    out_bytes = ow * oh * 12
+    FR = api.RUN_RECORD
+    for _ in range(max(1, warmup)):
+        g.run(FR)
+    g.run(api.RUN_WAIT)
+    api.lib.vkb_launch_count_reset()
+    g.band_mark(0)
+    for _ in range(steps):
+        g.run(FR)
+    g.band_mark(1)
+    t_kernel = g.band_elapsed_ms()
+    launches = api.launch_count()
+    stats = g.band_stats()
+    pool = g.pool_bytes()
+    # end to end: host frame in, host frame out
+    host_out = api.host_alloc(out_bytes)
+    g.set_sink_buffer(host_out, out_bytes)
+    FE = api.RUN_RECORD | api.RUN_UPLOAD | api.RUN_DOWNLOAD | api.RUN_WAIT
+    g.run(FE)
+    e2e_steps = max(3, min(steps, 8))
+    t0 = time.time()
+    for _ in range(e2e_steps):
+        g.run(FE)
+    t_e2e = (time.time() - t0) * 1e3
+    checksum = float(np.frombuffer((api.C.c_float * 4).from_address(host_out), dtype=np.float32).sum())
+    g.close()
+    single = None
+    if with_single:   # the same frame on ONE GPU, for the strong scaling efficiency
+        g1 = graph(devices[:1])
+        e0, e1 = api.Event(), api.Event()
+        for _ in range(max(1, warmup)):
+            g1.run(FR)
+        g1.run(api.RUN_WAIT)
+        st = g1.stream()
+        e0.record(st)
+        k1 = max(2, min(steps, 5))
+        for _ in range(k1):
+            g1.run(FR)
+        e1.record(st)
+        e1.sync()
+        single = e0.elapsed_ms(e1) / k1
+        g1.close()
+    api.host_free(host_in)
+    api.host_free(host_out)
+    mp = W * H / 1e6
+    out = {"workload": "still%d: ONE %dx%d bayer still (%.0f MP) split into %d horizontal bands, one per GPU, default darkroom graph incl. denoise 0.40 + hilite + llap + grade; "
+                       "halo rows pulled over NVLink peer access, result bit identical to the one GPU frame (tests/test_bands_gpu.py)" % (round(mp), W, H, mp, n),
+           "n_gpus": n, "scaling": "strong", "value": round(steps * mp / (t_kernel * 1e-3), 1), "unit": "MP/s", "ms_per_frame": round(t_kernel / steps, 3), "steps": steps,
+           "e2e": {"value": round(e2e_steps * mp / (t_e2e * 1e-3), 1), "unit": "MP/s", "ms_per_frame": round(t_e2e / e2e_steps, 3), "steps": e2e_steps,
+                   "h2d_bytes_per_step": int(raw.nbytes), "d2h_bytes_per_step": int(out_bytes), "timing": "wall clock around synchronous frames", "checksum": checksum},
+           "nvlink_bytes_per_frame": stats["bytes_total"], "nvlink_bytes_busiest_gpu": stats["bytes_max_device"], "peer_copies_per_frame": stats["pulls"],
+           "kernel_launches_per_frame": stats["launches"], "gpu_launches": int(launches), "pool_bytes_per_gpu": pool}
+    if single:
+        out["one_gpu_ms_per_frame"] = round(single, 3)
+        out["speedup_vs_one_gpu"] = round(single / (t_kernel / steps), 3)
+        out["efficiency"] = round(single / (t_kernel / steps) / n, 3)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -295,6 +408,9 @@ def main():
     ap.add_argument("--denoise", type=float, default=None, help="denoise:strength (default: 0.4 once the wavelet kernels are built, else 0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mlv", action="store_true", help="skip the extra MLV 4K frames/s measurement")
+    ap.add_argument("--no-bands", action="store_true", help="N > 1: skip the 201 MP band split leg")
+    ap.add_argument("--mode", default="strict", choices=["strict", "fast"],
+                    help="strict (default): kernels bit compatible with the CPU restatement; fast: SFU transcendentals + fma")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -303,19 +419,21 @@ def main():
     mp = W * H / 1e6
 
     if args.impl == "reference":
-        # the reference's own CPU-side implementation of the path = the oracle port (vkdt-cli needs vulkan + glslang: absent)
+        # the reference's own CPU-side implementation of the path = the oracle port (vkdt-cli needs vulkan + glslang: absent,
+        # profiles/r02_vulkan_probe.txt).  the FULL frame of the workload, bounded in the number of passes (one pass is ~15 s)
         if rank != 0:
             return 0
         strength = args.denoise if args.denoise is not None else 0.4
-        sample = (2376, 1584)  # 1/16 of the 61 MP frame, same graph
-        rate, dt, cores = cpu_reference_rate(sample, max(1, min(args.steps, 5)), max(1, min(args.warmup, 1)), strength)
+        steps_run, warm_run = max(1, min(args.steps, 2)), max(0, min(args.warmup, 1))
+        rate, dt, cores = cpu_reference_rate((W, H), steps_run, warm_run, strength, xtrans=args.workload == "xtrans26")
         print(json.dumps({
             "impl": "reference", "metric": "MP/s raw->display graph", "value": round(rate, 3), "unit": "MP/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+            "steps": steps_run, "warmup": warm_run, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s %dx%d bayer 14-bit, default darkroom graph, denoise strength %.2f" % (args.workload, W, H, strength)},
+            "config": {"workload": workload_name(args.workload, W, H, mp, strength)},
             "cpu_baseline": {"value": round(rate, 3), "unit": "MP/s", "cores": cores, "kind": "port",
-                             "sample": "%dx%d crop of the workload, %d timed passes of the CPU oracle (OpenMP)" % (sample[0], sample[1], max(1, min(args.steps, 5)))},
+                             "sample": "the full %dx%d frame, %d timed pass(es) of the CPU oracle (OpenMP, %d threads) after %d warm-up; requested steps %d / warmup %d are bounded to keep the run within minutes" % (
+                                 W, H, steps_run, cores, warm_run, args.steps, args.warmup)},
             "e2e": {"value": round(rate, 3), "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
 
@@ -347,12 +465,50 @@ def main():
     have_wavelet = ("denoise", "doub") in api.kernels()
     strength = args.denoise if args.denoise is not None else (0.4 if have_wavelet else 0.0)
 
+    mode = api.MODE_FAST if args.mode == "fast" else api.MODE_STRICT
+    gloo = dist.new_group(backend="gloo") if world > 1 else None
+    band_devices = list(range(world if world > 1 else args.gpus))
+    if os.environ.get("VKB_BENCH_BAND_DEVICES"):   # e.g. "0,0": bands sharing one GPU, to exercise the leg on a one GPU box
+        band_devices = [int(x) for x in os.environ["VKB_BENCH_BAND_DEVICES"].split(",")]
+    if args.workload == "still201" and len(band_devices) > 1:
+        # the band split IS the workload: rank 0 drives all the GPUs of the box, the other ranks stand by
+        if rank == 0:
+            api.set_mode(mode)
+            Bd = run_bands(api, synth, band_devices, W, H, strength, args.steps, args.warmup)
+            line = {"metric": "MP/s raw->display graph", "value": Bd["value"], "unit": "MP/s", "n_gpus": len(band_devices), "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": Bd["ms_per_frame"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                    "dtype": "f32", "data": "synthetic", "config": {"workload": Bd["workload"], "mode": args.mode,
+                    "timing": "pool of %.1f GB per GPU, far beyond the 126 MB L2" % (Bd["pool_bytes_per_gpu"] / 1e9)},
+                    "e2e": Bd["e2e"], "gpu_launches": Bd["gpu_launches"], "bands": Bd}
+            print(json.dumps(line))
+        if world > 1:
+            dist.barrier(group=gloo)
+            dist.destroy_process_group()
+        return 0
+
     mlv_W, mlv_H, mlv_src, mlv_bpp = WORKLOADS["mlv4k"]
-    R = run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, src, bpp, strength, args.steps, args.warmup)
+    R = run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, src, bpp, strength, args.steps, args.warmup, mode=mode)
+    # the other build of the kernels, kernel path only, for the record
+    other = api.MODE_STRICT if mode == api.MODE_FAST else api.MODE_FAST
+    F = run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, src, bpp, strength, max(4, min(args.steps, 10)), 3,
+                     sample_clocks=False, mode=other, e2e=False)
     M = None
     if args.workload != "mlv4k" and not args.no_mlv:
         M = run_workload(api, synth, torch, dist, args, rank, world, local_rank, mlv_W, mlv_H, mlv_src, mlv_bpp, strength,
-                         max(40, min(10 * args.steps, 200)), 3, sample_clocks=False)
+                         max(40, min(10 * args.steps, 200)), 3, sample_clocks=False, mode=mode)
+    Bd = None
+    if world > 1 and not args.no_bands:
+        # config 5 rides along in the scaling runs: one 201 MP still over all the GPUs of the box, driven by rank 0
+        torch.cuda.empty_cache()
+        dist.barrier(group=gloo)
+        if rank == 0:
+            try:
+                api.set_mode(mode)
+                bw, bh, _, _ = WORKLOADS["still201"]
+                Bd = run_bands(api, synth, band_devices, bw, bh, strength, max(5, min(args.steps, 10)), 3)
+            except Exception as e:   # report, do not lose the headline line
+                Bd = {"error": str(e)}
+        dist.barrier(group=gloo)
     t_kernel_ms, t_e2e_ms, e2e_steps, launches, per_kernel, clocks = R["t_kernel_ms"], R["t_e2e_ms"], R["e2e_steps"], R["launches"], R["per_kernel"], R["clocks"]
     in_bytes, out_bytes, ow, oh, checksum, nstills = R["in_bytes"], R["out_bytes"], R["ow"], R["oh"], R["checksum"], R["nstills"]
     if rank != 0:
@@ -382,16 +538,23 @@ def main():
         "metric": "MP/s raw->display graph", "value": round(world * args.steps * mp / (t_kernel_ms * 1e-3), 2), "unit": "MP/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t_kernel_ms / args.steps, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: %dx%d %s 14-bit still (%.1f MP), default darkroom graph incl. hilite + llap + grade, "
-                               "denoise strength %.2f, sink rgb f32 %dx%d (PFM payload, 12 B/px)" % (
-                                   args.workload, W, H, "x-trans" if args.workload == "xtrans26" else "bayer rggb", mp, strength, ow, oh),
+        "config": {"workload": workload_name(args.workload, W, H, mp, strength), "sink": "rgb f32 %dx%d (PFM payload, 12 B/px)" % (ow, oh),
+                   "mode": args.mode + (": kernels bit compatible with the CPU restatement (libm-exact transcendentals, no fma), output identical to the oracle at full size"
+                                        if args.mode == "strict" else ": SFU transcendentals + fma (round 1's arithmetic)"),
                    "timing": "inputs and intermediates (%.0f MB pool) exceed the 126 MB L2; %d distinct stills cycled" % (R["pool_bytes"] / 1e6, nstills),
-                   "parallelism": "independent stills per GPU, no collective", "edges": "f16 at every reference edge (strict)"},
+                   "parallelism": "independent stills per GPU, no collective"},
         "e2e": {"value": round(world * e2e_steps * mp / (t_e2e_ms * 1e-3), 2), "unit": "MP/s", "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": out_bytes, "ms_per_step": round(t_e2e_ms / e2e_steps, 3), "steps": e2e_steps, "checksum": checksum},
         "gpu_launches": int(launches) * world, "launches_per_step": int(launches // max(1, args.steps)),  # every rank launches the same sequence
         "clocks": clocks, "roofline": roof, "pool_bytes": R["pool_bytes"],
     }
+    other_name = "strict" if args.mode == "fast" else "fast"
+    fsteps = max(4, min(args.steps, 10))
+    line[other_name] = {"what": "the same kernel path with the %s build of the kernels" % other_name,
+                        "value": round(world * fsteps * mp / (F["t_kernel_ms"] * 1e-3), 2), "unit": "MP/s", "ms_per_step": round(F["t_kernel_ms"] / fsteps, 4),
+                        "kernels": {k: round(v[0] / v[1], 4) for k, v in sorted(F["per_kernel"].items(), key=lambda kv: -kv[1][0])[:8]}}
+    if Bd:
+        line["bands"] = Bd
     if M:
         msteps = max(40, min(10 * args.steps, 200))
         line["mlv4k"] = {"workload": "MLV 4096x2160 14-bit packed frames, default darkroom graph, frame f -> rank f mod N",
@@ -400,11 +563,13 @@ def main():
                          "h2d_bytes_per_frame": M["in_bytes"], "d2h_bytes_per_frame": M["out_bytes"], "n_gpus": world}
     line["config"]["host_placement"] = numa
     if not args.no_cpu_baseline:
-        sample = (2376, 1584)
         os.sched_setaffinity(0, full_affinity)
-        rate, dt, cores = cpu_reference_rate(sample, 3, 1, strength)
+        big = W * H > 100e6
+        sample = (W // 4, H // 4) if big else (W, H)
+        rate, dt, cores = cpu_reference_rate(sample, 1, 0, strength, xtrans=args.workload == "xtrans26")
         line["cpu_baseline"] = {"value": round(rate, 3), "unit": "MP/s", "cores": cores, "kind": "port",
-                                "sample": "%dx%d crop of the workload, 3 timed passes of the CPU oracle (OpenMP), %.2f s each" % (sample[0], sample[1], dt)}
+                                "sample": "%s %dx%d frame of the workload, 1 pass of the CPU oracle (OpenMP, %d threads), %.1f s" % (
+                                    "a quarter size" if big else "the full", sample[0], sample[1], cores, dt)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
