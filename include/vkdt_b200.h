@@ -127,7 +127,11 @@ VKB_API vkb_graph_t *vkb_graph_new(void);                                   /* d
 VKB_API void vkb_graph_free(vkb_graph_t *g);                                /* dt_graph_cleanup */
 VKB_API int  vkb_graph_read_config_ascii(vkb_graph_t *g, const char *filename); /* graph-io.c:282 */
 VKB_API int  vkb_graph_read_config_line(vkb_graph_t *g, const char *line);  /* graph-io.c:232: module: connect: param: frames: fps: */
-VKB_API int  vkb_graph_replace_display(vkb_graph_t *g, const char *sink_module); /* graph-export.c:23-96, e.g. "o-pfm" */
+VKB_API int  vkb_graph_replace_display(vkb_graph_t *g, const char *sink_module); /* graph-export.c:23-96, e.g. "o-pfm"; bt2020 / linear */
+/* the same with the export colour space (cli --colour-prim / --colour-trc: the values of dt_colour_primaries_t / dt_colour_trc_t,
+ * src/pipe/module.h:23-62: prim 1 sRGB/rec709, 2 bt2020, 3 AdobeRGB, 4 P3, 5 XYZ; trc 0 linear, 1 rec709, 2 sRGB, 3 PQ, 4 DCI, 5 HLG,
+ * 6 gamma 2.2).  a colenc module is put in front of the sink when the sink is 8 bit or prim / trc are not bt2020 / linear */
+VKB_API int  vkb_graph_replace_display_ex(vkb_graph_t *g, const char *inst, const char *sink_module, int prim, int trc);
 /* feed a source module from memory instead of a file (what read_source() would have written into the mapped
  * staging buffer): an already decoded u16 mosaic + the dt_image_params_t fields the source module would fill
  * (src/pipe/module.h:72-109).  the pointer must stay valid until the run that uploads it finished. */
@@ -165,6 +169,9 @@ VKB_API int  vkb_graph_state(vkb_graph_t *g, char *buf, size_t bufsize);
  * liblj92 (i-mlv/video_mlv.c:236-250): headers into width/height/bits/components, and, when `out` is not NULL,
  * width*height*components samples in scan order into out[0..count).  host only, bit exact. */
 VKB_API int  vkb_lj92_decode(const uint8_t *data, size_t size, uint16_t *out, size_t count, int *width, int *height, int *bits, int *components);
+/* the baseline jpeg writer behind the o-jpg sink (replaces libjpeg's use in o-jpg/main.c:102-172): rgba 8 bit in, 4:4:4 ycbcr,
+ * annex K tables scaled by `quality` (libjpeg's scale).  host only */
+VKB_API int  vkb_jpeg_write(const char *filename, const uint8_t *rgba, int width, int height, float quality);
 /* redirect a sink (o-pfm:main ...) into caller memory instead of a file: rgba f32, wd*ht*16 bytes */
 VKB_API int  vkb_graph_set_sink_buffer(vkb_graph_t *g, const char *inst, void *dst, size_t bytes);
 /* layout of a sink's pixels, on the device and in the caller's buffer.  VKB_SINK_RGBA_F32 (default for memory sinks) is
@@ -174,9 +181,17 @@ VKB_API int  vkb_graph_set_sink_buffer(vkb_graph_t *g, const char *inst, void *d
  * takes effect at the next vkb_graph_run with VKB_RUN_ALL. */
 #define VKB_SINK_RGBA_F32 0
 #define VKB_SINK_RGB_F32  1
+/* 8 bit sinks (the sink module's input is rgba:ui8 like o-jpg's, i.e. the graph ends in colenc, src/pipe/graph-export.c:66-86):
+ * VKB_SINK_RGBA_UI8 is the image the reference maps for write_sink (4 B/px, alpha 255); VKB_SINK_RGB_UI8 packs r g b (3 B/px,
+ * what o-jpg hands to the encoder, o-jpg/main.c:161-165): a quarter of the f32 payload's device->host bytes */
+#define VKB_SINK_RGBA_UI8 2
+#define VKB_SINK_RGB_UI8  3
 VKB_API int  vkb_graph_set_sink_layout(vkb_graph_t *g, const char *inst, int layout);
 VKB_API int  vkb_graph_sink_size(vkb_graph_t *g, const char *inst, uint32_t *wd, uint32_t *ht);
 VKB_API int  vkb_graph_set_frame(vkb_graph_t *g, uint32_t frame);
+/* graph->frame_cnt: set by a `frames:` config line or by a source that knows its length (i-mlv's modify_roi_out, i.e. after the
+ * first run), what dt_graph_export loops over (src/pipe/graph-export.c:251-268) */
+VKB_API int  vkb_graph_frame_count(vkb_graph_t *g);
 VKB_API int  vkb_graph_run(vkb_graph_t *g, int runflags);                   /* dt_graph_run, src/pipe/graph.c:719 */
 /* -d perf equivalent (graph.c:881-933): per-kernel milliseconds of the last run; returns number of entries */
 VKB_API int  vkb_graph_perf(vkb_graph_t *g, char *buf, size_t bufsize);

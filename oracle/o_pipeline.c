@@ -190,7 +190,7 @@ int o_darkroom_run(const o_darkroom_t *d, const uint16_t *raw, float *out, int s
   if(stage == 5) { copy_out(&col, stage_out); o_img_free(&col); return 0; }
 
   /* the last module before the sink stores f32 (graph-export.c:89-91) */
-  const int film_last = !d->enable_llap && !d->enable_grade;
+  const int film_last = !d->enable_llap && !d->enable_grade && !d->enable_colenc;
   oimg_t flm = o_img_alloc(ow, oh, 4);
   o_filmcurv_main(&col, &flm, &d->filmcurv, !film_last);
   o_img_free(&col);
@@ -200,7 +200,7 @@ int o_darkroom_run(const o_darkroom_t *d, const uint16_t *raw, float *out, int s
   if(d->enable_llap)
   {
     oimg_t ll = o_img_alloc(ow, oh, 4);
-    o_llap_module(&cur, &ll, &d->llap, d->enable_grade ? 1 : 0);
+    o_llap_module(&cur, &ll, &d->llap, (d->enable_grade || d->enable_colenc) ? 1 : 0);
     o_img_free(&cur);
     cur = ll;
     if(stage == 7) { copy_out(&cur, stage_out); o_img_free(&cur); return 0; }
@@ -208,9 +208,16 @@ int o_darkroom_run(const o_darkroom_t *d, const uint16_t *raw, float *out, int s
   if(d->enable_grade)
   {
     oimg_t gr = o_img_alloc(ow, oh, 4);
-    o_grade_main(&cur, &gr, &d->grade, 0);
+    o_grade_main(&cur, &gr, &d->grade, d->enable_colenc ? 1 : 0);
     o_img_free(&cur);
     cur = gr;
+  }
+  if(d->enable_colenc)
+  { /* graph-export.c:66-86: colenc's output takes the sink's format */
+    oimg_t ce = o_img_alloc(ow, oh, 4);
+    o_colenc_main(&cur, &ce, d->colenc_prim, d->colenc_trc, d->sink_unorm8 ? 2 : 0);
+    o_img_free(&cur);
+    cur = ce;
   }
   if(out) copy_out(&cur, out);
   o_img_free(&cur);

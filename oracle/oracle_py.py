@@ -64,7 +64,8 @@ class Darkroom(C.Structure):
                 ("denoise", DenoiseParams), ("hilite", HiliteParams), ("demosaic", DemosaicParams),
                 ("crop", CropParams), ("colour", ColourParams), ("filmcurv", FilmcurvParams),
                 ("llap", LlapParams), ("grade", GradeParams),
-                ("enable_llap", C.c_int), ("enable_grade", C.c_int)]
+                ("enable_llap", C.c_int), ("enable_grade", C.c_int),
+                ("enable_colenc", C.c_int), ("colenc_prim", C.c_int), ("colenc_trc", C.c_int), ("sink_unorm8", C.c_int)]
 
 
 _lib = None

@@ -111,9 +111,15 @@ typedef struct o_darkroom_t
   o_llap_params_t llap;
   o_grade_params_t grade;
   int enable_llap, enable_grade; /* graph variants without these modules */
+  /* export side (graph-export.c:66-86): colenc behind the last module (prim / trc of colenc/params), sink image format */
+  int enable_colenc, colenc_prim, colenc_trc;
+  int sink_unorm8;               /* 1: the sink image is rgba ui8 (o-jpg): values 0..255 returned as floats */
 } o_darkroom_t;
 
 void o_darkroom_defaults(o_darkroom_t *d, uint32_t width, uint32_t height);
+void o_colenc_px(float *rgb, int prim, int trc);
+float o_unorm8(float v);
+void o_colenc_main(const oimg_t *in, oimg_t *out, int prim, int trc, int fmt);
 /* output dimensions of the sink for this configuration */
 void o_darkroom_out_size(const o_darkroom_t *d, uint32_t *out_w, uint32_t *out_h);
 /* raw: width*height u16.  out: out_w*out_h*4 floats (rgba f32, what o-pfm receives).

@@ -233,8 +233,58 @@ def test_cli_dump_nodes_without_a_gpu(tmp_path):
     cfg.write_text(api.DARKROOM_CFG.format(src="i-raw") + "param:i-raw:main:filename:img.dng\n")
     r = subprocess.run([cli, "-g", str(cfg), "--dump-nodes"], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0, r.stderr
-    assert r.stdout.lstrip().startswith("digraph") and "hilite_reduce" in r.stdout and "llap_curve" in r.stdout and "o-pfm_main" in r.stdout
+    # the reference's default export: o-jpg behind a colenc (cli/main.c:58-59, graph-export.c:66-86)
+    assert r.stdout.lstrip().startswith("digraph") and "hilite_reduce" in r.stdout and "llap_curve" in r.stdout and "o-jpg_main" in r.stdout and "colenc_main" in r.stdout
+    r = subprocess.run([cli, "-g", str(cfg), "--dump-nodes", "--format", "o-pfm", "--colour-prim", "bt2020", "--colour-trc", "linear"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "o-pfm_main" in r.stdout and "colenc" not in r.stdout
     r = subprocess.run([cli, "-g", str(tmp_path / "missing.cfg"), "--dump-nodes"], capture_output=True, text=True, timeout=60)
     assert r.returncode != 0
     r = subprocess.run([cli, "--bogus"], capture_output=True, text=True, timeout=60)
     assert r.returncode != 0 and "usage" in r.stderr
+
+
+def test_jpeg_writer_round_trip(tmp_path):
+    """the baseline jpeg writer behind o-jpg (host only): a decoder reads it back close to what went in, at about the size
+    and fidelity of libjpeg at the same quality."""
+    import ctypes as C
+    import io
+    import numpy as np
+    from PIL import Image
+    from vkdt_b200 import api
+    w, h = 333, 201                                   # not a multiple of 8: edge blocks
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = np.zeros((h, w, 4), np.uint8)
+    img[..., 0] = xx * 255 // w; img[..., 1] = yy * 255 // h
+    img[..., 2] = ((np.sin(xx / 7.0) * np.cos(yy / 5.0) * 0.5 + 0.5) * 255).astype(np.uint8); img[..., 3] = 255
+    img[50:90, 100:180, :3] = [250, 10, 30]
+    fn = str(tmp_path / "t.jpg")
+    for q in (95, 60):
+        api.check(api.lib.vkb_jpeg_write(fn.encode(), img.ctypes.data_as(C.c_void_p), w, h, float(q)))
+        dec = np.asarray(Image.open(fn).convert("RGB")).astype(float)
+        ref = io.BytesIO()
+        Image.fromarray(img[..., :3]).save(ref, "JPEG", quality=q, subsampling=0)
+        pil = np.asarray(Image.open(io.BytesIO(ref.getvalue())).convert("RGB")).astype(float)
+        ps = lambda a: 10 * np.log10(255.0 ** 2 / ((a - img[..., :3]) ** 2).mean())
+        assert dec.shape == (h, w, 3) and ps(dec) > ps(pil) - 0.5 and os.path.getsize(fn) < 1.1 * len(ref.getvalue())
+
+
+def test_export_inserts_colenc_like_the_reference():
+    """graph-export.c:66-86: an 8 bit sink (o-jpg) or a colour space other than linear bt2020 puts colenc in front of the sink;
+    the launch plan fuses it behind the pointwise chain when there is no llap, else runs it as the last launch."""
+    import numpy as np
+    from vkdt_b200 import api
+    raw = np.zeros((384, 512), dtype=np.uint16)
+    for sink, prim, trc, want in (("o-jpg", 1, 1, True), ("o-pfm", 2, 0, False), ("o-pfm", 4, 2, True)):
+        g = api.Graph(cfg_text=api.DARKROOM_CFG.format(src="i-raw"), sink=sink, prim=prim, trc=trc)
+        g.set_source(raw.ctypes.data, api.raw_params(512, 384))
+        plan = g.plan()
+        assert ("colenc" in plan) == want, (sink, prim, trc, plan)
+        if sink == "o-jpg":
+            assert "ui8" in plan
+        g.close()
+    cfg = api.DARKROOM_CFG.format(src="i-raw").replace("connect:filmcurv:01:output:llap:01:input\n", "").replace(
+        "connect:llap:01:output:grade:01:input\n", "connect:filmcurv:01:output:grade:01:input\n")
+    g = api.Graph(cfg_text=cfg, sink="o-jpg", prim=1, trc=1)
+    g.set_source(raw.ctypes.data, api.raw_params(512, 384))
+    assert "crop+colour+filmcurv+grade+colenc" in g.plan()
+    g.close()

@@ -119,7 +119,7 @@ def test_imlv_file_source_and_cli(gpu, oracle, tmp_path):
     cfg.write_text(gpu.DARKROOM_CFG.format(src="i-mlv") + "param:i-mlv:main:filename:clip.mlv\n")
     cli = os.path.join(os.path.dirname(gpu.LIB_PATH), "vkdt-b200-cli")
     out = str(tmp_path / "dev")
-    r = subprocess.run([cli, "-g", str(cfg), "--format", "o-pfm", "--filename", out, "-d", "perf", "--config", "frames:2"],
+    r = subprocess.run([cli, "-g", str(cfg), "--format", "o-pfm", "--colour-prim", "bt2020", "--colour-trc", "linear", "--filename", out, "-d", "perf", "--config", "frames:2"],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     assert "[perf] total time" in r.stdout and "b200_rawnoop" in r.stdout

@@ -44,7 +44,7 @@ vkb_event_sync vkb_event_elapsed_ms vkb_event_destroy vkb_dispatch vkb_kernel_co
 vkb_kernel_name vkb_launch_count vkb_launch_count_reset vkb_graph_new vkb_graph_free vkb_graph_read_config_ascii
 vkb_graph_read_config_line vkb_graph_replace_display vkb_graph_set_source vkb_graph_set_sink_buffer
 vkb_graph_sink_size vkb_graph_set_frame vkb_graph_run vkb_graph_plan vkb_graph_perf vkb_graph_dump_nodes
-vkb_graph_set_source_device vkb_graph_sink_device vkb_graph_pool_bytes vkb_graph_stream vkb_graph_set_device vkb_dng_info vkb_graph_set_sink_layout vkb_lj92_decode vkb_graph_committed_params vkb_graph_describe vkb_graph_state vkb_graph_set_perf vkb_set_mode vkb_get_mode vkb_graph_set_mode vkb_graph_set_bands vkb_graph_band_plan vkb_graph_band_stats vkb_graph_band_mark vkb_graph_band_elapsed_ms""".split()
+vkb_graph_set_source_device vkb_graph_sink_device vkb_graph_pool_bytes vkb_graph_stream vkb_graph_set_device vkb_dng_info vkb_graph_set_sink_layout vkb_lj92_decode vkb_graph_committed_params vkb_graph_describe vkb_graph_state vkb_graph_set_perf vkb_set_mode vkb_get_mode vkb_graph_set_mode vkb_graph_set_bands vkb_graph_band_plan vkb_graph_band_stats vkb_graph_band_mark vkb_graph_band_elapsed_ms vkb_graph_replace_display_ex vkb_jpeg_write vkb_graph_frame_count""".split()
 
 
 def token(s):
@@ -103,7 +103,9 @@ def get_mode():
 
 # ---- graph layer -------------------------------------------------------------------------------------------
 RUN_ALL = -1
-SINK_RGBA_F32, SINK_RGB_F32 = 0, 1
+SINK_RGBA_F32, SINK_RGB_F32, SINK_RGBA_UI8, SINK_RGB_UI8 = 0, 1, 2, 3
+PRIM = {"custom": 0, "srgb": 1, "bt2020": 2, "adobergb": 3, "p3": 4, "xyz": 5}      # cli/main.c:14-23
+TRC = {"linear": 0, "709": 1, "srgb": 2, "pq": 3, "dci": 4, "hlg": 5, "gamma2.2": 6}  # cli/main.c:25-35
 RUN_ROI, RUN_CREATE_NODES, RUN_ALLOC, RUN_RECORD, RUN_UPLOAD, RUN_DOWNLOAD, RUN_WAIT, RUN_PERF = 1, 2, 4, 8, 16, 32, 64, 1 << 16
 
 lib.vkb_graph_new.restype = C.c_void_p
@@ -111,12 +113,15 @@ lib.vkb_graph_free.argtypes = [C.c_void_p]
 lib.vkb_graph_read_config_ascii.argtypes = [C.c_void_p, C.c_char_p]
 lib.vkb_graph_read_config_line.argtypes = [C.c_void_p, C.c_char_p]
 lib.vkb_graph_replace_display.argtypes = [C.c_void_p, C.c_char_p]
+lib.vkb_graph_replace_display_ex.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int]
+lib.vkb_jpeg_write.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_float]
 lib.vkb_graph_set_source.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(RawParams)]
 lib.vkb_graph_set_source_device.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(RawParams)]
 lib.vkb_graph_set_sink_buffer.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]
 lib.vkb_graph_sink_size.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
 lib.vkb_graph_sink_device.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
 lib.vkb_graph_set_frame.argtypes = [C.c_void_p, C.c_uint32]
+lib.vkb_graph_frame_count.argtypes = [C.c_void_p]
 lib.vkb_graph_run.argtypes = [C.c_void_p, C.c_int]
 lib.vkb_graph_plan.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
 lib.vkb_graph_perf.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
@@ -229,7 +234,7 @@ param:llap:01:clarity:0.2
 class Graph:
     """dt_graph_t behind the C-ABI: read cfg lines, feed a source from memory, run, fetch the sink."""
 
-    def __init__(self, cfg_text=None, cfg_file=None, sink="o-pfm"):
+    def __init__(self, cfg_text=None, cfg_file=None, sink="o-pfm", prim=None, trc=None):
         self.h = C.c_void_p(lib.vkb_graph_new())
         self._keep = []
         if cfg_file:
@@ -239,7 +244,9 @@ class Graph:
                 r = lib.vkb_graph_read_config_line(self.h, line.encode())
                 if r < 0:
                     raise VkbError(r, "config line failed: " + line)
-        if sink:
+        if sink and (prim is not None or trc is not None):
+            check(lib.vkb_graph_replace_display_ex(self.h, b"main", sink.encode(), 2 if prim is None else prim, 0 if trc is None else trc))
+        elif sink:
             check(lib.vkb_graph_replace_display(self.h, sink.encode()))
 
     def line(self, text):

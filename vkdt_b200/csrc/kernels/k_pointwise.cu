@@ -10,14 +10,15 @@
 #include <math.h>
 #include "pointwise.cuh"
 
-enum { PW_CROP = 1, PW_COLOUR = 2, PW_FILMCURV = 3, PW_GRADE = 4 };
+enum { PW_CROP = 1, PW_COLOUR = 2, PW_FILMCURV = 3, PW_GRADE = 4, PW_COLENC = 5 };
 
 struct pw_chain_t
 {
   int n_ops;
   int op[8];
   int shift, sx, sy;   // crop resolved to an integer translation on the host (the default 3 px micro-crop)
-  int out_f32;
+  int out_f32;         // 0 rgba f16, 1 rgba f32, 2 packed rgb f32 (PFM payload), 3 rgba ui8 (o-jpg's sink image), 4 packed rgb ui8
+  colenc_params_t colenc;
   crop_committed_t crop;
   filmcurv_params_t film;
   grade_params_t grade;
@@ -25,6 +26,13 @@ struct pw_chain_t
 };
 
 VKB_DEV f3 round3(f3 c) { return { f16r(c.x), f16r(c.y), f16r(c.z) }; }
+// 8 bit sinks: rgba ui8 as one 32 bit word per pixel (alpha 255), or packed rgb bytes
+VKB_DEV void st_sink_ui8(void *__restrict__ outv, int ow, int x, int y, f3 c, int mode)
+{
+  const uint32_t r = unorm8(c.x), g = unorm8(c.y), b = unorm8(c.z);
+  if(mode == 3) reinterpret_cast<uint32_t *>(outv)[(size_t)y * ow + x] = r | (g << 8) | (b << 16) | 0xff000000u;
+  else { uint8_t *o = reinterpret_cast<uint8_t *>(outv) + ((size_t)y * ow + x) * 3; o[0] = (uint8_t)r; o[1] = (uint8_t)g; o[2] = (uint8_t)b; }
+}
 
 // compile-time specialisations of the common chains: the op sequence is a template parameter pack, so the loop
 // below unrolls into straight-line code (the generic runtime-switch kernel needed 104 registers).
@@ -51,9 +59,11 @@ __global__ void __launch_bounds__(256) k_pointwise_t(const uint2 *__restrict__ i
     if(ops[o] == PW_COLOUR)        c = colour_px(c, P.colour);
     else if(ops[o] == PW_FILMCURV) c = filmcurv_px(c, P.film);
     else if(ops[o] == PW_GRADE)    c = grade_px(c, P.grade);
+    else if(ops[o] == PW_COLENC)   c = colenc_px(c, P.colenc);
     if(o < n - 1) c = round3(c);
   }
-  if(F32 && P.out_f32 == 2)
+  if(F32 && P.out_f32 >= 3) st_sink_ui8(outv, ow, x, y, c, P.out_f32);
+  else if(F32 && P.out_f32 == 2)
   { // packed rgb sink: the lanes with x < ow are still here, contiguous from lane 0
     __shared__ __align__(16) float stage[8][100];
     const int x0 = blockIdx.x * 32, nl = min(32, ow - x0);
@@ -86,9 +96,11 @@ __global__ void __launch_bounds__(256) k_pointwise(const uint2 *__restrict__ in,
       if(P.op[o] == PW_COLOUR)        c = colour_px(c, P.colour);
       else if(P.op[o] == PW_FILMCURV) c = filmcurv_px(c, P.film);
       else if(P.op[o] == PW_GRADE)    c = grade_px(c, P.grade);
+      else if(P.op[o] == PW_COLENC)   c = colenc_px(c, P.colenc);
       if(o < P.n_ops - 1) c = round3(c);
     }
-    if(P.out_f32) st_sink_f32(outv, ow, x, y, c.x, c.y, c.z, P.out_f32);
+    if(P.out_f32 >= 3) st_sink_ui8(outv, ow, x, y, c, P.out_f32);
+    else if(P.out_f32) st_sink_f32(outv, ow, x, y, c.x, c.y, c.z, P.out_f32);
     else st_rgba(reinterpret_cast<uint2 *>(outv), ow, x, y, make_float4(c.x, c.y, c.z, 1.0f));
   }
 }
@@ -318,12 +330,12 @@ static int launch_chain(const vkb_launch_t *l, int n_ops, const uint32_t *ops)
   VKB_REQUIRE(l->num_conn >= 2 && n_ops >= 1 && n_ops <= 8);
   const vkb_image_t *in = l->conn, *out = l->conn + 1;
   VKB_REQUIRE(in->chan == 4 && in->format == VKB_TOKEN_F16);
-  VKB_REQUIRE(out->format == VKB_TOKEN_F16 || out->format == VKB_TOKEN_F32);
-  VKB_REQUIRE(out->chan == 4 || (out->chan == 3 && out->format == VKB_TOKEN_F32)); // 3: packed rgb f32 sink (VKB_SINK_RGB_F32)
+  VKB_REQUIRE(out->format == VKB_TOKEN_F16 || out->format == VKB_TOKEN_F32 || out->format == VKB_TOKEN_UI8);
+  VKB_REQUIRE(out->chan == 4 || (out->chan == 3 && out->format != VKB_TOKEN_F16)); // 3: packed rgb sinks (VKB_SINK_RGB_F32 / VKB_SINK_RGB_UI8)
   pw_chain_t P;
   memset(&P, 0, sizeof(P));
   P.n_ops = n_ops;
-  P.out_f32 = out->format == VKB_TOKEN_F32 ? (out->chan == 3 ? 2 : 1) : 0;
+  P.out_f32 = out->format == VKB_TOKEN_F32 ? (out->chan == 3 ? 2 : 1) : (out->format == VKB_TOKEN_UI8 ? (out->chan == 3 ? 4 : 3) : 0);
   const uint8_t *pp = (const uint8_t *)l->params;
   uint32_t left = l->params_size;
   for(int o = 0; o < n_ops; o++)
@@ -350,6 +362,9 @@ static int launch_chain(const vkb_launch_t *l, int n_ops, const uint32_t *ops)
       case PW_GRADE:
         need = sizeof(grade_params_t); VKB_REQUIRE(left >= need);
         memcpy(&P.grade, pp, need); break;
+      case PW_COLENC:
+        need = sizeof(colenc_params_t); VKB_REQUIRE(left >= need);
+        memcpy(&P.colenc, pp, need); break;
       default: return vkb_set_error(VKB_ERR_BAD_ARG, "pointwise chain: unknown op %u", ops[o]);
     }
     pp += need; left -= need;
@@ -414,6 +429,9 @@ static int launch_chain(const vkb_launch_t *l, int n_ops, const uint32_t *ops)
     PW_CASE(PW_COLOUR, 0, 0, 0)
     PW_CASE(PW_FILMCURV, 0, 0, 0)
     PW_CASE(PW_GRADE, 0, 0, 0)
+    PW_CASE(PW_COLENC, 0, 0, 0)
+    PW_CASE(PW_GRADE, PW_COLENC, 0, 0)
+    PW_CASE(PW_CROP, PW_COLOUR, PW_FILMCURV, PW_COLENC)
     default:
     generic:
   k_pointwise<<<grid, block, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, out->data, out->wd, out->ht, P);
@@ -427,6 +445,7 @@ static int launch_crop(const vkb_launch_t *l)     { const uint32_t op = PW_CROP;
 static int launch_colour(const vkb_launch_t *l)   { const uint32_t op = PW_COLOUR;   return launch_chain(l, 1, &op); }
 static int launch_filmcurv(const vkb_launch_t *l) { const uint32_t op = PW_FILMCURV; return launch_chain(l, 1, &op); }
 static int launch_grade(const vkb_launch_t *l)    { const uint32_t op = PW_GRADE;    return launch_chain(l, 1, &op); }
+static int launch_colenc(const vkb_launch_t *l)   { const uint32_t op = PW_COLENC;   return launch_chain(l, 1, &op); }
 static int launch_pointw(const vkb_launch_t *l)
 {
   VKB_REQUIRE(l->push_size >= 8);
@@ -438,6 +457,7 @@ VKB_REGISTER("crop", "main", launch_crop);
 VKB_REGISTER("colour", "main", launch_colour);
 VKB_REGISTER("filmcurv", "main", launch_filmcurv);
 VKB_REGISTER("grade", "main", launch_grade);
+VKB_REGISTER("colenc", "main", launch_colenc);
 VKB_REGISTER("b200", "pointw", launch_pointw);
 
 VKB_NS_END

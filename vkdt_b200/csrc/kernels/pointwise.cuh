@@ -13,6 +13,7 @@
 struct crop_committed_t { float H[12]; float r[4]; float crop[4]; };                     // crop/main.c:311-335
 struct filmcurv_params_t { float light, contrast, bias; int colour; float chroma, rolloff, red, yellow, blue, shadows; };
 struct grade_params_t { float lift[4], gamma[4], gain[4], off[4]; int mode; float sh_pivot, hi_pivot; };
+struct colenc_params_t { int prim, trc; };                                               // colenc/params
 // colour: host side digest of the 242-float committed block (colour/main.c:260-364)
 struct colour_digest_t
 {
@@ -350,6 +351,49 @@ VKB_DEV f3 filmcurv_px(f3 in, const filmcurv_params_t &p)
     return oklab_to_rec2020({ L1, C1 * cr * ch, C1 * cr * sh });
   }
   return { 0, 0, 0 }; // colour == 2 (munsell lut) is out of scope
+}
+
+// ---- colenc (colenc/main.comp:17-81): rec2020 -> output primaries, output transfer curve ----
+// constants: glslang folds constant expressions in double and rounds once
+VKB_DEV f3 colenc_px(f3 c, const colenc_params_t &p)
+{
+  if(p.prim == 1)       c = f3{ 1.66022677f * c.x - 0.58754761f * c.y - 0.07283825f * c.z, -0.12455334f * c.x + 1.13292605f * c.y - 0.00834963f * c.z, -0.01815514f * c.x - 0.10060303f * c.y + 1.11899817f * c.z };
+  else if(p.prim == 3)  c = f3{ 1.15194302f * c.x - 0.09753232f * c.y - 0.05448118f * c.z, -0.12454585f * c.x + 1.13290963f * c.y - 0.00837122f * c.z, -0.02253539f * c.x - 0.04979918f * c.y + 1.07275365f * c.z };
+  else if(p.prim == 4)  c = f3{ 1.34353337f * c.x - 0.28218904f * c.y - 0.06142427f * c.z, -0.06530851f * c.x + 1.07578268f * c.y - 0.01048453f * c.z, 0.00282971f * c.x - 0.01961215f * c.y + 1.01717851f * c.z };
+  else if(p.prim == 5)  c = rec2020_to_xyz(c);
+  else if(p.prim == 6)  c = f3{ 6.68685575e-01f * c.x + 1.51817679e-01f * c.y + 1.77189677e-01f * c.z, 4.49002044e-02f * c.x + 8.62145497e-01f * c.y + 1.01922441e-01f * c.z, -2.66851927e-09f * c.x + 2.78271109e-02f * c.y + 1.05170358f * c.z };
+  else if(p.prim == 7)  c = f3{ 9.62918591e-01f * c.x + 1.16137050e-02f * c.y + 2.55863361e-02f * c.z, 4.16800770e-04f * c.x + 9.99378426e-01f * c.y - 8.82457347e-05f * c.z, 5.31123331e-03f * c.x + 2.18655328e-02f * c.y + 9.75907920e-01f * c.z };
+  else if(p.prim == 10) c = f3{ 0.853263f * c.x + 0.079695f * c.y + 0.067042f * c.z, 0.029375f * c.x + 0.809195f * c.y + 0.161430f * c.z, 0.051575f * c.x + 0.208097f * c.y + 0.740329f * c.z };
+  float v[3] = { c.x, c.y, c.z };
+#pragma unroll
+  for(int k = 0; k < 3; k++)
+  {
+    float t = v[k];
+    if(p.trc == 1)
+    {
+      const float a = 1.09929682680944f, b = 0.018053968510807f;
+      t = t > b ? PW_POW(t, (float)(1.0 / 2.2)) * a - (a - 1) : t * 4.5f;
+    }
+    else if(p.trc == 2) t = t > 0.0031308f ? PW_POW(t, (float)(1.0 / 2.4)) * 1.055f - 0.055f : t * 12.92f;
+    else if(p.trc == 3)
+    {
+      const float c3 = (float)(2392.0 / 128.0), c2 = (float)(2413.0 / 128.0), c1 = c3 - c2 + 1.0f;
+      const float m1 = (float)(1305.0 / 8192.0), m2 = (float)(2523.0 / 32.0);
+      t = fmaxf(0.0f, t);
+      t = PW_POW(t, m1);
+      const float num = (c1 - 1.0f) + (c2 - c3) * t, den = 1.0f + c3 * t;
+      t = PW_POW(1.0f + num / den, m2);
+    }
+    else if(p.trc == 4) t = PW_POW(t, (float)(1.0 / 2.6));
+    else if(p.trc == 5)
+    {
+      const float a = 0.17883277f, b = 1.0f - 4.0f * a, cc = 0.5f - a * -0.33500978350639343f; // c = 0.5 - a log(4a): logf(4 * 0.17883277f) = -0.33500978 (libm)
+      t = t > (float)(1.0 / 12.0) ? a * m_log(12.0f * t - b) + cc : sqrtf(3.0f * t);
+    }
+    else if(p.trc == 6) t = PW_POW(t, (float)(1.0 / 2.2));
+    v[k] = t;
+  }
+  return { v[0], v[1], v[2] };
 }
 
 // ---- grade (grade/main.comp:21-62) ----

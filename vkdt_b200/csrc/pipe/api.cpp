@@ -3,6 +3,7 @@
 #include "dng.h"
 #include "lj92.h"
 #include "mlv.h"
+#include "jpeg.h"
 
 int vkb_plan_sink(dt_graph_t *g, int modid, uint32_t *wd, uint32_t *ht, void **dptr);
 uint64_t vkb_plan_pool_bytes(dt_graph_t *g);
@@ -53,10 +54,18 @@ int vkb_graph_read_config_line(vkb_graph_t *h, const char *line)
   std::string s(line);
   return dt_graph_read_config_line(h->g, &s[0]);
 }
+int vkb_graph_replace_display_ex(vkb_graph_t *h, const char *inst, const char *sink_module, int prim, int trc)
+{
+  if(!h) return VKB_ERR_BAD_ARG;
+  const int m = dt_graph_replace_display(h->g, dt_token(inst && inst[0] ? inst : "main"), dt_token(sink_module && sink_module[0] ? sink_module : "o-jpg"), prim, trc);
+  if(m < 0) return vkb_set_error(VKB_ERR_GRAPH, "replace display failed (%d)", m);
+  dt_graph_disconnect_display_modules(h->g);
+  return VKB_OK;
+}
 int vkb_graph_replace_display(vkb_graph_t *h, const char *sink_module)
 {
   if(!h) return VKB_ERR_BAD_ARG;
-  const int m = dt_graph_replace_display(h->g, dt_token("main"), dt_token(sink_module && sink_module[0] ? sink_module : "o-pfm"));
+  const int m = dt_graph_replace_display(h->g, dt_token("main"), dt_token(sink_module && sink_module[0] ? sink_module : "o-pfm"), 2, 0);
   if(m < 0) return vkb_set_error(VKB_ERR_GRAPH, "replace display failed (%d)", m);
   dt_graph_disconnect_display_modules(h->g);
   return VKB_OK;
@@ -84,7 +93,7 @@ int vkb_graph_set_sink_buffer(vkb_graph_t *h, const char *inst, void *dst, size_
 }
 int vkb_graph_set_sink_layout(vkb_graph_t *h, const char *inst, int layout)
 {
-  if(!h || (layout != VKB_SINK_RGBA_F32 && layout != VKB_SINK_RGB_F32)) return VKB_ERR_BAD_ARG;
+  if(!h || layout < VKB_SINK_RGBA_F32 || layout > VKB_SINK_RGB_UI8) return VKB_ERR_BAD_ARG;
   const int m = find_inst(h->g, inst, false);
   if(m < 0) return vkb_set_error(VKB_ERR_BAD_ARG, "no sink module with instance '%s'", inst ? inst : "main");
   h->g->mem_sink[m].layout = layout;
@@ -105,6 +114,7 @@ int vkb_graph_sink_device(vkb_graph_t *h, const char *inst, void **d_ptr)
   return vkb_plan_sink(h->g, m, 0, 0, d_ptr) ? vkb_set_error(VKB_ERR_GRAPH, "graph has not been run yet") : VKB_OK;
 }
 int vkb_graph_set_frame(vkb_graph_t *h, uint32_t frame) { if(!h) return VKB_ERR_BAD_ARG; h->g->frame = frame; return VKB_OK; }
+int vkb_graph_frame_count(vkb_graph_t *h) { return h ? (int)h->g->frame_cnt : VKB_ERR_BAD_ARG; }
 int vkb_graph_run(vkb_graph_t *h, int runflags) { if(!h) return VKB_ERR_BAD_ARG; return dt_graph_run(h->g, (uint32_t)runflags); }
 int vkb_graph_perf(vkb_graph_t *h, char *buf, size_t bufsize)
 {
@@ -216,6 +226,11 @@ int vkb_graph_band_stats(vkb_graph_t *h, uint64_t *bytes_total, uint64_t *bytes_
 { if(!h) return VKB_ERR_BAD_ARG; return vkb_plan_band_stats(h->g, bytes_total, bytes_max_device, pulls, launches) ? vkb_set_error(VKB_ERR_GRAPH, "no band split planned") : VKB_OK; }
 int vkb_graph_band_mark(vkb_graph_t *h, int which) { if(!h) return VKB_ERR_BAD_ARG; return vkb_plan_band_mark(h->g, which); }
 int vkb_graph_band_elapsed_ms(vkb_graph_t *h, float *ms) { if(!h || !ms) return VKB_ERR_BAD_ARG; return vkb_plan_band_elapsed(h->g, ms); }
+int vkb_jpeg_write(const char *filename, const uint8_t *rgba, int width, int height, float quality)
+{
+  if(!filename || !rgba) return VKB_ERR_BAD_ARG;
+  return jpeg_write_rgba8(filename, rgba, width, height, quality) ? vkb_set_error(VKB_ERR_IO, "could not write '%s'", filename) : VKB_OK;
+}
 int vkb_graph_set_device(vkb_graph_t *h, int device) { if(!h) return VKB_ERR_BAD_ARG; h->g->device = device; return VKB_OK; }
 uint64_t vkb_graph_pool_bytes(vkb_graph_t *h) { return h ? vkb_plan_pool_bytes(h->g) : 0; }
 

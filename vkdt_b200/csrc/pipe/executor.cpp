@@ -115,13 +115,14 @@ void dt_graph_cleanup(dt_graph_t *g)
 static inline bool is_node(const dt_node_t *n, const char *name, const char *kernel) { return n->name == dt_token(name) && n->kernel == dt_token(kernel); }
 static inline bool is_pointwise(const dt_node_t *n)
 {
-  return is_node(n, "crop", "main") || is_node(n, "colour", "main") || is_node(n, "filmcurv", "main") || is_node(n, "grade", "main");
+  return is_node(n, "crop", "main") || is_node(n, "colour", "main") || is_node(n, "filmcurv", "main") || is_node(n, "grade", "main") || is_node(n, "colenc", "main");
 }
 static inline uint32_t pw_op(const dt_node_t *n)
 {
   if(is_node(n, "crop", "main")) return 1;
   if(is_node(n, "colour", "main")) return 2;
   if(is_node(n, "filmcurv", "main")) return 3;
+  if(is_node(n, "colenc", "main")) return 5;
   return 4;
 }
 static size_t conn_bytes(const dt_connector_t *c)
@@ -423,7 +424,7 @@ static int build_plan(dt_graph_t *g, bool with_device)
       plan_sink_t s;
       const plan_img_t in = B.img_in(n, 0);
       s.modid = modid; s.nodeid = n; s.buf = in.buf; s.wd = in.wd; s.ht = in.ht;
-      s.bytes = (size_t)in.wd * in.ht * in.chan * (in.format == dt_token("f32") ? 4 : 2);
+      s.bytes = (size_t)in.wd * in.ht * in.chan * (in.format == dt_token("f32") ? 4 : (in.format == dt_token("ui8") ? 1 : 2));
       s.rgb = 0;
       if(in.buf >= 0 && (in.wd == 0 || in.ht == 0 || (uint64_t)in.wd * in.ht > (1ull << 32)))
       { // e.g. a crop window with no area: the reference signals failure by an empty roi (graph-run-modules.h:652-666)
@@ -434,6 +435,19 @@ static int build_plan(dt_graph_t *g, bool with_device)
       // packed rgb f32 (the PFM payload): asked for by the caller, or implied by o-pfm writing a file
       const vkb_mem_sink_t *msk = modid < (int)g->mem_sink.size() ? &g->mem_sink[modid] : 0;
       const bool to_file = !(msk && msk->valid) && nd->module->name == dt_token("o-pfm");
+      if(in.buf >= 0 && in.chan == 4 && in.format == dt_token("ui8") && msk && msk->valid && msk->layout == VKB_SINK_RGB_UI8)
+      { // packed 8 bit rgb (3 B/px) into caller memory: the pointwise kernel that ends in colenc stores it directly
+        for(int li = (int)p->launch.size() - 1; li >= 0; li--)
+        {
+          plan_launch_t &pl = p->launch[li];
+          int ci = -1;
+          for(size_t c = 0; c < pl.conn.size(); c++) if(pl.conn[c].buf == in.buf) ci = (int)c;
+          if(ci < 0) continue;
+          if((pl.name == dt_token("b200") && pl.kernel == dt_token("pointw") && ci == 1) || (pl.name == dt_token("colenc") && ci == 1))
+          { pl.conn[ci].chan = 3; s.bytes = (size_t)in.wd * in.ht * 3; s.rgb = 1; }
+          break;
+        }
+      }
       if(in.buf >= 0 && in.chan == 4 && in.format == dt_token("f32") && (to_file || (msk && msk->layout == VKB_SINK_RGB_F32)))
       {
         // the launch that writes this buffer: if it is one of the fused kernels it stores r g b directly
@@ -1123,7 +1137,7 @@ int dt_graph_run(dt_graph_t *g, uint32_t run)
         size_t bytes = 0; // unique bytes in + out of this launch
         std::set<int> seen;
         for(const plan_img_t &im : p->launch[i].conn) if(im.buf >= 0 && seen.insert(im.buf).second)
-          bytes += (size_t)im.wd * im.ht * im.chan * im.layers * (im.format == dt_token("f32") ? 4 : 2);
+          bytes += (size_t)im.wd * im.ht * im.chan * im.layers * (im.format == dt_token("f32") ? 4 : (im.format == dt_token("ui8") ? 1 : 2));
         snprintf(b, sizeof(b), "[perf] %-60s:\t%8.3f ms\t%12zu B\n", p->launch[i].label.c_str(), p->launch[i].ms, bytes);
         g->perf_text += b;
       }

@@ -475,8 +475,8 @@ int dt_graph_read_config_ascii(dt_graph_t *g, const char *filename)
 }
 
 // graph-export.c:23-96 (no resize / colenc: the hot path exports linear rec2020 f32)
-int dt_graph_replace_display(dt_graph_t *g, dt_token_t inst, dt_token_t mod)
-{
+int dt_graph_replace_display(dt_graph_t *g, dt_token_t inst, dt_token_t mod, int prim, int trc)
+{ // graph-export.c:23-96 without the resize branch
   if(inst == 0) inst = dt_token("main");
   const int mid = dt_module_get(g, dt_token("display"), inst);
   if(mid < 0) return -1;
@@ -487,6 +487,22 @@ int dt_graph_replace_display(dt_graph_t *g, dt_token_t inst, dt_token_t mod)
   const int m2 = dt_module_add(g, mod, inst);
   if(m2 < 0) return -3;
   const int i2 = dt_module_get_connector(&g->module[m2], dt_token("input"));
+  if(g->module[m2].connector[i2].format == dt_token("ui8") || prim != 2 || trc != 0)
+  { // :66-86: 8 bit sinks and other colour spaces than linear bt2020 get a colenc module in front
+    const int m1 = dt_module_add(g, dt_token("colenc"), inst);
+    if(m1 < 0) return -3;
+    dt_module_t *ce = &g->module[m1];
+    const int i1 = dt_module_get_connector(ce, dt_token("input")), o1 = dt_module_get_connector(ce, dt_token("output"));
+    if(prim == 0xffff) prim = g->module[m0].img_param.colour_primaries;
+    if(trc  == 0xffff) trc  = g->module[m0].img_param.colour_trc;
+    *(int32_t *)dt_module_param_int(ce, dt_module_get_param(ce->so, dt_token("prim"))) = prim;
+    *(int32_t *)dt_module_param_int(ce, dt_module_get_param(ce->so, dt_token("trc")))  = trc;
+    ce->connector[o1].format = g->module[m2].connector[i2].format;
+    ce->connector[o1].chan   = g->module[m2].connector[i2].chan;
+    if(dt_module_connect(g, m0, o0, m1, i1)) return -4;
+    if(dt_module_connect(g, m1, o1, m2, i2)) return -4;
+    return m2;
+  }
   if(g->module[m2].connector[i2].format != dt_token("*")) g->module[m0].connector[o0].format = g->module[m2].connector[i2].format;
   if(g->module[m2].connector[i2].chan != dt_token("*"))   g->module[m0].connector[o0].chan   = g->module[m2].connector[i2].chan;
   const int err = dt_module_connect(g, m0, o0, m2, i2);

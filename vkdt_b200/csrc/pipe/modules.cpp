@@ -6,6 +6,7 @@
 #include "pipe.h"
 #include "mlv.h"
 #include "dng.h"
+#include "jpeg.h"
 #include <strings.h>
 #include <math.h>
 #include <stdlib.h>
@@ -38,7 +39,9 @@ static const module_def_t g_defs[] = {
   { "grade",    "input:read:*:*\noutput:write:*:*",
                 "lift:float:4:0.0:0.0:0.0:0\ngamma:float:4:1.0:1.0:1.0:0\ngain:float:4:1.0:1.0:1.0:0\noffset:float:4:0.0:0.0:0.0:0\n"
                 "mode:int:1:0\nsh_pivot:float:1:0.3\nhi_pivot:float:1:0.4" },
+  { "colenc",   "input:read:rgba:*\noutput:write:rgba:*", "prim:int:1:1\ntrc:int:1:0" },
   { "o-pfm",    "input:sink:rgba:f32", "filename:string:256:output" },
+  { "o-jpg",    "input:sink:rgba:ui8", "filename:string:256:output\nquality:float:1:95\nexif:int:1:1" },
   { "o-null",   "input:sink:*:*", "" },
   { "display",  "input:sink:rgba:*", "" },
   // present in the default darkroom graph but never reachable from the exported sink: parse only
@@ -147,6 +150,8 @@ static void filmcurv_roi_out(dt_graph_t *, dt_module_t *);
 static void filmcurv_create_nodes(dt_graph_t *, dt_module_t *);
 static void llap_create_nodes(dt_graph_t *, dt_module_t *);
 static void opfm_write_sink(dt_module_t *, void *, dt_write_sink_params_t *);
+static void ojpg_write_sink(dt_module_t *, void *, dt_write_sink_params_t *);
+static void colenc_roi_out(dt_graph_t *, dt_module_t *);
 
 static std::vector<dt_module_so_t> &registry()
 {
@@ -168,6 +173,8 @@ static std::vector<dt_module_so_t> &registry()
     if(n == "filmcurv") { so.modify_roi_out = filmcurv_roi_out; so.create_nodes = filmcurv_create_nodes; }
     if(n == "llap")     { so.create_nodes = llap_create_nodes; }
     if(n == "o-pfm")    { so.write_sink = opfm_write_sink; }
+    if(n == "o-jpg")    { so.write_sink = ojpg_write_sink; }
+    if(n == "colenc")   { so.modify_roi_out = colenc_roi_out; }
     r.push_back(so);
   }
   return r;
@@ -1066,6 +1073,27 @@ static void llap_create_nodes(dt_graph_t *graph, dt_module_t *module)
 
 // ------------------------------------------------------------------------------------------------
 // o-pfm (o-pfm/main.c:8-42)
+// colenc/main.c: the image downstream is in the encoded colour space
+static void colenc_roi_out(dt_graph_t *, dt_module_t *module)
+{
+  module->img_param.colour_primaries = dt_module_param_int(module, dt_module_get_param(module->so, dt_token("prim")))[0];
+  module->img_param.colour_trc       = dt_module_param_int(module, dt_module_get_param(module->so, dt_token("trc")))[0];
+  module->connector[1].roi.full_wd = module->connector[0].roi.full_wd;
+  module->connector[1].roi.full_ht = module->connector[0].roi.full_ht;
+}
+
+// o-jpg/main.c:102-172 with an own baseline encoder (pipe/jpeg.cpp); no icc profile, no exif copy (needs exiftool)
+static void ojpg_write_sink(dt_module_t *module, void *buf, dt_write_sink_params_t *)
+{
+  const char *basename = dt_module_param_string(module, 0);
+  fprintf(stderr, "[o-jpg] writing '%s'\n", basename);
+  char filename[512];
+  snprintf(filename, sizeof(filename), "%s.jpg", basename);
+  const float quality = dt_module_param_float(module, 1)[0];
+  if(jpeg_write_rgba8(filename, (const uint8_t *)buf, module->connector[0].roi.wd, module->connector[0].roi.ht, quality))
+    fprintf(stderr, "[o-jpg] could not write '%s'\n", filename);
+}
+
 static void opfm_write_sink(dt_module_t *module, void *buf, dt_write_sink_params_t *)
 {
   const char *basename = dt_module_param_string(module, 0);

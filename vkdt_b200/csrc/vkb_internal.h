@@ -41,6 +41,7 @@ void vkb_count_launch(int n);
 #define VKB_TOKEN_F16  0x363166ull        /* "f16"  */
 #define VKB_TOKEN_F32  0x323366ull        /* "f32"  */
 #define VKB_TOKEN_UI16 0x36316975ull      /* "ui16" */
+#define VKB_TOKEN_UI8  0x386975ull        /* "ui8"  */
 
 struct vkb_registrar_t { vkb_registrar_t(const char *n, const char *k, vkb_kernel_fn f) { vkb_register_kernel(n, k, f, VKB_FAST); } };
 #define VKB_REGISTER(name, kernel, fn) static vkb_registrar_t vkb_reg_##fn(name, kernel, fn)
