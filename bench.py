@@ -164,7 +164,7 @@ def ncu_traffic(label, key="bytes_per_launch"):
 
 
 def run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, src, bpp, strength, steps, warmup, sample_clocks=True,
-                 mode=0, e2e=True):
+                 mode=0, e2e=True, sink8=False):
     """both legs (kernel path with HBM-resident input, end to end with host buffers) of one workload on this rank.
     mode: api.MODE_STRICT (the headline) or api.MODE_FAST; e2e=False: kernel leg only."""
     # ---- synthetic input: a few distinct stills per rank, cycled (deterministic seeds per SURVEY §8d) ----
@@ -198,11 +198,15 @@ def run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, s
     api.check(api.lib.vkb_stream_sync(None))
 
     def make_graph():
-        g = api.Graph(cfg_text=api.DARKROOM_CFG.format(src=src))
+        if sink8:   # the reference's default export: o-jpg behind colenc (sRGB primaries, rec709 curve), packed 8 bit rgb
+            g = api.Graph(cfg_text=api.DARKROOM_CFG.format(src=src), sink="o-jpg", prim=1, trc=1)
+            g.set_sink_layout(api.SINK_RGB_UI8)
+        else:
+            g = api.Graph(cfg_text=api.DARKROOM_CFG.format(src=src))
+            g.set_sink_layout(api.SINK_RGB_F32)   # the PFM payload (r g b f32, 12 B/px) is what o-pfm puts into the file
         g.set_device(local_rank)
         if strength > 0:
             g.line("param:denoise:01:strength:%g" % strength)
-        g.set_sink_layout(api.SINK_RGB_F32)   # the PFM payload (r g b f32, 12 B/px) is what o-pfm puts into the file
         g.set_mode(mode)
         return g
 
@@ -212,7 +216,7 @@ def run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, s
     g.set_sink_buffer(None, 0)
     g.run()                              # builds the plan, allocates the pool
     ow, oh = g.sink_size()
-    out_bytes = ow * oh * 12
+    out_bytes = ow * oh * (3 if sink8 else 12)
     stream = g.stream()
     FR = api.RUN_RECORD
     for i in range(warmup):
@@ -297,7 +301,7 @@ def run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, s
         t = torch.tensor([t_e2e_ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e_ms = float(t.item())
-    checksum = float(np.frombuffer((api.C.c_float * 4).from_address(host_out[(e2e_steps - 1) % NG]), dtype=np.float32).sum())
+    checksum = float(np.frombuffer((api.C.c_uint8 * 16).from_address(host_out[(e2e_steps - 1) % NG]), dtype=np.uint8 if sink8 else np.float32).sum())
 
     for hp in host_in + host_out:
         api.host_free(hp)
@@ -496,6 +500,13 @@ def main():
     if args.workload != "mlv4k" and not args.no_mlv:
         M = run_workload(api, synth, torch, dist, args, rank, world, local_rank, mlv_W, mlv_H, mlv_src, mlv_bpp, strength,
                          max(40, min(10 * args.steps, 200)), 3, sample_clocks=False, mode=mode)
+    M8 = S8 = None
+    if not args.no_mlv:
+        if args.workload != "mlv4k":
+            M8 = run_workload(api, synth, torch, dist, args, rank, world, local_rank, mlv_W, mlv_H, mlv_src, mlv_bpp, strength,
+                              max(40, min(10 * args.steps, 200)), 3, sample_clocks=False, mode=mode, sink8=True)
+        S8 = run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, src, bpp, strength, max(4, min(args.steps, 10)), 3,
+                          sample_clocks=False, mode=mode, sink8=True)
     Bd = None
     if world > 1 and not args.no_bands:
         # config 5 rides along in the scaling runs: one 201 MP still over all the GPUs of the box, driven by rank 0
@@ -561,6 +572,16 @@ def main():
                          "frames_per_s": round(world * msteps / (M["t_kernel_ms"] * 1e-3), 1), "ms_per_frame": round(M["t_kernel_ms"] / msteps, 3),
                          "e2e_frames_per_s": round(world * M["e2e_steps"] / (M["t_e2e_ms"] * 1e-3), 1),
                          "h2d_bytes_per_frame": M["in_bytes"], "d2h_bytes_per_frame": M["out_bytes"], "n_gpus": world}
+    if M8:
+        msteps = max(40, min(10 * args.steps, 200))
+        line["mlv4k"]["sink_8bit"] = {"what": "the reference's default export (o-jpg: colenc sRGB / rec709 curve, packed rgb ui8, 3 B/px) instead of the f32 PFM payload",
+                                      "frames_per_s": round(world * msteps / (M8["t_kernel_ms"] * 1e-3), 1), "e2e_frames_per_s": round(world * M8["e2e_steps"] / (M8["t_e2e_ms"] * 1e-3), 1),
+                                      "d2h_bytes_per_frame": M8["out_bytes"]}
+    if S8:
+        s8steps = max(4, min(args.steps, 10))
+        line["e2e_8bit"] = {"what": "the same stills through the reference's default export (o-jpg: colenc + packed rgb ui8 sink, 3 B/px)",
+                            "value": round(world * S8["e2e_steps"] * mp / (S8["t_e2e_ms"] * 1e-3), 2), "unit": "MP/s", "d2h_bytes_per_step": S8["out_bytes"],
+                            "kernel_path_value": round(world * s8steps * mp / (S8["t_kernel_ms"] * 1e-3), 2)}
     line["config"]["host_placement"] = numa
     if not args.no_cpu_baseline:
         os.sched_setaffinity(0, full_affinity)

@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""how much pinned host traffic can the GPUs of this box move together?  concurrent device->host, host->device and both at
+once on 1 / 2 / 4 / 8 GPUs (one thread and one pinned buffer per GPU, first touched by the thread next to its GPU).
+answers VERDICT r01 weak point 7: is the ~100 GB/s the 8 GPU end to end rates saturate at the box or the placement?
+output: one json line per configuration (kept under profiles/)."""
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+
+def run(n, direction, mb=512, reps=8, pin_numa=True):
+    bufs, devs, streams = [], [], []
+    for d in range(n):
+        torch.cuda.set_device(d)
+        if pin_numa:
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(d))
+            except Exception:
+                pass
+        h = torch.empty(mb << 20, dtype=torch.uint8).pin_memory()
+        h.fill_(1)                                     # first touch here
+        bufs.append(h)
+        devs.append(torch.empty(mb << 20, dtype=torch.uint8, device="cuda:%d" % d))
+        streams.append(torch.cuda.Stream(device=d))
+    try:
+        os.sched_setaffinity(0, range(os.cpu_count()))
+    except Exception:
+        pass
+    barrier = threading.Barrier(n + 1)
+    times = [0.0] * n
+
+    def work(d):
+        torch.cuda.set_device(d)
+        s = streams[d]
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                bufs[d].copy_(devs[d], non_blocking=True)
+            s.synchronize()
+            barrier.wait()
+            t0 = time.time()
+            for _ in range(reps):
+                if direction in ("d2h", "both"):
+                    bufs[d].copy_(devs[d], non_blocking=True)
+                if direction in ("h2d",):
+                    devs[d].copy_(bufs[d], non_blocking=True)
+            if direction == "both":
+                s2 = torch.cuda.Stream(device=d)
+                with torch.cuda.stream(s2):
+                    d2 = torch.empty_like(devs[d]); h2 = torch.empty(mb << 20, dtype=torch.uint8).pin_memory()
+                    for _ in range(reps):
+                        d2.copy_(h2, non_blocking=True)
+                s2.synchronize()
+            s.synchronize()
+            times[d] = time.time() - t0
+
+    th = [threading.Thread(target=work, args=(d,)) for d in range(n)]
+    for t in th:
+        t.start()
+    barrier.wait()
+    for t in th:
+        t.join()
+    tot = n * reps * (mb << 20) * (2 if direction == "both" else 1)
+    return tot / max(times) / 1e9
+
+
+if __name__ == "__main__":
+    ndev = torch.cuda.device_count()
+    for n in (1, 2, 4, 8):
+        if n > ndev:
+            break
+        for direction in ("d2h", "h2d", "both"):
+            print(json.dumps({"gpus": n, "direction": direction, "aggregate_gbs": round(run(n, direction), 1)}), flush=True)
