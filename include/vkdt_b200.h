@@ -102,6 +102,16 @@ VKB_API int  vkb_get_mode(void);
 VKB_API uint64_t vkb_launch_count(void);
 VKB_API void     vkb_launch_count_reset(void);
 
+/* ---- module registry (src/pipe/global.c:86-415, dt_pipe_global_init :442) ---- */
+/* name a vkdt installation (<dir>/modules/<name>/connectors, params) or checkout (<vkdt>/src/pipe): its module files then are
+ * the source of truth for connectors and parameters of every module, the tables built into the library only the fallback, and
+ * every module directory found there can be named in a cfg (modules without kernels here parse, and fail only when a sink
+ * reaches them).  also: environment VKDT_B200_BASEDIR.  call before creating graphs. */
+VKB_API int  vkb_set_basedir(const char *dir);
+/* the registered connectors and parameters of a module: "connector name:type:chan:format" and
+ * "param name:type:cnt:offset:<default value blob, hex>" lines.  host only. */
+VKB_API int  vkb_module_describe(const char *name, char *buf, size_t bufsize);
+
 /* ---- 3. graph ---- */
 typedef struct vkb_graph_t vkb_graph_t;
 

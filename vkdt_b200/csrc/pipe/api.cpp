@@ -226,6 +226,16 @@ int vkb_graph_band_stats(vkb_graph_t *h, uint64_t *bytes_total, uint64_t *bytes_
 { if(!h) return VKB_ERR_BAD_ARG; return vkb_plan_band_stats(h->g, bytes_total, bytes_max_device, pulls, launches) ? vkb_set_error(VKB_ERR_GRAPH, "no band split planned") : VKB_OK; }
 int vkb_graph_band_mark(vkb_graph_t *h, int which) { if(!h) return VKB_ERR_BAD_ARG; return vkb_plan_band_mark(h->g, which); }
 int vkb_graph_band_elapsed_ms(vkb_graph_t *h, float *ms) { if(!h || !ms) return VKB_ERR_BAD_ARG; return vkb_plan_band_elapsed(h->g, ms); }
+int vkb_set_basedir(const char *dir) { return dt_pipe_set_basedir(dir); }
+int vkb_module_describe(const char *name, char *buf, size_t bufsize)
+{
+  if(!name || !buf || !bufsize) return VKB_ERR_BAD_ARG;
+  std::string s;
+  if(dt_module_so_describe(dt_token(name), &s)) return vkb_set_error(VKB_ERR_BAD_ARG, "no module '%s'", name);
+  if(s.size() + 1 > bufsize) return vkb_set_error(VKB_ERR_BAD_ARG, "buffer too small: %zu < %zu", bufsize, s.size() + 1);
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return VKB_OK;
+}
 int vkb_jpeg_write(const char *filename, const uint8_t *rgba, int width, int height, float quality)
 {
   if(!filename || !rgba) return VKB_ERR_BAD_ARG;

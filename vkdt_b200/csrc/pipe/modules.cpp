@@ -153,11 +153,71 @@ static void opfm_write_sink(dt_module_t *, void *, dt_write_sink_params_t *);
 static void ojpg_write_sink(dt_module_t *, void *, dt_write_sink_params_t *);
 static void colenc_roi_out(dt_graph_t *, dt_module_t *);
 
+// ---- module discovery (global.c:86-415, :442): <basedir>/modules/<name>/{connectors,params} are the source of truth when a
+// vkdt installation (or checkout: basedir = <vkdt>/src/pipe) is named by vkb_set_basedir() / VKDT_B200_BASEDIR; the built-in
+// tables above are the fallback for a stand-alone library.  callbacks stay statically registered (the reference dlopens
+// lib<name>.so); a directory of a module that has no callbacks here registers with the defaults (one node "main", roi copied
+// through), so that every cfg of the installation parses: such a module fails at run time only if a sink reaches it.
+static std::string &basedir()
+{
+  static std::string d = getenv("VKDT_B200_BASEDIR") ? getenv("VKDT_B200_BASEDIR") : "";
+  return d;
+}
+static bool read_text(const std::string &fn, std::string *out)
+{
+  FILE *f = fopen(fn.c_str(), "rb");
+  if(!f) return false;
+  char b[4096]; size_t n;
+  out->clear();
+  while((n = fread(b, 1, sizeof(b), f)) > 0) out->append(b, n);
+  fclose(f);
+  return true;
+}
+static std::vector<dt_module_so_t> &registry_storage() { static std::vector<dt_module_so_t> r; return r; }
+static std::vector<std::string> &registry_strings() { static std::vector<std::string> s; return s; }
+int dt_pipe_set_basedir(const char *dir)
+{ // takes effect for graphs created afterwards
+  basedir() = dir ? dir : "";
+  registry_storage().clear();
+  return 0;
+}
+#include <dirent.h>
 static std::vector<dt_module_so_t> &registry()
 {
-  static std::vector<dt_module_so_t> r;
+  std::vector<dt_module_so_t> &r = registry_storage();
   if(!r.empty()) return r;
-  for(const module_def_t &d : g_defs)
+  std::vector<module_def_t> defs(g_defs, g_defs + sizeof(g_defs) / sizeof(g_defs[0]));
+  std::vector<std::string> &keep = registry_strings();
+  keep.clear(); keep.reserve(1024);
+  if(!basedir().empty())
+  {
+    const std::string mdir = basedir() + "/modules";
+    for(module_def_t &d : defs)
+    { // a known module: the installation's files override the built-in tables
+      std::string c, p;
+      if(read_text(mdir + "/" + d.name + "/connectors", &c)) { keep.push_back(c); d.connectors = keep.back().c_str(); }
+      else continue;
+      if(read_text(mdir + "/" + d.name + "/params", &p)) { keep.push_back(p); d.params = keep.back().c_str(); } else d.params = "";
+    }
+    if(DIR *dp = opendir(mdir.c_str()))
+    { // every other module directory: parse only
+      while(struct dirent *ep = readdir(dp))
+      {
+        if(ep->d_name[0] == '.' || strlen(ep->d_name) > 8) continue;
+        bool known = false;
+        for(const module_def_t &d : defs) if(!strcmp(d.name, ep->d_name)) known = true;
+        std::string c, p;
+        if(known || !read_text(mdir + "/" + ep->d_name + "/connectors", &c)) continue;
+        read_text(mdir + "/" + ep->d_name + "/params", &p);
+        keep.push_back(ep->d_name); const char *nm = keep.back().c_str();
+        keep.push_back(c); const char *cs = keep.back().c_str();
+        keep.push_back(p); const char *ps = keep.back().c_str();
+        defs.push_back(module_def_t{ nm, cs, ps });
+      }
+      closedir(dp);
+    }
+  }
+  for(const module_def_t &d : defs)
   {
     dt_module_so_t so = {};
     parse_def(d, &so);
@@ -183,6 +243,23 @@ static std::vector<dt_module_so_t> &registry()
 dt_module_so_t *dt_module_so_get(dt_token_t name)
 {
   for(dt_module_so_t &so : registry()) if(so.name == name) return &so;
+  return 0;
+}
+
+int dt_module_so_describe(dt_token_t name, std::string *text)
+{ // "connector <name>:<type>:<chan>:<format>" and "param <name>:<type>:<cnt>:<offset>:<default blob, hex>" lines
+  const dt_module_so_t *so = dt_module_so_get(name);
+  if(!so) return 1;
+  char b[128];
+  for(const dt_connector_t &c : so->connector)
+  { *text += "connector " + dt_token_string(c.name) + ":" + dt_token_string(c.type) + ":" + dt_token_string(c.chan) + ":" + dt_token_string(c.format) + "\n"; }
+  for(const dt_ui_param_t &p : so->param)
+  {
+    snprintf(b, sizeof(b), ":%d:%d:", p.cnt, p.offset);
+    *text += "param " + dt_token_string(p.name) + ":" + dt_token_string(p.type) + b;
+    for(uint8_t v : p.def) { snprintf(b, sizeof(b), "%02x", v); *text += b; }
+    *text += "\n";
+  }
   return 0;
 }
 

@@ -224,6 +224,8 @@ std::string dt_graph_dump_nodes(dt_graph_t *g);
 std::string dt_graph_describe(dt_graph_t *g, const std::vector<int> &modid);
 
 dt_module_so_t *dt_module_so_get(dt_token_t name);   // registry (global.c:442)
+int dt_pipe_set_basedir(const char *dir);            // <basedir>/modules/<name>/{connectors,params} override the built-in tables
+int dt_module_so_describe(dt_token_t name, std::string *text); // connectors and params of a registered module, in the files' grammar
 
 // ---- module author api (modules/api.h) ----
 #define dt_no_roi ((const dt_roi_t *)(uintptr_t)-1)
