@@ -199,6 +199,13 @@ VKB_API int  vkb_graph_set_sink_buffer(vkb_graph_t *g, const char *inst, void *d
 VKB_API int  vkb_graph_set_sink_layout(vkb_graph_t *g, const char *inst, int layout);
 VKB_API int  vkb_graph_sink_size(vkb_graph_t *g, const char *inst, uint32_t *wd, uint32_t *ht);
 VKB_API int  vkb_graph_set_frame(vkb_graph_t *g, uint32_t frame);
+/* dt_graph_apply_keyframes (src/pipe/graph.c:1025): evaluate the `keyframe:` lines of the config (frame:module:inst:param:beg:end:
+ * values; spelled keyframE / Keyframe / KeyframE / keyFRAME for ease out / ease in / smooth / step, graph-io.c:243-247) at the
+ * current frame (vkb_graph_set_frame) into the parameters; the export frame loop calls it before every frame
+ * (graph-export.c:280-283).  vkb_graph_has_feedback: 1 if the config held a `feedback:` connection: such a graph carries images
+ * from frame to frame (connector.h:116), is not frame parallel, and is refused by vkb_graph_run when a sink reaches the connector */
+VKB_API int  vkb_graph_apply_keyframes(vkb_graph_t *g);
+VKB_API int  vkb_graph_has_feedback(vkb_graph_t *g);
 /* graph->frame_cnt: set by a `frames:` config line or by a source that knows its length (i-mlv's modify_roi_out, i.e. after the
  * first run), what dt_graph_export loops over (src/pipe/graph-export.c:251-268) */
 VKB_API int  vkb_graph_frame_count(vkb_graph_t *g);

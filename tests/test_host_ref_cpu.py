@@ -318,11 +318,11 @@ def test_config_lines_match_reference_reader():
     assert 12 in codes and 4 in codes and 2 in codes and 1 in codes     # cycle, index out of range, no such parameter, no such module
 
 
-def test_keyframe_and_feedback_lines_warn():
-    """deliberate: the reference accepts these (0); keyframes and feedback connectors are outside the path, the product says so (1)
-    instead of silently developing something else."""
-    codes, _ = _product_cfg_lines(["module:grade:02", "keyframe:3:colour:01:exposure:0:1.5", "feedback:grade:01:output:grade:02:input"])
-    assert codes == [0, 1, 1]
+def test_keyframe_and_feedback_lines_are_read():
+    """like the reference's reader (graph-io.c:243-249) both are accepted; tests/test_keyframes_cpu.py covers what they do."""
+    codes, _ = _product_cfg_lines(["module:grade:02", "keyframe:3:colour:01:exposure:0:1:1.5", "feedback:grade:01:output:grade:02:input",
+                                   "keyframe:3:nosuch:01:exposure:0:1:1.5", "keyframe:3:colour:01:nosuch:0:1:1.5", "keyframe:3:colour:01:exposure:0:5:1.5"])
+    assert codes == [0, 0, 0, 1, 2, 4]
 
 
 def test_live_config_line_fuzz(oracle):
@@ -366,3 +366,33 @@ def test_pfm_writer_matches_reference_live(oracle, tmp_path):
         href.ref_write_pfm(b.encode(), oracle.fptr(rgba), w, h)
         da, db = open(a + ".pfm", "rb").read(), open(b + ".pfm", "rb").read()
         assert da == db, (w, h, da[:40], db[:40])
+
+
+def test_imlv_known_camera_matrix_from_the_checkout(oracle):
+    """a clip of a camera that IS in dcraw's adobe_coeff table (i-mlv/main.c:165-201): with the vkdt checkout named as basedir the
+    product reads that table from the checkout's own file and has to hand on the reference's image parameters (white balance from
+    the matrix, cam_to_rec2020) bit for bit: compared through the whole module pass with the reference's own i-mlv/main.c."""
+    if oracle.ref_host_lib() is None or not hasattr(oracle.ref_host_lib(), "ref_graph_describe") or not os.path.isdir("/root/reference/src/pipe/modules"):
+        pytest.skip("oracle/_ref/libhostref.so or /root/reference not present")
+    mg = _make_golden_module()
+    os.makedirs(mg.MLV_DIR, exist_ok=True)
+    for camera in ("Canon EOS 5D Mark III", "canon eos 7d", "Nikon D850"):          # the lookup ignores case
+        fn = os.path.join(mg.MLV_DIR, "known.mlv")
+        pix = mg.synth.mosaic(256, 192, seed=5)
+        mg.synth.write_mlv(fn, [pix], bpp=14, black=2048, white=15000, camera_name=camera)
+        lines = ["param:i-mlv:main:filename:" + fn]
+        ref = _graph_text_reference(dict(lines=lines, mlv="known"), oracle.ref_graph_describe(256, 192, lines, {}, cfg="bin/default-darkroom.i-mlv"))
+        try:
+            api.set_basedir("/root/reference/src/pipe")
+            g = api.Graph(cfg_text=MLV_CFG)
+            for ln in lines:
+                assert g.line(ln) == 0, ln
+            got = g.describe().splitlines()
+            g.close()
+        finally:
+            api.set_basedir("")
+        bad = [(a[:240], b[:240]) for a, b in zip(ref, got) if a != b]
+        assert len(ref) == len(got) and not bad, (camera, bad[:3])
+        # and it is not the identity branch
+        img = [ln for ln in got if ln.startswith("module i-mlv")][0]
+        assert "1.71665" not in img or camera == "", img[:200]

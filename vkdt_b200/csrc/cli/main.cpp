@@ -143,6 +143,7 @@ int main(int argc, char *argv[])
   }
   // frame 0 decides how many frames there are (graph-export.c:251-268: graph->frame_cnt, set by a `frames:` line or by the source)
   int frames = vkb_graph_frame_count(g);
+  vkb_graph_apply_keyframes(g);
   if(frames > 1) frame_name(g, o, 0);
   int flags0 = VKB_RUN_ALL;
   if(o.last_only && frames > 1) flags0 &= ~VKB_RUN_DOWNLOAD_SINK;
@@ -161,6 +162,7 @@ int main(int argc, char *argv[])
   std::mutex print_mtx;
   auto develop = [&](vkb_graph_t *gr, int f) {
     vkb_graph_set_frame(gr, f);
+    vkb_graph_apply_keyframes(gr);   // graph-export.c:280-283
     frame_name(gr, o, f);
     int flags = frame_flags;
     if(o.last_only && f < frames - 1) flags &= ~VKB_RUN_DOWNLOAD_SINK;
@@ -170,6 +172,8 @@ int main(int argc, char *argv[])
     if(o.progress) fprintf(stderr, "[cli] frame %d / %d\n", f + 1, frames);
     if(o.perf && !e && vkb_graph_perf(gr, buf.data(), buf.size()) > 0) fputs(buf.data(), stdout);
   };
+  if(frames > 1 && o.gpus > 1 && !o.bands && vkb_graph_has_feedback(g))
+  { fprintf(stderr, "[cli] the graph has feedback connectors (frames depend on each other): one gpu\n"); o.gpus = 1; }
   if(frames > 1 && o.gpus > 1 && !o.bands)
   { // frame parallel: frames are independent units, no exchange between the gpus.  gpu 0 keeps the graph
     // that developed frame 0; every other gpu builds its own from the same cfg (a graph belongs to one thread, graph.h:66-69)
@@ -182,7 +186,7 @@ int main(int argc, char *argv[])
       {
         if(first)
         { // this gpu's first frame builds its plan and pool
-          vkb_graph_set_frame(gr, f); frame_name(gr, o, f);
+          vkb_graph_set_frame(gr, f); vkb_graph_apply_keyframes(gr); frame_name(gr, o, f);
           int fl = VKB_RUN_ALL; if(o.last_only && f < frames - 1) fl &= ~VKB_RUN_DOWNLOAD_SINK;
           if(vkb_graph_run(gr, fl)) { std::lock_guard<std::mutex> lk(print_mtx); fprintf(stderr, "[cli] frame %d: %s\n", f, vkb_last_error()); failed = 1; }
           first = false;

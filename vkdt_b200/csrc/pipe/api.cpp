@@ -114,6 +114,8 @@ int vkb_graph_sink_device(vkb_graph_t *h, const char *inst, void **d_ptr)
   return vkb_plan_sink(h->g, m, 0, 0, d_ptr) ? vkb_set_error(VKB_ERR_GRAPH, "graph has not been run yet") : VKB_OK;
 }
 int vkb_graph_set_frame(vkb_graph_t *h, uint32_t frame) { if(!h) return VKB_ERR_BAD_ARG; h->g->frame = frame; return VKB_OK; }
+int vkb_graph_apply_keyframes(vkb_graph_t *h) { if(!h) return VKB_ERR_BAD_ARG; dt_graph_apply_keyframes(h->g); return VKB_OK; }
+int vkb_graph_has_feedback(vkb_graph_t *h) { return h ? dt_graph_has_feedback(h->g) : VKB_ERR_BAD_ARG; }
 int vkb_graph_frame_count(vkb_graph_t *h) { return h ? (int)h->g->frame_cnt : VKB_ERR_BAD_ARG; }
 int vkb_graph_run(vkb_graph_t *h, int runflags) { if(!h) return VKB_ERR_BAD_ARG; return dt_graph_run(h->g, (uint32_t)runflags); }
 int vkb_graph_perf(vkb_graph_t *h, char *buf, size_t bufsize)

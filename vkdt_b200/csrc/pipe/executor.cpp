@@ -280,6 +280,13 @@ static int build_plan(dt_graph_t *g, bool with_device)
   vkb_plan_t *p = new vkb_plan_t();
   int r = dt_graph_run_modules(g, p->modid);
   if(r) { delete p; return r; }
+  // feedback connectors read the frame before (connector.h:116, double buffering graph-run-modules.h:169-196): not built
+  for(int m : p->modid) for(int c = 0; c < g->module[m].num_connectors; c++) if(g->module[m].connector[c].flags & s_conn_feedback)
+  {
+    delete p;
+    return vkb_set_error(VKB_ERR_GRAPH, "module %s:%s reads a feedback connector: graphs that carry images from frame to frame are outside the raw->display path",
+        dt_token_string(g->module[m].name).c_str(), dt_token_string(g->module[m].inst).c_str());
+  }
   builder_t B;
   B.g = g; B.p = p;
   dt_graph_node_order(g, B.order);

@@ -226,6 +226,12 @@ int dt_module_connect(dt_graph_t *g, int m0, int c0, int m1, int c1)
   if(connection_is_cyclic(g, m0, m1)) return 12;
   return connect_generic<dt_module_t, true>(g->module, m0, c0, m1, c1);
 }
+int dt_module_feedback(dt_graph_t *g, int m0, int c0, int m1, int c1)
+{ // connector.c:30-38: connect without the cycle test (a feedback edge closes one on purpose) and flag the input
+  const int err = connect_generic<dt_module_t, true>(g->module, m0, c0, m1, c1);
+  if(!err && m1 >= 0 && c1 >= 0) g->module[m1].connector[c1].flags |= s_conn_feedback;
+  return err;
+}
 // the node layer (connector.c node flavour): wildcards on either side take the other side's channels / format
 // (connector.inc:94-106); a mismatch of declared formats is not an error here, nodes declare what they read
 int dt_node_connect(dt_graph_t *g, int n0, int c0, int n1, int c1)
@@ -363,7 +369,7 @@ static float io_float(char *&c)
   if(*e && e != c) e++;
   c = e; return r;
 }
-static int read_param_values(dt_graph_t *g, char *line, dt_token_t name, dt_token_t inst, dt_token_t parm, int beg, int end, int mode)
+static int read_param_values(dt_graph_t *g, char *line, dt_token_t name, dt_token_t inst, dt_token_t parm, int beg, int end, int mode, int frame = -1, int anim = 0)
 {
   const int modid = dt_module_get(g, name, inst);
   if(modid < 0) { fprintf(stderr, "[vkdt_b200] no such module/instance %s/%s\n", dt_token_string(name).c_str(), dt_token_string(inst).c_str()); return 1; }
@@ -375,6 +381,15 @@ static int read_param_values(dt_graph_t *g, char *line, dt_token_t name, dt_toke
   uint8_t *data = m->param + p->offset;
   if(beg < 0 || beg >= cnt || end < 0 || end > cnt) return 4;
   if(end == 0) end = cnt;
+  if(frame >= 0)
+  { // graph-io.c:56-76: the values go into a keyframe's own copy of the parameter instead (one per parameter and frame)
+    dt_keyframe_t *kf = 0;
+    for(dt_keyframe_t &k : m->keyframe) if(!kf && k.param == parm && (int)k.frame == frame) kf = &k;
+    if(!kf) { m->keyframe.push_back(dt_keyframe_t()); kf = &m->keyframe.back(); }
+    kf->frame = frame; kf->anim = anim; kf->param = parm; kf->beg = beg; kf->end = end;
+    kf->data.assign(p->def.size(), 0);   // a fresh block from the (zeroed) parameter pool
+    data = kf->data.data();
+  }
   if(p->type == dt_token("float"))
   {
     float *block = (float *)data + beg;
@@ -437,8 +452,11 @@ int dt_graph_read_config_line(dt_graph_t *g, char *c)
     if(mod0 == dt_token("-1")) modid0 = -1;
     else conid0 = dt_module_get_connector(&g->module[modid0], conn0);
     const int conid1 = dt_module_get_connector(&g->module[modid1], conn1);
-    if(cmd == dt_token("feedback")) { fprintf(stderr, "[vkdt_b200] feedback connectors carry state between frames and are outside the hot path\n"); return 1; }
-    const int err = dt_module_connect(g, modid0, conid0, modid1, conid1);
+    const int err = cmd == dt_token("feedback") ? dt_module_feedback(g, modid0, conid0, modid1, conid1) : dt_module_connect(g, modid0, conid0, modid1, conid1);
+    // graph-io.c:163-186: a feedback connection is an ordinary one flagged on its input; the traversal does not follow it
+    // (graph-traverse.inc), the data comes from the frame before.  the executor refuses to run a graph that reaches one
+    // (double buffered connectors are not built), frame parallel drivers fall back to one gpu (dt_graph_has_feedback)
+
     if(err) fprintf(stderr, "[vkdt_b200] connect %s:%s:%s -> %s:%s:%s failed: error %d\n", dt_token_string(mod0).c_str(), dt_token_string(inst0).c_str(),
         dt_token_string(conn0).c_str(), dt_token_string(mod1).c_str(), dt_token_string(inst1).c_str(), dt_token_string(conn1).c_str(), err);
     return err;
@@ -446,8 +464,68 @@ int dt_graph_read_config_line(dt_graph_t *g, char *c)
   if(cmd == dt_token("frames")) { g->frame_cnt = atol(c); return 0; }
   if(cmd == dt_token("fps"))    { g->frame_rate = atof(c); return 0; }
   if(cmd == dt_token("keyframe") || cmd == dt_token("keyframE") || cmd == dt_token("Keyframe") || cmd == dt_token("KeyframE") || cmd == dt_token("keyFRAME"))
-    return 1; // keyframes: SURVEY §8f.4, warning like any unknown line
+  { // graph-io.c:139-153, :243-247: frame:module:instance:param:beg:end:values, the spelling picks the easing
+    const int anim = cmd == dt_token("keyframe") ? s_anim_lerp : cmd == dt_token("keyframE") ? s_anim_ease_out : cmd == dt_token("Keyframe") ? s_anim_ease_in :
+                     cmd == dt_token("KeyframE") ? s_anim_smooth : s_anim_step;
+    const int frame = io_int(c);
+    const dt_token_t name = io_token(c), inst = io_token(c), parm = io_token(c);
+    const int beg = io_int(c), end = io_int(c);
+    return read_param_values(g, c, name, inst, parm, beg, end, 0, frame, anim);
+  }
   return 1;
+}
+
+static float anim_warp(float t, int mode)
+{ // anim.h:34-47
+  switch(mode)
+  {
+    default:
+    case s_anim_lerp:     return t;
+    case s_anim_step:     return t > 0.5f ? 1.0f : 0.0f;
+    case s_anim_ease_in:  return t * t * t;
+    case s_anim_ease_out: { const float t1 = 1.0f - t; return 1.0f - t1 * t1 * t1; }
+    case s_anim_smooth:   return 3.0f * t * t - 2.0f * t * t * t;
+  }
+}
+// graph.c:1025-1100: for every parameter with keyframes take the latest one at or before the current frame (the earliest if
+// all lie ahead) and, for floats, interpolate towards the next one with that keyframe's easing.  kept as the reference has it,
+// including that the sub range values are read from the start of the keyframe's block and written to the start of the parameter
+void dt_graph_apply_keyframes(dt_graph_t *g)
+{
+  for(dt_module_t &m : g->module)
+  {
+    if(!m.name || m.keyframe.empty()) continue;
+    std::vector<dt_keyframe_t> &kf = m.keyframe;
+    for(const dt_ui_param_t &p : m.so->param)
+    {
+      int ki = -1, kiM = -1;
+      for(int i = 0; i < (int)kf.size(); i++) if(kf[i].param == p.name)
+      {
+        if(ki == -1) ki = i;
+        else if(kf[ki].frame >  (int)g->frame && kf[i].frame < kf[ki].frame) ki = i;
+        else if(kf[ki].frame <= (int)g->frame && kf[i].frame <= (int)g->frame && kf[i].frame > kf[ki].frame) ki = i;
+      }
+      if(ki == -1) continue;
+      for(int i = 0; i < (int)kf.size(); i++) if(kf[i].param == p.name)
+        if(kf[i].frame > (int)g->frame && (kiM == -1 || kf[kiM].frame > kf[i].frame)) kiM = i;
+      if(kiM == ki) kiM = -1;
+      uint8_t *pdat = m.param + p.offset;
+      const uint8_t *fdat = kf[ki].data.data();
+      const size_t els = p.type == dt_token("string") ? 1 : 4;
+      if(kiM >= 0 && p.type == dt_token("float"))
+      {
+        const float t = anim_warp(((int)g->frame - kf[ki].frame) / (float)(kf[kiM].frame - kf[ki].frame), kf[kiM].anim);
+        float *dst = (float *)pdat; const float *src0 = (const float *)fdat, *src1 = (const float *)kf[kiM].data.data();
+        for(int i = kf[ki].beg; i < kf[ki].end; i++) dst[i] = t * src1[i - kf[ki].beg] + (1.0f - t) * src0[i - kf[ki].beg];
+      }
+      else memcpy(pdat, fdat + els * kf[ki].beg, els * (kf[ki].end - kf[ki].beg));
+    }
+  }
+}
+int dt_graph_has_feedback(const dt_graph_t *g)
+{
+  for(const dt_module_t &m : g->module) if(m.name) for(int c = 0; c < m.num_connectors; c++) if(m.connector[c].flags & s_conn_feedback) return 1;
+  return 0;
 }
 int dt_graph_read_config_ascii(dt_graph_t *g, const char *filename)
 {

@@ -475,6 +475,36 @@ static int imlv_open(dt_module_t *mod)
   c->filename = fname;
   return 0;
 }
+// dt_dcraw_adobe_coeff (i-mlv/adobe_coeff.h): camera name -> xyz_to_cam / 10000, from the table of the vkdt installation named
+// with vkb_set_basedir() (<basedir>/modules/i-mlv/adobe_coeff.h, parsed as text: { "name", { n, n, ... } }).  1: not found
+static int imlv_adobe_coeff(const char *name, float *xyz_to_cam)
+{
+  for(int j = 0; j < 12; j++) xyz_to_cam[j] = -1.0f;
+  if(!name[0] || basedir().empty()) return 1;
+  std::string text;
+  if(!read_text(basedir() + "/modules/i-mlv/adobe_coeff.h", &text)) return 1;
+  size_t pos = 0;
+  while((pos = text.find("{ \"", pos)) != std::string::npos)
+  {
+    const size_t n0 = pos + 3, n1 = text.find('"', n0);
+    if(n1 == std::string::npos) break;
+    pos = n1;
+    if(strcasecmp(text.substr(n0, n1 - n0).c_str(), name)) continue;
+    const size_t b0 = text.find('{', n1), b1 = text.find('}', n1);
+    if(b0 == std::string::npos || b1 == std::string::npos || b1 < b0) return 1;
+    short trans[12] = { 0 };
+    const char *c = text.c_str() + b0 + 1;
+    for(int j = 0; j < 12 && c < text.c_str() + b1; j++)
+    {
+      char *e; trans[j] = (short)strtol(c, &e, 10);
+      if(e == c) break;
+      c = e; while(*c == ',' || *c == ' ') c++;
+    }
+    for(int j = 0; j < 12; j++) xyz_to_cam[j] = (float)(trans[j] / 10000.0);
+    return 0;
+  }
+  return 1;
+}
 static void imlv_roi_out(dt_graph_t *g, dt_module_t *mod)
 {
   const int mid = (int)(mod - g->module.data());
@@ -496,16 +526,45 @@ static void imlv_roi_out(dt_graph_t *g, dt_module_t *mod)
   for(int k = 0; k < 4; k++) { ip->black[k] = b; ip->white[k] = w; ip->whitebalance[k] = 1.0f; }
   ip->filters = 0x5d5d5d5d; // i-mlv/main.c:127
   ip->crop_aabb[2] = c->width; ip->crop_aabb[3] = c->height;
-  // :165-201: camera rgb -> xyz comes from dcraw's adobe_coeff table by camera name; a camera that is not in it gets the
-  // identity there, and the matrix handed on is xyz_to_rec2020 * identity (white balance 1: the row sums of the identity).
-  // the table itself is not built here, so every clip takes that branch (a named camera is told so once).
+  // :165-201: camera rgb -> xyz comes from dcraw's adobe_coeff table by camera name (xyz_to_cam, inverted); a camera that is
+  // not in it gets the identity, the white balance is the row sums of cam_to_xyz normalised to green, and the matrix handed on
+  // is xyz_to_rec2020 * cam_to_xyz.  the table is the vkdt installation's own file (imlv_adobe_coeff below): without a
+  // basedir every clip takes the identity branch (a named camera is told so once).
   static const float xyz_to_rec2020[9] = {
      1.7166511880f, -0.3556707838f, -0.2533662814f,
     -0.6666843518f,  1.6164812366f,  0.0157685458f,
      0.0176398574f, -0.0427706133f,  0.9421031212f };
-  for(int k = 0; k < 9; k++) ip->cam_to_rec2020[k] = xyz_to_rec2020[k];
+  float xyz_to_cam[12], mat[9] = { 0 };
+  const int unknown = imlv_adobe_coeff(c->camera_name, xyz_to_cam);
+  if(unknown) mat[0] = mat[4] = mat[8] = 1.0f;
+  else
+  { // core/mat3.h:21-46 mat3inv, operation for operation
+    const float *A = xyz_to_cam;
+#define A_(y, x) A[(y - 1) * 3 + (x - 1)]
+    const float det = A_(1, 1) * (A_(3, 3) * A_(2, 2) - A_(3, 2) * A_(2, 3)) - A_(2, 1) * (A_(3, 3) * A_(1, 2) - A_(3, 2) * A_(1, 3)) + A_(3, 1) * (A_(2, 3) * A_(1, 2) - A_(2, 2) * A_(1, 3));
+    if(!(det > -1e-7f && det < 1e-7f))
+    {
+      const float idet = 1.f / det;
+      mat[0] =  idet * (A_(3, 3) * A_(2, 2) - A_(3, 2) * A_(2, 3)); mat[1] = -idet * (A_(3, 3) * A_(1, 2) - A_(3, 2) * A_(1, 3)); mat[2] =  idet * (A_(2, 3) * A_(1, 2) - A_(2, 2) * A_(1, 3));
+      mat[3] = -idet * (A_(3, 3) * A_(2, 1) - A_(3, 1) * A_(2, 3)); mat[4] =  idet * (A_(3, 3) * A_(1, 1) - A_(3, 1) * A_(1, 3)); mat[5] = -idet * (A_(2, 3) * A_(1, 1) - A_(2, 1) * A_(1, 3));
+      mat[6] =  idet * (A_(3, 2) * A_(2, 1) - A_(3, 1) * A_(2, 2)); mat[7] = -idet * (A_(3, 2) * A_(1, 1) - A_(3, 1) * A_(1, 2)); mat[8] =  idet * (A_(2, 2) * A_(1, 1) - A_(2, 1) * A_(1, 2));
+    }
+#undef A_
+  }
+  const double cam_to_xyz[9] = { mat[0], mat[1], mat[2], mat[3], mat[4], mat[5], mat[6], mat[7], mat[8] };
+  ip->whitebalance[0] = (float)(cam_to_xyz[0] + cam_to_xyz[1] + cam_to_xyz[2]);
+  ip->whitebalance[1] = (float)(cam_to_xyz[3] + cam_to_xyz[4] + cam_to_xyz[5]);
+  ip->whitebalance[2] = (float)(cam_to_xyz[6] + cam_to_xyz[7] + cam_to_xyz[8]);
+  ip->whitebalance[0] /= ip->whitebalance[1];
+  ip->whitebalance[2] /= ip->whitebalance[1];
+  ip->whitebalance[1]  = 1.0f;
+  float cam_to_rec2020[9] = { 0.0f };
+  for(int j = 0; j < 3; j++) for(int i = 0; i < 3; i++) for(int k = 0; k < 3; k++)
+    cam_to_rec2020[3 * j + i] += xyz_to_rec2020[3 * j + k] * cam_to_xyz[3 * k + i];
+  for(int k = 0; k < 9; k++) ip->cam_to_rec2020[k] = cam_to_rec2020[k];
   static int told = 0;
-  if(c->camera_name[0] && !told++) fprintf(stderr, "[i-mlv] no colour matrix table: `%s' is developed with camera rgb = xyz\n", c->camera_name);
+  if(unknown && c->camera_name[0] && basedir().empty() && !told++)
+    fprintf(stderr, "[i-mlv] no vkdt installation named (vkb_set_basedir): `%s' is developed with camera rgb = xyz\n", c->camera_name);
   ip->noise_a = 1.0f; ip->noise_b = 1.0f; // :140-141; the nprof lookup is outside the hot path
   snprintf(ip->model, sizeof(ip->model), "%s", c->camera_name);
   snprintf(ip->maker, sizeof(ip->maker), "%s", c->camera_name);

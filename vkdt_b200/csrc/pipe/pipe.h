@@ -118,6 +118,10 @@ struct dt_ui_param_t
   std::vector<uint8_t> def;   // default value blob
 };
 
+// module.h dt_keyframe_t: a parameter (or the sub range [beg, end) of it) pinned at a frame, anim.h: how to get there
+struct dt_keyframe_t { int frame; int anim; dt_token_t param; int beg, end; std::vector<uint8_t> data; };
+enum { s_anim_lerp = 0, s_anim_step = 1, s_anim_ease_in = 2, s_anim_ease_out = 3, s_anim_smooth = 4 };
+
 struct dt_graph_t;
 struct dt_module_t;
 struct dt_node_t;
@@ -160,6 +164,7 @@ struct dt_module_t
   uint32_t flags;
   void    *data;
   float    gui_x, gui_y;
+  std::vector<dt_keyframe_t> keyframe;
 };
 
 // node.h:19-52
@@ -220,6 +225,8 @@ int  dt_graph_read_config_ascii(dt_graph_t *g, const char *filename);
 int  dt_graph_replace_display(dt_graph_t *g, dt_token_t inst, dt_token_t mod, int prim, int trc);
 void dt_graph_disconnect_display_modules(dt_graph_t *g);
 int  dt_graph_run(dt_graph_t *g, uint32_t runflags);
+void dt_graph_apply_keyframes(dt_graph_t *g);           // graph.c:1025
+int  dt_graph_has_feedback(const dt_graph_t *g);         // any connector flagged s_conn_feedback: frames depend on each other
 std::string dt_graph_dump_nodes(dt_graph_t *g);
 std::string dt_graph_describe(dt_graph_t *g, const std::vector<int> &modid);
 
