@@ -112,6 +112,30 @@ VKB_API int  vkb_set_basedir(const char *dir);
  * "param name:type:cnt:offset:<default value blob, hex>" lines.  host only. */
 VKB_API int  vkb_module_describe(const char *name, char *buf, size_t bufsize);
 
+/* ---- module authors (src/pipe/modules/api.h, the dlopen'd lib<name>.so of src/pipe/global.c:106-119) ----
+ * a module outside this library = the text of its `connectors` and `params` files + one kernel per node.  modules registered
+ * this way get the reference's default callbacks (graph-run-modules.h:65-107, :289-322, :456-490): one node (name, "main")
+ * with the module's connectors copied 1:1, dispatched over the `output` connector's size, output roi = input roi; the raw
+ * parameter block is what the kernel receives as `params`.  (modules with their own create_nodes / commit_params / roi
+ * callbacks are the ones compiled into this library; their C++ side mirrors api.h: dt_node_add, dt_connector_copy,
+ * dt_connector_bypass, dt_node_connect in csrc/pipe/pipe.h.)
+ * the kernel is a host function that launches CUDA work on args->stream and returns 0: the same contract as this library's
+ * own launchers (csrc/vkb_internal.h), images in connector order, asynchronous.  band_y0 / band_y1 >= 0 only ever reach
+ * kernels the band split knows (never a caller's).  mode: VKB_MODE_STRICT, VKB_MODE_FAST or -1 for both.
+ * register before creating the graphs that use the module. */
+typedef struct vkb_kernel_args_t
+{
+  uint32_t wd, ht, dp;                         /* the node's dispatch extent */
+  const void *push;   uint32_t push_size;      /* push constants (none for default nodes) */
+  const void *params; uint32_t params_size;    /* the module's parameter block */
+  const vkb_image_t *conn; uint32_t num_conn;  /* connector images in connector order (device pointers) */
+  void *stream;                                /* cudaStream_t */
+  int32_t band_y0, band_y1;                    /* -1 */
+} vkb_kernel_args_t;
+typedef int (*vkb_kernel_fn_t)(const vkb_kernel_args_t *);
+VKB_API int  vkb_register_module(const char *name, const char *connectors, const char *params);
+VKB_API int  vkb_register_kernel(const char *name, const char *kernel, vkb_kernel_fn_t fn, int mode);
+
 /* ---- 3. graph ---- */
 typedef struct vkb_graph_t vkb_graph_t;
 

@@ -34,6 +34,10 @@ def run(n, direction, mb=512, reps=8, pin_numa=True):
         pass
     barrier = threading.Barrier(n + 1)
     times = [0.0] * n
+    # second buffer pair and stream per gpu for the simultaneous opposite direction, allocated before anything is timed
+    bufs2 = [torch.empty(mb << 20, dtype=torch.uint8).pin_memory() for _ in range(n)] if direction == "both" else []
+    devs2 = [torch.empty(mb << 20, dtype=torch.uint8, device="cuda:%d" % d) for d in range(n)] if direction == "both" else []
+    streams2 = [torch.cuda.Stream(device=d) for d in range(n)] if direction == "both" else []
 
     def work(d):
         torch.cuda.set_device(d)
@@ -41,23 +45,22 @@ def run(n, direction, mb=512, reps=8, pin_numa=True):
         with torch.cuda.stream(s):
             for _ in range(2):
                 bufs[d].copy_(devs[d], non_blocking=True)
-            s.synchronize()
-            barrier.wait()
-            t0 = time.time()
-            for _ in range(reps):
+        s.synchronize()
+        barrier.wait()
+        t0 = time.time()
+        for _ in range(reps):
+            with torch.cuda.stream(s):
                 if direction in ("d2h", "both"):
                     bufs[d].copy_(devs[d], non_blocking=True)
-                if direction in ("h2d",):
+                if direction == "h2d":
                     devs[d].copy_(bufs[d], non_blocking=True)
             if direction == "both":
-                s2 = torch.cuda.Stream(device=d)
-                with torch.cuda.stream(s2):
-                    d2 = torch.empty_like(devs[d]); h2 = torch.empty(mb << 20, dtype=torch.uint8).pin_memory()
-                    for _ in range(reps):
-                        d2.copy_(h2, non_blocking=True)
-                s2.synchronize()
-            s.synchronize()
-            times[d] = time.time() - t0
+                with torch.cuda.stream(streams2[d]):
+                    devs2[d].copy_(bufs2[d], non_blocking=True)
+        s.synchronize()
+        if direction == "both":
+            streams2[d].synchronize()
+        times[d] = time.time() - t0
 
     th = [threading.Thread(target=work, args=(d,)) for d in range(n)]
     for t in th:

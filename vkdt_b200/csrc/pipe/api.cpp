@@ -228,6 +228,18 @@ int vkb_graph_band_stats(vkb_graph_t *h, uint64_t *bytes_total, uint64_t *bytes_
 { if(!h) return VKB_ERR_BAD_ARG; return vkb_plan_band_stats(h->g, bytes_total, bytes_max_device, pulls, launches) ? vkb_set_error(VKB_ERR_GRAPH, "no band split planned") : VKB_OK; }
 int vkb_graph_band_mark(vkb_graph_t *h, int which) { if(!h) return VKB_ERR_BAD_ARG; return vkb_plan_band_mark(h->g, which); }
 int vkb_graph_band_elapsed_ms(vkb_graph_t *h, float *ms) { if(!h || !ms) return VKB_ERR_BAD_ARG; return vkb_plan_band_elapsed(h->g, ms); }
+int vkb_register_module(const char *name, const char *connectors, const char *params)
+{
+  if(dt_pipe_register_module(name, connectors, params)) return vkb_set_error(VKB_ERR_BAD_ARG, "module name (1..8 chars) and connectors are needed");
+  return VKB_OK;
+}
+int vkb_register_kernel(const char *name, const char *kernel, vkb_kernel_fn_t fn, int mode)
+{
+  if(!name || !kernel || !fn || mode > VKB_MODE_FAST) return VKB_ERR_BAD_ARG;
+  if(mode < 0) { vkb_register_kernel(name, kernel, (vkb_kernel_fn)fn, VKB_MODE_STRICT); vkb_register_kernel(name, kernel, (vkb_kernel_fn)fn, VKB_MODE_FAST); }
+  else vkb_register_kernel(name, kernel, (vkb_kernel_fn)fn, mode);
+  return VKB_OK;
+}
 int vkb_set_basedir(const char *dir) { return dt_pipe_set_basedir(dir); }
 int vkb_module_describe(const char *name, char *buf, size_t bufsize)
 {

@@ -174,6 +174,17 @@ static bool read_text(const std::string &fn, std::string *out)
   return true;
 }
 static std::vector<dt_module_so_t> &registry_storage() { static std::vector<dt_module_so_t> r; return r; }
+// modules registered by a caller (vkb_register_module): name, connectors, params as the text of the reference's module files
+struct external_module_t { std::string name, connectors, params; };
+static std::vector<external_module_t> &external_modules() { static std::vector<external_module_t> e; return e; }
+int dt_pipe_register_module(const char *name, const char *connectors, const char *params)
+{
+  if(!name || !name[0] || strlen(name) > 8 || !connectors) return 1;
+  for(external_module_t &e : external_modules()) if(e.name == name) { e.connectors = connectors; e.params = params ? params : ""; registry_storage().clear(); return 0; }
+  external_modules().push_back(external_module_t{ name, connectors, params ? params : "" });
+  registry_storage().clear();   // rebuilt at the next lookup
+  return 0;
+}
 static std::vector<std::string> &registry_strings() { static std::vector<std::string> s; return s; }
 int dt_pipe_set_basedir(const char *dir)
 { // takes effect for graphs created afterwards
@@ -216,6 +227,12 @@ static std::vector<dt_module_so_t> &registry()
       }
       closedir(dp);
     }
+  }
+  for(const external_module_t &e : external_modules())
+  { // a caller's module replaces a built-in of the same name
+    bool replaced = false;
+    for(module_def_t &d : defs) if(e.name == d.name) { d.connectors = e.connectors.c_str(); d.params = e.params.c_str(); replaced = true; }
+    if(!replaced) defs.push_back(module_def_t{ e.name.c_str(), e.connectors.c_str(), e.params.c_str() });
   }
   for(const module_def_t &d : defs)
   {

@@ -231,6 +231,7 @@ std::string dt_graph_dump_nodes(dt_graph_t *g);
 std::string dt_graph_describe(dt_graph_t *g, const std::vector<int> &modid);
 
 dt_module_so_t *dt_module_so_get(dt_token_t name);   // registry (global.c:442)
+int dt_pipe_register_module(const char *name, const char *connectors, const char *params); // a caller's module (vkb_register_module)
 int dt_pipe_set_basedir(const char *dir);            // <basedir>/modules/<name>/{connectors,params} override the built-in tables
 int dt_module_so_describe(dt_token_t name, std::string *text); // connectors and params of a registered module, in the files' grammar
 

@@ -145,3 +145,8 @@ uint64_t vkb_launch_count(void) { return g_launches.load(); }
 void vkb_launch_count_reset(void) { g_launches.store(0); }
 
 } // extern "C"
+
+// a caller's kernel (vkb_register_kernel) sees the launch through the public struct: same layout as the internal one
+static_assert(sizeof(vkb_kernel_args_t) == sizeof(vkb_launch_t) && offsetof(vkb_kernel_args_t, stream) == offsetof(vkb_launch_t, stream) &&
+              offsetof(vkb_kernel_args_t, band_y0) == offsetof(vkb_launch_t, band_y0) && offsetof(vkb_kernel_args_t, conn) == offsetof(vkb_launch_t, conn),
+              "vkb_kernel_args_t and vkb_launch_t have to agree");
