@@ -164,7 +164,7 @@ def ncu_traffic(label, key="bytes_per_launch"):
 
 
 def run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, src, bpp, strength, steps, warmup, sample_clocks=True,
-                 mode=0, e2e=True, sink8=False):
+                 mode=0, e2e=True, sink8=False, gloo=None):
     """both legs (kernel path with HBM-resident input, end to end with host buffers) of one workload on this rank.
     mode: api.MODE_STRICT (the headline) or api.MODE_FAST; e2e=False: kernel leg only."""
     # ---- synthetic input: a few distinct stills per rank, cycled (deterministic seeds per SURVEY §8d) ----
@@ -282,6 +282,15 @@ def run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, s
         dist.barrier()
     torch.cuda.synchronize()
     e2e_steps = max(4, min(steps, 12 if out_bytes > 400e6 else 200))
+    # the job: a sequence of world * e2e_steps frames (stills), frame f on rank f mod world (vkdt_b200/shard.py), every rank
+    # keeps a small record per frame it developed, rank 0 gathers them in frame order afterwards: no data-path collective
+    from vkdt_b200 import shard
+    my_frames = shard.frames_for_rank(world * e2e_steps, rank, world)
+    records = {}
+
+    def landed(i):      # frame my_frames[i] is in host memory: note its first bytes
+        records[my_frames[i]] = bytes((api.C.c_uint8 * 16).from_address(host_out[i % NG]))
+
     f0, f1 = api.Event(), api.Event()
     t0 = time.time()
     f0.record(gs[0].stream())
@@ -289,10 +298,13 @@ def run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, s
         gk = gs[i % NG]
         if i >= NG:
             gk.run(api.RUN_WAIT)          # frame i-NG has fully landed in host memory before its buffers are reused
-        gk.set_source(host_in[i % nstills], rp)
+            landed(i - NG)
+        gk.set_source(host_in[my_frames[i] % nstills], rp)
         gk.run(FE)
     for k in range(NG):
-        gs[k].run(api.RUN_WAIT)
+        gs[(e2e_steps + k) % NG].run(api.RUN_WAIT)
+        if e2e_steps - NG + k >= 0:
+            landed(e2e_steps - NG + k)
     t_wall_ms = (time.time() - t0) * 1e3
     f1.record(gs[0].stream())
     f1.sync()
@@ -302,6 +314,8 @@ def run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, s
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e_ms = float(t.item())
     checksum = float(np.frombuffer((api.C.c_uint8 * 16).from_address(host_out[(e2e_steps - 1) % NG]), dtype=np.uint8 if sink8 else np.float32).sum())
+    gathered = shard.gather_in_frame_order(records, world * e2e_steps, rank, world, group=gloo)   # rank 0: every frame, in order
+    frames_gathered = len(gathered) if gathered is not None else 0
 
     for hp in host_in + host_out:
         api.host_free(hp)
@@ -310,7 +324,7 @@ def run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, s
     for gk in gs + [g]:
         gk.close()
     return dict(t_kernel_ms=t_kernel_ms, t_e2e_ms=t_e2e_ms, e2e_steps=e2e_steps, launches=launches, per_kernel=per_kernel, clocks=clocks,
-                in_bytes=in_bytes, out_bytes=out_bytes, ow=ow, oh=oh, pool_bytes=pool_bytes, checksum=checksum, nstills=nstills)
+                in_bytes=in_bytes, out_bytes=out_bytes, ow=ow, oh=oh, pool_bytes=pool_bytes, checksum=checksum, nstills=nstills, frames_gathered=frames_gathered)
 
 
 
@@ -491,7 +505,7 @@ def main():
         return 0
 
     mlv_W, mlv_H, mlv_src, mlv_bpp = WORKLOADS["mlv4k"]
-    R = run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, src, bpp, strength, args.steps, args.warmup, mode=mode)
+    R = run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, src, bpp, strength, args.steps, args.warmup, mode=mode, gloo=gloo)
     # the other build of the kernels, kernel path only, for the record
     other = api.MODE_STRICT if mode == api.MODE_FAST else api.MODE_FAST
     F = run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, src, bpp, strength, max(4, min(args.steps, 10)), 3,
@@ -499,14 +513,14 @@ def main():
     M = None
     if args.workload != "mlv4k" and not args.no_mlv:
         M = run_workload(api, synth, torch, dist, args, rank, world, local_rank, mlv_W, mlv_H, mlv_src, mlv_bpp, strength,
-                         max(40, min(10 * args.steps, 200)), 3, sample_clocks=False, mode=mode)
+                         max(40, min(10 * args.steps, 200)), 3, sample_clocks=False, mode=mode, gloo=gloo)
     M8 = S8 = None
     if not args.no_mlv:
         if args.workload != "mlv4k":
             M8 = run_workload(api, synth, torch, dist, args, rank, world, local_rank, mlv_W, mlv_H, mlv_src, mlv_bpp, strength,
-                              max(40, min(10 * args.steps, 200)), 3, sample_clocks=False, mode=mode, sink8=True)
+                              max(40, min(10 * args.steps, 200)), 3, sample_clocks=False, mode=mode, sink8=True, gloo=gloo)
         S8 = run_workload(api, synth, torch, dist, args, rank, world, local_rank, W, H, src, bpp, strength, max(4, min(args.steps, 10)), 3,
-                          sample_clocks=False, mode=mode, sink8=True)
+                          sample_clocks=False, mode=mode, sink8=True, gloo=gloo)
     Bd = None
     if world > 1 and not args.no_bands:
         # config 5 rides along in the scaling runs: one 201 MP still over all the GPUs of the box, driven by rank 0
@@ -538,7 +552,8 @@ def main():
     roof = {"bound": "hbm", "kernel": top_label, "achieved": round(achieved, 1), "peak": pk["hbm_gbs"], "peak_kind": pk_kind + " copy bandwidth",
             "unit": "GB/s", "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": ncu_traffic(top_label),
             "sm_issue_pct": ncu_traffic(top_label, "sm_issue_pct"),
-            "note": "instruction bound, not HBM bound: see sm_issue_pct (ncu smsp__issue_active of this kernel) and DESIGN.md section 3",
+            "note": "instruction bound, not HBM bound: see sm_issue_pct (ncu smsp__issue_active of this kernel) and DESIGN.md section 3; the strict build spends its "
+                    "issue slots on libm-exact exp / pow in fp64 (profiles/r02_summary.md)",
             "algorithmic_bytes_per_launch": top_bytes, "avg_launch_ms": round(top_ms, 4),
             "share_of_step": round(top_ms / total_ms, 4),
             "graph": {"algorithmic_bytes_per_step": graph_alg_bytes, "achieved_gbs": round(graph_alg_bytes / (t_kernel_ms / args.steps * 1e-3) / 1e9, 1),
@@ -555,14 +570,19 @@ def main():
                    "timing": "inputs and intermediates (%.0f MB pool) exceed the 126 MB L2; %d distinct stills cycled" % (R["pool_bytes"] / 1e6, nstills),
                    "parallelism": "independent stills per GPU, no collective"},
         "e2e": {"value": round(world * e2e_steps * mp / (t_e2e_ms * 1e-3), 2), "unit": "MP/s", "h2d_bytes_per_step": in_bytes,
-                "d2h_bytes_per_step": out_bytes, "ms_per_step": round(t_e2e_ms / e2e_steps, 3), "steps": e2e_steps, "checksum": checksum},
+                "d2h_bytes_per_step": out_bytes, "ms_per_step": round(t_e2e_ms / e2e_steps, 3), "steps": e2e_steps, "checksum": checksum,
+                "frames_gathered_in_order": R["frames_gathered"]},
         "gpu_launches": int(launches) * world, "launches_per_step": int(launches // max(1, args.steps)),  # every rank launches the same sequence
         "clocks": clocks, "roofline": roof, "pool_bytes": R["pool_bytes"],
     }
     other_name = "strict" if args.mode == "fast" else "fast"
     fsteps = max(4, min(args.steps, 10))
+    ftop_label, (ftop_sum, ftop_n, ftop_bytes) = max(F["per_kernel"].items(), key=lambda kv: kv[1][0])
+    ftop_ms = ftop_sum / ftop_n
     line[other_name] = {"what": "the same kernel path with the %s build of the kernels" % other_name,
                         "value": round(world * fsteps * mp / (F["t_kernel_ms"] * 1e-3), 2), "unit": "MP/s", "ms_per_step": round(F["t_kernel_ms"] / fsteps, 4),
+                        "roofline": {"bound": "hbm", "kernel": ftop_label, "achieved": round(ftop_bytes / (ftop_ms * 1e-3) / 1e9, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                     "frac": round(ftop_bytes / (ftop_ms * 1e-3) / 1e9 / pk["hbm_gbs"], 4), "algorithmic_bytes_per_launch": ftop_bytes, "avg_launch_ms": round(ftop_ms, 4)},
                         "kernels": {k: round(v[0] / v[1], 4) for k, v in sorted(F["per_kernel"].items(), key=lambda kv: -kv[1][0])[:8]}}
     if Bd:
         line["bands"] = Bd

@@ -17,8 +17,9 @@ def graph_is_frame_parallel(cfg_text):
     return not any(l.startswith("feedback:") for l in cfg_text.splitlines())
 
 
-def gather_in_frame_order(local, n_frames, rank=None, world=None, dst=0):
-    """local: {frame: small record}.  returns the list of records in frame order on rank `dst`, None elsewhere."""
+def gather_in_frame_order(local, n_frames, rank=None, world=None, dst=0, group=None):
+    """local: {frame: small record}.  returns the list of records in frame order on rank `dst`, None elsewhere.
+    group: a process group for the (host side) gather, e.g. a gloo group next to an nccl default group."""
     if world is None:
         world = dist.get_world_size() if dist.is_initialized() else 1
     if rank is None:
@@ -26,7 +27,7 @@ def gather_in_frame_order(local, n_frames, rank=None, world=None, dst=0):
     if world == 1:
         return [local[f] for f in range(n_frames)]
     parts = [None] * world if rank == dst else None
-    dist.gather_object(local, parts, dst=dst)
+    dist.gather_object(local, parts, dst=dst, group=group)
     if rank != dst:
         return None
     merged = {}
