@@ -2,7 +2,7 @@
 //   libm_exact_check <stride> <pow_pairs>     every stride-th float bit pattern for expf/exp2f/logf/log2f (1 = all 2^32),
 //                                            pow_pairs random (x, y) pairs + structured pairs for powf
 // prints the number of mismatching results per function (NaNs compare equal when both are NaN); exit code 1 on any.
-// build: gcc -O2 -mfma -ffp-contract=off -fopenmp libm_exact_check.c -lm   (test infrastructure, not product)
+// build: g++ -x c++ -std=c++17 -O2 -mfma -ffp-contract=off -fopenmp libm_exact_check.c -lm   (test infrastructure, not product)
 #include "../../vkdt_b200/csrc/kernels/libm_exact.h"
 #include <stdio.h>
 #include <stdlib.h>

@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(256, 5) k_denoise_downcov(const uint2 *__restr
   __shared__ float4 tinv[DC_H][DC_W];  // lum, 1/lum | lum*lum, 1/(lum*lum): every tap's divisions, done once per input texel
   const int tx0 = blockIdx.x * 32 - 2, ty0 = BAND_BY * 8 - 2;
   const int tid = threadIdx.y * 32 + threadIdx.x;
+  LME_SMEM_STAGE(tid);
   for(int t = tid; t < DC_W * DC_H; t += 256)
   {
     const int r = t / DC_W, c = t - r * DC_W;
@@ -173,20 +174,26 @@ __global__ void __launch_bounds__(256, 5) k_denoise_downcov(const uint2 *__restr
     }
   }
 #else
-  // cov.glsl:116-133 tap for tap: rotate the offset into the eigenbasis, libm's exponential, unfused accumulation
-#pragma unroll 1
-  for(int j = 0; j < 5; j++)
-  {
-    const float fj = (float)(j - 2);
+  // cov.glsl:116-133: rotate the offset into the eigenbasis, libm's exponential, unfused accumulation in the shader's tap
+  // order.  the weight of tap (i, j) is that of tap (-i, -j) bit for bit (every operation on the way is odd or even in the
+  // offset, nan included), so 13 exponentials serve the 25 taps; the two divisors are the pixel's: div_rd
+  const double rde0 = rcp_dn(e0), rde1 = rcp_dn(e1);   // both clamped to [0.01, 25]
+  float wq[13];
 #pragma unroll
-    for(int i = 0; i < 5; i++)
+  for(int k = 0; k < 13; k++)
+  {
+    const float fi = (float)(k % 5 - 2), fj = (float)(k / 5 - 2);
+    const float x0 = fi * v0x + fj * v0y;
+    const float x1 = fi * v1x + fj * v1y;
+    wq[k] = fmaxf(1e-9f, m_exp_s(-0.5f * (div_rd(x0, rde0) * x0 + div_rd(x1, rde1) * x1), lme_ctx));
+  }
+#pragma unroll
+  for(int k = 0; k < 25; k++)
+  {
+    const float4 t = tile[ly + k / 5][lx + k % 5];
+    const float wgt = wq[k < 13 ? k : 24 - k];
+    if(!(t.x > 2.0f * mean_b)) // hot pixels get no weight
     {
-      const float fi = (float)(i - 2);
-      const float4 t = tile[ly + j][lx + i];
-      if(t.x > 2.0f * mean_b) continue; // hot pixels
-      const float x0 = fi * v0x + fj * v0y;
-      const float x1 = fi * v1x + fj * v1y;
-      const float wgt = fmaxf(1e-9f, m_exp(-0.5f * (x0 / e0 * x0 + x1 / e1 * x1)));
       r += wgt * t.x; g += wgt * t.y; b += wgt * t.z;
       wt += wgt;
     }
@@ -197,13 +204,19 @@ __global__ void __launch_bounds__(256, 5) k_denoise_downcov(const uint2 *__restr
   edge = smoothstepf(0.4f, 0.75f, edge);
   edge = clampf(0.02f + edge, 0.0f, 1.0f);
   int ox, oy; swizzle(x, y, w, h, ox, oy);
+#if VKB_FAST
   st_rgba(out, w, ox, oy, make_float4(r / iw_, g / iw_, b / iw_, edge));
+#else
+  const double riw = rcp_dn(iw_);   // >= 1e-8
+  st_rgba(out, w, ox, oy, make_float4(div_rd(r, riw), div_rd(g, riw), div_rd(b, riw), edge));
+#endif
 }
 
 #define DN_F02 0.20000004768371582f
 #define DN_F04 0.3999999761581421f
 // x^0.8 on the SFU (fast): ~1e-6 relative, i.e. <= 1e-4 in the [0,1] edge weight even at the 1e-3 noise floor of noise.glsl
 VKB_DEV float gamma08(float f) { return f < 0.0f ? f : m_pow(f, 0.8f); }
+VKB_DEV float gamma08(float f, const lme_ctx_t &L) { return f < 0.0f ? f : m_pow_s(f, 0.8f, L); }
 
 // ---- down: levels 1..3, 5 tap flower with edge stopping (down.comp:59-107) ----
 __global__ void __launch_bounds__(256) k_denoise_down(const uint2 *__restrict__ in, int w, int h, uint2 *__restrict__ out,
@@ -258,9 +271,10 @@ VKB_DEV float4 unpack_rgba(uint2 v)
   return make_float4(a.x, a.y, b.x, b.y);
 }
 __global__ void __launch_bounds__(256, 6) k_denoise_down_tiled(const uint2 *__restrict__ in, int w, int h, uint2 *__restrict__ out,
-    denoise_params_t p, float black, float white, float noise_a, float noise_b, float lv, float blk, const band_t bd)
+    denoise_params_t p, float black, float white, float noise_a, float noise_b, float lv, float blk, double rd_wb, double rd_blk, const band_t bd)
 {
   __shared__ uint2 tile[DD_H][DD_W];
+  LME_SMEM_STAGE(threadIdx.y * 32 + threadIdx.x);
   const int tx0 = blockIdx.x * 32 - 2, ty0 = BAND_BY * 8 - 2;
   // thread (tx, ty) stages rows ty, ty + 8 and columns tx, tx + 32 of the window: no division, one mirror per row / column
   {
@@ -282,15 +296,27 @@ __global__ void __launch_bounds__(256, 6) k_denoise_down_tiled(const uint2 *__re
   const float t = 0.2f;
   const float4 c0 = unpack_rgba(tile[ly][lx]);
   float sigma[3], sum[3], wgt[3], wc[3], g0[3];
+#if VKB_FAST
   noise_sigma(noise_a, noise_b, black, white, p.edges, c0.x, sigma);
+#else
+  { // noise_sigma() with its quotient by the launch constant (white - black) through div_rd
+    const float s = sqrtf(noise_a + fmaxf(0.0f, div_rd(c0.x - black, rd_wb)) * noise_b);
+#pragma unroll
+    for(int k = 0; k < 3; k++) sigma[k] = clampf(p.edges[k] * s, 1e-3f, 1e3f);
+  }
+#endif
   const float cc[3] = { c0.x, c0.y, c0.z };
 #pragma unroll
   for(int k = 0; k < 3; k++)
   {
     sum[k] = t * cc[k]; wgt[k] = t;
+#if VKB_FAST
     sigma[k] = lv * sigma[k] / blk;
+#else
+    sigma[k] = div_rd(lv * sigma[k], rd_blk);
+#endif
     wc[k] = 1.0f / sigma[k];
-    g0[k] = gamma08(cc[k]);
+    g0[k] = gamma08(cc[k], lme_ctx);
   }
   constexpr int   bx[4] = { 1, -2, 0, -1 }, by[4] = { 0, -1, -2, 1 };
   constexpr float ax[4] = { DN_F02, 0.8f, DN_F04, 0.6f }, ay[4] = { DN_F04, 0.6f, 0.8f, DN_F02 };
@@ -306,7 +332,7 @@ __global__ void __launch_bounds__(256, 6) k_denoise_down_tiled(const uint2 *__re
 #pragma unroll
     for(int k = 0; k < 3; k++)
     {
-      const float e = clampf(1.0f - 0.5f * (wc[k] * fabsf(gamma08(c[k]) - g0[k])), 0.0f, 1.0f);
+      const float e = clampf(1.0f - 0.5f * (wc[k] * fabsf(gamma08(c[k], lme_ctx) - g0[k])), 0.0f, 1.0f);
       const float ww = e * (1.0f - t) / 4.0f;
       sum[k] += ww * c[k];
       wgt[k] += ww;
@@ -317,7 +343,8 @@ __global__ void __launch_bounds__(256, 6) k_denoise_down_tiled(const uint2 *__re
 }
 
 struct asm_consts_t { float rgb_to_yuv[9], yuv_to_rgb[9]; float wb[3], black[3], white[3]; float noise_a, noise_b, blk, thrs0, i2thrs0; float inorm[3], denorm[3];
-                      float bb[4], ibb[4]; }; // 0.7^(l+1) / blk and its reciprocal: launch constants, evaluated on the host
+                      float bb[4], ibb[4];   // 0.7^(l+1) / blk and its reciprocal: launch constants, evaluated on the host
+                      double rd_wb[3], rd_wbal[3], rd_2t0, rd_2t1; }; // strict, for div_rd: 1 / (white - black), 1 / wb, 1 / (2 thrs0), 1 / (2 * 10000)
 
 // ---- assemble: wavelet shrinkage over the 4 detail bands (assemble.comp:43-165) ----
 __global__ void __launch_bounds__(256, 5) k_denoise_assemble(const uint2 *__restrict__ s0, const uint2 *__restrict__ s1, const uint2 *__restrict__ s2,
@@ -340,7 +367,15 @@ __global__ void __launch_bounds__(256, 5) k_denoise_assemble(const uint2 *__rest
     d[l][0] = v.x; d[l][1] = v.y; d[l][2] = v.z;
   }
   float sigma[3];
+#if VKB_FAST
   noise_sigma(K.noise_a, K.noise_b, K.black[1], K.white[1], p.edges, fmaxf(d[2][0], 0.0f), sigma);
+#else
+  { // noise_sigma() with its quotient by the launch constant (white - black) through div_rd
+    const float sq = sqrtf(K.noise_a + fmaxf(0.0f, div_rd(fmaxf(d[2][0], 0.0f) - K.black[1], K.rd_wb[1])) * K.noise_b);
+#pragma unroll
+    for(int k = 0; k < 3; k++) sigma[k] = clampf(p.edges[k] * sq, 1e-3f, 1e3f);
+  }
+#endif
   const float bb[4] = { K.bb[0], K.bb[1], K.bb[2], K.bb[3] };
 #if VKB_FAST
   const float isig[3] = { __frcp_rn(sigma[0]), __frcp_rn(sigma[1]), __frcp_rn(sigma[2]) };
@@ -379,7 +414,7 @@ __global__ void __launch_bounds__(256, 5) k_denoise_assemble(const uint2 *__rest
 #if VKB_FAST
       const float tt = fminf(1.0f, a * i2t);
 #else
-      const float tt = fminf(1.0f, a / (2.0f * thrs));
+      const float tt = fminf(1.0f, div_rd(a, big ? K.rd_2t1 : K.rd_2t0));   // a / (2.0f * thrs)
 #endif
       down4[k] += sigma[k] * bb[l] * signf(d[l][k]) * mixf(fmaxf(a - thrs, 0.0f), a, tt);
     }
@@ -393,8 +428,8 @@ __global__ void __launch_bounds__(256, 5) k_denoise_assemble(const uint2 *__rest
     v[k]  = (down4[k] - K.black[k]) * K.inorm[k];
     vo[k] = (og[k]    - K.black[k]) * K.inorm[k];
 #else
-    v[k]  = (down4[k] - K.black[k]) / (K.white[k] - K.black[k]) * K.wb[k];
-    vo[k] = (og[k]    - K.black[k]) / (K.white[k] - K.black[k]) * K.wb[k];
+    v[k]  = div_rd(down4[k] - K.black[k], K.rd_wb[k]) * K.wb[k];   // (x - black) / (white - black) * wb
+    vo[k] = div_rd(og[k]    - K.black[k], K.rd_wb[k]) * K.wb[k];
 #endif
   }
 #pragma unroll
@@ -409,8 +444,9 @@ __global__ void __launch_bounds__(256, 5) k_denoise_assemble(const uint2 *__rest
 #if VKB_FAST
   st_rgba(out, w, x, y, make_float4(rgb[0] * K.denorm[0] + K.black[0], rgb[1] * K.denorm[1] + K.black[1], rgb[2] * K.denorm[2] + K.black[2], test));
 #else
-  st_rgba(out, w, x, y, make_float4(rgb[0] / K.wb[0] * (K.white[0] - K.black[0]) + K.black[0], rgb[1] / K.wb[1] * (K.white[1] - K.black[1]) + K.black[1],
-        rgb[2] / K.wb[2] * (K.white[2] - K.black[2]) + K.black[2], test));
+  st_rgba(out, w, x, y, make_float4(div_rd(rgb[0], K.rd_wbal[0]) * (K.white[0] - K.black[0]) + K.black[0],
+        div_rd(rgb[1], K.rd_wbal[1]) * (K.white[1] - K.black[1]) + K.black[1],
+        div_rd(rgb[2], K.rd_wbal[2]) * (K.white[2] - K.black[2]) + K.black[2], test));   // rgb / wb * (white - black) + black
 #endif
 }
 
@@ -560,13 +596,14 @@ static int launch_down(const vkb_launch_t *l)
   denoise_params_t p; memset(&p, 0, sizeof(p)); memcpy(&p, l->params, l->params_size < sizeof(p) ? l->params_size : sizeof(p));
   const float blk = pc->block == 3 ? 2.23607f : (pc->block == 2 ? 1.414213f : 1.0f);
   host_escale(&p);
+  const volatile float wmb = pc->white[1] - pc->black[1];
   if(in->wd >= DD_W && in->ht >= DD_H) // a window overhangs the image by less than its size: one reflection is enough
   {
     dim3 grid = grid2d(out->wd, out->ht);
     const band_t bd = band_of(l, 1, 8, out->ht, &grid.y);
     if(!grid.y) return VKB_OK;
     k_denoise_down_tiled<<<grid, blk2d, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, (uint2 *)out->data,
-        p, pc->black[1], pc->white[1], pc->noise_a, pc->noise_b, powf(0.7f, (float)pc->level), blk, bd);
+        p, pc->black[1], pc->white[1], pc->noise_a, pc->noise_b, powf(0.7f, (float)pc->level), blk, 1.0 / (double)wmb, 1.0 / (double)blk, bd);
   }
   else
   k_denoise_down<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, (uint2 *)out->data,
@@ -606,6 +643,12 @@ static int launch_assemble(const vkb_launch_t *l)
     K.inorm[k]  = (float)((double)K.wb[k] / ((double)K.white[k] - (double)K.black[k]));
     K.denorm[k] = (float)(((double)K.white[k] - (double)K.black[k]) / (double)K.wb[k]);
   }
+  for(int k = 0; k < 3; k++)
+  {
+    const volatile float wmb = K.white[k] - K.black[k];
+    K.rd_wb[k] = 1.0 / (double)wmb; K.rd_wbal[k] = 1.0 / (double)K.wb[k];
+  }
+  { const volatile float t0 = 2.0f * K.thrs0; K.rd_2t0 = 1.0 / (double)t0; K.rd_2t1 = 1.0 / 20000.0; }
   host_escale(&p);
   dim3 grid = grid2d(out->wd, out->ht);
   const band_t bd = band_of(l, 1, 8, out->ht, &grid.y);

@@ -44,11 +44,38 @@ VKB_DEV float llap_curve(float x, float g, const llap_params_t &p)
   val += p.clarity * c * m_exp(-c * c / (2.0f * p.sigma * p.sigma / 3.0f));
   return val;
 }
+// strict: the shader's two quotients (divisors 2 ssigma and 2 sigma^2 / 3 are launch constants: div_rd) and libm's exponential
+struct llap_rd_t { double rd2s, rdk; };
+static llap_rd_t llap_rd_host(const llap_params_t &p)
+{ // the divisors as the shader's fp32 expressions form them (volatile: one rounding per operation on the host too)
+  const volatile float two_s = 2.0f * p.sigma;
+  const volatile float ss = two_s * p.sigma;
+  const volatile float k = ss / 3.0f;
+  llap_rd_t r = { 1.0 / (double)two_s, 1.0 / (double)k };
+  return r;
+}
+VKB_DEV float llap_curve_x(float x, float g, const llap_params_t &p, const llap_rd_t &R, const lme_ctx_t &L)
+{
+  const float c = x - g;
+  float val;
+  const float ssigma = c > 0.0f ? p.sigma : -p.sigma;
+  const float shadhi = c > 0.0f ? p.shadows : p.hilights;
+  if(fabsf(c) > 2 * p.sigma) val = g + ssigma + shadhi * (c - ssigma);
+  else
+  {
+    const float t = clampf(div_rd(c, c > 0.0f ? R.rd2s : -R.rd2s), 0.0f, 1.0f);
+    const float t2 = t * t;
+    const float mt = 1.0f - t;
+    val = g + ssigma * 2.0f * mt * t + t2 * (ssigma + ssigma * shadhi);
+  }
+  val += p.clarity * c * m_exp_s(div_rd(-c * c, R.rdk), L);
+  return val;
+}
 template <bool CLARITY>
-VKB_DEV float llap_curve_k(float x, float g, const llap_params_t &p, float inv2s, float invd)
+VKB_DEV float llap_curve_k(float x, float g, const llap_params_t &p, float inv2s, float invd, const llap_rd_t &R, const lme_ctx_t &L)
 {
 #if !VKB_FAST
-  if(CLARITY) return llap_curve(x, g, p); // strict: the shader's divisions and libm's exponential
+  if(CLARITY) return llap_curve_x(x, g, p, R, L);
 #endif
   const float c = x - g;
   float val;
@@ -81,12 +108,14 @@ VKB_DEV float llap_grey(float4 px)
 #define R0_TH 17
 template <bool CLARITY>
 __global__ void __launch_bounds__(256, 6) k_llap_reduce0(const uint2 *__restrict__ in, int iw, int ih,
-    __half *__restrict__ out, int ow, int oh, llap_params_t p, const band_t bd)
+    __half *__restrict__ out, int ow, int oh, llap_params_t p, const llap_rd_t R, const band_t bd)
 {
   __shared__ __align__(16) __half tile[NL][R0_TH][R0_TW + 1];
   const int tx0 = blockIdx.x * 64 - 1, ty0 = BAND_BY * 16 - 1;
   const int tid = threadIdx.y * 32 + threadIdx.x;
   const float inv2s = 1.0f / (2.0f * p.sigma), invd = 1.0f / (2.0f * p.sigma * p.sigma / 3.0f);
+  LME_SMEM_STAGE(tid);
+  __syncthreads();
   for(int t = tid; t < R0_TW * R0_TH; t += 256)
   {
     const int lx = t % R0_TW, ly = t / R0_TW;
@@ -94,7 +123,7 @@ __global__ void __launch_bounds__(256, 6) k_llap_reduce0(const uint2 *__restrict
     const int gx = big ? mirror1(tx0 + lx, iw) : mirrori(tx0 + lx, iw), gy = big ? mirror1(ty0 + ly, ih) : mirrori(ty0 + ly, ih);
     const float y = llap_grey(ld_rgba(in, iw, gx, gy));
 #pragma unroll
-    for(int g = 0; g < NUM_GAMMA; g++) tile[g][ly][lx] = __float2half_rn(llap_curve_k<CLARITY>(y, gamma_from_i(g), p, inv2s, invd));
+    for(int g = 0; g < NUM_GAMMA; g++) tile[g][ly][lx] = __float2half_rn(llap_curve_k<CLARITY>(y, gamma_from_i(g), p, inv2s, invd, R, lme_ctx));
     tile[NUM_GAMMA][ly][lx] = __float2half_rn(y);
   }
   __syncthreads();
@@ -340,10 +369,10 @@ static int launch_llapr0(const vkb_launch_t *l)
   if(!grid.y) return VKB_OK;
   if(lp->clarity == 0.0f)
     k_llap_reduce0<false><<<grid, blk2d, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht,
-        (__half *)out->data, out->wd, out->ht, *lp, bd);
+        (__half *)out->data, out->wd, out->ht, *lp, llap_rd_host(*lp), bd);
   else
     k_llap_reduce0<true><<<grid, blk2d, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht,
-        (__half *)out->data, out->wd, out->ht, *lp, bd);
+        (__half *)out->data, out->wd, out->ht, *lp, llap_rd_host(*lp), bd);
   VKB_CHECK_LAUNCH();
   return VKB_OK;
 }

@@ -17,7 +17,8 @@
 struct llap_params_t { float sigma, shadows, hilights, clarity; };
 // everything below `grade` is a function of the launch's parameters only and is evaluated once on the host with the same
 // fp32 operations the kernel used to repeat per pixel (1/(2 sigma), 1/(2 sigma^2/3); grade: lift, 1 - lift, gain, offset, 1/gamma)
-struct llapfin_t { llap_params_t p; int first; int have_grade; int out_f32; grade_params_t grade;
+struct llap_rd_t { double rd2s, rdk; };   // 1 / (2 sigma), 1 / (2 sigma^2 / 3) for div_rd (strict)
+struct llapfin_t { llap_rd_t rd; llap_params_t p; int first; int have_grade; int out_f32; grade_params_t grade;
                    float inv2s, invd; float g_lift[3], g_oml[3], g_gain[3], g_off[3], g_ig[3]; };
 
 VKB_DEV float gamma_from_i(int i) { return (float)i / (NUM_GAMMA - 1.0f); }
@@ -64,6 +65,25 @@ VKB_DEV float llap_curve(float x, float g, const llap_params_t &p)
   }
   // the gaussian term is < 3% of val: __expf's 1e-6 relative error on it is below an fp32 ulp of val
   val += p.clarity * c * m_exp(-c * c / (2.0f * p.sigma * p.sigma / 3.0f));
+  return val;
+}
+
+// strict: the two quotients by launch constants through div_rd, libm's exponential with its tables in shared memory
+VKB_DEV float llap_curve_x(float x, float g, const llap_params_t &p, const llap_rd_t &R, const lme_ctx_t &L)
+{
+  const float c = x - g;
+  float val;
+  const float ssigma = c > 0.0f ? p.sigma : -p.sigma;
+  const float shadhi = c > 0.0f ? p.shadows : p.hilights;
+  if(fabsf(c) > 2 * p.sigma) val = g + ssigma + shadhi * (c - ssigma);
+  else
+  {
+    const float t = clampf(div_rd(c, c > 0.0f ? R.rd2s : -R.rd2s), 0.0f, 1.0f);
+    const float t2 = t * t;
+    const float mt = 1.0f - t;
+    val = g + ssigma * 2.0f * mt * t + t2 * (ssigma + ssigma * shadhi);
+  }
+  val += p.clarity * c * m_exp_s(div_rd(-c * c, R.rdk), L);
   return val;
 }
 
@@ -168,6 +188,11 @@ __global__ void __launch_bounds__(256, 4) k_llap_final4(const uint2 *__restrict_
   const int tid = threadIdx.y * 32 + threadIdx.x;
   if(tid == 0) { s_pmin = NUM_GAMMA; s_pmax = 0; }
   if(tid < NUM_GAMMA) s_gamma[tid] = gamma_from_i(tid);
+#if !VKB_FAST
+  __shared__ double s_rdg[NUM_GAMMA];  // 1 / (gamma[i] - gamma[i - 1]): the blend weight's quotient through div_rd
+  if(tid > 32 && tid < 32 + NUM_GAMMA) s_rdg[tid - 32] = rcp_d(gamma_from_i(tid - 32) - gamma_from_i(tid - 33));
+#endif
+  LME_SMEM_STAGE(tid);
   const int kx = blockIdx.x * 32 + threadIdx.x, ky = BAND_BY * 8 + threadIdx.y;
   const int cx0 = blockIdx.x * 32 - 2, cy0 = BAND_BY * 8 - 2;
   const size_t p1 = (size_t)cw * ch;
@@ -273,13 +298,14 @@ __global__ void __launch_bounds__(256, 4) k_llap_final4(const uint2 *__restrict_
     f3 c = { fmaxf(0.0f, px[q].x * ratio), fmaxf(0.0f, px[q].y * ratio), fmaxf(0.0f, px[q].z * ratio) };
 #else
     // assemble.comp:66-87 and colour.comp:23-35 operation for operation
-    const float a = clampf((v[q] - glo) / (ghi - glo), 0.0f, 1.0f);
-    const float lap0 = f16r(llap_curve(grey[q], glo, P.p)) - e0[q];
-    const float lap1 = f16r(llap_curve(grey[q], ghi, P.p)) - e1[q];
+    const float a = clampf(div_rd(v[q] - glo, s_rdg[hi[q]]), 0.0f, 1.0f);
+    const float lap0 = f16r(llap_curve_x(grey[q], glo, P.p, P.rd, lme_ctx)) - e0[q];
+    const float lap1 = f16r(llap_curve_x(grey[q], ghi, P.p, P.rd, lme_ctx)) - e1[q];
     float l = f16r(res[q] + lap0 * (1.0f - a) + lap1 * a);
     const float yo = fmaxf(lum2020(px[q].x, px[q].y, px[q].z), 1e-8f);
-    if(l < yo) l = yo * m_exp(1.0f * (l - yo));
-    f3 c = { fmaxf(0.0f, px[q].x * l / yo), fmaxf(0.0f, px[q].y * l / yo), fmaxf(0.0f, px[q].z * l / yo) };
+    if(l < yo) l = yo * m_exp_s(1.0f * (l - yo), lme_ctx);
+    const double ryo = rcp_dn(yo);   // yo >= 1e-8: normal
+    f3 c = { fmaxf(0.0f, div_rd(px[q].x * l, ryo)), fmaxf(0.0f, div_rd(px[q].y * l, ryo)), fmaxf(0.0f, div_rd(px[q].z * l, ryo)) };
 #endif
     if(GRADE)
     {
@@ -316,6 +342,12 @@ static int launch_llapfin2(const vkb_launch_t *l)
   memcpy(&P.p, l->params, sizeof(llap_params_t));
   P.first = pc[0]; P.have_grade = pc[1]; P.out_f32 = out->format == VKB_TOKEN_F32 ? (out->chan == 3 ? 2 : 1) : 0;
   P.inv2s = 1.0f / (2.0f * P.p.sigma); P.invd = 1.0f / (2.0f * P.p.sigma * P.p.sigma / 3.0f);
+  { // the divisors as the kernel's fp32 expressions form them (volatile: one rounding per operation on the host too)
+    const volatile float two_s = 2.0f * P.p.sigma;
+    const volatile float ss = two_s * P.p.sigma;
+    const volatile float k = ss / 3.0f;
+    P.rd.rd2s = 1.0 / (double)two_s; P.rd.rdk = 1.0 / (double)k;
+  }
   if(P.have_grade)
   {
     VKB_REQUIRE(l->params_size >= sizeof(llap_params_t) + sizeof(grade_params_t));

@@ -21,10 +21,12 @@
 
 #if defined(__CUDACC__)
 #define LME_FN __host__ __device__ __forceinline__
-#define LME_TAB static __device__ const
+#define LME_MFN __host__ __device__ __forceinline__
+#define LME_COLD static __host__ __device__ __noinline__
 #else
 #define LME_FN static inline
-#define LME_TAB static const
+#define LME_MFN inline
+#define LME_COLD static __attribute__((noinline))
 #endif
 
 #if defined(__CUDA_ARCH__)
@@ -100,7 +102,7 @@ LME_FN double lme_exp2_tail(double kd_plus_shift, double r, double c0, double c1
   return LME_MUL(y, s);
 }
 
-LME_FN float lme_expf(float x)
+LME_FN float lme_expf_gen(float x)
 {
   const uint32_t abstop = (LME_F2U(x) >> 20) & 0x7ff;
   if(abstop > 0x42a)
@@ -189,7 +191,7 @@ LME_FN float lme_log2f(float x)
 }
 
 // x^y for x >= 0 or integer y like libm; the shaders guard their arguments (pow of a negative base is undefined in GLSL)
-LME_FN float lme_powf(float x, float y)
+LME_FN float lme_powf_gen(float x, float y)
 {
   uint32_t ix = LME_F2U(x);
   const uint32_t iy = LME_F2U(y);
@@ -258,3 +260,134 @@ LME_FN float lme_powf(float x, float y)
   res = LME_FMA(zz, rr2, res);
   return LME_D2F(LME_MUL(res, s));
 }
+
+// ---- what the kernels call: the same results, without a data dependent branch in the common case ----
+// the generic functions above spend a third of their issued instructions on libm's special case ladders, and every double
+// literal costs two moves in front of the instruction that uses it.  here the common case is one straight line, everything
+// rare is one predicated call of the generic function kept out of line, the polynomial coefficients sit in the constant
+// bank (an operand of DFMA / DMUL, no instruction), and the two tables can be staged in shared memory by the kernel
+// (lme_smem_t: a 32 bit address instead of 64 bit arithmetic on a global one).
+LME_COLD float lme_powf_cold(float x, float y) { return lme_powf_gen(x, y); }
+
+#define LME_KI_INVLN2N 0
+#define LME_KI_EXP_C0  1
+#define LME_KI_EXP_C1  2
+#define LME_KI_EXP_C2  3
+#define LME_KI_EXP2_C0 4
+#define LME_KI_EXP2_C1 5
+#define LME_KI_EXP2_C2 6
+#define LME_KI_POW_A0  7
+#define LME_KI_POW_A1  8
+#define LME_KI_POW_A2  9
+#define LME_KI_POW_A3  10
+#define LME_KI_POW_A4  11
+#if defined(__CUDACC__)
+static __constant__ double lme_kc[12] = { LME_INVLN2N, LME_EXP_C0, LME_EXP_C1, LME_EXP_C2, LME_EXP2_C0, LME_EXP2_C1, LME_EXP2_C2,
+                                          LME_POW_A0, LME_POW_A1, LME_POW_A2, LME_POW_A3, LME_POW_A4 };
+struct __align__(16) lme_smem_t { double log2tab[32]; uint64_t exp2tab[32]; };
+// the first 32 threads of a CTA fill the tables; the caller synchronises before the first use
+__device__ __forceinline__ void lme_smem_fill(lme_smem_t &s, int tid)
+{
+  if(tid < 32) { s.log2tab[tid] = lme_log2f_tab_dev[tid]; s.exp2tab[tid] = lme_exp2_tab_dev[tid]; }
+}
+#endif
+#if defined(__CUDA_ARCH__)
+#define LME_K(n) lme_kc[LME_KI_##n]
+#else
+#define LME_K(n) LME_##n
+#endif
+
+// expf: arguments below -104 give +0 like libm's underflow return (the formula rounds 2^-150.0x to zero as well), above 89
+// +inf like its overflow return (the conversion overflows)
+template <class TAB> LME_FN float lme_expf_t(float x, const TAB tab)
+{
+  const float xc = fminf(fmaxf(x, -104.0f), 89.0f);
+  const double xd = (double)xc;
+  double kd = LME_FMA(LME_K(INVLN2N), xd, LME_SHIFT);
+  const uint64_t ki = LME_D2U(kd);
+  kd = LME_ADD(kd, -LME_SHIFT);
+  const double r = LME_FMA(LME_K(INVLN2N), xd, -kd);
+  uint64_t t = tab.exp2(ki);
+  t += ki << 47;
+  const double sc = LME_U2D(t);
+  const double z = LME_FMA(LME_K(EXP_C0), r, LME_K(EXP_C1));
+  const double r2 = LME_MUL(r, r);
+  double y = LME_FMA(LME_K(EXP_C2), r, 1.0);
+  y = LME_FMA(z, r2, y);
+  const float res = LME_D2F(LME_MUL(y, sc));
+  return x != x ? x + x : res;
+}
+
+// powf: straight line for a positive normal x and a finite non zero y whose y log2 x stays inside +-126; x = +0 with a
+// positive y is answered in line (black pixels are common); the rest (subnormal, negative, inf, nan, over/underflow) is rare
+template <class TAB> LME_FN float lme_powf_t(float x, float y, const TAB tab)
+{
+  const uint32_t ix = LME_F2U(x), iy = LME_F2U(y);
+  int rare = (ix - 0x00800000u >= 0x7f000000u) || (2 * iy - 1 >= 2u * 0x7f800000u - 1);
+  const uint32_t ixs = rare ? 0x3f800000u : ix;
+  const uint32_t tmp = ixs - 0x3f330000u;
+  const int i = (tmp >> 19) & 15;
+  const uint32_t top = tmp & 0xff800000u;
+  const uint32_t iz = ixs - top;
+  const int k = (int32_t)tmp >> 23;
+  double invc, logc; tab.log2(i, invc, logc);
+  const double z = (double)LME_U2F(iz);
+  const double r = LME_FMA(z, invc, -1.0);
+  const double y0 = LME_ADD(logc, (double)k);
+  const double r2 = LME_MUL(r, r);
+  const double yy = LME_FMA(LME_K(POW_A0), r, LME_K(POW_A1));
+  const double p = LME_FMA(LME_K(POW_A2), r, LME_K(POW_A3));
+  const double r4 = LME_MUL(r2, r2);
+  double q = LME_FMA(LME_K(POW_A4), r, y0);
+  q = LME_FMA(p, r2, q);
+  const double logx = LME_FMA(yy, r4, q);
+  const double ylogx = LME_MUL((double)y, logx);
+  rare = rare || (((uint32_t)(LME_D2U(ylogx) >> 47) & 0xffffu) >= 0x80bfu);
+  double kd = LME_ADD(ylogx, LME_SHIFT_SCALED);
+  const uint64_t ki = LME_D2U(kd);
+  kd = LME_ADD(kd, -LME_SHIFT_SCALED);
+  const double rr = LME_ADD(ylogx, -kd);
+  uint64_t t = tab.exp2(ki);
+  t += ki << 47;
+  const double sc = LME_U2D(t);
+  const double zz = LME_FMA(LME_K(EXP2_C0), rr, LME_K(EXP2_C1));
+  const double rr2 = LME_MUL(rr, rr);
+  double res = LME_FMA(LME_K(EXP2_C2), rr, 1.0);
+  res = LME_FMA(zz, rr2, res);
+  const float out = LME_D2F(LME_MUL(res, sc));
+  if(rare)
+  {
+    if(ix == 0 && iy - 1u < 0x7f7fffffu) return 0.0f;   // +0 ^ (positive finite y)
+    return lme_powf_cold(x, y);
+  }
+  return out;
+}
+// tables in global memory (L1 resident)
+struct lme_gtab_t
+{
+  LME_MFN uint64_t exp2(uint64_t ki) const { return LME_T(lme_exp2_tab)[ki & 31]; }
+  LME_MFN void log2(int i, double &invc, double &logc) const { invc = LME_T(lme_log2f_tab)[2 * i]; logc = LME_T(lme_log2f_tab)[2 * i + 1]; }
+};
+LME_FN float lme_expf(float x) { return lme_expf_t(x, lme_gtab_t()); }
+LME_FN float lme_powf(float x, float y) { return lme_powf_t(x, y, lme_gtab_t()); }
+#if defined(__CUDACC__)
+// tables in shared memory: `base` is the 32 bit shared address of a filled lme_smem_t, kept in one register
+struct lme_stab_t
+{
+  uint32_t base;
+  __device__ __forceinline__ uint64_t exp2(uint64_t ki) const
+  {
+    uint64_t t; asm("ld.shared.u64 %0, [%1+256];" : "=l"(t) : "r"(base + (((uint32_t)ki & 31u) << 3))); return t;
+  }
+  __device__ __forceinline__ void log2(int i, double &invc, double &logc) const
+  {
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(invc), "=d"(logc) : "r"(base + ((uint32_t)i << 4)));
+  }
+};
+__device__ __forceinline__ lme_stab_t lme_stab(const lme_smem_t &s)
+{
+  lme_stab_t t; t.base = (uint32_t)__cvta_generic_to_shared(&s);
+  asm volatile("" : "+r"(t.base));   // one register for the kernel's lifetime instead of five uniform instructions per use
+  return t;
+}
+#endif
