@@ -216,7 +216,8 @@ __global__ void __launch_bounds__(256, 5) k_denoise_downcov(const uint2 *__restr
 #define DN_F04 0.3999999761581421f
 // x^0.8 on the SFU (fast): ~1e-6 relative, i.e. <= 1e-4 in the [0,1] edge weight even at the 1e-3 noise floor of noise.glsl
 VKB_DEV float gamma08(float f) { return f < 0.0f ? f : m_pow(f, 0.8f); }
-VKB_DEV float gamma08(float f, const lme_ctx_t &L) { return f < 0.0f ? f : m_pow_s(f, 0.8f, L); }
+// (the branch stays: below black every other noisy value is negative, and a select would pay for the power all the same)
+VKB_DEV float gamma08(float f, const lme_ctx_t &L) { return f < 0.0f ? f : m_pow_sy(f, 0.8f, L); }
 
 // ---- down: levels 1..3, 5 tap flower with edge stopping (down.comp:59-107) ----
 __global__ void __launch_bounds__(256) k_denoise_down(const uint2 *__restrict__ in, int w, int h, uint2 *__restrict__ out,

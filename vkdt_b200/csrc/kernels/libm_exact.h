@@ -320,7 +320,9 @@ template <class TAB> LME_FN float lme_expf_t(float x, const TAB tab)
 
 // powf: straight line for a positive normal x and a finite non zero y whose y log2 x stays inside +-126; x = +0 with a
 // positive y is answered in line (black pixels are common); the rest (subnormal, negative, inf, nan, over/underflow) is rare
-template <class TAB> LME_FN float lme_powf_t(float x, float y, const TAB tab)
+// SMALLY: the caller guarantees |y| <= 0.84, so that |y log2 x| < 126 for every positive finite x (|log2 x| < 150) and the
+// over / underflow test of the general case is dead
+template <bool SMALLY, class TAB> LME_FN float lme_powf_tt(float x, float y, const TAB tab)
 {
   const uint32_t ix = LME_F2U(x), iy = LME_F2U(y);
   int rare = (ix - 0x00800000u >= 0x7f000000u) || (2 * iy - 1 >= 2u * 0x7f800000u - 1);
@@ -342,7 +344,7 @@ template <class TAB> LME_FN float lme_powf_t(float x, float y, const TAB tab)
   q = LME_FMA(p, r2, q);
   const double logx = LME_FMA(yy, r4, q);
   const double ylogx = LME_MUL((double)y, logx);
-  rare = rare || (((uint32_t)(LME_D2U(ylogx) >> 47) & 0xffffu) >= 0x80bfu);
+  if(!SMALLY) rare = rare || (((uint32_t)(LME_D2U(ylogx) >> 47) & 0xffffu) >= 0x80bfu);
   double kd = LME_ADD(ylogx, LME_SHIFT_SCALED);
   const uint64_t ki = LME_D2U(kd);
   kd = LME_ADD(kd, -LME_SHIFT_SCALED);
@@ -362,6 +364,7 @@ template <class TAB> LME_FN float lme_powf_t(float x, float y, const TAB tab)
   }
   return out;
 }
+template <class TAB> LME_FN float lme_powf_t(float x, float y, const TAB tab) { return lme_powf_tt<false>(x, y, tab); }
 // tables in global memory (L1 resident)
 struct lme_gtab_t
 {
@@ -370,6 +373,7 @@ struct lme_gtab_t
 };
 LME_FN float lme_expf(float x) { return lme_expf_t(x, lme_gtab_t()); }
 LME_FN float lme_powf(float x, float y) { return lme_powf_t(x, y, lme_gtab_t()); }
+LME_FN float lme_powf_smally(float x, float y) { return lme_powf_tt<true>(x, y, lme_gtab_t()); }
 #if defined(__CUDACC__)
 // tables in shared memory: `base` is the 32 bit shared address of a filled lme_smem_t, kept in one register
 struct lme_stab_t
