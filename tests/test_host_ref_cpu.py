@@ -300,6 +300,22 @@ def test_live_reference_graph_random(oracle):
         assert len(ref) == len(got) and not bad, (case, len(ref), len(got), bad[:3])
 
 
+def test_live_reference_graph_with_feedback_edges(oracle):
+    """`feedback:` connections through the whole module pass (traversal incl. the second round of graph-traverse.inc:131-148,
+    roi negotiation, create_nodes, repointing) against the compiled reference."""
+    if oracle.ref_host_lib() is None or not hasattr(oracle.ref_host_lib(), "ref_graph_describe") or not os.path.isdir("/root/reference/src/pipe/modules"):
+        pytest.skip("oracle/_ref/libhostref.so or /root/reference not present")
+    raw = dict(black=1024.0, white=15000.0, wb=(2.0, 1.0, 1.5), noise_a=10.0, noise_b=1.0)
+    for lines, w, h in ((["feedback:grade:01:output:colour:01:spectra"], 640, 480),
+                        (["feedback:llap:01:output:colour:01:spectra", "param:denoise:01:strength:0.3"], 1002, 668),
+                        (["feedback:crop:01:output:colour:01:spectra", "param:crop:01:rotate:90"], 322, 246)):
+        case = dict(lines=lines, w=w, h=h, raw=raw)
+        ref = _graph_text_reference(case, oracle.ref_graph_describe(w, h, lines, raw))
+        got = _graph_text_product(case)
+        bad = [(a[:200], b[:200]) for a, b in zip(ref, got) if a != b]
+        assert len(ref) == len(got) and not bad, (case, len(ref), len(got), bad[:3])
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # the config grammar against the REFERENCE's own graph-io.c: return code per line (0 ok, > 0 warning, < 0 fatal) and the
 # state the lines leave behind (tests/golden/host_cfg.json.gz)

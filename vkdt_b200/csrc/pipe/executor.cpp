@@ -26,8 +26,10 @@ struct plan_buf_t
   int first = 1 << 30, last = -1;   // launch indices of first write / last read
   void *external = 0;               // device pointer owned by the caller (vkb_graph_set_source_device)
   int pinned_live = 0;              // must survive the whole run (sink input)
+  int frames = 1;                   // 2: double buffered (an s_conn_feedback input reads it): two copies of `bytes`, back to back,
+                                    // never recycled.  frame f writes copy f & 1, feedback inputs read copy 1 - (f & 1)
 };
-struct plan_img_t { int buf; uint32_t wd, ht, chan, layers; dt_token_t format; };
+struct plan_img_t { int buf; uint32_t wd, ht, chan, layers; dt_token_t format; int fb = 0; }; // fb: reads the other frame's copy
 struct plan_launch_t
 {
   dt_token_t name, kernel;
@@ -146,6 +148,9 @@ struct builder_t
     {
       plan_buf_t b;
       b.bytes = ((conn_bytes(cn) + 255) / 256) * 256 + 256;
+      // double buffered when an s_conn_feedback input is wired to it (dt_module_feedback / dt_connector_copy carry frames = 2 to
+      // the owner, init_connector_images graph-run-modules.h:169-196); such a buffer outlives the frame
+      if(cn->frames == 2) { b.frames = 2; b.pinned_live = 1; b.first = -1; }
       p->buf.push_back(b);
       cn->buf = (int)p->buf.size() - 1;
     }
@@ -160,7 +165,10 @@ struct builder_t
   { // an input sees the image its owner declared
     const dt_cid_t src = g->node[n].connector[c].connected;
     if(src.i < 0 || src.i >= (int)g->node.size() || src.c < 0) return plan_img_t{ -1, 0, 0, 1, 1, dt_token("f16") };
-    return img_out(src.i, src.c);
+    plan_img_t im = img_out(src.i, src.c);
+    // feedback inputs cross the frame wires (graph-run-nodes-allocate.h:222-229): they see what the owner wrote one frame ago
+    if((g->node[n].connector[c].flags & s_conn_feedback) && p->buf[im.buf].frames == 2) im.fb = 1;
+    return im;
   }
   const std::vector<std::pair<int,int>> &cons(int n, int c) { return consumers[{n, c}]; }
   void add_launch(plan_launch_t &l)
@@ -280,13 +288,6 @@ static int build_plan(dt_graph_t *g, bool with_device)
   vkb_plan_t *p = new vkb_plan_t();
   int r = dt_graph_run_modules(g, p->modid);
   if(r) { delete p; return r; }
-  // feedback connectors read the frame before (connector.h:116, double buffering graph-run-modules.h:169-196): not built
-  for(int m : p->modid) for(int c = 0; c < g->module[m].num_connectors; c++) if(g->module[m].connector[c].flags & s_conn_feedback)
-  {
-    delete p;
-    return vkb_set_error(VKB_ERR_GRAPH, "module %s:%s reads a feedback connector: graphs that carry images from frame to frame are outside the raw->display path",
-        dt_token_string(g->module[m].name).c_str(), dt_token_string(g->module[m].inst).c_str());
-  }
   builder_t B;
   B.g = g; B.p = p;
   dt_graph_node_order(g, B.order);
@@ -570,8 +571,8 @@ static int build_plan(dt_graph_t *g, bool with_device)
   };
   for(int t = -1; t <= nl; t++)
   {
-    for(plan_buf_t &b : p->buf) if(!b.external && b.last >= 0 && b.first == t) b.offset = alloc(b.bytes);
-    for(plan_buf_t &b : p->buf) if(!b.external && b.last == t && b.first <= t && b.last >= 0) release(b.offset, b.bytes);
+    for(plan_buf_t &b : p->buf) if(!b.external && b.last >= 0 && b.first == t) b.offset = alloc(b.bytes * b.frames);
+    for(plan_buf_t &b : p->buf) if(!b.external && b.last == t && b.first <= t && b.last >= 0) release(b.offset, b.bytes * b.frames);
   }
   p->pool_bytes = peak + 256;
   for(const plan_source_t &s : p->source) if(!s.external) p->staging_up_bytes = std::max(p->staging_up_bytes, s.bytes);
@@ -580,6 +581,9 @@ static int build_plan(dt_graph_t *g, bool with_device)
   cudaError_t e = cudaSetDevice(g->device);
   if(e == cudaSuccess) e = cudaMalloc(&p->pool, p->pool_bytes);
   if(e != cudaSuccess) { const char *msg = cudaGetErrorString(e); plan_free(p); return vkb_set_error(e == cudaErrorMemoryAllocation ? VKB_ERR_OOM : VKB_ERR_NO_DEVICE, "pool allocation of %zu bytes failed: %s", peak, msg); }
+  // double buffered connectors are read one frame before they are first written: frame 0 sees zeros (the reference leaves
+  // fresh device memory there unless the connector asks for s_conn_clear_once)
+  for(const plan_buf_t &b : p->buf) if(b.frames == 2 && !b.external) cudaMemset((uint8_t *)p->pool + b.offset, 0, b.bytes * 2);
   cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
   if(p->staging_up_bytes && cudaHostAlloc(&p->staging_up, p->staging_up_bytes, cudaHostAllocDefault) != cudaSuccess)
   { plan_free(p); return vkb_set_error(VKB_ERR_OOM, "pinned upload staging allocation failed"); }
@@ -702,6 +706,8 @@ static int plan_bands(dt_graph_t *g, vkb_bands_t **out)
   const int n = (int)g->band_devices.size();
   const int nl = (int)p->launch.size();
   if(p->source.empty()) return vkb_set_error(VKB_ERR_GRAPH, "band split: no source");
+  for(const plan_buf_t &b : p->buf) if(b.frames == 2)
+    return vkb_set_error(VKB_ERR_GRAPH, "band split: the graph has double buffered (feedback) connectors, which are kept per device: run it on one GPU");
   const int hfull = (int)g->node[p->source[0].nodeid].connector[0].roi.ht;
   vkb_bands_t *B = new vkb_bands_t();
   B->dev.resize(n);
@@ -955,11 +961,11 @@ static int run_bands(dt_graph_t *g, uint32_t run)
   return VKB_OK;
 }
 
-static void *buf_ptr(const vkb_plan_t *p, int b)
+static void *buf_ptr(const vkb_plan_t *p, int b, int copy = 0)
 {
   if(b < 0) return 0;
   if(p->buf[b].external) return p->buf[b].external;
-  return (uint8_t *)p->pool + p->buf[b].offset;
+  return (uint8_t *)p->pool + p->buf[b].offset + (p->buf[b].frames == 2 && copy ? p->buf[b].bytes : 0);
 }
 
 int dt_graph_run(dt_graph_t *g, uint32_t run)
@@ -998,6 +1004,7 @@ int dt_graph_run(dt_graph_t *g, uint32_t run)
     return run_bands(g, run);
   }
   cudaSetDevice(g->device);
+  const int parity = g->frame & 1;
   // sources with s_module_request_read_source re-upload every run (graph-run-modules.h:573-587)
   for(const plan_source_t &s : p->source)
   {
@@ -1045,7 +1052,8 @@ int dt_graph_run(dt_graph_t *g, uint32_t run)
         l.arg_params.insert(l.arg_params.end(), src, src + sz);
       }
       l.arg_conn.clear();
-      for(const plan_img_t &im : l.conn) l.arg_conn.push_back(vkb_image_t{ buf_ptr(p, im.buf), im.wd, im.ht, im.chan, im.layers, im.format });
+      // graph->double_buffer of the reference's frame loop (graph-export.c:294): frame f writes copy f & 1
+      for(const plan_img_t &im : l.conn) l.arg_conn.push_back(vkb_image_t{ buf_ptr(p, im.buf, im.fb ? 1 - parity : parity), im.wd, im.ht, im.chan, im.layers, im.format });
       mix(l.arg_params.data(), l.arg_params.size());
       mix(l.push.data(), l.push.size());
       for(const vkb_image_t &im : l.arg_conn) { mix(&im.data, sizeof(im.data)); mix(&im.wd, 4); mix(&im.ht, 4); mix(&im.chan, 4); mix(&im.layers, 4); mix(&im.format, sizeof(im.format)); }
@@ -1113,13 +1121,13 @@ int dt_graph_run(dt_graph_t *g, uint32_t run)
       if(ms && ms->dst)
       {
         if(ms->bytes < s.bytes) return vkb_set_error(VKB_ERR_BAD_ARG, "sink buffer too small: %zu < %zu", ms->bytes, s.bytes);
-        cudaMemcpyAsync(ms->dst, buf_ptr(p, s.buf), s.bytes, cudaMemcpyDeviceToHost, p->stream);
+        cudaMemcpyAsync(ms->dst, buf_ptr(p, s.buf, parity), s.bytes, cudaMemcpyDeviceToHost, p->stream);
       }
       else if(mod->so->write_sink && !(ms && !ms->dst))
       {
         if(!p->staging_down && cudaHostAlloc(&p->staging_down, p->staging_down_bytes, cudaHostAllocDefault) != cudaSuccess)
           return vkb_set_error(VKB_ERR_OOM, "pinned download staging allocation failed");
-        cudaMemcpyAsync(p->staging_down, buf_ptr(p, s.buf), s.bytes, cudaMemcpyDeviceToHost, p->stream);
+        cudaMemcpyAsync(p->staging_down, buf_ptr(p, s.buf, parity), s.bytes, cudaMemcpyDeviceToHost, p->stream);
         cudaStreamSynchronize(p->stream);
         dt_write_sink_params_t wp = { &g->node[s.nodeid], 0, 0 };
         mod->so->write_sink(mod, p->staging_down, &wp);
@@ -1170,7 +1178,8 @@ int dt_graph_plan(dt_graph_t *g, std::string *text)
     for(const plan_img_t &im : l.conn)
     {
       if(im.buf < 0) { *text += " -"; continue; }
-      snprintf(b, sizeof(b), " b%d:%ux%ux%ux%u:%s@%zu", im.buf, im.wd, im.ht, im.chan, im.layers, dt_token_string(im.format).c_str(), p->buf[im.buf].offset);
+      snprintf(b, sizeof(b), " b%d:%ux%ux%ux%u:%s@%zu%s", im.buf, im.wd, im.ht, im.chan, im.layers, dt_token_string(im.format).c_str(), p->buf[im.buf].offset,
+          p->buf[im.buf].frames == 2 ? (im.fb ? "[fb:last frame]" : "[x2]") : "");
       *text += b;
     }
     *text += "\n";

@@ -229,7 +229,12 @@ int dt_module_connect(dt_graph_t *g, int m0, int c0, int m1, int c1)
 int dt_module_feedback(dt_graph_t *g, int m0, int c0, int m1, int c1)
 { // connector.c:30-38: connect without the cycle test (a feedback edge closes one on purpose) and flag the input
   const int err = connect_generic<dt_module_t, true>(g->module, m0, c0, m1, c1);
-  if(!err && m1 >= 0 && c1 >= 0) g->module[m1].connector[c1].flags |= s_conn_feedback;
+  if(!err && m1 >= 0 && c1 >= 0)
+  { // both ends are double buffered: written in frame f, read through this edge in frame f + 1
+    g->module[m1].connector[c1].flags |= s_conn_feedback;
+    g->module[m1].connector[c1].frames = 2;
+    if(m0 >= 0 && c0 >= 0) g->module[m0].connector[c0].frames = 2;
+  }
   return err;
 }
 // the node layer (connector.c node flavour): wildcards on either side take the other side's channels / format
@@ -606,6 +611,11 @@ static void traverse_post(std::vector<T> &arr, F is_main, std::vector<int> &orde
   for(int i = cnt - 1; i >= 0; i--)
     if(arr[i].num_connectors && arr[i].connector[0].type == dt_token("sink") && dt_connected(arr[i].connector) && !mark[i])
     { mark[i] = 1; stack.push_back(i); done.push_back(0); }
+  // graph-traverse.inc:71-148: elements only reached through a feedback edge are not dependencies of this frame; they are
+  // collected and traversed in a second round (they still have to run: the next frame reads what they write)
+  std::vector<int> feedback_stack;
+  for(;;)
+  {
   while(!stack.empty())
   {
     const int curr = stack.back();
@@ -631,8 +641,19 @@ static void traverse_post(std::vector<T> &arr, F is_main, std::vector<int> &orde
           stack.push_back(el); done.push_back(0);
           if(mark[el] < 1) mark[el] = 1;
         }
+        if(mark[el] != 3 && (arr[curr].connector[i].flags & s_conn_feedback))
+        {
+          if(feedback_stack.size() > 100000) { order.clear(); return; }
+          feedback_stack.push_back(el);
+          mark[el] = 1;
+        }
       }
     }
+  }
+  if(feedback_stack.empty()) break;
+  stack = feedback_stack;
+  done.assign(stack.size(), 0);
+  feedback_stack.clear();
   }
 }
 
