@@ -274,9 +274,22 @@ VKB_DEV float4 unpack_rgba(uint2 v)
 __global__ void __launch_bounds__(256, 6) k_denoise_down_tiled(const uint2 *__restrict__ in, int w, int h, uint2 *__restrict__ out,
     denoise_params_t p, float black, float white, float noise_a, float noise_b, float lv, float blk, double rd_wb, double rd_blk, const band_t bd)
 {
-  __shared__ uint2 tile[DD_H][DD_W];
-  LME_SMEM_STAGE(threadIdx.y * 32 + threadIdx.x);
+  __shared__ __align__(128) uint2 tile[DD_H][DD_W];
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  LME_SMEM_STAGE(tid);
   const int tx0 = blockIdx.x * 32 - 2, ty0 = BAND_BY * 8 - 2;
+  // a window inside the image: twelve bulk copies of one 288 byte row segment each (rows start on 16 bytes when w is even)
+  const bool interior = tx0 >= 0 && ty0 >= 0 && tx0 + DD_W <= w && ty0 + DD_H <= h && !(w & 1);
+  if(interior)
+  {
+    if(tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if(tid == 0) mbar_expect_tx(&bar, DD_H * DD_W * (uint32_t)sizeof(uint2));
+    if(tid < DD_H) bulk_g2s(tile[tid], in + (size_t)(ty0 + tid) * w + tx0, DD_W * (uint32_t)sizeof(uint2), &bar);
+    mbar_wait(&bar, 0);
+  }
+  else
   // thread (tx, ty) stages rows ty, ty + 8 and columns tx, tx + 32 of the window: no division, one mirror per row / column
   {
     const int c0 = threadIdx.x, c1 = threadIdx.x + 32, r0 = threadIdx.y, r1 = threadIdx.y + 8;
@@ -289,8 +302,8 @@ __global__ void __launch_bounds__(256, 6) k_denoise_down_tiled(const uint2 *__re
       tile[r1][c0] = __ldg(in + gy1 + gx0);
       if(c1 < DD_W) tile[r1][c1] = __ldg(in + gy1 + gx1);
     }
+    __syncthreads();
   }
-  __syncthreads();
   const int x = blockIdx.x * 32 + threadIdx.x, y = BAND_BY * 8 + threadIdx.y;
   if(x >= w || y >= h || BAND_SKIP(y)) return;
   const int lx = threadIdx.x + 2, ly = threadIdx.y + 2;
