@@ -623,3 +623,41 @@ def test_parameter_variants_end_to_end(gpu, oracle, name):
         assert p >= 60.0 and (err > 1e-3).mean() <= 1e-4 and err.max() <= 5e-2
     else:
         parity_gate(got[..., :3], want[..., :3], "variant " + name)
+
+
+@pytest.mark.parametrize("src,packed", [("i-raw", False), ("i-mlv", True)])
+def test_prefetched_upload_matches_the_plain_run(gpu, src, packed):
+    """an upload on its own (RUN_UPLOAD, nothing else) prefetches the next source on the executor's upload stream while the
+    frame before may still be downloading; the recorded run behind it must see exactly that source."""
+    w, h = 640, 482
+    frames = [synth.mosaic(w, h, seed=21 + k) for k in range(3)]
+    bufs = []
+    for raw in frames:
+        if packed:
+            words = synth.pack_bits_fast14(raw)
+            b = np.zeros(words.size + 64, dtype=np.uint16); b[:words.size] = words
+        else:
+            b = np.ascontiguousarray(raw)
+        bufs.append(b)
+    rp = gpu.raw_params(w, h, wb=WB, cam_to_rec2020=CAM, packed_bpp=14 if packed else 0)
+    want = []
+    for k in range(3):
+        out, g = _run_graph(gpu, frames[k], src=src, packed=packed)
+        want.append(out.copy()); g.close()
+    g = gpu.Graph(cfg_text=gpu.DARKROOM_CFG.format(src=src))
+    g.set_source(bufs[0].ctypes.data, rp)
+    g.set_sink_buffer(None, 0)
+    g.run()
+    ow, oh = g.sink_size()
+    out = np.zeros((oh, ow, 4), dtype=np.float32)
+    g.set_sink_buffer(out.ctypes.data, out.nbytes)
+    g.run(gpu.RUN_RECORD | gpu.RUN_UPLOAD | gpu.RUN_DOWNLOAD)          # frame 0, download in flight
+    for k in (1, 2):
+        g.set_source(bufs[k].ctypes.data, rp)
+        g.run(gpu.RUN_UPLOAD)                                          # prefetch frame k behind frame k-1's launches
+        g.run(gpu.RUN_WAIT)                                            # frame k-1 landed
+        assert np.array_equal(out, want[k - 1]), k - 1
+        g.run(gpu.RUN_RECORD | gpu.RUN_DOWNLOAD)                       # no upload flag: the prefetched source
+    g.run(gpu.RUN_WAIT)
+    assert np.array_equal(out, want[2])
+    g.close()

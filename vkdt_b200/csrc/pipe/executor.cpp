@@ -87,6 +87,11 @@ struct vkb_plan_t
   void *staging_up = 0; size_t staging_up_bytes = 0;     // pinned host
   void *staging_down = 0; size_t staging_down_bytes = 0; // pinned host
   cudaStream_t stream = 0;
+  // upload-only runs (VKB_RUN_UPLOAD_SOURCE alone) prefetch the next frame's source on a stream of their own: the copy waits
+  // for the launches that still read the old source, not for the download behind them, and the next recorded run waits for it
+  cudaStream_t up_stream = 0;
+  cudaEvent_t ev_src_free = 0, ev_src_ready = 0;
+  int src_prefetched = 0;
   std::vector<cudaEvent_t> ev;
   std::vector<plan_graph_t> graphs = std::vector<plan_graph_t>(4); // small cache keyed by the fingerprint of the launch arguments
   unsigned graph_next = 0;
@@ -103,6 +108,9 @@ static void plan_free(vkb_plan_t *p)
   if(p->staging_down) cudaFreeHost(p->staging_down);
   for(cudaEvent_t e : p->ev) cudaEventDestroy(e);
   for(plan_graph_t &cg : p->graphs) if(cg.exec) cudaGraphExecDestroy(cg.exec);
+  if(p->ev_src_free) cudaEventDestroy(p->ev_src_free);
+  if(p->ev_src_ready) cudaEventDestroy(p->ev_src_ready);
+  if(p->up_stream) cudaStreamDestroy(p->up_stream);
   if(p->stream) cudaStreamDestroy(p->stream);
   delete p;
 }
@@ -585,6 +593,9 @@ static int build_plan(dt_graph_t *g, bool with_device)
   // fresh device memory there unless the connector asks for s_conn_clear_once)
   for(const plan_buf_t &b : p->buf) if(b.frames == 2 && !b.external) cudaMemset((uint8_t *)p->pool + b.offset, 0, b.bytes * 2);
   cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&p->up_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&p->ev_src_free, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&p->ev_src_ready, cudaEventDisableTiming);
   if(p->staging_up_bytes && cudaHostAlloc(&p->staging_up, p->staging_up_bytes, cudaHostAllocDefault) != cudaSuccess)
   { plan_free(p); return vkb_set_error(VKB_ERR_OOM, "pinned upload staging allocation failed"); }
   p->ev.resize(nl + 1);
@@ -1006,10 +1017,18 @@ int dt_graph_run(dt_graph_t *g, uint32_t run)
   cudaSetDevice(g->device);
   const int parity = g->frame & 1;
   // sources with s_module_request_read_source re-upload every run (graph-run-modules.h:573-587)
+  // an upload on its own (no record, no download, no wait) is a prefetch: see up_stream above
+  const bool prefetch = (run & VKB_RUN_UPLOAD_SOURCE) && !(run & (VKB_RUN_RECORD_CMD_BUF | VKB_RUN_DOWNLOAD_SINK | VKB_RUN_WAIT_DONE));
+  const bool was_prefetched = p->src_prefetched && (run & VKB_RUN_RECORD_CMD_BUF) && !(run & VKB_RUN_UPLOAD_SOURCE);
+  if(was_prefetched) { cudaStreamWaitEvent(p->stream, p->ev_src_ready, 0); p->src_prefetched = 0; }
+  cudaStream_t up = p->stream;
+  if(prefetch) { up = p->up_stream; cudaStreamWaitEvent(up, p->ev_src_free, 0); }
+  else if((run & VKB_RUN_UPLOAD_SOURCE) && p->src_prefetched)
+  { cudaStreamWaitEvent(p->stream, p->ev_src_ready, 0); p->src_prefetched = 0; }   // a later plain upload overwrites the prefetched one, in order
   for(const plan_source_t &s : p->source)
   {
     dt_module_t *mod = &g->module[s.modid];
-    const bool want = (run & VKB_RUN_UPLOAD_SOURCE) || ((run & VKB_RUN_RECORD_CMD_BUF) && (mod->flags & s_module_request_read_source));
+    const bool want = (run & VKB_RUN_UPLOAD_SOURCE) || ((run & VKB_RUN_RECORD_CMD_BUF) && (mod->flags & s_module_request_read_source) && !was_prefetched);
     if(!want) continue;
     if(s.external)
     { // caller owned device memory: just repoint
@@ -1022,16 +1041,18 @@ int dt_graph_run(dt_graph_t *g, uint32_t run)
       if(ms && (s.packed_bpp || swd == ms->p.width))
       { // the caller's buffer already has the staging layout: copy straight from it (pinned if it came from vkb_host_alloc)
         const size_t payload = s.packed_bpp ? ((size_t)ms->p.width * ms->p.height * s.packed_bpp + 7) / 8 : s.bytes;
-        cudaMemcpyAsync(buf_ptr(p, s.buf_upload), ms->data, payload, cudaMemcpyHostToDevice, p->stream);
+        cudaMemcpyAsync(buf_ptr(p, s.buf_upload), ms->data, payload, cudaMemcpyHostToDevice, up);
         continue;
       }
     }
     if(!mod->so->read_source) return vkb_set_error(VKB_ERR_GRAPH, "source module %s has no read_source", dt_token_string(mod->name).c_str());
+    if(prefetch) { cudaStreamSynchronize(up); up = p->stream; } // file sources go through the one staging buffer: in stream order
     cudaStreamSynchronize(p->stream); // staging is reused
     dt_read_source_params_t rp = { &g->node[s.nodeid], 0, 0 };
     if(mod->so->read_source(mod, p->staging_up, &rp)) return vkb_set_error(VKB_ERR_IO, "read_source failed for %s:%s", dt_token_string(mod->name).c_str(), dt_token_string(mod->inst).c_str());
     cudaMemcpyAsync(buf_ptr(p, s.buf_upload), p->staging_up, s.bytes, cudaMemcpyHostToDevice, p->stream);
   }
+  if(prefetch && up == p->up_stream) { cudaEventRecord(p->ev_src_ready, up); p->src_prefetched = 1; }
   if(run & VKB_RUN_RECORD_CMD_BUF)
   {
     // commit_params for every module in traversal order (graph-run-modules.h:5-31)
@@ -1112,6 +1133,7 @@ int dt_graph_run(dt_graph_t *g, uint32_t run)
       }
     }
   }
+  if(run & VKB_RUN_RECORD_CMD_BUF) cudaEventRecord(p->ev_src_free, p->stream);   // the launches above were the source's last readers
   if(run & VKB_RUN_DOWNLOAD_SINK)
   {
     for(const plan_sink_t &s : p->sink)
