@@ -166,6 +166,9 @@ VKB_API int  vkb_graph_replace_display(vkb_graph_t *g, const char *sink_module);
  * src/pipe/module.h:23-62: prim 1 sRGB/rec709, 2 bt2020, 3 AdobeRGB, 4 P3, 5 XYZ; trc 0 linear, 1 rec709, 2 sRGB, 3 PQ, 4 DCI, 5 HLG,
  * 6 gamma 2.2).  a colenc module is put in front of the sink when the sink is 8 bit or prim / trc are not bt2020 / linear */
 VKB_API int  vkb_graph_replace_display_ex(vkb_graph_t *g, const char *inst, const char *sink_module, int prim, int trc);
+/* the same with an output size limit (cli --width / --height, dt_graph_export's max_width / max_height, graph-export.c:170-180,
+ * 54-62, 93-94): a `resize` module (src/pipe/modules/resize) goes in front of the sink and the sink's roi request shrinks to fit */
+VKB_API int  vkb_graph_replace_display_sized(vkb_graph_t *g, const char *inst, const char *sink_module, int prim, int trc, int max_width, int max_height);
 /* feed a source module from memory instead of a file (what read_source() would have written into the mapped
  * staging buffer): an already decoded u16 mosaic + the dt_image_params_t fields the source module would fill
  * (src/pipe/module.h:72-109).  the pointer must stay valid until the run that uploads it finished. */

@@ -47,7 +47,7 @@ void dt_raytrace_graph_cleanup(dt_graph_t *graph) {}
   void M##_ref_create_nodes(dt_graph_t *, dt_module_t *); void M##_ref_modify_roi_out(dt_graph_t *, dt_module_t *); \
   void M##_ref_modify_roi_in(dt_graph_t *, dt_module_t *); int M##_ref_init(dt_module_t *); void M##_ref_cleanup(dt_module_t *); \
   void M##_ref_commit_params(dt_graph_t *, dt_module_t *);
-REF_DECL(imlv) REF_DECL(ipfm) REF_DECL(denoise) REF_DECL(hilite) REF_DECL(demosaic) REF_DECL(llap) REF_DECL(filmcurv) REF_DECL(crop) REF_DECL(colour)
+REF_DECL(imlv) REF_DECL(ipfm) REF_DECL(denoise) REF_DECL(hilite) REF_DECL(demosaic) REF_DECL(llap) REF_DECL(filmcurv) REF_DECL(crop) REF_DECL(colour) REF_DECL(resize)
 
 static const ref_nodes_in_t *ref_src; /* what the stand-in source hands over */
 static void src_modify_roi_out(dt_graph_t *graph, dt_module_t *mod)
@@ -86,7 +86,7 @@ static int ref_pipe_init(const char *basedir)
 #define BIND(M, RO, RI, IN, CP) { dt_module_so_t *so = so_get(#M); if(!so) return -10; so->create_nodes = M##_ref_create_nodes; \
     if(RO) so->modify_roi_out = M##_ref_modify_roi_out; if(RI) so->modify_roi_in = M##_ref_modify_roi_in; \
     if(IN) so->init = M##_ref_init; if(CP) so->commit_params = M##_ref_commit_params; }
-    BIND(denoise, 1, 1, 1, 0) BIND(hilite, 0, 0, 0, 0) BIND(demosaic, 1, 1, 0, 0) BIND(llap, 0, 0, 0, 0) BIND(filmcurv, 1, 0, 0, 0)
+    BIND(denoise, 1, 1, 1, 0) BIND(hilite, 0, 0, 0, 0) BIND(demosaic, 1, 1, 0, 0) BIND(llap, 0, 0, 0, 0) BIND(filmcurv, 1, 0, 0, 0) BIND(resize, 1, 1, 0, 0)
     { dt_module_so_t *so = so_get("denoise"); so->cleanup = denoise_ref_cleanup; }
     { dt_module_so_t *so = so_get("crop"); if(!so) return -10; so->modify_roi_out = crop_ref_modify_roi_out; so->modify_roi_in = crop_ref_modify_roi_in; so->init = crop_ref_init; so->commit_params = crop_ref_commit_params; }
     { dt_module_so_t *so = so_get("colour"); if(!so) return -10; so->modify_roi_out = colour_ref_modify_roi_out; so->modify_roi_in = colour_ref_modify_roi_in; so->init = colour_ref_init; so->commit_params = colour_ref_commit_params; so->create_nodes = colour_ref_create_nodes; }
@@ -113,6 +113,7 @@ int ref_graph_describe(const char *basedir, const char *cfgfile, const char *ext
   g->params_max = 16u << 20; g->params_pool = calloc(1, g->params_max);
   g->conn_image_max = 30*2*2000; g->conn_image_pool = calloc(sizeof(dt_connector_image_t), g->conn_image_max);
   int ret = -20;
+  int max_wd = 0, max_ht = 0;
   if(dt_graph_read_config_ascii(g, cfgfile)) goto done;
   if(extra && extra[0])
   {
@@ -121,13 +122,15 @@ int ref_graph_describe(const char *basedir, const char *cfgfile, const char *ext
     {
       char *e = strchr(c, '\n'); if(e) *e++ = 0;
       char line[4096]; snprintf(line, sizeof(line), "%s", c);
+      /* "#export:max:<w>:<h>": vkdt-cli --width / --height (cli/main.c:68-71 -> dt_graph_export -> replace_display's resize) */
+      if(!strncmp(line, "#export:max:", 12)) { sscanf(line + 12, "%d:%d", &max_wd, &max_ht); c = e; continue; }
       if(line[0] && dt_graph_read_config_line(g, line) < 0) { free(copy); ret = -21; goto done; }
       c = e;
     }
     free(copy);
   }
   /* what vkdt-cli does (cli/main.c, graph-export.c:160-230): the main display becomes the output module, linear rec2020 */
-  if(dt_graph_replace_display(g, dt_token("main"), 0, dt_token(sink), 0, 0, 0, s_colour_primaries_2020, s_colour_trc_linear) < 0) { ret = -22; goto done; }
+  if(dt_graph_replace_display(g, dt_token("main"), 0, dt_token(sink), max_wd > 0 || max_ht > 0, max_wd, max_ht, s_colour_primaries_2020, s_colour_trc_linear) < 0) { ret = -22; goto done; }
   dt_graph_disconnect_display_modules(g);
   {
     dt_graph_run_t run = s_graph_run_roi | s_graph_run_create_nodes;

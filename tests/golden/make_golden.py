@@ -208,6 +208,15 @@ GRAPH_CASES = NODE_CASES + [  # parameter lines travel through the reference's o
     (["param:colour:01:matrix:2", "param:colour:01:mat:1.1:-0.05:-0.05:0.02:0.9:0.08:0.0:-0.1:1.1", "param:colour:01:clip:1"], 512, 384, dict(wb=(1.9, 1.0, 1.7))),
     (["param:filmcurv:01:light:2.5", "param:filmcurv:01:contrast:1.4", "param:filmcurv:01:colour:1", "param:llap:01:clarity:0.5", "param:llap:01:sigma:0.2",
       "param:grade:01:gain:1.1:1.0:0.9:1.0", "param:hilite:01:white:0.9", "param:denoise:01:luma:0.3", "param:demosaic:01:colour:1"], 516, 390, dict(filters=9)),
+    # "#export:max:<w>:<h>": vkdt-cli --width / --height, i.e. dt_graph_replace_display with a resize module (blur + slice above a
+    # factor of three, catmull-rom below, bypass when nothing shrinks)
+    (["#export:max:200:200"], 640, 480, {}),
+    (["#export:max:400:0", "param:denoise:01:strength:0.3"], 640, 480, dict(wb=(2.0, 1.0, 1.5))),
+    (["#export:max:0:500"], 1002, 666, dict(filters=9)),
+    (["#export:max:1000:1000"], 322, 246, {}),
+    # feedback edges through the module pass (second traversal round, frames = 2)
+    (["feedback:grade:01:output:colour:01:spectra"], 640, 480, {}),
+    (["feedback:llap:01:output:colour:01:spectra", "param:denoise:01:strength:0.3"], 1002, 668, {}),
 ]
 
 

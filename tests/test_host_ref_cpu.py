@@ -234,10 +234,15 @@ def _graph_text_product(case):
         for ln in case["lines"]:
             assert g.line(ln) == 0, ln
         return g.describe().splitlines()
-    g = api.Graph(cfg_text=api.DARKROOM_CFG.format(src="i-raw"))
+    mw = mh = 0
+    for ln in case["lines"]:    # "#export:max:<w>:<h>": the cli's --width / --height (a resize module in front of the sink)
+        if ln.startswith("#export:max:"):
+            mw, mh = [int(x) for x in ln.split(":")[2:4]]
+    g = api.Graph(cfg_text=api.DARKROOM_CFG.format(src="i-raw"), max_width=mw, max_height=mh)
     assert g.line("param:i-raw:main:filename:none.raw") == 0   # the last line of the reference's default-darkroom.i-raw
     for ln in case["lines"]:
-        assert g.line(ln) == 0, ln
+        if not ln.startswith("#"):
+            assert g.line(ln) == 0, ln
     buf = np.zeros((case["h"], case["w"]), np.uint16)
     kw = dict(case["raw"])
     for k in ("wb", "crop_aabb"):
@@ -265,7 +270,8 @@ def test_product_module_pass_matches_reference_graph_code():
         assert len(ref) == len(got), (case["lines"], case["w"], case["h"], len(ref), len(got))
         bad = [(a[:200], b[:200]) for a, b in zip(ref, got) if a != b]
         assert not bad, (case["lines"], case["w"], case["h"], bad[:3])
-    assert len(GRAPHS) >= 25 and sum("mlv" in c for c in GRAPHS) == 2 and sum("pfm" in c for c in GRAPHS) == 1
+    assert len(GRAPHS) >= 31 and sum("mlv" in c for c in GRAPHS) == 2 and sum("pfm" in c for c in GRAPHS) == 1
+    assert sum(any(l.startswith("#export:max") for l in c["lines"]) for c in GRAPHS) == 4 and sum(any(l.startswith("feedback:") for l in c["lines"]) for c in GRAPHS) == 2
 
 
 def test_live_reference_graph_random(oracle):

@@ -247,7 +247,7 @@ param:llap:01:clarity:0.2
 class Graph:
     """dt_graph_t behind the C-ABI: read cfg lines, feed a source from memory, run, fetch the sink."""
 
-    def __init__(self, cfg_text=None, cfg_file=None, sink="o-pfm", prim=None, trc=None):
+    def __init__(self, cfg_text=None, cfg_file=None, sink="o-pfm", prim=None, trc=None, max_width=0, max_height=0):
         self.h = C.c_void_p(lib.vkb_graph_new())
         self._keep = []
         if cfg_file:
@@ -257,7 +257,11 @@ class Graph:
                 r = lib.vkb_graph_read_config_line(self.h, line.encode())
                 if r < 0:
                     raise VkbError(r, "config line failed: " + line)
-        if sink and (prim is not None or trc is not None):
+        if sink and (max_width or max_height):   # cli --width / --height: a resize module in front of the sink
+            lib.vkb_graph_replace_display_sized.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
+            check(lib.vkb_graph_replace_display_sized(self.h, b"main", sink.encode(), 2 if prim is None else prim, 0 if trc is None else trc,
+                                                      int(max_width), int(max_height)))
+        elif sink and (prim is not None or trc is not None):
             check(lib.vkb_graph_replace_display_ex(self.h, b"main", sink.encode(), 2 if prim is None else prim, 0 if trc is None else trc))
         elif sink:
             check(lib.vkb_graph_replace_display(self.h, sink.encode()))

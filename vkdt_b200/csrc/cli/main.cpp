@@ -30,6 +30,8 @@ static int usage()
       "    [--quality <0-100>]           (jpg) output quality\n"
       "    [--filename <f>]              output filename (without extension or frame number)\n"
       "    [--format <fm>]               output format (o-jpg, o-pfm, o-null)\n"
+      "    [--width <x>]                 max output width\n"
+      "    [--height <y>]                max output height\n"
       "    [--colour-prim <prim-id>]     colour primaries to use for encoding, one of: sRGB, bt2020, AdobeRGB, P3, XYZ\n"
       "    [--colour-trc <trc-id>]       tone response curve for encoding, one of: linear, 709, sRGB, PQ, DCI, HLG, gamma2.2\n"
       "    [--output <inst>]             name the instance of the display to replace (default: main)\n"
@@ -66,6 +68,7 @@ struct opts_t
   const char *cfg = 0, *format = "o-jpg", *filename = "output", *inst = "main";
   int device = 0, perf = 0, mem = 0, dump = 0, last_only = 0, progress = 0, gpus = 1, bands = 0, fast = 0;
   int prim = 1, trc = 1; float quality = -1.0f;
+  int max_width = 0, max_height = 0;
   int config_start = 0, argc = 0; char **argv = 0;
 };
 
@@ -77,7 +80,7 @@ static vkb_graph_t *make_graph(const opts_t &o, int device)
   vkb_graph_set_perf(g, o.perf);
   if(o.fast) vkb_graph_set_mode(g, VKB_MODE_FAST);
   if(vkb_graph_read_config_ascii(g, o.cfg)) { fprintf(stderr, "[cli] %s\n", vkb_last_error()); vkb_graph_free(g); return 0; }
-  if(vkb_graph_replace_display_ex(g, o.inst, o.format, o.prim, o.trc)) { fprintf(stderr, "[cli] %s\n", vkb_last_error()); vkb_graph_free(g); return 0; }
+  if(vkb_graph_replace_display_sized(g, o.inst, o.format, o.prim, o.trc, o.max_width, o.max_height)) { fprintf(stderr, "[cli] %s\n", vkb_last_error()); vkb_graph_free(g); return 0; }
   if(o.config_start) for(int i = o.config_start; i < o.argc; i++) vkb_graph_read_config_line(g, o.argv[i]);
   char line[1024];
   snprintf(line, sizeof(line), "param:%s:%s:filename:%s", o.format, o.inst, o.filename);
@@ -114,8 +117,8 @@ int main(int argc, char *argv[])
     else if(!strcmp(argv[i], "--fast")) o.fast = 1;
     else if(!strcmp(argv[i], "--last-frame-only")) o.last_only = 1;
     else if(!strcmp(argv[i], "--progress")) o.progress = 1;
-    else if((!strcmp(argv[i], "--width") || !strcmp(argv[i], "--height")) && i + 1 < argc)
-    { fprintf(stderr, "[cli] %s %s ignored: the resize module is not on this path, the export keeps the graph's size\n", argv[i], argv[i + 1]); i++; }
+    else if(!strcmp(argv[i], "--width") && i + 1 < argc) o.max_width = (int)atof(argv[++i]);    // cli/main.c:68-71
+    else if(!strcmp(argv[i], "--height") && i + 1 < argc) o.max_height = (int)atof(argv[++i]);
     else if(!strcmp(argv[i], "--audio") && i + 1 < argc) i++;
     else if(!strcmp(argv[i], "--config")) { o.config_start = i + 1; break; }
     else return usage();

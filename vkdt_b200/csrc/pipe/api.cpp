@@ -62,6 +62,15 @@ int vkb_graph_replace_display_ex(vkb_graph_t *h, const char *inst, const char *s
   dt_graph_disconnect_display_modules(h->g);
   return VKB_OK;
 }
+int vkb_graph_replace_display_sized(vkb_graph_t *h, const char *inst, const char *sink_module, int prim, int trc, int max_width, int max_height)
+{ // graph-export.c:170-180: a resize module is inserted when either limit is given
+  if(!h || max_width < 0 || max_height < 0) return VKB_ERR_BAD_ARG;
+  const int m = dt_graph_replace_display(h->g, dt_token(inst && inst[0] ? inst : "main"), dt_token(sink_module && sink_module[0] ? sink_module : "o-jpg"), prim, trc,
+      max_width > 0 || max_height > 0, max_width, max_height);
+  if(m < 0) return vkb_set_error(VKB_ERR_GRAPH, "replace display failed (%d)", m);
+  dt_graph_disconnect_display_modules(h->g);
+  return VKB_OK;
+}
 int vkb_graph_replace_display(vkb_graph_t *h, const char *sink_module)
 {
   if(!h) return VKB_ERR_BAD_ARG;

@@ -557,19 +557,28 @@ int dt_graph_read_config_ascii(dt_graph_t *g, const char *filename)
   return 0;
 }
 
-// graph-export.c:23-96 (no resize / colenc: the hot path exports linear rec2020 f32)
-int dt_graph_replace_display(dt_graph_t *g, dt_token_t inst, dt_token_t mod, int prim, int trc)
-{ // graph-export.c:23-96 without the resize branch
+// graph-export.c:23-96
+int dt_graph_replace_display(dt_graph_t *g, dt_token_t inst, dt_token_t mod, int prim, int trc, int resize, int max_wd, int max_ht)
+{
   if(inst == 0) inst = dt_token("main");
   const int mid = dt_module_get(g, dt_token("display"), inst);
   if(mid < 0) return -1;
   const int cid = dt_module_get_connector(&g->module[mid], dt_token("input"));
-  const int m0 = g->module[mid].connector[cid].connected.i, o0 = g->module[mid].connector[cid].connected.c;
+  int m0 = g->module[mid].connector[cid].connected.i, o0 = g->module[mid].connector[cid].connected.c;
   if(m0 < 0) return -2;
   if(mod == 0) mod = dt_token("o-pfm");
+  if(resize)
+  { // :54-62: a resize module between the graph and the output
+    const int m1 = dt_module_add(g, dt_token("resize"), inst);
+    if(m1 < 0) return -3;
+    if(dt_module_connect(g, m0, o0, m1, 0)) return -4;
+    m0 = m1; o0 = 1;
+  }
   const int m2 = dt_module_add(g, mod, inst);
   if(m2 < 0) return -3;
   const int i2 = dt_module_get_connector(&g->module[m2], dt_token("input"));
+  g->module[m2].connector[i2].max_wd = max_wd;   // :93-94
+  g->module[m2].connector[i2].max_ht = max_ht;
   if(g->module[m2].connector[i2].format == dt_token("ui8") || prim != 2 || trc != 0)
   { // :66-86: 8 bit sinks and other colour spaces than linear bt2020 get a colenc module in front
     const int m1 = dt_module_add(g, dt_token("colenc"), inst);

@@ -40,6 +40,7 @@ static const module_def_t g_defs[] = {
                 "lift:float:4:0.0:0.0:0.0:0\ngamma:float:4:1.0:1.0:1.0:0\ngain:float:4:1.0:1.0:1.0:0\noffset:float:4:0.0:0.0:0.0:0\n"
                 "mode:int:1:0\nsh_pivot:float:1:0.3\nhi_pivot:float:1:0.4" },
   { "colenc",   "input:read:rgba:*\noutput:write:rgba:*", "prim:int:1:1\ntrc:int:1:0" },
+  { "resize",   "input:read:*:*\noutput:write:*:*", "width:int:1:0\nheight:int:1:0" },
   { "o-pfm",    "input:sink:rgba:f32", "filename:string:256:output" },
   { "o-jpg",    "input:sink:rgba:ui8", "filename:string:256:output\nquality:float:1:95\nexif:int:1:1" },
   { "o-null",   "input:sink:*:*", "" },
@@ -152,6 +153,9 @@ static void llap_create_nodes(dt_graph_t *, dt_module_t *);
 static void opfm_write_sink(dt_module_t *, void *, dt_write_sink_params_t *);
 static void ojpg_write_sink(dt_module_t *, void *, dt_write_sink_params_t *);
 static void colenc_roi_out(dt_graph_t *, dt_module_t *);
+static void resize_roi_out(dt_graph_t *, dt_module_t *);
+static void resize_roi_in(dt_graph_t *, dt_module_t *);
+static void resize_create_nodes(dt_graph_t *, dt_module_t *);
 
 // ---- module discovery (global.c:86-415, :442): <basedir>/modules/<name>/{connectors,params} are the source of truth when a
 // vkdt installation (or checkout: basedir = <vkdt>/src/pipe) is named by vkb_set_basedir() / VKDT_B200_BASEDIR; the built-in
@@ -252,6 +256,7 @@ static std::vector<dt_module_so_t> &registry()
     if(n == "o-pfm")    { so.write_sink = opfm_write_sink; }
     if(n == "o-jpg")    { so.write_sink = ojpg_write_sink; }
     if(n == "colenc")   { so.modify_roi_out = colenc_roi_out; }
+    if(n == "resize")   { so.modify_roi_out = resize_roi_out; so.modify_roi_in = resize_roi_in; so.create_nodes = resize_create_nodes; }
     r.push_back(so);
   }
   return r;
@@ -1233,6 +1238,76 @@ static void colenc_roi_out(dt_graph_t *, dt_module_t *module)
   module->img_param.colour_trc       = dt_module_param_int(module, dt_module_get_param(module->so, dt_token("trc")))[0];
   module->connector[1].roi.full_wd = module->connector[0].roi.full_wd;
   module->connector[1].roi.full_ht = module->connector[0].roi.full_ht;
+}
+
+// ------------------------------------------------------------------------------------------------
+// resize (resize/main.c): what `vkdt-cli --width / --height` puts in front of the sink (graph-export.c:54-62).  the sink's
+// max_wd / max_ht shrink its roi request (graph-run-modules.h:458-476), this module asks its input for the full image
+// and rescales: catmull-rom when minifying (behind a separable gaussian above a factor of three), flower taps when magnifying
+static void resize_roi_out(dt_graph_t *, dt_module_t *module)
+{ // resize/main.c:6-27
+  module->connector[1].roi = module->connector[0].roi;
+  const int wd = dt_module_param_int(module, 0)[0], ht = dt_module_param_int(module, 1)[0];
+  if(!wd || !ht) { module->connector[1].roi.marker = s_roi_mark_soft_fwd; return; }
+  const double scale = std::min(1.0, std::min(wd / (double)module->connector[1].roi.full_wd, ht / (double)module->connector[1].roi.full_ht));
+  if(scale < 1.0)
+  {
+    module->connector[1].roi.full_wd = (int)(module->connector[0].roi.full_wd * scale + 0.5);
+    module->connector[1].roi.full_ht = (int)(module->connector[0].roi.full_ht * scale + 0.5);
+  }
+}
+static void resize_roi_in(dt_graph_t *, dt_module_t *module)
+{ // resize/main.c:29-39: request the full thing, we'll rescale
+  module->connector[0].roi.wd = module->connector[0].roi.full_wd;
+  module->connector[0].roi.ht = module->connector[0].roi.full_ht;
+  module->connector[0].roi.marker = (module->connector[1].roi.marker & ~s_roi_mark_hard) | s_roi_mark_soft;
+}
+// modules/api.h:506-578 dt_api_blur_sep: two nodes (shared, blurh) -> (shared, blurv) with the input's channels, format and roi;
+// returns blurv, *id_in = blurh.  nodeid_input < 0: the module's connector is the input (wired by the caller with dt_connector_copy)
+static int api_blur_sep(dt_graph_t *g, dt_module_t *module, int nodeid_input, int connid_input, int *id_in, float radius)
+{
+  const dt_connector_t ci = nodeid_input >= 0 ? g->node[nodeid_input].connector[connid_input] : module->connector[connid_input];
+  const int dp = ci.array_length > 0 ? ci.array_length : 1;
+  const std::string chan = dt_token_string(ci.chan), format = dt_token_string(ci.format);
+  int id[2];
+  for(int k = 0; k < 2; k++)
+  {
+    id[k] = dt_node_add(g, module, "shared", k ? "blurv" : "blurh", ci.roi.wd, ci.roi.ht, dp, sizeof(float), &radius, 2,
+        "input", "read", chan.c_str(), format.c_str(), dt_no_roi,
+        "output", "write", chan.c_str(), format.c_str(), &ci.roi);
+    for(int c = 0; c < 2; c++)
+    { // the reference fills both connectors from the input's (roi, array length), connected = unset
+      g->node[id[k]].connector[c].roi = ci.roi;
+      g->node[id[k]].connector[c].array_length = ci.array_length;
+    }
+    g->node[id[k]].connector[0].connected = s_cid_unset;
+  }
+  if(nodeid_input >= 0) CONN(dt_node_connect(g, nodeid_input, connid_input, id[0], 0));
+  CONN(dt_node_connect(g, id[0], 1, id[1], 0));
+  if(id_in) *id_in = id[0];
+  return id[1];
+}
+static void resize_create_nodes(dt_graph_t *g, dt_module_t *module)
+{ // resize/main.c:57-83
+  if(module->connector[0].roi.wd == module->connector[1].roi.wd && module->connector[0].roi.ht == module->connector[1].roi.ht)
+    return dt_connector_bypass(g, module, 0, 1);
+  const float scale = module->connector[0].roi.wd / (float)module->connector[1].roi.wd;   // downscaling factor
+  int mode = scale < 0.99f ? 0 : scale > 1.01f ? 2 : 1;                                    // magnify / 1:1 / minify
+  if(scale > 3) mode = 1;                                                                  // slice after blur
+  const int32_t pc[] = { mode };
+  const int id_resize = dt_node_add(g, module, "resize", "main", module->connector[1].roi.wd, module->connector[1].roi.ht, 1, sizeof(pc), pc, 2,
+      "input", "read", "*", "*", dt_no_roi,
+      "output", "write", "rgba", "f16", &module->connector[1].roi);
+  if(scale > 3)
+  { // 3x3 is the natural support of the catmull-rom spline: blur above that only.  radius in px = 3 sigma
+    const float blur = scale + 0.5f;
+    int id_blur_in = -1;
+    const int id_blur = api_blur_sep(g, module, -1, 0, &id_blur_in, blur);
+    CONN(dt_node_connect_named(g, id_blur, "output", id_resize, "input"));
+    dt_connector_copy(g, module, 0, id_blur_in, 0);
+  }
+  else dt_connector_copy(g, module, 0, id_resize, 0);
+  dt_connector_copy(g, module, 1, id_resize, 1);
 }
 
 // o-jpg/main.c:102-172 with an own baseline encoder (pipe/jpeg.cpp); no icc profile, no exif copy (needs exiftool)

@@ -222,7 +222,7 @@ int  dt_node_connect(dt_graph_t *g, int n0, int c0, int n1, int c1);
 int  dt_node_connect_named(dt_graph_t *g, int n0, const char *c0, int n1, const char *c1);
 int  dt_graph_read_config_line(dt_graph_t *g, char *line);
 int  dt_graph_read_config_ascii(dt_graph_t *g, const char *filename);
-int  dt_graph_replace_display(dt_graph_t *g, dt_token_t inst, dt_token_t mod, int prim, int trc);
+int  dt_graph_replace_display(dt_graph_t *g, dt_token_t inst, dt_token_t mod, int prim, int trc, int resize = 0, int max_wd = 0, int max_ht = 0);
 void dt_graph_disconnect_display_modules(dt_graph_t *g);
 int  dt_graph_run(dt_graph_t *g, uint32_t runflags);
 void dt_graph_apply_keyframes(dt_graph_t *g);           // graph.c:1025
