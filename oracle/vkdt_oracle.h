@@ -50,6 +50,9 @@ void o_hilite_doub(const oimg_t *in, const oimg_t *coarse, oimg_t *out, const o_
 void o_demosaic_down(const oimg_t *in, oimg_t *out, uint32_t filters);
 void o_demosaic_halfsize(const oimg_t *in, oimg_t *out, uint32_t filters);
 void o_resample(const oimg_t *in, oimg_t *out);
+/* resize/main.comp (mode 0 magnify / 1 slice / 2 minify), shared/blurh.comp + blurv.comp */
+void o_resize_main(const oimg_t *in, oimg_t *out, int mode, int out_f16);
+void o_blur_sep(const oimg_t *in, oimg_t *out, float radius, int vertical, int out_f16);
 void o_rcd_conv(const oimg_t *cfa, oimg_t *vh, oimg_t *pq, oimg_t *lp);
 void o_rcd_fill(const oimg_t *cfa, const oimg_t *vh, const oimg_t *pq, const oimg_t *lp, oimg_t *out, const float *wb);
 void o_demosaic_gauss(const oimg_t *orig, oimg_t *out, uint32_t filters);

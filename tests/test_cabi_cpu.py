@@ -237,6 +237,11 @@ def test_cli_dump_nodes_without_a_gpu(tmp_path):
     assert r.stdout.lstrip().startswith("digraph") and "hilite_reduce" in r.stdout and "llap_curve" in r.stdout and "o-jpg_main" in r.stdout and "colenc_main" in r.stdout
     r = subprocess.run([cli, "-g", str(cfg), "--dump-nodes", "--format", "o-pfm", "--colour-prim", "bt2020", "--colour-trc", "linear"], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and "o-pfm_main" in r.stdout and "colenc" not in r.stdout
+    # --width / --height (cli/main.c:68-71): a resize module in front of the sink; beyond a factor of three behind a separable blur
+    r = subprocess.run([cli, "-g", str(cfg), "--dump-nodes", "--width", "250"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "resize_main" in r.stdout and "shared_blurh" not in r.stdout and "colenc_main" in r.stdout, r.stdout + r.stderr
+    r = subprocess.run([cli, "-g", str(cfg), "--dump-nodes", "--width", "100", "--height", "100"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "resize_main" in r.stdout and "shared_blurh" in r.stdout and "shared_blurv" in r.stdout, r.stdout + r.stderr
     r = subprocess.run([cli, "-g", str(tmp_path / "missing.cfg"), "--dump-nodes"], capture_output=True, text=True, timeout=60)
     assert r.returncode != 0
     r = subprocess.run([cli, "--bogus"], capture_output=True, text=True, timeout=60)

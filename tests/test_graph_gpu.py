@@ -661,3 +661,53 @@ def test_prefetched_upload_matches_the_plain_run(gpu, src, packed):
     g.run(gpu.RUN_WAIT)
     assert np.array_equal(out, want[2])
     g.close()
+
+
+@pytest.mark.parametrize("limit", [(300, 0), (0, 110), (150, 150), (1000, 1000), (634, 0)])
+def test_export_with_a_size_limit(gpu, oracle, limit):
+    """vkdt-cli --width / --height (graph-export.c:54-62, 93-94): a resize module in front of the sink.  catmull-rom below a
+    factor of three, gaussian blur + slice above, flower taps when the limit is LARGER than the image (the reference's sink fits
+    its request to the limit both ways, graph-run-modules.h:466-471), nothing at 1:1; against the oracle's restatement of
+    resize/main.comp and shared/blur{h,v}.comp on the oracle's own darkroom output."""
+    w, h = 640, 482
+    raw = synth.mosaic(w, h, seed=31)
+    d = oracle.darkroom_defaults(w, h)
+    for k in range(3): d.whitebalance[k] = WB[k]
+    for k in range(9): d.cam_to_rec2020[k] = CAM[k]
+    full = oracle.darkroom_run(d, raw)
+    ih, iw = full.shape[:2]
+    mw, mh = limit
+    sx = iw / mw if mw else 1.0
+    sy = ih / mh if mh else 1.0
+    s = np.float32(max(sx, sy))                       # graph-run-modules.h:466-471 in fp32
+    ow, oh = int(np.float32(iw) / s + np.float32(0.5)), int(np.float32(ih) / s + np.float32(0.5))
+    L = oracle.lib()
+    L.o_blur_sep.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int]
+    if (ow, oh) == (iw, ih):
+        want = full
+    else:
+        src = full.astype(np.float16).astype(np.float32)      # grade's output is an f16 edge once a module follows it
+        src[..., 3] = 1.0
+        scale = np.float32(iw) / np.float32(ow)
+        mode = 0 if scale < 0.99 else (2 if scale > 1.01 else 1)
+        if scale > 3:
+            mode = 1
+            bh, bhi = oracle.new_img(ih, iw, 4)
+            L.o_blur_sep(C.byref(oracle.img(src)), C.byref(bhi), float(scale + np.float32(0.5)), 0, 1)
+            bv, bvi = oracle.new_img(ih, iw, 4)
+            L.o_blur_sep(C.byref(oracle.img(bh)), C.byref(bvi), float(scale + np.float32(0.5)), 1, 1)
+            src = bv
+        want, wi = oracle.new_img(oh, ow, 4)
+        L.o_resize_main(C.byref(oracle.img(src)), C.byref(wi), mode, 0)
+    g = gpu.Graph(cfg_text=gpu.DARKROOM_CFG.format(src="i-raw"), max_width=mw, max_height=mh)
+    buf = np.ascontiguousarray(raw)
+    g.set_source(buf.ctypes.data, gpu.raw_params(w, h, wb=WB, cam_to_rec2020=CAM))
+    g.set_sink_buffer(None, 0)
+    g.run()
+    assert g.sink_size() == (ow, oh), (g.sink_size(), ow, oh)
+    out = np.zeros((oh, ow, 4), dtype=np.float32)
+    g.set_sink_buffer(out.ctypes.data, out.nbytes)
+    g.run(gpu.RUN_RECORD | gpu.RUN_UPLOAD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT)
+    plan = g.plan_text() if hasattr(g, "plan_text") else ""
+    assert np.array_equal(out[..., :3], want[..., :3]), (limit, float(np.abs(out[..., :3] - want[..., :3]).max()), plan)
+    g.close()

@@ -74,12 +74,10 @@ def test_feedback_lines_flag_the_graph():
     assert g.line("feedback:grade:01:output:grade:02:input") == 0
     assert g.has_feedback()
     g.close()
-    # a graph that REACHES a feedback connector is refused by the planner (double buffered connectors are not built)
+    # a graph that reaches a feedback connector plans with a double buffered owner (tests/test_feedback.py runs one)
     g = api.Graph(cfg_text=api.DARKROOM_CFG.format(src="i-raw"))
     assert g.line("feedback:grade:01:output:colour:01:spectra") == 0
     raw = np.zeros((384, 512), dtype=np.uint16)
     g.set_source(raw.ctypes.data, api.raw_params(512, 384))
-    with pytest.raises(api.VkbError) as e:
-        g.plan()
-    assert "feedback" in str(e.value), str(e.value)
+    assert "[x2]" in g.plan()
     g.close()

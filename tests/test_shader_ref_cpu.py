@@ -384,6 +384,27 @@ def cases(O):
             got = np.zeros((oh, ow, 4), np.float32)
             O.ref_shader("shared", "resample", b"", b"", [[(a, 0)], [(got, 1)]], ow, oh)
             return [want], [got]
+    # the export side's resize module: slice / flower (magnify) / catmull-rom (minify), f16 and f32 outputs, and the separable blur
+    for mode, (ow, oh), f16o in ((1, (30, 20), 0), (2, (60, 40), 1), (2, (41, 29), 1), (0, (150, 100), 1)):
+        @add("resize.main mode %d to %dx%d" % (mode, ow, oh))
+        def _(mode=mode, ow=ow, oh=oh, f16o=f16o):
+            a = rgba(np.random.default_rng(50 + mode), 96, 64, 0.0, 1.5)
+            want, wi = img_out(oh, ow, 4)
+            L.o_resize_main(C.byref(O.img(a)), C.byref(wi), mode, f16o)
+            got = np.zeros((oh, ow, 4), np.float32)
+            O.ref_shader("resize", "main", b"", np.array([mode], np.int32).tobytes(), [(a, 0), (got, f16o)], ow, oh)
+            return [want], [got]
+    for radius in (3.67, 4.0, 1.5, 0.7):
+        for vert in (0, 1):
+            @add("shared.blur%s radius %g" % ("v" if vert else "h", radius))
+            def _(radius=radius, vert=vert):
+                a = rgba(np.random.default_rng(55), 96, 64, 0.0, 1.5)
+                want, wi = img_out(64, 96, 4)
+                L.o_blur_sep.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int]
+                L.o_blur_sep(C.byref(O.img(a)), C.byref(wi), radius, vert, 1)
+                got = np.zeros((64, 96, 4), np.float32)
+                O.ref_shader("shared", "blurv" if vert else "blurh", b"", np.array([radius], np.float32).tobytes(), [[(a, 0)], [(got, 1)]], 96, 64)
+                return [want], [got]
     return out
 
 
@@ -403,7 +424,7 @@ def _f16_ulps(a, b):
 # kernels that FILTER (texture() at fractional coordinates): the shader computes its texture coordinates in fp32, the oracle is an
 # ideal sampler that carries them in double (oracle/o_common.h:122-143), so a weight can differ in its last bits and an
 # f16 store can then round the other way.  everything else is bit exact.
-SAMPLED = ("llap.reduce", "llap.assemble", "denoise.half..doub", "shared.resample")
+SAMPLED = ("llap.reduce", "llap.assemble", "denoise.half..doub", "shared.resample", "resize.main mode 0", "resize.main mode 2", "shared.blur")
 
 
 def _report(name, want, got):

@@ -319,6 +319,17 @@ static int build_plan(dt_graph_t *g, bool with_device)
     if((is_node(nd, "colour", "main") && c >= 2) || (is_node(nd, "denoise", "noop") && c == 2) || (is_node(nd, "denoise", "doub") && c == 4)) continue;
     B.consumers[{cn->connected.i, cn->connected.c}].push_back({n, c});
   }
+  // a module between the graph and an f32 sink that bypassed itself (resize at 1:1): the sink then hangs on an f16 edge.  the
+  // image a sink downloads has the sink's format (dt_graph_replace_display pushes it onto the producer, graph-export.c:88-91):
+  // do the same here when the sink is that edge's only reader
+  for(int n : B.order)
+  {
+    dt_connector_t *sc = &g->node[n].connector[0];
+    if(sc->type != dt_token("sink") || sc->connected.i < 0 || sc->connected.i >= (int)g->node.size()) continue;
+    dt_connector_t *oc = &g->node[sc->connected.i].connector[sc->connected.c];
+    if(sc->format == dt_token("f32") && oc->format == dt_token("f16") && B.consumers[{sc->connected.i, sc->connected.c}].size() == 1)
+      oc->format = dt_token("f32");
+  }
   // identity resample: alias output to input (demosaic/main.c:193-201 appends it in cli exports)
   for(int n : B.order)
   {
