@@ -247,6 +247,11 @@ VKB_API int  vkb_graph_plan(vkb_graph_t *g, char *buf, size_t bufsize);
 VKB_API int  vkb_graph_dump_nodes(vkb_graph_t *g, char *buf, size_t bufsize); /* --dump-nodes, graph-print.h:76 */
 /* device-resident variant for kernel-only timing: source already in HBM, sink left in HBM */
 VKB_API int  vkb_graph_set_source_device(vkb_graph_t *g, const char *inst, const void *d_data, const vkb_raw_params_t *p);
+/* an in-memory i-raw source's DNG OpcodeList2 tag (51009; big endian bytes as stored) and the cfa offset of the emitted window:
+ * what the reference's loader hands on as s_image_metadata_dngop (i-raw/main.c:62-92).  denoise applies its four Bayer GainMap
+ * opcodes (denoise/main.c:12-43, 172-200; noop.comp:48-57, doub.comp:106-114).  bytes == 0 removes it.  dng FILES carry their own. */
+VKB_API int  vkb_dng_opcodes_describe(const void *opcode_list, size_t bytes, char *out, size_t out_size); /* the decoded list as text (i-raw/dng_opcode_decode.c) */
+VKB_API int  vkb_graph_set_dng_opcodes(vkb_graph_t *g, const char *inst, const void *opcode_list2, size_t bytes, int cfa_off_x, int cfa_off_y);
 VKB_API int  vkb_graph_sink_device(vkb_graph_t *g, const char *inst, void **d_ptr);
 VKB_API uint64_t vkb_graph_pool_bytes(vkb_graph_t *g);
 VKB_API void *vkb_graph_stream(vkb_graph_t *g);                            /* the cudaStream_t the graph launches on (after the first run) */

@@ -17,6 +17,32 @@ void o_denoise_noop(const oimg_t *in, oimg_t *out, const int *crop, const float 
   }
 }
 
+/* the DNG GainMap branch of noop.comp:48-57 and doub.comp:106-114: a low resolution rgba f32 texture (one gain per cfa site of
+ * the 2x2 block) sampled at the pixel's position in the uncropped image; map_os = { origin x, origin y, 1 / extent x, 1 / extent y }
+ * (denoise/main.c:188-195).  block = 1: noop (full resolution position), 2: doub (position of the 2x2 block) */
+static float o_gainmap_gain(const oimg_t *gm, const float *map_os, int x, int y, int cx, int cy, int sw, int sh, int block)
+{
+  float px, py;
+  if(block == 1) { px = (0.5f + (float)(x + cx)) / (float)sw; py = (0.5f + (float)(y + cy)) / (float)sh; }
+  else           { px = (0.5f + (float)((x + cx) / 2)) / (float)(sw / 2); py = (0.5f + (float)((y + cy) / 2)) / (float)(sh / 2); }
+  px = o_clamp(px * map_os[2] - map_os[0], 0.0f, 1.0f);
+  py = o_clamp(py * map_os[3] - map_os[1], 0.0f, 1.0f);
+  float g[4];
+  o_tex4(gm, (double)px, (double)py, g);
+  return g[(x & 1) + (y & 1) * 2];
+}
+/* noop.comp with a gain map (bayer only: filters != 0 && filters != 9, push.gainmap == 1 && params.gainmap == 1) */
+void o_denoise_noop_gm(const oimg_t *in, oimg_t *out, const int *crop, const float *black, const float *white, const oimg_t *gm, const float *map_os)
+{
+#pragma omp parallel for schedule(static)
+  for(int y = 0; y < out->h; y++) for(int x = 0; x < out->w; x++)
+  {
+    float col = o_fetch1(in, x + crop[0], y + crop[1]);
+    col = o_max(0.0f, (col - black[0]) / (white[0] - black[0]));
+    col *= o_gainmap_gain(gm, map_os, x, y, crop[0], crop[1], in->w, in->h, 1);
+    o_store1(out, x, y, col, 1);
+  }
+}
 /* X-Trans colour at absolute position: demosaic/splat.comp:52-68, denoise/doub.comp:52-66.
  * returns 0 red, 1 green, 2 blue */
 int o_xtrans_colour(int x, int y)
@@ -283,6 +309,13 @@ void o_denoise_doub(const oimg_t *in, const oimg_t *crs0, const oimg_t *crs1, oi
     const o_denoise_params_t *p, const int *crop, const float *black4, const float *white4,
     float noise_a, float noise_b, uint32_t filters)
 {
+  o_denoise_doub_gm(in, crs0, crs1, out, p, crop, black4, white4, noise_a, noise_b, filters, 0, 0);
+}
+/* gm != 0: with the gain map branch (doub.comp:106-114; filters != 9 && push.gainmap == 1 && params.gainmap == 1) */
+void o_denoise_doub_gm(const oimg_t *in, const oimg_t *crs0, const oimg_t *crs1, oimg_t *out,
+    const o_denoise_params_t *p, const int *crop, const float *black4, const float *white4,
+    float noise_a, float noise_b, uint32_t filters, const oimg_t *gm, const float *map_os)
+{
 #pragma omp parallel for schedule(static)
   for(int y = 0; y < out->h; y++) for(int x = 0; x < out->w; x++)
   {
@@ -313,6 +346,7 @@ void o_denoise_doub(const oimg_t *in, const oimg_t *crs0, const oimg_t *crs1, oi
       val = o_mix(val, o_max(0.0f, crs + sigma[1] * o_sign(wav) * o_mix(o_max(0.0f, fabsf(wav) - T), fabsf(wav), tt)), uw * blendw);
     }
     val = o_max(0.0f, (val - black) / (white - black));
+    if(gm && filters != 9) val *= o_gainmap_gain(gm, map_os, x, y, crop[0], crop[1], out->w, out->h, 2);
     o_store1(out, x, y, val, 1);
   }
 }

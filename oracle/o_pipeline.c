@@ -85,13 +85,29 @@ void o_demosaic_module(const oimg_t *in, oimg_t *out, const o_demosaic_params_t 
   o_img_free(&cov); o_img_free(&green);
 }
 
+/* the dng gain maps of the source (denoise/main.c:172-200), set by the caller before o_denoise_module / o_darkroom_run:
+ * rgba f32 texture + { origin x, origin y, 1 / extent x, 1 / extent y }; 0 = none */
+static const oimg_t *o_gainmap_img = 0;
+static float o_gainmap_os[4];
+void o_set_gainmap(const oimg_t *gm, const float *map_os)
+{
+  o_gainmap_img = gm;
+  if(gm) for(int k = 0; k < 4; k++) o_gainmap_os[k] = map_os[k];
+}
+
 /* denoise/main.c:134-333 for mosaic input */
 void o_denoise_module(const oimg_t *in, oimg_t *out, const o_denoise_params_t *p, const int *crop, const float *wb4,
     const float *black4, const float *white4, float noise_a, float noise_b, uint32_t filters)
 {
   float black[4], white[4];
   for(int k = 0; k < 4; k++) { black[k] = black4[k] / 65535.0f; white[k] = white4[k] / 65535.0f; }
-  if(p->strength <= 0.0f) { o_denoise_noop(in, out, crop, black, white); return; }
+  const oimg_t *gm = (o_gainmap_img && filters != 9 && p->gainmap == 1) ? o_gainmap_img : 0;
+  if(p->strength <= 0.0f)
+  {
+    if(gm) o_denoise_noop_gm(in, out, crop, black, white, gm, o_gainmap_os);
+    else o_denoise_noop(in, out, crop, black, white);
+    return;
+  }
   const int block = filters == 9 ? 3 : 2;
   const int hw = out->w / block, hh = out->h / block;
   oimg_t half = o_img_alloc(hw, hh, 4), cov = o_img_alloc(hw, hh, 4), assembled = o_img_alloc(hw, hh, 4);
@@ -101,7 +117,7 @@ void o_denoise_module(const oimg_t *in, oimg_t *out, const o_denoise_params_t *p
   o_denoise_downcov(&half, &dn[0], &cov);
   for(int i = 1; i < 4; i++) o_denoise_down(&dn[i-1], &dn[i], p, black, white, noise_a, noise_b, i, block);
   o_denoise_assemble(&half, &dn[0], &dn[1], &dn[2], &dn[3], &assembled, p, wb4, black, white, noise_a, noise_b, filters);
-  o_denoise_doub(in, &assembled, &half, out, p, crop, black, white, noise_a, noise_b, filters);
+  o_denoise_doub_gm(in, &assembled, &half, out, p, crop, black, white, noise_a, noise_b, filters, gm, o_gainmap_os);
   for(int i = 0; i < 4; i++) o_img_free(&dn[i]);
   o_img_free(&half); o_img_free(&cov); o_img_free(&assembled);
 }

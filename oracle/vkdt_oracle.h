@@ -38,6 +38,10 @@ void o_denoise_assemble(const oimg_t *s0, const oimg_t *s1, const oimg_t *s2, co
     float noise_a, float noise_b, uint32_t filters);
 void o_denoise_doub(const oimg_t *in, const oimg_t *crs0, const oimg_t *crs1, oimg_t *out, const o_denoise_params_t *p,
     const int *crop, const float *black4, const float *white4, float noise_a, float noise_b, uint32_t filters);
+/* the same with a DNG gain map (rgba f32 texture, map_os = origin x, y, 1 / extent x, y): noop.comp:48-57, doub.comp:106-114 */
+void o_denoise_noop_gm(const oimg_t *in, oimg_t *out, const int *crop, const float *black, const float *white, const oimg_t *gm, const float *map_os);
+void o_denoise_doub_gm(const oimg_t *in, const oimg_t *crs0, const oimg_t *crs1, oimg_t *out, const o_denoise_params_t *p,
+    const int *crop, const float *black4, const float *white4, float noise_a, float noise_b, uint32_t filters, const oimg_t *gm, const float *map_os);
 int  o_xtrans_colour(int x, int y);
 
 /* hilite */
@@ -120,6 +124,8 @@ typedef struct o_darkroom_t
 } o_darkroom_t;
 
 void o_darkroom_defaults(o_darkroom_t *d, uint32_t width, uint32_t height);
+/* dng gain maps for the denoise module of the next runs (rgba f32 texture + origin / inverse extent); gm = 0 removes them */
+void o_set_gainmap(const oimg_t *gm, const float *map_os);
 void o_colenc_px(float *rgb, int prim, int trc);
 float o_unorm8(float v);
 void o_colenc_main(const oimg_t *in, oimg_t *out, int prim, int trc, int fmt);

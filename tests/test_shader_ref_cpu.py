@@ -291,6 +291,20 @@ def cases(O):
             O.ref_shader("denoise", "noop", bytes(dp) + b"\0" * 12, push, [(m, 0), (got, 1), (m, 0)], cw, ch)
             return [want.reshape(ch, cw)], [got[..., 0]]            # the shader stores (v, 0, 0, 1); consumers read .r
 
+        if filters == BAYER:   # the DNG GainMap branch (noop.comp:48-57): a 9 x 7 rgba f32 gain texture over the uncropped image
+            @add("denoise.noop gainmap " + tag)
+            def _(filters=filters, crop=crop, cw=cw, ch=ch, black=black, white=white, dp=dp, raw_unorm=raw_unorm, f4=f4, i4=i4):
+                m = raw_unorm(82)
+                gm = np.ascontiguousarray(np.random.default_rng(83).uniform(0.8, 1.6, (7, 9, 4)).astype(np.float32))
+                mos = [0.02, 0.01, 1.05, 0.98]
+                want, wi = img_out(ch, cw, 1)
+                L.o_denoise_noop_gm(C.byref(O.img(m)), C.byref(wi), (C.c_int * 4)(*crop), (C.c_float * 4)(*black), (C.c_float * 4)(*white),
+                                    C.byref(O.img(gm)), (C.c_float * 4)(*mos))
+                got = np.zeros((ch, cw, 4), np.float32)
+                push = i4(crop) + f4(black) + f4(white) + f4(mos) + np.array([filters], np.uint32).tobytes() + i4([1])
+                O.ref_shader("denoise", "noop", bytes(dp) + b"\0" * 12, push, [(m, 0), (got, 1), (gm, 0)], cw, ch)
+                return [want.reshape(ch, cw)], [got[..., 0]]
+
         @add("denoise.half..doub " + tag)
         def _(filters=filters, blk=blk, crop=crop, cw=cw, ch=ch, black=black, white=white, wb=wb, na=na, nb=nb, dp=dp, raw_unorm=raw_unorm, f4=f4, i4=i4):
             m = raw_unorm(81)
@@ -330,6 +344,15 @@ def cases(O):
             gd = np.zeros((ch, cw), np.float32)
             O.ref_shader("denoise", "doub", params, head + fbits + f4([na, nb]) + i4([0]) + f4([0, 0, 0, 0]), [(m, 0), (asm, 0), (half, 0), (gd, 1), (half, 0)], cw, ch)
             res_o.append(out.reshape(ch, cw)); res_s.append(gd)
+            if filters == BAYER:   # doub.comp:106-114: the same stage with a gain map
+                gm = np.ascontiguousarray(np.random.default_rng(84).uniform(0.8, 1.6, (7, 9, 4)).astype(np.float32))
+                mos = [0.02, 0.01, 1.05, 0.98]
+                out2, oi2 = img_out(ch, cw, 1)
+                L.o_denoise_doub_gm(C.byref(O.img(m)), C.byref(ai), C.byref(hi), C.byref(oi2), C.byref(dp), cI, bI, wI, C.c_float(na), C.c_float(nb), C.c_uint32(filters),
+                                    C.byref(O.img(gm)), (C.c_float * 4)(*mos))
+                gd2 = np.zeros((ch, cw), np.float32)
+                O.ref_shader("denoise", "doub", params, head + fbits + f4([na, nb]) + i4([1]) + f4(mos), [(m, 0), (asm, 0), (half, 0), (gd2, 1), (gm, 0)], cw, ch)
+                res_o.append(out2.reshape(ch, cw)); res_s.append(gd2)
             return res_o, res_s
 
     for filters, (w, h) in ((BAYER, (96, 64)), (XTRANS, (96, 66))):
@@ -424,7 +447,7 @@ def _f16_ulps(a, b):
 # kernels that FILTER (texture() at fractional coordinates): the shader computes its texture coordinates in fp32, the oracle is an
 # ideal sampler that carries them in double (oracle/o_common.h:122-143), so a weight can differ in its last bits and an
 # f16 store can then round the other way.  everything else is bit exact.
-SAMPLED = ("llap.reduce", "llap.assemble", "denoise.half..doub", "shared.resample", "resize.main mode 0", "resize.main mode 2", "shared.blur")
+SAMPLED = ("llap.reduce", "llap.assemble", "denoise.half..doub", "denoise.noop gainmap", "shared.resample", "resize.main mode 0", "resize.main mode 2", "shared.blur")
 
 
 def _report(name, want, got):

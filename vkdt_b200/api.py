@@ -44,7 +44,7 @@ vkb_event_sync vkb_event_elapsed_ms vkb_event_destroy vkb_dispatch vkb_kernel_co
 vkb_kernel_name vkb_launch_count vkb_launch_count_reset vkb_graph_new vkb_graph_free vkb_graph_read_config_ascii
 vkb_graph_read_config_line vkb_graph_replace_display vkb_graph_set_source vkb_graph_set_sink_buffer
 vkb_graph_sink_size vkb_graph_set_frame vkb_graph_run vkb_graph_plan vkb_graph_perf vkb_graph_dump_nodes
-vkb_graph_set_source_device vkb_graph_sink_device vkb_graph_pool_bytes vkb_graph_stream vkb_graph_set_device vkb_dng_info vkb_graph_set_sink_layout vkb_lj92_decode vkb_graph_committed_params vkb_graph_describe vkb_graph_state vkb_graph_set_perf vkb_set_mode vkb_get_mode vkb_graph_set_mode vkb_graph_set_bands vkb_graph_band_plan vkb_graph_band_stats vkb_graph_band_mark vkb_graph_band_elapsed_ms vkb_graph_replace_display_ex vkb_graph_replace_display_sized vkb_jpeg_write vkb_graph_frame_count vkb_set_basedir vkb_module_describe vkb_graph_apply_keyframes vkb_graph_has_feedback vkb_register_module vkb_register_kernel""".split()
+vkb_graph_set_source_device vkb_graph_sink_device vkb_graph_pool_bytes vkb_graph_stream vkb_graph_set_device vkb_dng_info vkb_graph_set_sink_layout vkb_lj92_decode vkb_graph_committed_params vkb_graph_describe vkb_graph_state vkb_graph_set_perf vkb_set_mode vkb_get_mode vkb_graph_set_mode vkb_graph_set_bands vkb_graph_band_plan vkb_graph_band_stats vkb_graph_band_mark vkb_graph_band_elapsed_ms vkb_graph_replace_display_ex vkb_graph_replace_display_sized vkb_graph_set_dng_opcodes vkb_dng_opcodes_describe vkb_jpeg_write vkb_graph_frame_count vkb_set_basedir vkb_module_describe vkb_graph_apply_keyframes vkb_graph_has_feedback vkb_register_module vkb_register_kernel""".split()
 
 
 def token(s):
@@ -272,6 +272,11 @@ class Graph:
     def set_source(self, data_ptr, params, inst="main", device=False):
         fn = lib.vkb_graph_set_source_device if device else lib.vkb_graph_set_source
         check(fn(self.h, inst.encode(), C.c_void_p(data_ptr), C.byref(params)))
+
+    def set_dng_opcodes(self, blob, ox=0, oy=0, inst="main"):
+        """OpcodeList2 of an in-memory i-raw source (bytes as in the dng tag) + the cfa offset of the window"""
+        lib.vkb_graph_set_dng_opcodes.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_size_t, C.c_int, C.c_int]
+        check(lib.vkb_graph_set_dng_opcodes(self.h, inst.encode(), bytes(blob), len(blob), ox, oy))
 
     def set_sink_buffer(self, ptr, nbytes, inst="main"):
         check(lib.vkb_graph_set_sink_buffer(self.h, inst.encode(), C.c_void_p(ptr) if ptr else None, nbytes))

@@ -497,7 +497,7 @@ VKB_DEV float doub_shrink(float val, float upsm_c, float down_c, float upw, int 
 
 __global__ void __launch_bounds__(256) k_denoise_doub(const uint16_t *__restrict__ in, int iw, int ih,
     const uint2 *__restrict__ crs0, const uint2 *__restrict__ crs1, int cw, int ch, __half *__restrict__ out, int ow, int oh,
-    const __grid_constant__ denoise_params_t p, const __grid_constant__ dn_push_doub_t P)
+    const __grid_constant__ denoise_params_t p, const __grid_constant__ dn_push_doub_t P, const gainmap_t G)
 {
   const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
   if(x >= ow || y >= oh) return;
@@ -520,7 +520,9 @@ __global__ void __launch_bounds__(256) k_denoise_doub(const uint16_t *__restrict
   const int col = xt ? xtrans_colour(x, y) : bayer_colour(x, y);
   const float val = (float)__ldg(in + (size_t)mirrori(y + P.crop[1], ih) * iw + mirrori(x + P.crop[0], iw)) / 65535.0f;
   const float uc = col == 1 ? upsm.y : (col == 0 ? upsm.x : upsm.z), dc = col == 1 ? down.y : (col == 0 ? down.x : down.z);
-  out[(size_t)y * ow + x] = __float2half_rn(doub_shrink(val, uc, dc, upsm.w, col, xt, p, P));
+  float res = doub_shrink(val, uc, dc, upsm.w, col, xt, p, P);
+  if(G.map) res *= gainmap_gain(G, x, y, P.crop[0], P.crop[1], ow, oh, 2);   // doub.comp:106-114
+  out[(size_t)y * ow + x] = __float2half_rn(res);
 }
 
 // bayer, output exactly twice the coarse size: one thread per 2x2 block.  the four pixels' bilinear taps (fractions
@@ -683,7 +685,15 @@ static int launch_doub(const vkb_launch_t *l)
   denoise_params_t p; memset(&p, 0, sizeof(p)); memcpy(&p, l->params, l->params_size < sizeof(p) ? l->params_size : sizeof(p));
   dn_push_doub_t P; memcpy(&P, l->push, sizeof(P));
   host_escale(&p);
-  if(P.filters != 9u && P.filters != 0u && out->wd == 2 * c0->wd && out->ht == 2 * c0->ht)
+  // [4] gain map rgba f32 (a dummy binding unless push.gainmap, denoise/main.c:315-319); bayer only (doub.comp:106)
+  gainmap_t G = { 0, 0, 0, { 0, 0, 0, 0 } };
+  if(P.filters != 9u && P.gainmap == 1 && p.gainmap == 1)
+  {
+    VKB_REQUIRE(l->num_conn >= 5 && l->conn[4].format == VKB_TOKEN_F32 && l->conn[4].chan == 4 && l->conn[4].data && l->band_y0 < 0);
+    G.map = (const float4 *)l->conn[4].data; G.w = (int)l->conn[4].wd; G.h = (int)l->conn[4].ht;
+    for(int k = 0; k < 4; k++) G.os[k] = P.map_os[k];
+  }
+  if(!G.map && P.filters != 9u && P.filters != 0u && out->wd == 2 * c0->wd && out->ht == 2 * c0->ht)
   {
     dim3 grid = grid2d(c0->wd, c0->ht);
     const band_t bd = band_of(l, 2, 8, c0->ht, &grid.y); // band image: the output mosaic, two rows per thread row
@@ -693,7 +703,7 @@ static int launch_doub(const vkb_launch_t *l)
   }
   else
   k_denoise_doub<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint16_t *)in->data, in->wd, in->ht, (const uint2 *)c0->data,
-      (const uint2 *)c1->data, c0->wd, c0->ht, (__half *)out->data, out->wd, out->ht, p, P);
+      (const uint2 *)c1->data, c0->wd, c0->ht, (__half *)out->data, out->wd, out->ht, p, P, G);
   VKB_CHECK_LAUNCH();
   return VKB_OK;
 }

@@ -128,13 +128,36 @@ __global__ void __launch_bounds__(256) k_denoise_noop(const uint16_t *__restrict
   }
 }
 
-// conn: [0] input ui16 1ch, [1] output f16 1ch ([2] gainmap ignored: DNG gain maps are out of scope)
+// the same with a DNG gain map (noop.comp:48-57): one pixel per thread
+__global__ void __launch_bounds__(256) k_denoise_noop_gm(const uint16_t *__restrict__ in, int iw, int ih,
+    __half *__restrict__ out, int ow, int oh, int cx, int cy, float black, float white, const gainmap_t G)
+{
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if(x >= ow || y >= oh) return;
+  const float a = (float)__ldg(in + (size_t)clampi(y + cy, 0, ih - 1) * iw + clampi(x + cx, 0, iw - 1)) / 65535.0f;
+  float col = fmaxf(0.0f, (a - black) / (white - black));
+  col *= gainmap_gain(G, x, y, cx, cy, iw, ih, 1);
+  out[(size_t)y * ow + x] = __float2half_rn(col);
+}
+
+// conn: [0] input ui16 1ch, [1] output f16 1ch, [2] gain map rgba f32 (a dummy binding unless push.gainmap, denoise/main.c:216-221)
+// params: the denoise parameter block (its last int switches the gain map off)
 static int launch_denoise_noop(const vkb_launch_t *l)
 {
   VKB_REQUIRE(l->num_conn >= 2 && l->push_size >= sizeof(noop_push_t));
   const noop_push_t *p = (const noop_push_t *)l->push;
   const vkb_image_t *in = l->conn + 0, *out = l->conn + 1;
   VKB_REQUIRE(in->format == VKB_TOKEN_UI16 && out->format == VKB_TOKEN_F16 && in->chan == 1 && out->chan == 1);
+  const int par_gainmap = l->params_size >= 36 ? ((const int32_t *)l->params)[8] : 1;   // strength luma detail pad edges[4] gainmap
+  if(p->filters != 0 && p->filters != 9 && p->gainmap == 1 && par_gainmap == 1)
+  {
+    VKB_REQUIRE(l->num_conn >= 3 && l->conn[2].format == VKB_TOKEN_F32 && l->conn[2].chan == 4 && l->conn[2].data && l->band_y0 < 0);
+    gainmap_t G = { (const float4 *)l->conn[2].data, (int)l->conn[2].wd, (int)l->conn[2].ht, { p->map_os[0], p->map_os[1], p->map_os[2], p->map_os[3] } };
+    k_denoise_noop_gm<<<dim3(vkb_cdiv(out->wd, 32), vkb_cdiv(out->ht, 8)), dim3(32, 8), 0, l->stream>>>((const uint16_t *)in->data, in->wd, in->ht,
+        (__half *)out->data, out->wd, out->ht, p->crop[0], p->crop[1], p->black[0], p->white[0], G);
+    VKB_CHECK_LAUNCH();
+    return VKB_OK;
+  }
   dim3 block(32, 8), grid(vkb_cdiv(out->wd, 256), vkb_cdiv(out->ht, 8));
   k_denoise_noop<<<grid, block, 0, l->stream>>>((const uint16_t *)in->data, in->wd, in->ht,
       (__half *)out->data, out->wd, out->ht, p->crop[0], p->crop[1], p->black[0], p->white[0]);

@@ -29,6 +29,8 @@ static int find_inst(dt_graph_t *g, const char *inst, bool source)
   return -1;
 }
 
+int dt_iraw_set_dng_opcodes(dt_module_t *mod, const void *blob, size_t len, int ox, int oy);   // modules.cpp
+
 extern "C" {
 
 vkb_graph_t *vkb_graph_new(void)
@@ -91,6 +93,42 @@ static int set_source(vkb_graph_t *h, const char *inst, const void *data, const 
 }
 int vkb_graph_set_source(vkb_graph_t *h, const char *inst, const void *data, const vkb_raw_params_t *p) { return set_source(h, inst, data, p, 0); }
 int vkb_graph_set_source_device(vkb_graph_t *h, const char *inst, const void *d, const vkb_raw_params_t *p) { return set_source(h, inst, d, p, 1); }
+int vkb_dng_opcodes_describe(const void *opcode_list, size_t bytes, char *out, size_t out_size)
+{ // what the opcode list decoder makes of a tag, as text (tests compare it with the reference's own decoder)
+  if(!opcode_list || !out || !out_size) return VKB_ERR_BAD_ARG;
+  dt_dng_opcode_list_t ol;
+  std::string t;
+  char b[512];
+  if(dng_opcode_list_decode((const uint8_t *)opcode_list, bytes, &ol)) t = "none\n";
+  else
+  {
+    snprintf(b, sizeof(b), "count %d\n", (int)ol.ops.size()); t += b;
+    for(const dt_dng_opcode_t &op : ol.ops)
+    {
+      snprintf(b, sizeof(b), "op %u optional %u preview_skip %u\n", op.id, op.optional, op.preview_skip); t += b;
+      if(op.gain_map < 0) continue;
+      const dt_dng_gain_map_t &g = ol.gain_maps[op.gain_map];
+      snprintf(b, sizeof(b), " region %u %u %u %u plane %u %u pitch %u %u points %u %u spacing %.17g %.17g origin %.17g %.17g planes %u\n gains",
+          g.top, g.left, g.bottom, g.right, g.plane, g.planes, g.row_pitch, g.col_pitch, g.map_points_v, g.map_points_h,
+          g.map_spacing_v, g.map_spacing_h, g.map_origin_v, g.map_origin_h, g.map_planes);
+      t += b;
+      for(float v : g.map_gain) { uint32_t u; memcpy(&u, &v, 4); snprintf(b, sizeof(b), " %08x", u); t += b; }
+      t += "\n";
+    }
+  }
+  snprintf(out, out_size, "%s", t.c_str());
+  return VKB_OK;
+}
+int vkb_graph_set_dng_opcodes(vkb_graph_t *h, const char *inst, const void *opcode_list2, size_t bytes, int cfa_off_x, int cfa_off_y)
+{ // what rawler hands the reference beside the pixels (i-raw/main.c:62-92): the OpcodeList2 tag and the cfa offset of the window
+  if(!h) return VKB_ERR_BAD_ARG;
+  const int m = find_inst(h->g, inst, true);
+  if(m < 0) return vkb_set_error(VKB_ERR_BAD_ARG, "no source module with instance '%s'", inst ? inst : "main");
+  const int r = dt_iraw_set_dng_opcodes(&h->g->module[m], opcode_list2, bytes, cfa_off_x, cfa_off_y);
+  if(r == 1) return vkb_set_error(VKB_ERR_BAD_ARG, "dng opcode lists belong to an i-raw source");
+  if(r) return vkb_set_error(VKB_ERR_BAD_ARG, "the opcode list does not decode (sizes that do not add up)");
+  return VKB_OK;
+}
 int vkb_graph_set_sink_buffer(vkb_graph_t *h, const char *inst, void *dst, size_t bytes)
 { // dst == NULL: keep the result on the device (no download, no file)
   if(!h) return VKB_ERR_BAD_ARG;

@@ -99,6 +99,9 @@ int dng_read(const char *filename, dng_image_t *img)
   if(find(t, raw, 50717, &e)) img->white = (float)value(t, e, 0);
   img->active[0] = 0; img->active[1] = 0; img->active[2] = img->height; img->active[3] = img->width;
   if(find(t, raw, 50829, &e) && e.count == 4) for(int i = 0; i < 4; i++) img->active[i] = (uint32_t)value(t, e, i);
+  img->opcode_list2.clear();
+  if(find(t, raw, 51009, &e) && e.count >= 4 && e.value_off + (size_t)e.count <= t.d.size())
+    img->opcode_list2.assign(t.d.begin() + e.value_off, t.d.begin() + e.value_off + e.count);
   // colour / identification tags live in IFD0
   if(find(t, ifd0, 50728, &e) && e.count >= 3) for(int i = 0; i < 3; i++) img->neutral[i] = (float)value(t, e, i);
   bool have2 = false;

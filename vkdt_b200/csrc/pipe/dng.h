@@ -19,6 +19,7 @@ struct dng_image_t
   char     make[32] = {0}, model[32] = {0};
   float    iso = 0.0f;
   uint32_t orientation = 0;
+  std::vector<uint8_t> opcode_list2; // the OpcodeList2 tag (51009) as stored: big endian whatever the file's byte order
 };
 
 // 0 on success

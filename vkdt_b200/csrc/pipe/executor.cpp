@@ -316,7 +316,9 @@ static int build_plan(dt_graph_t *g, bool with_device)
     }
     // dummy bindings (unconnected lut / gainmap inputs are wired to `input` in the reference) are not consumers
     const dt_node_t *nd = &g->node[n];
-    if((is_node(nd, "colour", "main") && c >= 2) || (is_node(nd, "denoise", "noop") && c == 2) || (is_node(nd, "denoise", "doub") && c == 4)) continue;
+    // (a gain map input that is wired to the module's (denoise, gainmap) source node is real)
+    const bool real_gainmap = is_node(&g->node[cn->connected.i], "denoise", "gainmap");
+    if((is_node(nd, "colour", "main") && c >= 2) || (!real_gainmap && ((is_node(nd, "denoise", "noop") && c == 2) || (is_node(nd, "denoise", "doub") && c == 4)))) continue;
     B.consumers[{cn->connected.i, cn->connected.c}].push_back({n, c});
   }
   // a module between the graph and an f32 sink that bypassed itself (resize at 1:1): the sink then hangs on an f16 edge.  the
@@ -393,7 +395,7 @@ static int build_plan(dt_graph_t *g, bool with_device)
           const dt_node_t *nn = &g->node[cs[0].first];
           const int32_t *pc = (const int32_t *)nn->push_constant;
           const int oc = find_conn(nn, "output");
-          if(pc[0] == 0 && pc[1] == 0 && nn->connector[oc].roi.wd == wd && nn->connector[oc].roi.ht == ht)
+          if(pc[0] == 0 && pc[1] == 0 && pc[17] == 0 && nn->connector[oc].roi.wd == wd && nn->connector[oc].roi.ht == ht)   // uncropped, no gain map
           {
             plan_launch_t l;
             l.name = dt_token("b200"); l.kernel = dt_token("rawnoop"); l.wd = wd; l.ht = ht; l.dp = 1;
@@ -420,6 +422,10 @@ static int build_plan(dt_graph_t *g, bool with_device)
           l.label = dt_token_string(nd->module->name) + " i-mlv_unpack";
           B.add_launch(l);
         }
+      }
+      else if(is_node(nd, "denoise", "gainmap"))
+      { // the dng gain maps of denoise (denoise/main.c:181-196): a small rgba f32 texture, sampled as it is
+        s.buf_upload = out; s.bytes = conn_bytes(nd->connector);
       }
       else if(nd->connector[0].format == dt_token("f32") || (nd->module->num_connectors > 0 && nd->module->connector[0].format == dt_token("f32")))
       { // f32 sources (i-pfm): the kernels of this path read f16 edges.  upload as is, convert once on the device and let

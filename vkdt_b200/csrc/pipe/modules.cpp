@@ -134,6 +134,9 @@ static int  imlv_read_source(dt_module_t *, void *, dt_read_source_params_t *);
 static void denoise_roi_in(dt_graph_t *, dt_module_t *);
 static void denoise_roi_out(dt_graph_t *, dt_module_t *);
 static void denoise_create_nodes(dt_graph_t *, dt_module_t *);
+static int  denoise_init(dt_module_t *);
+static void denoise_cleanup(dt_module_t *);
+static int  denoise_read_source(dt_module_t *, void *, dt_read_source_params_t *);
 static void hilite_create_nodes(dt_graph_t *, dt_module_t *);
 static void demosaic_roi_in(dt_graph_t *, dt_module_t *);
 static void demosaic_roi_out(dt_graph_t *, dt_module_t *);
@@ -246,7 +249,8 @@ static std::vector<dt_module_so_t> &registry()
     if(n == "i-raw")    { so.init = iraw_init; so.cleanup = iraw_cleanup; so.modify_roi_out = iraw_roi_out; so.read_source = iraw_read_source; }
     if(n == "i-pfm")    { so.init = ipfm_init; so.cleanup = ipfm_cleanup; so.modify_roi_out = ipfm_roi_out; so.read_source = ipfm_read_source; }
     if(n == "i-mlv")    { so.init = imlv_init; so.cleanup = imlv_cleanup; so.modify_roi_out = imlv_roi_out; so.read_source = imlv_read_source; }
-    if(n == "denoise")  { so.modify_roi_in = denoise_roi_in; so.modify_roi_out = denoise_roi_out; so.create_nodes = denoise_create_nodes; }
+    if(n == "denoise")  { so.init = denoise_init; so.cleanup = denoise_cleanup; so.modify_roi_in = denoise_roi_in; so.modify_roi_out = denoise_roi_out;
+                          so.create_nodes = denoise_create_nodes; so.read_source = denoise_read_source; }
     if(n == "hilite")   { so.create_nodes = hilite_create_nodes; }
     if(n == "demosaic") { so.modify_roi_in = demosaic_roi_in; so.modify_roi_out = demosaic_roi_out; so.create_nodes = demosaic_create_nodes; }
     if(n == "crop")     { so.init = crop_init; so.modify_roi_in = crop_roi_in; so.modify_roi_out = crop_roi_out; so.commit_params = crop_commit; }
@@ -304,7 +308,24 @@ static void fill_img_param(dt_module_t *mod, const vkb_raw_params_t *p)
   ip->colour_trc = 0;       // linear
 }
 // file source: uncompressed 16-bit cfa dng (pipe/dng.cpp); camera formats proper stay with rawler / rawspeed
-struct iraw_file_t { std::string filename; dng_image_t img; vkb_raw_params_t p; uint32_t ox = 0, oy = 0; bool loaded = false; };
+struct iraw_file_t
+{
+  std::string filename; dng_image_t img; vkb_raw_params_t p; uint32_t ox = 0, oy = 0; bool loaded = false;
+  // i-raw/main.c:62-92: OpcodeList2 decoded into what denoise reads, handed on through img_param.meta.  `file` from the dng,
+  // `mem` for an in-memory source (vkb_graph_set_dng_opcodes: the tag's bytes as rawler hands them to the reference)
+  dt_image_metadata_dngop_t dngop_file, dngop_mem; bool have_dngop_file = false, have_dngop_mem = false;
+};
+int dt_iraw_set_dng_opcodes(dt_module_t *mod, const void *blob, size_t len, int ox, int oy)
+{
+  if(!mod || mod->name != dt_token("i-raw") || !mod->data) return 1;
+  iraw_file_t *d = (iraw_file_t *)mod->data;
+  d->have_dngop_mem = false;
+  if(!blob || !len) return 0;
+  if(dng_opcode_list_decode((const uint8_t *)blob, len, &d->dngop_mem.list2)) return 2;
+  d->dngop_mem.ox = ox; d->dngop_mem.oy = oy;
+  d->have_dngop_mem = true;
+  return 0;
+}
 static std::string resource_path(const dt_module_t *mod, const char *fname)
 { // dt_graph_get_resource_filename: relative to the cfg's directory first
   std::string path = fname;
@@ -329,6 +350,8 @@ static int iraw_load(dt_module_t *mod)
   const int err = dng_read(path.c_str(), &d->img);
   if(err) { fprintf(stderr, "[i-raw] failed to load raw file %s (%d)\n", path.c_str(), err); return 1; }
   if(dng_raw_params(&d->img, &d->p, &d->ox, &d->oy)) return 1;
+  d->have_dngop_file = !d->img.opcode_list2.empty() && !dng_opcode_list_decode(d->img.opcode_list2.data(), d->img.opcode_list2.size(), &d->dngop_file.list2);
+  d->dngop_file.ox = (int)d->ox; d->dngop_file.oy = (int)d->oy;
   d->filename = fname;
   d->loaded = true;
   return 0;
@@ -360,10 +383,12 @@ static void iraw_roi_out(dt_graph_t *g, dt_module_t *mod)
     mod->connector[0].roi.full_wd = d->p.width;  // already rounded to the cfa block
     mod->connector[0].roi.full_ht = d->p.height;
     mod->connector[0].chan = dt_token("rggb");
+    ip->meta = d->have_dngop_file ? &d->dngop_file : 0;
     return;
   }
   const vkb_raw_params_t *p = &g->mem_source[mid].p;
   fill_img_param(mod, p);
+  { iraw_file_t *d = (iraw_file_t *)mod->data; mod->img_param.meta = d && d->have_dngop_mem ? &d->dngop_mem : 0; }
   // i-raw/main.c:156-157: dimensions rounded down to the cfa block
   const int block = p->filters == 9u ? 3 : (p->filters ? 2 : 1);
   mod->connector[0].roi.full_wd = (p->width / block) * block;
@@ -642,6 +667,42 @@ static void denoise_roi_out(dt_graph_t *graph, dt_module_t *module)
   }
 }
 static inline int32_t fbits(float f) { int32_t i; memcpy(&i, &f, 4); return i; }
+// denoise/main.c:12-43 get_gain_maps_bayer: the list has to hold four GainMap opcodes up front, one per site of the 2x2 cfa block
+// (plane 0, pitch 2 x 2, the same grid and, up to the site's offset, the same region); gm[filter] by the site the region starts on
+struct denoise_data_t { const dt_dng_gain_map_t *gm[4] = { 0, 0, 0, 0 }; };
+static int denoise_init(dt_module_t *mod) { mod->data = new denoise_data_t(); return 0; }
+static void denoise_cleanup(dt_module_t *mod) { delete (denoise_data_t *)mod->data; mod->data = 0; }
+static int get_gain_maps_bayer(const dt_dng_opcode_list_t *ol, int index, denoise_data_t *dat, uint32_t ox, uint32_t oy)
+{
+  if((int)ol->ops.size() - index < 4) return 0;
+  for(int i = 0; i < 4; i++) if(ol->ops[i].id != 9) return 0;   // (the reference looks at ops[0..3] whatever `index` is)
+  for(int i = 0; i < 4; i++) dat->gm[i] = 0;
+  for(int i = 0; i < 4; i++)
+  {
+    const dt_dng_gain_map_t *gm = &ol->gain_maps[ol->ops[i].gain_map];
+    if(!(gm->plane == 0 && gm->planes == 1 && gm->map_planes == 1 && gm->row_pitch == 2 && gm->col_pitch == 2)) return 0;
+    if(gm->map_points_h < 2 && gm->map_points_v < 2) return 0;
+    const int filter = (((gm->top + oy) & 1) << 1) + ((gm->left + ox) & 1);
+    dat->gm[filter] = gm;
+  }
+  for(int i = 0; i < 4; i++) if(!dat->gm[i]) return 0;
+  for(int i = 1; i < 4; i++)
+    if(dat->gm[0]->map_points_h != dat->gm[i]->map_points_h || dat->gm[0]->map_points_v != dat->gm[i]->map_points_v ||
+       dat->gm[0]->map_spacing_h != dat->gm[i]->map_spacing_h || dat->gm[0]->map_spacing_v != dat->gm[i]->map_spacing_v ||
+       dat->gm[0]->map_origin_h != dat->gm[i]->map_origin_h || dat->gm[0]->map_origin_v != dat->gm[i]->map_origin_v ||
+       dat->gm[0]->top / 2 != dat->gm[i]->top / 2 || dat->gm[0]->left / 2 != dat->gm[i]->left / 2 ||
+       dat->gm[0]->bottom / 2 != dat->gm[i]->bottom / 2 || dat->gm[0]->right / 2 != dat->gm[i]->right / 2) return 0;
+  return 1;
+}
+static int denoise_read_source(dt_module_t *mod, void *mapped, dt_read_source_params_t *p)
+{ // denoise/main.c:61-80: the four gain planes interleaved into the rgba f32 texture of the (denoise, gainmap) node
+  const denoise_data_t *dat = (const denoise_data_t *)mod->data;
+  if(p->node->kernel != dt_token("gainmap") || !dat || !dat->gm[0]) return 0;
+  const int wd = dat->gm[0]->map_points_h, ht = dat->gm[0]->map_points_v;
+  for(int j = 0; j < ht; j++) for(int i = 0; i < wd; i++) for(int c = 0; c < 4; c++)
+    ((float *)mapped)[(j * wd + i) * 4 + c] = dat->gm[c]->map_gain[j * wd + i];
+  return 0;
+}
 static void denoise_create_nodes(dt_graph_t *graph, dt_module_t *module)
 {
   const dt_image_params_t *img_param = dt_module_get_input_img_param(graph, module, dt_token("input"));
@@ -658,12 +719,29 @@ static void denoise_create_nodes(dt_graph_t *graph, dt_module_t *module)
   const uint32_t crop_aabb[4] = { (uint32_t)(caf[0] * cs), (uint32_t)(caf[1] * cs), (uint32_t)(caf[2] * cs), (uint32_t)(caf[3] * cs) };
   for(int k = 0; k < 4; k++) { wbi[k] = fbits(wb[k]); blacki[k] = fbits(img_param->black[k] / 65535.0f); whitei[k] = fbits(img_param->white[k] / 65535.0f); }
   const int32_t noisei[2] = { fbits(img_param->noise_a), fbits(img_param->noise_b) };
+  // denoise/main.c:172-200: a source node for the gain maps of a dng, and where they sit in the image
+  int32_t gainmap = 0, gainmap_sx = 0, gainmap_sy = 0, gainmap_ox = 0, gainmap_oy = 0;
+  denoise_data_t *dat = (denoise_data_t *)module->data;
+  const dt_image_metadata_dngop_t *dngop = (const dt_image_metadata_dngop_t *)module->img_param.meta;
+  if(dngop && dat) for(int op = 0; op < (int)dngop->list2.ops.size() && !gainmap; op++) gainmap = get_gain_maps_bayer(&dngop->list2, op, dat, dngop->ox, dngop->oy);
+  int id_gmdata = -1;
+  if(gainmap)
+  {
+    const int map_wd = dat->gm[0]->map_points_h, map_ht = dat->gm[0]->map_points_v;
+    dt_roi_t gmdata_roi = {}; gmdata_roi.wd = map_wd; gmdata_roi.ht = map_ht;
+    id_gmdata = dt_node_add(graph, module, "denoise", "gainmap", map_wd, map_ht, 1, 0, 0, 1, "source", "source", "rgba", "f32", &gmdata_roi);
+    const float ox = dat->gm[0]->map_origin_h, oy = dat->gm[0]->map_origin_v;
+    const float sx = 1.0 / (dat->gm[0]->map_spacing_h * (map_wd - 1)), sy = 1.0 / (dat->gm[0]->map_spacing_v * (map_ht - 1));
+    gainmap_ox = fbits(ox); gainmap_oy = fbits(oy); gainmap_sx = fbits(sx); gainmap_sy = fbits(sy);
+  }
+  else if(dat) dat->gm[0] = dat->gm[1] = dat->gm[2] = dat->gm[3] = 0;
   const float strength = dt_module_param_float(module, param_id(module, "strength"))[0];
   if(strength <= 0.0f)
   {
     if(img_param->filters == 0) return dt_connector_bypass(graph, module, 0, 1);
     const int32_t pc[] = { (int32_t)crop_aabb[0], (int32_t)crop_aabb[1], (int32_t)crop_aabb[2], (int32_t)crop_aabb[3],
-      blacki[0], blacki[1], blacki[2], blacki[3], whitei[0], whitei[1], whitei[2], whitei[3], 0, 0, 0, 0, (int32_t)img_param->filters, 0 };
+      blacki[0], blacki[1], blacki[2], blacki[3], whitei[0], whitei[1], whitei[2], whitei[3],
+      gainmap_ox, gainmap_oy, gainmap_sx, gainmap_sy, (int32_t)img_param->filters, gainmap };
     // the reference declares the output rgba and stores (v,0,0,1); every consumer reads .r: we keep one channel
     const int id_noop = dt_node_add(graph, module, "denoise", "noop", module->connector[1].roi.wd, module->connector[1].roi.ht, 1, sizeof(pc), pc, 3,
         "input",   "read",  "rgba", "f16", dt_no_roi,
@@ -671,6 +749,7 @@ static void denoise_create_nodes(dt_graph_t *graph, dt_module_t *module)
         "gainmap", "read",  "rgba", "*",   dt_no_roi);
     dt_connector_copy(graph, module, 0, id_noop, 0);
     dt_connector_copy(graph, module, 0, id_noop, 2);
+    if(gainmap) CONN(dt_node_connect(graph, id_gmdata, 0, id_noop, 2));
     dt_connector_copy(graph, module, 1, id_noop, 1);
     return;
   }
@@ -709,13 +788,14 @@ static void denoise_create_nodes(dt_graph_t *graph, dt_module_t *module)
         "output", "write", "rgba", "f16", &roi_half);
     const int32_t pc[] = { wbi[0], wbi[1], wbi[2], wbi[3], blacki[0], blacki[1], blacki[2], blacki[3], whitei[0], whitei[1], whitei[2], whitei[3],
       (int32_t)crop_aabb[0], (int32_t)crop_aabb[1], (int32_t)crop_aabb[2], (int32_t)crop_aabb[3],
-      (int32_t)img_param->filters, noisei[0], noisei[1], 0, 0, 0, 0, 0 };
+      (int32_t)img_param->filters, noisei[0], noisei[1], gainmap, gainmap_ox, gainmap_oy, gainmap_sx, gainmap_sy };
     const int id_doub = dt_node_add(graph, module, "denoise", "doub", module->connector[1].roi.wd, module->connector[1].roi.ht, 1, sizeof(pc), pc, 5,
         "orig", "read", "rggb", "f16", dt_no_roi, "crs0", "read", "rgba", "f16", dt_no_roi, "crs1", "read", "rgba", "f16", dt_no_roi,
         "output", "write", "rggb", "f16", &module->connector[1].roi, "gainmap", "read", "rgba", "*", dt_no_roi);
     CONN(dt_node_connect(graph, id_assemble, 5, id_doub, 1));
     CONN(dt_node_connect(graph, id_half, 1, id_doub, 2));
-    CONN(dt_node_connect(graph, id_half, 1, id_doub, 4));
+    if(gainmap) CONN(dt_node_connect(graph, id_gmdata, 0, id_doub, 4));
+    else        CONN(dt_node_connect(graph, id_half, 1, id_doub, 4)); // connect dummy gainmap
     dt_connector_copy(graph, module, 0, id_doub, 0);
     dt_connector_copy(graph, module, 1, id_doub, 3);
     CONN(dt_node_connect(graph, id_half, 1, id_down[0], 0));

@@ -94,6 +94,7 @@ static inline size_t dt_connector_bytes_per_channel(const dt_connector_t *c)
 }
 
 // module.h:72-109
+#include "dngop.h"
 struct dt_image_params_t
 {
   float    black[4], white[4], whitebalance[4];
@@ -107,7 +108,7 @@ struct dt_image_params_t
   int      snd_format, snd_channels, snd_samplerate;
   float    noise_a, noise_b;
   dt_token_t input_name;
-  void    *meta;
+  void    *meta;   // metadata.h's list reduced to the one entry this path reads: a dt_image_metadata_dngop_t of the source module, or 0
 };
 
 // params.h:6-23 (gui annotations dropped)

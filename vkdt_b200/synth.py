@@ -144,7 +144,7 @@ def write_mlv(filename, frames, bpp=14, black=BLACK, white=WHITE, fps=(24000, 10
 
 def write_dng(filename, raw, cfa=((0, 1), (1, 2)), black=2048, white=15000, neutral=(0.5, 1.0, 0.6),
               color_matrix=None, illuminant=21, active_area=None, make="b200", model="synth", iso=100,
-              orientation=1, big_endian=False):
+              orientation=1, big_endian=False, opcode_list2=None):
     """Write `raw` (h x w uint16) as an uncompressed 16-bit CFA DNG (TIFF/EP + DNG 1.4 tags, one strip, raw data in IFD0).
     cfa: 2x2 or 6x6 nested sequence of 0 r / 1 g / 2 b as stored.  Test input for the i-raw file path."""
     import struct
@@ -195,6 +195,8 @@ def write_dng(filename, raw, cfa=((0, 1), (1, 2)), black=2048, white=15000, neut
     add(50778, 3, 1, short(illuminant))
     if active_area is not None:
         add(50829, 4, 4, b"".join(long_(v) for v in active_area))
+    if opcode_list2 is not None:      # OpcodeList2, type UNDEFINED: big endian bytes whatever the file's order (dng_opcode_list())
+        add(51009, 7, len(opcode_list2), bytes(opcode_list2))
     entries.sort(key=lambda t: t[0])
     n = len(entries)
     ifd_off = 8
@@ -301,3 +303,20 @@ def lj92_encode(img, bits=14, components=1, predictor=1, lengths=None):
     if nbits:
         put((1 << (8 - nbits)) - 1, 8 - nbits)      # pad with ones
     return bytes(out + body + b"\xff\xd9")
+
+
+def dng_gain_map_opcode(gains, top, left, bottom, right, spacing=(None, None), origin=(0.0, 0.0), row_pitch=2, col_pitch=2):
+    """one GainMap opcode (DNG 1.4, opcode id 9) for a single plane: `gains` is map_points_v x map_points_h float32"""
+    import struct
+    g = np.asarray(gains, dtype=np.float32)
+    pv, ph = g.shape
+    sv = spacing[0] if spacing[0] is not None else 1.0 / (pv - 1)
+    sh = spacing[1] if spacing[1] is not None else 1.0 / (ph - 1)
+    body = struct.pack(">8I2I4dI", top, left, bottom, right, 0, 1, row_pitch, col_pitch, pv, ph, sv, sh, origin[0], origin[1], 1)
+    body += g.astype(">f4").tobytes()
+    return struct.pack(">4I", 9, 0x01030000, 0, len(body)) + body
+
+
+def dng_opcode_list(opcodes):
+    import struct
+    return struct.pack(">I", len(opcodes)) + b"".join(opcodes)
