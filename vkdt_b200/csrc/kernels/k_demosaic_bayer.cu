@@ -15,11 +15,20 @@ VKB_DEV float splat_fetch(const __half *__restrict__ in, int w, int h, int px, i
   if(py >= h) py -= 6;
   return ld_h_clamp(in, w, h, px, py);
 }
-VKB_DEV float splat_weight(float e0, float e1, float cz, float cw, int i, int j)
+#if VKB_FAST
+typedef float ediv_t;                      // the eigenvalue itself
+VKB_DEV ediv_t ediv(float e) { return e; }
+VKB_DEV float edivide(float x, ediv_t e) { return x / e; }
+#else
+typedef double ediv_t;                     // its reciprocal in double: a block's eight / ten quotients share two divisors (div_rd)
+VKB_DEV ediv_t ediv(float e) { return rcp_dn(e); }   // clamped to [0.01, 98]: normal
+VKB_DEV float edivide(float x, ediv_t e) { return div_rd(x, e); }
+#endif
+VKB_DEV float splat_weight(ediv_t e0, ediv_t e1, float cz, float cw, int i, int j)
 { // splat.comp:33-37
   const float of0 = cz * (float)i + cw * (float)j;
   const float of1 = -cw * (float)i + cz * (float)j;
-  return clampf(m_exp(-0.5f * (of0 / e0 * of0 + of1 / e1 * of1)), 1e-4f, 1.0f);
+  return clampf(m_exp(-0.5f * (edivide(of0, e0) * of0 + edivide(of1, e1) * of1)), 1e-4f, 1.0f);
 }
 
 __global__ void __launch_bounds__(256, 6) k_bayer_splat(const __half *__restrict__ in, int w, int h,
@@ -28,7 +37,7 @@ __global__ void __launch_bounds__(256, 6) k_bayer_splat(const __half *__restrict
   const int b = blockIdx.x * 32 + threadIdx.x, c = BAND_BY * 8 + threadIdx.y;
   if(2 * b - 1 >= w || 2 * c - 1 >= h) return;
   const float4 cov = ld_rgba_clamp(gauss, gw, gh, b, c);
-  const float e0 = clampf(cov.x, 0.01f, 25.0f), e1 = clampf(cov.y, 0.01f, 25.0f);
+  const ediv_t e0 = ediv(clampf(cov.x, 0.01f, 25.0f)), e1 = ediv(clampf(cov.y, 0.01f, 25.0f));
   const float w11 = splat_weight(e0, e1, cov.z, cov.w, 1, 1), w1m = splat_weight(e0, e1, cov.z, cov.w, 1, -1);
   const float w10 = splat_weight(e0, e1, cov.z, cov.w, 1, 0), w01 = splat_weight(e0, e1, cov.z, cov.w, 0, 1);
   // 4x4 neighbourhood m[j][i] = mosaic(2b-2+i, 2c-2+j)
@@ -76,11 +85,11 @@ __global__ void __launch_bounds__(256, 6) k_bayer_splat(const __half *__restrict
   }
 }
 
-VKB_DEV float fixw(float e0, float e1, float cz, float cw, int i, int j)
+VKB_DEV float fixw(ediv_t e0, ediv_t e1, float cz, float cw, int i, int j)
 { // fix.comp:16-23
   const float of0 = cz * (float)i + cw * (float)j;
   const float of1 = -cw * (float)i + cz * (float)j;
-  return clampf(m_exp(-0.5f * (of0 / e0 * of0 + of1 / e1 * of1)), 1e-3f, 1.0f);
+  return clampf(m_exp(-0.5f * (edivide(of0, e0) * of0 + edivide(of1, e1) * of1)), 1e-3f, 1.0f);
 }
 
 __global__ void __launch_bounds__(256, 5) k_bayer_fix(const __half *__restrict__ in, const __half *__restrict__ green, int w, int h,
@@ -90,7 +99,7 @@ __global__ void __launch_bounds__(256, 5) k_bayer_fix(const __half *__restrict__
   if(2 * b - 1 >= w || 2 * c - 1 >= h) return;
   float4 cov = ld_rgba_clamp(covimg, gw, gh, b, c);
   cov.x = clampf(cov.x, 1.0f, 49.f); cov.y = clampf(cov.y, 1.0f, 49.f);
-  const float e0 = 2.0f * cov.x, e1 = 2.0f * cov.y;
+  const ediv_t e0 = ediv(2.0f * cov.x), e1 = ediv(2.0f * cov.y);
   const float w00 = fixw(e0, e1, cov.z, cov.w, 0, 0);
   const float w11 = fixw(e0, e1, cov.z, cov.w, 1, 1), w1m = fixw(e0, e1, cov.z, cov.w, 1, -1);
   const float w10 = fixw(e0, e1, cov.z, cov.w, 1, 0), w01 = fixw(e0, e1, cov.z, cov.w, 0, 1);
