@@ -224,7 +224,7 @@ VKB_DEV float gauss_expand(const __half *__restrict__ img, int w, int h, const s
       r += v;
     }
   }
-  return r / 9.0f;
+  return div9(r);
 }
 
 // ---- assemble for coarse levels (both l0 and l1 stacks are in memory) ----
@@ -282,7 +282,7 @@ VKB_DEV float gauss_expand_tile(const float (*T)[AT_W + 1], const soft_local_t &
       r += v;
     }
   }
-  return r / 9.0f;
+  return div9(r);
 }
 __global__ void __launch_bounds__(256) k_llap_assemble_tiled(const __half *__restrict__ coarse, const __half *__restrict__ l0,
     const __half *__restrict__ l1, int cw, int ch, __half *__restrict__ out, int ow, int oh, int first)

@@ -46,7 +46,7 @@ VKB_DEV float expand_q(const float (&W)[5][5])
       else v = top;
       r += v;
     }
-  return r / 9.0f;
+  return div9(r);
 }
 
 __global__ void __launch_bounds__(256, 4) k_llap_assemble4(const __half *__restrict__ coarse, const __half *__restrict__ l0,

@@ -149,7 +149,7 @@ VKB_DEV float expand_q(const float (&W)[5][5])
       else v = top;
       r += v;
     }
-  return r / 9.0f;
+  return div9(r);
 }
 VKB_DEV void expand4_exact(const float (*T)[F3_W + 1], int lx, int ly, float *t)
 {
