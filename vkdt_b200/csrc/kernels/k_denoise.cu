@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) k_denoise_half(const uint16_t *__restrict
   const int x = blockIdx.x * 32 + threadIdx.x, y = BAND_BY * 8 + threadIdx.y;
   if(x >= ow || y >= oh || BAND_SKIP(y)) return;
   float4 rgba;
-#define RAW(X, Y) ((float)__ldg(in + (size_t)clampi((Y), 0, ih - 1) * iw + clampi((X), 0, iw - 1)) / 65535.0f)
+#define RAW(X, Y) div_c((float)__ldg(in + (size_t)clampi((Y), 0, ih - 1) * iw + clampi((X), 0, iw - 1)), 65535.0f)
   if(xtrans)
   {
     float c[9];
@@ -57,8 +57,8 @@ __global__ void __launch_bounds__(256) k_denoise_half(const uint16_t *__restrict
   else
   { // textureGather at the block centre: x=(0,1) y=(1,1) z=(1,0) w=(0,0), mirrored repeat
     const int x0 = mirrori(cx + 2 * x, iw), x1 = mirrori(cx + 2 * x + 1, iw), y0 = mirrori(cy + 2 * y, ih), y1 = mirrori(cy + 2 * y + 1, ih);
-    float gx = (float)__ldg(in + (size_t)y1 * iw + x0) / 65535.0f, gy = (float)__ldg(in + (size_t)y1 * iw + x1) / 65535.0f;
-    float gz = (float)__ldg(in + (size_t)y0 * iw + x1) / 65535.0f, gw = (float)__ldg(in + (size_t)y0 * iw + x0) / 65535.0f;
+    float gx = div_c((float)__ldg(in + (size_t)y1 * iw + x0), 65535.0f), gy = div_c((float)__ldg(in + (size_t)y1 * iw + x1), 65535.0f);
+    float gz = div_c((float)__ldg(in + (size_t)y0 * iw + x1), 65535.0f), gw = div_c((float)__ldg(in + (size_t)y0 * iw + x0), 65535.0f);
     if(gx >= white) gx = gz;
     if(gz >= white) gz = gx;
     rgba = make_float4(gw, (gx + gz) / 2.0f, gy, 1.0f);
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256, 5) k_denoise_downcov(const uint2 *__restr
     const int r = t / DC_W, c = t - r * DC_W;
     const float4 v = ld_rgba(in, w, mirrori(tx0 + c, w), mirrori(ty0 + r, h));
     const float l = lum2020(v.x, v.y, v.z), l2 = l * l;
-    tile[r][c] = make_float4(v.x, v.y, v.z, l / 25.0f);
+    tile[r][c] = make_float4(v.x, v.y, v.z, div_c(l, 25.0f));
     tinv[r][c] = make_float4(l, 1.0f / l, l2, 1.0f / l2);
   }
   __syncthreads();
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(256, 6) k_denoise_down_tiled(const uint2 *__re
   noise_sigma(noise_a, noise_b, black, white, p.edges, c0.x, sigma);
 #else
   { // noise_sigma() with its quotient by the launch constant (white - black) through div_rd
-    const float s = sqrtf(noise_a + fmaxf(0.0f, div_rd(c0.x - black, rd_wb)) * noise_b);
+    const float s = sqrt_f(noise_a + fmaxf(0.0f, div_rd(c0.x - black, rd_wb)) * noise_b);   // noise_a, noise_b > 0
 #pragma unroll
     for(int k = 0; k < 3; k++) sigma[k] = clampf(p.edges[k] * s, 1e-3f, 1e3f);
   }
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(256, 6) k_denoise_down_tiled(const uint2 *__re
 #else
     sigma[k] = div_rd(lv * sigma[k], rd_blk);
 #endif
-    wc[k] = 1.0f / sigma[k];
+    wc[k] = div_f(1.0f, sigma[k]);   // clamped to [1e-3, 1e3] * lv / blk
     g0[k] = gamma08(cc[k], lme_ctx);
   }
   constexpr int   bx[4] = { 1, -2, 0, -1 }, by[4] = { 0, -1, -2, 1 };
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(256, 6) k_denoise_down_tiled(const uint2 *__re
     }
   }
   int ox, oy; swizzle(x, y, w, h, ox, oy);
-  st_rgba(out, w, ox, oy, make_float4(sum[0] / wgt[0], sum[1] / wgt[1], sum[2] / wgt[2], 1.0f));
+  st_rgba(out, w, ox, oy, make_float4(div_f(sum[0], wgt[0]), div_f(sum[1], wgt[1]), div_f(sum[2], wgt[2]), 1.0f));   // wgt >= 0.2
 }
 
 struct asm_consts_t { float rgb_to_yuv[9], yuv_to_rgb[9]; float wb[3], black[3], white[3]; float noise_a, noise_b, blk, thrs0, i2thrs0; float inorm[3], denorm[3];
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(256, 5) k_denoise_assemble(const uint2 *__rest
   noise_sigma(K.noise_a, K.noise_b, K.black[1], K.white[1], p.edges, fmaxf(d[2][0], 0.0f), sigma);
 #else
   { // noise_sigma() with its quotient by the launch constant (white - black) through div_rd
-    const float sq = sqrtf(K.noise_a + fmaxf(0.0f, div_rd(fmaxf(d[2][0], 0.0f) - K.black[1], K.rd_wb[1])) * K.noise_b);
+    const float sq = sqrt_f(K.noise_a + fmaxf(0.0f, div_rd(fmaxf(d[2][0], 0.0f) - K.black[1], K.rd_wb[1])) * K.noise_b);
 #pragma unroll
     for(int k = 0; k < 3; k++) sigma[k] = clampf(p.edges[k] * sq, 1e-3f, 1e3f);
   }
@@ -402,12 +402,12 @@ __global__ void __launch_bounds__(256, 5) k_denoise_assemble(const uint2 *__rest
 #if VKB_FAST
     for(int k = 0; k < 3; k++) d[l][k] = (d[l][k] - d[l + 1][k]) * (isig[k] * K.ibb[l]); // 1/(sigma bb) as a product of reciprocals: 3 instead of 12
 #else
-    for(int k = 0; k < 3; k++) d[l][k] = (d[l][k] - d[l + 1][k]) / (sigma[k] * bb[l]);
+    for(int k = 0; k < 3; k++) d[l][k] = div_f(d[l][k] - d[l + 1][k], sigma[k] * bb[l]);   // sigma in [1e-3, 1e3], bb > 0
 #endif
-    len[l] = sqrtf(d[l][0] * d[l][0] + d[l][1] * d[l][1] + d[l][2] * d[l][2]);
+    len[l] = sqrt_f(d[l][0] * d[l][0] + d[l][1] * d[l][1] + d[l][2] * d[l][2]);
   }
-  const float slope = ((len[3] - len[0]) / 3.0f + (len[2] - len[1]) / 1.0f + (len[1] - len[0]) / 1.0f
-      + (len[3] - len[2]) / 1.0f + (len[2] - len[0]) / 2.0f + (len[3] - len[1]) / 2.0f) / 6.0f;
+  const float slope = div_c(div_c(len[3] - len[0], 3.0f) + (len[2] - len[1]) / 1.0f + (len[1] - len[0]) / 1.0f
+      + (len[3] - len[2]) / 1.0f + (len[2] - len[0]) / 2.0f + (len[3] - len[1]) / 2.0f, 6.0f);
   float test = fmaxf(0.0f, -slope);
   test = fmaxf(0.0f, 1.0f - test);
 #if VKB_FAST
@@ -482,8 +482,8 @@ VKB_DEV float doub_shrink(float val, float upsm_c, float down_c, float upw, int 
   blendw = 0.5f * (blendw + 1.0f);
   if(val < white)
   {
-    const float wav = (val - down_c) / fmaxf(sigma[0] + sigma[2], 1e-8f);
-    const float tt = fminf(1.0f, wav / fmaxf(2.0f * T, 1e-8f));
+    const float wav = div_f(val - down_c, fmaxf(sigma[0] + sigma[2], 1e-8f));
+    const float tt = fminf(1.0f, div_f(wav, fmaxf(2.0f * T, 1e-8f)));
 #if VKB_FAST
     float uw = fminf(1.0f, 1.0f * upw); uw = uw * uw; uw = uw * uw; // pow(.., 4)
 #else
@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(256) k_denoise_doub(const uint16_t *__restrict
   const float4 down = bilin_rgba(crs1, cw, ch, bx, by, ax, ay);
   const bool xt = P.filters == 9;
   const int col = xt ? xtrans_colour(x, y) : bayer_colour(x, y);
-  const float val = (float)__ldg(in + (size_t)mirrori(y + P.crop[1], ih) * iw + mirrori(x + P.crop[0], iw)) / 65535.0f;
+  const float val = div_c((float)__ldg(in + (size_t)mirrori(y + P.crop[1], ih) * iw + mirrori(x + P.crop[0], iw)), 65535.0f);
   const float uc = col == 1 ? upsm.y : (col == 0 ? upsm.x : upsm.z), dc = col == 1 ? down.y : (col == 0 ? down.x : down.z);
   float res = doub_shrink(val, uc, dc, upsm.w, col, xt, p, P);
   if(G.map) res *= gainmap_gain(G, x, y, P.crop[0], P.crop[1], ow, oh, 2);   // doub.comp:106-114
@@ -554,8 +554,8 @@ __global__ void __launch_bounds__(256, 5) k_denoise_doub_bayer(const uint16_t *_
 #define AX(D) ((D) ? 0.25f : 0.75f)
   const int ry0 = mirrori(2 * Y + P.crop[1], ih), ry1 = mirrori(2 * Y + 1 + P.crop[1], ih);
   const int rx0 = mirrori(2 * X + P.crop[0], iw), rx1 = mirrori(2 * X + 1 + P.crop[0], iw);
-  const float v00 = (float)__ldg(in + (size_t)ry0 * iw + rx0) / 65535.0f, v10 = (float)__ldg(in + (size_t)ry0 * iw + rx1) / 65535.0f;
-  const float v01 = (float)__ldg(in + (size_t)ry1 * iw + rx0) / 65535.0f, v11 = (float)__ldg(in + (size_t)ry1 * iw + rx1) / 65535.0f;
+  const float v00 = div_c((float)__ldg(in + (size_t)ry0 * iw + rx0), 65535.0f), v10 = div_c((float)__ldg(in + (size_t)ry0 * iw + rx1), 65535.0f);
+  const float v01 = div_c((float)__ldg(in + (size_t)ry1 * iw + rx0), 65535.0f), v11 = div_c((float)__ldg(in + (size_t)ry1 * iw + rx1), 65535.0f);
   const float o00 = doub_shrink(v00, BIL(u[0], 0, 0), BIL(d[0], 0, 0), BIL(u[3], 0, 0), 0, false, p, P); // r
   const float o10 = doub_shrink(v10, BIL(u[1], 1, 0), BIL(d[1], 1, 0), BIL(u[3], 1, 0), 1, false, p, P); // g
   const float o01 = doub_shrink(v01, BIL(u[1], 0, 1), BIL(d[1], 0, 1), BIL(u[3], 0, 1), 1, false, p, P); // g

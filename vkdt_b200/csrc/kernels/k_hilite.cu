@@ -141,12 +141,12 @@ __global__ void __launch_bounds__(256) k_hilite_assemble(const uint2 *__restrict
     }
   }
   if(wgt == 0.0f) { ur = 0.0f; ug = 1.0f; ub = 1.0f; }
-  else { ur /= wgt; ug /= wgt; ub /= wgt; }
+  else { ur = div_f(ur, wgt); ug = div_f(ug, wgt); ub = div_f(ub, wgt); }   // a sum of the positive tap weights
   float4 fine = ld_rgba(fine_img, ow, x, y);
   const float white = p.white;
-  const float sr = fine.x / fmaxf(0.001f, ur);
-  const float sg = fine.y / fmaxf(0.001f, ug);
-  const float sb = fine.z / fmaxf(0.001f, ub);
+  const float sr = div_f(fine.x, fmaxf(0.001f, ur));
+  const float sg = div_f(fine.y, fmaxf(0.001f, ug));
+  const float sb = div_f(fine.z, fmaxf(0.001f, ub));
   // blend weights: libm's exponential bit for bit (strict) or the SFU one (fast, 2 ulp), three times per pixel
   const float wr = m_exp(ur - fmaxf(ug, ub));
   const float wg = m_exp(ug - fmaxf(ur, ub));
