@@ -14,7 +14,9 @@
 
 struct llap_params_t { float sigma, shadows, hilights, clarity; };
 
-VKB_DEV float gamma_from_i(int i) { return (float)i / (NUM_GAMMA - 1.0f); }
+VKB_DEV float gamma_from_i(int i) { return div_c((float)i, NUM_GAMMA - 1.0f); }
+// for an index the compiler knows (unrolled loops): the plain quotient folds to a constant, the intrinsics of div_c do not
+VKB_DEV float gamma_from_const_i(int i) { return (float)i / (NUM_GAMMA - 1.0f); }
 VKB_DEV int gamma_hi_from_v(float v)
 { // llap.glsl:17-22 without a loop of divisions: 1 + #{ i in 1..8 : i/9 <= v }, the i/9 fold to constants
   int hi = 1;
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(256, 6) k_llap_reduce0(const uint2 *__restrict
     const int gx = big ? mirror1(tx0 + lx, iw) : mirrori(tx0 + lx, iw), gy = big ? mirror1(ty0 + ly, ih) : mirrori(ty0 + ly, ih);
     const float y = llap_grey(ld_rgba(in, iw, gx, gy));
 #pragma unroll
-    for(int g = 0; g < NUM_GAMMA; g++) tile[g][ly][lx] = __float2half_rn(llap_curve_k<CLARITY>(y, gamma_from_i(g), p, inv2s, invd, R, lme_ctx));
+    for(int g = 0; g < NUM_GAMMA; g++) tile[g][ly][lx] = __float2half_rn(llap_curve_k<CLARITY>(y, gamma_from_const_i(g), p, inv2s, invd, R, lme_ctx));
     tile[NUM_GAMMA][ly][lx] = __float2half_rn(y);
   }
   __syncthreads();

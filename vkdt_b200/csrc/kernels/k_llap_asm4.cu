@@ -12,7 +12,7 @@
 #define A4_W 36
 #define A4_H 12
 
-VKB_DEV float gamma_from_i(int i) { return (float)i / (NUM_GAMMA - 1.0f); }
+VKB_DEV float gamma_from_i(int i) { return div_c((float)i, NUM_GAMMA - 1.0f); }
 VKB_DEV int gamma_hi_from_v(float v)
 { // llap.glsl:17-22: 1 + #{ i in 1..8 : i/9 <= v }
   int hi = 1;
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256, 4) k_llap_assemble4(const __half *__restr
     const int x = 2 * kx + (q & 1), y = 2 * ky + (q >> 1);
     const int lo = hi[q] - 1;
     const float glo = gamma_from_i(lo), ghi = gamma_from_i(hi[q]);
-    const float a = clampf((v[q] - glo) / (ghi - glo), 0.0f, 1.0f);
+    const float a = clampf(div_f(v[q] - glo, ghi - glo), 0.0f, 1.0f);   // the spacing of two gamma values: 1 / 9
     const float lap0 = ld_h(l0 + lo * p0, ow, x, y) - e0[q];
     const float lap1 = ld_h(l0 + hi[q] * p0, ow, x, y) - e1[q];
     // explicit _rn ops: this blend feeds the next pyramid level, keep it unfused whatever the compiler flags say

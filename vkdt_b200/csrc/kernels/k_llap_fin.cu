@@ -21,7 +21,7 @@ struct llap_rd_t { double rd2s, rdk; };   // 1 / (2 sigma), 1 / (2 sigma^2 / 3) 
 struct llapfin_t { llap_rd_t rd; llap_params_t p; int first; int have_grade; int out_f32; grade_params_t grade;
                    float inv2s, invd; float g_lift[3], g_oml[3], g_gain[3], g_off[3], g_ig[3]; };
 
-VKB_DEV float gamma_from_i(int i) { return (float)i / (NUM_GAMMA - 1.0f); }
+VKB_DEV float gamma_from_i(int i) { return div_c((float)i, NUM_GAMMA - 1.0f); }
 // llap.glsl:17-22 gamma_hi_from_v without the loop of divisions: 1 + #{ i in 1..8 : i/9 <= v } (the i/9 are compile time constants)
 VKB_DEV int gamma_hi(float v)
 {
@@ -162,9 +162,11 @@ VKB_DEV void expand4_exact(const float (*T)[F3_W + 1], int lx, int ly, float *t)
 }
 
 // grade/main.comp:21-40 (mode 0) on the host-evaluated constants of llapfin_t: same operations, same order as grade_px()
+// (the other grading modes stay out of line: inlined, their quotients, logarithms and powers cost the default path registers)
+static __device__ __noinline__ f3 grade_px_other(f3 c, const grade_params_t &g) { return grade_px(c, g); }
 VKB_DEV f3 grade_px_digest(f3 c, const llapfin_t &P)
 {
-  if(P.grade.mode != 0) return grade_px(c, P.grade);
+  if(P.grade.mode != 0) return grade_px_other(c, P.grade);
   float v[3] = { c.x, c.y, c.z };
 #pragma unroll
   for(int k = 0; k < 3; k++)
