@@ -88,14 +88,17 @@ int parse(const uint8_t *d, size_t size, frame_t *f)
     else if(marker == 0xda)
     { // SOS
       if(!have_sof || n < 1 || s[0] != f->ncomp || n < (size_t)(4 + 2 * f->ncomp)) return 1;
+      bool assigned[4] = { false, false, false, false };
       for(int c = 0; c < f->ncomp; c++)
       {
         int idx = -1;
         for(int k = 0; k < f->ncomp; k++) if(f->comp_id[k] == s[1 + 2 * c]) idx = k;
-        if(idx < 0) return 1;
+        if(idx < 0 || idx >= 4 || assigned[idx]) return 1;   // unknown component, or one listed twice (another would keep no table)
+        assigned[idx] = true;
         f->comp_table[idx] = s[2 + 2 * c] >> 4;
         if(f->comp_table[idx] > 3 || !f->huff[f->comp_table[idx]].present) return 1;
       }
+      for(int k = 0; k < f->ncomp; k++) if(!assigned[k]) return 1;
       f->predictor = s[1 + 2 * f->ncomp];
       f->pt = s[3 + 2 * f->ncomp] & 15;
       if(f->predictor < 1 || f->predictor > 7 || f->pt >= f->precision) return 1;
