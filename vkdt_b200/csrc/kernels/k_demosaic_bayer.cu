@@ -18,7 +18,7 @@ VKB_DEV float splat_fetch(const __half *__restrict__ in, int w, int h, int px, i
 #if VKB_FAST
 typedef float ediv_t;                      // the eigenvalue itself
 VKB_DEV ediv_t ediv(float e) { return e; }
-VKB_DEV float edivide(float x, ediv_t e) { return x / e; }
+VKB_DEV float edivide(float x, ediv_t e) { return div_f(x, e); }   // clamped eigenvalue: the call free exact quotient
 #else
 typedef double ediv_t;                     // its reciprocal in double: a block's eight / ten quotients share two divisors (div_rd)
 VKB_DEV ediv_t ediv(float e) { return rcp_dn(e); }   // clamped to [0.01, 98]: normal

@@ -105,10 +105,10 @@ VKB_DEV void expand4(const float (*T)[F3_W + 1], int lx, int ly, float &ee, floa
     he[r] = 0.5f * (t0 + t1) + t2 + 0.5f * (t3 + t4);
     ho[r] = t1 + 0.5f * (t2 + t3) + t4;
   }
-  ee = (0.5f * (he[0] + he[1]) + he[2] + 0.5f * (he[3] + he[4])) / 9.0f;
-  oe = (0.5f * (ho[0] + ho[1]) + ho[2] + 0.5f * (ho[3] + ho[4])) / 9.0f;
-  eo = (he[1] + 0.5f * (he[2] + he[3]) + he[4]) / 9.0f;
-  oo = (ho[1] + 0.5f * (ho[2] + ho[3]) + ho[4]) / 9.0f;
+  ee = div9(0.5f * (he[0] + he[1]) + he[2] + 0.5f * (he[3] + he[4]));
+  oe = div9(0.5f * (ho[0] + ho[1]) + ho[2] + 0.5f * (ho[3] + ho[4]));
+  eo = div9(he[1] + 0.5f * (he[2] + he[3]) + he[4]);
+  oo = div9(ho[1] + 0.5f * (ho[2] + ho[3]) + ho[4]);
 }
 
 VKB_DEV float expand1(const float (*T)[F3_W + 1], int lx, int ly, int q)
@@ -123,7 +123,7 @@ VKB_DEV float expand1(const float (*T)[F3_W + 1], int lx, int ly, int q)
     const float *row = T[ly - 2 + r] + lx - 2;
     acc += (row[0] * wx[0] + row[1] * wx[1] + row[2] * wx[2] + row[3] * wx[3] + row[4] * wx[4]) * wy[r];
   }
-  return acc / 9.0f;
+  return div9(acc);
 }
 
 // strict build: sample_soft's nine bilinear taps in the shader's order (as k_llap_asm4.cu's expand_q), from the 5x5 window
