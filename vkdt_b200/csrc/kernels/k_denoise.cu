@@ -19,7 +19,11 @@ struct dn_push_doub_t { float wb[4], black[4], white[4]; int32_t crop[4]; uint32
 // `escale[k]` = exp2(12*edges[k] + edges[3]) is a function of the module params only: evaluated once per launch on the host
 VKB_DEV void noise_sigma(float a, float b, float black, float white, const float *escale, float val, float *sig)
 {
+#if VKB_FAST   // call free forms (white > black, a, b >= 0: a noise profile)
+  const float s = sqrt_f(a + fmaxf(0.0f, div_f(val - black, white - black)) * b);
+#else
   const float s = sqrtf(a + fmaxf(0.0f, (val - black) / (white - black)) * b);
+#endif
 #pragma unroll
   for(int k = 0; k < 3; k++) sig[k] = clampf(escale[k] * s, 1e-3f, 1e3f);
 }
@@ -492,7 +496,11 @@ VKB_DEV float doub_shrink(float val, float upsm_c, float down_c, float upw, int 
     uw = 1.0f - (1.0f - uw) * p.detail;
     val = mixf(val, fmaxf(0.0f, upsm_c + sigma[1] * signf(wav) * mixf(fmaxf(0.0f, fabsf(wav) - T), fabsf(wav), tt)), uw * blendw);
   }
+#if VKB_FAST
+  return fmaxf(0.0f, div_f(val - black, white - black));
+#else
   return fmaxf(0.0f, (val - black) / (white - black));
+#endif
 }
 
 __global__ void __launch_bounds__(256) k_denoise_doub(const uint16_t *__restrict__ in, int iw, int ih,
