@@ -67,6 +67,8 @@ int main(int argc, char **argv)
       const float x = lme_u2f((uint32_t)u);
       if(!same(lme_powf(x, ys[j]), powf(x, ys[j]))) b++;
       if(fabsf(ys[j]) <= 0.84f && !same(lme_powf_smally(x, ys[j]), powf(x, ys[j]))) b++;
+      // positive normal x, |y log2 x| < 120: the variant without any special case (the default tone curve's power)
+      if(u >= 0x00800000u && fabs((double)ys[j] * log2((double)x)) < 120.0 && !same(lme_powf_safe(x, ys[j]), powf(x, ys[j]))) b++;
     }
     b4 += b;
   }

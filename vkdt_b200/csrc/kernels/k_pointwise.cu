@@ -254,17 +254,21 @@ static int colour_digest(const float *f, uint32_t size, colour_digest_t *d)
 // weibull_cdf() of pointwise.cuh on the bare SFU instructions.  __powf / __expf expand to the same ex2.approx / lg2.approx
 // but wrap each in a denormal guard (compare, scale, unscale: 4 instructions instead of 1); arguments here are >= 1e-7 * il
 // and a result below 2^-126 only ever enters 1 - x, so flushing it changes nothing.
+// SAFE (strict): the launcher has checked that il and k are finite and that k log2(x il) stays inside +-126 for every x in
+// [1e-7, 65541] (the clamp in front of the curve): powf then has no special case left and the kernel no out of line call
+template <bool SAFE>
 VKB_DEV float weibull_cdf_ftz(float x, float il, float k)
 {
 #if VKB_FAST
   const float p = ex2_ftz(k * lg2_ftz(fmaxf(x, 1e-7f) * il));   // __powf(x * il, k)
   return 1.0f - ex2_ftz(-p * 1.4426950408889634f);               // __expf(-p)
 #else
+  if(SAFE) return 1.0f - m_exp(-lme_powf_safe(fmaxf(x, 1e-7f) * il, k));
   return weibull_cdf(x, il, k);                                  // libm's powf and expf bit for bit
 #endif
 }
 #define PW_NPX 4
-template <bool F32>
+template <bool F32, bool SAFE>
 __global__ void __launch_bounds__(256) k_pointwise_dflt(const uint2 *__restrict__ in, int iw, int ih,
     void *__restrict__ outv, int ow, int oh, const __grid_constant__ pw_chain_t P, const band_t bd)
 {
@@ -307,8 +311,12 @@ __global__ void __launch_bounds__(256) k_pointwise_dflt(const uint2 *__restrict_
   const bool fx = s2 > s1; if(fx) { t = s2; s2 = s1; s1 = t; }
   const bool fy = s1 > s0; if(fy) { t = s0; s0 = s1; s1 = t; }
   const bool fz = s2 > s1; if(fz) { t = s2; s2 = s1; s1 = t; }
-  float r0 = weibull_cdf_ftz(s0, il, k), r2 = weibull_cdf_ftz(s2, il, k);
+  float r0 = weibull_cdf_ftz<SAFE>(s0, il, k), r2 = weibull_cdf_ftz<SAFE>(s2, il, k);
+#if VKB_FAST
   float r1 = mixf(r2, r0, m_div(s1 - s2 + 1e-6f, s0 - s2 + 1e-6f));
+#else  // sorted and clamped to +-65535: the divisor lies in [1e-6, 131071], the call free exact quotient applies
+  float r1 = mixf(r2, r0, div_f(s1 - s2 + 1e-6f, s0 - s2 + 1e-6f));
+#endif
   if(fz) { t = r2; r2 = r1; r1 = t; }
   if(fy) { t = r0; r0 = r1; r1 = t; }
   if(fx) { t = r2; r2 = r1; r1 = t; }
@@ -404,8 +412,15 @@ static int launch_chain(const vkb_launch_t *l, int n_ops, const uint32_t *ops)
     dim3 gridn(vkb_cdiv(out->wd, 32 * PW_NPX), vkb_cdiv(out->ht, 8));
     const band_t bd = band_of(l, 1, 8, out->ht, &gridn.y);
     if(!gridn.y) return VKB_OK;
-    if(P.out_f32) k_pointwise_dflt<true><<<gridn, block, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, out->data, out->wd, out->ht, P, bd);
-    else          k_pointwise_dflt<false><<<gridn, block, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, out->data, out->wd, out->ht, P, bd);
+    // the curve's power: x il in [1e-7 il, 65541 il] (col0 = clamp(+-65535) + bias; the shader's max(x, 1e-7)), exponent k
+    const float il = fmaxf(5e-3f, P.film.light), kk = fmaxf(1e-4f, P.film.contrast);
+    const double lo = log2(1e-7 * (double)il), hi = log2((65536.0 + fabs((double)P.film.bias)) * (double)il);
+    const bool safe = std::isfinite(il) && std::isfinite(kk) && std::isfinite(P.film.bias) && il < 1e30f &&
+                      (double)kk * fmax(fabs(lo), fabs(hi)) < 120.0;
+#define GO(F, S) k_pointwise_dflt<F, S><<<gridn, block, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, out->data, out->wd, out->ht, P, bd)
+    if(P.out_f32) { if(safe) GO(true, true); else GO(true, false); }
+    else          { if(safe) GO(false, true); else GO(false, false); }
+#undef GO
     VKB_CHECK_LAUNCH();
     return VKB_OK;
   }

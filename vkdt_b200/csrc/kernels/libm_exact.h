@@ -322,10 +322,12 @@ template <class TAB> LME_FN float lme_expf_t(float x, const TAB tab)
 // positive y is answered in line (black pixels are common); the rest (subnormal, negative, inf, nan, over/underflow) is rare
 // SMALLY: the caller guarantees |y| <= 0.84, so that |y log2 x| < 126 for every positive finite x (|log2 x| < 150) and the
 // over / underflow test of the general case is dead
-template <bool SMALLY, class TAB> LME_FN float lme_powf_tt(float x, float y, const TAB tab)
+// POSX: the caller guarantees a positive, normal, finite x and a finite non zero y: no special case is left in front of the
+// logarithm; together with SMALLY (here: |y log2 x| < 126 checked by the caller for its range of x) nothing can call
+template <bool SMALLY, bool POSX, class TAB> LME_FN float lme_powf_ttt(float x, float y, const TAB tab)
 {
   const uint32_t ix = LME_F2U(x), iy = LME_F2U(y);
-  int rare = (ix - 0x00800000u >= 0x7f000000u) || (2 * iy - 1 >= 2u * 0x7f800000u - 1);
+  int rare = POSX ? 0 : ((ix - 0x00800000u >= 0x7f000000u) || (2 * iy - 1 >= 2u * 0x7f800000u - 1));
   const uint32_t ixs = rare ? 0x3f800000u : ix;
   const uint32_t tmp = ixs - 0x3f330000u;
   const int i = (tmp >> 19) & 15;
@@ -364,6 +366,7 @@ template <bool SMALLY, class TAB> LME_FN float lme_powf_tt(float x, float y, con
   }
   return out;
 }
+template <bool SMALLY, class TAB> LME_FN float lme_powf_tt(float x, float y, const TAB tab) { return lme_powf_ttt<SMALLY, false>(x, y, tab); }
 template <class TAB> LME_FN float lme_powf_t(float x, float y, const TAB tab) { return lme_powf_tt<false>(x, y, tab); }
 // tables in global memory (L1 resident)
 struct lme_gtab_t
@@ -374,6 +377,7 @@ struct lme_gtab_t
 LME_FN float lme_expf(float x) { return lme_expf_t(x, lme_gtab_t()); }
 LME_FN float lme_powf(float x, float y) { return lme_powf_t(x, y, lme_gtab_t()); }
 LME_FN float lme_powf_smally(float x, float y) { return lme_powf_tt<true>(x, y, lme_gtab_t()); }
+LME_FN float lme_powf_safe(float x, float y) { return lme_powf_ttt<true, true>(x, y, lme_gtab_t()); }
 #if defined(__CUDACC__)
 // tables in shared memory: `base` is the 32 bit shared address of a filled lme_smem_t, kept in one register
 struct lme_stab_t
