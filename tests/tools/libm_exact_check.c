@@ -67,11 +67,15 @@ int main(int argc, char **argv)
       const float x = lme_u2f((uint32_t)u);
       if(!same(lme_powf(x, ys[j]), powf(x, ys[j]))) b++;
       if(fabsf(ys[j]) <= 0.84f && !same(lme_powf_smally(x, ys[j]), powf(x, ys[j]))) b++;
+      // +0, positive normal, (+inf, nan: below) and |y log2 x| < 120, positive y: the variant that answers the specials by selects
+      if((u == 0 || u >= 0x00800000u) && ys[j] > 0.0f && (u == 0 || fabs((double)ys[j] * log2((double)x)) < 120.0) && !same(lme_powf_nonneg(x, ys[j]), powf(x, ys[j]))) b++;
       // positive normal x, |y log2 x| < 120: the variant without any special case (the default tone curve's power)
       if(u >= 0x00800000u && fabs((double)ys[j] * log2((double)x)) < 120.0 && !same(lme_powf_safe(x, ys[j]), powf(x, ys[j]))) b++;
     }
     b4 += b;
   }
+  { const float sp[3] = { INFINITY, NAN, lme_u2f(0x7fc12345u) };
+    for(int k = 0; k < 3; k++) { if(!same(lme_powf_nonneg(sp[k], 0.8f), powf(sp[k], 0.8f))) b4++; if(!same(lme_powf_nonneg(sp[k], 4.0f), powf(sp[k], 4.0f))) b4++; } }
   bad[4] = b4;
   const char *name[5] = { "expf", "exp2f", "logf", "log2f", "powf" };
   int rc = 0;

@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(256, 5) k_denoise_downcov(const uint2 *__restr
 // x^0.8 on the SFU (fast): ~1e-6 relative, i.e. <= 1e-4 in the [0,1] edge weight even at the 1e-3 noise floor of noise.glsl
 VKB_DEV float gamma08(float f) { return f < 0.0f ? f : m_pow(f, 0.8f); }
 // (the branch stays: below black every other noisy value is negative, and a select would pay for the power all the same)
-VKB_DEV float gamma08(float f, const lme_ctx_t &L) { return f < 0.0f ? f : m_pow_sy(f, 0.8f, L); }
+// f >= 0 here is a non negative combination of f16 texels: +0 or far above the subnormal range (m_pow_nn: no call)
+VKB_DEV float gamma08(float f, const lme_ctx_t &L) { return f < 0.0f ? f : m_pow_nn(f, 0.8f, L); }
 
 // ---- down: levels 1..3, 5 tap flower with edge stopping (down.comp:59-107) ----
 __global__ void __launch_bounds__(256) k_denoise_down(const uint2 *__restrict__ in, int w, int h, uint2 *__restrict__ out,
@@ -470,8 +471,10 @@ __global__ void __launch_bounds__(256, 5) k_denoise_assemble(const uint2 *__rest
 
 // ---- doub: per-colour residual shrink on the full resolution mosaic (doub.comp:35-115) ----
 // the per pixel part after the two coarse lookups: upsm_c / down_c are the pixel's own colour channel of crs0 / crs1, upw = crs0.w
+// strict: 1 / (white - black) per colour in double, from the launcher (div_rd: the quotient by a launch constant)
+struct doub_rd_t { double rd[3]; };
 VKB_DEV float doub_shrink(float val, float upsm_c, float down_c, float upw, int col, bool xt,
-    const denoise_params_t &p, const dn_push_doub_t &P)
+    const denoise_params_t &p, const dn_push_doub_t &P, const doub_rd_t &R)
 {
   float black = P.black[1], white = P.white[1];
   float T = 0.5f * p.strength * upw, blendw = p.luma;
@@ -482,7 +485,15 @@ VKB_DEV float doub_shrink(float val, float upsm_c, float down_c, float upw, int 
     if(xt) T /= fmaxf(1e-4f, upw);
   }
   float sigma[3];
+#if VKB_FAST
   noise_sigma(P.noise_a, P.noise_b, black, white, p.edges, upsm_c, sigma);
+#else
+  { // noise_sigma() without an out of line call: the quotient by (white - black) through div_rd, sqrt.rn's fast path (a, b >= 0)
+    const float s = sqrt_f(P.noise_a + fmaxf(0.0f, div_rd(upsm_c - black, R.rd[col])) * P.noise_b);
+#pragma unroll
+    for(int k = 0; k < 3; k++) sigma[k] = clampf(p.edges[k] * s, 1e-3f, 1e3f);
+  }
+#endif
   blendw = 0.5f * (blendw + 1.0f);
   if(val < white)
   {
@@ -491,7 +502,7 @@ VKB_DEV float doub_shrink(float val, float upsm_c, float down_c, float upw, int 
 #if VKB_FAST
     float uw = fminf(1.0f, 1.0f * upw); uw = uw * uw; uw = uw * uw; // pow(.., 4)
 #else
-    float uw = m_pow(fminf(1.0f, 1.0f * upw), 4.0f);
+    float uw = m_pow_nn(fminf(1.0f, 1.0f * upw), 4.0f);   // upw: a bilinear blend of f16 edge values in [0, 1]: +0 or >= 2^-24 * 1/16, 4 log2 < 126
 #endif
     uw = 1.0f - (1.0f - uw) * p.detail;
     val = mixf(val, fmaxf(0.0f, upsm_c + sigma[1] * signf(wav) * mixf(fmaxf(0.0f, fabsf(wav) - T), fabsf(wav), tt)), uw * blendw);
@@ -499,13 +510,13 @@ VKB_DEV float doub_shrink(float val, float upsm_c, float down_c, float upw, int 
 #if VKB_FAST
   return fmaxf(0.0f, div_f(val - black, white - black));
 #else
-  return fmaxf(0.0f, (val - black) / (white - black));
+  return fmaxf(0.0f, div_rd(val - black, R.rd[col]));
 #endif
 }
 
 __global__ void __launch_bounds__(256) k_denoise_doub(const uint16_t *__restrict__ in, int iw, int ih,
     const uint2 *__restrict__ crs0, const uint2 *__restrict__ crs1, int cw, int ch, __half *__restrict__ out, int ow, int oh,
-    const __grid_constant__ denoise_params_t p, const __grid_constant__ dn_push_doub_t P, const gainmap_t G)
+    const __grid_constant__ denoise_params_t p, const __grid_constant__ dn_push_doub_t P, const gainmap_t G, const doub_rd_t R)
 {
   const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
   if(x >= ow || y >= oh) return;
@@ -528,7 +539,7 @@ __global__ void __launch_bounds__(256) k_denoise_doub(const uint16_t *__restrict
   const int col = xt ? xtrans_colour(x, y) : bayer_colour(x, y);
   const float val = div_c((float)__ldg(in + (size_t)mirrori(y + P.crop[1], ih) * iw + mirrori(x + P.crop[0], iw)), 65535.0f);
   const float uc = col == 1 ? upsm.y : (col == 0 ? upsm.x : upsm.z), dc = col == 1 ? down.y : (col == 0 ? down.x : down.z);
-  float res = doub_shrink(val, uc, dc, upsm.w, col, xt, p, P);
+  float res = doub_shrink(val, uc, dc, upsm.w, col, xt, p, P, R);
   if(G.map) res *= gainmap_gain(G, x, y, P.crop[0], P.crop[1], ow, oh, 2);   // doub.comp:106-114
   out[(size_t)y * ow + x] = __float2half_rn(res);
 }
@@ -539,7 +550,7 @@ __global__ void __launch_bounds__(256) k_denoise_doub(const uint16_t *__restrict
 // expressions are those of bilin_rgba() term by term.
 __global__ void __launch_bounds__(256, 5) k_denoise_doub_bayer(const uint16_t *__restrict__ in, int iw, int ih,
     const uint2 *__restrict__ crs0, const uint2 *__restrict__ crs1, int cw, int ch, __half *__restrict__ out, int ow, int oh,
-    const __grid_constant__ denoise_params_t p, const __grid_constant__ dn_push_doub_t P, const band_t bd)
+    const __grid_constant__ denoise_params_t p, const __grid_constant__ dn_push_doub_t P, const doub_rd_t R, const band_t bd)
 {
   const int X = blockIdx.x * 32 + threadIdx.x, Y = BAND_BY * 8 + threadIdx.y;
   if(X >= cw || Y >= ch || BAND_SKIP(Y)) return;
@@ -564,10 +575,10 @@ __global__ void __launch_bounds__(256, 5) k_denoise_doub_bayer(const uint16_t *_
   const int rx0 = mirrori(2 * X + P.crop[0], iw), rx1 = mirrori(2 * X + 1 + P.crop[0], iw);
   const float v00 = div_c((float)__ldg(in + (size_t)ry0 * iw + rx0), 65535.0f), v10 = div_c((float)__ldg(in + (size_t)ry0 * iw + rx1), 65535.0f);
   const float v01 = div_c((float)__ldg(in + (size_t)ry1 * iw + rx0), 65535.0f), v11 = div_c((float)__ldg(in + (size_t)ry1 * iw + rx1), 65535.0f);
-  const float o00 = doub_shrink(v00, BIL(u[0], 0, 0), BIL(d[0], 0, 0), BIL(u[3], 0, 0), 0, false, p, P); // r
-  const float o10 = doub_shrink(v10, BIL(u[1], 1, 0), BIL(d[1], 1, 0), BIL(u[3], 1, 0), 1, false, p, P); // g
-  const float o01 = doub_shrink(v01, BIL(u[1], 0, 1), BIL(d[1], 0, 1), BIL(u[3], 0, 1), 1, false, p, P); // g
-  const float o11 = doub_shrink(v11, BIL(u[2], 1, 1), BIL(d[2], 1, 1), BIL(u[3], 1, 1), 2, false, p, P); // b
+  const float o00 = doub_shrink(v00, BIL(u[0], 0, 0), BIL(d[0], 0, 0), BIL(u[3], 0, 0), 0, false, p, P, R); // r
+  const float o10 = doub_shrink(v10, BIL(u[1], 1, 0), BIL(d[1], 1, 0), BIL(u[3], 1, 0), 1, false, p, P, R); // g
+  const float o01 = doub_shrink(v01, BIL(u[1], 0, 1), BIL(d[1], 0, 1), BIL(u[3], 0, 1), 1, false, p, P, R); // g
+  const float o11 = doub_shrink(v11, BIL(u[2], 1, 1), BIL(d[2], 1, 1), BIL(u[3], 1, 1), 2, false, p, P, R); // b
 #undef BIL
 #undef AX
   *reinterpret_cast<__half2 *>(out + (size_t)(2 * Y) * ow + 2 * X)     = __floats2half2_rn(o00, o10);
@@ -701,17 +712,19 @@ static int launch_doub(const vkb_launch_t *l)
     G.map = (const float4 *)l->conn[4].data; G.w = (int)l->conn[4].wd; G.h = (int)l->conn[4].ht;
     for(int k = 0; k < 4; k++) G.os[k] = P.map_os[k];
   }
+  doub_rd_t R;
+  for(int k = 0; k < 3; k++) { const volatile float wmb = P.white[k] - P.black[k]; R.rd[k] = 1.0 / (double)wmb; }
   if(!G.map && P.filters != 9u && P.filters != 0u && out->wd == 2 * c0->wd && out->ht == 2 * c0->ht)
   {
     dim3 grid = grid2d(c0->wd, c0->ht);
     const band_t bd = band_of(l, 2, 8, c0->ht, &grid.y); // band image: the output mosaic, two rows per thread row
     if(!grid.y) return VKB_OK;
     k_denoise_doub_bayer<<<grid, blk2d, 0, l->stream>>>((const uint16_t *)in->data, in->wd, in->ht, (const uint2 *)c0->data,
-        (const uint2 *)c1->data, c0->wd, c0->ht, (__half *)out->data, out->wd, out->ht, p, P, bd);
+        (const uint2 *)c1->data, c0->wd, c0->ht, (__half *)out->data, out->wd, out->ht, p, P, R, bd);
   }
   else
   k_denoise_doub<<<grid2d(out->wd, out->ht), blk2d, 0, l->stream>>>((const uint16_t *)in->data, in->wd, in->ht, (const uint2 *)c0->data,
-      (const uint2 *)c1->data, c0->wd, c0->ht, (__half *)out->data, out->wd, out->ht, p, P, G);
+      (const uint2 *)c1->data, c0->wd, c0->ht, (__half *)out->data, out->wd, out->ht, p, P, G, R);
   VKB_CHECK_LAUNCH();
   return VKB_OK;
 }

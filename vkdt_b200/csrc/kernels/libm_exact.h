@@ -324,10 +324,12 @@ template <class TAB> LME_FN float lme_expf_t(float x, const TAB tab)
 // over / underflow test of the general case is dead
 // POSX: the caller guarantees a positive, normal, finite x and a finite non zero y: no special case is left in front of the
 // logarithm; together with SMALLY (here: |y log2 x| < 126 checked by the caller for its range of x) nothing can call
-template <bool SMALLY, bool POSX, class TAB> LME_FN float lme_powf_ttt(float x, float y, const TAB tab)
+// POSX == 2: x is +0, positive normal, +inf or nan (an image value that cannot be negative or subnormal, e.g. a non negative
+// combination of f16 texels) and y is positive and finite: the three special values are answered by selects, nothing calls
+template <bool SMALLY, int POSX, class TAB> LME_FN float lme_powf_ttt(float x, float y, const TAB tab)
 {
   const uint32_t ix = LME_F2U(x), iy = LME_F2U(y);
-  int rare = POSX ? 0 : ((ix - 0x00800000u >= 0x7f000000u) || (2 * iy - 1 >= 2u * 0x7f800000u - 1));
+  int rare = POSX == 1 ? 0 : ((ix - 0x00800000u >= 0x7f000000u) || (POSX == 0 && (2 * iy - 1 >= 2u * 0x7f800000u - 1)));
   const uint32_t ixs = rare ? 0x3f800000u : ix;
   const uint32_t tmp = ixs - 0x3f330000u;
   const int i = (tmp >> 19) & 15;
@@ -359,6 +361,7 @@ template <bool SMALLY, bool POSX, class TAB> LME_FN float lme_powf_ttt(float x, 
   double res = LME_FMA(LME_K(EXP2_C2), rr, 1.0);
   res = LME_FMA(zz, rr2, res);
   const float out = LME_D2F(LME_MUL(res, sc));
+  if(POSX == 2) return (ix << 1) == 0 ? 0.0f : (ix >= 0x7f800000u ? x + x : out);   // +-0 -> +0 (y is no odd integer), +inf -> +inf, nan -> nan
   if(rare)
   {
     if(ix == 0 && iy - 1u < 0x7f7fffffu) return 0.0f;   // +0 ^ (positive finite y)
@@ -366,7 +369,7 @@ template <bool SMALLY, bool POSX, class TAB> LME_FN float lme_powf_ttt(float x, 
   }
   return out;
 }
-template <bool SMALLY, class TAB> LME_FN float lme_powf_tt(float x, float y, const TAB tab) { return lme_powf_ttt<SMALLY, false>(x, y, tab); }
+template <bool SMALLY, class TAB> LME_FN float lme_powf_tt(float x, float y, const TAB tab) { return lme_powf_ttt<SMALLY, 0>(x, y, tab); }
 template <class TAB> LME_FN float lme_powf_t(float x, float y, const TAB tab) { return lme_powf_tt<false>(x, y, tab); }
 // tables in global memory (L1 resident)
 struct lme_gtab_t
@@ -377,7 +380,8 @@ struct lme_gtab_t
 LME_FN float lme_expf(float x) { return lme_expf_t(x, lme_gtab_t()); }
 LME_FN float lme_powf(float x, float y) { return lme_powf_t(x, y, lme_gtab_t()); }
 LME_FN float lme_powf_smally(float x, float y) { return lme_powf_tt<true>(x, y, lme_gtab_t()); }
-LME_FN float lme_powf_safe(float x, float y) { return lme_powf_ttt<true, true>(x, y, lme_gtab_t()); }
+LME_FN float lme_powf_safe(float x, float y) { return lme_powf_ttt<true, 1>(x, y, lme_gtab_t()); }
+LME_FN float lme_powf_nonneg(float x, float y) { return lme_powf_ttt<true, 2>(x, y, lme_gtab_t()); }
 #if defined(__CUDACC__)
 // tables in shared memory: `base` is the 32 bit shared address of a filled lme_smem_t, kept in one register
 struct lme_stab_t
