@@ -18,7 +18,8 @@ struct llap_params_t { float sigma, shadows, hilights, clarity; };
 // everything below `grade` is a function of the launch's parameters only and is evaluated once on the host with the same
 // fp32 operations the kernel used to repeat per pixel (1/(2 sigma), 1/(2 sigma^2/3); grade: lift, 1 - lift, gain, offset, 1/gamma)
 struct llap_rd_t { double rd2s, rdk; };   // 1 / (2 sigma), 1 / (2 sigma^2 / 3) for div_rd (strict)
-struct llapfin_t { llap_rd_t rd; llap_params_t p; int first; int have_grade; int out_f32; grade_params_t grade;
+struct llapfin_t { llap_rd_t rd; double rdg[NUM_GAMMA];   // rdg[i] = 1 / (gamma[i] - gamma[i - 1]): the blend weight's quotient (strict)
+                   llap_params_t p; int first; int have_grade; int out_f32; grade_params_t grade;
                    float inv2s, invd; float g_lift[3], g_oml[3], g_gain[3], g_off[3], g_ig[3]; };
 
 VKB_DEV float gamma_from_i(int i) { return div_c((float)i, NUM_GAMMA - 1.0f); }
@@ -164,9 +165,12 @@ VKB_DEV void expand4_exact(const float (*T)[F3_W + 1], int lx, int ly, float *t)
 // grade/main.comp:21-40 (mode 0) on the host-evaluated constants of llapfin_t: same operations, same order as grade_px()
 // (the other grading modes stay out of line: inlined, their quotients, logarithms and powers cost the default path registers)
 static __device__ __noinline__ f3 grade_px_other(f3 c, const grade_params_t &g) { return grade_px(c, g); }
+// PLAIN: mode 0 with gamma 1 in every channel (the default parameters, checked by the launcher): no power, no other mode, and
+// therefore no out of line call in the kernel
+template <bool PLAIN>
 VKB_DEV f3 grade_px_digest(f3 c, const llapfin_t &P)
 {
-  if(P.grade.mode != 0) return grade_px_other(c, P.grade);
+  if(!PLAIN && P.grade.mode != 0) return grade_px_other(c, P.grade);
   float v[3] = { c.x, c.y, c.z };
 #pragma unroll
   for(int k = 0; k < 3; k++)
@@ -174,13 +178,14 @@ VKB_DEV f3 grade_px_digest(f3 c, const llapfin_t &P)
     float t = P.g_gain[k] * v[k];
     t = t * P.g_oml[k] + P.g_lift[k];
     t = fmaxf(t, 0.0f);
-    t = (P.g_ig[k] == 1.0f) ? t : PW_POW(t, P.g_ig[k]);
+    if(!PLAIN) t = (P.g_ig[k] == 1.0f) ? t : PW_POW(t, P.g_ig[k]);
     v[k] = t + P.g_off[k];
   }
   return { v[0], v[1], v[2] };
 }
 
-template <bool F32, bool GRADE>
+// GRADE: 0 no grade module behind llap, 1 grade with its default shape (mode 0, gamma 1: grade_px_digest<true>), 2 any grade
+template <bool F32, int GRADE>
 __global__ void __launch_bounds__(256, 4) k_llap_final4(const uint2 *__restrict__ in, const __half *__restrict__ coarse,
     const __half *__restrict__ l1, int cw, int ch, void *__restrict__ outv, int ow, int oh, const __grid_constant__ llapfin_t P, const band_t bd)
 {
@@ -190,10 +195,6 @@ __global__ void __launch_bounds__(256, 4) k_llap_final4(const uint2 *__restrict_
   const int tid = threadIdx.y * 32 + threadIdx.x;
   if(tid == 0) { s_pmin = NUM_GAMMA; s_pmax = 0; }
   if(tid < NUM_GAMMA) s_gamma[tid] = gamma_from_i(tid);
-#if !VKB_FAST
-  __shared__ double s_rdg[NUM_GAMMA];  // 1 / (gamma[i] - gamma[i - 1]): the blend weight's quotient through div_rd
-  if(tid > 32 && tid < 32 + NUM_GAMMA) s_rdg[tid - 32] = rcp_d(gamma_from_i(tid - 32) - gamma_from_i(tid - 33));
-#endif
   LME_SMEM_STAGE(tid);
   const int kx = blockIdx.x * 32 + threadIdx.x, ky = BAND_BY * 8 + threadIdx.y;
   const int cx0 = blockIdx.x * 32 - 2, cy0 = BAND_BY * 8 - 2;
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(256, 4) k_llap_final4(const uint2 *__restrict_
     f3 c = { fmaxf(0.0f, px[q].x * ratio), fmaxf(0.0f, px[q].y * ratio), fmaxf(0.0f, px[q].z * ratio) };
 #else
     // assemble.comp:66-87 and colour.comp:23-35 operation for operation
-    const float a = clampf(div_rd(v[q] - glo, s_rdg[hi[q]]), 0.0f, 1.0f);
+    const float a = clampf(div_rd(v[q] - glo, P.rdg[hi[q]]), 0.0f, 1.0f);
     const float lap0 = f16r(llap_curve_x(grey[q], glo, P.p, P.rd, lme_ctx)) - e0[q];
     const float lap1 = f16r(llap_curve_x(grey[q], ghi, P.p, P.rd, lme_ctx)) - e1[q];
     float l = f16r(res[q] + lap0 * (1.0f - a) + lap1 * a);
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(256, 4) k_llap_final4(const uint2 *__restrict_
     if(GRADE)
     {
       c = { f16r(c.x), f16r(c.y), f16r(c.z) };
-      c = grade_px_digest(c, P);
+      c = GRADE == 1 ? grade_px_digest<true>(c, P) : grade_px_digest<false>(c, P);
     }
     if(F32 && P.out_f32 == 2) { oc[3 * (q & 1)] = c.x; oc[3 * (q & 1) + 1] = c.y; oc[3 * (q & 1) + 2] = c.z; }
     else if(F32) st_sink_f32(outv, ow, x, y, c.x, c.y, c.z, P.out_f32);
@@ -349,6 +350,13 @@ static int launch_llapfin2(const vkb_launch_t *l)
     const volatile float ss = two_s * P.p.sigma;
     const volatile float k = ss / 3.0f;
     P.rd.rd2s = 1.0 / (double)two_s; P.rd.rdk = 1.0 / (double)k;
+    P.rdg[0] = 0.0;
+    for(int i = 1; i < NUM_GAMMA; i++)
+    { // gamma_from_i() in fp32: i / 9
+      const volatile float g1 = (float)i / (NUM_GAMMA - 1.0f), g0 = (float)(i - 1) / (NUM_GAMMA - 1.0f);
+      const volatile float d = g1 - g0;
+      P.rdg[i] = 1.0 / (double)d;
+    }
   }
   if(P.have_grade)
   {
@@ -369,8 +377,9 @@ static int launch_llapfin2(const vkb_launch_t *l)
   if(!grid.y) return VKB_OK;
 #define GO(F, G) k_llap_final4<F, G><<<grid, block, 0, l->stream>>>((const uint2 *)in->data, (const __half *)coarse->data, \
       (const __half *)l1->data, l1->wd, l1->ht, out->data, out->wd, out->ht, P, bd)
-  if(P.out_f32) { if(P.have_grade) GO(true, true); else GO(true, false); }
-  else          { if(P.have_grade) GO(false, true); else GO(false, false); }
+  const bool plain = P.have_grade && P.grade.mode == 0 && P.g_ig[0] == 1.0f && P.g_ig[1] == 1.0f && P.g_ig[2] == 1.0f;
+  if(P.out_f32) { if(plain) GO(true, 1); else if(P.have_grade) GO(true, 2); else GO(true, 0); }
+  else          { if(plain) GO(false, 1); else if(P.have_grade) GO(false, 2); else GO(false, 0); }
 #undef GO
   VKB_CHECK_LAUNCH();
   return VKB_OK;
