@@ -37,14 +37,14 @@ __global__ void __launch_bounds__(256, 5) k_demosaic_gauss(const __half *__restr
   {
     if(xtrans ? (((j + i) & 1) == 1) : (((j + i) & 1) != 1)) continue;
     const float p = ld_h(orig, iw, xi[i - lo], yi[j - lo]);
-    const f2 L = pk2(p, 1.0f / p);
+    const f2 L = pk2(p, div_g(1.0f, p));
     px[4 * (j - lo) + (i - lo)] = L;
     MX = add2(MX, mul2(pk2((float)i, (float)i), L));
     MY = add2(MY, mul2(pk2((float)j, (float)j), L));
     SM = add2(SM, L);
   }
   const float smw = lo2(SM), smb = hi2(SM);
-  const float mwx = lo2(MX) / smw, mwy = lo2(MY) / smw, mbx = hi2(MX) / smb, mby = hi2(MY) / smb;
+  const float mwx = div_g(lo2(MX), smw), mwy = div_g(lo2(MY), smw), mbx = div_g(hi2(MX), smb), mby = div_g(hi2(MY), smb);
   float Sw0 = 0, Sw1 = 0, Sw2 = 0, Sw3 = 0, Sb0 = 0, Sb1 = 0, Sb2 = 0, Sb3 = 0;
   f2 SS = pk2(0.0f, 0.0f);
 #pragma unroll
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256, 5) k_demosaic_gauss(const __half *__restr
     if(xtrans ? (((j + i) & 1) == 1) : (((j + i) & 1) != 1)) continue;
     const float p = lo2(px[4 * (j - lo) + (i - lo)]);
     const float p2 = p * p;
-    const f2 Q = pk2(p2, 1.0f / p2);
+    const f2 Q = pk2(p2, div_g(1.0f, p2));
     const f2 P0 = pk2((float)i - mwx, (float)i - mbx), P1 = pk2((float)j - mwy, (float)j - mby);
     const f2 T0 = mul2(Q, P0), T1 = mul2(Q, P1);
     const f2 A = mul2(T0, P0), B = mul2(T0, P1), C = mul2(T1, P0), D = mul2(T1, P1);
@@ -64,8 +64,8 @@ __global__ void __launch_bounds__(256, 5) k_demosaic_gauss(const __half *__restr
     SS = add2(SS, Q);
   }
   const float sw = lo2(SS), sb = hi2(SS);
-  Sw0 /= sw; Sw1 /= sw; Sw2 /= sw; Sw3 /= sw;
-  Sb0 /= sb; Sb1 /= sb; Sb2 /= sb; Sb3 /= sb;
+  Sw0 = div_g(Sw0, sw); Sw1 = div_g(Sw1, sw); Sw2 = div_g(Sw2, sw); Sw3 = div_g(Sw3, sw);
+  Sb0 = div_g(Sb0, sb); Sb1 = div_g(Sb1, sb); Sb2 = div_g(Sb2, sb); Sb3 = div_g(Sb3, sb);
   const bool usew = (Sw0 * Sw3 - Sw1 * Sw2) < (Sb0 * Sb3 - Sb1 * Sb2);
   float e0, e1, v0x, v0y, v1x, v1y;
   evd2x2(usew ? Sw0 : Sb0, usew ? Sw2 : Sb2, usew ? Sw3 : Sb3, e0, e1, v0x, v0y, v1x, v1y);

@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256, 5) k_denoise_downcov(const uint2 *__restr
     const float4 v = ld_rgba(in, w, mirrori(tx0 + c, w), mirrori(ty0 + r, h));
     const float l = lum2020(v.x, v.y, v.z), l2 = l * l;
     tile[r][c] = make_float4(v.x, v.y, v.z, div_c(l, 25.0f));
-    tinv[r][c] = make_float4(l, 1.0f / l, l2, 1.0f / l2);
+    tinv[r][c] = make_float4(l, div_g(1.0f, l), l2, div_g(1.0f, l2));
   }
   __syncthreads();
   const int x = blockIdx.x * 32 + threadIdx.x, y = BAND_BY * 8 + threadIdx.y;
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256, 5) k_denoise_downcov(const uint2 *__restr
     }
   }
   const float smw = lo2(SM), smb = hi2(SM);
-  const float mwx = lo2(MX) / smw, mwy = lo2(MY) / smw, mbx = hi2(MX) / smb, mby = hi2(MY) / smb;
+  const float mwx = div_g(lo2(MX), smw), mwy = div_g(lo2(MY), smw), mbx = div_g(hi2(MX), smb), mby = div_g(hi2(MY), smb);
   // the products run packed; the sums of products stay scalar: ptxas contracts a packed multiply into a following packed
   // add (FFMA2) whatever --fmad says, and a fused sum would not round like the restatement's
   f2 SS = pk2(0.0f, 0.0f);
@@ -145,8 +145,8 @@ __global__ void __launch_bounds__(256, 5) k_denoise_downcov(const uint2 *__restr
     }
   }
   const float sw = lo2(SS), sb = hi2(SS);
-  Sw0 /= sw; Sw1 /= sw; Sw2 /= sw; Sw3 /= sw;
-  Sb0 /= sb; Sb1 /= sb; Sb2 /= sb; Sb3 /= sb;
+  Sw0 = div_g(Sw0, sw); Sw1 = div_g(Sw1, sw); Sw2 = div_g(Sw2, sw); Sw3 = div_g(Sw3, sw);
+  Sb0 = div_g(Sb0, sb); Sb1 = div_g(Sb1, sb); Sb2 = div_g(Sb2, sb); Sb3 = div_g(Sb3, sb);
   const bool usew = (Sw0 * Sw3 - Sw1 * Sw2) < (Sb0 * Sb3 - Sb1 * Sb2);
   float e0, e1, v0x, v0y, v1x, v1y;
   evd2x2(usew ? Sw0 : Sb0, usew ? Sw2 : Sb2, usew ? Sw3 : Sb3, e0, e1, v0x, v0y, v1x, v1y);
