@@ -69,6 +69,13 @@ int main(int argc, char **argv)
       if(fabsf(ys[j]) <= 0.84f && !same(lme_powf_smally(x, ys[j]), powf(x, ys[j]))) b++;
       // +0, positive normal, (+inf, nan: below) and |y log2 x| < 120, positive y: the variant that answers the specials by selects
       if((u == 0 || u >= 0x00800000u) && ys[j] > 0.0f && (u == 0 || fabs((double)ys[j] * log2((double)x)) < 120.0) && !same(lme_powf_nonneg(x, ys[j]), powf(x, ys[j]))) b++;
+      // +0 or positive normal x <= 1, positive y of any size: the variant that also answers underflow in line (denoise's test^16)
+      if((u == 0 || u >= 0x00800000u) && u <= 0x3f800000u && ys[j] > 0.0f)
+      {
+        if(!same(lme_powf_nonneg_le1(x, ys[j]), powf(x, ys[j]))) b++;
+        if(!same(lme_powf_nonneg_le1(x, 16.0f), powf(x, 16.0f))) b++;
+        if(!same(lme_powf_nonneg_le1(x, 40.0f), powf(x, 40.0f))) b++;
+      }
       // positive normal x, |y log2 x| < 120: the variant without any special case (the default tone curve's power)
       if(u >= 0x00800000u && fabs((double)ys[j] * log2((double)x)) < 120.0 && !same(lme_powf_safe(x, ys[j]), powf(x, ys[j]))) b++;
     }

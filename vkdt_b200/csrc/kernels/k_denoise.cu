@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(256, 5) k_denoise_assemble(const uint2 *__rest
 #if VKB_FAST
   test = test * test; test = test * test; test = test * test; test = test * test; // pow(test, 16)
 #else
-  test = m_pow(test, 16.0f);
+  test = m_pow_nn_le1(test, 16.0f);   // test in [0, 1], a multiple of 2^-24 (or nan): no out of line call
 #endif
   test = clampf(1.5f * test, 0.0f, 1.0f);
 #pragma unroll

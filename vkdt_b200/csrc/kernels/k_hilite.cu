@@ -73,13 +73,13 @@ __global__ void __launch_bounds__(256) k_hilite_reduce(const uint2 *__restrict__
       const float rw = rgb.x * wbr, gw = rgb.y * wbg, bw = rgb.z * wbb;
       const float cmax = fmaxf(rw, fmaxf(gw, bw));
       const float cmin = fminf(rw, fminf(gw, bw));
-      const float sat = (cmax - cmin) / fmaxf(1e-3f, cmax);
-      const float s = smoothstepf(0.2f, 1.0f, fmaxf(rgb.x, fmaxf(rgb.y, rgb.z)) / white);
+      const float sat = div_g(cmax - cmin, fmaxf(1e-3f, cmax));
+      const float s = smoothstepf(0.2f, 1.0f, div_g(fmaxf(rgb.x, fmaxf(rgb.y, rgb.z)), white));
       float tt = smoothstepf(0.15f, 0.9f, sat);
       tt = clampf(5.0f * ds * ds * s * tt, 0.0f, 1.0f);
-      m.x = mixf(rgb.x, (cmax + cmin) / wbr * .5f, tt);
-      m.y = mixf(rgb.y, (cmax + cmin) / wbg * .5f, tt);
-      m.z = mixf(rgb.z, (cmax + cmin) / wbb * .5f, tt);
+      m.x = mixf(rgb.x, div_g(cmax + cmin, wbr) * .5f, tt);
+      m.y = mixf(rgb.y, div_g(cmax + cmin, wbg) * .5f, tt);
+      m.z = mixf(rgb.z, div_g(cmax + cmin, wbb) * .5f, tt);
     }
     tile[r][HR_COL(c)] = m;
     okay[r][HR_COL(c)] = ok ? 1.0f : 0.0f;
@@ -108,8 +108,8 @@ __global__ void __launch_bounds__(256) k_hilite_reduce(const uint2 *__restrict__
     }
   float4 o;
   if(wgt == 0.0f) { o.x = o.y = o.z = 1.0f; }
-  else { o.x = cr / wgt; o.y = cg / wgt; o.z = cb / wgt; }
-  o.w = sqrtf(ex * ex + ey * ey);
+  else { o.x = div_g(cr, wgt); o.y = div_g(cg, wgt); o.z = div_g(cb, wgt); }
+  o.w = sqrt_g(ex * ex + ey * ey);
   st_rgba(out, ow, x, y, o);
 }
 
@@ -151,11 +151,11 @@ __global__ void __launch_bounds__(256) k_hilite_assemble(const uint2 *__restrict
   const float wr = m_exp(ur - fmaxf(ug, ub));
   const float wg = m_exp(ug - fmaxf(ur, ub));
   const float wb = m_exp(ub - fmaxf(ur, ug));
-  const float scale = (sr * wr + sg * wg + sb * wb) / (wr + wg + wb);
+  const float scale = div_g(sr * wr + sg * wg + sb * wb, wr + wg + wb);
   float t = p.soft;
   if(fine.x >= white || fine.y >= white || fine.z >= white) t = 1.0f;
   if(isnan(fine.w)) fine.w = 0.0f;
-  t = clampf(mixf(t, 1.0f, sqrtf(fmaxf(0.0f, fine.w))), 0.0f, 1.0f);
+  t = clampf(mixf(t, 1.0f, sqrt_g(fmaxf(0.0f, fine.w))), 0.0f, 1.0f);
   float4 o;
   o.x = mixf(fine.x, clampf(ur * scale, -65535.0f, 65535.0f), t);
   o.y = mixf(fine.y, clampf(ug * scale, -65535.0f, 65535.0f), t);
@@ -183,13 +183,13 @@ __global__ void __launch_bounds__(256) k_hilite_doub(const __half *__restrict__ 
       for(int j = 0; j < 3; j++) c[3 * i + j] = ld_h_clamp(in, iw, ih, 3 * x + i, 3 * y + j);
     const float minr = fminf(c[1], c[7]), minb = fminf(c[3], c[5]);
     const float ming = fminf(fminf(fminf(c[0], c[2]), c[4]), fminf(c[6], c[8]));
-    const float sr = minr / fmaxf(0.001f, upsm.x);
-    const float sg = ming / fmaxf(0.001f, upsm.y);
-    const float sb = minb / fmaxf(0.001f, upsm.z);
+    const float sr = div_g(minr, fmaxf(0.001f, upsm.x));
+    const float sg = div_g(ming, fmaxf(0.001f, upsm.y));
+    const float sb = div_g(minb, fmaxf(0.001f, upsm.z));
     const float wr = m_exp(upsm.x - fmaxf(upsm.y, upsm.z));
     const float wg = m_exp(upsm.y - fmaxf(upsm.x, upsm.z));
     const float wb = m_exp(upsm.z - fmaxf(upsm.x, upsm.y));
-    const float scale = (sr * wr + sg * wg + sb * wb) / (wr + wg + wb);
+    const float scale = div_g(sr * wr + sg * wg + sb * wb, wr + wg + wb);
     const float maxr = fmaxf(c[1], c[7]), maxb = fmaxf(c[3], c[5]);
     const float maxg = fmaxf(fmaxf(fmaxf(c[0], c[2]), c[4]), fmaxf(c[6], c[8]));
     const float maxrgb = fmaxf(maxr, fmaxf(maxg, maxb));
@@ -214,13 +214,13 @@ __global__ void __launch_bounds__(256) k_hilite_doub(const __half *__restrict__ 
     const int x0 = mirror1(2 * x, iw), x1 = mirror1(2 * x + 1, iw), y0 = mirror1(2 * y, ih), y1 = mirror1(2 * y + 1, ih);
     float c[4] = { ld_h(in, iw, x0, y1), ld_h(in, iw, x1, y1), ld_h(in, iw, x1, y0), ld_h(in, iw, x0, y0) };
     const float ming = fminf(c[0], c[2]);
-    const float sr = c[3] / fmaxf(0.001f, upsm.x);
-    const float sg = ming / fmaxf(0.001f, upsm.y);
-    const float sb = c[1] / fmaxf(0.001f, upsm.z);
+    const float sr = div_g(c[3], fmaxf(0.001f, upsm.x));
+    const float sg = div_g(ming, fmaxf(0.001f, upsm.y));
+    const float sb = div_g(c[1], fmaxf(0.001f, upsm.z));
     const float wr = m_exp(upsm.x - fmaxf(upsm.y, upsm.z));
     const float wg = m_exp(upsm.y - fmaxf(upsm.x, upsm.z));
     const float wb = m_exp(upsm.z - fmaxf(upsm.x, upsm.y));
-    const float scale = (sr * wr + sg * wg + sb * wb) / (wr + wg + wb);
+    const float scale = div_g(sr * wr + sg * wg + sb * wb, wr + wg + wb);
     const float maxrgb = fmaxf(fmaxf(c[0], c[1]), fmaxf(c[2], c[3]));
     if(maxrgb > softw)
     {

@@ -348,11 +348,17 @@ template <bool SMALLY, int POSX, class TAB> LME_FN float lme_powf_ttt(float x, f
   q = LME_FMA(p, r2, q);
   const double logx = LME_FMA(yy, r4, q);
   const double ylogx = LME_MUL((double)y, logx);
-  if(!SMALLY) rare = rare || (((uint32_t)(LME_D2U(ylogx) >> 47) & 0xffffu) >= 0x80bfu);
-  double kd = LME_ADD(ylogx, LME_SHIFT_SCALED);
+  double ylogx_c = ylogx;
+  if(!SMALLY && POSX == 2)
+  { // underflow answered in line: at y log2 x <= -150 libm returns +0, and so does the formula from -150 down (2^-151 rounds to
+    // zero); the clamp keeps the exponent arithmetic in range.  (the overflow side is the caller's to exclude.)
+    ylogx_c = ylogx < -151.0 ? -151.0 : ylogx;
+  }
+  else if(!SMALLY) rare = rare || (((uint32_t)(LME_D2U(ylogx) >> 47) & 0xffffu) >= 0x80bfu);
+  double kd = LME_ADD(ylogx_c, LME_SHIFT_SCALED);
   const uint64_t ki = LME_D2U(kd);
   kd = LME_ADD(kd, -LME_SHIFT_SCALED);
-  const double rr = LME_ADD(ylogx, -kd);
+  const double rr = LME_ADD(ylogx_c, -kd);
   uint64_t t = tab.exp2(ki);
   t += ki << 47;
   const double sc = LME_U2D(t);
@@ -382,6 +388,7 @@ LME_FN float lme_powf(float x, float y) { return lme_powf_t(x, y, lme_gtab_t());
 LME_FN float lme_powf_smally(float x, float y) { return lme_powf_tt<true>(x, y, lme_gtab_t()); }
 LME_FN float lme_powf_safe(float x, float y) { return lme_powf_ttt<true, 1>(x, y, lme_gtab_t()); }
 LME_FN float lme_powf_nonneg(float x, float y) { return lme_powf_ttt<true, 2>(x, y, lme_gtab_t()); }
+LME_FN float lme_powf_nonneg_le1(float x, float y) { return lme_powf_ttt<false, 2>(x, y, lme_gtab_t()); }   // x <= 1: may underflow, cannot overflow
 #if defined(__CUDACC__)
 // tables in shared memory: `base` is the 32 bit shared address of a filled lme_smem_t, kept in one register
 struct lme_stab_t
