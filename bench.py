@@ -586,6 +586,18 @@ def main():
                         "roofline": {"bound": "hbm", "kernel": ftop_label, "achieved": round(ftop_bytes / (ftop_ms * 1e-3) / 1e9, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
                                      "frac": round(ftop_bytes / (ftop_ms * 1e-3) / 1e9 / pk["hbm_gbs"], 4), "algorithmic_bytes_per_launch": ftop_bytes, "avg_launch_ms": round(ftop_ms, 4)},
                         "kernels": {k: round(v[0] / v[1], 4) for k, v in sorted(F["per_kernel"].items(), key=lambda kv: -kv[1][0])[:8]}}
+    # BASELINE.json north_star: ">= 60 % of the HBM roofline on the fused pointwise chain" (crop + colour + filmcurv in one launch:
+    # 8 B/px in, 8 B/px out): both builds, live CUDA events of this run
+    def pointwise_roof(per_kernel):
+        for k, v in per_kernel.items():
+            if "b200_pointw" in k and v[1] > 0:
+                ms = v[0] / v[1]
+                gbs = v[2] / (ms * 1e-3) / 1e9
+                return {"kernel": k, "avg_launch_ms": round(ms, 4), "algorithmic_bytes_per_launch": v[2], "achieved": round(gbs, 1), "unit": "GB/s",
+                        "peak": pk["hbm_gbs"], "frac": round(gbs / pk["hbm_gbs"], 4)}
+        return None
+    line["pointwise_chain"] = {("fast" if args.mode == "fast" else "strict"): pointwise_roof(per_kernel), other_name: pointwise_roof(F["per_kernel"]),
+                               "target": "frac >= 0.6 (north_star); the strict build pays for libm-exact pow / exp in its tone curve, the fast build is the HBM-bound form"}
     if Bd:
         line["bands"] = Bd
     if M:
