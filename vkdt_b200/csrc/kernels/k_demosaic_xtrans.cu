@@ -12,7 +12,7 @@ VKB_DEV float xt_weight(float e0, float e1, float cz, float cw, int i, int j, fl
 { // splat.comp:33-37 (lo = 1e-4), fix.comp:16-23 (lo = 1e-3)
   const float of0 = cz * (float)i + cw * (float)j;
   const float of1 = -cw * (float)i + cz * (float)j;
-  return clampf(m_exp(-0.5f * (of0 / e0 * of0 + of1 / e1 * of1)), lo, 1.0f);
+  return clampf(m_exp(-0.5f * (div_f(of0, e0) * of0 + div_f(of1, e1) * of1)), lo, 1.0f);   // the eigenvalues are clamped: div_f
 }
 // the 13 distinct weights of a 5x5 window: index (j+2)*5 + (i+2), mirrored index 24 - idx
 #define XT_WEIGHTS(W, E0, E1, CZ, CW, LO) \
@@ -38,7 +38,7 @@ VKB_DEV float xt_splat_px(const __half *__restrict__ in, int w, int h, const uin
     if(i == 0 && j == 0) weight = 666.0f;
     g += col * weight; wg += weight;
   }
-  return g / fmaxf(1e-8f, wg);
+  return div_f(g, fmaxf(1e-8f, wg));
 }
 
 __global__ void __launch_bounds__(128, 8) k_xtrans_splat(const __half *__restrict__ in, int w, int h,
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(128, 8) k_xtrans_splat(const __half *__restric
           const float weight = (i == 0 && j == 0) ? 666.0f : wt[(j + 2) * 5 + i + 2];
           g += m[v][u] * weight; wg += weight;
         }
-      out[(size_t)(y0 + dy) * w + x0 + dx] = __float2half_rn(g / fmaxf(1e-8f, wg));
+      out[(size_t)(y0 + dy) * w + x0 + dx] = __float2half_rn(div_f(g, fmaxf(1e-8f, wg)));
     }
 }
 
@@ -99,11 +99,11 @@ VKB_DEV float4 xt_fix_px(const __half *__restrict__ in, const __half *__restrict
     const float gh_ = ld_h_mirror(green, w, h, px, py);
     const float col = ld_h_mirror(in, w, h, px, py);
     const float weight = xt_weight(3.0f * cov.x, 3.0f * cov.y, cov.z, cov.w, i, j, 1e-3f);
-    const float corr = (1e-4f + gc) / (1e-4f + gh_);
+    const float corr = div_f(1e-4f + gc, 1e-4f + gh_);   // 1e-4f + an f16 value is never zero
     rgb[c] += col * corr * weight;
     wt[c] += weight;
   }
-  return make_float4(rgb[0] / fmaxf(1e-8f, wt[0]), rgb[1] / fmaxf(1e-8f, wt[1]), rgb[2] / fmaxf(1e-8f, wt[2]), 1.0f);
+  return make_float4(div_f(rgb[0], fmaxf(1e-8f, wt[0])), div_f(rgb[1], fmaxf(1e-8f, wt[1])), div_f(rgb[2], fmaxf(1e-8f, wt[2])), 1.0f);
 }
 
 __global__ void __launch_bounds__(128, 6) k_xtrans_fix(const __half *__restrict__ in, const __half *__restrict__ green, int w, int h,
@@ -155,11 +155,11 @@ __global__ void __launch_bounds__(128, 6) k_xtrans_fix(const __half *__restrict_
           if(((u % 3 + v % 3) & 1) == 0) continue;
           const bool base_blue = (((u / 3 + v / 3) & 1) != 0) != (v % 3 == 1);
           const float weight = wt[(j + 2) * 5 + i + 2];
-          const float corr = (1e-4f + gc) / (1e-4f + g[v][u]);
+          const float corr = div_f(1e-4f + gc, 1e-4f + g[v][u]);
           if(base_blue) { a2 += m[v][u] * corr * weight; w2 += weight; }
           else          { a0 += m[v][u] * corr * weight; w0 += weight; }
         }
-      const float r0 = a0 / fmaxf(1e-8f, w0), r2 = a2 / fmaxf(1e-8f, w2);
+      const float r0 = div_f(a0, fmaxf(1e-8f, w0)), r2 = div_f(a2, fmaxf(1e-8f, w2));
       // a 5x5 window always holds green sites: rgb[1] = gc, w[1] = 1
       st_rgba(out, w, x0 + dx, y0 + dy, make_float4(swap ? r2 : r0, gc / fmaxf(1e-8f, 1.0f), swap ? r0 : r2, 1.0f));
     }

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) k_denoise_half(const uint16_t *__restrict
     const float col0 = (c[1] + c[7]) * 0.5f, col1 = (c[3] + c[5]) * 0.5f;
     if(((x + y + cx + cy) & 1) > 0) { rgba.x = col0; rgba.z = col1; }
     else                            { rgba.z = col0; rgba.x = col1; }
-    rgba.y = (c[0] + c[2] + c[4] + c[6] + c[8]) * 1.0f / 5.0f;
+    rgba.y = div_c((c[0] + c[2] + c[4] + c[6] + c[8]) * 1.0f, 5.0f);
     rgba.w = 1.0f;
   }
   else
@@ -482,7 +482,7 @@ VKB_DEV float doub_shrink(float val, float upsm_c, float down_c, float upw, int 
   {
     black = col == 0 ? P.black[0] : P.black[2]; white = col == 0 ? P.white[0] : P.white[2];
     blendw = 1.0f;
-    if(xt) T /= fmaxf(1e-4f, upw);
+    if(xt) T = div_f(T, fmaxf(1e-4f, upw));
   }
   float sigma[3];
 #if VKB_FAST

@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(256) k_hilite_half(const __half *__restrict__ 
     const float col0 = (c[1] + c[7]) * 0.5f, col1 = (c[3] + c[5]) * .5f;
     if(((x + y) & 1) > 0) { rgba.x = col0; rgba.z = col1; }
     else                  { rgba.z = col0; rgba.x = col1; }
-    rgba.y = (c[0] + c[2] + c[4] + c[6] + c[8]) / 5.0f;
+    rgba.y = div_c(c[0] + c[2] + c[4] + c[6] + c[8], 5.0f);
     rgba.w = 1.0f;
   }
   else
