@@ -527,6 +527,16 @@ __global__ void __launch_bounds__(256) k_denoise_doub(const uint16_t *__restrict
     bx = (x >> 1) - ((x & 1) ? 0 : 1); ax = (x & 1) ? 0.25f : 0.75f;
     by = (y >> 1) - ((y & 1) ? 0 : 1); ay = (y & 1) ? 0.25f : 0.75f;
   }
+  else if(ow == 3 * cw && oh == 3 * ch)
+  { // x-trans: (x+0.5)/3 - 0.5 = (x-1)/3: texel floor((x-1)/3), fraction 0, 1/3 or 2/3.  the double arithmetic of the general
+    // branch below lands within 1e-12 of those, which rounds to the floats 0x3eaaaaab / 0x3f2aaaab (their neighbours' midpoints
+    // are 5e-9 away); a fraction of 0 +- 1e-13 selects the same texel either way.  no double division per pixel.
+    const int qx = x + 2, qy = y + 2;                      // (x - 1) + 3: non negative
+    const int rx = qx % 3, ry = qy % 3;
+    bx = qx / 3 - 1; by = qy / 3 - 1;
+    ax = rx == 0 ? 0.0f : (rx == 1 ? __uint_as_float(0x3eaaaaabu) : __uint_as_float(0x3f2aaaabu));
+    ay = ry == 0 ? 0.0f : (ry == 1 ? __uint_as_float(0x3eaaaaabu) : __uint_as_float(0x3f2aaaabu));
+  }
   else
   {
     const double ux = ((double)x + 0.5) / (double)ow * (double)cw - 0.5, uy = ((double)y + 0.5) / (double)oh * (double)ch - 0.5;
