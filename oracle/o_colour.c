@@ -125,6 +125,41 @@ void o_colour_commit(const o_colour_params_t *p, float *p_wb, const float *img_w
   else ii[16] = ii[17] = ii[18] = ii[19] = 0;
 }
 
+/* camera gamuts -> xyz (matrices.h:89-112), the fp32 value of every entry; index = primaries 8, 9, 11..16 */
+static const float M_camgamut_to_xyz[8][9] = {
+  /*  8 arriwg3         */ { 0.638007641f, 0.214703858f, 0.09774445f, 0.291953772f, 0.823841035f, -0.115794823f, 0.00279827905f, -0.0670342371f, 1.15329373f },
+  /*  9 arriwg4         */ { 0.704858303f, 0.129760295f, 0.115837313f, 0.254524171f, 0.781477749f, -0.0360019095f, 0.0f, 0.0f, 1.0890578f },
+  /* 11 sonysgamut3     */ { 0.706482708f, 0.128801048f, 0.115172163f, 0.270979673f, 0.786606431f, -0.0575860813f, -0.00967784505f, 0.00460003735f, 1.09413552f },
+  /* 12 sonysgamut3cine */ { 0.5990839f, 0.248925522f, 0.102446489f, 0.215075821f, 0.885068476f, -0.100144319f, -0.0320658498f, -0.0276583899f, 1.14878201f },
+  /* 13 vgamut          */ { 0.679644465f, 0.152211413f, 0.118600048f, 0.260685563f, 0.774894476f, -0.0355800129f, -0.00931019802f, -0.00461246725f, 1.10298038f },
+  /* 14 egamut          */ { 0.705396831f, 0.164041325f, 0.0810177475f, 0.280130714f, 0.820206642f, -0.100337364f, -0.103781514f, -0.0729072541f, 1.26574647f },
+  /* 15 egamut2         */ { 0.736477673f, 0.130739644f, 0.0832385793f, 0.275069982f, 0.828017771f, -0.103087775f, -0.124225155f, -0.0871597677f, 1.3004427f },
+  /* 16 davinciwg       */ { 0.70062238f, 0.148774818f, 0.101058722f, 0.274118513f, 0.873631895f, -0.147750407f, -0.0989629105f, -0.137895331f, 1.32591593f },
+};
+static int camgamut_index(uint32_t prim) { return prim == 8 ? 0 : prim == 9 ? 1 : prim >= 11 && prim <= 16 ? (int)prim - 9 : -1; }
+
+/* camera log curves to scene linear (shared/oetf.glsl:2-38), every operation in fp32 as written there.
+ * glsl's mix(a, b, cond) with a bvec selects: both sides are evaluated, b is taken where cond holds */
+static float decode_log(float x, uint32_t trc)
+{
+  switch(trc)
+  {
+    case 7:  return x > 0.02740668f ? exp2f(x / 0.07329248f - 7.0f) - 0.0075f : x / 10.44426855f;                      /* davinci intermediate */
+    case 8:  return x < 0.075f ? (x - 0.075f) / 16.184376489665897f : expf((x - 0.5520126568606655f) / 0.09232902596577353f) - 0.0057048244042473785f; /* filmlight t-log */
+    case 9:  return x <= 0.155251141552511f ? (x - 0.0729055341958355f) / 10.5402377416545f : exp2f(x * 17.52f - 9.72f);   /* aces cct */
+    case 10: return x < 5.367655f * 0.010591f + 0.092809f ? (x - 0.092809f) / 5.367655f : (powf(10.0f, (x - 0.385537f) / 0.247190f) - 0.052272f) / 5.555556f; /* arri logC3 */
+    case 11: return x < -0.7774983977293537f ? x * 0.3033266726886969f - 0.7774983977293537f
+                  : (exp2f(14.0f * (x - 0.09286412512218964f) / 0.9071358748778103f + 6.0f) - 64.0f) / 2231.8263090676883f;  /* arri logC4 */
+    case 12: return x < 0.0f ? (x / 15.1927f) - 0.01f : (powf(10.0f, x / 0.224282f) - 1.0f) / 155.975327f - 0.01f;       /* red log3G10 */
+    case 13: return x < 0.181f ? (x - 0.125f) / 5.6f : powf(10.0f, (x - 0.598206f) / 0.241514f) - 0.00873f;              /* panasonic v-log */
+    case 14: return x < 171.2102946929f / 1023.0f ? (x * 1023.0f - 95.0f) * 0.01125f / (171.2102946929f - 95.0f)
+                  : powf(10.0f, (x * 1023.0f - 420.0f) / 261.5f) * (0.18f + 0.01f) - 0.01f;                                /* sony s-log3 */
+    case 15: return x < 0.100686685370811f ? (x - 0.092864f) / 8.799461f
+                  : powf(10.0f, (x - 0.384316f) / 0.245281f) / 5.555556f - 0.064829f / 5.555556f;                          /* fuji f-log2 */
+    default: return x;
+  }
+}
+
 /* colour/main-impl.glsl:118-198 */
 static void decode_colour(const float *f, float *rgb)
 {
@@ -156,6 +191,7 @@ static void decode_colour(const float *f, float *rgb)
     for(int k = 0; k < 3; k++) rgb[k] = rgb[k] <= 0.5f ? rgb[k] * rgb[k] / 3.0f : (expf((rgb[k] - c) / a) + b) / 12.0f;
   }
   else if(trc == 6) { for(int k = 0; k < 3; k++) rgb[k] = powf(o_max(rgb[k], 0.0f), 2.2f); }
+  else if(trc >= 7 && trc <= 15) { for(int k = 0; k < 3; k++) rgb[k] = decode_log(rgb[k], trc); }
   if(prim == 0)
   { /* custom matrix, uploaded column major in f[4..15] */
     const float r = f[4] * rgb[0] + f[8]  * rgb[1] + f[12] * rgb[2];
@@ -170,6 +206,14 @@ static void decode_colour(const float *f, float *rgb)
   else if(prim == 6) o_mat3mulv(M_ap0_to_2020, rgb, rgb);
   else if(prim == 7) o_mat3mulv(M_ap1_to_2020, rgb, rgb);
   else if(prim == 10) o_mat3mulv(M_redwg_to_2020, rgb, rgb);
+  else if(camgamut_index(prim) >= 0)
+  { /* main-impl.glsl:179-196: M1 * M0 * rgb, evaluated left to right: the fp32 matrix product first */
+    const float *M0 = M_camgamut_to_xyz[camgamut_index(prim)];
+    float M[9];
+    for(int j = 0; j < 3; j++) for(int i = 0; i < 3; i++)
+      M[3*j+i] = M_xyz_to_2020[3*j+0] * M0[i] + M_xyz_to_2020[3*j+1] * M0[3+i] + M_xyz_to_2020[3*j+2] * M0[6+i];
+    o_mat3mulv(M, rgb, rgb);
+  }
 }
 
 /* colour/main-impl.glsl:49-67.  glsl evaluates M16 * rec2020_to_xyz * v left to right: (M16*R)*v */

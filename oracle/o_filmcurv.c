@@ -1,9 +1,11 @@
 /* ORACLE — test infrastructure only (see o_common.h).
  * CPU restatement of src/pipe/modules/filmcurv/main.comp:18-166, params.glsl:15-34,
  * shared.glsl:371-387 (adjust_colour_dng) and colourspaces.glsl:20-78 (oklab, "hsv").
- * colour mode 2 (munsell LUT) is out of scope: it needs the 840-entry table of shared/munsell.glsl. */
+ * colour mode 2: shared/munsell.glsl:7-137 (hue constancy along munsell hue lines) + colourspaces.glsl:2-19; its table of
+ * chromaticities is data shared with the product (munsell_table.h, made by scripts/make_munsell_table.py). */
 #include "o_common.h"
 #include "vkdt_oracle.h"
+#include "../vkdt_b200/csrc/kernels/munsell_table.h"
 
 static const float M_2020_to_xyz[9] = {0.636958048301290991f, 0.144616903586208406f, 0.168880975164172054f, 0.26270021201126692f, 0.677998071518871148f, 0.0593017164698619384f, 4.9999999999999999e-17f, 0.0280726930490874452f, 1.06098505771079066f};
 static const float M_xyz_to_2020[9] = {1.71665119f, -0.35567078f, -0.25336628f, -0.66668435f, 1.61648124f, 0.01576855f, 0.01763986f, -0.04277061f, 0.94210312f};
@@ -83,6 +85,105 @@ static float hue_bump(float h, float h0, float w)
   const float pi = (float)M_PI;
   const float d = fabsf(glsl_mod(h - h0 + pi, 2.0f * pi) - pi);
   return d < w ? 0.5f + 0.5f * cosf(pi * d / w) : 0.0f;
+}
+
+/* ---- shared/munsell.glsl ---- */
+static const uint32_t munsell_xy[VKB_MUNSELL_HDIM * VKB_MUNSELL_CDIM] = { VKB_MUNSELL_WORDS };
+#define MH VKB_MUNSELL_HDIM
+#define MC VKB_MUNSELL_CDIM
+static const float mun_ill[2] = { 0.31271f, 0.32902f };
+/* :7-16 */
+static float xy_to_monotone_hue_angle(const float *xy)
+{
+  const float pi = (float)M_PI;
+  return glsl_mod(2.0f * pi - 2.52f - atan2f(xy[1] - mun_ill[1], xy[0] - mun_ill[0]), 2.0f * pi);
+}
+/* :19-27 */
+static void munsell_lookup(int hue_idx, int chroma_idx, float *xy)
+{
+  hue_idx = (hue_idx % MH + MH) % MH;
+  chroma_idx = chroma_idx < 0 ? 0 : chroma_idx > MC - 1 ? MC - 1 : chroma_idx;
+  const uint32_t w = munsell_xy[MC * hue_idx + chroma_idx];
+  xy[0] = o_f16_bits_to_f32((uint16_t)(w & 0xffffu));
+  xy[1] = o_f16_bits_to_f32((uint16_t)(w >> 16));
+}
+/* :30-38 */
+static float munsell_side(const float *v0, const float *v1, const float *p)
+{
+  const float ax = v1[0] - v0[0], ay = v1[1] - v0[1], bx = p[0] - v0[0], by = p[1] - v0[1];
+  return ax * by - ay * bx;
+}
+/* :41-62 */
+static void munsell_to_xy(const float *mhc, float *xy)
+{
+  const float hm = mhc[0] * MH, cm = o_max(mhc[1], 0.0f) * MC;
+  const int hidxm = (int)hm, cidxm = (int)cm;
+  const float hu = hm - hidxm, cu = cm - cidxm;
+  float r0[2], r1[2], r2[2], r3[2];
+  munsell_lookup(hidxm, cidxm + 1, r3); munsell_lookup(hidxm + 1, cidxm + 1, r2);
+  munsell_lookup(hidxm, cidxm, r0);     munsell_lookup(hidxm + 1, cidxm, r1);
+  for(int c = 0; c < 2; c++)
+    xy[c] = hu >= cu ? (1 - hu) * r0[c] + (hu - cu) * r1[c] + cu * r2[c]
+                     : hu * r2[c] + (cu - hu) * r3[c] + (1 - cu) * r0[c];
+}
+/* :67-137 */
+static void munsell_from_xy(const float *xy, float *mhc)
+{
+  int hidxm = 0, hidxM = MH, cidxm = 0, cidxM = MC - 1;
+  const float theta = xy_to_monotone_hue_angle(xy);
+  const float dx = xy[0] - mun_ill[0], dy = xy[1] - mun_ill[1];
+  const float rad2 = dx * dx + dy * dy;
+  for(int i = 0; i < 10; i++)
+  {
+    const int hidx = (hidxm + hidxM) / 2, cidx = (cidxm + cidxM) / 2;
+    float res[2];
+    munsell_lookup(hidx, cidx, res);
+    const float th = xy_to_monotone_hue_angle(res);
+    const float ex = res[0] - mun_ill[0], ey = res[1] - mun_ill[1];
+    const float r2 = ex * ex + ey * ey;
+    if(th <= theta) hidxm = hidx; else hidxM = hidx;
+    if(r2 <= rad2)  cidxm = cidx; else cidxM = cidx;
+    if(hidxM <= hidxm + 1 && cidxM <= cidxm + 1) break;
+  }
+  for(int i = 0; i < 10; i++)
+  {
+    float r0[2], r1[2], r2[2], r3[2];
+    munsell_lookup(hidxm, cidxm + 1, r3); munsell_lookup(hidxm + 1, cidxm + 1, r2);
+    munsell_lookup(hidxm, cidxm, r0);     munsell_lookup(hidxm + 1, cidxm, r1);
+    const float s0 = munsell_side(r0, r1, xy), s1 = munsell_side(r1, r2, xy);
+    const float s2 = munsell_side(r2, r3, xy), s3 = munsell_side(r3, r0, xy);
+    /* the indices step before the containment test, and the result below uses the stepped ones, as the shader does */
+    if(s0 < 0 && cidxm > 0) cidxm--;
+    else if(s0 < 0 && cidxm == 0) hidxm = ((hidxm + MH / 2) % MH + MH) % MH;
+    else if(s2 < 0 && cidxm < MC - 2) cidxm++;
+    if(s1 < 0) hidxm++;
+    else if(s3 < 0) hidxm--;
+    if(s0 >= 0 && s1 >= 0 && s3 >= 0 && (s2 >= 0 || cidxm >= MC - 2))
+    {
+      const float t0 = munsell_side(r0, r1, r2), t1 = munsell_side(r2, r3, r0);
+      float u0, u1, u2, u3;
+      if(cidxm > 0 && s0 + s1 <= t0) { u2 = s0 / t0; u0 = s1 / t0; u1 = 1.0f - u0 - u2; u3 = 0.0f; }
+      else                           { u2 = s3 / t1; u0 = s2 / t1; u3 = 1.0f - u0 - u2; u1 = 0.0f; }
+      const float hi = u0 * hidxm + u1 * (hidxm + 1.0f) + u2 * (hidxm + 1.0f) + u3 * hidxm;
+      const float ci = u0 * cidxm + u1 * cidxm + u2 * (cidxm + 1.0f) + u3 * (cidxm + 1.0f);
+      mhc[0] = hi / MH; mhc[1] = o_max(0.0f, ci / MC);
+      return;
+    }
+  }
+  mhc[0] = mhc[1] = 1.0f;
+}
+/* colourspaces.glsl:2-19 */
+static void fc_rec2020_to_xyY(const float *rgb, float *xyY)
+{
+  float xyz[3];
+  o_mat3mulv(M_2020_to_xyz, rgb, xyz);
+  const float s = 1.0f * xyz[0] + 1.0f * xyz[1] + 1.0f * xyz[2];
+  xyY[0] = xyz[0] / s; xyY[1] = xyz[1] / s; xyY[2] = xyz[1];
+}
+static void fc_xyY_to_rec2020(const float *xyY, float *rgb)
+{
+  const float xyz[3] = { xyY[0] * xyY[2] / xyY[1], xyY[1] * xyY[2] / xyY[1], (1.0f - xyY[0] - xyY[1]) * xyY[2] / xyY[1] };
+  o_mat3mulv(M_xyz_to_2020, xyz, rgb);
 }
 
 /* one pixel of filmcurv/main.comp:68-166 */
@@ -176,7 +277,19 @@ void o_filmcurv_px(const float *col_in, float *col1, const o_filmcurv_params_t *
     const float lab1[3] = { L1, C1 * cr * cosf(h), C1 * cr * sinf(h) };
     oklab_to_rec2020(lab1, col1);
   }
-  else { col1[0] = col1[1] = col1[2] = 0.0f; } /* mode 2 (munsell) not restated; glsl would store an undefined col1 */
+  else if(p->colour == 2)
+  { /* :96-104 */
+    for(int c = 0; c < 3; c++) col1[c] = weibull_cdf(col0[c], il, k);
+    float xyY0[3], xyY1[3], m0[2], m1[2];
+    fc_rec2020_to_xyY(col0, xyY0);
+    munsell_from_xy(xyY0, m0);
+    fc_rec2020_to_xyY(col1, xyY1);
+    munsell_from_xy(xyY1, m1);
+    const float mhc[2] = { m0[0], m1[1] };
+    munsell_to_xy(mhc, xyY1);
+    fc_xyY_to_rec2020(xyY1, col1);
+  }
+  else { col1[0] = col1[1] = col1[2] = 0.0f; } /* no such mode; glsl would store an undefined col1 */
 }
 
 void o_filmcurv_main(const oimg_t *in, oimg_t *out, const o_filmcurv_params_t *p, int out_f16)

@@ -579,6 +579,7 @@ VARIANTS = {
                        [("filmcurv.colour", 1), ("filmcurv.light", 1.4), ("filmcurv.contrast", 1.2)]),
     "filmcurv-ucs":   (["param:filmcurv:01:colour:0"], [("filmcurv.colour", 0)]),
     "filmcurv-agx":   (["param:filmcurv:01:colour:4"], [("filmcurv.colour", 4)]),
+    "filmcurv-munsell": (["param:filmcurv:01:colour:2"], [("filmcurv.colour", 2)]),
     "filmcurv-oklab": (["param:filmcurv:01:colour:5", "param:filmcurv:01:bias:0.01"], [("filmcurv.colour", 5), ("filmcurv.bias", 0.01)]),
     "llap-flat":      (["param:llap:01:clarity:0", "param:llap:01:shadows:0.8", "param:llap:01:hilights:1.2"],
                        [("llap.clarity", 0.0), ("llap.shadows", 0.8), ("llap.hilights", 1.2)]),

@@ -201,7 +201,29 @@ def test_colour(gpu, oracle, case):
     assert_f16_close(got[..., :3], want[..., :3], 3 if case == "saturation" else 2, 0.90, "colour " + case)
 
 
-@pytest.mark.parametrize("mode", [0, 1, 3, 4, 5])
+@pytest.mark.parametrize("trc,prim,clip", [(1, 1, 0), (3, 4, 0), (5, 6, 1), (7, 16, 0), (8, 14, 1), (9, 7, 0), (10, 8, 0), (11, 9, 1), (12, 10, 0),
+                                           (13, 13, 0), (14, 11, 1), (14, 12, 0), (15, 15, 0)])
+def test_colour_input_curves_and_gamuts(gpu, oracle, trc, prim, clip):
+    """the input side of colour (main-impl.glsl:104-198): transfer curves 1..6, the camera log curves 7..15 of shared/oetf.glsl,
+    the camera wide gamuts that go through xyz; the clip level runs through the same decode on the host."""
+    O = oracle
+    w, h = 192, 128
+    d = O.darkroom_defaults(w, h)
+    d.colour_primaries, d.colour_trc = prim, trc
+    d.colour.clip, d.colour.clipmax = clip, 0.9
+    f = _colour_committed(O, d)
+    rng = np.random.default_rng(900 + 20 * trc + prim)
+    a = rng.uniform(-0.05, 1.0, (h, w, 4)).astype(np.float16).astype(np.float32)
+    a[1, :, :3] = np.linspace(-0.2, 1.2, w).astype(np.float16).astype(np.float32)[:, None]
+    a[..., 3] = 1.0
+    want, wi = O.new_img(h, w, 4)
+    O.lib().o_colour_main(C.byref(O.img(a)), C.byref(wi), O.fptr(f), 1)
+    d_out = dev_f16(h, w, 4)
+    gpu.dispatch("colour", "main", [gpu.image(to_dev_f16(a), w, h, 4, "f16"), gpu.image(d_out, w, h, 4, "f16")], b"\0" * 12, f.tobytes())
+    assert_f16_close(to_host(d_out)[..., :3], want[..., :3], 2, 0.90, "colour trc %d prim %d" % (trc, prim))
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5])
 def test_filmcurv(gpu, oracle, mode):
     O = oracle
     w, h = 192, 128
@@ -212,7 +234,7 @@ def test_filmcurv(gpu, oracle, mode):
     d_out = dev_f16(h, w, 4)
     gpu.dispatch("filmcurv", "main", [gpu.image(to_dev_f16(a), w, h, 4, "f16"), gpu.image(d_out, w, h, 4, "f16")], b"", bytes(fp))
     got = to_host(d_out)
-    tol = {0: 6, 4: 6, 5: 6}.get(mode, 2)
+    tol = {0: 6, 2: 6, 4: 6, 5: 6}.get(mode, 2)
     assert_close_mixed(got[..., :3], want[..., :3], tol, 4e-6, 0.85, "filmcurv mode %d" % mode)
 
 

@@ -202,7 +202,7 @@ def cases(O):
                 res_s.append(go)
             return res_o, res_s
     # ---- pointwise chain: crop, colour, filmcurv ------------------------------------------------------------------------
-    for mode in (0, 1, 3, 4, 5):                      # 2 (munsell) needs the lookup table input, not restated
+    for mode in (0, 1, 2, 3, 4, 5):
         @add("filmcurv.main mode %d" % mode)
         def _(mode=mode):
             a = rgba(np.random.default_rng(50 + mode), 96, 64, -0.02, 2.0)
@@ -242,6 +242,26 @@ def cases(O):
                 res_o.append(want)
                 res_s.append(got)
             return res_o, res_s
+
+    # input transfer curves (709 .. gamma, then the camera log curves of shared/oetf.glsl) and input gamuts (camera wide gamuts
+    # go through xyz): main-impl.glsl:104-198
+    for trc, prim, clip in ((1, 1, 0), (2, 3, 1), (3, 4, 0), (4, 5, 0), (5, 6, 0), (6, 7, 1), (7, 16, 0), (8, 14, 1), (9, 7, 0), (10, 8, 0), (11, 9, 1),
+                            (12, 10, 0), (13, 13, 0), (14, 11, 1), (14, 12, 0), (15, 15, 0), (8, 2, 0)):
+        @add("colour.main trc %d prim %d" % (trc, prim))
+        def _(trc=trc, prim=prim, clip=clip):
+            rng = np.random.default_rng(600 + 20 * trc + prim)
+            a = rgba(rng, 96, 64, -0.05, 1.0)
+            a[1, :, :3] = f16(np.linspace(-0.2, 1.2, 96))[:, None]     # a ramp across every curve's knee
+            d = O.darkroom_defaults(64, 64)
+            p = d.colour
+            p.exposure, p.sat, p.matrix, p.clip, p.clipmax = 0.0, 1.0, 1, clip, 0.9
+            f, _wb = O.colour_commit_oracle(bytes(p), [1.0, 1.0, 1.0, 1.0], [1, 0, 0, 0, 1, 0, 0, 0, 1], prim, trc)
+            f = np.ascontiguousarray(f, np.float32)
+            want, wi = img_out(64, 96, 4)
+            L.o_colour_main(C.byref(O.img(a)), C.byref(wi), O.fptr(f), 1)
+            got = np.zeros((64, 96, 4), np.float32)
+            O.ref_shader("colour", "main", f.tobytes(), np.zeros(3, np.int32).tobytes(), [(a, 0), (got, 1), (a, 0), (a, 0), (a, 0), (a, 0), (a, 0)], 96, 64)
+            return [want], [got]
 
     for k, (rot, crop, ori) in enumerate(((1337.0, (1.0, 3.0, 3.0, 7.0), 0), (90.0, (0.1, 0.9, 0.2, 0.8), 0), (7.5, (0.1, 0.9, 0.2, 0.8), 0), (1337.0, (1.0, 3.0, 3.0, 7.0), 6))):
         @add("crop.main set %d" % k)

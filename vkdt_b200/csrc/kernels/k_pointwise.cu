@@ -122,6 +122,17 @@ static const double M_ap0_to_2020[9] = {1.51286139, -0.2589874, -0.22978603, -0.
 static const double M_ap1_to_2020[9] = {1.03866457, -1.14744180e-02, -2.72327263e-02, -4.33683734e-04, 1.00062477, 1.01851049e-04, -5.64306018e-03, -2.23568741e-02, 1.02483276};
 static const double M_redwg_to_2020[9] = {1.180431, -0.094040, -0.086391, -0.028017, 1.311442, -0.283425, -0.074360, -0.362078, 1.436437};
 static const double M_ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+// camera gamuts -> xyz (matrices.h:89-112), the fp32 value of every entry; rows: primaries 8, 9, 11..16
+static const float M_camgamut_to_xyz[8][9] = {
+  /*  8 arriwg3         */ { 0.638007641f, 0.214703858f, 0.09774445f, 0.291953772f, 0.823841035f, -0.115794823f, 0.00279827905f, -0.0670342371f, 1.15329373f },
+  /*  9 arriwg4         */ { 0.704858303f, 0.129760295f, 0.115837313f, 0.254524171f, 0.781477749f, -0.0360019095f, 0.0f, 0.0f, 1.0890578f },
+  /* 11 sonysgamut3     */ { 0.706482708f, 0.128801048f, 0.115172163f, 0.270979673f, 0.786606431f, -0.0575860813f, -0.00967784505f, 0.00460003735f, 1.09413552f },
+  /* 12 sonysgamut3cine */ { 0.5990839f, 0.248925522f, 0.102446489f, 0.215075821f, 0.885068476f, -0.100144319f, -0.0320658498f, -0.0276583899f, 1.14878201f },
+  /* 13 vgamut          */ { 0.679644465f, 0.152211413f, 0.118600048f, 0.260685563f, 0.774894476f, -0.0355800129f, -0.00931019802f, -0.00461246725f, 1.10298038f },
+  /* 14 egamut          */ { 0.705396831f, 0.164041325f, 0.0810177475f, 0.280130714f, 0.820206642f, -0.100337364f, -0.103781514f, -0.0729072541f, 1.26574647f },
+  /* 15 egamut2         */ { 0.736477673f, 0.130739644f, 0.0832385793f, 0.275069982f, 0.828017771f, -0.103087775f, -0.124225155f, -0.0871597677f, 1.3004427f },
+  /* 16 davinciwg       */ { 0.70062238f, 0.148774818f, 0.101058722f, 0.274118513f, 0.873631895f, -0.147750407f, -0.0989629105f, -0.137895331f, 1.32591593f },
+};
 
 static double host_decode_trc(double v, uint32_t trc)
 {
@@ -134,7 +145,40 @@ static double host_decode_trc(double v, uint32_t trc)
     case 4: return pow(v, 2.6);
     case 5: { const double a = 0.17883277, b = 0.28466892, c = 0.55991073; return v <= 0.5 ? v * v / 3.0 : (exp((v - c) / a) + b) / 12.0; }
     case 6: return pow(fmax(v, 0.0), 2.2);
+    case 7:  return v > 0.02740668 ? exp2(v / 0.07329248 - 7.0) - 0.0075 : v / 10.44426855;
+    case 8:  return v < 0.075 ? (v - 0.075) / 16.184376489665897 : exp((v - 0.5520126568606655) / 0.09232902596577353) - 0.0057048244042473785;
+    case 9:  return v <= 0.155251141552511 ? (v - 0.0729055341958355) / 10.5402377416545 : exp2(v * 17.52 - 9.72);
+    case 10: return v < 5.367655 * 0.010591 + 0.092809 ? (v - 0.092809) / 5.367655 : (pow(10.0, (v - 0.385537) / 0.247190) - 0.052272) / 5.555556;
+    case 11: return v < -0.7774983977293537 ? v * 0.3033266726886969 - 0.7774983977293537 : (exp2(14.0 * (v - 0.09286412512218964) / 0.9071358748778103 + 6.0) - 64.0) / 2231.8263090676883;
+    case 12: return v < 0.0 ? (v / 15.1927) - 0.01 : (pow(10.0, v / 0.224282) - 1.0) / 155.975327 - 0.01;
+    case 13: return v < 0.181 ? (v - 0.125) / 5.6 : pow(10.0, (v - 0.598206) / 0.241514) - 0.00873;
+    case 14: return v < 171.2102946929 / 1023.0 ? (v * 1023.0 - 95.0) * 0.01125 / (171.2102946929 - 95.0) : pow(10.0, (v * 1023.0 - 420.0) / 261.5) * (0.18 + 0.01) - 0.01;
+    case 15: return v < 0.100686685370811 ? (v - 0.092864) / 8.799461 : pow(10.0, (v - 0.384316) / 0.245281) / 5.555556 - 0.064829 / 5.555556;
     default: return v;
+  }
+}
+
+// shared/oetf.glsl:2-38 in fp32, one rounding per operation (volatile keeps the host compiler from folding or widening)
+static float host_decode_log_f(float x, uint32_t trc)
+{
+  volatile float t, u;
+  switch(trc)
+  {
+    case 7:  if(x > 0.02740668f) { t = x / 0.07329248f; t = t - 7.0f; t = exp2f(t); t = t - 0.0075f; return t; } t = x / 10.44426855f; return t;
+    case 8:  if(x < 0.075f) { t = x - 0.075f; t = t / 16.184376489665897f; return t; } t = x - 0.5520126568606655f; t = t / 0.09232902596577353f; t = expf(t); t = t - 0.0057048244042473785f; return t;
+    case 9:  if(x <= 0.155251141552511f) { t = x - 0.0729055341958355f; t = t / 10.5402377416545f; return t; } t = x * 17.52f; t = t - 9.72f; t = exp2f(t); return t;
+    case 10: u = 5.367655f; u = u * 0.010591f; u = u + 0.092809f;
+             if(x < u) { t = x - 0.092809f; t = t / 5.367655f; return t; } t = x - 0.385537f; t = t / 0.247190f; t = powf(10.0f, t); t = t - 0.052272f; t = t / 5.555556f; return t;
+    case 11: if(x < -0.7774983977293537f) { t = x * 0.3033266726886969f; t = t - 0.7774983977293537f; return t; }
+             t = x - 0.09286412512218964f; t = 14.0f * t; t = t / 0.9071358748778103f; t = t + 6.0f; t = exp2f(t); t = t - 64.0f; t = t / 2231.8263090676883f; return t;
+    case 12: if(x < 0.0f) { t = x / 15.1927f; t = t - 0.01f; return t; } t = x / 0.224282f; t = powf(10.0f, t); t = t - 1.0f; t = t / 155.975327f; t = t - 0.01f; return t;
+    case 13: if(x < 0.181f) { t = x - 0.125f; t = t / 5.6f; return t; } t = x - 0.598206f; t = t / 0.241514f; t = powf(10.0f, t); t = t - 0.00873f; return t;
+    case 14: u = 171.2102946929f; u = u / 1023.0f;
+             if(x < u) { t = x * 1023.0f; t = t - 95.0f; t = t * 0.01125f; u = 171.2102946929f; u = u - 95.0f; t = t / u; return t; }
+             t = x * 1023.0f; t = t - 420.0f; t = t / 261.5f; t = powf(10.0f, t); u = 0.18f; u = u + 0.01f; t = t * u; t = t - 0.01f; return t;
+    case 15: if(x < 0.100686685370811f) { t = x - 0.092864f; t = t / 8.799461f; return t; }
+             t = x - 0.384316f; t = t / 0.245281f; t = powf(10.0f, t); t = t / 5.555556f; u = 0.064829f; u = u / 5.555556f; t = t - u; return t;
+    default: return x;
   }
 }
 
@@ -150,6 +194,7 @@ static float host_decode_trc_f(float v, uint32_t trc)
     case 4: return powf(v, 2.6f);
     case 5: { const float a = 0.17883277f, b = 0.28466892f, c = 0.55991073f; return v <= 0.5f ? v * v / 3.0f : (expf((v - c) / a) + b) / 12.0f; }
     case 6: return powf(fmaxf(v, 0.0f), 2.2f);
+    case 7: case 8: case 9: case 10: case 11: case 12: case 13: case 14: case 15: return host_decode_log_f(v, trc);
     default: return v;
   }
 }
@@ -166,8 +211,9 @@ static int colour_digest(const float *f, uint32_t size, colour_digest_t *d)
   memset(d, 0, sizeof(*d));
   const uint32_t prim = ii[off + 5];
   d->trc = ii[off + 6];
-  if(d->trc > 6) return vkb_set_error(VKB_ERR_BAD_ARG, "colour: trc %u (camera log curves) is outside the hot-path scope", d->trc);
+  if(d->trc > 15) return vkb_set_error(VKB_ERR_BAD_ARG, "colour: unknown transfer curve %u", d->trc);
   double P[9];
+  float Pf[9]; bool have_Pf = false; // a primaries matrix the shader itself forms in fp32 (camera gamuts)
   switch(prim)
   {
     case 0: for(int j = 0; j < 3; j++) for(int i = 0; i < 3; i++) P[3 * j + i] = f[4 + 4 * i + j]; break; // column major upload
@@ -179,7 +225,20 @@ static int colour_digest(const float *f, uint32_t size, colour_digest_t *d)
     case 6: memcpy(P, M_ap0_to_2020, sizeof(P)); break;
     case 7: memcpy(P, M_ap1_to_2020, sizeof(P)); break;
     case 10: memcpy(P, M_redwg_to_2020, sizeof(P)); break;
-    default: return vkb_set_error(VKB_ERR_BAD_ARG, "colour: primaries %u (camera gamuts) are outside the hot-path scope", prim);
+    case 8: case 9: case 11: case 12: case 13: case 14: case 15: case 16:
+    { // main-impl.glsl:179-196: xyz_to_rec2020 * gamut_to_xyz, the product formed in fp32 (left to right) before it meets the pixel
+      const float *M0 = M_camgamut_to_xyz[prim < 10 ? prim - 8 : prim - 9];
+      static const float fX[9] = {1.71665119f, -0.35567078f, -0.25336628f, -0.66668435f, 1.61648124f, 0.01576855f, 0.01763986f, -0.04277061f, 0.94210312f};
+      volatile float t;
+      for(int j = 0; j < 3; j++) for(int i = 0; i < 3; i++)
+      {
+        t = fX[3 * j + 0] * M0[i]; float a = t; t = fX[3 * j + 1] * M0[3 + i]; a = a + t; t = fX[3 * j + 2] * M0[6 + i]; a = a + t;
+        Pf[3 * j + i] = a; P[3 * j + i] = a;
+      }
+      have_Pf = true;
+      break;
+    }
+    default: return vkb_set_error(VKB_ERR_BAD_ARG, "colour: unknown primaries %u", prim);
   }
   // cat16(rgb, src = 1, dst = mul.rgb): xyz_to_rec2020 * M16i * diag(cl_dst / cl_src) * M16 * rec2020_to_xyz (main-impl.glsl:49-67)
   double MR[9], XM[9], D[9] = {0}, T0[9], T1[9], A[9];
@@ -213,7 +272,7 @@ static int colour_digest(const float *f, uint32_t size, colour_digest_t *d)
       t = cd / cs; d->ratio[j] = t;
     }
     d->has_P = prim != 2;
-    for(int k = 0; k < 9; k++) d->P[k] = (float)P[k]; // the double constants above are the fp32 literals' decimal strings: exact round trip
+    for(int k = 0; k < 9; k++) d->P[k] = have_Pf ? Pf[k] : (float)P[k]; // the double constants above are the fp32 literals' decimal strings: exact round trip
   }
   d->exposure = f[3];
   const float clip = f[off + 7];
@@ -365,7 +424,7 @@ static int launch_chain(const vkb_launch_t *l, int n_ops, const uint32_t *ops)
       case PW_FILMCURV:
         need = sizeof(filmcurv_params_t); VKB_REQUIRE(left >= need);
         memcpy(&P.film, pp, need);
-        if(P.film.colour == 2) return vkb_set_error(VKB_ERR_BAD_ARG, "filmcurv: colour mode 2 (munsell lut) is outside the hot-path scope");
+        if(P.film.colour < 0 || P.film.colour > 5) return vkb_set_error(VKB_ERR_BAD_ARG, "filmcurv: no colour mode %d", P.film.colour);
         break;
       case PW_GRADE:
         need = sizeof(grade_params_t); VKB_REQUIRE(left >= need);

@@ -5,6 +5,7 @@
 // build and the SFU intrinsics (what GLSL pow/exp compile to on a GPU) in the fast one.
 #pragma once
 #include "common.cuh"
+#include "munsell_table.h"
 
 #define PW_POW(x, y) m_pow((x), (y))
 #define PW_EXP(x)    m_exp((x))
@@ -158,6 +159,19 @@ VKB_DEV float decode_trc(float v, uint32_t trc)
     case 5: { const float a = 0.17883277f, b = 0.28466892f, c = 0.55991073f;
               return v <= 0.5f ? v * v / 3.0f : (PW_EXP((v - c) / a) + b) / 12.0f; }
     case 6: return PW_POW(fmaxf(v, 0.0f), 2.2f);
+    // camera log curves to scene linear (shared/oetf.glsl:2-38; mix() with a bvec selects)
+    case 7:  return v > 0.02740668f ? m_exp2(v / 0.07329248f - 7.0f) - 0.0075f : v / 10.44426855f;
+    case 8:  return v < 0.075f ? (v - 0.075f) / 16.184376489665897f : PW_EXP((v - 0.5520126568606655f) / 0.09232902596577353f) - 0.0057048244042473785f;
+    case 9:  return v <= 0.155251141552511f ? (v - 0.0729055341958355f) / 10.5402377416545f : m_exp2(v * 17.52f - 9.72f);
+    case 10: return v < __fadd_rn(__fmul_rn(5.367655f, 0.010591f), 0.092809f) ? (v - 0.092809f) / 5.367655f : (PW_POW(10.0f, (v - 0.385537f) / 0.247190f) - 0.052272f) / 5.555556f;
+    case 11: return v < -0.7774983977293537f ? v * 0.3033266726886969f - 0.7774983977293537f
+                  : (m_exp2(14.0f * (v - 0.09286412512218964f) / 0.9071358748778103f + 6.0f) - 64.0f) / 2231.8263090676883f;
+    case 12: return v < 0.0f ? (v / 15.1927f) - 0.01f : (PW_POW(10.0f, v / 0.224282f) - 1.0f) / 155.975327f - 0.01f;
+    case 13: return v < 0.181f ? (v - 0.125f) / 5.6f : PW_POW(10.0f, (v - 0.598206f) / 0.241514f) - 0.00873f;
+    case 14: return v < __fdiv_rn(171.2102946929f, 1023.0f) ? (v * 1023.0f - 95.0f) * 0.01125f / __fsub_rn(171.2102946929f, 95.0f)
+                  : PW_POW(10.0f, (v * 1023.0f - 420.0f) / 261.5f) * __fadd_rn(0.18f, 0.01f) - 0.01f;
+    case 15: return v < 0.100686685370811f ? (v - 0.092864f) / 8.799461f
+                  : PW_POW(10.0f, (v - 0.384316f) / 0.245281f) / 5.555556f - __fdiv_rn(0.064829f, 5.555556f);
     default: return v;
   }
 }
@@ -270,6 +284,80 @@ VKB_DEV float hue_bump(float h, float h0, float w)
   return d < w ? 0.5f + 0.5f * cosf(pi * d / w) : 0.0f;
 }
 
+// ---- munsell hue lines (shared/munsell.glsl:7-137): chromaticity <-> (hue, chroma) on the renotation grid ----
+static __device__ const uint32_t munsell_xy[VKB_MUNSELL_HDIM * VKB_MUNSELL_CDIM] = { VKB_MUNSELL_WORDS };
+#define MUN_ILLX 0.31271f
+#define MUN_ILLY 0.32902f
+VKB_DEV float2 munsell_lookup(int hue_idx, int chroma_idx)
+{
+  hue_idx = (hue_idx % VKB_MUNSELL_HDIM + VKB_MUNSELL_HDIM) % VKB_MUNSELL_HDIM;
+  chroma_idx = min(max(chroma_idx, 0), VKB_MUNSELL_CDIM - 1);
+  const uint32_t w = __ldg(munsell_xy + VKB_MUNSELL_CDIM * hue_idx + chroma_idx);
+  return make_float2(__half2float(__ushort_as_half((unsigned short)(w & 0xffffu))), __half2float(__ushort_as_half((unsigned short)(w >> 16))));
+}
+VKB_DEV float munsell_hue_angle(float2 xy)
+{ // grows monotonically with the hue index, from zero at hue 0: what the search below needs
+  const float pi = 3.14159265358979323846f;
+  return glsl_mod(2.0f * pi - 2.52f - atan2f(xy.y - MUN_ILLY, xy.x - MUN_ILLX), 2.0f * pi);
+}
+VKB_DEV float munsell_side(float2 v0, float2 v1, float2 p)
+{ // which side of the line v0--v1 p lies on
+  const float ax = v1.x - v0.x, ay = v1.y - v0.y, bx = p.x - v0.x, by = p.y - v0.y;
+  return ax * by - ay * bx;
+}
+VKB_DEV float2 munsell_to_xy(float2 mhc)
+{
+  const float hm = mhc.x * VKB_MUNSELL_HDIM, cm = fmaxf(mhc.y, 0.0f) * VKB_MUNSELL_CDIM;
+  const int hi = (int)hm, ci = (int)cm;
+  const float hu = hm - (float)hi, cu = cm - (float)ci;
+  const float2 r3 = munsell_lookup(hi, ci + 1), r2 = munsell_lookup(hi + 1, ci + 1);
+  const float2 r0 = munsell_lookup(hi, ci),     r1 = munsell_lookup(hi + 1, ci);
+  if(hu >= cu) return make_float2((1.0f - hu) * r0.x + (hu - cu) * r1.x + cu * r2.x, (1.0f - hu) * r0.y + (hu - cu) * r1.y + cu * r2.y);
+  return make_float2(hu * r2.x + (cu - hu) * r3.x + (1.0f - cu) * r0.x, hu * r2.y + (cu - hu) * r3.y + (1.0f - cu) * r0.y);
+}
+VKB_DEV float2 munsell_from_xy(float2 xy)
+{
+  int hm = 0, hM = VKB_MUNSELL_HDIM, cm = 0, cM = VKB_MUNSELL_CDIM - 1;
+  const float theta = munsell_hue_angle(xy);
+  const float dx = xy.x - MUN_ILLX, dy = xy.y - MUN_ILLY;
+  const float rad2 = dx * dx + dy * dy;
+  for(int i = 0; i < 10; i++)
+  { // bisection on hue angle and on distance from the white point
+    const int h = (hm + hM) / 2, c = (cm + cM) / 2;
+    const float2 res = munsell_lookup(h, c);
+    const float th = munsell_hue_angle(res);
+    const float ex = res.x - MUN_ILLX, ey = res.y - MUN_ILLY;
+    const float r2 = ex * ex + ey * ey;
+    if(th <= theta) hm = h; else hM = h;
+    if(r2 <= rad2)  cm = c; else cM = c;
+    if(hM <= hm + 1 && cM <= cm + 1) break;
+  }
+  for(int i = 0; i < 10; i++)
+  { // the grid is not polar: walk to the cell that contains xy
+    const float2 r3 = munsell_lookup(hm, cm + 1), r2 = munsell_lookup(hm + 1, cm + 1);
+    const float2 r0 = munsell_lookup(hm, cm),     r1 = munsell_lookup(hm + 1, cm);
+    const float s0 = munsell_side(r0, r1, xy), s1 = munsell_side(r1, r2, xy);
+    const float s2 = munsell_side(r2, r3, xy), s3 = munsell_side(r3, r0, xy);
+    if(s0 < 0.0f && cm > 0) cm--;
+    else if(s0 < 0.0f && cm == 0) hm = ((hm + VKB_MUNSELL_HDIM / 2) % VKB_MUNSELL_HDIM + VKB_MUNSELL_HDIM) % VKB_MUNSELL_HDIM;
+    else if(s2 < 0.0f && cm < VKB_MUNSELL_CDIM - 2) cm++;
+    if(s1 < 0.0f) hm++;
+    else if(s3 < 0.0f) hm--;
+    if(s0 >= 0.0f && s1 >= 0.0f && s3 >= 0.0f && (s2 >= 0.0f || cm >= VKB_MUNSELL_CDIM - 2))
+    { // inside: barycentric coordinates in the triangle, interpolating the (stepped, like the shader's) corner indices
+      const float t0 = munsell_side(r0, r1, r2), t1 = munsell_side(r2, r3, r0);
+      float u0, u1, u2, u3;
+      if(cm > 0 && s0 + s1 <= t0) { u2 = s0 / t0; u0 = s1 / t0; u1 = 1.0f - u0 - u2; u3 = 0.0f; }
+      else                        { u2 = s3 / t1; u0 = s2 / t1; u3 = 1.0f - u0 - u2; u1 = 0.0f; }
+      const float fh = (float)hm, fc = (float)cm;
+      const float hi = u0 * fh + u1 * (fh + 1.0f) + u2 * (fh + 1.0f) + u3 * fh;
+      const float ci = u0 * fc + u1 * fc + u2 * (fc + 1.0f) + u3 * (fc + 1.0f);
+      return make_float2(hi / VKB_MUNSELL_HDIM, fmaxf(0.0f, ci / VKB_MUNSELL_CDIM));
+    }
+  }
+  return make_float2(1.0f, 1.0f);
+}
+
 VKB_DEV f3 filmcurv_px(f3 in, const filmcurv_params_t &p)
 { // filmcurv/main.comp:68-166
   const float il = fmaxf(5e-3f, p.light);
@@ -289,6 +377,16 @@ VKB_DEV f3 filmcurv_px(f3 in, const filmcurv_params_t &p)
     const float m = fmaxf(1e-4f, y);
     const f3 q = { x * xyz1.y / m, y * xyz1.y / m, (1.0f - x - y) * xyz1.y / m };
     return xyz_to_rec2020(q);
+  }
+  if(p.colour == 2)
+  { // hue of the input, chroma of the per channel curve, along munsell's hue lines (main.comp:96-104, colourspaces.glsl:2-19)
+    const f3 xyz0 = rec2020_to_xyz(col0), xyz1 = rec2020_to_xyz(col1);
+    const float s0 = 1.0f * xyz0.x + 1.0f * xyz0.y + 1.0f * xyz0.z, s1 = 1.0f * xyz1.x + 1.0f * xyz1.y + 1.0f * xyz1.z;
+    const float2 m0 = munsell_from_xy(make_float2(xyz0.x / s0, xyz0.y / s0));
+    const float2 m1 = munsell_from_xy(make_float2(xyz1.x / s1, xyz1.y / s1));
+    const float2 xy = munsell_to_xy(make_float2(m0.x, m1.y));
+    const float Y = xyz1.y;
+    return xyz_to_rec2020({ xy.x * Y / xy.y, xy.y * Y / xy.y, (1.0f - xy.x - xy.y) * Y / xy.y });
   }
   if(p.colour == 4)
   { // agx
