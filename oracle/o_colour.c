@@ -285,25 +285,72 @@ void o_dt_UCS_JCH_to_xyY(const float *JCH, float L_white, float *xyY)
   xyY[2] = powf((1.12426773749357f * L_star / (2.098883786377f - L_star)), 1.5831518565279648f);
 }
 
-/* colour/main-impl.glsl:200-341 with have_clut = have_pick = have_abney = 0 */
-void o_colour_main(const oimg_t *in, oimg_t *out, const float *f, int out_f16)
+/* ---- lut inputs: main-impl.glsl:76-102 (process_clut), clut.glsl:1-20 ---- */
+static void tri2quad(float *tc)
+{
+  tc[1] = tc[1] / (1.0f - tc[0]);
+  tc[0] = (1.0f - tc[0]) * (1.0f - tc[0]);
+}
+static void clut_chroma(const oimg_t *clut, const float *tc, int idx, int nbands, float *rb)
+{
+  const int band = (nbands == 3) ? 2 * idx : idx;
+  float t[4];
+  o_tex4(clut, (tc[0] + (float)band) / (float)nbands, tc[1], t);
+  rb[0] = t[0]; rb[1] = t[1];
+}
+static float clut_luminance(const oimg_t *clut, const float *tc, int idx, int n, int nbands)
+{
+  float t[4];
+  if(nbands == 3) { o_tex4(clut, (tc[0] + 1.0f) / 3.0f, tc[1], t); return t[idx]; }
+  o_tex4(clut, (tc[0] + (float)(n + idx / 2)) / (float)nbands, tc[1], t);
+  return (idx % 2 == 0) ? t[0] : t[1];
+}
+static void process_clut(const oimg_t *clut, const float *f, float auto_temp, float *rgb)
+{
+  const float b = rgb[0] + rgb[1] + rgb[2];
+  float tc[2] = { rgb[0] / b, rgb[2] / b };
+  tri2quad(tc);
+  const int nbands = clut->w / clut->h;
+  const int n = (nbands * 2) / 3;
+  const float temp = f[224] < 0.0f ? auto_temp : f[224];
+  const float bp = o_clamp(temp, 0.0f, 1.0f) * (float)(n - 1);
+  const int k0 = (int)bp;
+  const int k1 = k0 + 1 < n - 1 ? k0 + 1 : n - 1;
+  const float frac = bp - (float)k0;
+  float rb0[2], rb1[2];
+  clut_chroma(clut, tc, k0, nbands, rb0);
+  clut_chroma(clut, tc, k1, nbands, rb1);
+  const float rbx = o_mix(rb0[0], rb1[0], frac), rby = o_mix(rb0[1], rb1[1], frac);
+  const float L = o_mix(clut_luminance(clut, tc, k0, n, nbands), clut_luminance(clut, tc, k1, n, nbands), frac);
+  rgb[0] = rbx * L * b; rgb[1] = (1.0f - rbx - rby) * L * b; rgb[2] = rby * L * b;
+}
+
+/* colour/main-impl.glsl:200-341.  clut / (abney and spectra) may be null: have_clut = 0 / have_abney = 0; have_pick = 0 always
+ * (the colour picker is not part of the path).  auto_temp: what the autotemp node would deliver, read if the committed
+ * temperature is negative */
+void o_colour_main_lut(const oimg_t *in, oimg_t *out, const float *f, int out_f16, const oimg_t *clut, const oimg_t *abney, const oimg_t *spectra, float auto_temp)
 {
   const uint32_t *ii = (const uint32_t *)f;
   const int off = 224;
   const float sat = f[off+2], clip_hl = f[off+7];
   const uint32_t N = ii[16] > 24 ? 24 : ii[16];
+  const uint32_t gamut_mode = ii[off+4];
+  const int use_clut = clut && ii[off+1] != 0;
+  const int have_abney = abney && spectra;
   const float one[3] = {1.0f, 1.0f, 1.0f};
 #pragma omp parallel for schedule(static)
   for(int y = 0; y < out->h; y++) for(int x = 0; x < out->w; x++)
   {
     float rgb[4];
     o_tex4(in, (x + 0.5) / (double)out->w, (y + 0.5) / (double)out->h, rgb);
-    decode_colour(f, rgb);
+    if(!use_clut) decode_colour(f, rgb);
+    else process_clut(clut, f, auto_temp, rgb);
     cat16(rgb, one, f);
     if(clip_hl > 0.0f)
     {
       float clip[3] = { clip_hl, clip_hl, clip_hl };
-      decode_colour(f, clip);
+      if(!use_clut) decode_colour(f, clip);
+      else { rgb[0] = rgb[1] = rgb[2] = clip_hl; process_clut(clut, f, auto_temp, rgb); } /* :245 assigns the PIXEL, not the clip colour */
       cat16(clip, one, f);
       const float t = o_min(clip[0], o_min(clip[1], clip[2]));
       for(int k = 0; k < 3; k++) rgb[k] = o_min(rgb[k], t);
@@ -321,7 +368,7 @@ void o_colour_main(const oimg_t *in, oimg_t *out, const float *f, int out_f16)
       }
       for(int k = 0; k < 3; k++) rgb[k] = co[k];
     }
-    if(sat != 1.0f)
+    if(!have_abney && sat != 1.0f)
     {
       for(int k = 0; k < 3; k++) rgb[k] = o_max(rgb[k], 0.0f);
       float xyY[3], JCH[3];
@@ -331,8 +378,53 @@ void o_colour_main(const oimg_t *in, oimg_t *out, const float *f, int out_f16)
       o_dt_UCS_JCH_to_xyY(JCH, 1.0f, xyY);
       xyY_to_rec2020(xyY, rgb);
     }
+    else if(have_abney && (sat != 1.0f || gamut_mode > 0))
+    { /* :287-335 saturation along lines of constant dominant wavelength, gamut compression */
+      float xyY[3], lut[4], t4[4];
+      rec2020_to_xyY(rgb, xyY);
+      tri2quad(xyY);
+      o_tex4(spectra, xyY[0], xyY[1], lut);
+      float slx = lut[3], sly = -lut[1] / (2.0f * lut[0]);
+      const float norm = (sly - 400.0f) / (700.0f - 400.0f) - 0.5f;
+      sly = 0.5f * (0.5f + 0.5f * norm / sqrtf(norm * norm + 0.25f));
+      if(lut[0] > 0.0f) sly += 0.5f;
+      float m = sat * slx;
+      const int sw = abney->w, sh = abney->h;
+      if(gamut_mode > 0)
+      {
+        float bound = 1.0f;
+        if(gamut_mode == 1) { o_fetch4(abney, sw - 1, (int)(sly * sh), t4); bound = t4[1]; }
+        else if(gamut_mode == 2)
+        {
+          o_fetch4(abney, sw - 1, (int)(sly * sh), t4);
+          bound = t4[0];
+          slx *= t4[0] / t4[1];
+          m = sat * slx;
+        }
+        else if(gamut_mode == 3)
+        {
+          o_fetch4(abney, sw - 2, (int)(sly * sh), t4);
+          bound = t4[0];
+          slx *= t4[0] / t4[1];
+          m = sat * slx;
+        }
+        if(sat > 1.0f) slx = o_mix(slx, bound, (m - slx) / (m - slx + 1.0f));
+        else slx = m;
+        if(slx > bound) slx = bound;
+      }
+      slx = o_clamp(slx, 0.0f, (sw - 3.0f) / sw);
+      o_tex4(abney, slx, sly, t4);
+      xyY[0] = t4[0]; xyY[1] = t4[1];
+      xyY_to_rec2020(xyY, rgb);
+    }
     for(int k = 0; k < 3; k++) rgb[k] = o_clamp(rgb[k], -65535.0f, 65535.0f);
     rgb[3] = 1.0f;
     o_store4(out, x, y, rgb, out_f16);
   }
+}
+
+/* the same without lut inputs */
+void o_colour_main(const oimg_t *in, oimg_t *out, const float *f, int out_f16)
+{
+  o_colour_main_lut(in, out, f, out_f16, 0, 0, 0, 0.0f);
 }

@@ -108,8 +108,9 @@ static inline int o_mirror(int i, int n)
 static inline void o_px4(const oimg_t *im, int x, int y, float *o)
 {
   const float *s = im->p + ((size_t)y * im->w + x) * im->c;
-  if(im->c == 4) { o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; o[3] = s[3]; }
-  else           { o[0] = s[0]; o[1] = 0.0f; o[2] = 0.0f; o[3] = 1.0f; }
+  if(im->c == 4)      { o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; o[3] = s[3]; }
+  else if(im->c == 2) { o[0] = s[0]; o[1] = s[1]; o[2] = 0.0f; o[3] = 1.0f; }
+  else                { o[0] = s[0]; o[1] = 0.0f; o[2] = 0.0f; o[3] = 1.0f; }
 }
 /* texelFetch(img, ivec2(x,y), 0): clamp out of range to the edge */
 static inline void o_fetch4(const oimg_t *im, int x, int y, float *o)

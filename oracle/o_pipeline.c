@@ -87,6 +87,12 @@ void o_demosaic_module(const oimg_t *in, oimg_t *out, const o_demosaic_params_t 
 
 /* the dng gain maps of the source (denoise/main.c:172-200), set by the caller before o_denoise_module / o_darkroom_run:
  * rgba f32 texture + { origin x, origin y, 1 / extent x, 1 / extent y }; 0 = none */
+/* the lut inputs of colour (i-lut modules wired to its clut / abney / spectra connectors), same convention as the gain map */
+static const oimg_t *o_lut_clut = 0, *o_lut_abney = 0, *o_lut_spectra = 0;
+void o_set_colour_luts(const oimg_t *clut, const oimg_t *abney, const oimg_t *spectra)
+{
+  o_lut_clut = clut; o_lut_abney = abney; o_lut_spectra = spectra;
+}
 static const oimg_t *o_gainmap_img = 0;
 static float o_gainmap_os[4];
 void o_set_gainmap(const oimg_t *gm, const float *map_os)
@@ -201,7 +207,17 @@ int o_darkroom_run(const o_darkroom_t *d, const uint16_t *raw, float *out, int s
   float p_wb[4] = { d->colour.white[0], d->colour.white[1], d->colour.white[2], d->colour.white[3] };
   o_colour_commit(&d->colour, p_wb, d->whitebalance, d->cam_to_rec2020, d->colour_primaries, d->colour_trc, fcol);
   oimg_t col = o_img_alloc(ow, oh, 4);
-  o_colour_main(&crp, &col, fcol, 1);
+  if(o_lut_clut && d->colour.temp > 0.0f)
+  { /* colour/main.c:268-292: the anchor blend of a clut with more than three bands is uniform in mired, 2000 .. 15000 K */
+    const int nbands = o_lut_clut->w / o_lut_clut->h;
+    if(nbands > 3)
+    {
+      const float T_lo = 2000.0f, T_hi = 15000.0f, m_lo = 1e6f / T_hi, m_hi = 1e6f / T_lo;
+      const float m = 1e6f / o_clamp(d->colour.temp, T_lo, T_hi);
+      fcol[224] = o_clamp((m - m_lo) / (m_hi - m_lo), 0.0f, 1.0f);
+    }
+  }
+  o_colour_main_lut(&crp, &col, fcol, 1, o_lut_clut, o_lut_abney, o_lut_spectra, 0.0f);
   o_img_free(&crp);
   if(stage == 5) { copy_out(&col, stage_out); o_img_free(&col); return 0; }
 

@@ -75,6 +75,8 @@ void o_sample_catmull_rom(const oimg_t *tex, float u, float v, float *res);
 void o_colour_commit(const o_colour_params_t *p, float *p_wb, const float *img_wb, const float *img_cam_to_rec2020,
     int img_primaries, int img_trc, float *f);
 void o_colour_main(const oimg_t *in, oimg_t *out, const float *f, int out_f16);
+/* with the lut inputs (clut: rg; abney: rg; spectra: rgba; any of them null = not connected) */
+void o_colour_main_lut(const oimg_t *in, oimg_t *out, const float *f, int out_f16, const oimg_t *clut, const oimg_t *abney, const oimg_t *spectra, float auto_temp);
 void o_xyY_to_dt_UCS_JCH(const float *xyY, float L_white, float *JCH);
 void o_dt_UCS_JCH_to_xyY(const float *JCH, float L_white, float *xyY);
 
@@ -126,6 +128,8 @@ typedef struct o_darkroom_t
 void o_darkroom_defaults(o_darkroom_t *d, uint32_t width, uint32_t height);
 /* dng gain maps for the denoise module of the next runs (rgba f32 texture + origin / inverse extent); gm = 0 removes them */
 void o_set_gainmap(const oimg_t *gm, const float *map_os);
+/* the tables o_darkroom_run's colour step reads (null: not connected); they stay set until cleared */
+void o_set_colour_luts(const oimg_t *clut, const oimg_t *abney, const oimg_t *spectra);
 void o_colenc_px(float *rgb, int prim, int trc);
 float o_unorm8(float v);
 void o_colenc_main(const oimg_t *in, oimg_t *out, int prim, int trc, int fmt);

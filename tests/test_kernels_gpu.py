@@ -223,6 +223,55 @@ def test_colour_input_curves_and_gamuts(gpu, oracle, trc, prim, clip):
     assert_f16_close(to_host(d_out)[..., :3], want[..., :3], 2, 0.90, "colour trc %d prim %d" % (trc, prim))
 
 
+def _synthetic_luts(rng, nbands):
+    """luts of the shapes the reference's offline tools write (clut: nbands squares of rg side by side; spectra: rgba, the
+    dominant wavelength is -y / 2x; abney: rg with the gamut bounds in its last two columns)"""
+    ch = 32
+    h16 = lambda a: np.ascontiguousarray(a.astype(np.float16).astype(np.float32))
+    clut = h16(rng.uniform(0.05, 0.6, (ch, nbands * ch, 2)))
+    spectra = np.zeros((48, 48, 4), np.float32)
+    sx = rng.uniform(0.5, 2.0, (48, 48)) * np.where(rng.uniform(0, 1, (48, 48)) < 0.5, -1.0, 1.0)
+    lam = rng.uniform(380.0, 720.0, (48, 48))
+    spectra[..., 0], spectra[..., 1], spectra[..., 2], spectra[..., 3] = sx, -2.0 * sx * lam, rng.uniform(0, 1, (48, 48)), rng.uniform(0.0, 0.9, (48, 48))
+    abney = h16(rng.uniform(0.1, 0.6, (40, 64, 2)))
+    abney[:, -2:, 0] = h16(rng.uniform(0.5, 0.9, (40, 2)))
+    abney[:, -2:, 1] = h16(rng.uniform(0.6, 1.0, (40, 2)))
+    return clut, np.ascontiguousarray(spectra), abney
+
+
+@pytest.mark.parametrize("nbands,temp,use_clut,use_abney,sat,gamut,clip", [(3, 0.3, 1, 0, 1.0, 0, 0), (6, 0.62, 1, 0, 1.2, 0, 0), (3, 1.0, 1, 1, 1.3, 0, 0),
+                                                                         (3, 0.0, 0, 1, 1.0, 1, 0), (3, 0.0, 0, 1, 1.4, 2, 0), (3, 0.0, 0, 1, 0.7, 3, 0),
+                                                                         (6, 0.2, 1, 1, 1.5, 3, 1), (9, 0.85, 1, 0, 1.0, 0, 0)])
+def test_colour_lut_inputs(gpu, oracle, nbands, temp, use_clut, use_abney, sat, gamut, clip):
+    """colour with its lut connectors (main-impl.glsl:76-102 + clut.glsl: camera rgb -> rec2020 through a clut with temperature
+    anchors; :287-335: saturation and gamut compression through the abney / spectra luts), the node's seven connectors and the
+    push constants { have_clut, have_pick, have_abney } as colour/main.c:444-465 passes them."""
+    import torch
+    O = oracle
+    w, h = 192, 128
+    rng = np.random.default_rng(7000 + 10 * nbands + gamut)
+    clut, spectra, abney = _synthetic_luts(rng, nbands)
+    d = O.darkroom_defaults(w, h)
+    d.colour.exposure, d.colour.sat, d.colour.matrix, d.colour.gamut, d.colour.clip, d.colour.clipmax = 0.2, sat, 4 if use_clut else 1, gamut, clip, 0.9
+    f = _colour_committed(O, d)
+    f[224] = temp
+    a = rng.uniform(0.01, 1.2, (h, w, 4)).astype(np.float16).astype(np.float32)
+    a[..., 3] = 1.0
+    want, wi = O.new_img(h, w, 4)
+    O.lib().o_colour_main_lut(C.byref(O.img(a)), C.byref(wi), O.fptr(f), 1, C.byref(O.img(clut)) if use_clut else None,
+                              C.byref(O.img(abney)) if use_abney else None, C.byref(O.img(spectra)) if use_abney else None, C.c_float(0.0))
+    d_in, d_out = to_dev_f16(a), dev_f16(h, w, 4)
+    d_clut, d_abney, d_spec = to_dev_f16(clut), to_dev_f16(abney), torch.from_numpy(spectra).cuda()
+    i_in = gpu.image(d_in, w, h, 4, "f16")
+    conn = [i_in, gpu.image(d_out, w, h, 4, "f16"),
+            gpu.image(d_clut, clut.shape[1], clut.shape[0], 2, "f16") if use_clut else i_in, i_in,
+            gpu.image(d_abney, abney.shape[1], abney.shape[0], 2, "f16") if use_abney else i_in,
+            gpu.image(d_spec, 48, 48, 4, "f32") if use_abney else i_in, i_in]
+    gpu.dispatch("colour", "main", conn, np.array([use_clut, 0, use_abney], np.int32).tobytes(), f.tobytes())
+    # the plain saturation runs through sin / cos / atan2 (not libm's bit for bit on the device): 3 ulps there, like test_colour
+    assert_f16_close(to_host(d_out)[..., :3], want[..., :3], 3 if (sat != 1.0 and not use_abney) else 2, 0.90, "colour luts %d/%d/%d" % (nbands, use_clut, use_abney))
+
+
 @pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5])
 def test_filmcurv(gpu, oracle, mode):
     O = oracle

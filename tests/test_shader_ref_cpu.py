@@ -263,6 +263,43 @@ def cases(O):
             O.ref_shader("colour", "main", f.tobytes(), np.zeros(3, np.int32).tobytes(), [(a, 0), (got, 1), (a, 0), (a, 0), (a, 0), (a, 0), (a, 0)], 96, 64)
             return [want], [got]
 
+    # lut inputs (main-impl.glsl:76-102, clut.glsl; :287-335): synthetic luts of the shapes the reference's tools write
+    def luts(rng, nbands):
+        ch = 32
+        clut = f16(rng.uniform(0.05, 0.6, (ch, nbands * ch, 2)))
+        spectra = np.zeros((48, 48, 4), np.float32)
+        sx = rng.uniform(0.5, 2.0, (48, 48)) * np.where(rng.uniform(0, 1, (48, 48)) < 0.5, -1.0, 1.0)
+        lam = rng.uniform(380.0, 720.0, (48, 48))
+        spectra[..., 0], spectra[..., 1], spectra[..., 2], spectra[..., 3] = sx, -2.0 * sx * lam, rng.uniform(0, 1, (48, 48)), rng.uniform(0.0, 0.9, (48, 48))
+        abney = f16(rng.uniform(0.1, 0.6, (40, 64, 2)))
+        abney[:, -2:, 0] = f16(rng.uniform(0.5, 0.9, (40, 2)))      # the last two columns: gamut bounds (rec709, then spectral locus / rec2020)
+        abney[:, -2:, 1] = f16(rng.uniform(0.6, 1.0, (40, 2)))
+        return clut, np.ascontiguousarray(spectra), abney
+
+    for k, (nbands, temp, use_clut, use_abney, sat, gamut, clip) in enumerate(((3, 0.3, 1, 0, 1.0, 0, 0), (6, 0.62, 1, 0, 1.2, 0, 0), (3, 1.0, 1, 1, 1.3, 0, 0),
+                                                                             (3, 0.0, 0, 1, 1.0, 1, 0), (3, 0.0, 0, 1, 1.4, 2, 0), (3, 0.0, 0, 1, 0.7, 3, 0),
+                                                                             (6, 0.2, 1, 1, 1.5, 3, 1), (9, 0.85, 1, 0, 1.0, 0, 0))):
+        @add("colour.main lut set %d" % k)
+        def _(k=k, nbands=nbands, temp=temp, use_clut=use_clut, use_abney=use_abney, sat=sat, gamut=gamut, clip=clip):
+            rng = np.random.default_rng(640 + k)
+            a = rgba(rng, 96, 64, 0.01, 1.2)
+            a[0, 0, :3] = [0.3, 0.5, 0.2]                            # the nan of rgba() would be one here and there alike; keep the case finite
+            clut, spectra, abney = luts(rng, nbands)
+            d = O.darkroom_defaults(64, 64)
+            p = d.colour
+            p.exposure, p.sat, p.matrix, p.gamut, p.clip, p.clipmax = 0.2, sat, 4 if use_clut else 1, gamut, clip, 0.9
+            f, _wb = O.colour_commit_oracle(bytes(p), [2.1, 1.0, 1.6, 1.0], [0.8, 0.15, 0.05, 0.1, 0.85, 0.05, 0.02, 0.18, 0.8], 0, 0)
+            f = np.ascontiguousarray(f, np.float32)
+            f[224] = temp                                           # the anchor blend of colour/main.c:272-292, set directly
+            want, wi = img_out(64, 96, 4)
+            L.o_colour_main_lut(C.byref(O.img(a)), C.byref(wi), O.fptr(f), 1, C.byref(O.img(clut)) if use_clut else None,
+                                C.byref(O.img(abney)) if use_abney else None, C.byref(O.img(spectra)) if use_abney else None, C.c_float(0.0))
+            got = np.zeros((64, 96, 4), np.float32)
+            push = np.array([use_clut, 0, use_abney], np.int32).tobytes()
+            O.ref_shader("colour", "main", f.tobytes(), push, [(a, 0), (got, 1), (clut if use_clut else a, 0), (a, 0),
+                                                               (abney if use_abney else a, 0), (spectra if use_abney else a, 0), (a, 0)], 96, 64)
+            return [want], [got]
+
     for k, (rot, crop, ori) in enumerate(((1337.0, (1.0, 3.0, 3.0, 7.0), 0), (90.0, (0.1, 0.9, 0.2, 0.8), 0), (7.5, (0.1, 0.9, 0.2, 0.8), 0), (1337.0, (1.0, 3.0, 3.0, 7.0), 6))):
         @add("crop.main set %d" % k)
         def _(k=k, rot=rot, crop=crop, ori=ori):

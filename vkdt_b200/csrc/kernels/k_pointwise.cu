@@ -515,8 +515,202 @@ static int launch_chain(const vkb_launch_t *l, int n_ops, const uint32_t *ops)
   return VKB_OK;
 }
 
+// ---- colour with lut inputs (colour/main-impl.glsl:76-102 process_clut + clut.glsl, :287-335 abney / spectra) ----
+// the luts are small images of the reference's offline tools: clut (rg f16, nbands x 1 squares side by side), abney (rg f16,
+// the last two columns hold gamut bounds), spectra (rgba).  any channel count / f16 or f32 storage is read.
+struct lut_t { const void *p; int w, h, chan, f32; };
+VKB_DEV float4 lut_px(const lut_t &t, int x, int y)
+{ // vulkan's fill rules for absent channels: (0, 0, 0, 1)
+  float v[4] = { 0.0f, 0.0f, 0.0f, 1.0f };
+  const size_t o = ((size_t)y * t.w + x) * t.chan;
+  for(int c = 0; c < t.chan && c < 4; c++)
+    v[c] = t.f32 ? __ldg((const float *)t.p + o + c) : __half2float(__ushort_as_half(__ldg((const unsigned short *)t.p + o + c)));
+  return make_float4(v[0], v[1], v[2], v[3]);
+}
+VKB_DEV float4 lut_fetch(const lut_t &t, int x, int y) { return lut_px(t, min(max(x, 0), t.w - 1), min(max(y, 0), t.h - 1)); }
+VKB_DEV float4 lut_tex(const lut_t &t, float u, float v)
+{ // texture(): linear, mirrored repeat; the restatement's ideal sampler (oracle/o_common.h o_tex4) in both builds
+  double x = (double)u * (double)t.w - 0.5, y = (double)v * (double)t.h - 0.5;
+  if(fabs(x - rint(x)) < 1.0 / 4096.0) x = rint(x);
+  if(fabs(y - rint(y)) < 1.0 / 4096.0) y = rint(y);
+  const double fx = floor(x), fy = floor(y);
+  const float ax = (float)(x - fx), ay = (float)(y - fy);
+  const int x0 = mirrori((int)fx, t.w), x1 = mirrori((int)fx + 1, t.w), y0 = mirrori((int)fy, t.h), y1 = mirrori((int)fy + 1, t.h);
+  const float4 a = lut_px(t, x0, y0), b = lut_px(t, x1, y0), c = lut_px(t, x0, y1), d = lut_px(t, x1, y1);
+  return make_float4((a.x * (1.0f - ax) + b.x * ax) * (1.0f - ay) + (c.x * (1.0f - ax) + d.x * ax) * ay,
+                     (a.y * (1.0f - ax) + b.y * ax) * (1.0f - ay) + (c.y * (1.0f - ax) + d.y * ax) * ay,
+                     (a.z * (1.0f - ax) + b.z * ax) * (1.0f - ay) + (c.z * (1.0f - ax) + d.z * ax) * ay,
+                     (a.w * (1.0f - ax) + b.w * ax) * (1.0f - ay) + (c.w * (1.0f - ax) + d.w * ax) * ay);
+}
+VKB_DEV void tri2quad(float &x, float &y) { y = y / (1.0f - x); x = (1.0f - x) * (1.0f - x); }
+VKB_DEV float2 clut_chroma(const lut_t &clut, float tx, float ty, int idx, int nbands)
+{
+  const int band = nbands == 3 ? 2 * idx : idx;
+  const float4 t = lut_tex(clut, (tx + (float)band) / (float)nbands, ty);
+  return make_float2(t.x, t.y);
+}
+VKB_DEV float clut_luminance(const lut_t &clut, float tx, float ty, int idx, int n, int nbands)
+{
+  if(nbands == 3) { const float4 t = lut_tex(clut, (tx + 1.0f) / 3.0f, ty); return idx == 0 ? t.x : idx == 1 ? t.y : idx == 2 ? t.z : t.w; }
+  const float4 t = lut_tex(clut, (tx + (float)(n + idx / 2)) / (float)nbands, ty);
+  return (idx % 2 == 0) ? t.x : t.y;
+}
+VKB_DEV f3 process_clut(const lut_t &clut, float temp, f3 rgb)
+{ // camera rgb -> rec2020 through the two nearest temperature anchors of the lut
+  const float b = rgb.x + rgb.y + rgb.z;
+  float tx = rgb.x / b, ty = rgb.z / b;
+  tri2quad(tx, ty);
+  const int nbands = clut.w / clut.h;
+  const int n = (nbands * 2) / 3;
+  const float bp = clampf(temp, 0.0f, 1.0f) * (float)(n - 1);
+  const int k0 = (int)bp, k1 = min(k0 + 1, n - 1);
+  const float frac = bp - (float)k0;
+  const float2 rb0 = clut_chroma(clut, tx, ty, k0, nbands), rb1 = clut_chroma(clut, tx, ty, k1, nbands);
+  const float rbx = mixf(rb0.x, rb1.x, frac), rby = mixf(rb0.y, rb1.y, frac);
+  const float L = mixf(clut_luminance(clut, tx, ty, k0, n, nbands), clut_luminance(clut, tx, ty, k1, n, nbands), frac);
+  return { rbx * L * b, (1.0f - rbx - rby) * L * b, rby * L * b };
+}
+struct colour_lut_t
+{
+  lut_t clut, abney, spectra;
+  int use_clut, have_abney;
+  float temp, clip_hl;
+  uint32_t gamut_mode;
+};
+__global__ void __launch_bounds__(256) k_colour_lut(const uint2 *__restrict__ in, int w, int h, void *__restrict__ outv, int out_f32, const colour_digest_t P, const colour_lut_t Q)
+{
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if(x >= w || y >= h) return;
+  const float4 px = ld_rgba(in, w, x, y);
+  colour_digest_t noP = P;     // cat16 on its own: the lut delivers rec2020
+  noP.has_P = 0;
+  f3 c = { px.x, px.y, px.z }, o;
+  if(!Q.use_clut)
+  {
+    if(P.trc) { c.x = decode_trc(c.x, P.trc); c.y = decode_trc(c.y, P.trc); c.z = decode_trc(c.z, P.trc); }
+    o = colour_matrices(c, P);
+    if(P.clip_t > 0.0f) { o.x = fminf(o.x, P.clip_t); o.y = fminf(o.y, P.clip_t); o.z = fminf(o.z, P.clip_t); }
+  }
+  else
+  {
+    o = colour_matrices(process_clut(Q.clut, Q.temp, c), noP);
+    if(Q.clip_hl > 0.0f)
+    { // main-impl.glsl:245 assigns the converted clip colour to the PIXEL and leaves the clip colour as it was: followed to the letter
+      o = process_clut(Q.clut, Q.temp, { Q.clip_hl, Q.clip_hl, Q.clip_hl });
+      const f3 cl = colour_matrices({ Q.clip_hl, Q.clip_hl, Q.clip_hl }, noP);
+      const float t = fminf(cl.x, fminf(cl.y, cl.z));
+      o.x = fminf(o.x, t); o.y = fminf(o.y, t); o.z = fminf(o.z, t);
+    }
+  }
+  o.x *= P.exposure; o.y *= P.exposure; o.z *= P.exposure;
+  if(P.N > 0)
+  {
+    f3 co = { P.rbf_P[0] * o.x + P.rbf_P[1] * o.y + P.rbf_P[2] * o.z,
+              P.rbf_P[3] * o.x + P.rbf_P[4] * o.y + P.rbf_P[5] * o.z,
+              P.rbf_P[6] * o.x + P.rbf_P[7] * o.y + P.rbf_P[8] * o.z };
+    for(uint32_t i = 0; i < P.N; i++)
+    {
+      const float d0 = o.x - P.rbf_p[i][0], d1 = o.y - P.rbf_p[i][1], d2 = o.z - P.rbf_p[i][2];
+      const float r = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+      co.x += P.rbf_c[i][0] * r; co.y += P.rbf_c[i][1] * r; co.z += P.rbf_c[i][2] * r;
+    }
+    o = co;
+  }
+  if(!Q.have_abney && P.sat != 1.0f)
+  {
+    o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f);
+    const f3 xyz = rec2020_to_xyz(o);
+    const float s = xyz.x + xyz.y + xyz.z;
+    float J, C, H, xx, yy, Y;
+    xyY_to_dt_UCS_JCH(xyz.x / s, xyz.y / s, xyz.y, 1.0f, J, C, H);
+    C = clampf(C * P.sat, 0.0f, 1.0f);
+    dt_UCS_JCH_to_xyY(J, C, H, 1.0f, xx, yy, Y);
+    o = xyz_to_rec2020({ xx * Y / yy, yy * Y / yy, (1.0f - xx - yy) * Y / yy });
+  }
+  else if(Q.have_abney && (P.sat != 1.0f || Q.gamut_mode > 0))
+  { // saturation along lines of constant dominant wavelength, compressed into the chosen gamut
+    const f3 xyz = rec2020_to_xyz(o);
+    const float s = xyz.x + xyz.y + xyz.z;
+    float qx = xyz.x / s, qy = xyz.y / s;
+    const float Y = xyz.y;
+    tri2quad(qx, qy);
+    const float4 lut = lut_tex(Q.spectra, qx, qy);
+    float slx = lut.w, sly = -lut.y / (2.0f * lut.x);
+    const float norm = (sly - 400.0f) / (700.0f - 400.0f) - 0.5f;
+    sly = 0.5f * (0.5f + 0.5f * norm / sqrtf(norm * norm + 0.25f));
+    if(lut.x > 0.0f) sly += 0.5f;
+    float m = P.sat * slx;
+    const int sw = Q.abney.w, sh = Q.abney.h;
+    if(Q.gamut_mode > 0)
+    {
+      float bound = 1.0f;
+      if(Q.gamut_mode == 1) bound = lut_fetch(Q.abney, sw - 1, (int)(sly * (float)sh)).y;
+      else if(Q.gamut_mode == 2 || Q.gamut_mode == 3)
+      { // rec2020 / rec709: the lower bound moves with the spectral locus scaled into the triangle
+        const float4 ms = lut_fetch(Q.abney, Q.gamut_mode == 2 ? sw - 1 : sw - 2, (int)(sly * (float)sh));
+        bound = ms.x;
+        slx *= ms.x / ms.y;
+        m = P.sat * slx;
+      }
+      if(P.sat > 1.0f) slx = mixf(slx, bound, (m - slx) / (m - slx + 1.0f));
+      else slx = m;
+      if(slx > bound) slx = bound;
+    }
+    slx = clampf(slx, 0.0f, ((float)sw - 3.0f) / (float)sw);
+    const float4 xy = lut_tex(Q.abney, slx, sly);
+    o = xyz_to_rec2020({ xy.x * Y / xy.y, xy.y * Y / xy.y, (1.0f - xy.x - xy.y) * Y / xy.y });
+  }
+  o.x = clampf(o.x, -65535.0f, 65535.0f); o.y = clampf(o.y, -65535.0f, 65535.0f); o.z = clampf(o.z, -65535.0f, 65535.0f);
+  if(out_f32) reinterpret_cast<float4 *>(outv)[(size_t)y * w + x] = make_float4(o.x, o.y, o.z, 1.0f);
+  else st_rgba(reinterpret_cast<uint2 *>(outv), w, x, y, make_float4(o.x, o.y, o.z, 1.0f));
+}
+static int lut_of(const vkb_image_t *im, lut_t *t)
+{
+  VKB_REQUIRE(im->data && im->wd > 0 && im->ht > 0 && im->chan >= 1 && im->chan <= 4);
+  VKB_REQUIRE(im->format == VKB_TOKEN_F16 || im->format == VKB_TOKEN_F32);
+  *t = { im->data, (int)im->wd, (int)im->ht, (int)im->chan, im->format == VKB_TOKEN_F32 ? 1 : 0 };
+  return VKB_OK;
+}
+// (colour, main) with the node's seven connectors (colour/main.c:444-465: input output clut picked abney spectra autotemp) and
+// the push constants { have_clut, have_pick, have_abney }
+static int launch_colour_lut(const vkb_launch_t *l)
+{
+  const int32_t *pc = (const int32_t *)l->push;
+  VKB_REQUIRE(l->num_conn >= 6);
+  const vkb_image_t *in = l->conn, *out = l->conn + 1;
+  VKB_REQUIRE(in->chan == 4 && in->format == VKB_TOKEN_F16 && out->chan == 4 && (out->format == VKB_TOKEN_F16 || out->format == VKB_TOKEN_F32));
+  VKB_REQUIRE(in->wd == out->wd && in->ht == out->ht);
+  if(pc[1]) return vkb_set_error(VKB_ERR_BAD_ARG, "colour: the colour picker input is outside the hot-path scope");
+  colour_digest_t P;
+  colour_lut_t Q;
+  memset(&Q, 0, sizeof(Q));
+  const float *f = (const float *)l->params;
+  const uint32_t *fi = (const uint32_t *)l->params;
+  const int r = colour_digest(f, l->params_size < 242 * 4 ? l->params_size : 242 * 4, &P);
+  if(r) return r;
+  Q.use_clut = pc[0] && fi[225] != 0;
+  Q.have_abney = pc[2] != 0;
+  Q.temp = f[224]; Q.clip_hl = f[231]; Q.gamut_mode = fi[228];
+  if(Q.use_clut)
+  {
+    if(Q.temp < 0.0f) return vkb_set_error(VKB_ERR_BAD_ARG, "colour: an automatic clut temperature (temp <= 0) needs the autotemp node, which is not built: set temp");
+    if(lut_of(l->conn + 2, &Q.clut)) return VKB_ERR_BAD_ARG;
+    VKB_REQUIRE(Q.clut.w / Q.clut.h >= 3);
+  }
+  if(Q.have_abney) { if(lut_of(l->conn + 4, &Q.abney) || lut_of(l->conn + 5, &Q.spectra)) return VKB_ERR_BAD_ARG; }
+  dim3 block(32, 8), grid(vkb_cdiv(out->wd, 32), vkb_cdiv(out->ht, 8));
+  k_colour_lut<<<grid, block, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, out->data, out->format == VKB_TOKEN_F32, P, Q);
+  VKB_CHECK_LAUNCH();
+  return VKB_OK;
+}
+
 static int launch_crop(const vkb_launch_t *l)     { const uint32_t op = PW_CROP;     return launch_chain(l, 1, &op); }
-static int launch_colour(const vkb_launch_t *l)   { const uint32_t op = PW_COLOUR;   return launch_chain(l, 1, &op); }
+static int launch_colour(const vkb_launch_t *l)
+{
+  const int32_t *pc = (const int32_t *)l->push;
+  if(l->push_size >= 12 && l->num_conn >= 6 && (pc[0] || pc[1] || pc[2])) return launch_colour_lut(l);
+  const uint32_t op = PW_COLOUR; return launch_chain(l, 1, &op);
+}
 static int launch_filmcurv(const vkb_launch_t *l) { const uint32_t op = PW_FILMCURV; return launch_chain(l, 1, &op); }
 static int launch_grade(const vkb_launch_t *l)    { const uint32_t op = PW_GRADE;    return launch_chain(l, 1, &op); }
 static int launch_colenc(const vkb_launch_t *l)   { const uint32_t op = PW_COLENC;   return launch_chain(l, 1, &op); }

@@ -123,8 +123,15 @@ void dt_graph_cleanup(dt_graph_t *g)
 }
 
 static inline bool is_node(const dt_node_t *n, const char *name, const char *kernel) { return n->name == dt_token(name) && n->kernel == dt_token(kernel); }
+static inline bool colour_lut_input(const dt_node_t *n, int c)
+{ // (colour, main) connectors 2.. are dummies wired to `input` unless the push constants { have_clut, have_pick, have_abney } say otherwise
+  if(!is_node(n, "colour", "main") || n->push_constant_size < 12) return false;
+  const int32_t *pc = (const int32_t *)n->push_constant;
+  return (c == 2 && pc[0]) || ((c == 4 || c == 5) && pc[2]);
+}
 static inline bool is_pointwise(const dt_node_t *n)
 {
+  if(colour_lut_input(n, 2) || colour_lut_input(n, 4)) return false; // reads luts: a launch of its own (k_colour_lut)
   return is_node(n, "crop", "main") || is_node(n, "colour", "main") || is_node(n, "filmcurv", "main") || is_node(n, "grade", "main") || is_node(n, "colenc", "main");
 }
 static inline uint32_t pw_op(const dt_node_t *n)
@@ -318,7 +325,7 @@ static int build_plan(dt_graph_t *g, bool with_device)
     const dt_node_t *nd = &g->node[n];
     // (a gain map input that is wired to the module's (denoise, gainmap) source node is real)
     const bool real_gainmap = is_node(&g->node[cn->connected.i], "denoise", "gainmap");
-    if((is_node(nd, "colour", "main") && c >= 2) || (!real_gainmap && ((is_node(nd, "denoise", "noop") && c == 2) || (is_node(nd, "denoise", "doub") && c == 4)))) continue;
+    if((is_node(nd, "colour", "main") && c >= 2 && !colour_lut_input(nd, c)) || (!real_gainmap && ((is_node(nd, "denoise", "noop") && c == 2) || (is_node(nd, "denoise", "doub") && c == 4)))) continue;
     B.consumers[{cn->connected.i, cn->connected.c}].push_back({n, c});
   }
   // a module between the graph and an f32 sink that bypassed itself (resize at 1:1): the sink then hangs on an f16 edge.  the
@@ -373,6 +380,12 @@ static int build_plan(dt_graph_t *g, bool with_device)
       s.modid = modid; s.nodeid = n; s.packed_bpp = 0; s.external = 0;
       const vkb_mem_source_t *ms = modid < (int)g->mem_source.size() && g->mem_source[modid].valid ? &g->mem_source[modid] : 0;
       const uint32_t wd = nd->connector[0].roi.wd, ht = nd->connector[0].roi.ht;
+      if(!wd || !ht || dt_module_source_failed(nd->module))
+      { // a file that could not be read (the reference shows a 32x32 placeholder in the gui; an export has nothing to show for it)
+        const std::string who = dt_token_string(nd->module->name) + ":" + dt_token_string(nd->module->inst);
+        delete p;
+        return vkb_set_error(VKB_ERR_IO, "source %s has no image (file missing or unreadable)", who.c_str());
+      }
       if(nd->module->name == dt_token("i-mlv"))
       {
         if(ms) s.packed_bpp = ms->p.packed_bpp;
@@ -425,6 +438,10 @@ static int build_plan(dt_graph_t *g, bool with_device)
       }
       else if(is_node(nd, "denoise", "gainmap"))
       { // the dng gain maps of denoise (denoise/main.c:181-196): a small rgba f32 texture, sampled as it is
+        s.buf_upload = out; s.bytes = conn_bytes(nd->connector);
+      }
+      else if(nd->module->name == dt_token("i-lut"))
+      { // lookup tables are sampled as stored (f16 or f32, 1 / 2 / 4 channels)
         s.buf_upload = out; s.bytes = conn_bytes(nd->connector);
       }
       else if(nd->connector[0].format == dt_token("f32") || (nd->module->num_connectors > 0 && nd->module->connector[0].format == dt_token("f32")))

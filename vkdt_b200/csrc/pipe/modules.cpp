@@ -21,6 +21,7 @@ static const module_def_t g_defs[] = {
   { "i-raw",    "output:source:*:ui16", "filename:string:256:test.cr2\nnoise a:float:1:0.0\nnoise b:float:1:0.0\nstartid:int:1:0" },
   { "i-mlv",    "output:source:rggb:ui16", "filename:string:256:test.mlv" },
   { "i-pfm",    "output:source:rgba:f32", "filename:string:256:test.pfm\nstartid:int:1:0\nnoise a:float:1:0.0\nnoise b:float:1:0.0" },
+  { "i-lut",    "output:source:*:*", "filename:string:256:test.lut" },
   { "denoise",  "input:read:*:*\noutput:write:&input:*",
                 "strength:float:1:0.0\nluma:float:1:0.6\ndetail:float:1:1.0\npad:float:1:0\nedges:float:4:0:0:0:0\ngainmap:int:1:1" },
   { "hilite",   "input:read:*:*\noutput:write:&input:*", "white:float:1:0.985\ndesat:float:1:0.3\nsoft:float:1:0.6" },
@@ -145,6 +146,10 @@ static int  crop_init(dt_module_t *);
 static void crop_roi_in(dt_graph_t *, dt_module_t *);
 static void crop_roi_out(dt_graph_t *, dt_module_t *);
 static void crop_commit(dt_graph_t *, dt_module_t *);
+static int  ilut_init(dt_module_t *);
+static void ilut_cleanup(dt_module_t *);
+static void ilut_roi_out(dt_graph_t *, dt_module_t *);
+static int  ilut_read_source(dt_module_t *, void *, dt_read_source_params_t *);
 static int  colour_init(dt_module_t *);
 static void colour_roi_in(dt_graph_t *, dt_module_t *);
 static void colour_roi_out(dt_graph_t *, dt_module_t *);
@@ -248,6 +253,7 @@ static std::vector<dt_module_so_t> &registry()
     const std::string n = d.name;
     if(n == "i-raw")    { so.init = iraw_init; so.cleanup = iraw_cleanup; so.modify_roi_out = iraw_roi_out; so.read_source = iraw_read_source; }
     if(n == "i-pfm")    { so.init = ipfm_init; so.cleanup = ipfm_cleanup; so.modify_roi_out = ipfm_roi_out; so.read_source = ipfm_read_source; }
+    if(n == "i-lut")    { so.init = ilut_init; so.cleanup = ilut_cleanup; so.modify_roi_out = ilut_roi_out; so.read_source = ilut_read_source; }
     if(n == "i-mlv")    { so.init = imlv_init; so.cleanup = imlv_cleanup; so.modify_roi_out = imlv_roi_out; so.read_source = imlv_read_source; }
     if(n == "denoise")  { so.init = denoise_init; so.cleanup = denoise_cleanup; so.modify_roi_in = denoise_roi_in; so.modify_roi_out = denoise_roi_out;
                           so.create_nodes = denoise_create_nodes; so.read_source = denoise_read_source; }
@@ -488,6 +494,90 @@ static int ipfm_read_source(dt_module_t *mod, void *mapped, dt_read_source_param
     if(fread(row.data(), sizeof(float), row.size(), p->f) != row.size()) return 1;
     float *o = out + (size_t)4 * j * p->width;
     for(uint32_t i = 0; i < p->width; i++) { o[4*i] = row[3*i]; o[4*i+1] = row[3*i+1]; o[4*i+2] = row[3*i+2]; o[4*i+3] = 1.0f; }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// i-lut (i-lut/main.c:23-263, core/lut.h): the small tables colour reads (camera clut, abney, spectra), one .lut file each:
+// { u32 magic 1234, u16 version 2, u8 channels, u8 datatype (0 f16, 1 f32), u32 wd, u32 ht } + texels.  single files only
+// (lists of textures and ssbo payloads belong to other modules' inputs)
+struct ilut_t { std::string filename; FILE *f = 0; uint32_t wd = 0, ht = 0; int channels = 0, datatype = 0; long data_begin = 0; };
+static int ilut_init(dt_module_t *mod) { mod->data = new ilut_t(); return 0; }
+static void ilut_cleanup(dt_module_t *mod)
+{
+  ilut_t *p = (ilut_t *)mod->data;
+  if(p) { if(p->f) fclose(p->f); delete p; }
+  mod->data = 0;
+}
+static std::string ilut_expand(const dt_module_t *mod, const char *pattern)
+{ // ${maker} ${model} ${flen} of the main input (i-lut/main.c:33-37, core/strexpand.h)
+  char flen[16];
+  snprintf(flen, sizeof(flen), "%g", mod->graph->main_img_param.focal_length);
+  const char *key[] = { "${maker}", "${model}", "${flen}" };
+  const char *val[] = { mod->graph->main_img_param.maker, mod->graph->main_img_param.model, flen };
+  std::string out = pattern;
+  for(int k = 0; k < 3; k++)
+    for(size_t pos = out.find(key[k]); pos != std::string::npos; pos = out.find(key[k], pos + strlen(val[k])))
+      out.replace(pos, strlen(key[k]), val[k]);
+  return out;
+}
+static int ilut_read_header(dt_module_t *mod)
+{
+  ilut_t *p = (ilut_t *)mod->data;
+  const std::string fname = ilut_expand(mod, dt_module_param_string(mod, 0));
+  if(p->f && p->filename == fname) return 0;
+  if(p->f) fclose(p->f);
+  p->f = 0; p->filename.clear();
+  std::string path = resource_path(mod, fname.c_str());
+  p->f = fopen(path.c_str(), "rb");
+  if(!p->f && fname[0] != '/' && !basedir().empty()) p->f = fopen((basedir() + "/" + fname).c_str(), "rb"); // dt_graph_open_resource: the installation's data
+  if(!p->f) { fprintf(stderr, "[i-lut] %s could not load file `%s'!\n", dt_token_string(mod->inst).c_str(), fname.c_str()); return 1; }
+  uint8_t h[16];
+  uint32_t magic, wd, ht; uint16_t version;
+  if(fread(h, 1, 16, p->f) != 16) { fclose(p->f); p->f = 0; return 1; }
+  memcpy(&magic, h, 4); memcpy(&version, h + 4, 2); memcpy(&wd, h + 8, 4); memcpy(&ht, h + 12, 4);
+  if(magic != 1234 || version != 2 || !wd || !ht || wd > 65536 || ht > 65536 || h[6] < 1 || h[6] > 4 || h[7] > 1)
+  {
+    fprintf(stderr, "[i-lut] `%s' is not a lut file this path reads (magic %u version %u channels %u datatype %u)\n", fname.c_str(), magic, version, h[6], h[7]);
+    fclose(p->f); p->f = 0; return 1;
+  }
+  p->wd = wd; p->ht = ht; p->channels = h[6]; p->datatype = h[7];
+  p->data_begin = 16;
+  p->filename = fname;
+  return 0;
+}
+static void ilut_roi_out(dt_graph_t *, dt_module_t *mod)
+{
+  if(ilut_read_header(mod)) { mod->connector[0].roi.full_wd = 0; mod->connector[0].roi.full_ht = 0; return; } // no 32x32 placeholder: fail at planning
+  const ilut_t *p = (const ilut_t *)mod->data;
+  mod->connector[0].roi.full_wd = p->wd;
+  mod->connector[0].roi.full_ht = p->ht;
+  mod->connector[0].chan = p->channels == 1 ? dt_token("r") : p->channels == 2 ? dt_token("rg") : dt_token("rgba");
+  mod->connector[0].format = p->datatype == 0 ? dt_token("f16") : dt_token("f32");
+  dt_image_params_t *ip = &mod->img_param;
+  for(int k = 0; k < 4; k++) { ip->black[k] = 0.0f; ip->white[k] = 1.0f; ip->whitebalance[k] = 1.0f; }
+  ip->colour_primaries = 2; ip->colour_trc = 0; ip->filters = 0;
+}
+int dt_module_source_failed(const dt_module_t *mod)
+{ // a file source whose header could not be read (the roi pass keeps such a graph alive with a placeholder size)
+  if(mod->name == dt_token("i-lut") && mod->data) return ((const ilut_t *)mod->data)->f == 0;
+  if(mod->name == dt_token("i-pfm") && mod->data) return ((const ipfm_t *)mod->data)->f == 0;
+  return 0;
+}
+static int ilut_read_source(dt_module_t *mod, void *mapped, dt_read_source_params_t *)
+{ // i-lut/main.c:87-113 (read_plain): three channels are padded to four (the pad is all ones bits there; here a proper 1.0)
+  if(ilut_read_header(mod)) return 1;
+  ilut_t *p = (ilut_t *)mod->data;
+  fseek(p->f, p->data_begin, SEEK_SET);
+  const size_t sz = p->datatype == 0 ? 2 : 4, n = (size_t)p->wd * p->ht;
+  if(p->channels != 3) return fread(mapped, sz * p->channels, n, p->f) == n ? 0 : 1;
+  uint8_t *o = (uint8_t *)mapped;
+  const uint16_t one16 = 0x3c00; const float one32 = 1.0f;
+  for(size_t k = 0; k < n; k++)
+  {
+    if(fread(o + 4 * sz * k, sz, 3, p->f) != 3) return 1;
+    memcpy(o + sz * (4 * k + 3), sz == 2 ? (const void *)&one16 : (const void *)&one32, sz);
   }
   return 0;
 }
@@ -1166,7 +1256,18 @@ static void colour_commit(dt_graph_t *graph, dt_module_t *module)
   f[0] = p_wb[0] / p_wb[1]; f[1] = 1.0f; f[2] = p_wb[2] / p_wb[1];
   f[3] = powf(2.0f, ((float *)module->param)[0]);
   const int off = 4+12+4+12+4*24+4*24;
-  if(p_tmp <= 0.0f) f[off+0] = -1.0f;
+  // three bands identify the legacy clut layout (colour/main.c:268-292)
+  const uint32_t clut_ht = module->connector[2].roi.full_ht;
+  const uint32_t nbands  = clut_ht ? module->connector[2].roi.full_wd / clut_ht : 3;
+  if(p_tmp <= 0.0f) f[off+0] = -1.0f; // as-shot: resolved by the autotemp node in the reference; the kernel here refuses it
+  else if(nbands > 3)
+  { // anchors uniform in mired, 2000 .. 15000 K
+    const float T_lo = 2000.0f, T_hi = 15000.0f;
+    const float m_lo = 1e6f / T_hi, m_hi = 1e6f / T_lo;
+    const float m = 1e6f / (p_tmp < T_lo ? T_lo : p_tmp > T_hi ? T_hi : p_tmp);
+    const float v = (m - m_lo) / (m_hi - m_lo);
+    f[off+0] = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
+  }
   else
   {
     float v = tanf(asinhf(46.3407f + p_tmp)) + (-0.0287128f * cosf(0.000798585f * (714.855f - p_tmp))) + 0.942275f;
@@ -1209,10 +1310,12 @@ static void colour_commit(dt_graph_t *graph, dt_module_t *module)
   else i[16] = i[17] = i[18] = i[19] = 0;
 }
 static void colour_create_nodes(dt_graph_t *graph, dt_module_t *module)
-{ // colour/main.c:416-465 with have_clut = have_pick = have_abney = 0 (lut inputs are outside the hot path)
-  for(int k = 2; k <= 5; k++) if(dt_connected(module->connector + k))
-    fprintf(stderr, "[vkdt_b200] colour: lut/picker inputs are ignored (outside the hot path)\n");
-  const int pc[] = { 0, 0, 0 };
+{ // colour/main.c:416-465.  the colour picker input and the autotemp / sink pair that turns `temp:0` into an as-shot
+  // temperature are not part of the path: a connected picker is ignored, temp <= 0 with a clut fails at launch
+  const int have_clut = dt_connected(module->connector + 2);
+  const int have_abney = dt_connected(module->connector + 4) && dt_connected(module->connector + 5);
+  if(dt_connected(module->connector + 3)) fprintf(stderr, "[vkdt_b200] colour: the colour picker input is ignored (outside the hot path)\n");
+  const int pc[] = { have_clut, 0, have_abney };
   const int nodeid = dt_node_add(graph, module, "colour", "main", module->connector[0].roi.wd, module->connector[0].roi.ht, 1, sizeof(pc), pc, 7,
       "input",   "read",  "rgba", "f16", dt_no_roi,
       "output",  "write", "rgba", "f16", &module->connector[0].roi,
@@ -1223,7 +1326,11 @@ static void colour_create_nodes(dt_graph_t *graph, dt_module_t *module)
       "autotemp", "read", "y",    "f32", dt_no_roi);
   dt_connector_copy(graph, module, 0, nodeid, 0);
   dt_connector_copy(graph, module, 1, nodeid, 1);
-  for(int k = 2; k <= 6; k++) dt_connector_copy(graph, module, 0, nodeid, k); // dummies
+  dt_connector_copy(graph, module, have_clut ? 2 : 0, nodeid, 2);
+  dt_connector_copy(graph, module, 0, nodeid, 3);
+  dt_connector_copy(graph, module, have_abney ? 4 : 0, nodeid, 4);
+  dt_connector_copy(graph, module, have_abney ? 5 : 0, nodeid, 5);
+  dt_connector_copy(graph, module, 0, nodeid, 6);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -77,6 +77,8 @@ static inline int dt_connected(const dt_connector_t *c)
   return c->connected.i > 0;
 }
 // connector.h:281-301
+struct dt_module_t;
+int dt_module_source_failed(const dt_module_t *mod); // modules.cpp: a file source without a readable file
 static inline int dt_connector_channels(const dt_connector_t *c)
 {
   if(c->chan == dt_token("ssbo") || c->chan == dt_token("rggb") || c->chan == dt_token("rgbx")) return 1;
