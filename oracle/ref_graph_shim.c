@@ -47,7 +47,7 @@ void dt_raytrace_graph_cleanup(dt_graph_t *graph) {}
   void M##_ref_create_nodes(dt_graph_t *, dt_module_t *); void M##_ref_modify_roi_out(dt_graph_t *, dt_module_t *); \
   void M##_ref_modify_roi_in(dt_graph_t *, dt_module_t *); int M##_ref_init(dt_module_t *); void M##_ref_cleanup(dt_module_t *); \
   void M##_ref_commit_params(dt_graph_t *, dt_module_t *);
-REF_DECL(imlv) REF_DECL(ipfm) REF_DECL(denoise) REF_DECL(hilite) REF_DECL(demosaic) REF_DECL(llap) REF_DECL(filmcurv) REF_DECL(crop) REF_DECL(colour) REF_DECL(resize)
+REF_DECL(imlv) REF_DECL(ipfm) REF_DECL(ilut) REF_DECL(denoise) REF_DECL(hilite) REF_DECL(demosaic) REF_DECL(llap) REF_DECL(filmcurv) REF_DECL(crop) REF_DECL(colour) REF_DECL(resize)
 
 static const ref_nodes_in_t *ref_src; /* what the stand-in source hands over */
 static void src_modify_roi_out(dt_graph_t *graph, dt_module_t *mod)
@@ -76,7 +76,7 @@ static int ref_pipe_init(const char *basedir)
     snprintf(dt_pipe.basedir, sizeof(dt_pipe.basedir), "%s", basedir);
     snprintf(dt_pipe.homedir, sizeof(dt_pipe.homedir), "/nonexistent");
     static const char *names[] = { "i-raw", "denoise", "hilite", "demosaic", "colour", "filmcurv", "llap", "grade", "hist", "zones", "crop", "lens", "pick",
-      "display", "o-pfm", "colenc", "resize", "i-mlv", "contrast", "i-pfm", 0 };
+      "display", "o-pfm", "colenc", "resize", "i-mlv", "contrast", "i-pfm", "i-lut", 0 };
     int n = 0; while(names[n]) n++;
     dt_pipe.module = malloc(sizeof(dt_module_so_t) * n);
     int i = 0;
@@ -92,6 +92,7 @@ static int ref_pipe_init(const char *basedir)
     { dt_module_so_t *so = so_get("colour"); if(!so) return -10; so->modify_roi_out = colour_ref_modify_roi_out; so->modify_roi_in = colour_ref_modify_roi_in; so->init = colour_ref_init; so->commit_params = colour_ref_commit_params; so->create_nodes = colour_ref_create_nodes; }
     { dt_module_so_t *so = so_get("i-raw"); if(!so) return -10; so->modify_roi_out = src_modify_roi_out; }
     { dt_module_so_t *so = so_get("i-pfm"); if(!so) return -10; so->init = ipfm_ref_init; so->cleanup = ipfm_ref_cleanup; so->modify_roi_out = ipfm_ref_modify_roi_out; }
+    { dt_module_so_t *so = so_get("i-lut"); if(!so) return -10; so->init = ilut_ref_init; so->cleanup = ilut_ref_cleanup; so->modify_roi_out = ilut_ref_modify_roi_out; }
     { dt_module_so_t *so = so_get("i-mlv"); if(!so) return -10; so->init = imlv_ref_init; so->cleanup = imlv_ref_cleanup; so->modify_roi_out = imlv_ref_modify_roi_out; }
     inited = 1;
   }

@@ -251,6 +251,22 @@ def write_golden_pfm():
     return fn, cfg
 
 
+LUT_LINES = ["module:i-lut:abney", "module:i-lut:spectra", "param:i-lut:abney:filename:%(dir)s/abney.lut", "param:i-lut:spectra:filename:%(dir)s/spectra.lut",
+             "connect:i-lut:abney:output:colour:01:abney", "connect:i-lut:spectra:output:colour:01:spectra", "param:colour:01:gamut:2", "param:colour:01:sat:1.2"]
+
+
+def write_golden_luts():
+    """abney (rg f16) and spectra (rgba f32) tables of the shapes the reference's tools write (core/lut.h), synthetic content"""
+    import struct
+    os.makedirs(MLV_DIR, exist_ok=True)
+    rng = np.random.default_rng(4)
+    for name, a in (("abney", rng.uniform(0.25, 0.4, (40, 64, 2)).astype(np.float16)), ("spectra", rng.uniform(0.1, 1.0, (48, 48, 4)).astype(np.float32))):
+        with open(os.path.join(MLV_DIR, name + ".lut"), "wb") as f:
+            f.write(struct.pack("<IHBBII", 1234, 2, a.shape[2], 0 if a.dtype == np.float16 else 1, a.shape[1], a.shape[0]))
+            f.write(a.tobytes())
+    return [ln % dict(dir=MLV_DIR) for ln in LUT_LINES]
+
+
 def graph_goldens():
     """the module pass of the REFERENCE's own graph code over its own bin/default-darkroom.i-raw (oracle/ref_graph_shim.c: global.c,
     module.c, graph-io.c, connector.c, graph-export.c, graph-run-modules.h and the seven module main.c files compiled in place; only
@@ -269,6 +285,9 @@ def graph_goldens():
     # i-pfm (the reference's own i-pfm/main.c reading the header) in front of colour and filmcurv
     fn, cfg = write_golden_pfm()
     cases.append(dict(lines=[], w=64, h=40, raw={}, pfm=1, text=O.ref_graph_describe(64, 40, [], {}, cfg=cfg)))
+    # the reference's own i-lut/main.c reading two tables into colour's abney / spectra connectors
+    lines = write_golden_luts()
+    cases.append(dict(lines=lines, w=640, h=480, raw={}, luts=1, text=O.ref_graph_describe(640, 480, lines, {})))
     with gzip.GzipFile(os.path.join(HERE, "host_graph.json.gz"), "wb", mtime=0) as f:
         f.write(json.dumps(cases, indent=0).encode())
     print("graph goldens:", len(cases), "graphs,", sum(c["text"].count("\n") for c in cases), "lines")

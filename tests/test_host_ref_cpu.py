@@ -234,6 +234,8 @@ def _graph_text_product(case):
         for ln in case["lines"]:
             assert g.line(ln) == 0, ln
         return g.describe().splitlines()
+    if "luts" in case:
+        _make_golden_module().write_golden_luts()                # same tables, same path as when the golden was made
     mw = mh = 0
     for ln in case["lines"]:    # "#export:max:<w>:<h>": the cli's --width / --height (a resize module in front of the sink)
         if ln.startswith("#export:max:"):
@@ -270,7 +272,7 @@ def test_product_module_pass_matches_reference_graph_code():
         assert len(ref) == len(got), (case["lines"], case["w"], case["h"], len(ref), len(got))
         bad = [(a[:200], b[:200]) for a, b in zip(ref, got) if a != b]
         assert not bad, (case["lines"], case["w"], case["h"], bad[:3])
-    assert len(GRAPHS) >= 31 and sum("mlv" in c for c in GRAPHS) == 2 and sum("pfm" in c for c in GRAPHS) == 1
+    assert len(GRAPHS) >= 32 and sum("mlv" in c for c in GRAPHS) == 2 and sum("pfm" in c for c in GRAPHS) == 1 and sum("luts" in c for c in GRAPHS) == 1
     assert sum(any(l.startswith("#export:max") for l in c["lines"]) for c in GRAPHS) == 4 and sum(any(l.startswith("feedback:") for l in c["lines"]) for c in GRAPHS) == 2
 
 
