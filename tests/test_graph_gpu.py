@@ -25,9 +25,10 @@ def _oracle_cfg(O, w, h, llap=True, grade=True, strength=0.0, noise=(1.0, 1.0)):
     return d
 
 
-def _run_graph(gpu, raw, src="i-raw", packed=False, extra=(), noise=(1.0, 1.0)):
+def _run_graph(gpu, raw, src="i-raw", packed=False, extra=(), noise=(1.0, 1.0), cfg_tail=()):
+    """extra: config lines after the graph exists (its display is the o-pfm sink by then); cfg_tail: lines of the cfg itself"""
     h, w = raw.shape
-    g = gpu.Graph(cfg_text=gpu.DARKROOM_CFG.format(src=src))
+    g = gpu.Graph(cfg_text=gpu.DARKROOM_CFG.format(src=src) + "".join(l + "\n" for l in cfg_tail))
     for l in extra:
         assert g.line(l) == 0, l
     if packed:
@@ -711,4 +712,72 @@ def test_export_with_a_size_limit(gpu, oracle, limit):
     g.run(gpu.RUN_RECORD | gpu.RUN_UPLOAD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT)
     plan = g.plan_text() if hasattr(g, "plan_text") else ""
     assert np.array_equal(out[..., :3], want[..., :3]), (limit, float(np.abs(out[..., :3] - want[..., :3]).max()), plan)
+    g.close()
+
+
+def test_two_grade_instances_keep_their_own_parameters(gpu, oracle):
+    """grade:01 -> grade:02 with different settings: a fused pointwise launch has one parameter slot per module type, so the
+    second instance must become a launch of its own (the chain stops growing at a repeated type)."""
+    w, h = 512, 384
+    raw = synth.mosaic(w, h, seed=51)
+    d = _oracle_cfg(oracle, w, h)
+    _set(d, "grade.gain", (1.2, 1.0, 0.9, 0.0)); _set(d, "grade.lift", (0.02, 0.0, 0.01, 0.0))
+    first = oracle.darkroom_run(d, raw)
+    mid = first.astype(np.float16).astype(np.float32)     # the edge between the two instances is f16
+    mid[..., 3] = 1.0
+    gp = oracle.GradeParams((C.c_float * 4)(0.0, 0.01, 0.0, 0.0), (C.c_float * 4)(0.9, 1.1, 1.0, 0.0), (C.c_float * 4)(0.8, 1.0, 1.3, 0.0),
+                            (C.c_float * 4)(0.0, 0.0, 0.02, 0.0), 0, 0.3, 0.4)
+    want, wi = oracle.new_img(mid.shape[0], mid.shape[1], 4)
+    oracle.lib().o_grade_main(C.byref(oracle.img(mid)), C.byref(wi), C.byref(gp), 0)
+    extra = ("param:grade:01:gain:1.2:1.0:0.9:0", "param:grade:01:lift:0.02:0.0:0.01:0", "module:grade:02",
+             "param:grade:02:lift:0.0:0.01:0.0:0", "param:grade:02:gamma:0.9:1.1:1.0:0", "param:grade:02:gain:0.8:1.0:1.3:0", "param:grade:02:offset:0.0:0.0:0.02:0",
+             "connect:grade:01:output:grade:02:input", "connect:grade:02:output:display:main:input")
+    got, g = _run_graph(gpu, raw, cfg_tail=extra)
+    plan = g.plan()
+    assert "grade+grade" not in plan, plan
+    parity_gate(got[..., :3], want[..., :3], "grade:01 -> grade:02")
+    # and it is not what one grade with the second instance's parameters would give
+    assert np.abs(got[..., :3] - first[..., :3]).max() > 1e-2
+    g.close()
+
+
+@pytest.mark.parametrize("src", ["i-raw", "i-pfm"])
+def test_rerun_without_upload_after_a_parameter_change(gpu, tmp_path, src):
+    """RUN_RECORD | RUN_DOWNLOAD | RUN_WAIT without RUN_UPLOAD_SOURCE (what a parameter change asks for, graph.h's run flags): the
+    source pixels of the first run must still be there — upload buffers are never recycled by the pool (the reference keeps source
+    connectors protected for the same reason, graph-run-nodes-allocate.h:959-963)."""
+    w, h = 512, 384
+    def graph(lines):
+        if src == "i-raw":
+            raw = synth.mosaic(w, h, seed=61)
+            g = gpu.Graph(cfg_text=gpu.DARKROOM_CFG.format(src="i-raw"))
+            g._keep = raw
+            for ln in lines: assert g.line(ln) == 0, ln
+            g.set_source(raw.ctypes.data, gpu.raw_params(w, h, wb=WB, cam_to_rec2020=CAM))
+        else:
+            fn = str(tmp_path / "mid.pfm")
+            synth.write_pfm(fn, np.random.default_rng(7).random((h, w, 3), dtype=np.float32))
+            g = gpu.Graph(cfg_text=TAIL_CFG)
+            assert g.line("param:i-pfm:main:filename:%s" % fn) == 0
+            for ln in lines: assert g.line(ln) == 0, ln
+        return g
+    def develop(g, flags):
+        g.set_sink_buffer(None, 0)
+        g.run()
+        ow, oh = g.sink_size()
+        out = np.zeros((oh, ow, 4), dtype=np.float32)
+        g.set_sink_buffer(out.ctypes.data, out.nbytes)
+        g.run(flags)
+        return out
+    change = "param:filmcurv:01:light:2.0"
+    g = graph([change])
+    want = develop(g, gpu.RUN_RECORD | gpu.RUN_UPLOAD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT)
+    g.close()
+    g = graph([])
+    before = develop(g, gpu.RUN_RECORD | gpu.RUN_UPLOAD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT).copy()
+    assert g.line(change) == 0
+    out = np.zeros_like(before)
+    g.set_sink_buffer(out.ctypes.data, out.nbytes)
+    g.run(gpu.RUN_RECORD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT)
+    assert not np.array_equal(out, before) and np.array_equal(out, want)
     g.close()
