@@ -325,6 +325,36 @@ static void process_clut(const oimg_t *clut, const float *f, float auto_temp, fl
   rgb[0] = rbx * L * b; rgb[1] = (1.0f - rbx - rby) * L * b; rgb[2] = rby * L * b;
 }
 
+/* colour/atemp-impl.glsl:57-87 (autotemp.comp, one invocation): where between the clut's temperature anchors the as-shot white
+ * balance comes out neutral; -1 if the committed temperature is explicit.  have_pick = 0 */
+float o_colour_autotemp(const oimg_t *clut, const float *f)
+{
+  if(f[224] >= 0.0f) return -1.0f;
+  const int nbands = clut->w / clut->h;
+  const int n = (nbands * 2) / 3;
+  const float neutral[3] = { 1.0f / o_max(f[232], 1e-6f), 1.0f, 1.0f / o_max(f[234], 1e-6f) };
+  const float nb = o_max(neutral[0] + neutral[1] + neutral[2], 1e-6f);
+  float ntc[2] = { neutral[0] / nb, neutral[2] / nb };
+  tri2quad(ntc);
+  const float target = 1.0f / 3.0f;
+  float prev[2], next[2];
+  clut_chroma(clut, ntc, 0, nbands, prev);
+  float best_bp = 0.0f, best_res = 1e30f;
+  for(int k = 0; k < n - 1; k++)
+  {
+    clut_chroma(clut, ntc, k + 1, nbands, next);
+    const float dv[2] = { next[0] - prev[0], next[1] - prev[1] };
+    const float denom = dv[0] * dv[0] + dv[1] * dv[1];
+    const float m = denom > 1e-12f ? ((target - prev[0]) * dv[0] + (target - prev[1]) * dv[1]) / denom : 0.0f;
+    const float mc = o_clamp(m, 0.0f, 1.0f);
+    const float ex = target - (prev[0] + mc * dv[0]), ey = target - (prev[1] + mc * dv[1]);
+    const float res = sqrtf(ex * ex + ey * ey);
+    if(res < best_res) { best_res = res; best_bp = (float)k + mc; }
+    prev[0] = next[0]; prev[1] = next[1];
+  }
+  return best_bp / (float)(n - 1 > 1 ? n - 1 : 1);
+}
+
 /* colour/main-impl.glsl:200-341.  clut / (abney and spectra) may be null: have_clut = 0 / have_abney = 0; have_pick = 0 always
  * (the colour picker is not part of the path).  auto_temp: what the autotemp node would deliver, read if the committed
  * temperature is negative */

@@ -217,7 +217,9 @@ int o_darkroom_run(const o_darkroom_t *d, const uint16_t *raw, float *out, int s
       fcol[224] = o_clamp((m - m_lo) / (m_hi - m_lo), 0.0f, 1.0f);
     }
   }
-  o_colour_main_lut(&crp, &col, fcol, 1, o_lut_clut, o_lut_abney, o_lut_spectra, 0.0f);
+  /* temp <= 0: the autotemp node's answer for this frame (colour/main.c:425-441; its write-back into the parameter is a gui matter) */
+  const float auto_temp = (o_lut_clut && fcol[224] < 0.0f) ? o_colour_autotemp(o_lut_clut, fcol) : 0.0f;
+  o_colour_main_lut(&crp, &col, fcol, 1, o_lut_clut, o_lut_abney, o_lut_spectra, auto_temp);
   o_img_free(&crp);
   if(stage == 5) { copy_out(&col, stage_out); o_img_free(&col); return 0; }
 

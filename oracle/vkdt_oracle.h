@@ -75,6 +75,7 @@ void o_sample_catmull_rom(const oimg_t *tex, float u, float v, float *res);
 void o_colour_commit(const o_colour_params_t *p, float *p_wb, const float *img_wb, const float *img_cam_to_rec2020,
     int img_primaries, int img_trc, float *f);
 void o_colour_main(const oimg_t *in, oimg_t *out, const float *f, int out_f16);
+float o_colour_autotemp(const oimg_t *clut, const float *f);
 /* with the lut inputs (clut: rg; abney: rg; spectra: rgba; any of them null = not connected) */
 void o_colour_main_lut(const oimg_t *in, oimg_t *out, const float *f, int out_f16, const oimg_t *clut, const oimg_t *abney, const oimg_t *spectra, float auto_temp);
 void o_xyY_to_dt_UCS_JCH(const float *xyY, float L_white, float *JCH);

@@ -1,6 +1,6 @@
 """colour's lut inputs end to end: `i-lut` modules (i-lut/main.c, core/lut.h) wired to colour's clut / abney /
-spectra connectors (colour/main.c:416-465), the temperature anchor blend of colour/main.c:268-292, the (colour, main) launch with
-its seven connectors.  the per pixel arithmetic is pinned against the reference's shader in tests/test_shader_ref_cpu.py; here
+spectra connectors (colour/main.c:416-465), the temperature anchor blend of colour/main.c:268-292 or the autotemp node's as-shot
+answer (atemp-impl.glsl), the (colour, main) launch with its seven connectors.  the per pixel arithmetic is pinned against the reference's shader in tests/test_shader_ref_cpu.py; here
 the planner's wiring on the host and the developed frame against the oracle on the GPU.  the tables are synthetic (the
 reference's own are made by its offline tools from measured camera data and do not come with a checkout)."""
 import ctypes as C
@@ -55,6 +55,7 @@ def test_planner_wires_the_luts_as_sources(tmp_path):
     plan = g.plan()
     col = [ln for ln in plan.splitlines() if "colour_main" in ln]
     assert len(col) == 1, plan                     # a launch of its own: the fused pointwise chain does not read luts
+    assert plan.count("launch 21 colour_autotemp ") == 1 and ":1x1x1x1:f32" in col[0]   # the as-shot temperature node comes with a clut
     assert ":192x32x2x1:f16" in col[0] and ":64x40x2x1:f16" in col[0] and ":48x48x4x1:f32" in col[0], col[0]
     assert plan.count("source i-lut") == 3 and "source i-lut bytes %d" % spectra.nbytes in plan
     g.close()
@@ -86,6 +87,7 @@ CASES = {
     "abney-rec2020":  (("abney", "spectra"), 3, ["param:colour:01:gamut:2", "param:colour:01:sat:1.3"], [("colour.gamut", 2), ("colour.sat", 1.3)]),
     "abney-locus":    (("abney", "spectra"), 3, ["param:colour:01:gamut:1"], [("colour.gamut", 1)]),
     "clut-legacy":    (("clut",), 3, ["param:colour:01:matrix:4", "param:colour:01:temp:4500"], [("colour.matrix", 4), ("colour.temp", 4500.0)]),
+    "clut-as-shot":   (("clut",), 6, ["param:colour:01:matrix:4", "param:colour:01:temp:0"], [("colour.matrix", 4), ("colour.temp", 0.0)]),
     "clut-anchors":   (("clut", "abney", "spectra"), 6, ["param:colour:01:matrix:4", "param:colour:01:temp:5200", "param:colour:01:gamut:3", "param:colour:01:sat:0.8"],
                        [("colour.matrix", 4), ("colour.temp", 5200.0), ("colour.gamut", 3), ("colour.sat", 0.8)]),
 }
@@ -121,16 +123,28 @@ def test_luts_end_to_end(gpu, oracle, tmp_path, name):
 
 
 @pytest.mark.gpu
-def test_an_as_shot_clut_temperature_is_refused(gpu, tmp_path):
-    """temp <= 0 asks for the autotemp node (colour/main.c:425-441), which is not built: the launch says so instead of guessing"""
-    clut, spectra, abney = synthetic_luts(np.random.default_rng(6), 3)
-    write_lut(tmp_path / "clut.lut", clut)
-    g = gpu.Graph(cfg_text=gpu.DARKROOM_CFG.format(src="i-raw"))
-    for ln in lut_lines(str(tmp_path), ("clut",)) + ["param:colour:01:matrix:4", "param:colour:01:temp:0"]:
-        assert g.line(ln) == 0, ln
-    raw = synth.mosaic(512, 384, seed=3)
-    g.set_source(raw.ctypes.data, gpu.raw_params(512, 384, wb=WB, cam_to_rec2020=CAM))
-    g.set_sink_buffer(None, 0)
-    with pytest.raises(gpu.VkbError, match="autotemp"):
-        g.run()
-    g.close()
+@pytest.mark.parametrize("nbands", [3, 6, 9])
+def test_autotemp_kernel(gpu, oracle, nbands):
+    """(colour, autotemp) on its own: clut, 1x1 f32 answer, picked (a dummy) against the restatement of atemp-impl.glsl"""
+    import torch
+    from helpers import to_dev_f16
+    O = oracle
+    clut, _s, _a = synthetic_luts(np.random.default_rng(8 + nbands), nbands)
+    clut = clut.astype(np.float32)
+    for b in range(nbands):
+        clut[:, b * 32:(b + 1) * 32, 0] += np.float32(0.04 * b - 0.1)
+    clut = np.ascontiguousarray(clut.astype(np.float16).astype(np.float32))
+    O.lib().o_colour_autotemp.restype = C.c_float
+    for temp, wb in ((0.0, (2.1, 1.0, 1.6)), (0.0, (1.3, 1.0, 2.4)), (5000.0, (2.1, 1.0, 1.6))):
+        d = O.darkroom_defaults(64, 64)
+        d.colour.temp, d.colour.matrix = temp, 4
+        for k in range(3): d.whitebalance[k] = wb[k]
+        f = np.zeros(242, dtype=np.float32)
+        O.lib().o_colour_commit(C.byref(d.colour), (C.c_float * 4)(*d.colour.white), d.whitebalance, d.cam_to_rec2020, 0, 0, O.fptr(f))
+        want = O.lib().o_colour_autotemp(C.byref(O.img(clut)), O.fptr(f))
+        d_clut, d_out = to_dev_f16(clut), torch.zeros(1, dtype=torch.float32, device="cuda")
+        i_clut = gpu.image(d_clut, clut.shape[1], clut.shape[0], 2, "f16")
+        gpu.dispatch("colour", "autotemp", [i_clut, gpu.image(d_out, 1, 1, 1, "f32"), i_clut], np.zeros(1, np.int32).tobytes(), f.tobytes())
+        got = float(d_out.cpu()[0])
+        assert got == want, (nbands, temp, wb, got, want)
+        assert (temp > 0) == (want == -1.0)

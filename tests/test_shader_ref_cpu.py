@@ -300,6 +300,29 @@ def cases(O):
                                                                (abney if use_abney else a, 0), (spectra if use_abney else a, 0), (a, 0)], 96, 64)
             return [want], [got]
 
+    for nbands in (3, 6, 9):
+        @add("colour.autotemp %d bands" % nbands)
+        def _(nbands=nbands):
+            rng = np.random.default_rng(680 + nbands)
+            clut, _s, _a = luts(rng, nbands)
+            # chroma anchors that walk across the neutral point, so that the best segment is an inner one
+            for b in range(nbands if nbands > 3 else 3):
+                clut[:, b * 32:(b + 1) * 32, 0] += f16(np.float32(0.05 * b - 0.1))
+            clut = f16(clut)
+            res_o, res_s = [], []
+            for temp, wb in ((-1.0, (2.1, 1.0, 1.6)), (-1.0, (1.3, 1.0, 2.4)), (5000.0, (2.1, 1.0, 1.6))):
+                d = O.darkroom_defaults(64, 64)
+                d.colour.temp, d.colour.matrix = temp, 4
+                f, _wb = O.colour_commit_oracle(bytes(d.colour), list(wb) + [1.0], [0.8, 0.15, 0.05, 0.1, 0.85, 0.05, 0.02, 0.18, 0.8], 0, 0)
+                f = np.ascontiguousarray(f, np.float32)
+                L.o_colour_autotemp.restype = C.c_float
+                want = np.full((1, 1), L.o_colour_autotemp(C.byref(O.img(clut)), O.fptr(f)), np.float32)
+                got = np.zeros((1, 1), np.float32)
+                O.ref_shader("colour", "autotemp", f.tobytes(), np.zeros(1, np.int32).tobytes(), [(clut, 0), (got, 0), (clut, 0)], 1, 1)
+                res_o.append(want)
+                res_s.append(got)
+            return res_o, res_s
+
     for k, (rot, crop, ori) in enumerate(((1337.0, (1.0, 3.0, 3.0, 7.0), 0), (90.0, (0.1, 0.9, 0.2, 0.8), 0), (7.5, (0.1, 0.9, 0.2, 0.8), 0), (1337.0, (1.0, 3.0, 3.0, 7.0), 6))):
         @add("crop.main set %d" % k)
         def _(k=k, rot=rot, crop=crop, ori=ori):

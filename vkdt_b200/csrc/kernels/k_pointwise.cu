@@ -576,12 +576,14 @@ struct colour_lut_t
   int use_clut, have_abney;
   float temp, clip_hl;
   uint32_t gamut_mode;
+  const float *auto_temp;   // the autotemp node's 1x1 answer, read when the committed temperature is negative
 };
 __global__ void __launch_bounds__(256) k_colour_lut(const uint2 *__restrict__ in, int w, int h, void *__restrict__ outv, int out_f32, const colour_digest_t P, const colour_lut_t Q)
 {
   const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
   if(x >= w || y >= h) return;
   const float4 px = ld_rgba(in, w, x, y);
+  const float temp = Q.temp < 0.0f && Q.auto_temp ? __ldg(Q.auto_temp) : Q.temp;
   colour_digest_t noP = P;     // cat16 on its own: the lut delivers rec2020
   noP.has_P = 0;
   f3 c = { px.x, px.y, px.z }, o;
@@ -593,10 +595,10 @@ __global__ void __launch_bounds__(256) k_colour_lut(const uint2 *__restrict__ in
   }
   else
   {
-    o = colour_matrices(process_clut(Q.clut, Q.temp, c), noP);
+    o = colour_matrices(process_clut(Q.clut, temp, c), noP);
     if(Q.clip_hl > 0.0f)
     { // main-impl.glsl:245 assigns the converted clip colour to the PIXEL and leaves the clip colour as it was: followed to the letter
-      o = process_clut(Q.clut, Q.temp, { Q.clip_hl, Q.clip_hl, Q.clip_hl });
+      o = process_clut(Q.clut, temp, { Q.clip_hl, Q.clip_hl, Q.clip_hl });
       const f3 cl = colour_matrices({ Q.clip_hl, Q.clip_hl, Q.clip_hl }, noP);
       const float t = fminf(cl.x, fminf(cl.y, cl.z));
       o.x = fminf(o.x, t); o.y = fminf(o.y, t); o.z = fminf(o.z, t);
@@ -693,13 +695,64 @@ static int launch_colour_lut(const vkb_launch_t *l)
   Q.temp = f[224]; Q.clip_hl = f[231]; Q.gamut_mode = fi[228];
   if(Q.use_clut)
   {
-    if(Q.temp < 0.0f) return vkb_set_error(VKB_ERR_BAD_ARG, "colour: an automatic clut temperature (temp <= 0) needs the autotemp node, which is not built: set temp");
+    if(Q.temp < 0.0f)
+    { // as shot: the (colour, autotemp) node's answer on connector 6
+      const vkb_image_t *at = l->num_conn >= 7 ? l->conn + 6 : 0;
+      if(!at || !at->data || at->format != VKB_TOKEN_F32 || at->wd != 1 || at->ht != 1 || at->chan != 1)
+        return vkb_set_error(VKB_ERR_BAD_ARG, "colour: an as-shot clut temperature (temp <= 0) needs the autotemp node's 1x1 f32 image on connector 6");
+      Q.auto_temp = (const float *)at->data;
+    }
     if(lut_of(l->conn + 2, &Q.clut)) return VKB_ERR_BAD_ARG;
     VKB_REQUIRE(Q.clut.w / Q.clut.h >= 3);
   }
   if(Q.have_abney) { if(lut_of(l->conn + 4, &Q.abney) || lut_of(l->conn + 5, &Q.spectra)) return VKB_ERR_BAD_ARG; }
   dim3 block(32, 8), grid(vkb_cdiv(out->wd, 32), vkb_cdiv(out->ht, 8));
   k_colour_lut<<<grid, block, 0, l->stream>>>((const uint2 *)in->data, in->wd, in->ht, out->data, out->format == VKB_TOKEN_F32, P, Q);
+  VKB_CHECK_LAUNCH();
+  return VKB_OK;
+}
+
+// (colour, autotemp) (colour/atemp-impl.glsl:57-87, one invocation): the position between the clut's temperature anchors at which
+// the as-shot white balance comes out neutral; -1 when the committed temperature is explicit.  connectors: clut, temp (1x1 f32), picked
+__global__ void k_colour_autotemp(const lut_t clut, float *__restrict__ out, float temp, float awb_r, float awb_b)
+{
+  if(threadIdx.x || blockIdx.x) return;
+  if(temp >= 0.0f) { out[0] = -1.0f; return; }
+  const int nbands = clut.w / clut.h;
+  const int n = (nbands * 2) / 3;
+  const float nr = 1.0f / fmaxf(awb_r, 1e-6f), nbl = 1.0f / fmaxf(awb_b, 1e-6f);
+  const float nb = fmaxf(nr + 1.0f + nbl, 1e-6f);
+  float tx = nr / nb, ty = nbl / nb;
+  tri2quad(tx, ty);
+  const float target = 1.0f / 3.0f;
+  float2 prev = clut_chroma(clut, tx, ty, 0, nbands);
+  float best_bp = 0.0f, best_res = 1e30f;
+  for(int k = 0; k < n - 1; k++)
+  {
+    const float2 next = clut_chroma(clut, tx, ty, k + 1, nbands);
+    const float dx = next.x - prev.x, dy = next.y - prev.y;
+    const float denom = dx * dx + dy * dy;
+    const float m = denom > 1e-12f ? ((target - prev.x) * dx + (target - prev.y) * dy) / denom : 0.0f;
+    const float mc = clampf(m, 0.0f, 1.0f);
+    const float ex = target - (prev.x + mc * dx), ey = target - (prev.y + mc * dy);
+    const float res = sqrtf(ex * ex + ey * ey);
+    if(res < best_res) { best_res = res; best_bp = (float)k + mc; }
+    prev = next;
+  }
+  out[0] = best_bp / (float)max(n - 1, 1);
+}
+static int launch_colour_autotemp(const vkb_launch_t *l)
+{
+  VKB_REQUIRE(l->num_conn >= 2 && l->params_size >= 236 * 4);
+  const int32_t *pc = (const int32_t *)l->push;
+  if(l->push_size >= 4 && pc[0]) return vkb_set_error(VKB_ERR_BAD_ARG, "colour: the colour picker input is outside the hot-path scope");
+  const vkb_image_t *out = l->conn + 1;
+  VKB_REQUIRE(out->data && out->format == VKB_TOKEN_F32 && out->wd == 1 && out->ht == 1 && out->chan == 1);
+  lut_t clut;
+  if(lut_of(l->conn, &clut)) return VKB_ERR_BAD_ARG;
+  VKB_REQUIRE(clut.w / clut.h >= 3);
+  const float *f = (const float *)l->params;
+  k_colour_autotemp<<<1, 32, 0, l->stream>>>(clut, (float *)out->data, f[224], f[232], f[234]);
   VKB_CHECK_LAUNCH();
   return VKB_OK;
 }
@@ -723,6 +776,7 @@ static int launch_pointw(const vkb_launch_t *l)
 }
 VKB_REGISTER("crop", "main", launch_crop);
 VKB_REGISTER("colour", "main", launch_colour);
+VKB_REGISTER("colour", "autotemp", launch_colour_autotemp);
 VKB_REGISTER("filmcurv", "main", launch_filmcurv);
 VKB_REGISTER("grade", "main", launch_grade);
 VKB_REGISTER("colenc", "main", launch_colenc);

@@ -127,7 +127,7 @@ static inline bool colour_lut_input(const dt_node_t *n, int c)
 { // (colour, main) connectors 2.. are dummies wired to `input` unless the push constants { have_clut, have_pick, have_abney } say otherwise
   if(!is_node(n, "colour", "main") || n->push_constant_size < 12) return false;
   const int32_t *pc = (const int32_t *)n->push_constant;
-  return (c == 2 && pc[0]) || ((c == 4 || c == 5) && pc[2]);
+  return ((c == 2 || c == 6) && pc[0]) || ((c == 4 || c == 5) && pc[2]);   // 6: the autotemp node's answer, there with a clut
 }
 static inline bool is_pointwise(const dt_node_t *n)
 {
@@ -325,7 +325,7 @@ static int build_plan(dt_graph_t *g, bool with_device)
     const dt_node_t *nd = &g->node[n];
     // (a gain map input that is wired to the module's (denoise, gainmap) source node is real)
     const bool real_gainmap = is_node(&g->node[cn->connected.i], "denoise", "gainmap");
-    if((is_node(nd, "colour", "main") && c >= 2 && !colour_lut_input(nd, c)) || (!real_gainmap && ((is_node(nd, "denoise", "noop") && c == 2) || (is_node(nd, "denoise", "doub") && c == 4)))) continue;
+    if((is_node(nd, "colour", "main") && c >= 2 && !colour_lut_input(nd, c)) || (is_node(nd, "colour", "autotemp") && c == 2) || (!real_gainmap && ((is_node(nd, "denoise", "noop") && c == 2) || (is_node(nd, "denoise", "doub") && c == 4)))) continue;
     B.consumers[{cn->connected.i, cn->connected.c}].push_back({n, c});
   }
   // a module between the graph and an f32 sink that bypassed itself (resize at 1:1): the sink then hangs on an f16 edge.  the

@@ -1310,12 +1310,27 @@ static void colour_commit(dt_graph_t *graph, dt_module_t *module)
   else i[16] = i[17] = i[18] = i[19] = 0;
 }
 static void colour_create_nodes(dt_graph_t *graph, dt_module_t *module)
-{ // colour/main.c:416-465.  the colour picker input and the autotemp / sink pair that turns `temp:0` into an as-shot
-  // temperature are not part of the path: a connected picker is ignored, temp <= 0 with a clut fails at launch
+{ // colour/main.c:416-465.  the colour picker input is not part of the path (a connected picker is ignored).  of the autotemp /
+  // sink pair behind a clut the autotemp node is there: with temp <= 0 every run blends the clut's anchors where the as-shot
+  // white balance comes out neutral, like the reference's first run; the sink that writes this back into the parameter as
+  // an editable temperature (write_sink, :395-413) is a gui matter and is left out
   const int have_clut = dt_connected(module->connector + 2);
   const int have_abney = dt_connected(module->connector + 4) && dt_connected(module->connector + 5);
   if(dt_connected(module->connector + 3)) fprintf(stderr, "[vkdt_b200] colour: the colour picker input is ignored (outside the hot path)\n");
   const int pc[] = { have_clut, 0, have_abney };
+  int id_auto = -1;
+  if(have_clut)
+  {
+    const int pc_auto[] = { 0 };
+    dt_roi_t tiny = module->connector[0].roi;
+    tiny.wd = tiny.ht = tiny.full_wd = tiny.full_ht = 1;
+    id_auto = dt_node_add(graph, module, "colour", "autotemp", 1, 1, 1, sizeof(pc_auto), pc_auto, 3,
+        "clut",   "read",  "rg", "f16", dt_no_roi,
+        "temp",   "write", "y",  "f32", &tiny,
+        "picked", "read",  "r",  "f16", dt_no_roi);
+    dt_connector_copy(graph, module, 2, id_auto, 0);
+    dt_connector_copy(graph, module, 0, id_auto, 2); // dummy
+  }
   const int nodeid = dt_node_add(graph, module, "colour", "main", module->connector[0].roi.wd, module->connector[0].roi.ht, 1, sizeof(pc), pc, 7,
       "input",   "read",  "rgba", "f16", dt_no_roi,
       "output",  "write", "rgba", "f16", &module->connector[0].roi,
@@ -1330,7 +1345,8 @@ static void colour_create_nodes(dt_graph_t *graph, dt_module_t *module)
   dt_connector_copy(graph, module, 0, nodeid, 3);
   dt_connector_copy(graph, module, have_abney ? 4 : 0, nodeid, 4);
   dt_connector_copy(graph, module, have_abney ? 5 : 0, nodeid, 5);
-  dt_connector_copy(graph, module, 0, nodeid, 6);
+  if(id_auto >= 0) dt_node_connect(graph, id_auto, 1, nodeid, 6);
+  else             dt_connector_copy(graph, module, 0, nodeid, 6);
 }
 
 // ------------------------------------------------------------------------------------------------
