@@ -781,3 +781,28 @@ def test_rerun_without_upload_after_a_parameter_change(gpu, tmp_path, src):
     g.run(gpu.RUN_RECORD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT)
     assert not np.array_equal(out, before) and np.array_equal(out, want)
     g.close()
+
+
+def test_an_f32_sink_edge_with_a_second_reader(gpu):
+    """the export pushes the sink's f32 onto the image it hangs on (graph-export.c:88-91); when another module reads that image
+    too (here: filmcurv -> o-pfm:main and filmcurv -> grade -> o-null:aux) that reader gets an f16 copy, and the main sink
+    receives exactly what it receives without the side branch."""
+    w, h = 512, 384
+    raw = synth.mosaic(w, h, seed=71)
+    base = gpu.DARKROOM_CFG.format(src="i-raw").replace("connect:grade:01:output:display:main:input", "connect:filmcurv:01:output:display:main:input") \
+        .replace("connect:filmcurv:01:output:llap:01:input\n", "").replace("connect:llap:01:output:grade:01:input", "connect:filmcurv:01:output:grade:01:input")
+    outs = []
+    for tail in ("", "module:o-null:aux\nconnect:grade:01:output:o-null:aux:input\n"):
+        g = gpu.Graph(cfg_text=base + tail)
+        g.set_source(raw.ctypes.data, gpu.raw_params(w, h, wb=WB, cam_to_rec2020=CAM))
+        g.set_sink_buffer(None, 0)
+        g.run()
+        ow, oh = g.sink_size()
+        out = np.zeros((oh, ow, 4), dtype=np.float32)
+        g.set_sink_buffer(out.ctypes.data, out.nbytes)
+        g.run(gpu.RUN_RECORD | gpu.RUN_UPLOAD | gpu.RUN_DOWNLOAD | gpu.RUN_WAIT)
+        assert ("cvt16" in g.plan()) == bool(tail) and ("grade_main" in g.plan()) == bool(tail)
+        outs.append(out)
+        g.close()
+    assert np.isfinite(outs[0][..., :3]).all() and outs[0][..., :3].max() > 0.1
+    assert np.array_equal(outs[0], outs[1])

@@ -155,6 +155,7 @@ struct builder_t
   std::vector<int> order;                       // reachable nodes, topological
   std::vector<uint8_t> reach, consumed;
   std::map<std::pair<int,int>, std::vector<std::pair<int,int>>> consumers; // (node, out conn) -> [(node, in conn)]
+  std::map<std::pair<int,int>, plan_img_t> converted;                      // (node, out conn) -> its f16 copy, see img_in
 
   int out_buf(int n, int c)
   { // buffer of an owner connector, created on demand
@@ -181,6 +182,30 @@ struct builder_t
     const dt_cid_t src = g->node[n].connector[c].connected;
     if(src.i < 0 || src.i >= (int)g->node.size() || src.c < 0) return plan_img_t{ -1, 0, 0, 1, 1, dt_token("f16") };
     plan_img_t im = img_out(src.i, src.c);
+    // an rgba image that became f32 because an f32 sink hangs on it (dt_graph_replace_display pushes the sink's format onto
+    // its producer, graph-export.c:88-91) and that ANOTHER module reads as well: the reference samples it as it is, the
+    // kernels of this path read f16 edges.  the other reader gets a converted copy (what the edge held before the sink came)
+    if(im.format == dt_token("f32") && im.chan == 4 && im.layers == 1 && g->node[n].connector[0].type != dt_token("sink") &&
+       g->node[src.i].connector[0].type != dt_token("source"))
+    {
+      auto it = converted.find({src.i, src.c});
+      if(it == converted.end())
+      {
+        plan_buf_t b;
+        b.bytes = (((size_t)im.wd * im.ht * 4 * 2 + 255) / 256) * 256 + 256;
+        p->buf.push_back(b);
+        plan_img_t cv = im;
+        cv.buf = (int)p->buf.size() - 1; cv.format = dt_token("f16");
+        plan_launch_t l;
+        l.name = dt_token("b200"); l.kernel = dt_token("cvt16"); l.wd = im.wd; l.ht = im.ht; l.dp = 1;
+        l.conn.push_back(im);
+        l.conn.push_back(cv);
+        l.label = dt_token_string(g->node[src.i].module->name) + " b200_cvt16 (f32 -> f16 for a second reader)";
+        add_launch(l);
+        it = converted.insert({{src.i, src.c}, cv}).first;
+      }
+      return it->second;
+    }
     // feedback inputs cross the frame wires (graph-run-nodes-allocate.h:222-229): they see what the owner wrote one frame ago
     if((g->node[n].connector[c].flags & s_conn_feedback) && p->buf[im.buf].frames == 2) im.fb = 1;
     return im;
