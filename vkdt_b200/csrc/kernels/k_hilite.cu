@@ -171,16 +171,23 @@ __global__ void __launch_bounds__(256) k_hilite_doub(const __half *__restrict__ 
   const int x = blockIdx.x * 32 + threadIdx.x, y = BAND_BY * 8 + threadIdx.y;
   const int bw = xtrans ? ow / 3 : ow / 2, bh = xtrans ? oh / 3 : oh / 2;
   if(x >= bw || y >= bh || BAND_SKIP(y)) return;
-  float4 upsm = ld_rgba_clamp(coarse, cw, ch, x, y);
   const float softw = 0.97f * white;
+  // the reconstructed colour only enters a block whose brightest site is above the soft threshold (doub.comp:88, :113): every
+  // other block is copied, and neither the coarse texel nor the three exponentials and four quotients behind `scale` are needed
   if(xtrans)
   {
-    if(((x + y) & 1) == 0) { const float t = upsm.x; upsm.x = upsm.z; upsm.z = t; }
     float c[9];
 #pragma unroll
     for(int i = 0; i < 3; i++)
 #pragma unroll
       for(int j = 0; j < 3; j++) c[3 * i + j] = ld_h_clamp(in, iw, ih, 3 * x + i, 3 * y + j);
+    const float maxr = fmaxf(c[1], c[7]), maxb = fmaxf(c[3], c[5]);
+    const float maxg = fmaxf(fmaxf(fmaxf(c[0], c[2]), c[4]), fmaxf(c[6], c[8]));
+    const float maxrgb = fmaxf(maxr, fmaxf(maxg, maxb));
+    if(maxrgb > softw)
+    {
+    float4 upsm = ld_rgba_clamp(coarse, cw, ch, x, y);
+    if(((x + y) & 1) == 0) { const float t = upsm.x; upsm.x = upsm.z; upsm.z = t; }
     const float minr = fminf(c[1], c[7]), minb = fminf(c[3], c[5]);
     const float ming = fminf(fminf(fminf(c[0], c[2]), c[4]), fminf(c[6], c[8]));
     const float sr = div_g(minr, fmaxf(0.001f, upsm.x));
@@ -190,10 +197,6 @@ __global__ void __launch_bounds__(256) k_hilite_doub(const __half *__restrict__ 
     const float wg = m_exp(upsm.y - fmaxf(upsm.x, upsm.z));
     const float wb = m_exp(upsm.z - fmaxf(upsm.x, upsm.y));
     const float scale = div_g(sr * wr + sg * wg + sb * wb, wr + wg + wb);
-    const float maxr = fmaxf(c[1], c[7]), maxb = fmaxf(c[3], c[5]);
-    const float maxg = fmaxf(fmaxf(fmaxf(c[0], c[2]), c[4]), fmaxf(c[6], c[8]));
-    const float maxrgb = fmaxf(maxr, fmaxf(maxg, maxb));
-    if(maxrgb > softw)
     {
       float t = smoothstepf(softw, white, maxrgb);
       c[1] = mixf(c[1], upsm.x * scale, t); c[7] = mixf(c[7], upsm.x * scale, t);
@@ -202,6 +205,7 @@ __global__ void __launch_bounds__(256) k_hilite_doub(const __half *__restrict__ 
       c[0] = mixf(c[0], upsm.y * scale, t); c[2] = mixf(c[2], upsm.y * scale, t);
       c[4] = mixf(c[4], upsm.y * scale, t); c[6] = mixf(c[6], upsm.y * scale, t);
       c[8] = mixf(c[8], upsm.y * scale, t);
+    }
     }
 #pragma unroll
     for(int i = 0; i < 3; i++)
@@ -213,6 +217,10 @@ __global__ void __launch_bounds__(256) k_hilite_doub(const __half *__restrict__ 
   {
     const int x0 = mirror1(2 * x, iw), x1 = mirror1(2 * x + 1, iw), y0 = mirror1(2 * y, ih), y1 = mirror1(2 * y + 1, ih);
     float c[4] = { ld_h(in, iw, x0, y1), ld_h(in, iw, x1, y1), ld_h(in, iw, x1, y0), ld_h(in, iw, x0, y0) };
+    const float maxrgb = fmaxf(fmaxf(c[0], c[1]), fmaxf(c[2], c[3]));
+    if(maxrgb > softw)
+    {
+    const float4 upsm = ld_rgba_clamp(coarse, cw, ch, x, y);
     const float ming = fminf(c[0], c[2]);
     const float sr = div_g(c[3], fmaxf(0.001f, upsm.x));
     const float sg = div_g(ming, fmaxf(0.001f, upsm.y));
@@ -221,12 +229,9 @@ __global__ void __launch_bounds__(256) k_hilite_doub(const __half *__restrict__ 
     const float wg = m_exp(upsm.y - fmaxf(upsm.x, upsm.z));
     const float wb = m_exp(upsm.z - fmaxf(upsm.x, upsm.y));
     const float scale = div_g(sr * wr + sg * wg + sb * wb, wr + wg + wb);
-    const float maxrgb = fmaxf(fmaxf(c[0], c[1]), fmaxf(c[2], c[3]));
-    if(maxrgb > softw)
-    {
-      const float t = smoothstepf(softw, white, maxrgb);
-      c[0] = mixf(c[0], scale * upsm.y, t); c[1] = mixf(c[1], scale * upsm.z, t);
-      c[2] = mixf(c[2], scale * upsm.y, t); c[3] = mixf(c[3], scale * upsm.x, t);
+    const float t = smoothstepf(softw, white, maxrgb);
+    c[0] = mixf(c[0], scale * upsm.y, t); c[1] = mixf(c[1], scale * upsm.z, t);
+    c[2] = mixf(c[2], scale * upsm.y, t); c[3] = mixf(c[3], scale * upsm.x, t);
     }
     // two texels per row -> one 4 byte store each
     const __half2 top = __floats2half2_rn(c[3], c[2]), bot = __floats2half2_rn(c[0], c[1]);

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256, 6) k_llap_reduce0(const uint2 *__restrict
 
 // ---- reduce of coarse levels: one thread per output pixel, all layers: the nine mirrored offsets are formed once and
 // serve every plane (the per layer version spent four fifths of its instructions on them) ----
-__global__ void __launch_bounds__(256) k_llap_reduce(const __half *__restrict__ in, int iw, int ih,
+__global__ void __launch_bounds__(256, 4) k_llap_reduce(const __half *__restrict__ in, int iw, int ih,
     __half *__restrict__ out, int ow, int oh, int layers, const band_t bd)
 {
   const int x = blockIdx.x * 32 + threadIdx.x, y = BAND_BY * 8 + threadIdx.y;
@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(256) k_llap_reduce(const __half *__restrict__ 
   const size_t iplane = (size_t)iw * ih, oplane = (size_t)ow * oh;
   const __half *src = in;
   __half *dst = out + (size_t)y * ow + x;
+#pragma unroll 2
   for(int g = 0; g < layers; g++, src += iplane, dst += oplane)
   {
     float t[3][3];
