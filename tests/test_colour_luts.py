@@ -66,13 +66,18 @@ def test_planner_wires_the_luts_as_sources(tmp_path):
     g.close()
 
 
-@pytest.mark.parametrize("what", ["missing", "magic", "version", "short"])
+@pytest.mark.parametrize("what", ["missing", "magic", "version", "short", "truncated", "huge"])
 def test_a_lut_that_cannot_be_read_fails_the_plan(tmp_path, what):
     clut, spectra, abney = synthetic_luts(np.random.default_rng(2), 3)
     write_lut(tmp_path / "abney.lut", abney)
     if what == "magic": write_lut(tmp_path / "spectra.lut", spectra, magic=4321)
     elif what == "version": write_lut(tmp_path / "spectra.lut", spectra, version=1)
     elif what == "short": open(tmp_path / "spectra.lut", "wb").write(b"\xd2\x04\0\0\x02\0")
+    elif what == "truncated":
+        write_lut(tmp_path / "spectra.lut", spectra)
+        blob = open(tmp_path / "spectra.lut", "rb").read()
+        open(tmp_path / "spectra.lut", "wb").write(blob[:len(blob) // 2])
+    elif what == "huge": open(tmp_path / "spectra.lut", "wb").write(struct.pack("<IHBBII", 1234, 2, 4, 1, 60000, 60000) + b"\0" * 64)
     g = api.Graph(cfg_text=api.DARKROOM_CFG.format(src="i-raw"))
     for ln in lut_lines(str(tmp_path), ("abney", "spectra")):
         assert g.line(ln) == 0, ln

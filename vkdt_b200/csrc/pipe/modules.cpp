@@ -542,6 +542,16 @@ static int ilut_read_header(dt_module_t *mod)
     fprintf(stderr, "[i-lut] `%s' is not a lut file this path reads (magic %u version %u channels %u datatype %u)\n", fname.c_str(), magic, version, h[6], h[7]);
     fclose(p->f); p->f = 0; return 1;
   }
+  { // the payload the header promises has to be there (a truncated or hostile file must not size a buffer)
+    fseek(p->f, 0, SEEK_END);
+    const long have = ftell(p->f);
+    const uint64_t need = 16 + (uint64_t)wd * ht * h[6] * (h[7] == 0 ? 2 : 4);
+    if(have < 0 || (uint64_t)have < need)
+    {
+      fprintf(stderr, "[i-lut] `%s' is truncated: %ld bytes, its header asks for %llu\n", fname.c_str(), have, (unsigned long long)need);
+      fclose(p->f); p->f = 0; return 1;
+    }
+  }
   p->wd = wd; p->ht = ht; p->channels = h[6]; p->datatype = h[7];
   p->data_begin = 16;
   p->filename = fname;
