@@ -255,7 +255,10 @@ LUT_LINES = ["module:i-lut:abney", "module:i-lut:spectra", "param:i-lut:abney:fi
              "connect:i-lut:abney:output:colour:01:abney", "connect:i-lut:spectra:output:colour:01:spectra", "param:colour:01:gamut:2", "param:colour:01:sat:1.2"]
 
 
-def write_golden_luts():
+CLUT_LINES = ["module:i-lut:clut", "param:i-lut:clut:filename:%(dir)s/clut.lut", "connect:i-lut:clut:output:colour:01:clut", "param:colour:01:matrix:4", "param:colour:01:temp:5200"]
+
+
+def write_golden_luts(clut=False):
     """abney (rg f16) and spectra (rgba f32) tables of the shapes the reference's tools write (core/lut.h), synthetic content"""
     import struct
     os.makedirs(MLV_DIR, exist_ok=True)
@@ -264,7 +267,12 @@ def write_golden_luts():
         with open(os.path.join(MLV_DIR, name + ".lut"), "wb") as f:
             f.write(struct.pack("<IHBBII", 1234, 2, a.shape[2], 0 if a.dtype == np.float16 else 1, a.shape[1], a.shape[0]))
             f.write(a.tobytes())
-    return [ln % dict(dir=MLV_DIR) for ln in LUT_LINES]
+    if clut:
+        a = rng.uniform(0.2, 0.45, (32, 192, 2)).astype(np.float16)          # six bands: four temperature anchors
+        with open(os.path.join(MLV_DIR, "clut.lut"), "wb") as f:
+            f.write(struct.pack("<IHBBII", 1234, 2, 2, 0, 192, 32))
+            f.write(a.tobytes())
+    return [ln % dict(dir=MLV_DIR) for ln in LUT_LINES + (CLUT_LINES if clut else [])]
 
 
 def graph_goldens():
@@ -288,6 +296,8 @@ def graph_goldens():
     # the reference's own i-lut/main.c reading two tables into colour's abney / spectra connectors
     lines = write_golden_luts()
     cases.append(dict(lines=lines, w=640, h=480, raw={}, luts=1, text=O.ref_graph_describe(640, 480, lines, {})))
+    lines = write_golden_luts(clut=True)    # with a clut the reference adds its autotemp node and a sink that feeds the gui
+    cases.append(dict(lines=lines, w=640, h=480, raw={}, luts=2, text=O.ref_graph_describe(640, 480, lines, {})))
     with gzip.GzipFile(os.path.join(HERE, "host_graph.json.gz"), "wb", mtime=0) as f:
         f.write(json.dumps(cases, indent=0).encode())
     print("graph goldens:", len(cases), "graphs,", sum(c["text"].count("\n") for c in cases), "lines")

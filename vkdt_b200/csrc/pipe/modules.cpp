@@ -1332,8 +1332,8 @@ static void colour_create_nodes(dt_graph_t *graph, dt_module_t *module)
   if(have_clut)
   {
     const int pc_auto[] = { 0 };
-    dt_roi_t tiny = module->connector[0].roi;
-    tiny.wd = tiny.ht = tiny.full_wd = tiny.full_ht = 1;
+    dt_roi_t tiny = {};
+    tiny.wd = tiny.ht = 1;    // colour/main.c:427: only the extent is set
     id_auto = dt_node_add(graph, module, "colour", "autotemp", 1, 1, 1, sizeof(pc_auto), pc_auto, 3,
         "clut",   "read",  "rg", "f16", dt_no_roi,
         "temp",   "write", "y",  "f32", &tiny,
