@@ -5,6 +5,7 @@ oracle/_ref/libmlvref.so (the reference's own MLV decoder compiled in place).  O
 __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
 """
 import ctypes as C
+import struct
 import os
 import subprocess
 import numpy as np
@@ -406,6 +407,13 @@ def ref_pipeline_run(text, raw, trace=None):
         if n["name"] == "i-raw:main" or n["name"] == "i-mlv:main":
             n["conn"][0]["buf"] = [unorm]
             return
+        if n["name"] == "i-lut:main":                # the table the module's filename parameter names (core/lut.h), as stored
+            fn = m["params"].split(b"\0", 1)[0].decode()
+            with open(fn, "rb") as f:
+                magic, version, chan, dtype, lw, lh = struct.unpack("<IHBBII", f.read(16))
+                a = np.frombuffer(f.read(), dtype=np.float16 if dtype == 0 else np.float32, count=lw * lh * chan)
+            n["conn"][0]["buf"] = [np.ascontiguousarray(a.astype(np.float32).reshape(lh, lw, chan))]
+            return
         binds, first_input = [], None
         for c in n["conn"]:
             if c["type"] in ("write",):
@@ -418,7 +426,18 @@ def ref_pipeline_run(text, raw, trace=None):
                 run(mi, m["nodes"][k])
                 src = m["nodes"][k]["conn"][cc]["buf"]
             elif c["link"].startswith("mod.") and m["mconn"][int(c["link"][4:])]["name"] == "input":
-                pm, pn, pc = module_output(mi - 1)
+                prev = mi - 1
+                while mods[prev]["name"] == "i-lut":  # side inputs sit anywhere before their reader in the execution order
+                    prev -= 1
+                pm, pn, pc = module_output(prev)
+                run(pm, pn)
+                src = pc["buf"]
+            elif c["link"].startswith("mod.") and m["mconn"][int(c["link"][4:])]["name"] in ("clut", "abney", "spectra"):
+                # a lut connector that is wired: the i-lut module whose file carries the connector's name (the tests' convention)
+                want = m["mconn"][int(c["link"][4:])]["name"].encode() + b".lut"
+                lm = [k for k, x in enumerate(mods) if x["name"] == "i-lut" and want in x["params"].split(b"\0", 1)[0]]
+                assert len(lm) == 1, (want, lm)
+                pm, pn, pc = module_output(lm[0])
                 run(pm, pn)
                 src = pc["buf"]
             if src is None:                       # unconnected lut / gainmap inputs: the reference binds a dummy (graph-run-nodes-allocate.h)

@@ -115,6 +115,45 @@ def test_reference_pipeline_variants_live(oracle, k):
     check("variant %d" % k, ref, oracle.darkroom_run(d, raw)[..., :3])
 
 
+LUT_CASES = {  # name: (tables wired to colour, clut bands, config lines, the same settings on the oracle's struct)
+    "abney rec2020": (("abney", "spectra"), 3, ["param:colour:01:gamut:2", "param:colour:01:sat:1.3"], lambda d: (setattr(d.colour, "gamut", 2), setattr(d.colour, "sat", 1.3))),
+    "clut anchors":  (("clut", "abney", "spectra"), 6, ["param:colour:01:matrix:4", "param:colour:01:temp:5200", "param:colour:01:gamut:3"],
+                      lambda d: (setattr(d.colour, "matrix", 4), setattr(d.colour, "temp", 5200.0), setattr(d.colour, "gamut", 3))),
+    "clut as shot":  (("clut",), 6, ["param:colour:01:matrix:4", "param:colour:01:temp:0"], lambda d: (setattr(d.colour, "matrix", 4), setattr(d.colour, "temp", 0.0))),
+}
+
+
+@pytest.mark.parametrize("name", sorted(LUT_CASES))
+def test_reference_pipeline_with_luts_live(oracle, tmp_path, name):
+    """colour's lut inputs end to end: the reference's own i-lut/main.c reads the tables, its colour/main.c wires the clut / abney /
+    spectra connectors and the autotemp node, its shaders sample them; the oracle gets the same tables through o_set_colour_luts."""
+    if oracle.ref_shader_lib() is None or oracle.ref_host_lib() is None or not os.path.isdir("/root/reference/src/pipe/modules"):
+        pytest.skip("needs oracle/_ref/lib{host,shader}ref.so and /root/reference (make -C oracle ref)")
+    import ctypes as C
+    from test_colour_luts import synthetic_luts, write_lut, lut_lines
+    which, nbands, lines, setup = LUT_CASES[name]
+    w, h = 240, 180
+    clut, spectra, abney = synthetic_luts(np.random.default_rng(5), nbands)
+    write_lut(tmp_path / "clut.lut", clut); write_lut(tmp_path / "abney.lut", abney); write_lut(tmp_path / "spectra.lut", spectra)
+    raw = synth.mosaic(w, h, seed=5)
+    text = oracle.ref_graph_describe(w, h, lut_lines(str(tmp_path), which) + lines, dict(wb=WB, noise_a=NOISE[0], noise_b=NOISE[1]))
+    assert ("colour:autotemp" in text) == ("clut" in which)
+    ref = oracle.ref_pipeline_run(text, raw)[..., :3]
+    d = oracle.darkroom_defaults(w, h)
+    for c, v in enumerate(WB):
+        d.whitebalance[c] = v
+    d.noise_a, d.noise_b = NOISE
+    d.enable_grade = 1
+    setup(d)
+    imgs = {"clut": oracle.img(clut.astype(np.float32)), "abney": oracle.img(abney.astype(np.float32)), "spectra": oracle.img(spectra)}
+    oracle.lib().o_set_colour_luts(*[C.byref(imgs[k]) if k in which else None for k in ("clut", "abney", "spectra")])
+    try:
+        want = oracle.darkroom_run(d, raw)[..., :3]
+    finally:
+        oracle.lib().o_set_colour_luts(None, None, None)
+    print(name, "max abs %.3g, psnr %.1f dB" % check("luts " + name, ref, want))
+
+
 def test_reference_mlv_pipeline_live(oracle, tmp_path):
     """bin/default-darkroom.i-mlv with the reference's own i-mlv/main.c reading the clip header (image parameters incl. the camera
     matrix for a camera outside dcraw's table: xyz_to_rec2020) against the oracle configured the way tests/test_graph_gpu.py
