@@ -95,6 +95,8 @@ VARIANTS = [  # (width, height, config lines, the same settings on the oracle's 
     (240, 180, ["param:colour:01:exposure:0.7", "param:filmcurv:01:colour:1", "param:filmcurv:01:light:2.0", "param:llap:01:clarity:0.5"],
      lambda d: (setattr(d.colour, "exposure", 0.7), setattr(d.filmcurv, "colour", 1), setattr(d.filmcurv, "light", 2.0), setattr(d.llap, "clarity", 0.5))),
     (240, 180, ["param:demosaic:01:method:2"], lambda d: setattr(d.demosaic, "method", 2)),       # half size demosaic + resample
+    (240, 180, ["param:filmcurv:01:colour:2"], lambda d: setattr(d.filmcurv, "colour", 2)),       # tone curve along munsell hue lines
+    (240, 180, ["param:filmcurv:01:colour:0", "param:colour:01:sat:1.2"], lambda d: (setattr(d.filmcurv, "colour", 0), setattr(d.colour, "sat", 1.2))),
 ]
 
 
