@@ -6,7 +6,8 @@
 The shader is read where it lies under /root/reference; the output goes to oracle/_ref/ (git-ignored), never into the repo.
 What happens to the source: `#version` / `#extension` lines dropped, includes and `#if` resolved by cpp, interface blocks
 (`layout(...) uniform`) become plain structs / image_t globals bound by the entry point below, `out` / `inout` parameters become
-references, array constructors become brace lists, floating literals get an `f` (a GLSL literal is fp32), and functions that
+references, array constructors become brace lists, expressions of two floating literals are folded in double (what glslang's
+constant folding does: 0.18 + 0.01 is ONE fp32 constant), floating literals get an `f` (a GLSL literal is fp32), and functions that
 main() never reaches are left out (so that a shader only needs the parts of shared.glsl it uses to compile).  the function
 bodies - the arithmetic - are untouched."""
 import os
@@ -93,6 +94,57 @@ def std140(members):
     return res, off
 
 
+FLIT = r"(?:\d+\.\d*|\.\d+)(?:[eE][-+]?\d+)?|\d+[eE][-+]?\d+"
+
+
+def fold_literals(code):
+    """glslang folds constant expressions in double and rounds the result to fp32 once (1.0/2.2, 0.18 + 0.01): do the same for
+    expressions of two floating literals, where operator precedence allows it, before the literals get their `f`."""
+    mul = re.compile(r"(?<![\w.])(%s)\s*([*/])\s*(%s)(?![\w.])" % (FLIT, FLIT))
+    add = re.compile(r"(?<![\w.])(%s)\s*([-+])\s*(%s)(?![\w.])" % (FLIT, FLIT))
+
+    def prev_char(code, i):
+        while i > 0 and code[i - 1].isspace():
+            i -= 1
+        return code[i - 1] if i > 0 else "("
+
+    def next_char(code, i):
+        while i < len(code) and code[i].isspace():
+            i += 1
+        return code[i] if i < len(code) else ";"
+
+    changed = True
+    while changed:
+        changed = False
+        for pat, is_mul in ((mul, True), (add, False)):
+            pos = 0
+            while True:
+                m = pat.search(code, pos)
+                if not m:
+                    break
+                before, after = prev_char(code, m.start()), next_char(code, m.end())
+                ok = before not in "*/" if is_mul else (before in "(,=?:<>[{" and after not in "*/")
+                if is_mul and before in "-+" and prev_char(code, m.start() - 1 - (len(code[:m.start()]) - len(code[:m.start()].rstrip()))) in "eE":
+                    ok = False
+                if not ok:
+                    pos = m.end()
+                    continue
+                a, b = float(m.group(1)), float(m.group(3))
+                v = {"*": a * b, "/": a / b if b != 0.0 else None, "+": a + b, "-": a - b}[m.group(2)]
+                if v is None:
+                    pos = m.end()
+                    continue
+                lit = repr(v)
+                if "." not in lit and "e" not in lit and "inf" not in lit and "nan" not in lit:
+                    lit += ".0"
+                if v < 0:
+                    lit = "(" + lit + ")"
+                code = code[:m.start()] + lit + code[m.end():]
+                changed = True
+                pos = m.start() + len(lit)
+    return code
+
+
 def fix_body(code):
     code = re.sub(r"\b(?:in\s+)?(?:inout|out)\s+(\w+)\s+(\w+)", r"\1 &\2", code)           # out / inout parameters
     while True:                                                                                # array constructors: float[](a, b) -> {a, b}
@@ -105,6 +157,7 @@ def fix_body(code):
             j += 1
         code = code[:m.start()] + "{" + code[m.end():j - 1] + "}" + code[j:]
     code = code.replace("^^", "!=")                                                          # logical xor of two bools
+    code = fold_literals(code)
     code = re.sub(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][-+]?\d+)?|\d+[eE][-+]?\d+)(?![\w.])", r"\1f", code)   # fp32 literals
     code = re.sub(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][-+]?\d+)?)[lL][fF]\b", r"\1f", code)
     return code

@@ -138,7 +138,8 @@ static const float M_camgamut_to_xyz[8][9] = {
 };
 static int camgamut_index(uint32_t prim) { return prim == 8 ? 0 : prim == 9 ? 1 : prim >= 11 && prim <= 16 ? (int)prim - 9 : -1; }
 
-/* camera log curves to scene linear (shared/oetf.glsl:2-38), every operation in fp32 as written there.
+/* camera log curves to scene linear (shared/oetf.glsl:2-38), every operation in fp32 as written there; expressions of literals
+ * alone are constants that glslang folds in double and rounds once ((float)(0.18 + 0.01), not 0.18f + 0.01f).
  * glsl's mix(a, b, cond) with a bvec selects: both sides are evaluated, b is taken where cond holds */
 static float decode_log(float x, uint32_t trc)
 {
@@ -147,15 +148,15 @@ static float decode_log(float x, uint32_t trc)
     case 7:  return x > 0.02740668f ? exp2f(x / 0.07329248f - 7.0f) - 0.0075f : x / 10.44426855f;                      /* davinci intermediate */
     case 8:  return x < 0.075f ? (x - 0.075f) / 16.184376489665897f : expf((x - 0.5520126568606655f) / 0.09232902596577353f) - 0.0057048244042473785f; /* filmlight t-log */
     case 9:  return x <= 0.155251141552511f ? (x - 0.0729055341958355f) / 10.5402377416545f : exp2f(x * 17.52f - 9.72f);   /* aces cct */
-    case 10: return x < 5.367655f * 0.010591f + 0.092809f ? (x - 0.092809f) / 5.367655f : (powf(10.0f, (x - 0.385537f) / 0.247190f) - 0.052272f) / 5.555556f; /* arri logC3 */
+    case 10: return x < (float)(5.367655 * 0.010591 + 0.092809) ? (x - 0.092809f) / 5.367655f : (powf(10.0f, (x - 0.385537f) / 0.247190f) - 0.052272f) / 5.555556f; /* arri logC3 */
     case 11: return x < -0.7774983977293537f ? x * 0.3033266726886969f - 0.7774983977293537f
                   : (exp2f(14.0f * (x - 0.09286412512218964f) / 0.9071358748778103f + 6.0f) - 64.0f) / 2231.8263090676883f;  /* arri logC4 */
     case 12: return x < 0.0f ? (x / 15.1927f) - 0.01f : (powf(10.0f, x / 0.224282f) - 1.0f) / 155.975327f - 0.01f;       /* red log3G10 */
     case 13: return x < 0.181f ? (x - 0.125f) / 5.6f : powf(10.0f, (x - 0.598206f) / 0.241514f) - 0.00873f;              /* panasonic v-log */
-    case 14: return x < 171.2102946929f / 1023.0f ? (x * 1023.0f - 95.0f) * 0.01125f / (171.2102946929f - 95.0f)
-                  : powf(10.0f, (x * 1023.0f - 420.0f) / 261.5f) * (0.18f + 0.01f) - 0.01f;                                /* sony s-log3 */
+    case 14: return x < (float)(171.2102946929 / 1023.0) ? (x * 1023.0f - 95.0f) * 0.01125f / (float)(171.2102946929 - 95.0)
+                  : powf(10.0f, (x * 1023.0f - 420.0f) / 261.5f) * (float)(0.18 + 0.01) - 0.01f;                                /* sony s-log3 */
     case 15: return x < 0.100686685370811f ? (x - 0.092864f) / 8.799461f
-                  : powf(10.0f, (x - 0.384316f) / 0.245281f) / 5.555556f - 0.064829f / 5.555556f;                          /* fuji f-log2 */
+                  : powf(10.0f, (x - 0.384316f) / 0.245281f) / 5.555556f - (float)(0.064829 / 5.555556);                          /* fuji f-log2 */
     default: return x;
   }
 }

@@ -167,17 +167,17 @@ static float host_decode_log_f(float x, uint32_t trc)
     case 7:  if(x > 0.02740668f) { t = x / 0.07329248f; t = t - 7.0f; t = exp2f(t); t = t - 0.0075f; return t; } t = x / 10.44426855f; return t;
     case 8:  if(x < 0.075f) { t = x - 0.075f; t = t / 16.184376489665897f; return t; } t = x - 0.5520126568606655f; t = t / 0.09232902596577353f; t = expf(t); t = t - 0.0057048244042473785f; return t;
     case 9:  if(x <= 0.155251141552511f) { t = x - 0.0729055341958355f; t = t / 10.5402377416545f; return t; } t = x * 17.52f; t = t - 9.72f; t = exp2f(t); return t;
-    case 10: u = 5.367655f; u = u * 0.010591f; u = u + 0.092809f;
+    case 10: u = (float)(5.367655 * 0.010591 + 0.092809);   // constants of literals alone: folded in double, rounded once (glslang)
              if(x < u) { t = x - 0.092809f; t = t / 5.367655f; return t; } t = x - 0.385537f; t = t / 0.247190f; t = powf(10.0f, t); t = t - 0.052272f; t = t / 5.555556f; return t;
     case 11: if(x < -0.7774983977293537f) { t = x * 0.3033266726886969f; t = t - 0.7774983977293537f; return t; }
              t = x - 0.09286412512218964f; t = 14.0f * t; t = t / 0.9071358748778103f; t = t + 6.0f; t = exp2f(t); t = t - 64.0f; t = t / 2231.8263090676883f; return t;
     case 12: if(x < 0.0f) { t = x / 15.1927f; t = t - 0.01f; return t; } t = x / 0.224282f; t = powf(10.0f, t); t = t - 1.0f; t = t / 155.975327f; t = t - 0.01f; return t;
     case 13: if(x < 0.181f) { t = x - 0.125f; t = t / 5.6f; return t; } t = x - 0.598206f; t = t / 0.241514f; t = powf(10.0f, t); t = t - 0.00873f; return t;
-    case 14: u = 171.2102946929f; u = u / 1023.0f;
-             if(x < u) { t = x * 1023.0f; t = t - 95.0f; t = t * 0.01125f; u = 171.2102946929f; u = u - 95.0f; t = t / u; return t; }
-             t = x * 1023.0f; t = t - 420.0f; t = t / 261.5f; t = powf(10.0f, t); u = 0.18f; u = u + 0.01f; t = t * u; t = t - 0.01f; return t;
+    case 14: u = (float)(171.2102946929 / 1023.0);
+             if(x < u) { t = x * 1023.0f; t = t - 95.0f; t = t * 0.01125f; u = (float)(171.2102946929 - 95.0); t = t / u; return t; }
+             t = x * 1023.0f; t = t - 420.0f; t = t / 261.5f; t = powf(10.0f, t); u = (float)(0.18 + 0.01); t = t * u; t = t - 0.01f; return t;
     case 15: if(x < 0.100686685370811f) { t = x - 0.092864f; t = t / 8.799461f; return t; }
-             t = x - 0.384316f; t = t / 0.245281f; t = powf(10.0f, t); t = t / 5.555556f; u = 0.064829f; u = u / 5.555556f; t = t - u; return t;
+             t = x - 0.384316f; t = t / 0.245281f; t = powf(10.0f, t); t = t / 5.555556f; u = (float)(0.064829 / 5.555556); t = t - u; return t;
     default: return x;
   }
 }

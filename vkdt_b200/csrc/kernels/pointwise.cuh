@@ -159,19 +159,20 @@ VKB_DEV float decode_trc(float v, uint32_t trc)
     case 5: { const float a = 0.17883277f, b = 0.28466892f, c = 0.55991073f;
               return v <= 0.5f ? v * v / 3.0f : (PW_EXP((v - c) / a) + b) / 12.0f; }
     case 6: return PW_POW(fmaxf(v, 0.0f), 2.2f);
-    // camera log curves to scene linear (shared/oetf.glsl:2-38; mix() with a bvec selects)
+    // camera log curves to scene linear (shared/oetf.glsl:2-38; mix() with a bvec selects; expressions of literals alone are
+    // folded in double and rounded once, like glslang does)
     case 7:  return v > 0.02740668f ? m_exp2(v / 0.07329248f - 7.0f) - 0.0075f : v / 10.44426855f;
     case 8:  return v < 0.075f ? (v - 0.075f) / 16.184376489665897f : PW_EXP((v - 0.5520126568606655f) / 0.09232902596577353f) - 0.0057048244042473785f;
     case 9:  return v <= 0.155251141552511f ? (v - 0.0729055341958355f) / 10.5402377416545f : m_exp2(v * 17.52f - 9.72f);
-    case 10: return v < __fadd_rn(__fmul_rn(5.367655f, 0.010591f), 0.092809f) ? (v - 0.092809f) / 5.367655f : (PW_POW(10.0f, (v - 0.385537f) / 0.247190f) - 0.052272f) / 5.555556f;
+    case 10: return v < (float)(5.367655 * 0.010591 + 0.092809) ? (v - 0.092809f) / 5.367655f : (PW_POW(10.0f, (v - 0.385537f) / 0.247190f) - 0.052272f) / 5.555556f;
     case 11: return v < -0.7774983977293537f ? v * 0.3033266726886969f - 0.7774983977293537f
                   : (m_exp2(14.0f * (v - 0.09286412512218964f) / 0.9071358748778103f + 6.0f) - 64.0f) / 2231.8263090676883f;
     case 12: return v < 0.0f ? (v / 15.1927f) - 0.01f : (PW_POW(10.0f, v / 0.224282f) - 1.0f) / 155.975327f - 0.01f;
     case 13: return v < 0.181f ? (v - 0.125f) / 5.6f : PW_POW(10.0f, (v - 0.598206f) / 0.241514f) - 0.00873f;
-    case 14: return v < __fdiv_rn(171.2102946929f, 1023.0f) ? (v * 1023.0f - 95.0f) * 0.01125f / __fsub_rn(171.2102946929f, 95.0f)
-                  : PW_POW(10.0f, (v * 1023.0f - 420.0f) / 261.5f) * __fadd_rn(0.18f, 0.01f) - 0.01f;
+    case 14: return v < (float)(171.2102946929 / 1023.0) ? (v * 1023.0f - 95.0f) * 0.01125f / (float)(171.2102946929 - 95.0)
+                  : PW_POW(10.0f, (v * 1023.0f - 420.0f) / 261.5f) * (float)(0.18 + 0.01) - 0.01f;
     case 15: return v < 0.100686685370811f ? (v - 0.092864f) / 8.799461f
-                  : PW_POW(10.0f, (v - 0.384316f) / 0.245281f) / 5.555556f - __fdiv_rn(0.064829f, 5.555556f);
+                  : PW_POW(10.0f, (v - 0.384316f) / 0.245281f) / 5.555556f - (float)(0.064829 / 5.555556);
     default: return v;
   }
 }
