@@ -318,6 +318,40 @@ def test_live_reference_graph_random(oracle):
         assert len(ref) == len(got) and not bad, (case, len(ref), len(got), bad[:3])
 
 
+def test_live_reference_graph_with_random_luts(oracle, tmp_path):
+    """lut tables of random shapes (bands, channel counts, f16 / f32) wired to colour in random combinations, random temperatures
+    incl. as shot: i-lut's roi and formats, colour's connectors, nodes, push constants and committed block against the compiled
+    reference (its i-lut/main.c, colour/main.c)."""
+    if oracle.ref_host_lib() is None or not hasattr(oracle.ref_host_lib(), "ref_graph_describe") or not os.path.isdir("/root/reference/src/pipe/modules"):
+        pytest.skip("oracle/_ref/libhostref.so or /root/reference not present")
+    import struct
+    rng = np.random.default_rng(2024)
+    for t in range(16):
+        w, h = int(rng.integers(40, 700)) * 2, int(rng.integers(40, 500)) * 2
+        lines = []
+        use = [n for n, pr in (("clut", 0.6), ("abney", 0.7), ("spectra", 0.7)) if rng.uniform() < pr]
+        for name in use:
+            if name == "clut":
+                ht = int(rng.integers(8, 48)); wd = ht * int(rng.choice([3, 6, 9, 12])); ch, dt = 2, np.float16
+            elif name == "abney":
+                wd, ht, ch, dt = int(rng.integers(16, 128)), int(rng.integers(16, 96)), 2, np.float16
+            else:
+                wd, ht, ch, dt = int(rng.integers(16, 96)), int(rng.integers(16, 96)), 4, rng.choice([np.float16, np.float32])
+            fn = str(tmp_path / ("%s_%d.lut" % (name, t)))
+            with open(fn, "wb") as f:
+                f.write(struct.pack("<IHBBII", 1234, 2, ch, 0 if dt == np.float16 else 1, wd, ht))
+                f.write(rng.uniform(0.1, 0.9, (ht, wd, ch)).astype(dt).tobytes())
+            lines += ["module:i-lut:%s" % name, "param:i-lut:%s:filename:%s" % (name, fn), "connect:i-lut:%s:output:colour:01:%s" % (name, name)]
+        lines += ["param:colour:01:matrix:%d" % rng.choice([1, 4]), "param:colour:01:temp:%g" % rng.choice([0.0, rng.uniform(1500, 16000)]),
+                  "param:colour:01:gamut:%d" % rng.integers(0, 4), "param:colour:01:sat:%g" % rng.uniform(0.5, 1.5)]
+        raw = dict(wb=(float(rng.uniform(1, 3)), 1.0, float(rng.uniform(1, 3))))
+        case = dict(lines=lines, w=w, h=h, raw=raw)
+        ref = _graph_text_reference(case, oracle.ref_graph_describe(w, h, lines, raw))
+        got = _graph_text_product(case)
+        bad = [(a[:200], b[:200]) for a, b in zip(ref, got) if a != b]
+        assert len(ref) == len(got) and not bad, (case, len(ref), len(got), bad[:3])
+
+
 def test_live_reference_graph_with_feedback_edges(oracle):
     """`feedback:` connections through the whole module pass (traversal incl. the second round of graph-traverse.inc:131-148,
     roi negotiation, create_nodes, repointing) against the compiled reference."""
