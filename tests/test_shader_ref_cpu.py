@@ -323,6 +323,22 @@ def cases(O):
                 res_s.append(got)
             return res_o, res_s
 
+    # the export's colour encoding (colenc/main.comp): output primaries and transfer curves
+    for prim, trc in ((1, 1), (1, 2), (3, 6), (4, 3), (5, 0), (6, 4), (7, 5), (10, 2), (2, 1), (0, 0)):
+        @add("colenc.main prim %d trc %d" % (prim, trc))
+        def _(prim=prim, trc=trc):
+            a = rgba(np.random.default_rng(700 + 10 * prim + trc), 96, 64, -0.05, 1.5)
+            L.o_colenc_main.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+            res_o, res_s = [], []
+            for out16 in (1, 0):
+                want, wi = img_out(64, 96, 4)
+                L.o_colenc_main(C.byref(O.img(a)), C.byref(wi), prim, trc, out16)
+                got = np.zeros((64, 96, 4), np.float32)
+                O.ref_shader("colenc", "main", np.array([prim, trc], np.int32).tobytes(), b"", [(a, 0), (got, out16)], 96, 64)
+                res_o.append(want)
+                res_s.append(got)
+            return res_o, res_s
+
     for k, (rot, crop, ori) in enumerate(((1337.0, (1.0, 3.0, 3.0, 7.0), 0), (90.0, (0.1, 0.9, 0.2, 0.8), 0), (7.5, (0.1, 0.9, 0.2, 0.8), 0), (1337.0, (1.0, 3.0, 3.0, 7.0), 6))):
         @add("crop.main set %d" % k)
         def _(k=k, rot=rot, crop=crop, ori=ori):
