@@ -76,7 +76,7 @@ static int ref_pipe_init(const char *basedir)
     snprintf(dt_pipe.basedir, sizeof(dt_pipe.basedir), "%s", basedir);
     snprintf(dt_pipe.homedir, sizeof(dt_pipe.homedir), "/nonexistent");
     static const char *names[] = { "i-raw", "denoise", "hilite", "demosaic", "colour", "filmcurv", "llap", "grade", "hist", "zones", "crop", "lens", "pick",
-      "display", "o-pfm", "colenc", "resize", "i-mlv", "contrast", "i-pfm", "i-lut", 0 };
+      "display", "o-pfm", "colenc", "resize", "i-mlv", "contrast", "i-pfm", "i-lut", "o-jpg", 0 };
     int n = 0; while(names[n]) n++;
     dt_pipe.module = malloc(sizeof(dt_module_so_t) * n);
     int i = 0;
@@ -114,7 +114,8 @@ int ref_graph_describe(const char *basedir, const char *cfgfile, const char *ext
   g->params_max = 16u << 20; g->params_pool = calloc(1, g->params_max);
   g->conn_image_max = 30*2*2000; g->conn_image_pool = calloc(sizeof(dt_connector_image_t), g->conn_image_max);
   int ret = -20;
-  int max_wd = 0, max_ht = 0;
+  int max_wd = 0, max_ht = 0, prim = s_colour_primaries_2020, trc = s_colour_trc_linear;
+  char sinkname[16]; snprintf(sinkname, sizeof(sinkname), "%s", sink);
   if(dt_graph_read_config_ascii(g, cfgfile)) goto done;
   if(extra && extra[0])
   {
@@ -125,13 +126,17 @@ int ref_graph_describe(const char *basedir, const char *cfgfile, const char *ext
       char line[4096]; snprintf(line, sizeof(line), "%s", c);
       /* "#export:max:<w>:<h>": vkdt-cli --width / --height (cli/main.c:68-71 -> dt_graph_export -> replace_display's resize) */
       if(!strncmp(line, "#export:max:", 12)) { sscanf(line + 12, "%d:%d", &max_wd, &max_ht); c = e; continue; }
+      /* "#export:colour:<prim>:<trc>": --colour-prim / --colour-trc (cli/main.c:58-59, :80-81; the cli's own default is 1:1);
+       * "#export:sink:<module>": --format */
+      if(!strncmp(line, "#export:colour:", 15)) { sscanf(line + 15, "%d:%d", &prim, &trc); c = e; continue; }
+      if(!strncmp(line, "#export:sink:", 13)) { snprintf(sinkname, sizeof(sinkname), "%s", line + 13); c = e; continue; }
       if(line[0] && dt_graph_read_config_line(g, line) < 0) { free(copy); ret = -21; goto done; }
       c = e;
     }
     free(copy);
   }
   /* what vkdt-cli does (cli/main.c, graph-export.c:160-230): the main display becomes the output module, linear rec2020 */
-  if(dt_graph_replace_display(g, dt_token("main"), 0, dt_token(sink), max_wd > 0 || max_ht > 0, max_wd, max_ht, s_colour_primaries_2020, s_colour_trc_linear) < 0) { ret = -22; goto done; }
+  if(dt_graph_replace_display(g, dt_token("main"), 0, dt_token(sinkname), max_wd > 0 || max_ht > 0, max_wd, max_ht, prim, trc) < 0) { ret = -22; goto done; }
   dt_graph_disconnect_display_modules(g);
   {
     dt_graph_run_t run = s_graph_run_roi | s_graph_run_create_nodes;

@@ -214,6 +214,12 @@ GRAPH_CASES = NODE_CASES + [  # parameter lines travel through the reference's o
     (["#export:max:400:0", "param:denoise:01:strength:0.3"], 640, 480, dict(wb=(2.0, 1.0, 1.5))),
     (["#export:max:0:500"], 1002, 666, dict(filters=9)),
     (["#export:max:1000:1000"], 322, 246, {}),
+    # "#export:colour:<prim>:<trc>" / "#export:sink:<module>": --colour-prim / --colour-trc / --format, i.e. the colenc module that
+    # dt_graph_replace_display puts in front of an 8 bit sink or a colour space other than linear bt2020 (graph-export.c:66-86)
+    (["#export:colour:1:1", "#export:sink:o-jpg"], 640, 480, {}),                                  # what `vkdt-cli -g x.cfg` does
+    (["#export:colour:4:2"], 640, 480, dict(wb=(2.0, 1.0, 1.5))),                                  # f32 pfm in display p3 with the srgb curve
+    (["#export:colour:1:1", "#export:sink:o-jpg", "#export:max:300:0", "param:denoise:01:strength:0.3"], 804, 602, {}),
+    (["#export:colour:2:0", "#export:sink:o-jpg"], 322, 246, {}),                                  # 8 bit linear bt2020: colenc for the format alone
     # feedback edges through the module pass (second traversal round, frames = 2)
     (["feedback:grade:01:output:colour:01:spectra"], 640, 480, {}),
     (["feedback:llap:01:output:colour:01:spectra", "param:denoise:01:strength:0.3"], 1002, 668, {}),

@@ -247,10 +247,15 @@ def _graph_text_product(case):
     if "luts" in case:
         _make_golden_module().write_golden_luts(clut=case["luts"] == 2)   # same tables, same path as when the golden was made
     mw = mh = 0
+    sink, prim, trc = "o-pfm", None, None
     for ln in case["lines"]:    # "#export:max:<w>:<h>": the cli's --width / --height (a resize module in front of the sink)
         if ln.startswith("#export:max:"):
             mw, mh = [int(x) for x in ln.split(":")[2:4]]
-    g = api.Graph(cfg_text=api.DARKROOM_CFG.format(src="i-raw"), max_width=mw, max_height=mh)
+        if ln.startswith("#export:colour:"):   # --colour-prim / --colour-trc
+            prim, trc = [int(x) for x in ln.split(":")[2:4]]
+        if ln.startswith("#export:sink:"):     # --format
+            sink = ln.split(":")[2]
+    g = api.Graph(cfg_text=api.DARKROOM_CFG.format(src="i-raw"), sink=sink, prim=prim, trc=trc, max_width=mw, max_height=mh)
     assert g.line("param:i-raw:main:filename:none.raw") == 0   # the last line of the reference's default-darkroom.i-raw
     for ln in case["lines"]:
         if not ln.startswith("#"):
@@ -282,8 +287,9 @@ def test_product_module_pass_matches_reference_graph_code():
         assert len(ref) == len(got), (case["lines"], case["w"], case["h"], len(ref), len(got))
         bad = [(a[:200], b[:200]) for a, b in zip(ref, got) if a != b]
         assert not bad, (case["lines"], case["w"], case["h"], bad[:3])
-    assert len(GRAPHS) >= 33 and sum("mlv" in c for c in GRAPHS) == 2 and sum("pfm" in c for c in GRAPHS) == 1 and sum("luts" in c for c in GRAPHS) == 2
-    assert sum(any(l.startswith("#export:max") for l in c["lines"]) for c in GRAPHS) == 4 and sum(any(l.startswith("feedback:") for l in c["lines"]) for c in GRAPHS) == 2
+    assert len(GRAPHS) >= 37 and sum("mlv" in c for c in GRAPHS) == 2 and sum("pfm" in c for c in GRAPHS) == 1 and sum("luts" in c for c in GRAPHS) == 2
+    assert sum(any(l.startswith("#export:max") for l in c["lines"]) for c in GRAPHS) == 5 and sum(any(l.startswith("feedback:") for l in c["lines"]) for c in GRAPHS) == 2
+    assert sum(any(l.startswith("#export:colour") for l in c["lines"]) for c in GRAPHS) == 4 and sum(any(l.startswith("#export:sink:o-jpg") for l in c["lines"]) for c in GRAPHS) == 3
 
 
 def test_live_reference_graph_random(oracle):
