@@ -418,7 +418,7 @@ def ref_pipeline_run(text, raw, trace=None):
         for c in n["conn"]:
             if c["type"] in ("write",):
                 c["buf"] = [np.zeros((c["h"], c["w"]) if c["chan"] == 1 else (c["h"], c["w"], c["chan"]), np.float32) for _ in range(c["al"])]
-                binds.append([(b, 0 if c["fmt"] == "f32" else 1) for b in c["buf"]])
+                binds.append([(b, 0 if c["fmt"] in ("f32", "ui8") else 1) for b in c["buf"]])   # ui8: stored as float, quantised below
                 continue
             src = None
             if c["link"].startswith("n"):
@@ -452,6 +452,12 @@ def ref_pipeline_run(text, raw, trace=None):
         module, kernel = n["name"].split(":")
         ref_shader(module, kernel, m["committed"] if m["committed"] is not None else m["params"] + b"\0" * 16, n["push"] + b"\0" * 16,
                    [b if len(b) > 1 else b[0] for b in binds], n["wd"], n["ht"], n["dp"])
+        for c in n["conn"]:
+            if c["type"] == "write" and c["fmt"] == "ui8":
+                # imageStore to an rgba8 UNORM image: clamp to [0, 1], scale, round to nearest even; read back as the 8 bit value
+                for b in c["buf"]:
+                    with np.errstate(invalid="ignore"):
+                        b[...] = np.rint(np.clip(np.nan_to_num(b, nan=0.0), 0.0, 1.0) * np.float32(255.0))
         if trace is not None:
             trace["%s#%d" % (n["name"], m["nodes"].index(n))] = [c["buf"] for c in n["conn"] if c["type"] == "write"]
 

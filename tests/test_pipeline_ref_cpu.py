@@ -156,6 +156,34 @@ def test_reference_pipeline_with_luts_live(oracle, tmp_path, name):
     print(name, "max abs %.3g, psnr %.1f dB" % check("luts " + name, ref, want))
 
 
+@pytest.mark.parametrize("sink,prim,trc,strength", [("o-jpg", 1, 1, 0.0), ("o-jpg", 1, 1, 0.4), ("o-pfm", 4, 2, 0.0)])
+def test_reference_export_pipeline_live(oracle, sink, prim, trc, strength):
+    """what vkdt-cli writes: dt_graph_replace_display puts colenc in front of the sink (graph-export.c:66-86), its shader encodes
+    into the output primaries and curve, an o-jpg sink receives rgba8.  the reference's code all the way against the oracle's
+    export; 8 bit values may sit one level apart where the float images, one or two f16 ulps apart, straddle a rounding boundary."""
+    if oracle.ref_shader_lib() is None or oracle.ref_host_lib() is None or not os.path.isdir("/root/reference/src/pipe/modules"):
+        pytest.skip("needs oracle/_ref/lib{host,shader}ref.so and /root/reference (make -C oracle ref)")
+    w, h = 240, 180
+    raw = synth.mosaic(w, h, seed=9)
+    lines = ["#export:colour:%d:%d" % (prim, trc), "#export:sink:%s" % sink] + (["param:denoise:01:strength:%g" % strength] if strength > 0 else [])
+    ref = oracle.ref_pipeline_run(oracle.ref_graph_describe(w, h, lines, dict(wb=WB, noise_a=NOISE[0], noise_b=NOISE[1])), raw)[..., :3]
+    d = oracle.darkroom_defaults(w, h)
+    for c, v in enumerate(WB):
+        d.whitebalance[c] = v
+    d.noise_a, d.noise_b = NOISE
+    d.denoise.strength = strength
+    d.enable_grade = 1
+    d.enable_colenc, d.colenc_prim, d.colenc_trc, d.sink_unorm8 = 1, prim, trc, int(sink == "o-jpg")
+    want = oracle.darkroom_run(d, raw)[..., :3]
+    assert ref.shape == want.shape
+    if sink == "o-jpg":
+        diff = np.abs(ref - want)
+        print("8 bit export: %d of %d values one level apart" % (int((diff == 1).sum()), diff.size))
+        assert diff.max() <= 1.0 and (diff > 0).mean() < 0.02 and ref.max() > 100, (diff.max(), (diff > 0).mean())
+    else:
+        print("max abs %.3g, psnr %.1f dB" % check("export %d:%d" % (prim, trc), ref, want))
+
+
 def test_reference_mlv_pipeline_live(oracle, tmp_path):
     """bin/default-darkroom.i-mlv with the reference's own i-mlv/main.c reading the clip header (image parameters incl. the camera
     matrix for a camera outside dcraw's table: xyz_to_rec2020) against the oracle configured the way tests/test_graph_gpu.py
