@@ -184,6 +184,46 @@ def test_reference_export_pipeline_live(oracle, sink, prim, trc, strength):
         print("max abs %.3g, psnr %.1f dB" % check("export %d:%d" % (prim, trc), ref, want))
 
 
+@pytest.mark.parametrize("limit", [(100, 0), (0, 40), (300, 300)])
+def test_reference_sized_export_pipeline_live(oracle, limit):
+    """vkdt-cli --width / --height: the reference's dt_graph_replace_display adds its resize module, resize/main.c its blur nodes,
+    the shaders scale; against the oracle's restatement of resize/main.comp and shared/blur{h,v}.comp behind its own darkroom
+    output (catmull-rom below a factor of three, gaussian blur + slice above, flower taps when the limit magnifies)."""
+    if oracle.ref_shader_lib() is None or oracle.ref_host_lib() is None or not os.path.isdir("/root/reference/src/pipe/modules"):
+        pytest.skip("needs oracle/_ref/lib{host,shader}ref.so and /root/reference (make -C oracle ref)")
+    import ctypes as C
+    w, h = 240, 180
+    raw = synth.mosaic(w, h, seed=13)
+    mw, mh = limit
+    ref = oracle.ref_pipeline_run(oracle.ref_graph_describe(w, h, ["#export:max:%d:%d" % limit], dict(wb=WB, noise_a=NOISE[0], noise_b=NOISE[1])), raw)[..., :3]
+    d = oracle.darkroom_defaults(w, h)
+    for c, v in enumerate(WB):
+        d.whitebalance[c] = v
+    d.noise_a, d.noise_b = NOISE
+    d.enable_grade = 1
+    full = oracle.darkroom_run(d, raw)
+    ih, iw = full.shape[:2]
+    s = np.float32(max(iw / mw if mw else 1.0, ih / mh if mh else 1.0))      # graph-run-modules.h:466-471 in fp32
+    ow, oh = int(np.float32(iw) / s + np.float32(0.5)), int(np.float32(ih) / s + np.float32(0.5))
+    assert ref.shape[:2] == (oh, ow), (ref.shape, ow, oh)
+    L = oracle.lib()
+    L.o_blur_sep.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int]
+    src = full.astype(np.float16).astype(np.float32)                          # grade's output is an f16 edge once a module follows it
+    src[..., 3] = 1.0
+    scale = np.float32(iw) / np.float32(ow)
+    mode = 0 if scale < 0.99 else (2 if scale > 1.01 else 1)
+    if scale > 3:
+        mode = 1
+        bh, bhi = oracle.new_img(ih, iw, 4)
+        L.o_blur_sep(C.byref(oracle.img(src)), C.byref(bhi), float(scale + np.float32(0.5)), 0, 1)
+        bv, bvi = oracle.new_img(ih, iw, 4)
+        L.o_blur_sep(C.byref(oracle.img(bh)), C.byref(bvi), float(scale + np.float32(0.5)), 1, 1)
+        src = bv
+    want, wi = oracle.new_img(oh, ow, 4)
+    L.o_resize_main(C.byref(oracle.img(src)), C.byref(wi), mode, 0)
+    print(limit, "-> %dx%d, mode %d:" % (ow, oh, mode), "max abs %.3g, psnr %.1f dB" % check("sized export", ref, want[..., :3]))
+
+
 def test_reference_mlv_pipeline_live(oracle, tmp_path):
     """bin/default-darkroom.i-mlv with the reference's own i-mlv/main.c reading the clip header (image parameters incl. the camera
     matrix for a camera outside dcraw's table: xyz_to_rec2020) against the oracle configured the way tests/test_graph_gpu.py
