@@ -145,6 +145,57 @@ def fold_literals(code):
     return code
 
 
+def subst_const_floats(code):
+    """`const float a = 1.0993; ... (a - 1)`: for glslang `a` is a constant kept in double, and `a - 1` one fp32 constant.  replace
+    such names by their literal within their block, fold again (constant arguments of log / exp / sqrt included), repeat."""
+    import math
+    lit1 = r"\(?\s*-?\s*(?:%s)\s*\)?" % FLIT
+    fn = re.compile(r"\b(log|exp|sqrt|log2|exp2)\(\s*(%s)\s*\)" % FLIT)
+    mixed_a = re.compile(r"(?<![\w.])(%s)\s*([-+*/])\s*(\d+)(?![\w.])" % FLIT)
+    mixed_b = re.compile(r"(?<![\w.])(\d+)\s*([-+*/])\s*(%s)(?![\w.])" % FLIT)
+    done = set()
+    for _ in range(200):
+        code = fold_literals(code)
+        code2 = fn.sub(lambda m: repr({"log": math.log, "exp": math.exp, "sqrt": math.sqrt, "log2": math.log2, "exp2": lambda x: 2.0 ** x}[m.group(1)](float(m.group(2)))), code)
+        # an integer literal next to a floating one converts: make it floating so that the pair folds (only inside parentheses / after = ,)
+        code2 = re.sub(r"([(=,]\s*)(%s)(\s*[-+]\s*)(\d+)(\s*[),;])" % FLIT, lambda m: m.group(1) + m.group(2) + m.group(3) + m.group(4) + ".0" + m.group(5), code2)
+        if code2 != code:
+            code = code2
+            continue
+        m = None
+        for mm in re.finditer(r"\bconst\s+float\s+([^;]*);", code):
+            parts = [x.strip() for x in mm.group(1).split(",")]
+            for part in parts:
+                pm = re.match(r"^(\w+)\s*=\s*(%s)$" % lit1, part)
+                if pm and (mm.start(), pm.group(1)) not in done:
+                    m = (mm, pm)
+                    break
+            if m:
+                break
+        if not m:
+            break
+        mm, pm = m
+        done.add((mm.start(), pm.group(1)))
+        name, lit = pm.group(1), pm.group(2).strip()
+        if not lit.startswith("("):
+            lit = "(" + lit + ")" if lit.startswith("-") else lit
+        # scope: from the end of this declarator list to the end of the enclosing block
+        depth, j = 0, mm.end()
+        while j < len(code):
+            if code[j] == "{": depth += 1
+            elif code[j] == "}":
+                if depth == 0: break
+                depth -= 1
+            j += 1
+        # later declarators of the same statement may use the name too: substitute there as well
+        head, decl, body, tail = code[:mm.start()], code[mm.start():mm.end()], code[mm.end():j], code[j:]
+        k = decl.index(pm.group(0)) + len(pm.group(0))
+        decl = decl[:k] + re.sub(r"(?<![\w.])%s(?![\w.(])" % name, lit, decl[k:])
+        body = re.sub(r"(?<![\w.])%s(?![\w.(])" % name, lit, body)
+        code = head + decl + body + tail
+    return code
+
+
 def fix_body(code):
     code = re.sub(r"\b(?:in\s+)?(?:inout|out)\s+(\w+)\s+(\w+)", r"\1 &\2", code)           # out / inout parameters
     while True:                                                                                # array constructors: float[](a, b) -> {a, b}
@@ -158,6 +209,7 @@ def fix_body(code):
         code = code[:m.start()] + "{" + code[m.end():j - 1] + "}" + code[j:]
     code = code.replace("^^", "!=")                                                          # logical xor of two bools
     code = fold_literals(code)
+    code = subst_const_floats(code)   # glslang keeps a `const float` in double while it folds the expressions that use it
     code = re.sub(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][-+]?\d+)?|\d+[eE][-+]?\d+)(?![\w.])", r"\1f", code)   # fp32 literals
     code = re.sub(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][-+]?\d+)?)[lL][fF]\b", r"\1f", code)
     return code

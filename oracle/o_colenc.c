@@ -28,7 +28,7 @@ void o_colenc_px(float *rgb, int prim, int trc)
     if(trc == 1)
     {
       const float a = 1.09929682680944f, b = 0.018053968510807f;
-      v = v > b ? powf(v, (float)(1.0 / 2.2)) * a - (a - 1) : v * 4.5f;
+      v = v > b ? powf(v, (float)(1.0 / 2.2)) * a - (float)(1.09929682680944 - 1.0) : v * 4.5f; /* a - 1: a constant, folded in double */
     }
     else if(trc == 2) v = v > 0.0031308f ? powf(v, (float)(1.0 / 2.4)) * 1.055f - 0.055f : v * 12.92f;
     else if(trc == 3)

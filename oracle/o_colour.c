@@ -169,8 +169,8 @@ static void decode_colour(const float *f, float *rgb)
   const uint32_t trc = ii[off+6], prim = ii[off+5];
   if(trc == 1)
   {
-    const float a = 1.09929682680944f, b = 0.018053968510807f;
-    for(int k = 0; k < 3; k++) rgb[k] = rgb[k] > b * 4.5f ? powf((rgb[k] + (a - 1)) / a, 2.2f) : rgb[k] / 4.5f;
+    const float a = 1.09929682680944f;
+    for(int k = 0; k < 3; k++) rgb[k] = rgb[k] > (float)(0.018053968510807 * 4.5) ? powf((rgb[k] + (float)(1.09929682680944 - 1.0)) / a, 2.2f) : rgb[k] / 4.5f; /* constants of constants: folded in double */
   }
   else if(trc == 2)
   { for(int k = 0; k < 3; k++) rgb[k] = rgb[k] > 0.04045f ? powf((rgb[k] + 0.055f) / 1.055f, 2.4f) : rgb[k] / 12.92f; }

@@ -187,7 +187,7 @@ static float host_decode_trc_f(float v, uint32_t trc)
 {
   switch(trc)
   {
-    case 1: { const float a = 1.09929682680944f, b = 0.018053968510807f; return v > b * 4.5f ? powf((v + (a - 1)) / a, 2.2f) : v / 4.5f; }
+    case 1: { const float a = 1.09929682680944f; return v > (float)(0.018053968510807 * 4.5) ? powf((v + (float)(1.09929682680944 - 1.0)) / a, 2.2f) : v / 4.5f; }
     case 2: return v > 0.04045f ? powf((v + 0.055f) / 1.055f, 2.4f) : v / 12.92f;
     case 3: { const float m1 = 1305.0f / 8192.0f, m2 = 2523.0f / 32.0f, c1 = 107.0f / 128.0f, c2 = 2413.0f / 128.0f, c3 = 2392.0f / 128.0f;
               const float xp = powf(fmaxf(0.0f, v), 1.0f / m2); return powf(fmaxf(xp - c1, 0.0f) / fmaxf(c2 - c3 * xp, 1e-10f), 1.0f / m1); }

@@ -149,8 +149,8 @@ VKB_DEV float decode_trc(float v, uint32_t trc)
 { // main-impl.glsl:118-150
   switch(trc)
   {
-    case 1: { const float a = 1.09929682680944f, b = 0.018053968510807f;
-              return v > b * 4.5f ? PW_POW((v + (a - 1)) / a, 2.2f) : v / 4.5f; }
+    case 1: { const float a = 1.09929682680944f;
+              return v > (float)(0.018053968510807 * 4.5) ? PW_POW((v + (float)(1.09929682680944 - 1.0)) / a, 2.2f) : v / 4.5f; }   // b * 4.5, a - 1: constants, folded in double
     case 2: return v > 0.04045f ? PW_POW((v + 0.055f) / 1.055f, 2.4f) : v / 12.92f;
     case 3: { const float m1 = 1305.0f / 8192.0f, m2 = 2523.0f / 32.0f, c1 = 107.0f / 128.0f, c2 = 2413.0f / 128.0f, c3 = 2392.0f / 128.0f;
               const float xp = PW_POW(fmaxf(0.0f, v), 1.0f / m2);
@@ -471,7 +471,7 @@ VKB_DEV f3 colenc_px(f3 c, const colenc_params_t &p)
     if(p.trc == 1)
     {
       const float a = 1.09929682680944f, b = 0.018053968510807f;
-      t = t > b ? PW_POW(t, (float)(1.0 / 2.2)) * a - (a - 1) : t * 4.5f;
+      t = t > b ? PW_POW(t, (float)(1.0 / 2.2)) * a - (float)(1.09929682680944 - 1.0) : t * 4.5f;   // a - 1 is a constant: folded in double, rounded once (glslang)
     }
     else if(p.trc == 2) t = t > 0.0031308f ? PW_POW(t, (float)(1.0 / 2.4)) * 1.055f - 0.055f : t * 12.92f;
     else if(p.trc == 3)
